@@ -1,0 +1,332 @@
+/*
+ * soundbubble.h — C ABI of libsoundbubble_sm100a.so
+ *
+ * B200-native (sm_100a) kernels for the Sound Bubble separator forward pass: STFT front-end + inter-microphone
+ * features + causal conv-in, FiLM distance conditioning, intra-frame BiLSTM across frequency (plain and conv-LSTM
+ * variants), inter-frame LSTM across time with carried state, sliding-window full-band attention, causal deconv +
+ * iSTFT overlap-add.
+ *
+ * The reference (chentuochao/Sound_Bubble) is pure PyTorch and has no FFI; the interface each entry point
+ * replaces is therefore a span of the reference's Python hot path, cited per function as
+ *   DE3 = src/models/tfgridnet_realtime_clean_dis_embd3/tfgridnet_causal.py
+ *   OPT = src/models/tfgridnet_realtime_clean_optim/tfgridnet_causal.py
+ * The binding a maintainer would add on the reference side (ctypes) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float32 unless it says otherwise; nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call returns immediately;
+ *   - return value 0 = ok; > 0 = cudaError_t of the failed launch; < 0 = argument error (SB_E_*);
+ *     sb_last_error_string() describes the last non-zero return of the calling thread;
+ *   - activations between stages live in one layout: X[B][T][F][C], channel innermost ("BTFC").
+ *   - streaming state is read and written in the reference's own layouts (DE3:403-421, 696-720) so a state dict
+ *     can be handed back and forth between the reference module and this library.
+ */
+#ifndef SOUNDBUBBLE_H_
+#define SOUNDBUBBLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_VERSION 100          /* 0.1.0 */
+
+#define SB_E_BADARG   (-1)      /* null pointer / non-positive size */
+#define SB_E_UNSUPP   (-2)      /* a (C, H, mics, ...) combination no kernel is instantiated for */
+#define SB_E_SMEM     (-3)      /* device cannot provide the shared memory a kernel needs */
+
+#define SB_MAX_BLOCKS 16
+#define SB_MAX_MICS   8
+
+/* LSTM scheduling: which kernel family runs the recurrence */
+#define SB_ALGO_AUTO  0
+#define SB_ALGO_TILE  1         /* 8 sequences per warp, weights in shared memory, register-tiled gate GEMM      */
+#define SB_ALGO_LANE1 2         /* 1 sequence  per CTA, one gate column per thread, weights in registers        */
+#define SB_ALGO_LANE2 3         /* 2 sequences per CTA                                                           */
+#define SB_ALGO_LANE4 4         /* 4 sequences per CTA                                                           */
+
+/* feature modes of the front-end (DE3:486-507) */
+#define SB_FEAT_NONE        0   /* merge_method "None": conv-in sees [Re, Im] only                               */
+#define SB_FEAT_OMNI        1   /* MC_features_OMNX  (DE3:72-93): (M-1) ILD + (M-1) (sin, cos) IPD vs mic 0      */
+#define SB_FEAT_DIRECTIONAL 2   /* MC_features_direct (DE3:176-207): 1 + 3 ILD, 5 (sin, cos) IPD (6 mics)        */
+
+/* how the distance embedding is normalised / laid out (DE3:114-173) */
+#define SB_EMB_CONV    0        /* Dis_Embed_Conv:   view [B,F,Din] -> LayerNorm(Din) -> transpose                */
+#define SB_EMB_LINEAR  1        /* Dis_Embed_Linear: LayerNorm over the whole F*Din vector -> view [B,Din,F]      */
+
+/* variant of the intra-frame conv-LSTM tail (a9') */
+#define SB_CONVLSTM_PADCROP 0   /* DE3:810-813  deconv, pad 3 zeros, crop to F                                    */
+#define SB_CONVLSTM_OUTPAD  1   /* OPT:506-510  deconv with output_padding = F - (F/k)*k                          */
+
+/* process-wide options */
+#define SB_OPT_PDL 1            /* 1 = launch kernels with programmatic dependent launch (prologue overlap)       */
+int sb_set_option(int option, int value);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* One LSTM direction, packed by sound_bubble_b200/packing.py from the checkpoint tensors                       */
+/*   intra_rnn.{weight_ih,weight_hh,bias_ih,bias_hh}_l0[_reverse], intra_norm.norm, intra_linear  (DE3:623-629)  */
+/*   inter_rnn.*, inter_norm.norm, inter_linear                                                 (DE3:631-637)  */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_lstm_dir {
+    const float* w_tile;    /* [C+H][4H]  gate-GEMM operand, column p(g,u) = (g/2)*2H + 4*(u/2) + 2*(g%2) + u%2  */
+    const float* b_tile;    /* [4H]       b_ih + b_hh in the same column order                                  */
+    const float* w_lane;    /* [(C+H)/4][4H][4]  slot s = 4u+g holds row g*H+u of [W_ih | W_hh], 4 k per float4  */
+    const float* b_lane;    /* [4H]       b_ih + b_hh, slot order 4u+g                                           */
+    const float* lin_t;     /* [H][C]     output projection, transposed (this direction's half for the BiLSTM)  */
+    const float* lin_n;     /* [C][H]     output projection, natural                                             */
+    const float* lin_b;     /* [C]        projection bias (added by direction 0 only)                            */
+    const float* ln_g;      /* [C]        LayerNorm gain applied to the LSTM input                               */
+    const float* ln_b;      /* [C]                                                                               */
+} sb_lstm_dir;
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a3-a5: STFT + re/im regroup + inter-microphone features.                                                     */
+/* Replaces self.enc(input) (DE3:475, asteroid Encoder∘STFTFB), the split/cat (:482-484) and                    */
+/* MC_features_OMNX / MC_features_direct (:72-93, :176-207).                                                    */
+/*   wave  [B][M][n_samples], frame t covers samples [t*stride, t*stride + n_fft); T = (n_samples-n_fft)/stride+1 */
+/*   filt  [2F][n_fft]  the checkpoint buffer enc.filterbank._filters (rows 0..F-1 real, F..2F-1 imaginary)      */
+/*   feats [B][T][F][Cin], Cin = 2M (+ features): channels [Re m0..mM-1, Im m0..mM-1, ILD..., sin1,cos1,...]     */
+/*   spec  optional [B][T][S][2F]: STFT of the first `n_src` microphones (only for spectral masking, :529-530)   */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_stft_args {
+    const float* wave;
+    const float* filt;
+    float*       feats;
+    float*       spec;          /* may be NULL */
+    int B, M, n_samples, T;
+    int n_fft, stride, F;
+    int feat_mode, Cin, n_src;
+} sb_stft_args;
+int sb_stft_features_fwd(const sb_stft_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a6: causal Conv2d(Cin -> C, k=(3 time, 3 freq), pad (0,1)) over [2 history frames ; T frames] + LayerNorm(C). */
+/* Replaces torch.cat((conv_buf, batch)) / self.conv (DE3:504-507, :332-354, LayerNormPermuted :219-231).        */
+/*   w_pack [3][Cin][3][C] = conv.0.weight[o][c][kt][kf] re-ordered (kt, c, kf, o); bias [C]; ln_g/ln_b NULL if  */
+/*   use_first_ln is false.  conv_buf_in/out [B][Cin][2][F] (reference layout); in and out must NOT alias.       */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_conv_in_args {
+    const float* feats;         /* [B][T][F][Cin] */
+    const float* conv_buf_in;
+    float*       conv_buf_out;
+    const float* w_pack;
+    const float* bias;
+    const float* ln_g;
+    const float* ln_b;
+    float*       x;             /* [B][T][F][C] */
+    int B, T, F, Cin, C;
+} sb_conv_in_args;
+int sb_conv_in_fwd(const sb_conv_in_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a7 + a8 (parameter part): Dis_Embed_Conv / Dis_Embed_Linear (DE3:114-173) and the two 1x1 convs of every      */
+/* FilmLayer (:51-68).                                                                                           */
+/*   dis [B][3]; emb_w [F*Din][3]; emb_ln_g/b [Din] (conv) or [F*Din] (linear)                                    */
+/*   out film [n_layers][2][B][F][C]  (index 0 = scale, 1 = shift)                                               */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_film_args {
+    const float* dis;
+    const float* emb_w;
+    const float* emb_ln_g;
+    const float* emb_ln_b;
+    const float* w_w;           /* [n_layers][C][Din]  embeds.j.weight.weight */
+    const float* w_b;           /* [n_layers][C]       embeds.j.weight.bias   */
+    const float* b_w;           /* [n_layers][C][Din]  embeds.j.bias.weight   */
+    const float* b_b;           /* [n_layers][C]       embeds.j.bias.bias     */
+    float*       film;
+    int B, F, C, Din, n_layers;
+    int emb_mode;               /* SB_EMB_CONV / SB_EMB_LINEAR */
+} sb_film_args;
+int sb_film_params_fwd(const sb_film_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a8 (apply) + a9: FiLM, LayerNorm(C), BiLSTM across frequency (zero initial state every frame),                */
+/* Linear(2H -> C), residual.  Replaces FilmLayer.forward (DE3:51-68, called :509-513) and the intra branch of   */
+/* GridNetBlock.forward (DE3:794-827, conv_lstm=false).                                                          */
+/*   x [B][T][F][C] -> y_fwd, y_bwd [B][T][F][C] with  y_fwd + y_bwd = intra_linear(BiLSTM(LN(x'))) + x',        */
+/*   x' = x*film_scale + film_shift (film_* NULL for block 0 / the OPT variant).  The two directions are written */
+/*   by different CTAs to different buffers; the consumer (sb_inter_lstm_fwd) adds them while loading.           */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_intra_args {
+    const float* x;
+    const float* film_scale;    /* [B][F][C] or NULL */
+    const float* film_shift;
+    float*       y_fwd;
+    float*       y_bwd;
+    sb_lstm_dir  dir[2];
+    int B, T, F, C, H;
+    int algo;
+} sb_intra_args;
+int sb_intra_lstm_fwd(const sb_intra_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a8 (apply) + a9': the conv-LSTM intra branch (DE3:800-815, OPT:684-697, 494-510):                             */
+/*   FiLM -> Conv1d(C -> C, k = s = down) over frequency -> PReLU -> LayerNorm(C) -> BiLSTM over J = (F-k)/k + 1  */
+/*   steps -> ConvTranspose1d(2H -> C, k = s = down) -> (pad&crop | output_padding) -> + x'.                      */
+/*   conv_w [down][C][C] = blocks.i.conv.weight[o][c][j] re-ordered (j, c, o); deconv_w [2][down][H][C] =        */
+/*   blocks.i.deconv.weight[d*H+u][c][j] re-ordered (d, j, u, c).  The LSTM entries lin_* of dir[] are unused.   */
+/*   ws: workspace of B*T*J*(C + 2H) floats.  y [B][T][F][C].                                                    */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_intra_conv_args {
+    const float* x;
+    const float* film_scale;    /* [B][F][C] or NULL */
+    const float* film_shift;
+    float*       y;
+    const float* conv_w;
+    const float* conv_b;        /* [C] */
+    const float* prelu;         /* [1] */
+    const float* deconv_w;
+    const float* deconv_b;      /* [C] */
+    sb_lstm_dir  dir[2];        /* ln_g/ln_b = blocks.i.norm.norm */
+    float*       ws;
+    int B, T, F, C, H;
+    int down, tail_mode;
+    int algo;
+} sb_intra_conv_args;
+int sb_intra_convlstm_fwd(const sb_intra_conv_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a10: LayerNorm(C), LSTM across time from (h0, c0), Linear(H -> C), residual.  Replaces the inter branch of    */
+/* GridNetBlock.forward (DE3:829-849).  Input is x0 (+ x1 if not NULL, the two intra directions).                */
+/*   h0, c0, hN, cN [B*F][H] with row b*F + f (DE3:833,840); hN/cN may alias h0/c0.                              */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_inter_args {
+    const float* x0;
+    const float* x1;            /* may be NULL */
+    float*       y;             /* [B][T][F][C] */
+    const float* h0;
+    const float* c0;
+    float*       hN;
+    float*       cN;
+    sb_lstm_dir  dir;
+    int B, T, F, C, H;
+    int algo;
+} sb_inter_args;
+int sb_inter_lstm_fwd(const sb_inter_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a11: sliding-window full-band self-attention (DE3:639-684, 856-898, 722-744), heads L, window W:              */
+/*   Q,K = LN_{F*E}(PReLU(Linear(C -> L*E))) per head, V = LN_{F*Vd}(PReLU(Linear(C -> C))) per head (Vd = C/L); */
+/*   K,V <- [history (W-1 frames, zero-initialised, NOT masked) ; current]; per frame softmax(q.K^T/sqrt(F*E)) V; */
+/*   heads regrouped -> PReLU(Linear(C -> C)) -> LN_{F*C} -> + x.                                                 */
+/*   K_buf_in/out [B*L][W-1][F*E], V_buf_in/out [B*L][W-1][F*Vd] (reference layout); in/out must NOT alias.      */
+/*   ws: workspace of sb_attn_workspace_floats(B, T, F, C, L, E, W) floats.                                      */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_attn_proj {
+    const float* w;             /* [out][C]  attn_conv_*.0.weight      */
+    const float* b;             /* [out]                                */
+    const float* prelu;         /* [1]       attn_conv_*.1.weight       */
+    const float* ln_g;          /* [F*out/L] attn_conv_*.3.norm.weight  */
+    const float* ln_b;
+} sb_attn_proj;
+typedef struct sb_attn_args {
+    const float* x;             /* [B][T][F][C] */
+    float*       y;             /* [B][T][F][C]; may alias x */
+    sb_attn_proj q, k, v, o;
+    const float* K_buf_in;  float* K_buf_out;
+    const float* V_buf_in;  float* V_buf_out;
+    float*       ws;
+    int B, T, F, C, L, E, W;
+} sb_attn_args;
+size_t sb_attn_workspace_floats(int B, int T, int F, int C, int L, int E, int W);
+int    sb_attn_fwd(const sb_attn_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* a13-a15: causal ConvTranspose2d(C -> 2S, k=(3,3), pad (2,1)) over [2 history frames ; T frames], optional     */
+/* spectral masking, iSTFT with the previous frame carried, overlap-add, crops.  Replaces DE3:517-542.           */
+/*   w [C][2S][3][3] = deconv.weight as stored; bias [2S]; filt [2F][n_fft] = dec.filterbank._filters            */
+/*   deconv_buf_in/out [B][C][2][F]; istft_buf_in/out [B][S][2F] (reference shape [B,S,2F,1]); no in/out alias   */
+/*   wave_out [B][S][stride*T]                                                                                   */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_backend_args {
+    const float* x;             /* [B][T][F][C] */
+    const float* deconv_buf_in;
+    float*       deconv_buf_out;
+    const float* istft_buf_in;
+    float*       istft_buf_out;
+    const float* w;
+    const float* bias;
+    const float* filt;
+    const float* mask_spec;     /* optional [B][T][S][2F] from sb_stft_features_fwd, NULL = no spectral masking */
+    float*       wave_out;
+    float*       ws;            /* workspace of B*(T+1)*S*2F floats (the output spectrum incl. the carried frame) */
+    int B, T, F, C, n_src;
+    int n_fft, stride;
+} sb_backend_args;
+int sb_backend_fwd(const sb_backend_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* The whole path in one call: TFGridNet.forward (DE3:433-552 / OPT:328-441)                                     */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_block_desc {
+    sb_lstm_dir  intra[2];
+    sb_lstm_dir  inter;
+    /* conv-LSTM intra (conv_lstm = true), else NULL */
+    const float* cl_conv_w; const float* cl_conv_b; const float* cl_prelu;
+    const float* cl_deconv_w; const float* cl_deconv_b;
+    /* attention (use_attn = true), else w == NULL */
+    sb_attn_proj attn_q, attn_k, attn_v, attn_o;
+} sb_block_desc;
+
+typedef struct sb_net_desc {
+    int M, n_fft, stride, F;            /* microphones, window, hop, n_fft/2+1              */
+    int C, H, n_blocks, n_src;          /* emb_dim D, lstm hidden, B, num_src               */
+    int feat_mode, Cin;
+    int film_din;                       /* 0 = no distance embedding (OPT variant)          */
+    int emb_mode;
+    int spectral_masking;
+    int conv_lstm, lstm_down, tail_mode;
+    int use_attn, L, E, W;
+    const float* enc_filt;
+    const float* dec_filt;
+    const float* conv_w_pack;
+    const float* conv_bias;
+    const float* conv_ln_g;             /* NULL if use_first_ln false */
+    const float* conv_ln_b;
+    const float* emb_w;
+    const float* emb_ln_g;
+    const float* emb_ln_b;
+    const float* film_w_w;
+    const float* film_w_b;
+    const float* film_b_w;
+    const float* film_b_b;
+    const float* deconv_w;
+    const float* deconv_bias;
+    sb_block_desc blocks[SB_MAX_BLOCKS];
+} sb_net_desc;
+
+typedef struct sb_net_io {
+    const float* wave;                  /* [B][M][n_samples], n_samples = stride*T + (n_fft - stride)            */
+    const float* dis_embed;             /* [B][3] or NULL                                                         */
+    float*       wave_out;              /* [B][S][stride*T]                                                       */
+    const float* conv_buf_in;   float* conv_buf_out;
+    const float* deconv_buf_in; float* deconv_buf_out;
+    const float* istft_buf_in;  float* istft_buf_out;
+    const float* h_in[SB_MAX_BLOCKS];   float* h_out[SB_MAX_BLOCKS];      /* may alias */
+    const float* c_in[SB_MAX_BLOCKS];   float* c_out[SB_MAX_BLOCKS];
+    const float* K_in[SB_MAX_BLOCKS];   float* K_out[SB_MAX_BLOCKS];      /* must not alias */
+    const float* V_in[SB_MAX_BLOCKS];   float* V_out[SB_MAX_BLOCKS];
+    float*       workspace;             /* sb_workspace_floats(desc, B, T) floats                                 */
+    int B, T;
+    int intra_algo, inter_algo;
+} sb_net_io;
+
+size_t sb_workspace_floats(const sb_net_desc* d, int B, int T);
+int    sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
+int         sb_version(void);
+const char* sb_last_error_string(void);
+/* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches)      */
+uint64_t    sb_launch_count(void);
+/* sizeof() of the structs above as compiled, so the ctypes mirror can be checked without a GPU                 */
+/*   0 lstm_dir 1 stft 2 conv_in 3 film 4 intra 5 inter 6 backend 7 net_desc 8 net_io 9 intra_conv 10 attn_proj */
+/*   11 attn 12 block_desc                                                                                      */
+int         sb_abi_sizeof(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOUNDBUBBLE_H_ */

@@ -1,0 +1,164 @@
+"""ctypes mirror of include/soundbubble.h (struct layouts, constants, prototypes).  Pure declarations: no library is
+loaded here (see _lib.py for the product loader; tests/emu has its own loader for the host-emulated test build)."""
+from __future__ import annotations
+
+import ctypes as C
+
+SB_VERSION = 100
+SB_MAX_BLOCKS = 16
+SB_MAX_MICS = 8
+
+SB_ALGO_AUTO, SB_ALGO_TILE, SB_ALGO_LANE1, SB_ALGO_LANE2, SB_ALGO_LANE4 = 0, 1, 2, 3, 4
+SB_FEAT_NONE, SB_FEAT_OMNI, SB_FEAT_DIRECTIONAL = 0, 1, 2
+SB_EMB_CONV, SB_EMB_LINEAR = 0, 1
+SB_CONVLSTM_PADCROP, SB_CONVLSTM_OUTPAD = 0, 1
+SB_OPT_PDL = 1
+
+fp = C.c_void_p          # device float* (raw address)
+
+
+class LstmDir(C.Structure):
+    _fields_ = [(n, fp) for n in ("w_tile", "b_tile", "w_lane", "b_lane", "lin_t", "lin_n", "lin_b", "ln_g", "ln_b")]
+
+
+class StftArgs(C.Structure):
+    _fields_ = [("wave", fp), ("filt", fp), ("feats", fp), ("spec", fp),
+                ("B", C.c_int), ("M", C.c_int), ("n_samples", C.c_int), ("T", C.c_int),
+                ("n_fft", C.c_int), ("stride", C.c_int), ("F", C.c_int),
+                ("feat_mode", C.c_int), ("Cin", C.c_int), ("n_src", C.c_int)]
+
+
+class ConvInArgs(C.Structure):
+    _fields_ = [("feats", fp), ("conv_buf_in", fp), ("conv_buf_out", fp), ("w_pack", fp), ("bias", fp),
+                ("ln_g", fp), ("ln_b", fp), ("x", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("Cin", C.c_int), ("C", C.c_int)]
+
+
+class FilmArgs(C.Structure):
+    _fields_ = [("dis", fp), ("emb_w", fp), ("emb_ln_g", fp), ("emb_ln_b", fp),
+                ("w_w", fp), ("w_b", fp), ("b_w", fp), ("b_b", fp), ("film", fp),
+                ("B", C.c_int), ("F", C.c_int), ("C", C.c_int), ("Din", C.c_int), ("n_layers", C.c_int),
+                ("emb_mode", C.c_int)]
+
+
+class IntraArgs(C.Structure):
+    _fields_ = [("x", fp), ("film_scale", fp), ("film_shift", fp), ("y_fwd", fp), ("y_bwd", fp),
+                ("dir", LstmDir * 2),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("H", C.c_int), ("algo", C.c_int)]
+
+
+class IntraConvArgs(C.Structure):
+    _fields_ = [("x", fp), ("film_scale", fp), ("film_shift", fp), ("y", fp),
+                ("conv_w", fp), ("conv_b", fp), ("prelu", fp), ("deconv_w", fp), ("deconv_b", fp),
+                ("dir", LstmDir * 2), ("ws", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("H", C.c_int),
+                ("down", C.c_int), ("tail_mode", C.c_int), ("algo", C.c_int)]
+
+
+class InterArgs(C.Structure):
+    _fields_ = [("x0", fp), ("x1", fp), ("y", fp), ("h0", fp), ("c0", fp), ("hN", fp), ("cN", fp),
+                ("dir", LstmDir),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("H", C.c_int), ("algo", C.c_int)]
+
+
+class AttnProj(C.Structure):
+    _fields_ = [(n, fp) for n in ("w", "b", "prelu", "ln_g", "ln_b")]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("x", fp), ("y", fp), ("q", AttnProj), ("k", AttnProj), ("v", AttnProj), ("o", AttnProj),
+                ("K_buf_in", fp), ("K_buf_out", fp), ("V_buf_in", fp), ("V_buf_out", fp), ("ws", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("L", C.c_int), ("E", C.c_int),
+                ("W", C.c_int)]
+
+
+class BackendArgs(C.Structure):
+    _fields_ = [("x", fp), ("deconv_buf_in", fp), ("deconv_buf_out", fp), ("istft_buf_in", fp), ("istft_buf_out", fp),
+                ("w", fp), ("bias", fp), ("filt", fp), ("mask_spec", fp), ("wave_out", fp), ("ws", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("n_src", C.c_int),
+                ("n_fft", C.c_int), ("stride", C.c_int)]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("intra", LstmDir * 2), ("inter", LstmDir),
+                ("cl_conv_w", fp), ("cl_conv_b", fp), ("cl_prelu", fp), ("cl_deconv_w", fp), ("cl_deconv_b", fp),
+                ("attn_q", AttnProj), ("attn_k", AttnProj), ("attn_v", AttnProj), ("attn_o", AttnProj)]
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("M", C.c_int), ("n_fft", C.c_int), ("stride", C.c_int), ("F", C.c_int),
+                ("C", C.c_int), ("H", C.c_int), ("n_blocks", C.c_int), ("n_src", C.c_int),
+                ("feat_mode", C.c_int), ("Cin", C.c_int), ("film_din", C.c_int), ("emb_mode", C.c_int),
+                ("spectral_masking", C.c_int),
+                ("conv_lstm", C.c_int), ("lstm_down", C.c_int), ("tail_mode", C.c_int),
+                ("use_attn", C.c_int), ("L", C.c_int), ("E", C.c_int), ("W", C.c_int),
+                ("enc_filt", fp), ("dec_filt", fp), ("conv_w_pack", fp), ("conv_bias", fp),
+                ("conv_ln_g", fp), ("conv_ln_b", fp),
+                ("emb_w", fp), ("emb_ln_g", fp), ("emb_ln_b", fp),
+                ("film_w_w", fp), ("film_w_b", fp), ("film_b_w", fp), ("film_b_b", fp),
+                ("deconv_w", fp), ("deconv_bias", fp),
+                ("blocks", BlockDesc * SB_MAX_BLOCKS)]
+
+
+class NetIO(C.Structure):
+    _fields_ = [("wave", fp), ("dis_embed", fp), ("wave_out", fp),
+                ("conv_buf_in", fp), ("conv_buf_out", fp),
+                ("deconv_buf_in", fp), ("deconv_buf_out", fp),
+                ("istft_buf_in", fp), ("istft_buf_out", fp),
+                ("h_in", fp * SB_MAX_BLOCKS), ("h_out", fp * SB_MAX_BLOCKS),
+                ("c_in", fp * SB_MAX_BLOCKS), ("c_out", fp * SB_MAX_BLOCKS),
+                ("K_in", fp * SB_MAX_BLOCKS), ("K_out", fp * SB_MAX_BLOCKS),
+                ("V_in", fp * SB_MAX_BLOCKS), ("V_out", fp * SB_MAX_BLOCKS),
+                ("workspace", fp),
+                ("B", C.c_int), ("T", C.c_int), ("intra_algo", C.c_int), ("inter_algo", C.c_int)]
+
+
+# index used by sb_abi_sizeof(which)
+ABI_STRUCTS = {0: LstmDir, 1: StftArgs, 2: ConvInArgs, 3: FilmArgs, 4: IntraArgs, 5: InterArgs, 6: BackendArgs,
+               7: NetDesc, 8: NetIO, 9: IntraConvArgs, 10: AttnProj, 11: AttnArgs, 12: BlockDesc}
+
+# every symbol include/soundbubble.h declares: name -> (restype, argtypes)
+PROTOTYPES = {
+    "sb_set_option": (C.c_int, [C.c_int, C.c_int]),
+    "sb_stft_features_fwd": (C.c_int, [C.POINTER(StftArgs), C.c_void_p]),
+    "sb_conv_in_fwd": (C.c_int, [C.POINTER(ConvInArgs), C.c_void_p]),
+    "sb_film_params_fwd": (C.c_int, [C.POINTER(FilmArgs), C.c_void_p]),
+    "sb_intra_lstm_fwd": (C.c_int, [C.POINTER(IntraArgs), C.c_void_p]),
+    "sb_intra_convlstm_fwd": (C.c_int, [C.POINTER(IntraConvArgs), C.c_void_p]),
+    "sb_inter_lstm_fwd": (C.c_int, [C.POINTER(InterArgs), C.c_void_p]),
+    "sb_attn_workspace_floats": (C.c_size_t, [C.c_int] * 7),
+    "sb_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "sb_backend_fwd": (C.c_int, [C.POINTER(BackendArgs), C.c_void_p]),
+    "sb_workspace_floats": (C.c_size_t, [C.POINTER(NetDesc), C.c_int, C.c_int]),
+    "sb_net_forward": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_void_p]),
+    "sb_version": (C.c_int, []),
+    "sb_last_error_string": (C.c_char_p, []),
+    "sb_launch_count": (C.c_uint64, []),
+    "sb_abi_sizeof": (C.c_int, [C.c_int]),
+}
+
+
+class SoundBubbleError(RuntimeError):
+    pass
+
+
+def bind(cdll):
+    """Attach prototypes to a loaded CDLL and verify version + struct layouts.  Raises if any symbol is missing."""
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(cdll, name)            # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if cdll.sb_version() != SB_VERSION:
+        raise SoundBubbleError("libsoundbubble version %d != binding version %d" % (cdll.sb_version(), SB_VERSION))
+    for which, st in ABI_STRUCTS.items():
+        got = cdll.sb_abi_sizeof(which)
+        if got != C.sizeof(st):
+            raise SoundBubbleError("ABI mismatch: %s is %d bytes in the library, %d in the binding"
+                                   % (st.__name__, got, C.sizeof(st)))
+    return cdll
+
+
+def check(cdll, rc: int, what: str):
+    if rc != 0:
+        msg = cdll.sb_last_error_string()
+        raise SoundBubbleError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,150 @@
+// Shared device/host helpers for libsoundbubble_sm100a.so (sm_100a only).
+//
+// -DSB_EMU builds the same sources with g++ against tests/emu/cuda_emu.h; that build exists only so the tests can
+// check kernel logic in a GPU-less container and is never part of the product library.
+#pragma once
+
+#ifdef SB_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+#include <stdio.h>
+
+#include "soundbubble.h"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: error reporting, launch accounting, launch helper
+// ------------------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch();
+int  check_launch(const char* what);        // cudaGetLastError() -> 0 / cudaError_t, records the message
+bool pdl_enabled();                         // programmatic dependent launch (sb_set_option(SB_OPT_PDL, 1))
+int  sm_count();
+int  ensure_smem(const void* func, size_t bytes, const char* name);
+
+#define SB_REQUIRE(cond, code, ...)                 \
+    do {                                            \
+        if (!(cond)) {                              \
+            sb::set_error(__VA_ARGS__);             \
+            return (code);                          \
+        }                                           \
+    } while (0)
+
+#define SB_CHECK(expr)                              \
+    do {                                            \
+        const int sb_rc_ = (expr);                  \
+        if (sb_rc_ != 0) return sb_rc_;             \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// One place through which every kernel of the library is launched: opt-in shared memory, optional programmatic
+// dependent launch (the kernel then calls pdl_wait() before it touches anything a predecessor wrote), accounting.
+template <typename... KArgs, typename... Args>
+int launch(const char* name, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+           Args... args) {
+#ifdef SB_EMU
+    (void)st;
+    emu::launch_impl(grid, block, smem, [=]() { kern(args...); });
+    count_launch();
+    return 0;
+#else
+    if (smem > 48 * 1024) SB_CHECK(ensure_smem(reinterpret_cast<const void*>(kern), smem, name));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    unsigned n_attr = 0;
+    if (pdl_enabled()) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return check_launch(name);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------------------------
+#ifdef SB_EMU
+#define SB_DYN_SMEM(type, name) \
+    type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::g_block->dyn.data()) + 63) & ~uintptr_t(63))
+#else
+#define SB_DYN_SMEM(type, name)                                   \
+    extern __shared__ __align__(16) unsigned char sb_dyn_smem_[]; \
+    type* name = reinterpret_cast<type*>(sb_dyn_smem_)
+#endif
+
+// Programmatic dependent launch: everything before pdl_wait() (weight staging, index math) may overlap the tail of the
+// previous kernel in the stream; nothing a predecessor wrote may be read before it.  No-ops when launched normally.
+__device__ __forceinline__ void pdl_wait() {
+#ifndef SB_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef SB_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// sigmoid / tanh through ex2.approx + rcp: |abs err| ~ 1e-7, far inside the 1e-3 RMS waveform parity bar and
+// 5x fewer instructions than the libm versions.  tanh.approx (2^-11 rel err) is NOT accurate enough here.
+__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return fmaf(2.0f, sigmoid_f(2.0f * x), -1.0f); }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
+// read-only, streaming (do not pollute L1): activations are touched once per kernel
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+#ifdef SB_EMU
+    return ld4(p);
+#else
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+#endif
+}
+__device__ __forceinline__ float ldg1_stream(const float* p) {
+#ifdef SB_EMU
+    return *p;
+#else
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+#endif
+}
+// plain (coherent) loads for buffers an aliasing output of the same launch may point at
+__device__ __forceinline__ float ld_plain(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
+
+template <int WIDTH>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = WIDTH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+constexpr float kLnEps = 1e-5f;
+
+}  // namespace sb

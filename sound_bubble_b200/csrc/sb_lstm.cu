@@ -1,0 +1,601 @@
+// Intra-frame (across frequency, bidirectional) and inter-frame (across time, carried state) LSTM paths.
+//
+// Replaces, per GridNetBlock (reference DE3 = src/models/tfgridnet_realtime_clean_dis_embd3/tfgridnet_causal.py):
+//   intra:  FilmLayer (:51-68, applied :509-513) -> intra_norm -> intra_rnn (BiLSTM) -> intra_linear -> +x  (:794-827)
+//   inter:  inter_norm -> inter_rnn (h0, c0 carried) -> inter_linear -> +x                                  (:829-849)
+// Both are the same fused "sequence" kernel: [FiLM] -> LayerNorm(C) -> x W_ih^T + h W_hh^T + b -> gates -> Linear ->
+// residual, one launch per (block, path); every activation is read once and written once.
+//
+// Two kernel families share one argument block:
+//   lstm_tile_kernel : throughput path.  [W_ih|W_hh]^T (K x 256 fp32) lives in shared memory; every WARP owns 8
+//                      sequences end to end (A operand, gates, cell state, projection), so the step loop has no block
+//                      barrier and the warps of an SM drift apart and overlap FMA / MUFU / LDS phases.  Each lane
+//                      holds an 8-row x 8-column accumulator tile = all four gates of two hidden units (no shuffles
+//                      for the cell update); the output projection of step s-1 rides in the h-part of step s's GEMM.
+//   lstm_lane_kernel : latency path.  1/2/4 sequences per CTA, one gate column per thread with its K weights in
+//                      registers, h broadcast from shared memory, quad shuffles for the cell update, one barrier per
+//                      step.  Used for streaming chunks (B sequences x 145 serial steps) and small batches.
+#include <type_traits>
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+struct SeqArgs {
+    const float* x0;
+    const float* x1;            // optional second addend of the input (the two intra directions)
+    const float* film_scale;    // [n_rows / film_row_div][n_steps][C] or NULL
+    const float* film_shift;
+    float* out[2];              // per direction.  PROJ: same addressing as x.  RAW_H: [row][pos][H]
+    sb_lstm_dir w[2];
+    const float* h0;            // [n_rows][H] or NULL (zero state)
+    const float* c0;
+    float* hN;                  // [n_rows][H] or NULL
+    float* cN;
+    int n_rows, n_steps, n_dirs;
+    int rows_inner;             // row -> (row / rows_inner, row % rows_inner)
+    long long stride_outer, stride_inner, stride_pos;      // in floats
+    int film_row_div;
+};
+
+__device__ __forceinline__ long long row_base(const SeqArgs& a, int row) {
+    const int o = row / a.rows_inner;
+    return (long long)o * a.stride_outer + (long long)(row - o * a.rows_inner) * a.stride_inner;
+}
+
+// =============================================================================================================
+// tile kernel
+// =============================================================================================================
+template <int C>
+struct TileCfg {
+    static constexpr int H = 64, K = C + H, RW = 8;
+    static constexpr int AS = K + ((16 - K % 32 + 32) % 32);    // A row stride: == 16 (mod 32) -> conflict-free stores
+    static constexpr int RS = (C == 32) ? 48 : 16;              // residual row stride
+    static constexpr int warp_floats = RW * AS + 2 * RW * RS;
+    static constexpr size_t smem_floats(int nwarps) { return (size_t)K * 256 + H * C + (size_t)nwarps * warp_floats; }
+};
+
+template <int C, bool RAW_H>
+__global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
+    using Cfg = TileCfg<C>;
+    constexpr int H = Cfg::H, K = Cfg::K, RW = Cfg::RW, AS = Cfg::AS, RS = Cfg::RS;
+    constexpr int NV = C / 16;              // float4 per lane in the load / LayerNorm mapping (4 lanes per row)
+    constexpr int ORW = RW * C / 32;        // rows per lane in the projection / output mapping (lane -> channel)
+    static_assert(AS % 32 == 16 && AS % 4 == 0, "A stride");
+    SB_DYN_SMEM(float, smem);
+    float* Wt = smem;                       // [K][256]   column p(g,u) = (g/2)*128 + 4*(u/2) + 2*(g%2) + u%2
+    float* WlT = Wt + K * 256;              // [H][C]     projection, transposed
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const sb_lstm_dir& w = a.w[dir];
+    const int S = a.n_steps;
+
+    {   // stage the weights once per CTA (constant data: allowed before pdl_wait)
+        const float4* src = reinterpret_cast<const float4*>(w.w_tile);
+        float4* dst = reinterpret_cast<float4*>(Wt);
+        for (int i = tid; i < K * 64; i += blockDim.x) dst[i] = __ldg(src + i);
+        if (!RAW_H) {
+            const float4* s2 = reinterpret_cast<const float4*>(w.lin_t);
+            float4* d2 = reinterpret_cast<float4*>(WlT);
+            for (int i = tid; i < H * C / 4; i += blockDim.x) d2[i] = __ldg(s2 + i);
+        }
+    }
+    float bias[8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(w.b_tile) + lane);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(w.b_tile + 128) + lane);
+        bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+        bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+    pdl_trigger();
+    __syncthreads();                        // the only block-wide barrier
+    pdl_wait();
+
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * RW;
+    if (row0 >= a.n_rows) return;           // whole warp leaves; no barrier follows
+
+    float* A = WlT + H * C + warp * Cfg::warp_floats;      // [RW][AS]: cols 0..C-1 = LN(x_s), C..K-1 = h_{s-1}
+    float* res = A + RW * AS;                               // [2][RW][RS] x' kept for the residual
+
+    // ---- load / LayerNorm mapping: lane -> (row lr, channel group q): channels 16*v + 4*q .. +3 ------------------
+    const int lr = lane >> 2, q = lane & 3;
+    const int lrow = min(row0 + lr, a.n_rows - 1);
+    const long long lbase = row_base(a, lrow) + 4 * q;
+    const long long fbase = (long long)(lrow / a.film_row_div) * S * C + 4 * q;
+    float4 g4[NV], b4[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        g4[v] = __ldg(reinterpret_cast<const float4*>(w.ln_g + 16 * v) + q);
+        b4[v] = __ldg(reinterpret_cast<const float4*>(w.ln_b + 16 * v) + q);
+    }
+    auto load_x = [&](int step, float4 (&xv)[NV]) {
+        const int pos = dir ? S - 1 - step : step;
+        const long long off = lbase + (long long)pos * a.stride_pos;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float4 t = ldg4_stream(a.x0 + off + 16 * v);
+            if (a.x1) {
+                const float4 u = ldg4_stream(a.x1 + off + 16 * v);
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            if (a.film_scale) {
+                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + fbase + (long long)pos * C + 16 * v));
+                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + fbase + (long long)pos * C + 16 * v));
+                t.x = fmaf(t.x, fs.x, fb.x); t.y = fmaf(t.y, fs.y, fb.y);
+                t.z = fmaf(t.z, fs.z, fb.z); t.w = fmaf(t.w, fs.w, fb.w);
+            }
+            xv[v] = t;
+        }
+    };
+    auto ln_store = [&](const float4 (&xv)[NV], int slot) {
+        float s1 = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s1 += (xv[v].x + xv[v].y) + (xv[v].z + xv[v].w);
+        const float mean = group_sum<4>(s1) * (1.0f / C);
+        float s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float dx = xv[v].x - mean, dy = xv[v].y - mean, dz = xv[v].z - mean, dw = xv[v].w - mean;
+            s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+        const float rstd = rsqrtf(group_sum<4>(s2) * (1.0f / C) + kLnEps);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float4 n;
+            n.x = fmaf((xv[v].x - mean) * rstd, g4[v].x, b4[v].x);
+            n.y = fmaf((xv[v].y - mean) * rstd, g4[v].y, b4[v].y);
+            n.z = fmaf((xv[v].z - mean) * rstd, g4[v].z, b4[v].z);
+            n.w = fmaf((xv[v].w - mean) * rstd, g4[v].w, b4[v].w);
+            st4(A + lr * AS + 16 * v + 4 * q, n);
+            if (!RAW_H) st4(res + (slot * RW + lr) * RS + 16 * v + 4 * q, xv[v]);
+        }
+    };
+
+    // ---- projection / output mapping: lane -> channel oc, rows orow0 .. orow0 + ORW - 1 -------------------------
+    const int oc = lane % C;
+    const bool ohi = (ORW != RW) && (lane >= C);
+    const int orow0 = ohi ? ORW : 0;
+    long long obase[ORW];
+    bool ovalid[ORW];
+#pragma unroll
+    for (int i = 0; i < ORW; ++i) {
+        const int gr = row0 + orow0 + i;
+        ovalid[i] = gr < a.n_rows;
+        obase[i] = row_base(a, min(gr, a.n_rows - 1)) + oc;
+    }
+    const float blin = (!RAW_H && dir == 0) ? __ldg(w.lin_b + oc) : 0.0f;
+    float* const outp = a.out[dir];
+
+    auto emit = [&](int step, const float (&accp)[ORW]) {
+        const int pos = dir ? S - 1 - step : step;
+        const float* rs = res + ((step & 1) * RW + orow0) * RS + oc;
+#pragma unroll
+        for (int i = 0; i < ORW; ++i) {
+            float v = accp[i];
+            if (dir == 0) v += blin + rs[i * RS];
+            if (ovalid[i]) outp[obase[i] + (long long)pos * a.stride_pos] = v;
+        }
+    };
+
+    // ---- initial state: lane owns hidden units 2*lane, 2*lane+1 of all RW rows ------------------------------------
+    float c[RW][2];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+        const int gr = row0 + r;
+        float2 hv = make_float2(0.f, 0.f), cv = make_float2(0.f, 0.f);
+        if (a.h0 && gr < a.n_rows) {       // plain loads: hN / cN may alias h0 / c0
+            const float* hp = a.h0 + (long long)gr * H + 2 * lane;
+            const float* cp = a.c0 + (long long)gr * H + 2 * lane;
+            hv = make_float2(ld_plain(hp), ld_plain(hp + 1));
+            cv = make_float2(ld_plain(cp), ld_plain(cp + 1));
+        }
+        c[r][0] = cv.x; c[r][1] = cv.y;
+        st2(A + r * AS + C + 2 * lane, hv);
+    }
+    {
+        float4 x0v[NV];
+        load_x(0, x0v);
+        ln_store(x0v, 0);
+    }
+    __syncwarp();
+
+    const float* Wl = Wt + 4 * lane;
+    float hn[RW][2];
+    for (int s = 0; s < S; ++s) {
+        float4 xnext[NV];
+        if (s + 1 < S) load_x(s + 1, xnext);
+
+        float acc[RW][8];
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[r][j] = bias[j];
+        float accp[ORW];
+#pragma unroll
+        for (int i = 0; i < ORW; ++i) accp[i] = 0.f;
+
+        // one block of four k: 8 broadcast LDS.128 (A) + 8 LDS.128 (W) feed 256 FFMA (+ the projection of h_{s-1})
+        auto kblock = [&](int k4, auto with_proj) {
+            float av[RW][4];
+#pragma unroll
+            for (int r = 0; r < RW; ++r) {
+                const float4 t = ld4(A + r * AS + 4 * k4);
+                av[r][0] = t.x; av[r][1] = t.y; av[r][2] = t.z; av[r][3] = t.w;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = 4 * k4 + kk;
+                const float4 w0 = ld4(Wl + k * 256);
+                const float4 w1 = ld4(Wl + k * 256 + 128);
+#pragma unroll
+                for (int r = 0; r < RW; ++r) {
+                    const float x = av[r][kk];
+                    acc[r][0] = fmaf(x, w0.x, acc[r][0]); acc[r][1] = fmaf(x, w0.y, acc[r][1]);
+                    acc[r][2] = fmaf(x, w0.z, acc[r][2]); acc[r][3] = fmaf(x, w0.w, acc[r][3]);
+                    acc[r][4] = fmaf(x, w1.x, acc[r][4]); acc[r][5] = fmaf(x, w1.y, acc[r][5]);
+                    acc[r][6] = fmaf(x, w1.z, acc[r][6]); acc[r][7] = fmaf(x, w1.w, acc[r][7]);
+                }
+                if constexpr (decltype(with_proj)::value) {
+                    const float wl = WlT[(k - C) * C + oc];
+#pragma unroll
+                    for (int i = 0; i < ORW; ++i) {
+                        const float x = (ORW == RW) ? av[i][kk] : (ohi ? av[(i + ORW) % RW][kk] : av[i][kk]);
+                        accp[i] = fmaf(x, wl, accp[i]);
+                    }
+                }
+            }
+        };
+#pragma unroll 2
+        for (int k4 = 0; k4 < C / 4; ++k4) kblock(k4, std::false_type{});
+#pragma unroll 2
+        for (int k4 = C / 4; k4 < K / 4; ++k4) kblock(k4, std::integral_constant<bool, !RAW_H>{});
+        if (!RAW_H && s > 0) emit(s - 1, accp);
+
+        // gates: acc[r] = {i_u0, i_u1, f_u0, f_u1, g_u0, g_u1, o_u0, o_u1}  (PyTorch order i, f, g, o)
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float ig = sigmoid_f(acc[r][0 + j]);
+                const float fg = sigmoid_f(acc[r][2 + j]);
+                const float gg = tanh_f(acc[r][4 + j]);
+                const float og = sigmoid_f(acc[r][6 + j]);
+                c[r][j] = fmaf(fg, c[r][j], ig * gg);
+                hn[r][j] = og * tanh_f(c[r][j]);
+            }
+        __syncwarp();                       // every lane is done reading A and res[(s-1)&1]
+#pragma unroll
+        for (int r = 0; r < RW; ++r) st2(A + r * AS + C + 2 * lane, make_float2(hn[r][0], hn[r][1]));
+        if (RAW_H) {
+            const int pos = dir ? S - 1 - s : s;
+#pragma unroll
+            for (int r = 0; r < RW; ++r)
+                if (row0 + r < a.n_rows)
+                    st2(outp + ((long long)(row0 + r) * S + pos) * H + 2 * lane, make_float2(hn[r][0], hn[r][1]));
+        }
+        if (s + 1 < S) ln_store(xnext, (s + 1) & 1);
+        __syncwarp();
+    }
+
+    if (!RAW_H) {   // drain: projection of the last step
+        float accp[ORW];
+#pragma unroll
+        for (int i = 0; i < ORW; ++i) accp[i] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < H; ++k) {
+            const float wl = WlT[k * C + oc];
+#pragma unroll
+            for (int i = 0; i < ORW; ++i) accp[i] = fmaf(A[(orow0 + i) * AS + C + k], wl, accp[i]);
+        }
+        emit(S - 1, accp);
+    }
+    if (a.hN) {
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+            if (row0 + r < a.n_rows) {
+                st2(a.hN + (long long)(row0 + r) * H + 2 * lane, make_float2(hn[r][0], hn[r][1]));
+                st2(a.cN + (long long)(row0 + r) * H + 2 * lane, make_float2(c[r][0], c[r][1]));
+            }
+    }
+}
+
+// =============================================================================================================
+// lane kernel
+// =============================================================================================================
+template <int C, int RL, bool RAW_H>
+__global__ void __launch_bounds__(256, 1) lstm_lane_kernel(const SeqArgs a) {
+    constexpr int H = 64;
+    constexpr int LPP = C / 4;            // lanes per (step,row) pair in the load/LayerNorm mapping
+    constexpr int PB = 256 / LPP;         // pairs per block of steps
+    constexpr int SB = PB / RL;           // steps per block
+    constexpr int NP = H * C / 256;       // projection terms per thread
+    constexpr int LPO = H / NP;           // lanes per projection output
+    static_assert(PB * C == 1024, "block buffers are 1024 floats");
+    static_assert(SB >= 2, "phase_c needs two steps of slack");
+    __shared__ __align__(16) float xn[1024];
+    __shared__ __align__(16) float res[2][1024];
+    __shared__ __align__(16) float outb[2][1024];
+    __shared__ __align__(16) float hs[2][RL * H];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const sb_lstm_dir& w = a.w[dir];
+    const int S = a.n_steps;
+    const int row0 = blockIdx.x * RL;
+    const int nblk = (S + SB - 1) / SB;
+
+    // gate-column role: slot tid <-> hidden unit u = tid / 4, gate g = tid % 4 (weight row g*H + u)
+    const int g = lane & 3;
+    const int u = tid >> 2;
+    float wih[C], whh[H];
+    {
+        const float4* src = reinterpret_cast<const float4*>(w.w_lane) + tid;
+#pragma unroll
+        for (int qq = 0; qq < C / 4; ++qq) {
+            const float4 v = __ldg(src + qq * 256);
+            wih[4 * qq] = v.x; wih[4 * qq + 1] = v.y; wih[4 * qq + 2] = v.z; wih[4 * qq + 3] = v.w;
+        }
+#pragma unroll
+        for (int qq = 0; qq < H / 4; ++qq) {
+            const float4 v = __ldg(src + (C / 4 + qq) * 256);
+            whh[4 * qq] = v.x; whh[4 * qq + 1] = v.y; whh[4 * qq + 2] = v.z; whh[4 * qq + 3] = v.w;
+        }
+    }
+    const float bias = __ldg(w.b_lane + tid);
+    const float act_in = (g == 2) ? 2.0f : 1.0f;        // tanh(x) = 2 sigmoid(2x) - 1 for the cell gate
+    const float act_mul = (g == 2) ? 2.0f : 1.0f;
+    const float act_add = (g == 2) ? -1.0f : 0.0f;
+    const int quad = lane & ~3;
+
+    // projection role: output channel po, k-slice pk
+    const int po = tid / LPO, pk = tid % LPO;
+    float wlin[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) wlin[j] = RAW_H ? 0.f : __ldg(w.lin_n + NP * tid + j);
+
+    // load / LayerNorm role: pair pq (step-in-block, row), channel quad c4
+    const int pq = tid / LPP, c4 = tid % LPP;
+    const int p_sb = pq / RL, p_r = pq % RL;
+    const bool p_rowok = row0 + p_r < a.n_rows;
+    const int p_row = min(row0 + p_r, a.n_rows - 1);
+    const long long p_base = row_base(a, p_row) + 4 * c4;
+    const long long p_fbase = (long long)(p_row / a.film_row_div) * S * C + 4 * c4;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(w.ln_g) + c4);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.ln_b) + c4);
+    float4 blin4 = make_float4(0, 0, 0, 0);
+    if (!RAW_H && dir == 0) blin4 = __ldg(reinterpret_cast<const float4*>(w.lin_b) + c4);
+    float* const outp = a.out[dir];
+
+    pdl_trigger();
+    pdl_wait();
+
+    auto prefetch = [&](int blk) -> float4 {
+        const int s = blk * SB + p_sb;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (s < S && p_rowok) {
+            const int pos = dir ? S - 1 - s : s;
+            const long long off = p_base + (long long)pos * a.stride_pos;
+            v = ldg4_stream(a.x0 + off);
+            if (a.x1) {
+                const float4 t = ldg4_stream(a.x1 + off);
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            if (a.film_scale) {
+                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + p_fbase + (long long)pos * C));
+                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + p_fbase + (long long)pos * C));
+                v.x = fmaf(v.x, fs.x, fb.x); v.y = fmaf(v.y, fs.y, fb.y);
+                v.z = fmaf(v.z, fs.z, fb.z); v.w = fmaf(v.w, fs.w, fb.w);
+            }
+        }
+        return v;
+    };
+    auto phase_a = [&](int blk, const float4 v) {
+        const float mean = group_sum<LPP>((v.x + v.y) + (v.z + v.w)) * (1.0f / C);
+        const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+        const float var = group_sum<LPP>((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / C);
+        const float rstd = rsqrtf(var + kLnEps);
+        st4(xn + pq * C + 4 * c4, make_float4(fmaf(dx * rstd, g4.x, b4.x), fmaf(dy * rstd, g4.y, b4.y),
+                                              fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w)));
+        st4(res[blk & 1] + pq * C + 4 * c4, v);
+    };
+    auto phase_c = [&](int blk) {
+        if (RAW_H) return;
+        const int s = blk * SB + p_sb;
+        if (s < S && p_rowok) {
+            float4 v = ld4(outb[blk & 1] + pq * C + 4 * c4);
+            if (dir == 0) {
+                const float4 r = ld4(res[blk & 1] + pq * C + 4 * c4);
+                v.x += blin4.x + r.x; v.y += blin4.y + r.y; v.z += blin4.z + r.z; v.w += blin4.w + r.w;
+            }
+            const int pos = dir ? S - 1 - s : s;
+            st4(outp + p_base + (long long)pos * a.stride_pos, v);
+        }
+    };
+
+    // ---- initial state -------------------------------------------------------------------------------------
+    float c[RL], hlast[RL];
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+        const bool ok = a.h0 && row0 + r < a.n_rows;
+        hlast[r] = ok ? ld_plain(a.h0 + (long long)(row0 + r) * H + u) : 0.0f;
+        c[r] = ok ? ld_plain(a.c0 + (long long)(row0 + r) * H + u) : 0.0f;
+        if (g == 0) hs[0][r * H + u] = hlast[r];
+    }
+
+    float4 xpre = prefetch(0);
+    int cur = 0;
+    for (int s = 0; s <= S; ++s) {
+        const int blk = s / SB, sb = s - blk * SB;
+        if (sb == 0 && s < S) {
+            phase_a(blk, xpre);
+            __syncthreads();
+            xpre = prefetch(blk + 1);
+        }
+        float accx[RL];
+        if (s < S) {
+#pragma unroll
+            for (int r = 0; r < RL; ++r) {
+                const float* xr = xn + (sb * RL + r) * C;
+                float a0 = bias, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < C / 4; ++qq) {
+                    const float4 v = ld4(xr + 4 * qq);
+                    a0 = fmaf(wih[4 * qq], v.x, a0); a1 = fmaf(wih[4 * qq + 1], v.y, a1);
+                    a2 = fmaf(wih[4 * qq + 2], v.z, a2); a3 = fmaf(wih[4 * qq + 3], v.w, a3);
+                }
+                accx[r] = (a0 + a1) + (a2 + a3);
+            }
+        }
+        __syncthreads();                               // h_{s-1} of every column is in hs[cur]
+        if (sb == 1 && blk > 0) phase_c(blk - 1);
+
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+            const float* hrow = hs[cur] + r * H;
+            if (!RAW_H && s > 0) {                      // projection of step s-1 (needs the full h vector)
+                float pp = 0.f;
+#pragma unroll
+                for (int j = 0; j < NP; j += 4) {
+                    const float4 v = ld4(hrow + NP * pk + j);
+                    pp = fmaf(wlin[j], v.x, pp); pp = fmaf(wlin[j + 1], v.y, pp);
+                    pp = fmaf(wlin[j + 2], v.z, pp); pp = fmaf(wlin[j + 3], v.w, pp);
+                }
+                pp = group_sum<LPO>(pp);
+                if (pk == 0) {
+                    const int sp = s - 1;
+                    const int bp = sp / SB;
+                    outb[bp & 1][((sp - bp * SB) * RL + r) * C + po] = pp;
+                }
+            }
+            if (s < S) {
+                float a0 = accx[r], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < H / 4; ++qq) {
+                    const float4 v = ld4(hrow + 4 * qq);
+                    a0 = fmaf(whh[4 * qq], v.x, a0); a1 = fmaf(whh[4 * qq + 1], v.y, a1);
+                    a2 = fmaf(whh[4 * qq + 2], v.z, a2); a3 = fmaf(whh[4 * qq + 3], v.w, a3);
+                }
+                const float pre = (a0 + a1) + (a2 + a3);
+                const float act = fmaf(sigmoid_f(pre * act_in), act_mul, act_add);
+                const float ai = __shfl_sync(0xffffffffu, act, quad + 0);
+                const float af = __shfl_sync(0xffffffffu, act, quad + 1);
+                const float ag = __shfl_sync(0xffffffffu, act, quad + 2);
+                const float ao = __shfl_sync(0xffffffffu, act, quad + 3);
+                c[r] = fmaf(af, c[r], ai * ag);
+                hlast[r] = ao * tanh_f(c[r]);
+                if (g == 0) {
+                    hs[cur ^ 1][r * H + u] = hlast[r];
+                    if (RAW_H && row0 + r < a.n_rows) {
+                        const int pos = dir ? S - 1 - s : s;
+                        outp[((long long)(row0 + r) * S + pos) * H + u] = hlast[r];
+                    }
+                }
+            }
+        }
+        cur ^= 1;
+    }
+    __syncthreads();
+    phase_c(nblk - 1);
+
+    if (g == 0 && a.hN) {
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+            if (row0 + r < a.n_rows) {
+                a.hN[(long long)(row0 + r) * H + u] = hlast[r];
+                a.cN[(long long)(row0 + r) * H + u] = c[r];
+            }
+        }
+    }
+}
+
+// =============================================================================================================
+// host side
+// =============================================================================================================
+// Cost model in SM cycles (first-order; refined from the per-step timings in profiles/): tile = 8 rows per warp,
+// FMA-issue bound; lane = one barrier-bound recurrent step per sequence group.
+static int pick_algo(int n_rows, int n_dirs, int S, int sms) {
+    const double tile_warps = (double)ceil_div(n_rows, 8) * n_dirs;
+    const double tile_wps = tile_warps / sms;                       // warps an SM must host (<= 8 resident)
+    const double tile_rounds = tile_wps <= 8.0 ? 1.0 : (double)ceil_div((int)tile_warps, sms * 8);
+    const double tile_step = 1600.0 * (tile_wps < 1.0 ? 1.0 : (tile_wps > 8.0 ? 8.0 : tile_wps)) + 1800.0;
+    const double tile = tile_rounds * (S * (tile_step < 6500.0 ? 6500.0 : tile_step) + 12000.0);
+    auto lane = [&](int rl, double step) {
+        return (double)ceil_div(ceil_div(n_rows, rl) * n_dirs, sms) * (S * step + 6000.0);
+    };
+    const double cost[5] = {0.0, tile, lane(1, 330.0), lane(2, 520.0), lane(4, 900.0)};
+    int best = SB_ALGO_TILE;
+    for (int k = SB_ALGO_LANE1; k <= SB_ALGO_LANE4; ++k)
+        if (cost[k] < cost[best]) best = k;
+    return best;
+}
+
+template <int C, bool RAW_H>
+static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
+    const int sms = sm_count();
+    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sms);
+    switch (algo) {
+        case SB_ALGO_TILE: {
+            const int tasks = ceil_div(a.n_rows, 8);
+            int nw = ceil_div(tasks * a.n_dirs, sms);
+            nw = nw < 1 ? 1 : (nw > 8 ? 8 : nw);
+            dim3 grid(ceil_div(tasks, nw), a.n_dirs);
+            return launch("lstm_tile", lstm_tile_kernel<C, RAW_H>, grid, dim3(32 * nw),
+                          TileCfg<C>::smem_floats(nw) * sizeof(float), st, a);
+        }
+        case SB_ALGO_LANE1:
+            return launch("lstm_lane1", lstm_lane_kernel<C, 1, RAW_H>, dim3(a.n_rows, a.n_dirs), dim3(256), 0, st, a);
+        case SB_ALGO_LANE2:
+            return launch("lstm_lane2", lstm_lane_kernel<C, 2, RAW_H>, dim3(ceil_div(a.n_rows, 2), a.n_dirs), dim3(256), 0, st, a);
+        case SB_ALGO_LANE4:
+            return launch("lstm_lane4", lstm_lane_kernel<C, 4, RAW_H>, dim3(ceil_div(a.n_rows, 4), a.n_dirs), dim3(256), 0, st, a);
+        default: break;
+    }
+    set_error("unknown LSTM algo %d", algo);
+    return SB_E_BADARG;
+}
+
+int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t st) {
+    SB_REQUIRE(H == 64, SB_E_UNSUPP, "LSTM kernels are instantiated for H=64 only (got H=%d)", H);
+    SB_REQUIRE(C == 32 || C == 16, SB_E_UNSUPP, "LSTM kernels are instantiated for C in {16, 32} (got C=%d)", C);
+    SB_REQUIRE(a.n_rows > 0 && a.n_steps > 0, SB_E_BADARG, "empty LSTM problem (%d rows, %d steps)", a.n_rows, a.n_steps);
+    if (C == 32) return raw_h ? run_seq_c<32, true>(a, algo, st) : run_seq_c<32, false>(a, algo, st);
+    return raw_h ? run_seq_c<16, true>(a, algo, st) : run_seq_c<16, false>(a, algo, st);
+}
+
+}  // namespace sb
+
+extern "C" int sb_intra_lstm_fwd(const sb_intra_args* p, void* stream) {
+    using namespace sb;
+    SB_REQUIRE(p && p->x && p->y_fwd && p->y_bwd, SB_E_BADARG, "sb_intra_lstm_fwd: null pointer");
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0, SB_E_BADARG, "sb_intra_lstm_fwd: bad sizes");
+    SB_REQUIRE((p->film_scale == nullptr) == (p->film_shift == nullptr), SB_E_BADARG, "film scale/shift must come together");
+    SeqArgs a{};
+    a.x0 = p->x; a.x1 = nullptr;
+    a.film_scale = p->film_scale; a.film_shift = p->film_shift;
+    a.out[0] = p->y_fwd; a.out[1] = p->y_bwd;
+    a.w[0] = p->dir[0]; a.w[1] = p->dir[1];
+    a.n_rows = p->B * p->T; a.n_steps = p->F; a.n_dirs = 2;
+    a.rows_inner = a.n_rows;                               // row (b,t) -> row * F * C
+    a.stride_outer = 0; a.stride_inner = (long long)p->F * p->C; a.stride_pos = p->C;
+    a.film_row_div = p->T;                                 // film[b][f][c]
+    return run_seq(a, p->C, p->H, false, p->algo, (cudaStream_t)stream);
+}
+
+extern "C" int sb_inter_lstm_fwd(const sb_inter_args* p, void* stream) {
+    using namespace sb;
+    SB_REQUIRE(p && p->x0 && p->y, SB_E_BADARG, "sb_inter_lstm_fwd: null pointer");
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0, SB_E_BADARG, "sb_inter_lstm_fwd: bad sizes");
+    SB_REQUIRE((p->h0 == nullptr) == (p->c0 == nullptr), SB_E_BADARG, "h0/c0 must come together");
+    SB_REQUIRE((p->hN == nullptr) == (p->cN == nullptr), SB_E_BADARG, "hN/cN must come together");
+    SeqArgs a{};
+    a.x0 = p->x0; a.x1 = p->x1;
+    a.out[0] = p->y; a.out[1] = nullptr;
+    a.w[0] = p->dir; a.w[1] = p->dir;
+    a.h0 = p->h0; a.c0 = p->c0; a.hN = p->hN; a.cN = p->cN;
+    a.n_rows = p->B * p->F; a.n_steps = p->T; a.n_dirs = 1;
+    a.rows_inner = p->F;                                   // row b*F + f  (DE3:833)
+    a.stride_outer = (long long)p->T * p->F * p->C; a.stride_inner = p->C; a.stride_pos = (long long)p->F * p->C;
+    a.film_row_div = 1;
+    return run_seq(a, p->C, p->H, false, p->algo, (cudaStream_t)stream);
+}

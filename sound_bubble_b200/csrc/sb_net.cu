@@ -1,0 +1,136 @@
+// The whole separator forward pass as one C call: TFGridNet.forward (DE3:433-552 / OPT:328-441).
+//
+// Launch sequence (all on the caller's stream, nothing allocated, no host synchronisation):
+//   stft_features -> conv_in -> [film_params] -> n_blocks x { intra (BiLSTM | conv-LSTM) -> inter LSTM -> [attention] }
+//   -> deconv_spec -> istft_ola
+// Activations ping-pong between three [B][T][F][C] buffers of the workspace: a block reads X0, the two intra directions
+// write X1 / X2, the inter path reads X1 + X2 and writes X0.
+#include "sb_common.cuh"
+
+namespace sb {
+
+struct Workspace {
+    float *feats, *spec_in, *film, *x0, *x1, *x2, *spec_out, *extra;
+    size_t total;
+};
+
+static size_t align_up(size_t n) { return (n + 63) & ~size_t(63); }      // 256-byte granules
+
+static size_t extra_floats(const sb_net_desc* d, int B, int T) {
+    size_t n = 0;
+    if (d->conv_lstm) {
+        const int J = (d->F - d->lstm_down) / d->lstm_down + 1;
+        n = (size_t)B * T * J * (d->C + 2 * d->H);
+    }
+    if (d->use_attn) {
+        const size_t m = sb_attn_workspace_floats(B, T, d->F, d->C, d->L, d->E, d->W);
+        if (m > n) n = m;
+    }
+    return n;
+}
+
+static Workspace carve(const sb_net_desc* d, int B, int T, float* base) {
+    Workspace w{};
+    size_t off = 0;
+    auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += align_up(n); return p; };
+    const size_t act = (size_t)B * T * d->F * d->C;
+    w.feats = take((size_t)B * T * d->F * d->Cin);
+    w.spec_in = d->spectral_masking ? take((size_t)B * T * d->n_src * 2 * d->F) : nullptr;
+    w.film = d->film_din > 0 && d->n_blocks > 1 ? take((size_t)(d->n_blocks - 1) * 2 * B * d->F * d->C) : nullptr;
+    w.x0 = take(act);
+    w.x1 = take(act);
+    w.x2 = d->conv_lstm ? nullptr : take(act);
+    w.spec_out = take((size_t)B * d->n_src * T * 2 * d->F);
+    const size_t ex = extra_floats(d, B, T);
+    w.extra = ex ? take(ex) : nullptr;
+    w.total = off;
+    return w;
+}
+
+}  // namespace sb
+
+extern "C" size_t sb_workspace_floats(const sb_net_desc* d, int B, int T) {
+    if (!d || B <= 0 || T <= 0) return 0;
+    return sb::carve(d, B, T, nullptr).total;
+}
+
+extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream) {
+    using namespace sb;
+    SB_REQUIRE(d && io, SB_E_BADARG, "sb_net_forward: null descriptor");
+    SB_REQUIRE(io->wave && io->wave_out && io->workspace, SB_E_BADARG, "sb_net_forward: null wave / wave_out / workspace");
+    SB_REQUIRE(io->B > 0 && io->T > 0, SB_E_BADARG, "sb_net_forward: bad B/T");
+    SB_REQUIRE(d->n_blocks > 0 && d->n_blocks <= SB_MAX_BLOCKS, SB_E_UNSUPP, "sb_net_forward: n_blocks=%d out of range", d->n_blocks);
+    SB_REQUIRE(d->film_din == 0 || io->dis_embed, SB_E_BADARG, "sb_net_forward: dis_embed is required by this model");
+    SB_REQUIRE(((uintptr_t)io->workspace & 15) == 0, SB_E_BADARG, "sb_net_forward: workspace must be 16-byte aligned");
+    const int B = io->B, T = io->T;
+    const Workspace w = carve(d, B, T, io->workspace);
+
+    sb_stft_args sa{};
+    sa.wave = io->wave; sa.filt = d->enc_filt; sa.feats = w.feats; sa.spec = w.spec_in;
+    sa.B = B; sa.M = d->M; sa.n_samples = d->stride * T + (d->n_fft - d->stride); sa.T = T;
+    sa.n_fft = d->n_fft; sa.stride = d->stride; sa.F = d->F;
+    sa.feat_mode = d->feat_mode; sa.Cin = d->Cin; sa.n_src = d->n_src;
+    SB_CHECK(sb_stft_features_fwd(&sa, stream));
+
+    sb_conv_in_args ca{};
+    ca.feats = w.feats; ca.conv_buf_in = io->conv_buf_in; ca.conv_buf_out = io->conv_buf_out;
+    ca.w_pack = d->conv_w_pack; ca.bias = d->conv_bias; ca.ln_g = d->conv_ln_g; ca.ln_b = d->conv_ln_b;
+    ca.x = w.x0; ca.B = B; ca.T = T; ca.F = d->F; ca.Cin = d->Cin; ca.C = d->C;
+    SB_CHECK(sb_conv_in_fwd(&ca, stream));
+
+    if (w.film) {
+        sb_film_args fa{};
+        fa.dis = io->dis_embed; fa.emb_w = d->emb_w; fa.emb_ln_g = d->emb_ln_g; fa.emb_ln_b = d->emb_ln_b;
+        fa.w_w = d->film_w_w; fa.w_b = d->film_w_b; fa.b_w = d->film_b_w; fa.b_b = d->film_b_b;
+        fa.film = w.film; fa.B = B; fa.F = d->F; fa.C = d->C; fa.Din = d->film_din; fa.n_layers = d->n_blocks - 1;
+        fa.emb_mode = d->emb_mode;
+        SB_CHECK(sb_film_params_fwd(&fa, stream));
+    }
+
+    const size_t film_stride = (size_t)B * d->F * d->C;
+    for (int i = 0; i < d->n_blocks; ++i) {
+        const sb_block_desc& bd = d->blocks[i];
+        const float* fscale = (w.film && i > 0) ? w.film + (size_t)(i - 1) * 2 * film_stride : nullptr;
+        const float* fshift = fscale ? fscale + film_stride : nullptr;
+        const float* inter_x1 = nullptr;
+        if (d->conv_lstm) {
+            sb_intra_conv_args ia{};
+            ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y = w.x1;
+            ia.conv_w = bd.cl_conv_w; ia.conv_b = bd.cl_conv_b; ia.prelu = bd.cl_prelu;
+            ia.deconv_w = bd.cl_deconv_w; ia.deconv_b = bd.cl_deconv_b;
+            ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
+            ia.ws = w.extra; ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H;
+            ia.down = d->lstm_down; ia.tail_mode = d->tail_mode; ia.algo = io->intra_algo;
+            SB_CHECK(sb_intra_convlstm_fwd(&ia, stream));
+        } else {
+            sb_intra_args ia{};
+            ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y_fwd = w.x1; ia.y_bwd = w.x2;
+            ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
+            ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H; ia.algo = io->intra_algo;
+            SB_CHECK(sb_intra_lstm_fwd(&ia, stream));
+            inter_x1 = w.x2;
+        }
+        sb_inter_args na{};
+        na.x0 = w.x1; na.x1 = inter_x1; na.y = w.x0;
+        na.h0 = io->h_in[i]; na.c0 = io->c_in[i]; na.hN = io->h_out[i]; na.cN = io->c_out[i];
+        na.dir = bd.inter; na.B = B; na.T = T; na.F = d->F; na.C = d->C; na.H = d->H; na.algo = io->inter_algo;
+        SB_CHECK(sb_inter_lstm_fwd(&na, stream));
+        if (d->use_attn) {
+            sb_attn_args aa{};
+            aa.x = w.x0; aa.y = w.x0;
+            aa.q = bd.attn_q; aa.k = bd.attn_k; aa.v = bd.attn_v; aa.o = bd.attn_o;
+            aa.K_buf_in = io->K_in[i]; aa.K_buf_out = io->K_out[i];
+            aa.V_buf_in = io->V_in[i]; aa.V_buf_out = io->V_out[i];
+            aa.ws = w.extra; aa.B = B; aa.T = T; aa.F = d->F; aa.C = d->C; aa.L = d->L; aa.E = d->E; aa.W = d->W;
+            SB_CHECK(sb_attn_fwd(&aa, stream));
+        }
+    }
+
+    sb_backend_args ba{};
+    ba.x = w.x0; ba.deconv_buf_in = io->deconv_buf_in; ba.deconv_buf_out = io->deconv_buf_out;
+    ba.istft_buf_in = io->istft_buf_in; ba.istft_buf_out = io->istft_buf_out;
+    ba.w = d->deconv_w; ba.bias = d->deconv_bias; ba.filt = d->dec_filt;
+    ba.mask_spec = w.spec_in; ba.wave_out = io->wave_out; ba.ws = w.spec_out;
+    ba.B = B; ba.T = T; ba.F = d->F; ba.C = d->C; ba.n_src = d->n_src; ba.n_fft = d->n_fft; ba.stride = d->stride;
+    return sb_backend_fwd(&ba, stream);
+}

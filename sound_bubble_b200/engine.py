@@ -1,0 +1,159 @@
+"""Host driver of the C-ABI library: owns workspaces and state tensors, fills sb_net_io, calls sb_net_forward.
+
+``Engine`` is handed a bound CDLL (see _lib.py) and works on whatever device its tensors live on; the product path
+(``Net``) only ever gives it the sm_100a CUDA library and CUDA tensors.  Mirrors TFGridNet.forward / init_buffers
+(DE3 = src/models/tfgridnet_realtime_clean_dis_embd3/tfgridnet_causal.py:403-421, 433-552, 696-720).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _abi as abi
+from .packing import ModelConfig, PackedWeights
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream if t.is_cuda else 0
+
+
+def init_state(cfg: ModelConfig, batch: int, device) -> dict:
+    """TFGridNet.init_buffers (DE3:403-421) + GridNetBlock.init_buffers (DE3:696-720): same keys, shapes, order."""
+    Fq = cfg.n_freqs
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+    st = {"conv_buf": z(batch, cfg.conv_in_ch, 2, Fq),
+          "deconv_buf": z(batch, cfg.D, 2, Fq),
+          "istft_buf": z(batch, cfg.num_src, 2 * Fq, 1),
+          "gridnet_bufs": {}}
+    for i in range(cfg.B):
+        buf = {}
+        if cfg.use_attn:
+            W = cfg.local_atten_len
+            buf["K_buf"] = z(batch * cfg.L, W - 1, cfg.attn_E * Fq)
+            buf["V_buf"] = z(batch * cfg.L, W - 1, (cfg.D // cfg.L) * Fq)
+        buf["c0"] = z(1, batch * Fq, cfg.H)
+        buf["h0"] = z(1, batch * Fq, cfg.H)
+        st["gridnet_bufs"][f"buf{i}"] = buf
+    return st
+
+
+class Engine:
+    def __init__(self, cdll, cfg: ModelConfig, packed: PackedWeights):
+        self.lib = cdll
+        self.cfg = cfg
+        self.packed = packed
+        self.intra_algo = abi.SB_ALGO_AUTO
+        self.inter_algo = abi.SB_ALGO_AUTO
+        self._ws: Dict[Tuple[int, int, str], torch.Tensor] = {}
+
+    # -- helpers ---------------------------------------------------------------------------------------------
+    def workspace(self, B: int, T: int, device) -> torch.Tensor:
+        key = (B, T, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            n = self.lib.sb_workspace_floats(self.packed.desc_ref(), B, T)
+            if len(self._ws) > 4:
+                self._ws.clear()
+            ws = torch.empty(max(int(n), 1), dtype=torch.float32, device=device)
+            self._ws[key] = ws
+        return ws
+
+    def n_frames(self, n_samples: int) -> int:
+        cfg = self.cfg
+        return (n_samples - cfg.n_fft) // cfg.stft_chunk_size + 1
+
+    @staticmethod
+    def _f32c(t: torch.Tensor, shape=None) -> torch.Tensor:
+        if t.dtype != torch.float32:
+            t = t.float()
+        if not t.is_contiguous():
+            t = t.contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("state tensor has shape %s, expected %s" % (tuple(t.shape), tuple(shape)))
+        return t
+
+    # -- the forward pass ------------------------------------------------------------------------------------
+    def forward(self, wave: torch.Tensor, dis_embed: Optional[torch.Tensor], state: dict,
+                out: Optional[torch.Tensor] = None, new_state: Optional[dict] = None):
+        """wave [B, M, stride*T + n_fft - stride] -> ([B, S, stride*T], state).  `state` is updated in place (the
+        dict, as the reference does, DE3:547-552) with freshly written tensors unless `new_state` supplies them."""
+        cfg, lib = self.cfg, self.lib
+        B, M, N = wave.shape
+        if M != cfg.num_ch:
+            raise ValueError("mixture has %d channels, the model was built for num_ch=%d" % (M, cfg.num_ch))
+        T = self.n_frames(N)
+        if T < 1:
+            raise ValueError("input of %d samples is shorter than one window (%d)" % (N, cfg.n_fft))
+        need = cfg.stft_chunk_size * T + cfg.n_fft - cfg.stft_chunk_size
+        dev = wave.device
+        wave = self._f32c(wave if N == need else wave[..., :need])
+        Fq, S = cfg.n_freqs, cfg.num_src
+
+        io = abi.NetIO()
+        io.B, io.T = B, T
+        io.intra_algo, io.inter_algo = self.intra_algo, self.inter_algo
+        io.wave = wave.data_ptr()
+        keep = [wave]
+        if cfg.variant == "dis_embed":
+            if dis_embed is None:
+                raise KeyError("dis_embed")
+            dis = self._f32c(dis_embed.to(dev), (B, 3))
+            io.dis_embed = dis.data_ptr()
+            keep.append(dis)
+        if out is None:
+            out = torch.empty(B, S, cfg.stft_chunk_size * T, dtype=torch.float32, device=dev)
+        io.wave_out = out.data_ptr()
+
+        ns = new_state if new_state is not None else {}
+        def fresh(name, like):
+            t = ns.get(name)
+            if t is None:
+                t = torch.empty_like(like)
+            return t
+        conv_in = self._f32c(state["conv_buf"], (B, cfg.conv_in_ch, 2, Fq))
+        deconv_in = self._f32c(state["deconv_buf"], (B, cfg.D, 2, Fq))
+        istft_in = self._f32c(state["istft_buf"], (B, S, 2 * Fq, 1))
+        conv_out, deconv_out, istft_out = fresh("conv_buf", conv_in), fresh("deconv_buf", deconv_in), fresh("istft_buf", istft_in)
+        io.conv_buf_in, io.conv_buf_out = conv_in.data_ptr(), conv_out.data_ptr()
+        io.deconv_buf_in, io.deconv_buf_out = deconv_in.data_ptr(), deconv_out.data_ptr()
+        io.istft_buf_in, io.istft_buf_out = istft_in.data_ptr(), istft_out.data_ptr()
+        keep += [conv_in, deconv_in, istft_in]
+        bufs = state["gridnet_bufs"]
+        nbufs = ns.get("gridnet_bufs", {})
+        outs = {}
+        for i in range(cfg.B):
+            buf = bufs[f"buf{i}"]
+            nb = nbufs.get(f"buf{i}", {})
+            h_in = self._f32c(buf["h0"], (1, B * Fq, cfg.H))
+            c_in = self._f32c(buf["c0"], (1, B * Fq, cfg.H))
+            h_out = nb.get("h0") if nb.get("h0") is not None else torch.empty_like(h_in)
+            c_out = nb.get("c0") if nb.get("c0") is not None else torch.empty_like(c_in)
+            io.h_in[i], io.h_out[i] = h_in.data_ptr(), h_out.data_ptr()
+            io.c_in[i], io.c_out[i] = c_in.data_ptr(), c_out.data_ptr()
+            keep += [h_in, c_in]
+            o = {"h0": h_out, "c0": c_out}
+            if cfg.use_attn:
+                W = cfg.local_atten_len
+                k_in = self._f32c(buf["K_buf"], (B * cfg.L, W - 1, cfg.attn_E * Fq))
+                v_in = self._f32c(buf["V_buf"], (B * cfg.L, W - 1, (cfg.D // cfg.L) * Fq))
+                k_out = nb.get("K_buf") if nb.get("K_buf") is not None else torch.empty_like(k_in)
+                v_out = nb.get("V_buf") if nb.get("V_buf") is not None else torch.empty_like(v_in)
+                io.K_in[i], io.K_out[i] = k_in.data_ptr(), k_out.data_ptr()
+                io.V_in[i], io.V_out[i] = v_in.data_ptr(), v_out.data_ptr()
+                keep += [k_in, v_in]
+                o["K_buf"], o["V_buf"] = k_out, v_out
+            outs[i] = o
+        ws = self.workspace(B, T, dev)
+        io.workspace = ws.data_ptr()
+
+        rc = lib.sb_net_forward(self.packed.desc_ref(), ctypes.byref(io), _stream_ptr(wave))
+        abi.check(lib, rc, "sb_net_forward")
+
+        state["conv_buf"], state["deconv_buf"], state["istft_buf"] = conv_out, deconv_out, istft_out
+        for i in range(cfg.B):
+            buf = bufs[f"buf{i}"]
+            for k, v in outs[i].items():
+                buf[k] = v
+        return out, state
