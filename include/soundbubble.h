@@ -317,6 +317,23 @@ size_t sb_workspace_floats(const sb_net_desc* d, int B, int T);
 int    sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------- */
+/* Per-stage device timing of sb_net_forward with CUDA events on the launching stream (bench.py's roofline leg).  */
+/* sb_profile_begin() arms it; every sb_net_forward until sb_profile_end() brackets each stage with events (do    */
+/* not use while the stream is being captured into a graph).  sb_profile_end() synchronises the events and adds,  */
+/* per stage kind, the total milliseconds into ms[SB_STAGE_COUNT] and the launch count into calls[SB_STAGE_COUNT].*/
+/* ---------------------------------------------------------------------------------------------------------- */
+#define SB_STAGE_STFT    0
+#define SB_STAGE_CONV_IN 1
+#define SB_STAGE_FILM    2
+#define SB_STAGE_INTRA   3
+#define SB_STAGE_INTER   4
+#define SB_STAGE_ATTN    5
+#define SB_STAGE_BACKEND 6
+#define SB_STAGE_COUNT   7
+int sb_profile_begin(void);
+int sb_profile_end(double* ms, int64_t* calls);
+
+/* ---------------------------------------------------------------------------------------------------------- */
 int         sb_version(void);
 const char* sb_last_error_string(void);
 /* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches)      */

@@ -13,6 +13,7 @@ SB_FEAT_NONE, SB_FEAT_OMNI, SB_FEAT_DIRECTIONAL = 0, 1, 2
 SB_EMB_CONV, SB_EMB_LINEAR = 0, 1
 SB_CONVLSTM_PADCROP, SB_CONVLSTM_OUTPAD = 0, 1
 SB_OPT_PDL = 1
+SB_STAGES = ("stft_features", "conv_in", "film_params", "intra", "inter", "attention", "backend")
 
 fp = C.c_void_p          # device float* (raw address)
 
@@ -131,6 +132,8 @@ PROTOTYPES = {
     "sb_backend_fwd": (C.c_int, [C.POINTER(BackendArgs), C.c_void_p]),
     "sb_workspace_floats": (C.c_size_t, [C.POINTER(NetDesc), C.c_int, C.c_int]),
     "sb_net_forward": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_void_p]),
+    "sb_profile_begin": (C.c_int, []),
+    "sb_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "sb_version": (C.c_int, []),
     "sb_last_error_string": (C.c_char_p, []),
     "sb_launch_count": (C.c_uint64, []),

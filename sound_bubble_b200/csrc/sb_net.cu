@@ -5,9 +5,36 @@
 //   -> deconv_spec -> istft_ola
 // Activations ping-pong between three [B][T][F][C] buffers of the workspace: a block reads X0, the two intra directions
 // write X1 / X2, the inter path reads X1 + X2 and writes X0.
+#include <mutex>
+#include <vector>
+
 #include "sb_common.cuh"
 
 namespace sb {
+
+// ---- optional per-stage timing (CUDA events on the launching stream) ------------------------------------------------
+#ifndef SB_EMU
+struct StageEvent { int kind; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<StageEvent> g_prof_events;
+
+struct StageTimer {
+    cudaStream_t st; int kind; bool on; cudaEvent_t a, b;
+    StageTimer(void* stream, int k) : st((cudaStream_t)stream), kind(k), on(g_prof_on) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~StageTimer() {
+        if (on) {
+            cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lock(g_prof_mu);
+            g_prof_events.push_back({kind, a, b});
+        }
+    }
+};
+#else
+struct StageTimer { StageTimer(void*, int) {} };
+#endif
 
 struct Workspace {
     float *feats, *spec_in, *film, *x0, *x1, *x2, *spec_out, *extra;
@@ -70,13 +97,13 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     sa.B = B; sa.M = d->M; sa.n_samples = d->stride * T + (d->n_fft - d->stride); sa.T = T;
     sa.n_fft = d->n_fft; sa.stride = d->stride; sa.F = d->F;
     sa.feat_mode = d->feat_mode; sa.Cin = d->Cin; sa.n_src = d->n_src;
-    SB_CHECK(sb_stft_features_fwd(&sa, stream));
+    { StageTimer tm(stream, SB_STAGE_STFT); SB_CHECK(sb_stft_features_fwd(&sa, stream)); }
 
     sb_conv_in_args ca{};
     ca.feats = w.feats; ca.conv_buf_in = io->conv_buf_in; ca.conv_buf_out = io->conv_buf_out;
     ca.w_pack = d->conv_w_pack; ca.bias = d->conv_bias; ca.ln_g = d->conv_ln_g; ca.ln_b = d->conv_ln_b;
     ca.x = w.x0; ca.B = B; ca.T = T; ca.F = d->F; ca.Cin = d->Cin; ca.C = d->C;
-    SB_CHECK(sb_conv_in_fwd(&ca, stream));
+    { StageTimer tm(stream, SB_STAGE_CONV_IN); SB_CHECK(sb_conv_in_fwd(&ca, stream)); }
 
     if (w.film) {
         sb_film_args fa{};
@@ -84,7 +111,7 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
         fa.w_w = d->film_w_w; fa.w_b = d->film_w_b; fa.b_w = d->film_b_w; fa.b_b = d->film_b_b;
         fa.film = w.film; fa.B = B; fa.F = d->F; fa.C = d->C; fa.Din = d->film_din; fa.n_layers = d->n_blocks - 1;
         fa.emb_mode = d->emb_mode;
-        SB_CHECK(sb_film_params_fwd(&fa, stream));
+        { StageTimer tm(stream, SB_STAGE_FILM); SB_CHECK(sb_film_params_fwd(&fa, stream)); }
     }
 
     const size_t film_stride = (size_t)B * d->F * d->C;
@@ -101,20 +128,20 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
             ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
             ia.ws = w.extra; ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H;
             ia.down = d->lstm_down; ia.tail_mode = d->tail_mode; ia.algo = io->intra_algo;
-            SB_CHECK(sb_intra_convlstm_fwd(&ia, stream));
+            { StageTimer tm(stream, SB_STAGE_INTRA); SB_CHECK(sb_intra_convlstm_fwd(&ia, stream)); }
         } else {
             sb_intra_args ia{};
             ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y_fwd = w.x1; ia.y_bwd = w.x2;
             ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
             ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H; ia.algo = io->intra_algo;
-            SB_CHECK(sb_intra_lstm_fwd(&ia, stream));
+            { StageTimer tm(stream, SB_STAGE_INTRA); SB_CHECK(sb_intra_lstm_fwd(&ia, stream)); }
             inter_x1 = w.x2;
         }
         sb_inter_args na{};
         na.x0 = w.x1; na.x1 = inter_x1; na.y = w.x0;
         na.h0 = io->h_in[i]; na.c0 = io->c_in[i]; na.hN = io->h_out[i]; na.cN = io->c_out[i];
         na.dir = bd.inter; na.B = B; na.T = T; na.F = d->F; na.C = d->C; na.H = d->H; na.algo = io->inter_algo;
-        SB_CHECK(sb_inter_lstm_fwd(&na, stream));
+        { StageTimer tm(stream, SB_STAGE_INTER); SB_CHECK(sb_inter_lstm_fwd(&na, stream)); }
         if (d->use_attn) {
             sb_attn_args aa{};
             aa.x = w.x0; aa.y = w.x0;
@@ -122,7 +149,7 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
             aa.K_buf_in = io->K_in[i]; aa.K_buf_out = io->K_out[i];
             aa.V_buf_in = io->V_in[i]; aa.V_buf_out = io->V_out[i];
             aa.ws = w.extra; aa.B = B; aa.T = T; aa.F = d->F; aa.C = d->C; aa.L = d->L; aa.E = d->E; aa.W = d->W;
-            SB_CHECK(sb_attn_fwd(&aa, stream));
+            { StageTimer tm(stream, SB_STAGE_ATTN); SB_CHECK(sb_attn_fwd(&aa, stream)); }
         }
     }
 
@@ -132,5 +159,37 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     ba.w = d->deconv_w; ba.bias = d->deconv_bias; ba.filt = d->dec_filt;
     ba.mask_spec = w.spec_in; ba.wave_out = io->wave_out; ba.ws = w.spec_out;
     ba.B = B; ba.T = T; ba.F = d->F; ba.C = d->C; ba.n_src = d->n_src; ba.n_fft = d->n_fft; ba.stride = d->stride;
+    StageTimer tm(stream, SB_STAGE_BACKEND);
     return sb_backend_fwd(&ba, stream);
+}
+
+extern "C" int sb_profile_begin(void) {
+#ifndef SB_EMU
+    std::lock_guard<std::mutex> lock(sb::g_prof_mu);
+    sb::g_prof_on = true;
+#endif
+    return 0;
+}
+
+extern "C" int sb_profile_end(double* ms, int64_t* calls) {
+    using namespace sb;
+    SB_REQUIRE(ms && calls, SB_E_BADARG, "sb_profile_end: null output");
+#ifndef SB_EMU
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_prof_on = false;
+    int rc = 0;
+    for (auto& e : g_prof_events) {
+        float t = 0.f;
+        cudaError_t err = cudaEventSynchronize(e.b);
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&t, e.a, e.b);
+        if (err != cudaSuccess) { set_error("sb_profile_end: %s", cudaGetErrorString(err)); rc = (int)err; }
+        else if (e.kind >= 0 && e.kind < SB_STAGE_COUNT) { ms[e.kind] += t; calls[e.kind] += 1; }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof_events.clear();
+    return rc;
+#else
+    return 0;
+#endif
 }

@@ -1,0 +1,42 @@
+"""Kernel logic checked on the CPU through the host-emulated TEST build of the same .cu sources (tests/emu): indexing,
+layouts and barrier structure of the SIMT kernels against the oracle / golden fixtures before they go to a B200.
+This build is test infrastructure; the product library has no CPU path (see tests/test_abi.py)."""
+import pytest
+
+import kernel_cases as kc
+import parity_cases as pc
+from oracle.cases import OPI, RPI, SYN
+from sound_bubble_b200 import _abi as abi
+
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from emu.emu_lib import load
+    return load()
+
+
+def _ok(errs, tol=TOL):
+    assert all(v <= tol for v in errs.values()), errs
+
+
+def test_frontend_backend_kernels(lib):
+    _ok(kc.check_stft_features(lib, "cpu", "dis_embed", dict(SYN, spectral_masking=True), B=1, T=9, with_spec=True))
+    _ok(kc.check_stft_features(lib, "cpu", "dis_embed", dict(SYN, directional=True), B=1, T=1))
+    _ok(kc.check_conv_in(lib, "cpu", "dis_embed", SYN, B=2, T=5))
+    _ok(kc.check_conv_in(lib, "cpu", "optim", RPI, B=1, T=1))
+    _ok(kc.check_film(lib, "cpu", "dis_embed", SYN, B=4))
+    _ok(kc.check_backend(lib, "cpu", "dis_embed", SYN, B=1, T=11, with_mask=True))
+    _ok(kc.check_backend(lib, "cpu", "optim", RPI, B=2, T=1))
+
+
+@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE4])
+def test_lstm_kernels(lib, algo):
+    _ok(kc.check_inter(lib, "cpu", "dis_embed", SYN, algo, B=1, T=3, alias_state=True))
+    _ok(kc.check_intra(lib, "cpu", "dis_embed", SYN, algo, B=1, T=2))
+    _ok(kc.check_intra(lib, "cpu", "optim", dict(OPI, D=16), algo, B=1, T=2))
+
+
+def test_whole_path_golden_plain(lib):
+    pc.assert_parity(pc.run_golden(lib, "cpu", "syn_plain"))

@@ -1,0 +1,191 @@
+"""GPU parity tests proper (run with `-m gpu` on a B200): every call goes through the C ABI of
+libsoundbubble_sm100a.so, either directly (stage checks) or through the drop-in ``Net`` module."""
+import pytest
+import torch
+
+import kernel_cases as kc
+import parity_cases as pc
+from conftest import Golden, flatten_state, golden_names
+from oracle import tfgridnet_oracle as orc
+from oracle.cases import OPI, RPI, SYN
+from oracle.weights import make_state_dict, radius_one_hot, synthetic_mixture
+from sound_bubble_b200 import _abi as abi
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 2e-5          # max-abs for single stages on O(1) data (fp32 both sides, different summation order)
+C16 = dict(OPI, D=16)
+ALGOS = [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2, abi.SB_ALGO_LANE4, abi.SB_ALGO_AUTO]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sound_bubble_b200 import _lib
+    return _lib.load()
+
+
+def _ok(errs, tol=TOL):
+    assert all(v <= tol for v in errs.values()), errs
+
+
+# ---- stage-level -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw,B,T,spec", [(SYN, 2, 5, False), (dict(SYN, spectral_masking=True), 1, 9, True),
+                                         (dict(SYN, directional=True), 1, 1, False),
+                                         (dict(SYN, merge_method="None"), 1, 2, False), (SYN, 3, 37, False)])
+def test_stft_features(lib, kw, B, T, spec):
+    _ok(kc.check_stft_features(lib, DEV, "dis_embed", kw, B=B, T=T, with_spec=spec))
+
+
+@pytest.mark.parametrize("variant,kw,B,T", [("dis_embed", SYN, 2, 5), ("dis_embed", SYN, 2, 1), ("optim", RPI, 1, 2),
+                                            ("dis_embed", dict(SYN, merge_method="None", use_first_ln=False), 1, 4),
+                                            ("dis_embed", SYN, 2, 23)])
+def test_conv_in(lib, variant, kw, B, T):
+    _ok(kc.check_conv_in(lib, DEV, variant, kw, B=B, T=T))
+
+
+def test_film(lib):
+    _ok(kc.check_film(lib, DEV, "dis_embed", SYN, B=4))
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("variant,kw", [("dis_embed", SYN), ("optim", C16)])
+def test_intra_lstm(lib, algo, variant, kw):
+    _ok(kc.check_intra(lib, DEV, variant, kw, algo, B=2, T=13, block=1))
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("variant,kw", [("dis_embed", SYN), ("optim", C16)])
+def test_inter_lstm(lib, algo, variant, kw):
+    _ok(kc.check_inter(lib, DEV, variant, kw, algo, B=2, T=37, block=2))
+    _ok(kc.check_inter(lib, DEV, variant, kw, algo, B=1, T=1, alias_state=True, two_inputs=False))
+
+
+@pytest.mark.parametrize("variant,kw,B,T,mask", [("dis_embed", SYN, 2, 5, False), ("dis_embed", SYN, 2, 1, False),
+                                                 ("dis_embed", SYN, 1, 11, True), ("optim", RPI, 1, 3, False),
+                                                 ("dis_embed", SYN, 2, 70, False)])
+def test_backend(lib, variant, kw, B, T, mask):
+    _ok(kc.check_backend(lib, DEV, variant, kw, B=B, T=T, with_mask=mask))
+
+
+@pytest.mark.parametrize("variant,kw", [("dis_embed", dict(SYN, conv_lstm=True)), ("optim", RPI), ("optim", dict(RPI, lstm_down=4))])
+@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_AUTO])
+def test_intra_convlstm(lib, variant, kw, algo):
+    _ok(kc.check_intra(lib, DEV, variant, kw, algo, B=2, T=5, block=1))
+
+
+@pytest.mark.parametrize("variant,kw", [("dis_embed", dict(SYN, use_attn=True, local_atten_len=10)),
+                                        ("optim", dict(RPI, use_attn=True, local_atten_len=7)),
+                                        ("dis_embed", dict(SYN, use_attn=True, local_atten_len=100))])
+def test_attention(lib, variant, kw):
+    _ok(kc.check_attn(lib, DEV, variant, kw, B=2, T=21), tol=5e-5)
+
+
+# ---- whole path against the outputs of the unmodified reference ---------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_through_c_abi(lib, name):
+    pc.assert_parity(pc.run_golden(lib, DEV, name))
+
+
+@pytest.mark.parametrize("intra,inter", [(abi.SB_ALGO_TILE, abi.SB_ALGO_TILE), (abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2),
+                                         (abi.SB_ALGO_LANE4, abi.SB_ALGO_LANE1)])
+def test_golden_with_forced_lstm_algos(lib, intra, inter):
+    pc.assert_parity(pc.run_golden(lib, DEV, "syn_offline", intra, inter))
+
+
+def _net_for(g):
+    from sound_bubble_b200 import Net, NetOptim
+    cls = Net if g.variant == "dis_embed" else NetOptim
+    m = cls(**g.kwargs)
+    m.load_state_dict(make_state_dict(orc.OracleConfig.from_kwargs(g.variant, **g.kwargs), g.meta["seed"]), strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["syn_offline", "rpi_offline", "wav_syn_1m", "opi_offline"])
+def test_golden_through_net_module(name):
+    """The drop-in module: reference-layout checkpoint in, dict in, dict out (DE3/net.py:84-93)."""
+    g = Golden(name)
+    m = _net_for(g)
+    r = m(g.inputs(DEV), pad=g.pad)
+    assert set(r) == {"output", "next_state"}
+    res = {"out": pc.compare(r["output"], g.output)}
+    got = flatten_state(r["next_state"])
+    res["state_maxabs"] = max(float((got[k] - v).abs().max()) for k, v in g.state.items())
+    if g.mixture2 is not None:
+        r2 = m({"mixture": g.mixture2.to(DEV), "dis_embed": g.dis_embed.to(DEV)}, r["next_state"], pad=False)
+        res["out2"] = pc.compare(r2["output"], g.output2)
+    pc.assert_parity(res)
+
+
+def test_streaming_session_equals_offline_and_reference():
+    """edge/causal_infer.py:28-86: chunk-by-chunk with carried state == one offline call (atol 1e-3 there)."""
+    g = Golden("syn_nopad")
+    m = _net_for(g)
+    cfg = m.cfg
+    x = g.mixture.to(DEV)
+    off = m(g.inputs(DEV), pad=False)["output"]
+    for use_graph in (False, True):
+        sess = m.streaming(x.shape[0], g.dis_embed.to(DEV), use_graph=use_graph)
+        outs = []
+        T = (x.shape[-1] - cfg.n_fft) // cfg.stft_chunk_size + 1
+        for t in range(T):
+            win = x[..., t * cfg.stft_chunk_size: t * cfg.stft_chunk_size + cfg.n_fft]
+            outs.append(sess.feed(win).clone())
+        y = torch.cat(outs, dim=-1)
+        assert float((y - off).abs().max()) <= 2e-5, use_graph
+        r = pc.compare(y, g.output)
+        assert r["rms"] <= pc.RMS_TIGHT and r["maxabs"] <= pc.MAXABS_TIGHT, r
+        got = flatten_state(sess.state)
+        assert max(float((got[k] - v).abs().max()) for k, v in g.state.items()) <= pc.MAXABS_TIGHT
+
+
+def test_medium_clip_against_oracle():
+    """1 s clips, batch 3, TFG_S config: ours vs the CPU oracle run here on the same seeded input."""
+    ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
+    sd = make_state_dict(ocfg, 0)
+    mix = synthetic_mixture(3, 6, 24000)
+    dis = radius_one_hot(3)
+    with torch.no_grad():
+        ref = orc.net_forward(sd, ocfg, {"mixture": mix, "dis_embed": dis})["output"]
+    from sound_bubble_b200 import Net
+    m = Net(**SYN)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    out = m({"mixture": mix.to(DEV), "dis_embed": dis.to(DEV)})["output"]
+    r = pc.compare(out, ref)
+    assert out.shape == ref.shape == (3, 1, 24000)
+    assert r["rms"] <= 1e-4 and r["rms"] <= pc.RMS_BAR and r["si_sdr_db"] >= 60.0, r
+
+
+def test_full_size_properties():
+    """BASELINE config 2 shape (batch 32, 5 s, 625 frames): size-independent properties instead of an oracle run:
+    prefix causality, batch-shard independence (the multi-GPU split), streaming == offline on a prefix."""
+    from sound_bubble_b200 import Net
+    ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
+    m = Net(**SYN)
+    m.load_state_dict(make_state_dict(ocfg, 0))
+    m = m.to(DEV).eval()
+    mix = synthetic_mixture(32, 6, 120000).to(DEV)
+    dis = radius_one_hot(32).to(DEV)
+    full = m({"mixture": mix, "dis_embed": dis})["output"]
+    assert full.shape == (32, 1, 120000) and bool(torch.isfinite(full).all())
+    # causality: the first 100 chunks do not depend on what follows (OPT/net.py:94-140 self-check)
+    n = 192 * 100
+    part = m({"mixture": mix[..., : n + 96].contiguous(), "dis_embed": dis}, pad=False)["output"]
+    assert float((part - full[..., :n]).abs().max()) <= 2e-5
+    # sharding: utterances are independent, so a rank's shard gives the same rows
+    shard = m({"mixture": mix[8:16].contiguous(), "dis_embed": dis[8:16].contiguous()})["output"]
+    assert float((shard - full[8:16]).abs().max()) <= 2e-5
+    # streaming protocol on the first 40 chunks
+    sess = m.streaming(32, dis)
+    outs = [sess.feed(mix[..., t * 192: t * 192 + 288]).clone() for t in range(40)]
+    assert float((torch.cat(outs, -1) - full[..., : 192 * 40]).abs().max()) <= 2e-5
+
+
+def test_launches_are_counted():
+    from sound_bubble_b200 import _lib
+    g = Golden("syn_plain")
+    m = _net_for(g)
+    before = _lib.launch_count()
+    m(g.inputs(DEV), pad=g.pad)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - before == 2 + 1 + 2 * 2 + 2      # stft, conv_in, film, 2 x (intra, inter), deconv, istft
