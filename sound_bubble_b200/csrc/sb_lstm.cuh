@@ -1,0 +1,27 @@
+// Argument block of the fused sequence (LSTM) kernels of sb_lstm.cu, shared with the conv-LSTM wrapper.
+#pragma once
+#include "sb_common.cuh"
+
+namespace sb {
+
+struct SeqArgs {
+    const float* x0;
+    const float* x1;            // optional second addend of the input (the two intra directions)
+    const float* film_scale;    // [n_rows / film_row_div][n_steps][C] or NULL
+    const float* film_shift;
+    float* out[2];              // per direction.  PROJ: same addressing as x.  RAW_H: [row][pos][H]
+    sb_lstm_dir w[2];
+    const float* h0;            // [n_rows][H] or NULL (zero state)
+    const float* c0;
+    float* hN;                  // [n_rows][H] or NULL
+    float* cN;
+    int n_rows, n_steps, n_dirs;
+    int rows_inner;             // row -> (row / rows_inner, row % rows_inner)
+    long long stride_outer, stride_inner, stride_pos;      // in floats
+    int film_row_div;
+};
+
+// raw_h = true: write h_t to out[dir] as [row][pos][H] instead of the projected, residual-added activation
+int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t st);
+
+}  // namespace sb

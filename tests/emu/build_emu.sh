@@ -9,7 +9,7 @@ OBJS=""
 for f in sb_host sb_lstm sb_frontend sb_backend sb_convlstm sb_attn sb_net; do
   s="$ROOT/sound_bubble_b200/csrc/$f.cu"
   o="$HERE/build/$f.o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$ROOT/sound_bubble_b200/csrc/sb_common.cuh" -nt "$o" ] || [ "$ROOT/include/soundbubble.h" -nt "$o" ] || [ "$HERE/cuda_emu.h" -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$ROOT/sound_bubble_b200/csrc/sb_common.cuh" -nt "$o" ] || [ "$ROOT/include/soundbubble.h" -nt "$o" ] || [ "$HERE/cuda_emu.h" -nt "$o" ] || [ "$ROOT/sound_bubble_b200/csrc/sb_lstm.cuh" -nt "$o" ]; then
     g++ -std=c++20 -O2 -fPIC -DSB_EMU -x c++ -I"$HERE" -I"$ROOT/include" -I"$ROOT/sound_bubble_b200/csrc" -Wno-unknown-pragmas -c "$s" -o "$o" &
   fi
   OBJS="$OBJS $o"
