@@ -46,6 +46,8 @@ extern "C" {
 #define SB_ALGO_LANE1 2         /* 1 sequence  per CTA, one gate column per thread, weights in registers        */
 #define SB_ALGO_LANE2 3         /* 2 sequences per CTA                                                           */
 #define SB_ALGO_LANE4 4         /* 4 sequences per CTA                                                           */
+#define SB_ALGO_WS    5         /* 1 sequence per CTA, warp-specialised: 8 recurrence warps (K split over 4 lanes, */
+                                /* packed FFMA2) + 8 helper warps (loads, LayerNorm, input gates, stores)          */
 
 /* feature modes of the front-end (DE3:486-507) */
 #define SB_FEAT_NONE        0   /* merge_method "None": conv-in sees [Re, Im] only                               */
@@ -74,6 +76,9 @@ typedef struct sb_lstm_dir {
     const float* b_tile;    /* [4H]       b_ih + b_hh in the same column order                                  */
     const float* w_lane;    /* [(C+H)/4][4H][4]  slot s = 4u+g holds row g*H+u of [W_ih | W_hh], 4 k per float4  */
     const float* b_lane;    /* [4H]       b_ih + b_hh, slot order 4u+g                                           */
+    const float* w_rec;     /* [16][4H] float4: thread t=(u=t/4,kq=t%4), k -> W_hh[g*H+u][16kq+k] for g = 0..3       */
+    const float* w_xp;      /* [C/4][4H] float4: same thread map, k -> W_ih[g*H+u][(C/4)kq+k] for g = 0..3           */
+    const float* w_prj;     /* [(16C/H)/4][4H] float4: thread t -> lin[c=u%C][16kq + (16C/H)(u/C) + j]               */
     const float* lin_t;     /* [H][C]     output projection, transposed (this direction's half for the BiLSTM)  */
     const float* lin_n;     /* [C][H]     output projection, natural                                             */
     const float* lin_b;     /* [C]        projection bias (added by direction 0 only)                            */
@@ -300,6 +305,9 @@ typedef struct sb_net_desc {
 typedef struct sb_net_io {
     const float* wave;                  /* [B][M][n_samples], n_samples = stride*T + (n_fft - stride)            */
     const float* dis_embed;             /* [B][3] or NULL                                                         */
+    const float* film;                  /* optional FiLM table [n_blocks-1][2][B][F][C] precomputed by              */
+                                        /* sb_film_params_fwd for these dis_embed rows (a streaming session computes */
+                                        /* it once); NULL = computed from dis_embed inside every call                */
     float*       wave_out;              /* [B][S][stride*T]                                                       */
     const float* conv_buf_in;   float* conv_buf_out;
     const float* deconv_buf_in; float* deconv_buf_out;

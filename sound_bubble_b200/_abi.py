@@ -8,7 +8,7 @@ SB_VERSION = 100
 SB_MAX_BLOCKS = 16
 SB_MAX_MICS = 8
 
-SB_ALGO_AUTO, SB_ALGO_TILE, SB_ALGO_LANE1, SB_ALGO_LANE2, SB_ALGO_LANE4 = 0, 1, 2, 3, 4
+SB_ALGO_AUTO, SB_ALGO_TILE, SB_ALGO_LANE1, SB_ALGO_LANE2, SB_ALGO_LANE4, SB_ALGO_WS = 0, 1, 2, 3, 4, 5
 SB_FEAT_NONE, SB_FEAT_OMNI, SB_FEAT_DIRECTIONAL = 0, 1, 2
 SB_EMB_CONV, SB_EMB_LINEAR = 0, 1
 SB_CONVLSTM_PADCROP, SB_CONVLSTM_OUTPAD = 0, 1
@@ -19,7 +19,7 @@ fp = C.c_void_p          # device float* (raw address)
 
 
 class LstmDir(C.Structure):
-    _fields_ = [(n, fp) for n in ("w_tile", "b_tile", "w_lane", "b_lane", "lin_t", "lin_n", "lin_b", "ln_g", "ln_b")]
+    _fields_ = [(n, fp) for n in ("w_tile", "b_tile", "w_lane", "b_lane", "w_rec", "w_xp", "w_prj", "lin_t", "lin_n", "lin_b", "ln_g", "ln_b")]
 
 
 class StftArgs(C.Structure):
@@ -102,7 +102,7 @@ class NetDesc(C.Structure):
 
 
 class NetIO(C.Structure):
-    _fields_ = [("wave", fp), ("dis_embed", fp), ("wave_out", fp),
+    _fields_ = [("wave", fp), ("dis_embed", fp), ("film", fp), ("wave_out", fp),
                 ("conv_buf_in", fp), ("conv_buf_out", fp),
                 ("deconv_buf_in", fp), ("deconv_buf_out", fp),
                 ("istft_buf_in", fp), ("istft_buf_out", fp),

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(1024) istft_ola_kernel(const sb_backend_args a
 #pragma unroll
         for (int i = 0; i < NF; ++i) acc[i] = 0.f;
         const float* bp = a.filt + tid;
-#pragma unroll 4
+#pragma unroll 16
         for (int k = 0; k < F2; ++k) {
             const float bv = __ldg(bp + (size_t)k * n_fft);
             const float4 s0 = ld4(sp + k * NFP), s1 = ld4(sp + k * NFP + 4);
@@ -149,8 +149,137 @@ __global__ void __launch_bounds__(1024) istft_ola_kernel(const sb_backend_args a
     }
 }
 
+// Streaming-sized calls (T <= kIstftTT frames): deconv, masking, iSTFT and overlap-add in ONE launch per utterance; the
+// output spectrum never leaves shared memory.  Same arithmetic and mappings as the two kernels above.
+template <int C, int NO>
+__global__ void __launch_bounds__(512) backend_small_kernel(const sb_backend_args a) {
+    constexpr int LPP = C / 4, NG = 512 / LPP, NS = NO / 2, NF = kIstftTT + 1, NFP = 12;
+    SB_DYN_SMEM(float, smem);
+    const int F = a.F, F2 = 2 * F, T = a.T, n_fft = a.n_fft, hop = a.stride;
+    float* w_s = smem;                          // [C][NO][9]
+    float* sp = w_s + C * NO * 9;               // [NS][F2][NFP]: slot 0 = carried frame, slot 1 + t = frame t
+    float* ola = sp + NS * F2 * NFP;            // [NF][n_fft]
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int cq = tid % LPP, grp = tid / LPP;
+    for (int i = tid; i < C * NO * 9; i += 512) w_s[i] = __ldg(a.w + i);
+    float bias[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) bias[o] = __ldg(a.bias + o);
+    pdl_trigger();
+    pdl_wait();
+    for (int i = tid; i < NS * F2; i += 512) {
+        float* row = sp + i * NFP;
+        row[0] = ldg1_stream(a.istft_buf_in + (size_t)b * NS * F2 + i);
+        for (int fr = T + 1; fr < NFP; ++fr) row[fr] = 0.f;
+    }
+    __syncthreads();
+    float w[NO][9][4];
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[o][k][j] = w_s[((4 * cq + j) * NO + o) * 9 + k];
+
+    const int n_pos = T * F;
+    const float* xb = a.x + (size_t)b * T * F * C;
+    const float* hist = a.deconv_buf_in + (size_t)b * C * 2 * F;
+    for (int base = 0; base < n_pos; base += NG) {
+        const int pos = base + grp;
+        const bool valid = pos < n_pos;
+        const int pp = valid ? pos : 0;
+        const int t = pp / F, f = pp - t * F;
+        float acc[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            const int ft = t - kt;
+#pragma unroll
+            for (int kf = 0; kf < 3; ++kf) {
+                const int ff = f + 1 - kf;
+                if (ff < 0 || ff >= F) continue;
+                float4 v;
+                if (ft >= 0) {
+                    v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)ft * F + ff) * C) + cq);
+                } else {
+                    const float* hp = hist + (size_t)(2 + ft) * F + ff;
+                    v.x = __ldg(hp + (size_t)(4 * cq + 0) * 2 * F); v.y = __ldg(hp + (size_t)(4 * cq + 1) * 2 * F);
+                    v.z = __ldg(hp + (size_t)(4 * cq + 2) * 2 * F); v.w = __ldg(hp + (size_t)(4 * cq + 3) * 2 * F);
+                }
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    acc[o] = fmaf(v.x, w[o][kt * 3 + kf][0], acc[o]); acc[o] = fmaf(v.y, w[o][kt * 3 + kf][1], acc[o]);
+                    acc[o] = fmaf(v.z, w[o][kt * 3 + kf][2], acc[o]); acc[o] = fmaf(v.w, w[o][kt * 3 + kf][3], acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = group_sum<LPP>(acc[o]) + bias[o];
+        if (valid && cq == 0) {
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                const int in_frame = (o & 1) * F + f;
+                float v = acc[o];
+                if (a.mask_spec) v *= __ldg(a.mask_spec + ((size_t)(b * T + t) * NS + (o >> 1)) * F2 + in_frame);
+                sp[((o >> 1) * F2 + in_frame) * NFP + 1 + t] = v;
+                if (t == T - 1) a.istft_buf_out[((size_t)b * NS + (o >> 1)) * F2 + in_frame] = v;
+            }
+        }
+    }
+    {                                           // new deconv_buf = last two frames of [history ; x], layout [C][2][F]
+        float* dst = a.deconv_buf_out + (size_t)b * C * 2 * F;
+        for (int i = tid; i < C * 2 * F; i += 512) {
+            const int c = i / (2 * F), r = i - c * 2 * F;
+            const int j = r / F, f = r - j * F;
+            const int ft = T - 2 + j;
+            dst[i] = (ft >= 0) ? __ldg(xb + ((size_t)ft * F + f) * C + c) : __ldg(hist + (size_t)c * 2 * F + (size_t)(2 + ft) * F + f);
+        }
+    }
+    __syncthreads();
+    const int look = n_fft - hop;
+    for (int s = 0; s < NS; ++s) {
+        if (tid < n_fft) {
+            float acc[NF];
+#pragma unroll
+            for (int i = 0; i < NF; ++i) acc[i] = 0.f;
+            const float* bp = a.filt + tid;
+            const float* sps = sp + s * F2 * NFP;
+#pragma unroll 16
+            for (int k = 0; k < F2; ++k) {
+                const float bv = __ldg(bp + (size_t)k * n_fft);
+                const float4 s0 = ld4(sps + k * NFP), s1 = ld4(sps + k * NFP + 4);
+                const float s8 = sps[k * NFP + 8];
+                acc[0] = fmaf(s0.x, bv, acc[0]); acc[1] = fmaf(s0.y, bv, acc[1]);
+                acc[2] = fmaf(s0.z, bv, acc[2]); acc[3] = fmaf(s0.w, bv, acc[3]);
+                acc[4] = fmaf(s1.x, bv, acc[4]); acc[5] = fmaf(s1.y, bv, acc[5]);
+                acc[6] = fmaf(s1.z, bv, acc[6]); acc[7] = fmaf(s1.w, bv, acc[7]);
+                acc[8] = fmaf(s8, bv, acc[8]);
+            }
+#pragma unroll
+            for (int i = 0; i < NF; ++i) ola[i * n_fft + tid] = acc[i];
+        }
+        __syncthreads();
+        float* dst = a.wave_out + ((size_t)b * NS + s) * T * hop;
+        for (int i = tid; i < T * hop; i += 512) {
+            const int fr = i / hop, r = i - fr * hop;
+            float v = ola[(fr + 1) * n_fft + r];
+            if (r < look) v += ola[fr * n_fft + hop + r];
+            dst[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
 template <int C>
 static int launch_backend(const sb_backend_args& a, cudaStream_t st) {
+    if (a.T <= kIstftTT && a.n_fft <= 512) {           // streaming-sized call: one fused launch
+        const size_t smem = ((size_t)C * 2 * a.n_src * 9 + (size_t)a.n_src * 2 * a.F * 12 + (size_t)(kIstftTT + 1) * a.n_fft) * sizeof(float);
+        if (a.n_src == 1) return launch("backend_small", backend_small_kernel<C, 2>, dim3(a.B), dim3(512), smem, st, a);
+        if (a.n_src == 2) return launch("backend_small", backend_small_kernel<C, 4>, dim3(a.B), dim3(512), smem, st, a);
+        set_error("sb_backend_fwd: n_src must be 1 or 2 (got %d)", a.n_src);
+        return SB_E_UNSUPP;
+    }
     const int LPP = C / 4, PPB = 256 / LPP;
     const int n_pos = a.T * a.F;
     int gx = ceil_div(n_pos, PPB);

@@ -104,10 +104,43 @@ __device__ __forceinline__ void pdl_trigger() {
 #endif
 }
 
-// sigmoid / tanh through ex2.approx + rcp: |abs err| ~ 1e-7, far inside the 1e-3 RMS waveform parity bar and
-// 5x fewer instructions than the libm versions.  tanh.approx (2^-11 rel err) is NOT accurate enough here.
-__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+// sigmoid / tanh through one ex2.approx + one rcp.approx (2 MUFU ops, no slow paths): |abs err| ~ 1e-7, far inside the
+// 1e-3 RMS waveform parity bar.  tanh.approx (2^-11 rel err) is NOT accurate enough here.
+__device__ __forceinline__ float fast_ex2(float x) {
+#ifdef SB_EMU
+    return exp2f(x);
+#else
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef SB_EMU
+    return 1.0f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_f(float x) { return fmaf(2.0f, sigmoid_f(2.0f * x), -1.0f); }
+
+// packed fp32x2 FMA (Blackwell FFMA2): d.{x,y} += a.{x,y} * b.  Same rounding as two fmaf, half the issue slots.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float b) {
+#ifdef SB_EMU
+    d.x = fmaf(a.x, b, d.x);
+    d.y = fmaf(a.y, b, d.y);
+#else
+    unsigned long long dd, aa, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b), "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+#endif
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
@@ -137,6 +170,22 @@ __device__ __forceinline__ float ldg1_stream(const float* p) {
 }
 // plain (coherent) loads for buffers an aliasing output of the same launch may point at
 __device__ __forceinline__ float ld_plain(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
+
+// Cooperative global -> shared copy of n4 float4 with 8 independent 16-byte loads in flight per thread (a plain
+// load/store loop leaves one L2 round trip per iteration on the critical path of every prologue).
+__device__ __forceinline__ void stage_f4(float* dst, const float* src, int n4, int tid, int nthreads) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    int i = tid;
+    for (; i + 7 * nthreads < n4; i += 8 * nthreads) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(s4 + i + j * nthreads);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d4[i + j * nthreads] = v[j];
+    }
+    for (; i < n4; i += nthreads) d4[i] = __ldg(s4 + i);
+}
 
 template <int WIDTH>
 __device__ __forceinline__ float group_sum(float v) {

@@ -35,16 +35,31 @@ __global__ void __launch_bounds__(128, 2) stft_features_kernel(const sb_stft_arg
     const int nvalid = min(kStftTT, a.T - t0);
     const int nf = min(kStftFC, F - f0);
 
-    // basis chunk (constant data)
-    for (int i = tid; i < 2 * kStftFC * (n_fft / 4); i += 128) {
-        const int row = i / (n_fft / 4), k4 = i - row * (n_fft / 4);
-        const int ff = row & (kStftFC - 1);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ff < nf) {
-            const int grow = (row < kStftFC) ? f0 + ff : F + f0 + ff;
-            v = __ldg(reinterpret_cast<const float4*>(a.filt + (size_t)grow * n_fft) + k4);
+    // basis chunk (constant data), 4 independent 16-byte loads in flight per thread
+    {
+        const int q = n_fft / 4, total = 2 * kStftFC * q;
+        for (int i0 = tid; i0 < total; i0 += 4 * 128) {
+            float4 v[4];
+            int dsti[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * 128;
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                dsti[j] = -1;
+                if (i < total) {
+                    const int row = i / q, k4 = i - row * q;
+                    const int ff = row & (kStftFC - 1);
+                    dsti[j] = row * BS + 4 * k4;
+                    if (ff < nf) {
+                        const int grow = (row < kStftFC) ? f0 + ff : F + f0 + ff;
+                        v[j] = __ldg(reinterpret_cast<const float4*>(a.filt + (size_t)grow * n_fft) + k4);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (dsti[j] >= 0) st4(bs + dsti[j], v[j]);
         }
-        st4(bs + row * BS + 4 * k4, v);
     }
     pdl_trigger();
     pdl_wait();
@@ -58,6 +73,12 @@ __global__ void __launch_bounds__(128, 2) stft_features_kernel(const sb_stft_arg
     }
     __syncthreads();
 
+    // streaming-sized tiles (one frame pair): the four warps split the window instead of idling, partial sums meet in
+    // shared memory.  Otherwise warp w owns frame pair w.
+    const bool ksplit = nvalid <= 2 && (n_fft % 16) == 0;
+    const int fpair = ksplit ? 0 : warp;
+    const int kbeg = ksplit ? warp * (n_fft / 4) : 0;
+    const int kend = ksplit ? kbeg + n_fft / 4 : n_fft;
     float re[2][M], im[2][M];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
@@ -65,9 +86,9 @@ __global__ void __launch_bounds__(128, 2) stft_features_kernel(const sb_stft_arg
         for (int m = 0; m < M; ++m) { re[j][m] = 0.f; im[j][m] = 0.f; }
     const float* br = bs + lane * BS;
     const float* bi = bs + (kStftFC + lane) * BS;
-    const float* wa = ws + (2 * warp) * stride;
+    const float* wa = ws + (2 * fpair) * stride;
     const float* wb = wa + stride;
-    for (int k = 0; k < n_fft; k += 4) {
+    for (int k = kbeg; k < kend; k += 4) {
         const float4 r4 = ld4(br + k), i4 = ld4(bi + k);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -84,11 +105,38 @@ __global__ void __launch_bounds__(128, 2) stft_features_kernel(const sb_stft_arg
         }
     }
     __syncthreads();                    // everyone is done with the basis tile; reuse it as the staging buffer
+    if (ksplit) {
+        float* red = bs + kStftTT * kStftFC * Cin;          // [4 warps][4M][32], behind the feature staging area
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                red[((warp * 4 * M) + (2 * j) * M + m) * 32 + lane] = re[j][m];
+                red[((warp * 4 * M) + (2 * j + 1) * M + m) * 32 + lane] = im[j][m];
+            }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    float sr = 0.f, si = 0.f;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) {
+                        sr += red[((w4 * 4 * M) + (2 * j) * M + m) * 32 + lane];
+                        si += red[((w4 * 4 * M) + (2 * j + 1) * M + m) * 32 + lane];
+                    }
+                    re[j][m] = sr; im[j][m] = si;
+                }
+        }
+    }
+    const bool writer = !ksplit || warp == 0;
 
     const float eps = 1e-6f;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const int tt = 2 * warp + j;
+        if (!writer) continue;
+        const int tt = 2 * fpair + j;
         float* o = fs + (tt * kStftFC + lane) * Cin;
 #pragma unroll
         for (int m = 0; m < M; ++m) { o[m] = re[j][m]; o[M + m] = im[j][m]; }
@@ -144,52 +192,51 @@ static int launch_stft(const sb_stft_args& a, cudaStream_t st) {
 // follow.  One thread computes 8 output channels of one (t, f): per input value 1 LDS + 2 broadcast LDS.128 + 8 FMA.
 // The C/8 threads of a (t, f) are adjacent lanes, so LayerNorm(C) is two quad shuffles and the store is coalesced.
 template <int C>
-__global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a, const int TT) {
+__global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a, const int TT, const int FC) {
     constexpr int NOG = C / 8;
     SB_DYN_SMEM(float, smem);
-    const int F = a.F, Cin = a.Cin, FP = F + 2;
+    const int F = a.F, Cin = a.Cin, FP = FC + 2;
     float* w_s = smem;                                          // [3][Cin][3][C]
-    float* in_s = w_s + 9 * Cin * C;                            // [TT+2][Cin][FP]
+    float* in_s = w_s + 9 * Cin * C;                            // [TT+2][Cin][FP]; column j <-> bin f0 - 1 + j
     const int tid = threadIdx.x;
-    const int t0 = blockIdx.x * TT, b = blockIdx.y;
+    const int t0 = blockIdx.x * TT, b = blockIdx.y, f0 = blockIdx.z * FC;
     const int nvalid = min(TT, a.T - t0);
+    const int nf = min(FC, F - f0);
 
-    for (int i = tid; i < 9 * Cin * C / 4; i += blockDim.x)
-        st4(w_s + 4 * i, __ldg(reinterpret_cast<const float4*>(a.w_pack) + i));
+    stage_f4(w_s, a.w_pack, 9 * Cin * C / 4, tid, blockDim.x);
     pdl_trigger();
     pdl_wait();
 
     const int nfr = nvalid + 2;
-    for (int i = tid; i < nfr * Cin * 2; i += blockDim.x) {     // zero the two padding columns
-        const int fc = i >> 1;
-        in_s[fc * FP + ((i & 1) ? F + 1 : 0)] = 0.0f;
-    }
+    const int ncol = nf + 2;
     for (int fr = 0; fr < nfr; ++fr) {
         const int ft = t0 - 2 + fr;
         float* dst = in_s + fr * Cin * FP;
         if (ft >= 0) {
             const float* src = a.feats + (size_t)(b * a.T + ft) * F * Cin;
-            for (int i = tid; i < F * Cin; i += blockDim.x) {
-                const int f = i / Cin, c = i - f * Cin;
-                dst[c * FP + 1 + f] = ldg1_stream(src + i);
+            for (int i = tid; i < ncol * Cin; i += blockDim.x) {
+                const int j = i / Cin, c = i - j * Cin;
+                const int f = f0 - 1 + j;
+                dst[c * FP + j] = (f >= 0 && f < F) ? ldg1_stream(src + (size_t)f * Cin + c) : 0.0f;
             }
         } else {
             const float* src = a.conv_buf_in + (size_t)b * Cin * 2 * F + (size_t)(2 + ft) * F;
-            for (int i = tid; i < F * Cin; i += blockDim.x) {
-                const int c = i / F, f = i - c * F;
-                dst[c * FP + 1 + f] = ldg1_stream(src + (size_t)c * 2 * F + f);
+            for (int i = tid; i < ncol * Cin; i += blockDim.x) {
+                const int c = i / ncol, j = i - c * ncol;
+                const int f = f0 - 1 + j;
+                dst[c * FP + j] = (f >= 0 && f < F) ? ldg1_stream(src + (size_t)c * 2 * F + f) : 0.0f;
             }
         }
     }
     __syncthreads();
 
-    const int n_items = nvalid * F * NOG;
+    const int n_items = nvalid * nf * NOG;
     for (int base = 0; base < n_items; base += blockDim.x) {
         const int item = base + tid;
         const bool valid = item < n_items;
         const int it = valid ? item : 0;
         const int og = it % NOG, pf = it / NOG;
-        const int tt = pf / F, f = pf - tt * F;
+        const int tt = pf / nf, fl = pf - tt * nf;
         float acc[8];
         {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias) + 2 * og);
@@ -198,7 +245,7 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
             acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
         }
         for (int kt = 0; kt < 3; ++kt) {
-            const float* ip = in_s + (tt + kt) * Cin * FP + f;
+            const float* ip = in_s + (tt + kt) * Cin * FP + fl;
             const float* wp = w_s + (kt * Cin * 3) * C + og * 8;
             for (int c = 0; c < Cin; ++c) {
 #pragma unroll
@@ -227,7 +274,7 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
                 acc[j] = fmaf(acc[j] * rstd, __ldg(a.ln_g + og * 8 + j), __ldg(a.ln_b + og * 8 + j));
         }
         if (valid) {
-            float* dst = a.x + ((size_t)(b * a.T + t0 + tt) * F + f) * C + og * 8;
+            float* dst = a.x + ((size_t)(b * a.T + t0 + tt) * F + f0 + fl) * C + og * 8;
             st4(dst, make_float4(acc[0], acc[1], acc[2], acc[3]));
             st4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
         }
@@ -235,10 +282,10 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
 
     if (t0 + nvalid == a.T) {           // this CTA holds the last two frames of [history ; feats]: new conv_buf
         float* dst = a.conv_buf_out + (size_t)b * Cin * 2 * F;
-        for (int i = tid; i < Cin * 2 * F; i += blockDim.x) {
-            const int c = i / (2 * F), r = i - c * 2 * F;
-            const int j = r / F, f = r - j * F;
-            dst[i] = in_s[((nvalid + j) * Cin + c) * FP + 1 + f];
+        for (int i = tid; i < Cin * 2 * nf; i += blockDim.x) {
+            const int c = i / (2 * nf), r = i - c * 2 * nf;
+            const int j = r / nf, fl = r - j * nf;
+            dst[(size_t)c * 2 * F + (size_t)j * F + f0 + fl] = in_s[((nvalid + j) * Cin + c) * FP + 1 + fl];
         }
     }
 }
@@ -246,8 +293,9 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
 // =============================================================================================================
 // distance embedding + FiLM parameters
 // =============================================================================================================
-// One CTA per utterance: e = dis @ W^T (F*Din values), LayerNorm (per Din group, or over the whole vector for the
-// Linear variants), then scale/shift = 1x1 convs of every FiLM layer.  film[(j*2 + k)*B*F*C + (b*F + f)*C + c].
+// One CTA per (utterance, FiLM layer): e = dis @ W^T (F*Din values, recomputed per layer: it is tiny), LayerNorm (per
+// Din group, or over the whole vector for the Linear variants), then scale/shift = the layer's two 1x1 convs.
+// film[(j*2 + k)*B*F*C + (b*F + f)*C + c].
 __global__ void __launch_bounds__(256) film_params_kernel(const sb_film_args a) {
     SB_DYN_SMEM(float, e);              // [F*Din] (+ 64 floats of reduction scratch)
     __shared__ float red[64];
@@ -292,9 +340,10 @@ __global__ void __launch_bounds__(256) film_params_kernel(const sb_film_args a) 
     }
     __syncthreads();
     const int per = F * C;
-    for (int i = tid; i < a.n_layers * 2 * per; i += 256) {
-        const int jk = i / per, r = i - jk * per;
-        const int j = jk >> 1, k = jk & 1;
+    const int j = blockIdx.y;
+    for (int i = tid; i < 2 * per; i += 256) {
+        const int k = i / per, r = i - k * per;
+        const int jk = 2 * j + k;
         const int f = r / C, c = r - f * C;
         const float* ww = (k ? a.b_w : a.w_w) + ((size_t)j * C + c) * Din;
         float v = __ldg((k ? a.b_b : a.w_b) + j * C + c);
@@ -315,7 +364,8 @@ extern "C" int sb_stft_features_fwd(const sb_stft_args* p, void* stream) {
     SB_REQUIRE(p->M <= SB_MAX_MICS, SB_E_UNSUPP, "sb_stft_features_fwd: at most %d microphones (got %d)", SB_MAX_MICS, p->M);
     SB_REQUIRE(p->n_fft % 4 == 0 && p->stride % 4 == 0, SB_E_UNSUPP,
                "sb_stft_features_fwd: n_fft and stride must be multiples of 4 (got %d, %d)", p->n_fft, p->stride);
-    SB_REQUIRE(kStftTT * p->Cin <= 2 * (p->n_fft + 4), SB_E_UNSUPP, "sb_stft_features_fwd: n_fft=%d too small for Cin=%d", p->n_fft, p->Cin);
+    SB_REQUIRE(kStftTT * kStftFC * p->Cin + 16 * p->M * 32 <= 2 * kStftFC * (p->n_fft + 4), SB_E_UNSUPP,
+               "sb_stft_features_fwd: n_fft=%d too small for Cin=%d", p->n_fft, p->Cin);
     SB_REQUIRE(p->F == p->n_fft / 2 + 1, SB_E_BADARG, "sb_stft_features_fwd: F must be n_fft/2+1");
     SB_REQUIRE((long long)(p->T - 1) * p->stride + p->n_fft <= p->n_samples, SB_E_BADARG, "sb_stft_features_fwd: T frames do not fit n_samples");
     int feat = 0;
@@ -346,13 +396,17 @@ extern "C" int sb_conv_in_fwd(const sb_conv_in_args* p, void* stream) {
     SB_REQUIRE(p->C == 16 || p->C == 32, SB_E_UNSUPP, "sb_conv_in_fwd: C must be 16 or 32 (got %d)", p->C);
     SB_REQUIRE((p->ln_g == nullptr) == (p->ln_b == nullptr), SB_E_BADARG, "sb_conv_in_fwd: ln_g/ln_b must come together");
     SB_REQUIRE(p->conv_buf_in != p->conv_buf_out, SB_E_BADARG, "sb_conv_in_fwd: conv_buf_in and conv_buf_out must not alias");
+    // offline: 4 frames x all bins per CTA; streaming-sized calls: 1 frame x 16 bins per CTA so the few frames still
+    // spread over the whole chip (B * T * ceil(F/16) CTAs)
     const int TT = p->T >= 4 ? 4 : 1;
-    const size_t smem = ((size_t)9 * p->Cin * p->C + (size_t)(TT + 2) * p->Cin * (p->F + 2)) * sizeof(float);
+    const int FC = p->T >= 4 ? p->F : 16;
+    const int threads = p->T >= 4 ? 640 : 128;
+    const size_t smem = ((size_t)9 * p->Cin * p->C + (size_t)(TT + 2) * p->Cin * (FC + 2)) * sizeof(float);
     SB_REQUIRE(smem <= 227 * 1024, SB_E_SMEM, "sb_conv_in_fwd: Cin=%d F=%d needs %zu bytes of shared memory", p->Cin, p->F, smem);
-    dim3 grid(ceil_div(p->T, TT), p->B);
+    dim3 grid(ceil_div(p->T, TT), p->B, ceil_div(p->F, FC));
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->C == 32) return launch("conv_in", conv_in_kernel<32>, grid, dim3(640), smem, st, *p, TT);
-    return launch("conv_in", conv_in_kernel<16>, grid, dim3(640), smem, st, *p, TT);
+    if (p->C == 32) return launch("conv_in", conv_in_kernel<32>, grid, dim3(threads), smem, st, *p, TT, FC);
+    return launch("conv_in", conv_in_kernel<16>, grid, dim3(threads), smem, st, *p, TT, FC);
 }
 
 extern "C" int sb_film_params_fwd(const sb_film_args* p, void* stream) {
@@ -362,5 +416,5 @@ extern "C" int sb_film_params_fwd(const sb_film_args* p, void* stream) {
     SB_REQUIRE(p->B > 0 && p->F > 0 && p->C > 0 && p->Din > 0 && p->n_layers > 0, SB_E_BADARG, "sb_film_params_fwd: bad sizes");
     SB_REQUIRE(p->emb_mode == SB_EMB_CONV || p->emb_mode == SB_EMB_LINEAR, SB_E_BADARG, "sb_film_params_fwd: bad emb_mode");
     const size_t smem = (size_t)p->F * p->Din * sizeof(float);
-    return launch("film_params", film_params_kernel, dim3(p->B), dim3(256), smem, (cudaStream_t)stream, *p);
+    return launch("film_params", film_params_kernel, dim3(p->B, p->n_layers), dim3(256), smem, (cudaStream_t)stream, *p);
 }

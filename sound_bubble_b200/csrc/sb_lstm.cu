@@ -55,16 +55,9 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
     const sb_lstm_dir& w = a.w[dir];
     const int S = a.n_steps;
 
-    {   // stage the weights once per CTA (constant data: allowed before pdl_wait)
-        const float4* src = reinterpret_cast<const float4*>(w.w_tile);
-        float4* dst = reinterpret_cast<float4*>(Wt);
-        for (int i = tid; i < K * 64; i += blockDim.x) dst[i] = __ldg(src + i);
-        if (!RAW_H) {
-            const float4* s2 = reinterpret_cast<const float4*>(w.lin_t);
-            float4* d2 = reinterpret_cast<float4*>(WlT);
-            for (int i = tid; i < H * C / 4; i += blockDim.x) d2[i] = __ldg(s2 + i);
-        }
-    }
+    // stage the weights once per CTA (constant data: allowed before pdl_wait)
+    stage_f4(Wt, w.w_tile, K * 64, tid, blockDim.x);
+    if (!RAW_H) stage_f4(WlT, w.lin_t, H * C / 4, tid, blockDim.x);
     float bias[8];
     {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(w.b_tile) + lane);
@@ -494,22 +487,263 @@ __global__ void __launch_bounds__(256, 1) lstm_lane_kernel(const SeqArgs a) {
 }
 
 // =============================================================================================================
+// warp-specialised single-sequence kernel (streaming latency path)
+// =============================================================================================================
+// One sequence (and direction) per CTA, 512 threads.  Warps 0-7 run ONLY the recurrence: thread (u, kq) owns all four
+// gates of hidden unit u over a quarter of the hidden state (k = 16kq .. 16kq+15, 64 weights in registers), so a step
+// moves 4 LDS.128 per thread instead of 16 (shared-memory -> register bandwidth, not FMA issue, bounds this kernel),
+// 32 packed FFMA2, a 2-level shuffle all-reduce over the four kq lanes, then every lane of the quad evaluates the
+// cell itself (no gate exchange).  The projection of step s-1 reuses the h slice already in registers.
+// Warps 8-15 are helpers off the critical path: global loads + FiLM + LayerNorm per block of SB steps, the input part
+// of the gates (x W_ih^T + b) one step ahead, and the residual / bias / store of finished blocks.
+// One __syncthreads per step joins the two groups.
+template <int C>
+struct WsCfg {
+    static constexpr int H = 64, LPP = C / 4, SB = 256 / LPP, XK = C / 4, HS = 20;
+    static constexpr int NSUB = H / C, NPJ = 16 / NSUB;
+    static constexpr int xn_off = 0, res_off = 2 * SB * C, outp_off = 4 * SB * C;
+    static constexpr int gx_off = outp_off + 2 * NSUB * SB * C, hb_off = gx_off + 512;
+    static constexpr int smem_floats = hb_off + 2 * 4 * HS;
+    static_assert(SB >= 8 && NPJ % 4 == 0 && XK % 4 == 0, "block / slice sizes");
+};
+
+template <int C, bool RAW_H>
+__global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
+    using Cfg = WsCfg<C>;
+    constexpr int H = Cfg::H, LPP = Cfg::LPP, SB = Cfg::SB, XK = Cfg::XK, HS = Cfg::HS, NSUB = Cfg::NSUB, NPJ = Cfg::NPJ;
+    SB_DYN_SMEM(float, smem);
+    float* xn = smem + Cfg::xn_off;         // [2][SB][C]        LayerNorm(x') of the current / next block
+    float* res = smem + Cfg::res_off;       // [2][SB][C]        x' (residual)
+    float* outp = smem + Cfg::outp_off;     // [2][NSUB][SB][C]  partial projections
+    float* gx = smem + Cfg::gx_off;         // [2][256]          x W_ih^T + b of step s (slot 4u+g)
+    float* hb = smem + Cfg::hb_off;         // [2][4][HS]        h_{s-1}: four 16-float slices, padded to 20
+
+    const int tid = threadIdx.x;
+    const int dir = blockIdx.y;
+    const sb_lstm_dir& w = a.w[dir];
+    const int S = a.n_steps;
+    const int row = blockIdx.x;
+    const int nblk = (S + SB - 1) / SB;
+    const bool recur = tid < 256;                        // warp-uniform role
+    const int t8 = tid & 255;
+    const int u = t8 >> 2, kq = t8 & 3;
+
+    if (recur) {
+        // ---------------------------------------------------------------------------------------- recurrence warps
+        float4 wr[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w.w_rec) + k * 256 + t8);
+        float wp[NPJ];
+        if (!RAW_H) {
+#pragma unroll
+            for (int j4 = 0; j4 < NPJ / 4; ++j4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(w.w_prj) + j4 * 256 + t8);
+                wp[4 * j4] = v.x; wp[4 * j4 + 1] = v.y; wp[4 * j4 + 2] = v.z; wp[4 * j4 + 3] = v.w;
+            }
+        }
+        const int pc = u % C, sub = u / C;               // projection role: output channel, k-part (warp-uniform)
+        pdl_trigger();
+        pdl_wait();
+        const bool has0 = a.h0 != nullptr;
+        float c = has0 ? ld_plain(a.c0 + (long long)row * H + u) : 0.0f;
+        float hlast = has0 ? ld_plain(a.h0 + (long long)row * H + u) : 0.0f;
+        if (kq == 0) hb[(u >> 4) * HS + (u & 15)] = hlast;
+        float* const outr = a.out[dir];
+        __syncthreads();                                  // (P) pairs with the helpers' prologue barrier
+
+        for (int s = 0; s <= S; ++s) {
+            __syncthreads();
+            const float* hs = hb + (s & 1) * 4 * HS + kq * HS;
+            float hr[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = ld4(hs + 4 * i);
+                hr[4 * i] = v.x; hr[4 * i + 1] = v.y; hr[4 * i + 2] = v.z; hr[4 * i + 3] = v.w;
+            }
+            if (s < S) {
+                const float4 g4 = ld4(gx + (s & 1) * 256 + 4 * u);
+                float2 a01[2], a23[2];
+                a01[0] = make_float2(0.f, 0.f); a01[1] = a01[0]; a23[0] = a01[0]; a23[1] = a01[0];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    ffma2(a01[k & 1], make_float2(wr[k].x, wr[k].y), hr[k]);
+                    ffma2(a23[k & 1], make_float2(wr[k].z, wr[k].w), hr[k]);
+                }
+                float p0 = a01[0].x + a01[1].x, p1 = a01[0].y + a01[1].y;
+                float p2 = a23[0].x + a23[1].x, p3 = a23[0].y + a23[1].y;
+                p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+                p2 += __shfl_xor_sync(0xffffffffu, p2, 1); p3 += __shfl_xor_sync(0xffffffffu, p3, 1);
+                p0 += __shfl_xor_sync(0xffffffffu, p0, 2); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+                p2 += __shfl_xor_sync(0xffffffffu, p2, 2); p3 += __shfl_xor_sync(0xffffffffu, p3, 2);
+                const float ig = sigmoid_f(p0 + g4.x);
+                const float fg = sigmoid_f(p1 + g4.y);
+                const float gg = tanh_f(p2 + g4.z);
+                const float og = sigmoid_f(p3 + g4.w);
+                c = fmaf(fg, c, ig * gg);
+                hlast = og * tanh_f(c);
+                if (kq == 0) {
+                    hb[((s + 1) & 1) * 4 * HS + (u >> 4) * HS + (u & 15)] = hlast;
+                    if (RAW_H) {
+                        const int pos = dir ? S - 1 - s : s;
+                        outr[((long long)row * S + pos) * H + u] = hlast;
+                    }
+                }
+            }
+            if (!RAW_H && s > 0) {                       // projection of step s-1 from the slice already in registers
+                float pp = 0.f;
+#pragma unroll
+                for (int q = 0; q < NSUB; ++q) {
+                    if (sub == q) {
+#pragma unroll
+                        for (int j = 0; j < NPJ; ++j) pp = fmaf(wp[j], hr[NPJ * q + j], pp);
+                    }
+                }
+                pp += __shfl_xor_sync(0xffffffffu, pp, 1);
+                pp += __shfl_xor_sync(0xffffffffu, pp, 2);
+                if (kq == 0) {
+                    const int sp = s - 1, bp = sp / SB;
+                    outp[(((bp & 1) * NSUB + sub) * SB + (sp - bp * SB)) * C + pc] = pp;
+                }
+            }
+        }
+        __syncthreads();                                  // pairs with the helpers' closing barrier
+        if (kq == 0 && a.hN) {
+            a.hN[(long long)row * H + u] = hlast;
+            a.cN[(long long)row * H + u] = c;
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------------------------------------- helper warps
+    float4 wx[XK];
+#pragma unroll
+    for (int k = 0; k < XK; ++k) wx[k] = __ldg(reinterpret_cast<const float4*>(w.w_xp) + k * 256 + t8);
+    const float gbias = __ldg(w.b_lane + t8);             // slot 4u+g with g = kq after the reduce-scatter
+    const int pq = t8 / LPP, c4 = t8 % LPP;               // load / LayerNorm / store role: step pq of a block, channels 4c4..
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(w.ln_g) + c4);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.ln_b) + c4);
+    float4 blin4 = make_float4(0, 0, 0, 0);
+    if (!RAW_H && dir == 0) blin4 = __ldg(reinterpret_cast<const float4*>(w.lin_b) + c4);
+    const long long p_base = row_base(a, row) + 4 * c4;
+    const long long p_fbase = (long long)(row / a.film_row_div) * S * C + 4 * c4;
+    float* const outp_g = a.out[dir];
+    pdl_trigger();
+    pdl_wait();
+
+    auto prefetch = [&](int blk) -> float4 {
+        const int s = blk * SB + pq;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (s < S) {
+            const int pos = dir ? S - 1 - s : s;
+            const long long off = p_base + (long long)pos * a.stride_pos;
+            v = ldg4_stream(a.x0 + off);
+            if (a.x1) {
+                const float4 t = ldg4_stream(a.x1 + off);
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            if (a.film_scale) {
+                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + p_fbase + (long long)pos * C));
+                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + p_fbase + (long long)pos * C));
+                v.x = fmaf(v.x, fs.x, fb.x); v.y = fmaf(v.y, fs.y, fb.y);
+                v.z = fmaf(v.z, fs.z, fb.z); v.w = fmaf(v.w, fs.w, fb.w);
+            }
+        }
+        return v;
+    };
+    auto phase_a = [&](int blk, const float4 v) {         // LayerNorm(C) of one step by LPP adjacent lanes
+        const float mean = group_sum<LPP>((v.x + v.y) + (v.z + v.w)) * (1.0f / C);
+        const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+        const float var = group_sum<LPP>((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / C);
+        const float rstd = rsqrtf(var + kLnEps);
+        st4(xn + ((blk & 1) * SB + pq) * C + 4 * c4, make_float4(fmaf(dx * rstd, g4.x, b4.x), fmaf(dy * rstd, g4.y, b4.y),
+                                                                  fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w)));
+        if (!RAW_H) st4(res + ((blk & 1) * SB + pq) * C + 4 * c4, v);
+    };
+    auto phase_c = [&](int blk) {                         // finished block: partial projections + bias + residual -> global
+        if (RAW_H) return;
+        const int s = blk * SB + pq;
+        if (s < S) {
+            float4 v = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q < NSUB; ++q) {
+                const float4 t = ld4(outp + (((blk & 1) * NSUB + q) * SB + pq) * C + 4 * c4);
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            if (dir == 0) {
+                const float4 r = ld4(res + ((blk & 1) * SB + pq) * C + 4 * c4);
+                v.x += blin4.x + r.x; v.y += blin4.y + r.y; v.z += blin4.z + r.z; v.w += blin4.w + r.w;
+            }
+            const int pos = dir ? S - 1 - s : s;
+            st4(outp_g + p_base + (long long)pos * a.stride_pos, v);
+        }
+    };
+    auto x_part = [&](int s) {                            // gx[s] = LN(x_s) W_ih^T + b, K split over the 4 kq lanes
+        const int blk = s / SB;
+        const float* xr = xn + ((blk & 1) * SB + (s - blk * SB)) * C + XK * kq;
+        float xv[XK];
+#pragma unroll
+        for (int i = 0; i < XK / 4; ++i) {
+            const float4 v = ld4(xr + 4 * i);
+            xv[4 * i] = v.x; xv[4 * i + 1] = v.y; xv[4 * i + 2] = v.z; xv[4 * i + 3] = v.w;
+        }
+        float2 a01 = make_float2(0.f, 0.f), a23 = a01;
+#pragma unroll
+        for (int k = 0; k < XK; ++k) {
+            ffma2(a01, make_float2(wx[k].x, wx[k].y), xv[k]);
+            ffma2(a23, make_float2(wx[k].z, wx[k].w), xv[k]);
+        }
+        // reduce-scatter over the 4 kq lanes: lane kq ends with the total of gate kq
+        const bool hi = (kq & 2) != 0;
+        float k0 = hi ? a23.x : a01.x, k1 = hi ? a23.y : a01.y;         // the pair this lane's half keeps
+        const float s0 = hi ? a01.x : a23.x, s1 = hi ? a01.y : a23.y;   // the pair it sends
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const bool odd = (kq & 1) != 0;
+        float keep = odd ? k1 : k0;
+        const float send = odd ? k0 : k1;
+        keep += __shfl_xor_sync(0xffffffffu, send, 1);
+        gx[(s & 1) * 256 + t8] = keep + gbias;
+    };
+
+    float4 xpre = prefetch(0);
+    phase_a(0, xpre);
+    __syncthreads();                                      // (P) xn of block 0 is complete
+    x_part(0);
+    if (nblk > 1) xpre = prefetch(1);
+    int next_c = 0;
+    for (int s = 0; s <= S; ++s) {
+        __syncthreads();
+        const int blk = s / SB, sb = s - blk * SB;
+        if (s + 1 < S) x_part(s + 1);
+        if (sb == SB / 2 && blk + 1 < nblk) phase_a(blk + 1, xpre);
+        if (sb == SB / 2 + 1 && blk + 2 < nblk) xpre = prefetch(blk + 2);
+        if (sb == 2 && blk > 0) { phase_c(blk - 1); next_c = blk; }
+    }
+    __syncthreads();                                      // the projection of the last step is in outp
+    for (; next_c < nblk; ++next_c) phase_c(next_c);
+}
+
+// =============================================================================================================
 // host side
 // =============================================================================================================
-// Cost model in SM cycles (first-order; refined from the per-step timings in profiles/): tile = 8 rows per warp,
-// FMA-issue bound; lane = one barrier-bound recurrent step per sequence group.
+// Cost model in SM cycles per recurrent step, measured on B200 (profiles/r01_lstm_bench.txt):
+//   tile : a warp (8 sequences) needs ~24.5k cycles per step while <= 4 warps share an SM, ~32k with all 8 resident
+//   ws   : ~400 (one sequence per CTA, warp-specialised);  lane1/2/4 : 1360 / 2530 / 4950 (1/2/4 sequences per CTA)
+// plus a launch + prologue constant; the cheapest family for (rows, dirs, steps) wins.
 static int pick_algo(int n_rows, int n_dirs, int S, int sms) {
-    const double tile_warps = (double)ceil_div(n_rows, 8) * n_dirs;
-    const double tile_wps = tile_warps / sms;                       // warps an SM must host (<= 8 resident)
-    const double tile_rounds = tile_wps <= 8.0 ? 1.0 : (double)ceil_div((int)tile_warps, sms * 8);
-    const double tile_step = 1600.0 * (tile_wps < 1.0 ? 1.0 : (tile_wps > 8.0 ? 8.0 : tile_wps)) + 1800.0;
-    const double tile = tile_rounds * (S * (tile_step < 6500.0 ? 6500.0 : tile_step) + 12000.0);
-    auto lane = [&](int rl, double step) {
-        return (double)ceil_div(ceil_div(n_rows, rl) * n_dirs, sms) * (S * step + 6000.0);
+    const double tasks = (double)ceil_div(n_rows, 8) * n_dirs;
+    const double resident = sms * 8.0;
+    const double rounds = tasks <= resident ? 1.0 : (double)ceil_div((int)tasks, (int)resident);
+    const double wps = tasks / sms > 8.0 ? 8.0 : tasks / sms;
+    const double tile_step = wps <= 4.0 ? 24500.0 : 24500.0 + (wps - 4.0) * 1900.0;
+    const double tile = rounds * S * tile_step + 30000.0;
+    auto per_cta = [&](int rl, double step, double fixed) {
+        return (double)ceil_div(ceil_div(n_rows, rl) * n_dirs, sms) * (S * step + fixed);
     };
-    const double cost[5] = {0.0, tile, lane(1, 330.0), lane(2, 520.0), lane(4, 900.0)};
+    const double cost[6] = {0.0, tile, per_cta(1, 1360.0, 8000.0), per_cta(2, 2530.0, 8000.0), per_cta(4, 4950.0, 8000.0),
+                            per_cta(1, 420.0, 12000.0)};
     int best = SB_ALGO_TILE;
-    for (int k = SB_ALGO_LANE1; k <= SB_ALGO_LANE4; ++k)
+    for (int k = SB_ALGO_LANE1; k <= SB_ALGO_WS; ++k)
         if (cost[k] < cost[best]) best = k;
     return best;
 }
@@ -533,6 +767,9 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
             return launch("lstm_lane2", lstm_lane_kernel<C, 2, RAW_H>, dim3(ceil_div(a.n_rows, 2), a.n_dirs), dim3(256), 0, st, a);
         case SB_ALGO_LANE4:
             return launch("lstm_lane4", lstm_lane_kernel<C, 4, RAW_H>, dim3(ceil_div(a.n_rows, 4), a.n_dirs), dim3(256), 0, st, a);
+        case SB_ALGO_WS:
+            return launch("lstm_ws", lstm_ws_kernel<C, RAW_H>, dim3(a.n_rows, a.n_dirs), dim3(512),
+                          WsCfg<C>::smem_floats * sizeof(float), st, a);
         default: break;
     }
     set_error("unknown LSTM algo %d", algo);

@@ -87,7 +87,7 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     SB_REQUIRE(io->wave && io->wave_out && io->workspace, SB_E_BADARG, "sb_net_forward: null wave / wave_out / workspace");
     SB_REQUIRE(io->B > 0 && io->T > 0, SB_E_BADARG, "sb_net_forward: bad B/T");
     SB_REQUIRE(d->n_blocks > 0 && d->n_blocks <= SB_MAX_BLOCKS, SB_E_UNSUPP, "sb_net_forward: n_blocks=%d out of range", d->n_blocks);
-    SB_REQUIRE(d->film_din == 0 || io->dis_embed, SB_E_BADARG, "sb_net_forward: dis_embed is required by this model");
+    SB_REQUIRE(d->film_din == 0 || io->dis_embed || io->film, SB_E_BADARG, "sb_net_forward: dis_embed is required by this model");
     SB_REQUIRE(((uintptr_t)io->workspace & 15) == 0, SB_E_BADARG, "sb_net_forward: workspace must be 16-byte aligned");
     const int B = io->B, T = io->T;
     const Workspace w = carve(d, B, T, io->workspace);
@@ -105,7 +105,10 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     ca.x = w.x0; ca.B = B; ca.T = T; ca.F = d->F; ca.Cin = d->Cin; ca.C = d->C;
     { StageTimer tm(stream, SB_STAGE_CONV_IN); SB_CHECK(sb_conv_in_fwd(&ca, stream)); }
 
-    if (w.film) {
+    const float* film = w.film;
+    if (io->film && d->film_din > 0 && d->n_blocks > 1) {
+        film = io->film;
+    } else if (w.film) {
         sb_film_args fa{};
         fa.dis = io->dis_embed; fa.emb_w = d->emb_w; fa.emb_ln_g = d->emb_ln_g; fa.emb_ln_b = d->emb_ln_b;
         fa.w_w = d->film_w_w; fa.w_b = d->film_w_b; fa.b_w = d->film_b_w; fa.b_b = d->film_b_b;
@@ -117,7 +120,7 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     const size_t film_stride = (size_t)B * d->F * d->C;
     for (int i = 0; i < d->n_blocks; ++i) {
         const sb_block_desc& bd = d->blocks[i];
-        const float* fscale = (w.film && i > 0) ? w.film + (size_t)(i - 1) * 2 * film_stride : nullptr;
+        const float* fscale = (film && i > 0) ? film + (size_t)(i - 1) * 2 * film_stride : nullptr;
         const float* fshift = fscale ? fscale + film_stride : nullptr;
         const float* inter_x1 = nullptr;
         if (d->conv_lstm) {

@@ -74,9 +74,27 @@ class Engine:
             raise ValueError("state tensor has shape %s, expected %s" % (tuple(t.shape), tuple(shape)))
         return t
 
+    def film_table(self, dis_embed: torch.Tensor) -> Optional[torch.Tensor]:
+        """Dis_Embed_* + every FilmLayer's 1x1 convs (DE3:51-68,114-173) for these rows: [n_blocks-1, 2, B, F, C].
+        Time-invariant, so a streaming session computes it once and hands it to every chunk."""
+        cfg, pk = self.cfg, self.packed
+        if cfg.variant != "dis_embed" or cfg.B < 2:
+            return None
+        dis = self._f32c(dis_embed)
+        B = dis.shape[0]
+        film = torch.empty(cfg.B - 1, 2, B, cfg.n_freqs, cfg.D, dtype=torch.float32, device=dis.device)
+        a = abi.FilmArgs()
+        a.dis, a.emb_w, a.emb_ln_g, a.emb_ln_b = dis.data_ptr(), pk.ptr("emb_w"), pk.ptr("emb_ln_g"), pk.ptr("emb_ln_b")
+        a.w_w, a.w_b, a.b_w, a.b_b = pk.ptr("film_w_w"), pk.ptr("film_w_b"), pk.ptr("film_b_w"), pk.ptr("film_b_b")
+        a.film = film.data_ptr()
+        a.B, a.F, a.C, a.Din, a.n_layers, a.emb_mode = B, cfg.n_freqs, cfg.D, cfg.film_in, cfg.B - 1, pk.desc.emb_mode
+        abi.check(self.lib, self.lib.sb_film_params_fwd(ctypes.byref(a), _stream_ptr(dis)), "sb_film_params_fwd")
+        return film
+
     # -- the forward pass ------------------------------------------------------------------------------------
     def forward(self, wave: torch.Tensor, dis_embed: Optional[torch.Tensor], state: dict,
-                out: Optional[torch.Tensor] = None, new_state: Optional[dict] = None):
+                out: Optional[torch.Tensor] = None, new_state: Optional[dict] = None,
+                film: Optional[torch.Tensor] = None):
         """wave [B, M, stride*T + n_fft - stride] -> ([B, S, stride*T], state).  `state` is updated in place (the
         dict, as the reference does, DE3:547-552) with freshly written tensors unless `new_state` supplies them."""
         cfg, lib = self.cfg, self.lib
@@ -102,6 +120,8 @@ class Engine:
             dis = self._f32c(dis_embed.to(dev), (B, 3))
             io.dis_embed = dis.data_ptr()
             keep.append(dis)
+            if film is not None:
+                io.film = film.data_ptr()
         if out is None:
             out = torch.empty(B, S, cfg.stft_chunk_size * T, dtype=torch.float32, device=dev)
         io.wave_out = out.data_ptr()

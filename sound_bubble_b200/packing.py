@@ -112,7 +112,25 @@ def _lstm_dir(sd, prefix: str, sfx: str, H: int) -> Dict[str, torch.Tensor]:
     w_lane = w_slot.view(4 * H, K // 4, 4).permute(1, 0, 2).contiguous()     # [K/4][4H][4]
     b_lane = torch.empty(4 * H, dtype=torch.float32, device=w.device)
     b_lane[slot] = b
-    return {"w_tile": w_tile, "b_tile": b_tile, "w_lane": w_lane, "b_lane": b_lane}
+    # warp-specialised kernel: thread t = 4u + kq owns the four gates of unit u over a quarter of K
+    C = K - H
+    w_ih, w_hh = w[:, :C], w[:, C:]
+    w_rec = w_hh.reshape(4, H, 4, 16).permute(3, 1, 2, 0).reshape(16, 4 * H, 4).contiguous()          # [k][t][g]
+    w_xp = w_ih.reshape(4, H, 4, C // 4).permute(3, 1, 2, 0).reshape(C // 4, 4 * H, 4).contiguous()   # [k][t][g]
+    return {"w_tile": w_tile, "b_tile": b_tile, "w_lane": w_lane, "b_lane": b_lane, "w_rec": w_rec, "w_xp": w_xp}
+
+
+def _proj_ws(lin: torch.Tensor, H: int) -> torch.Tensor:
+    """lin [C, H] -> w_prj [(NPJ/4)][4H][4]: thread t = 4u + kq holds lin[u % C][16kq + NPJ*(u // C) + j], j < NPJ."""
+    C = lin.shape[0]
+    nsub = H // C
+    npj = 16 // nsub
+    t = torch.arange(4 * H)
+    u, kq = t // 4, t % 4
+    j = torch.arange(npj)
+    col = (16 * kq + npj * (u // C)).view(-1, 1) + j.view(1, -1)                 # [4H, NPJ]
+    p = lin.float()[(u % C).view(-1, 1).expand(-1, npj), col]                   # [4H, NPJ]
+    return p.view(4 * H, npj // 4, 4).permute(1, 0, 2).contiguous()
 
 
 class PackedWeights:
@@ -160,6 +178,7 @@ class PackedWeights:
                     lin = sd[b + "intra_linear.weight"][:, d * H:(d + 1) * H]       # [C, H]
                     add(f"b{i}.intra{d}.lin_n", lin)
                     add(f"b{i}.intra{d}.lin_t", lin.t())
+                    add(f"b{i}.intra{d}.w_prj", _proj_ws(lin, H))
             if not cfg.conv_lstm:
                 add(f"b{i}.intra.lin_b", sd[b + "intra_linear.bias"])
             add(f"b{i}.intra.ln_g", sd[b + norm + "weight"])
@@ -168,6 +187,7 @@ class PackedWeights:
                 add(f"b{i}.inter.{k}", v)
             add(f"b{i}.inter.lin_n", sd[b + "inter_linear.weight"])
             add(f"b{i}.inter.lin_t", sd[b + "inter_linear.weight"].t())
+            add(f"b{i}.inter.w_prj", _proj_ws(sd[b + "inter_linear.weight"], H))
             add(f"b{i}.inter.lin_b", sd[b + "inter_linear.bias"])
             add(f"b{i}.inter.ln_g", sd[b + "inter_norm.norm.weight"])
             add(f"b{i}.inter.ln_b", sd[b + "inter_norm.norm.bias"])
@@ -241,7 +261,7 @@ class PackedWeights:
         self.desc = d
 
     def _fill_dir(self, dst, own: str, shared: str):
-        for f in ("w_tile", "b_tile", "w_lane", "b_lane", "lin_t", "lin_n"):
+        for f in ("w_tile", "b_tile", "w_lane", "b_lane", "w_rec", "w_xp", "w_prj", "lin_t", "lin_n"):
             setattr(dst, f, self.ptr(own + f))
         for f in ("lin_b", "ln_g", "ln_b"):
             v = self.ptr(own + f)

@@ -38,6 +38,7 @@ class StreamingSession:
             if dis_embed is None:
                 raise KeyError("dis_embed")
             self.dis = dis_embed.to(dev, torch.float32).contiguous().clone()
+        self.film = self.engine.film_table(self.dis) if self.dis is not None else None      # time-invariant: once
         self.states = [init_state(cfg, batch_size, dev), init_state(cfg, batch_size, dev)]
         self.parity = 0
         self.graphs = None
@@ -49,7 +50,7 @@ class StreamingSession:
     def _step_eager(self, p: int):
         src, dst = self.states[p], self.states[p ^ 1]
         work = {k: (dict((kk, dict(vv)) for kk, vv in v.items()) if k == "gridnet_bufs" else v) for k, v in src.items()}
-        self.engine.forward(self.x, self.dis, work, out=self.y, new_state=dst)
+        self.engine.forward(self.x, self.dis, work, out=self.y, new_state=dst, film=self.film)
 
     def _capture(self):
         saved = [_clone_state(s) for s in self.states]

@@ -29,9 +29,11 @@ def test_frontend_backend_kernels(lib):
     _ok(kc.check_film(lib, "cpu", "dis_embed", SYN, B=4))
     _ok(kc.check_backend(lib, "cpu", "dis_embed", SYN, B=1, T=11, with_mask=True))
     _ok(kc.check_backend(lib, "cpu", "optim", RPI, B=2, T=1))
+    _ok(kc.check_backend(lib, "cpu", "dis_embed", dict(SYN, num_src=2), B=1, T=3, with_mask=True))
+    _ok(kc.check_backend(lib, "cpu", "dis_embed", dict(SYN, num_src=2), B=1, T=10))
 
 
-@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE4])
+@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE4, abi.SB_ALGO_WS])
 def test_lstm_kernels(lib, algo):
     _ok(kc.check_inter(lib, "cpu", "dis_embed", SYN, algo, B=1, T=3, alias_state=True))
     _ok(kc.check_intra(lib, "cpu", "dis_embed", SYN, algo, B=1, T=2))

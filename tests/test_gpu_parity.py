@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = 2e-5          # max-abs for single stages on O(1) data (fp32 both sides, different summation order)
 C16 = dict(OPI, D=16)
-ALGOS = [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2, abi.SB_ALGO_LANE4, abi.SB_ALGO_AUTO]
+ALGOS = [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2, abi.SB_ALGO_LANE4, abi.SB_ALGO_WS, abi.SB_ALGO_AUTO]
 
 
 @pytest.fixture(scope="module")
@@ -62,13 +62,16 @@ def test_inter_lstm(lib, algo, variant, kw):
 
 @pytest.mark.parametrize("variant,kw,B,T,mask", [("dis_embed", SYN, 2, 5, False), ("dis_embed", SYN, 2, 1, False),
                                                  ("dis_embed", SYN, 1, 11, True), ("optim", RPI, 1, 3, False),
+                                                 ("dis_embed", SYN, 2, 3, True), ("dis_embed", SYN, 1, 8, False),
+                                                 ("dis_embed", dict(SYN, num_src=2), 2, 2, True),
+                                                 ("dis_embed", dict(SYN, num_src=2), 1, 12, False),
                                                  ("dis_embed", SYN, 2, 70, False)])
 def test_backend(lib, variant, kw, B, T, mask):
     _ok(kc.check_backend(lib, DEV, variant, kw, B=B, T=T, with_mask=mask))
 
 
 @pytest.mark.parametrize("variant,kw", [("dis_embed", dict(SYN, conv_lstm=True)), ("optim", RPI), ("optim", dict(RPI, lstm_down=4))])
-@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_AUTO])
+@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_WS, abi.SB_ALGO_AUTO])
 def test_intra_convlstm(lib, variant, kw, algo):
     _ok(kc.check_intra(lib, DEV, variant, kw, algo, B=2, T=5, block=1))
 
@@ -87,7 +90,7 @@ def test_golden_through_c_abi(lib, name):
 
 
 @pytest.mark.parametrize("intra,inter", [(abi.SB_ALGO_TILE, abi.SB_ALGO_TILE), (abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2),
-                                         (abi.SB_ALGO_LANE4, abi.SB_ALGO_LANE1)])
+                                         (abi.SB_ALGO_LANE4, abi.SB_ALGO_LANE1), (abi.SB_ALGO_WS, abi.SB_ALGO_WS)])
 def test_golden_with_forced_lstm_algos(lib, intra, inter):
     pc.assert_parity(pc.run_golden(lib, DEV, "syn_offline", intra, inter))
 
@@ -188,4 +191,4 @@ def test_launches_are_counted():
     before = _lib.launch_count()
     m(g.inputs(DEV), pad=g.pad)
     torch.cuda.synchronize()
-    assert _lib.launch_count() - before == 2 + 1 + 2 * 2 + 2      # stft, conv_in, film, 2 x (intra, inter), deconv, istft
+    assert _lib.launch_count() - before == 2 + 1 + 2 * 2 + 1      # stft, conv_in, film, 2 x (intra, inter), fused backend
