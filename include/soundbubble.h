@@ -78,7 +78,7 @@ typedef struct sb_lstm_dir {
     const float* b_lane;    /* [4H]       b_ih + b_hh, slot order 4u+g                                           */
     const float* w_rec;     /* [16][4H] float4: thread t=(u=t/4,kq=t%4), k -> W_hh[g*H+u][16kq+k] for g = 0..3       */
     const float* w_xp;      /* [C/4][4H] float4: same thread map, k -> W_ih[g*H+u][(C/4)kq+k] for g = 0..3           */
-    const float* w_prj;     /* [(16C/H)/4][4H] float4: thread t -> lin[c=u%C][16kq + (16C/H)(u/C) + j]               */
+    const float* w_prj;     /* [(C/4)/4][4H] float4: thread t -> lin[t/(4H/C)][(C/4)(t%(4H/C)) + j], j < C/4         */
     const float* lin_t;     /* [H][C]     output projection, transposed (this direction's half for the BiLSTM)  */
     const float* lin_n;     /* [C][H]     output projection, natural                                             */
     const float* lin_b;     /* [C]        projection bias (added by direction 0 only)                            */

@@ -104,6 +104,15 @@ __device__ __forceinline__ void pdl_trigger() {
 #endif
 }
 
+// named barrier over a subset of the CTA's warps (PTX bar.sync id, nthreads; id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+#ifdef SB_EMU
+    emu::named_barrier(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 // sigmoid / tanh through one ex2.approx + one rcp.approx (2 MUFU ops, no slow paths): |abs err| ~ 1e-7, far inside the
 // 1e-3 RMS waveform parity bar.  tanh.approx (2^-11 rel err) is NOT accurate enough here.
 __device__ __forceinline__ float fast_ex2(float x) {

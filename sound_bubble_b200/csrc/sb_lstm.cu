@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
         float4 xnext[NV];
         if (s + 1 < S) load_x(s + 1, xnext);
 
-        float acc[RW][8];
+        float2 acc[RW][4];                  // {i, f, g, o} x (unit 2*lane, unit 2*lane+1): packed-FFMA2 accumulators
 #pragma unroll
         for (int r = 0; r < RW; ++r)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[r][j] = bias[j];
+            for (int j = 0; j < 4; ++j) acc[r][j] = make_float2(bias[2 * j], bias[2 * j + 1]);
         float accp[ORW];
 #pragma unroll
         for (int i = 0; i < ORW; ++i) accp[i] = 0.f;
@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
 #pragma unroll
                 for (int r = 0; r < RW; ++r) {
                     const float x = av[r][kk];
-                    acc[r][0] = fmaf(x, w0.x, acc[r][0]); acc[r][1] = fmaf(x, w0.y, acc[r][1]);
-                    acc[r][2] = fmaf(x, w0.z, acc[r][2]); acc[r][3] = fmaf(x, w0.w, acc[r][3]);
-                    acc[r][4] = fmaf(x, w1.x, acc[r][4]); acc[r][5] = fmaf(x, w1.y, acc[r][5]);
-                    acc[r][6] = fmaf(x, w1.z, acc[r][6]); acc[r][7] = fmaf(x, w1.w, acc[r][7]);
+                    ffma2(acc[r][0], make_float2(w0.x, w0.y), x);
+                    ffma2(acc[r][1], make_float2(w0.z, w0.w), x);
+                    ffma2(acc[r][2], make_float2(w1.x, w1.y), x);
+                    ffma2(acc[r][3], make_float2(w1.z, w1.w), x);
                 }
                 if constexpr (decltype(with_proj)::value) {
                     const float wl = WlT[(k - C) * C + oc];
@@ -229,18 +229,22 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
         for (int k4 = C / 4; k4 < K / 4; ++k4) kblock(k4, std::integral_constant<bool, !RAW_H>{});
         if (!RAW_H && s > 0) emit(s - 1, accp);
 
-        // gates: acc[r] = {i_u0, i_u1, f_u0, f_u1, g_u0, g_u1, o_u0, o_u1}  (PyTorch order i, f, g, o)
+        // gates: acc[r] = {i, f, g, o} pairs over the lane's two hidden units  (PyTorch order i, f, g, o)
 #pragma unroll
-        for (int r = 0; r < RW; ++r)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float ig = sigmoid_f(acc[r][0 + j]);
-                const float fg = sigmoid_f(acc[r][2 + j]);
-                const float gg = tanh_f(acc[r][4 + j]);
-                const float og = sigmoid_f(acc[r][6 + j]);
-                c[r][j] = fmaf(fg, c[r][j], ig * gg);
-                hn[r][j] = og * tanh_f(c[r][j]);
+        for (int r = 0; r < RW; ++r) {
+            {
+                const float ig = sigmoid_f(acc[r][0].x), fg = sigmoid_f(acc[r][1].x);
+                const float gg = tanh_f(acc[r][2].x), og = sigmoid_f(acc[r][3].x);
+                c[r][0] = fmaf(fg, c[r][0], ig * gg);
+                hn[r][0] = og * tanh_f(c[r][0]);
             }
+            {
+                const float ig = sigmoid_f(acc[r][0].y), fg = sigmoid_f(acc[r][1].y);
+                const float gg = tanh_f(acc[r][2].y), og = sigmoid_f(acc[r][3].y);
+                c[r][1] = fmaf(fg, c[r][1], ig * gg);
+                hn[r][1] = og * tanh_f(c[r][1]);
+            }
+        }
         __syncwarp();                       // every lane is done reading A and res[(s-1)&1]
 #pragma unroll
         for (int r = 0; r < RW; ++r) st2(A + r * AS + C + 2 * lane, make_float2(hn[r][0], hn[r][1]));
@@ -491,32 +495,34 @@ __global__ void __launch_bounds__(256, 1) lstm_lane_kernel(const SeqArgs a) {
 // =============================================================================================================
 // One sequence (and direction) per CTA, 512 threads.  Warps 0-7 run ONLY the recurrence: thread (u, kq) owns all four
 // gates of hidden unit u over a quarter of the hidden state (k = 16kq .. 16kq+15, 64 weights in registers), so a step
-// moves 4 LDS.128 per thread instead of 16 (shared-memory -> register bandwidth, not FMA issue, bounds this kernel),
-// 32 packed FFMA2, a 2-level shuffle all-reduce over the four kq lanes, then every lane of the quad evaluates the
-// cell itself (no gate exchange).  The projection of step s-1 reuses the h slice already in registers.
-// Warps 8-15 are helpers off the critical path: global loads + FiLM + LayerNorm per block of SB steps, the input part
-// of the gates (x W_ih^T + b) one step ahead, and the residual / bias / store of finished blocks.
-// One __syncthreads per step joins the two groups.
+// moves 4 LDS.128 per thread instead of 16 (shared-memory -> register bandwidth, not FMA issue, bounds the one-column-
+// per-thread kernel), 32 packed FFMA2, a one-level shuffle all-reduce over the four kq lanes, then every lane of the
+// quad evaluates the cell itself (no gate exchange).  They synchronise among themselves with a 256-thread named
+// barrier per step.  Warps 8-15 are helpers that work a GROUP of 4 steps at a time, off the critical path: global
+// loads + FiLM + LayerNorm per block of SB steps, the input part of the gates (x W_ih^T + b) for the next group, the
+// output projection of the previous group, and the residual / bias / store of finished blocks.  The two sides meet at
+// one full barrier per group; gate inputs and hidden states travel through 8-deep rings in shared memory.
 template <int C>
 struct WsCfg {
-    static constexpr int H = 64, LPP = C / 4, SB = 256 / LPP, XK = C / 4, HS = 20;
-    static constexpr int NSUB = H / C, NPJ = 16 / NSUB;
+    static constexpr int H = 64, LPP = C / 4, SB = 256 / LPP, XK = C / 4, HS = 20, G = 4, RING = 8;
+    static constexpr int LPO = 256 / C, KPT = H / LPO;      // projection: lanes per output channel, k per lane
     static constexpr int xn_off = 0, res_off = 2 * SB * C, outp_off = 4 * SB * C;
-    static constexpr int gx_off = outp_off + 2 * NSUB * SB * C, hb_off = gx_off + 512;
-    static constexpr int smem_floats = hb_off + 2 * 4 * HS;
-    static_assert(SB >= 8 && NPJ % 4 == 0 && XK % 4 == 0, "block / slice sizes");
+    static constexpr int gx_off = outp_off + 2 * SB * C, hb_off = gx_off + RING * 256;
+    static constexpr int smem_floats = hb_off + RING * 4 * HS;
+    static_assert(SB >= 16 && SB % G == 0 && KPT % 4 == 0 && XK % 4 == 0 && 16 % KPT == 0, "block / slice sizes");
 };
 
 template <int C, bool RAW_H>
 __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
     using Cfg = WsCfg<C>;
-    constexpr int H = Cfg::H, LPP = Cfg::LPP, SB = Cfg::SB, XK = Cfg::XK, HS = Cfg::HS, NSUB = Cfg::NSUB, NPJ = Cfg::NPJ;
+    constexpr int H = Cfg::H, LPP = Cfg::LPP, SB = Cfg::SB, XK = Cfg::XK, HS = Cfg::HS, LPO = Cfg::LPO, KPT = Cfg::KPT;
+    constexpr int G = Cfg::G, RING = Cfg::RING;
     SB_DYN_SMEM(float, smem);
-    float* xn = smem + Cfg::xn_off;         // [2][SB][C]        LayerNorm(x') of the current / next block
-    float* res = smem + Cfg::res_off;       // [2][SB][C]        x' (residual)
-    float* outp = smem + Cfg::outp_off;     // [2][NSUB][SB][C]  partial projections
-    float* gx = smem + Cfg::gx_off;         // [2][256]          x W_ih^T + b of step s (slot 4u+g)
-    float* hb = smem + Cfg::hb_off;         // [2][4][HS]        h_{s-1}: four 16-float slices, padded to 20
+    float* xn = smem + Cfg::xn_off;         // [2][SB][C]      LayerNorm(x') of the current / next block
+    float* res = smem + Cfg::res_off;       // [2][SB][C]      x' (residual)
+    float* outp = smem + Cfg::outp_off;     // [2][SB][C]      projections of finished steps
+    float* gx = smem + Cfg::gx_off;         // [RING][256]     x W_ih^T + b of step s in slot s % RING (thread slot 4u+g)
+    float* hb = smem + Cfg::hb_off;         // [RING][4][HS]   h_{s-1} in slot s % RING: four 16-float slices padded to 20
 
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;
@@ -524,6 +530,7 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
     const int S = a.n_steps;
     const int row = blockIdx.x;
     const int nblk = (S + SB - 1) / SB;
+    const int ngrp = (S + G - 1) / G;
     const bool recur = tid < 256;                        // warp-uniform role
     const int t8 = tid & 255;
     const int u = t8 >> 2, kq = t8 & 3;
@@ -533,35 +540,33 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
         float4 wr[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w.w_rec) + k * 256 + t8);
-        float wp[NPJ];
-        if (!RAW_H) {
-#pragma unroll
-            for (int j4 = 0; j4 < NPJ / 4; ++j4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(w.w_prj) + j4 * 256 + t8);
-                wp[4 * j4] = v.x; wp[4 * j4 + 1] = v.y; wp[4 * j4 + 2] = v.z; wp[4 * j4 + 3] = v.w;
-            }
-        }
-        const int pc = u % C, sub = u / C;               // projection role: output channel, k-part (warp-uniform)
         pdl_trigger();
         pdl_wait();
         const bool has0 = a.h0 != nullptr;
         float c = has0 ? ld_plain(a.c0 + (long long)row * H + u) : 0.0f;
         float hlast = has0 ? ld_plain(a.h0 + (long long)row * H + u) : 0.0f;
-        if (kq == 0) hb[(u >> 4) * HS + (u & 15)] = hlast;
+        const int hslot = (u >> 4) * HS + (u & 15);
+        if (kq == 0) hb[hslot] = hlast;
         float* const outr = a.out[dir];
-        __syncthreads();                                  // (P) pairs with the helpers' prologue barrier
+        __syncthreads();                                  // (P) pairs with the helpers' prologue barriers
+        __syncthreads();                                  // (Q)
 
-        for (int s = 0; s <= S; ++s) {
-            __syncthreads();
-            const float* hs = hb + (s & 1) * 4 * HS + kq * HS;
-            float hr[16];
+        for (int g = 0; g <= ngrp; ++g) {
+            __syncthreads();                              // group barrier: gx of this group is ready, helpers see h of the last
+            if (g == ngrp) break;
+#pragma unroll 1
+            for (int j = 0; j < G; ++j) {
+                const int s = g * G + j;
+                if (s >= S) break;
+                if (j > 0) bar_sync(1, 256);              // h_{s-1} of every unit is in the ring
+                const float* hs = hb + (s & (RING - 1)) * 4 * HS + kq * HS;
+                float hr[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = ld4(hs + 4 * i);
-                hr[4 * i] = v.x; hr[4 * i + 1] = v.y; hr[4 * i + 2] = v.z; hr[4 * i + 3] = v.w;
-            }
-            if (s < S) {
-                const float4 g4 = ld4(gx + (s & 1) * 256 + 4 * u);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = ld4(hs + 4 * i);
+                    hr[4 * i] = v.x; hr[4 * i + 1] = v.y; hr[4 * i + 2] = v.z; hr[4 * i + 3] = v.w;
+                }
+                const float4 g4 = ld4(gx + (s & (RING - 1)) * 256 + 4 * u);
                 float2 a01[2], a23[2];
                 a01[0] = make_float2(0.f, 0.f); a01[1] = a01[0]; a23[0] = a01[0]; a23[1] = a01[0];
 #pragma unroll
@@ -569,40 +574,26 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
                     ffma2(a01[k & 1], make_float2(wr[k].x, wr[k].y), hr[k]);
                     ffma2(a23[k & 1], make_float2(wr[k].z, wr[k].w), hr[k]);
                 }
-                float p0 = a01[0].x + a01[1].x, p1 = a01[0].y + a01[1].y;
-                float p2 = a23[0].x + a23[1].x, p3 = a23[0].y + a23[1].y;
-                p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
-                p2 += __shfl_xor_sync(0xffffffffu, p2, 1); p3 += __shfl_xor_sync(0xffffffffu, p3, 1);
-                p0 += __shfl_xor_sync(0xffffffffu, p0, 2); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
-                p2 += __shfl_xor_sync(0xffffffffu, p2, 2); p3 += __shfl_xor_sync(0xffffffffu, p3, 2);
-                const float ig = sigmoid_f(p0 + g4.x);
-                const float fg = sigmoid_f(p1 + g4.y);
-                const float gg = tanh_f(p2 + g4.z);
-                const float og = sigmoid_f(p3 + g4.w);
+                float p[4] = {a01[0].x + a01[1].x, a01[0].y + a01[1].y, a23[0].x + a23[1].x, a23[0].y + a23[1].y};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {             // one-level all-reduce over the quad: three independent shuffles
+                    const float v1 = __shfl_xor_sync(0xffffffffu, p[q], 1);
+                    const float v2 = __shfl_xor_sync(0xffffffffu, p[q], 2);
+                    const float v3 = __shfl_xor_sync(0xffffffffu, p[q], 3);
+                    p[q] = (p[q] + v1) + (v2 + v3);
+                }
+                const float ig = sigmoid_f(p[0] + g4.x);
+                const float fg = sigmoid_f(p[1] + g4.y);
+                const float gg = tanh_f(p[2] + g4.z);
+                const float og = sigmoid_f(p[3] + g4.w);
                 c = fmaf(fg, c, ig * gg);
                 hlast = og * tanh_f(c);
                 if (kq == 0) {
-                    hb[((s + 1) & 1) * 4 * HS + (u >> 4) * HS + (u & 15)] = hlast;
+                    hb[((s + 1) & (RING - 1)) * 4 * HS + hslot] = hlast;
                     if (RAW_H) {
                         const int pos = dir ? S - 1 - s : s;
                         outr[((long long)row * S + pos) * H + u] = hlast;
                     }
-                }
-            }
-            if (!RAW_H && s > 0) {                       // projection of step s-1 from the slice already in registers
-                float pp = 0.f;
-#pragma unroll
-                for (int q = 0; q < NSUB; ++q) {
-                    if (sub == q) {
-#pragma unroll
-                        for (int j = 0; j < NPJ; ++j) pp = fmaf(wp[j], hr[NPJ * q + j], pp);
-                    }
-                }
-                pp += __shfl_xor_sync(0xffffffffu, pp, 1);
-                pp += __shfl_xor_sync(0xffffffffu, pp, 2);
-                if (kq == 0) {
-                    const int sp = s - 1, bp = sp / SB;
-                    outp[(((bp & 1) * NSUB + sub) * SB + (sp - bp * SB)) * C + pc] = pp;
                 }
             }
         }
@@ -619,6 +610,16 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
 #pragma unroll
     for (int k = 0; k < XK; ++k) wx[k] = __ldg(reinterpret_cast<const float4*>(w.w_xp) + k * 256 + t8);
     const float gbias = __ldg(w.b_lane + t8);             // slot 4u+g with g = kq after the reduce-scatter
+    float wp[KPT];                                         // projection role: channel pc, hidden units KPT*ks ..
+    const int pc = t8 / LPO, ks = t8 % LPO;
+    if (!RAW_H) {
+#pragma unroll
+        for (int j4 = 0; j4 < KPT / 4; ++j4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(w.w_prj) + j4 * 256 + t8);
+            wp[4 * j4] = v.x; wp[4 * j4 + 1] = v.y; wp[4 * j4 + 2] = v.z; wp[4 * j4 + 3] = v.w;
+        }
+    }
+    const int pslot = ((KPT * ks) >> 4) * HS + ((KPT * ks) & 15);
     const int pq = t8 / LPP, c4 = t8 % LPP;               // load / LayerNorm / store role: step pq of a block, channels 4c4..
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(w.ln_g) + c4);
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.ln_b) + c4);
@@ -659,16 +660,11 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
                                                                   fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w)));
         if (!RAW_H) st4(res + ((blk & 1) * SB + pq) * C + 4 * c4, v);
     };
-    auto phase_c = [&](int blk) {                         // finished block: partial projections + bias + residual -> global
+    auto phase_c = [&](int blk) {                         // finished block: projection + bias + residual -> global
         if (RAW_H) return;
         const int s = blk * SB + pq;
         if (s < S) {
-            float4 v = make_float4(0, 0, 0, 0);
-#pragma unroll
-            for (int q = 0; q < NSUB; ++q) {
-                const float4 t = ld4(outp + (((blk & 1) * NSUB + q) * SB + pq) * C + 4 * c4);
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-            }
+            float4 v = ld4(outp + ((blk & 1) * SB + pq) * C + 4 * c4);
             if (dir == 0) {
                 const float4 r = ld4(res + ((blk & 1) * SB + pq) * C + 4 * c4);
                 v.x += blin4.x + r.x; v.y += blin4.y + r.y; v.z += blin4.z + r.z; v.w += blin4.w + r.w;
@@ -677,49 +673,85 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
             st4(outp_g + p_base + (long long)pos * a.stride_pos, v);
         }
     };
-    auto x_part = [&](int s) {                            // gx[s] = LN(x_s) W_ih^T + b, K split over the 4 kq lanes
-        const int blk = s / SB;
-        const float* xr = xn + ((blk & 1) * SB + (s - blk * SB)) * C + XK * kq;
-        float xv[XK];
+    // gx[s] = LN(x_s) W_ih^T + b for the G steps of a group, K split over the 4 kq lanes (G independent chains)
+    auto x_part_group = [&](int s0) {
+        const int blk = s0 / SB;
+        const float* xr = xn + ((blk & 1) * SB + (s0 - blk * SB)) * C + XK * kq;
+        float2 a01[G], a23[G];
 #pragma unroll
-        for (int i = 0; i < XK / 4; ++i) {
-            const float4 v = ld4(xr + 4 * i);
-            xv[4 * i] = v.x; xv[4 * i + 1] = v.y; xv[4 * i + 2] = v.z; xv[4 * i + 3] = v.w;
-        }
-        float2 a01 = make_float2(0.f, 0.f), a23 = a01;
+        for (int j = 0; j < G; ++j) {
+            float xv[XK];
 #pragma unroll
-        for (int k = 0; k < XK; ++k) {
-            ffma2(a01, make_float2(wx[k].x, wx[k].y), xv[k]);
-            ffma2(a23, make_float2(wx[k].z, wx[k].w), xv[k]);
+            for (int i = 0; i < XK / 4; ++i) {
+                const float4 v = ld4(xr + j * C + 4 * i);
+                xv[4 * i] = v.x; xv[4 * i + 1] = v.y; xv[4 * i + 2] = v.z; xv[4 * i + 3] = v.w;
+            }
+            a01[j] = make_float2(0.f, 0.f); a23[j] = a01[j];
+#pragma unroll
+            for (int k = 0; k < XK; ++k) {
+                ffma2(a01[j], make_float2(wx[k].x, wx[k].y), xv[k]);
+                ffma2(a23[j], make_float2(wx[k].z, wx[k].w), xv[k]);
+            }
         }
-        // reduce-scatter over the 4 kq lanes: lane kq ends with the total of gate kq
-        const bool hi = (kq & 2) != 0;
-        float k0 = hi ? a23.x : a01.x, k1 = hi ? a23.y : a01.y;         // the pair this lane's half keeps
-        const float s0 = hi ? a01.x : a23.x, s1 = hi ? a01.y : a23.y;   // the pair it sends
-        k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-        k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        const bool odd = (kq & 1) != 0;
-        float keep = odd ? k1 : k0;
-        const float send = odd ? k0 : k1;
-        keep += __shfl_xor_sync(0xffffffffu, send, 1);
-        gx[(s & 1) * 256 + t8] = keep + gbias;
+        const bool hi = (kq & 2) != 0, odd = (kq & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {                     // reduce-scatter over the quad: lane kq ends with gate kq
+            float k0 = hi ? a23[j].x : a01[j].x, k1 = hi ? a23[j].y : a01[j].y;
+            const float s0v = hi ? a01[j].x : a23[j].x, s1v = hi ? a01[j].y : a23[j].y;
+            k0 += __shfl_xor_sync(0xffffffffu, s0v, 2);
+            k1 += __shfl_xor_sync(0xffffffffu, s1v, 2);
+            float keep = odd ? k1 : k0;
+            const float send = odd ? k0 : k1;
+            keep += __shfl_xor_sync(0xffffffffu, send, 1);
+            if (s0 + j < S) gx[((s0 + j) & (RING - 1)) * 256 + t8] = keep + gbias;
+        }
+    };
+    // out[sp][pc] = lin[pc][:] . h_sp for the G steps of a group; h_sp sits in ring slot (sp + 1) % RING
+    auto project_group = [&](int s0) {
+        if (RAW_H) return;
+        float pp[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const float* hp = hb + ((s0 + j + 1) & (RING - 1)) * 4 * HS + pslot;
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < KPT / 4; ++j4) {
+                const float4 v = ld4(hp + 4 * j4);
+                p0 = fmaf(wp[4 * j4], v.x, p0); p1 = fmaf(wp[4 * j4 + 1], v.y, p1);
+                p0 = fmaf(wp[4 * j4 + 2], v.z, p0); p1 = fmaf(wp[4 * j4 + 3], v.w, p1);
+            }
+            pp[j] = p0 + p1;
+        }
+#pragma unroll
+        for (int o = LPO / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int j = 0; j < G; ++j) pp[j] += __shfl_xor_sync(0xffffffffu, pp[j], o);
+        if (ks == 0) {
+            const int bp = s0 / SB;
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (s0 + j < S) outp[((bp & 1) * SB + (s0 + j - bp * SB)) * C + pc] = pp[j];
+        }
     };
 
     float4 xpre = prefetch(0);
     phase_a(0, xpre);
     __syncthreads();                                      // (P) xn of block 0 is complete
-    x_part(0);
+    x_part_group(0);
     if (nblk > 1) xpre = prefetch(1);
+    __syncthreads();                                      // (Q) gx of group 0 is complete
     int next_c = 0;
-    for (int s = 0; s <= S; ++s) {
-        __syncthreads();
-        const int blk = s / SB, sb = s - blk * SB;
-        if (s + 1 < S) x_part(s + 1);
-        if (sb == SB / 2 && blk + 1 < nblk) phase_a(blk + 1, xpre);
-        if (sb == SB / 2 + 1 && blk + 2 < nblk) xpre = prefetch(blk + 2);
-        if (sb == 2 && blk > 0) { phase_c(blk - 1); next_c = blk; }
+    constexpr int GPB = SB / G;                           // groups per block
+    for (int g = 0; g <= ngrp; ++g) {
+        __syncthreads();                                  // group barrier
+        const int blk = g / GPB, gb = g - blk * GPB;
+        if (g + 1 < ngrp) x_part_group((g + 1) * G);      // needs xn of block (g+1)/GPB: written >= one group barrier ago
+        if (g > 0) project_group((g - 1) * G);
+        if (gb == GPB / 2 - 1 && blk + 1 < nblk) phase_a(blk + 1, xpre);
+        if (gb == GPB / 2 && blk + 2 < nblk) xpre = prefetch(blk + 2);
+        if (gb == 2 && blk > 0) { phase_c(blk - 1); next_c = blk; }
     }
-    __syncthreads();                                      // the projection of the last step is in outp
+    __syncthreads();                                      // every projection is in outp
     for (; next_c < nblk; ++next_c) phase_c(next_c);
 }
 
@@ -735,13 +767,13 @@ static int pick_algo(int n_rows, int n_dirs, int S, int sms) {
     const double resident = sms * 8.0;
     const double rounds = tasks <= resident ? 1.0 : (double)ceil_div((int)tasks, (int)resident);
     const double wps = tasks / sms > 8.0 ? 8.0 : tasks / sms;
-    const double tile_step = wps <= 4.0 ? 24500.0 : 24500.0 + (wps - 4.0) * 1900.0;
+    const double tile_step = wps <= 4.0 ? 9000.0 : 9000.0 + (wps - 4.0) * 1500.0;
     const double tile = rounds * S * tile_step + 30000.0;
     auto per_cta = [&](int rl, double step, double fixed) {
         return (double)ceil_div(ceil_div(n_rows, rl) * n_dirs, sms) * (S * step + fixed);
     };
     const double cost[6] = {0.0, tile, per_cta(1, 1360.0, 8000.0), per_cta(2, 2530.0, 8000.0), per_cta(4, 4950.0, 8000.0),
-                            per_cta(1, 420.0, 12000.0)};
+                            per_cta(1, 600.0, 12000.0)};
     int best = SB_ALGO_TILE;
     for (int k = SB_ALGO_LANE1; k <= SB_ALGO_WS; ++k)
         if (cost[k] < cost[best]) best = k;

@@ -121,16 +121,15 @@ def _lstm_dir(sd, prefix: str, sfx: str, H: int) -> Dict[str, torch.Tensor]:
 
 
 def _proj_ws(lin: torch.Tensor, H: int) -> torch.Tensor:
-    """lin [C, H] -> w_prj [(NPJ/4)][4H][4]: thread t = 4u + kq holds lin[u % C][16kq + NPJ*(u // C) + j], j < NPJ."""
+    """lin [C, H] -> w_prj [(KPT/4)][4H][4]: helper thread t holds lin[t // LPO][KPT*(t % LPO) + j], j < KPT, with
+    LPO = 4H / C lanes per output channel and KPT = H / LPO hidden units per lane (sb_lstm.cu, lstm_ws_kernel)."""
     C = lin.shape[0]
-    nsub = H // C
-    npj = 16 // nsub
+    lpo = 4 * H // C
+    kpt = H // lpo
     t = torch.arange(4 * H)
-    u, kq = t // 4, t % 4
-    j = torch.arange(npj)
-    col = (16 * kq + npj * (u // C)).view(-1, 1) + j.view(1, -1)                 # [4H, NPJ]
-    p = lin.float()[(u % C).view(-1, 1).expand(-1, npj), col]                   # [4H, NPJ]
-    return p.view(4 * H, npj // 4, 4).permute(1, 0, 2).contiguous()
+    col = (kpt * (t % lpo)).view(-1, 1) + torch.arange(kpt).view(1, -1)          # [4H, KPT]
+    p = lin.float()[(t // lpo).view(-1, 1).expand(-1, kpt), col]                # [4H, KPT]
+    return p.view(4 * H, kpt // 4, 4).permute(1, 0, 2).contiguous()
 
 
 class PackedWeights:

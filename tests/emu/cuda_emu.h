@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -65,6 +67,8 @@ struct Block {
     std::vector<std::unique_ptr<std::barrier<>>> wbar;
     std::vector<uint32_t> xch;                  // one exchange slot per thread (warp shuffles)
     std::vector<unsigned char> dyn;             // dynamic shared memory
+    std::map<int, std::unique_ptr<std::barrier<>>> named;   // bar.sync id, count
+    std::mutex mu;
 };
 extern Block* g_block;
 extern thread_local unsigned t_lane, t_warp;
@@ -76,6 +80,18 @@ extern dim3 blockDim, gridDim;
 
 static inline void __syncthreads() { emu::g_block->bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::g_block->wbar[emu::t_warp]->arrive_and_wait(); }
+namespace emu {
+static inline void named_barrier(int id, int nthreads) {       // PTX bar.sync id, nthreads
+    std::barrier<>* b;
+    {
+        std::lock_guard<std::mutex> lock(g_block->mu);
+        auto& slot = g_block->named[id];
+        if (!slot) slot = std::make_unique<std::barrier<>>(nthreads);
+        b = slot.get();
+    }
+    b->arrive_and_wait();
+}
+}   // namespace emu
 
 template <class T> static inline T emu_shfl_idx(T v, int src_lane) {
     static_assert(sizeof(T) == 4, "32-bit shuffles only");
