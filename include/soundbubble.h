@@ -76,9 +76,9 @@ typedef struct sb_lstm_dir {
     const float* b_tile;    /* [4H]       b_ih + b_hh in the same column order                                  */
     const float* w_lane;    /* [(C+H)/4][4H][4]  slot s = 4u+g holds row g*H+u of [W_ih | W_hh], 4 k per float4  */
     const float* b_lane;    /* [4H]       b_ih + b_hh, slot order 4u+g                                           */
-    const float* w_rec;     /* [16][4H] float4: thread t=(u=t/4,kq=t%4), k -> W_hh[g*H+u][16kq+k] for g = 0..3       */
-    const float* w_xp;      /* [C/4][4H] float4: same thread map, k -> W_ih[g*H+u][(C/4)kq+k] for g = 0..3           */
-    const float* w_prj;     /* [(C/4)/4][4H] float4: thread t -> lin[t/(4H/C)][(C/4)(t%(4H/C)) + j], j < C/4         */
+    const float* w_rec;     /* [16][2][2H] float4: thread t=(ur=t/4,kq=t%4), k, A|B -> W_hh[g*H+ur+32(A|B)][16kq+k], g=0..3 */
+    const float* w_xp;      /* [C/4][2][2H] float4: same thread map, k -> W_ih[g*H+unit][(C/4)kq+k] for g = 0..3             */
+    const float* w_prj;     /* [4][2H] float4: thread t -> lin[ur%C][16kq+j], j<16, zero outside its plane ur/C             */
     const float* lin_t;     /* [H][C]     output projection, transposed (this direction's half for the BiLSTM)  */
     const float* lin_n;     /* [C][H]     output projection, natural                                             */
     const float* lin_b;     /* [C]        projection bias (added by direction 0 only)                            */

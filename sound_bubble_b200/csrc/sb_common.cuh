@@ -162,7 +162,7 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
     return ld4(p);
 #else
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
     return r;
@@ -173,7 +173,7 @@ __device__ __forceinline__ float ldg1_stream(const float* p) {
     return *p;
 #else
     float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 #endif
 }

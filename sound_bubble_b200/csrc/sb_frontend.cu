@@ -63,12 +63,28 @@ __global__ void __launch_bounds__(128, 2) stft_features_kernel(const sb_stft_arg
     }
     pdl_trigger();
     pdl_wait();
-    {
+    {   // wave tile: only the samples the valid frames touch are read (float4 when the rows allow it), the rest is zeroed
         const int wvalid = (nvalid - 1) * stride + n_fft;
         const float* wsrc = a.wave + (size_t)b * M * a.n_samples + (size_t)t0 * stride;
-        for (int i = tid; i < M * WT; i += 128) {
-            const int m = i / WT, n = i - m * WT;
-            ws[i] = (n < wvalid) ? ldg1_stream(wsrc + (size_t)m * a.n_samples + n) : 0.0f;
+        const bool vec = ((a.n_samples & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.wave) & 15) == 0);
+        if (vec) {
+            const int q = wvalid / 4;                               // wvalid is a multiple of 4 (stride, n_fft are)
+            for (int i = tid; i < M * q; i += 128) {
+                const int m = i / q, n4 = i - m * q;
+                st4(ws + m * WT + 4 * n4, ldg4_stream(wsrc + (size_t)m * a.n_samples + 4 * n4));
+            }
+        } else {
+            for (int i = tid; i < M * wvalid; i += 128) {
+                const int m = i / wvalid, n = i - m * wvalid;
+                ws[m * WT + n] = ldg1_stream(wsrc + (size_t)m * a.n_samples + n);
+            }
+        }
+        if (wvalid < WT) {
+            const int rest = WT - wvalid;
+            for (int i = tid; i < M * rest; i += 128) {
+                const int m = i / rest, n = i - m * rest;
+                ws[m * WT + wvalid + n] = 0.0f;
+            }
         }
     }
     __syncthreads();

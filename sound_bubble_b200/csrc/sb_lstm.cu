@@ -493,36 +493,39 @@ __global__ void __launch_bounds__(256, 1) lstm_lane_kernel(const SeqArgs a) {
 // =============================================================================================================
 // warp-specialised single-sequence kernel (streaming latency path)
 // =============================================================================================================
-// One sequence (and direction) per CTA, 512 threads.  Warps 0-7 run ONLY the recurrence: thread (u, kq) owns all four
-// gates of hidden unit u over a quarter of the hidden state (k = 16kq .. 16kq+15, 64 weights in registers), so a step
-// moves 4 LDS.128 per thread instead of 16 (shared-memory -> register bandwidth, not FMA issue, bounds the one-column-
-// per-thread kernel), 32 packed FFMA2, a one-level shuffle all-reduce over the four kq lanes, then every lane of the
-// quad evaluates the cell itself (no gate exchange).  They synchronise among themselves with a 256-thread named
-// barrier per step.  Warps 8-15 are helpers that work a GROUP of 4 steps at a time, off the critical path: global
-// loads + FiLM + LayerNorm per block of SB steps, the input part of the gates (x W_ih^T + b) for the next group, the
-// output projection of the previous group, and the residual / bias / store of finished blocks.  The two sides meet at
-// one full barrier per group; gate inputs and hidden states travel through 8-deep rings in shared memory.
+// One sequence (and direction) per CTA, 256 threads.  What bounds a one-sequence LSTM step on an SM is not FMA issue
+// but BYTES INTO REGISTERS: every gate column needs all 64 h values, and shared memory delivers 128 B/clk.  So:
+//   warps 0-3 (recurrence): thread (ur, kq) owns all four gates of TWO hidden units (ur, ur+32) over a quarter of the
+//     hidden state (k = 16kq..16kq+15): 128 weights in registers, 4 LDS.128 feed 64 packed FFMA2 (each loaded h value
+//     is used 8 times -> 8 KB per step instead of 64 KB for one column per thread).  A two-stage shuffle
+//     reduce-scatter over the quad leaves (i,f) of one unit on the even lane and (g,o) on the odd lane; two more
+//     shuffles and the even lane updates c and h.  The projection of step s-1 reuses the h slice already in
+//     registers (16 FMA, no loads).  One 128-thread named barrier per step.
+//   warps 4-7 (helpers), a GROUP of 4 steps at a time, off the critical path: global loads + FiLM + LayerNorm per
+//     block of SB steps, the input part of the gates (x W_ih^T + b) for the next group with the same mapping, and
+//     the bias / residual / store of finished blocks.
+// The two sides meet at one full barrier per group; gate inputs and hidden states travel through 8-deep rings.
 template <int C>
 struct WsCfg {
     static constexpr int H = 64, LPP = C / 4, SB = 256 / LPP, XK = C / 4, HS = 20, G = 4, RING = 8;
-    static constexpr int LPO = 256 / C, KPT = H / LPO;      // projection: lanes per output channel, k per lane
+    static constexpr int NPL = 32 / C;                      // projection planes (threads per output channel and quad)
     static constexpr int xn_off = 0, res_off = 2 * SB * C, outp_off = 4 * SB * C;
-    static constexpr int gx_off = outp_off + 2 * SB * C, hb_off = gx_off + RING * 256;
+    static constexpr int gx_off = outp_off + 2 * NPL * SB * C, hb_off = gx_off + RING * 256;
     static constexpr int smem_floats = hb_off + RING * 4 * HS;
-    static_assert(SB >= 16 && SB % G == 0 && KPT % 4 == 0 && XK % 4 == 0 && 16 % KPT == 0, "block / slice sizes");
+    static_assert(SB >= 32 && SB % (2 * G) == 0 && XK % 4 == 0, "block / slice sizes");
 };
 
 template <int C, bool RAW_H>
-__global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
+__global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
     using Cfg = WsCfg<C>;
-    constexpr int H = Cfg::H, LPP = Cfg::LPP, SB = Cfg::SB, XK = Cfg::XK, HS = Cfg::HS, LPO = Cfg::LPO, KPT = Cfg::KPT;
+    constexpr int H = Cfg::H, LPP = Cfg::LPP, SB = Cfg::SB, XK = Cfg::XK, HS = Cfg::HS, NPL = Cfg::NPL;
     constexpr int G = Cfg::G, RING = Cfg::RING;
     SB_DYN_SMEM(float, smem);
-    float* xn = smem + Cfg::xn_off;         // [2][SB][C]      LayerNorm(x') of the current / next block
-    float* res = smem + Cfg::res_off;       // [2][SB][C]      x' (residual)
-    float* outp = smem + Cfg::outp_off;     // [2][SB][C]      projections of finished steps
-    float* gx = smem + Cfg::gx_off;         // [RING][256]     x W_ih^T + b of step s in slot s % RING (thread slot 4u+g)
-    float* hb = smem + Cfg::hb_off;         // [RING][4][HS]   h_{s-1} in slot s % RING: four 16-float slices padded to 20
+    float* xn = smem + Cfg::xn_off;         // [2][SB][C]        LayerNorm(x') of the current / next block
+    float* res = smem + Cfg::res_off;       // [2][SB][C]        x' (residual)
+    float* outp = smem + Cfg::outp_off;     // [2][NPL][SB][C]   (partial) projections of finished steps
+    float* gx = smem + Cfg::gx_off;         // [RING][64][4]     x W_ih^T + b of step s in slot s % RING: unit, gate
+    float* hb = smem + Cfg::hb_off;         // [RING][4][HS]     h_{s-1} in slot s % RING: four 16-float slices padded to 20
 
     const int tid = threadIdx.x;
     const int dir = blockIdx.y;
@@ -531,34 +534,50 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
     const int row = blockIdx.x;
     const int nblk = (S + SB - 1) / SB;
     const int ngrp = (S + G - 1) / G;
-    const bool recur = tid < 256;                        // warp-uniform role
-    const int t8 = tid & 255;
-    const int u = t8 >> 2, kq = t8 & 3;
+    const bool recur = tid < 128;                        // warp-uniform role
+    const int t7 = tid & 127;
+    const int ur = t7 >> 2, kq = t7 & 3;
+    const bool hi = (kq & 2) != 0, odd = (kq & 1) != 0;
+    const int ux = hi ? ur + 32 : ur;                     // the unit this lane ends up with after the reduce-scatter
+    const int gsl = 4 * ux + (odd ? 2 : 0);               // its two gates: (i,f) on even lanes, (g,o) on odd lanes
 
     if (recur) {
         // ---------------------------------------------------------------------------------------- recurrence warps
-        float4 wr[16];
+        float4 wA[16], wB[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w.w_rec) + k * 256 + t8);
+        for (int k = 0; k < 16; ++k) {
+            wA[k] = __ldg(reinterpret_cast<const float4*>(w.w_rec) + (2 * k) * 128 + t7);
+            wB[k] = __ldg(reinterpret_cast<const float4*>(w.w_rec) + (2 * k + 1) * 128 + t7);
+        }
+        float wp[16];
+        if (!RAW_H) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(w.w_prj) + j4 * 128 + t7);
+                wp[4 * j4] = v.x; wp[4 * j4 + 1] = v.y; wp[4 * j4 + 2] = v.z; wp[4 * j4 + 3] = v.w;
+            }
+        }
+        const int pc = ur % C, ppl = ur / C;             // projection: output channel, plane
         pdl_trigger();
         pdl_wait();
         const bool has0 = a.h0 != nullptr;
-        float c = has0 ? ld_plain(a.c0 + (long long)row * H + u) : 0.0f;
-        float hlast = has0 ? ld_plain(a.h0 + (long long)row * H + u) : 0.0f;
-        const int hslot = (u >> 4) * HS + (u & 15);
-        if (kq == 0) hb[hslot] = hlast;
+        float c = has0 ? ld_plain(a.c0 + (long long)row * H + ux) : 0.0f;       // meaningful on even lanes
+        float hlast = has0 ? ld_plain(a.h0 + (long long)row * H + ux) : 0.0f;
+        const int hslot = (ux >> 4) * HS + (ux & 15);
+        if (!odd) hb[hslot] = hlast;
         float* const outr = a.out[dir];
+        const float act_in = odd ? 2.0f : 1.0f;           // odd lanes: value 0 is the cell gate -> tanh(x) = 2 sigmoid(2x) - 1
+        const float act_mul = odd ? 2.0f : 1.0f, act_add = odd ? -1.0f : 0.0f;
         __syncthreads();                                  // (P) pairs with the helpers' prologue barriers
         __syncthreads();                                  // (Q)
 
         for (int g = 0; g <= ngrp; ++g) {
-            __syncthreads();                              // group barrier: gx of this group is ready, helpers see h of the last
-            if (g == ngrp) break;
+            __syncthreads();                              // group barrier: gx of this group is ready
 #pragma unroll 1
             for (int j = 0; j < G; ++j) {
                 const int s = g * G + j;
-                if (s >= S) break;
-                if (j > 0) bar_sync(1, 256);              // h_{s-1} of every unit is in the ring
+                if (s > S) break;
+                if (j > 0) bar_sync(1, 128);              // h_{s-1} of every unit is in the ring
                 const float* hs = hb + (s & (RING - 1)) * 4 * HS + kq * HS;
                 float hr[16];
 #pragma unroll
@@ -566,61 +585,80 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
                     const float4 v = ld4(hs + 4 * i);
                     hr[4 * i] = v.x; hr[4 * i + 1] = v.y; hr[4 * i + 2] = v.z; hr[4 * i + 3] = v.w;
                 }
-                const float4 g4 = ld4(gx + (s & (RING - 1)) * 256 + 4 * u);
-                float2 a01[2], a23[2];
-                a01[0] = make_float2(0.f, 0.f); a01[1] = a01[0]; a23[0] = a01[0]; a23[1] = a01[0];
+                if (!RAW_H) {                             // projection of step s-1 (h_{s-1} is what was just loaded)
+                    float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    ffma2(a01[k & 1], make_float2(wr[k].x, wr[k].y), hr[k]);
-                    ffma2(a23[k & 1], make_float2(wr[k].z, wr[k].w), hr[k]);
+                    for (int k = 0; k < 16; k += 2) { p0 = fmaf(wp[k], hr[k], p0); p1 = fmaf(wp[k + 1], hr[k + 1], p1); }
+                    float pp = p0 + p1;
+                    pp += __shfl_xor_sync(0xffffffffu, pp, 1);
+                    pp += __shfl_xor_sync(0xffffffffu, pp, 2);
+                    if (kq == 0 && s > 0) {
+                        const int sp = s - 1, bp = sp / SB;
+                        outp[(((bp & 1) * NPL + ppl) * SB + (sp - bp * SB)) * C + pc] = pp;
+                    }
                 }
-                float p[4] = {a01[0].x + a01[1].x, a01[0].y + a01[1].y, a23[0].x + a23[1].x, a23[0].y + a23[1].y};
+                if (s < S) {
+                    const float2 g2 = ld2(gx + (s & (RING - 1)) * 256 + gsl);
+                    float2 aA01[2], aA23[2], aB01[2], aB23[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {             // one-level all-reduce over the quad: three independent shuffles
-                    const float v1 = __shfl_xor_sync(0xffffffffu, p[q], 1);
-                    const float v2 = __shfl_xor_sync(0xffffffffu, p[q], 2);
-                    const float v3 = __shfl_xor_sync(0xffffffffu, p[q], 3);
-                    p[q] = (p[q] + v1) + (v2 + v3);
-                }
-                const float ig = sigmoid_f(p[0] + g4.x);
-                const float fg = sigmoid_f(p[1] + g4.y);
-                const float gg = tanh_f(p[2] + g4.z);
-                const float og = sigmoid_f(p[3] + g4.w);
-                c = fmaf(fg, c, ig * gg);
-                hlast = og * tanh_f(c);
-                if (kq == 0) {
-                    hb[((s + 1) & (RING - 1)) * 4 * HS + hslot] = hlast;
-                    if (RAW_H) {
-                        const int pos = dir ? S - 1 - s : s;
-                        outr[((long long)row * S + pos) * H + u] = hlast;
+                    for (int e = 0; e < 2; ++e) {
+                        aA01[e] = make_float2(0.f, 0.f); aA23[e] = aA01[e]; aB01[e] = aA01[e]; aB23[e] = aA01[e];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        ffma2(aA01[k & 1], make_float2(wA[k].x, wA[k].y), hr[k]);
+                        ffma2(aA23[k & 1], make_float2(wA[k].z, wA[k].w), hr[k]);
+                        ffma2(aB01[k & 1], make_float2(wB[k].x, wB[k].y), hr[k]);
+                        ffma2(aB23[k & 1], make_float2(wB[k].z, wB[k].w), hr[k]);
+                    }
+                    const float A0 = aA01[0].x + aA01[1].x, A1 = aA01[0].y + aA01[1].y;
+                    const float A2 = aA23[0].x + aA23[1].x, A3 = aA23[0].y + aA23[1].y;
+                    const float B0 = aB01[0].x + aB01[1].x, B1 = aB01[0].y + aB01[1].y;
+                    const float B2 = aB23[0].x + aB23[1].x, B3 = aB23[0].y + aB23[1].y;
+                    // stage 1 (xor 2): low half of the quad keeps unit A, high half keeps unit B
+                    float k0 = hi ? B0 : A0, k1 = hi ? B1 : A1, k2 = hi ? B2 : A2, k3 = hi ? B3 : A3;
+                    k0 += __shfl_xor_sync(0xffffffffu, hi ? A0 : B0, 2);
+                    k1 += __shfl_xor_sync(0xffffffffu, hi ? A1 : B1, 2);
+                    k2 += __shfl_xor_sync(0xffffffffu, hi ? A2 : B2, 2);
+                    k3 += __shfl_xor_sync(0xffffffffu, hi ? A3 : B3, 2);
+                    // stage 2 (xor 1): even lane keeps (i, f), odd lane keeps (g, o)
+                    float v0 = odd ? k2 : k0, v1 = odd ? k3 : k1;
+                    v0 += __shfl_xor_sync(0xffffffffu, odd ? k0 : k2, 1);
+                    v1 += __shfl_xor_sync(0xffffffffu, odd ? k1 : k3, 1);
+                    const float act0 = fmaf(sigmoid_f((v0 + g2.x) * act_in), act_mul, act_add);   // sigma(i) | tanh(g)
+                    const float act1 = sigmoid_f(v1 + g2.y);                                      // sigma(f) | sigma(o)
+                    const float tg = __shfl_xor_sync(0xffffffffu, act0, 1);      // even lanes receive tanh(g), sigma(o)
+                    const float so = __shfl_xor_sync(0xffffffffu, act1, 1);
+                    c = fmaf(act1, c, act0 * tg);                                // even: c = sigma(f) c + sigma(i) tanh(g)
+                    hlast = so * tanh_f(c);
+                    if (!odd) {
+                        hb[((s + 1) & (RING - 1)) * 4 * HS + hslot] = hlast;
+                        if (RAW_H) {
+                            const int pos = dir ? S - 1 - s : s;
+                            outr[((long long)row * S + pos) * H + ux] = hlast;
+                        }
                     }
                 }
             }
         }
         __syncthreads();                                  // pairs with the helpers' closing barrier
-        if (kq == 0 && a.hN) {
-            a.hN[(long long)row * H + u] = hlast;
-            a.cN[(long long)row * H + u] = c;
+        if (!odd && a.hN) {
+            a.hN[(long long)row * H + ux] = hlast;
+            a.cN[(long long)row * H + ux] = c;
         }
         return;
     }
 
     // -------------------------------------------------------------------------------------------------- helper warps
-    float4 wx[XK];
+    float4 xA[XK], xB[XK];
 #pragma unroll
-    for (int k = 0; k < XK; ++k) wx[k] = __ldg(reinterpret_cast<const float4*>(w.w_xp) + k * 256 + t8);
-    const float gbias = __ldg(w.b_lane + t8);             // slot 4u+g with g = kq after the reduce-scatter
-    float wp[KPT];                                         // projection role: channel pc, hidden units KPT*ks ..
-    const int pc = t8 / LPO, ks = t8 % LPO;
-    if (!RAW_H) {
-#pragma unroll
-        for (int j4 = 0; j4 < KPT / 4; ++j4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(w.w_prj) + j4 * 256 + t8);
-            wp[4 * j4] = v.x; wp[4 * j4 + 1] = v.y; wp[4 * j4 + 2] = v.z; wp[4 * j4 + 3] = v.w;
-        }
+    for (int k = 0; k < XK; ++k) {
+        xA[k] = __ldg(reinterpret_cast<const float4*>(w.w_xp) + (2 * k) * 128 + t7);
+        xB[k] = __ldg(reinterpret_cast<const float4*>(w.w_xp) + (2 * k + 1) * 128 + t7);
     }
-    const int pslot = ((KPT * ks) >> 4) * HS + ((KPT * ks) & 15);
-    const int pq = t8 / LPP, c4 = t8 % LPP;               // load / LayerNorm / store role: step pq of a block, channels 4c4..
+    const float2 gbias = __ldg(reinterpret_cast<const float2*>(w.b_lane + gsl));
+    // load / LayerNorm / store role: each helper thread serves steps pq and pq + SB/2 of a block, channels 4c4..4c4+3
+    const int pq = t7 / LPP, c4 = t7 % LPP;
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(w.ln_g) + c4);
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.ln_b) + c4);
     float4 blin4 = make_float4(0, 0, 0, 0);
@@ -631,8 +669,7 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
     pdl_trigger();
     pdl_wait();
 
-    auto prefetch = [&](int blk) -> float4 {
-        const int s = blk * SB + pq;
+    auto prefetch1 = [&](int s) -> float4 {
         float4 v = make_float4(0, 0, 0, 0);
         if (s < S) {
             const int pos = dir ? S - 1 - s : s;
@@ -651,33 +688,51 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
         }
         return v;
     };
-    auto phase_a = [&](int blk, const float4 v) {         // LayerNorm(C) of one step by LPP adjacent lanes
-        const float mean = group_sum<LPP>((v.x + v.y) + (v.z + v.w)) * (1.0f / C);
-        const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-        const float var = group_sum<LPP>((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / C);
-        const float rstd = rsqrtf(var + kLnEps);
-        st4(xn + ((blk & 1) * SB + pq) * C + 4 * c4, make_float4(fmaf(dx * rstd, g4.x, b4.x), fmaf(dy * rstd, g4.y, b4.y),
-                                                                  fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w)));
-        if (!RAW_H) st4(res + ((blk & 1) * SB + pq) * C + 4 * c4, v);
+    float4 xpre[2];
+    auto prefetch = [&](int blk) {
+        xpre[0] = prefetch1(blk * SB + pq);
+        xpre[1] = prefetch1(blk * SB + pq + SB / 2);
+    };
+    auto phase_a = [&](int blk) {                         // LayerNorm(C) of one step by LPP adjacent lanes
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float4 v = xpre[e];
+            const int st = pq + e * (SB / 2);
+            const float mean = group_sum<LPP>((v.x + v.y) + (v.z + v.w)) * (1.0f / C);
+            const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+            const float var = group_sum<LPP>((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / C);
+            const float rstd = rsqrtf(var + kLnEps);
+            st4(xn + ((blk & 1) * SB + st) * C + 4 * c4, make_float4(fmaf(dx * rstd, g4.x, b4.x), fmaf(dy * rstd, g4.y, b4.y),
+                                                                      fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w)));
+            if (!RAW_H) st4(res + ((blk & 1) * SB + st) * C + 4 * c4, v);
+        }
     };
     auto phase_c = [&](int blk) {                         // finished block: projection + bias + residual -> global
         if (RAW_H) return;
-        const int s = blk * SB + pq;
-        if (s < S) {
-            float4 v = ld4(outp + ((blk & 1) * SB + pq) * C + 4 * c4);
-            if (dir == 0) {
-                const float4 r = ld4(res + ((blk & 1) * SB + pq) * C + 4 * c4);
-                v.x += blin4.x + r.x; v.y += blin4.y + r.y; v.z += blin4.z + r.z; v.w += blin4.w + r.w;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int st = pq + e * (SB / 2);
+            const int s = blk * SB + st;
+            if (s < S) {
+                float4 v = make_float4(0, 0, 0, 0);
+#pragma unroll
+                for (int q = 0; q < NPL; ++q) {
+                    const float4 t = ld4(outp + (((blk & 1) * NPL + q) * SB + st) * C + 4 * c4);
+                    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                }
+                if (dir == 0) {
+                    const float4 r = ld4(res + ((blk & 1) * SB + st) * C + 4 * c4);
+                    v.x += blin4.x + r.x; v.y += blin4.y + r.y; v.z += blin4.z + r.z; v.w += blin4.w + r.w;
+                }
+                const int pos = dir ? S - 1 - s : s;
+                st4(outp_g + p_base + (long long)pos * a.stride_pos, v);
             }
-            const int pos = dir ? S - 1 - s : s;
-            st4(outp_g + p_base + (long long)pos * a.stride_pos, v);
         }
     };
-    // gx[s] = LN(x_s) W_ih^T + b for the G steps of a group, K split over the 4 kq lanes (G independent chains)
+    // gx[s] = LN(x_s) W_ih^T + b for the G steps of a group: same (two units, K quarter) mapping as the recurrence
     auto x_part_group = [&](int s0) {
         const int blk = s0 / SB;
         const float* xr = xn + ((blk & 1) * SB + (s0 - blk * SB)) * C + XK * kq;
-        float2 a01[G], a23[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             float xv[XK];
@@ -686,59 +741,31 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
                 const float4 v = ld4(xr + j * C + 4 * i);
                 xv[4 * i] = v.x; xv[4 * i + 1] = v.y; xv[4 * i + 2] = v.z; xv[4 * i + 3] = v.w;
             }
-            a01[j] = make_float2(0.f, 0.f); a23[j] = a01[j];
+            float2 aA01 = make_float2(0.f, 0.f), aA23 = aA01, aB01 = aA01, aB23 = aA01;
 #pragma unroll
             for (int k = 0; k < XK; ++k) {
-                ffma2(a01[j], make_float2(wx[k].x, wx[k].y), xv[k]);
-                ffma2(a23[j], make_float2(wx[k].z, wx[k].w), xv[k]);
+                ffma2(aA01, make_float2(xA[k].x, xA[k].y), xv[k]);
+                ffma2(aA23, make_float2(xA[k].z, xA[k].w), xv[k]);
+                ffma2(aB01, make_float2(xB[k].x, xB[k].y), xv[k]);
+                ffma2(aB23, make_float2(xB[k].z, xB[k].w), xv[k]);
             }
-        }
-        const bool hi = (kq & 2) != 0, odd = (kq & 1) != 0;
-#pragma unroll
-        for (int j = 0; j < G; ++j) {                     // reduce-scatter over the quad: lane kq ends with gate kq
-            float k0 = hi ? a23[j].x : a01[j].x, k1 = hi ? a23[j].y : a01[j].y;
-            const float s0v = hi ? a01[j].x : a23[j].x, s1v = hi ? a01[j].y : a23[j].y;
-            k0 += __shfl_xor_sync(0xffffffffu, s0v, 2);
-            k1 += __shfl_xor_sync(0xffffffffu, s1v, 2);
-            float keep = odd ? k1 : k0;
-            const float send = odd ? k0 : k1;
-            keep += __shfl_xor_sync(0xffffffffu, send, 1);
-            if (s0 + j < S) gx[((s0 + j) & (RING - 1)) * 256 + t8] = keep + gbias;
-        }
-    };
-    // out[sp][pc] = lin[pc][:] . h_sp for the G steps of a group; h_sp sits in ring slot (sp + 1) % RING
-    auto project_group = [&](int s0) {
-        if (RAW_H) return;
-        float pp[G];
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-            const float* hp = hb + ((s0 + j + 1) & (RING - 1)) * 4 * HS + pslot;
-            float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-            for (int j4 = 0; j4 < KPT / 4; ++j4) {
-                const float4 v = ld4(hp + 4 * j4);
-                p0 = fmaf(wp[4 * j4], v.x, p0); p1 = fmaf(wp[4 * j4 + 1], v.y, p1);
-                p0 = fmaf(wp[4 * j4 + 2], v.z, p0); p1 = fmaf(wp[4 * j4 + 3], v.w, p1);
-            }
-            pp[j] = p0 + p1;
-        }
-#pragma unroll
-        for (int o = LPO / 2; o > 0; o >>= 1)
-#pragma unroll
-            for (int j = 0; j < G; ++j) pp[j] += __shfl_xor_sync(0xffffffffu, pp[j], o);
-        if (ks == 0) {
-            const int bp = s0 / SB;
-#pragma unroll
-            for (int j = 0; j < G; ++j)
-                if (s0 + j < S) outp[((bp & 1) * SB + (s0 + j - bp * SB)) * C + pc] = pp[j];
+            float k0 = hi ? aB01.x : aA01.x, k1 = hi ? aB01.y : aA01.y, k2 = hi ? aB23.x : aA23.x, k3 = hi ? aB23.y : aA23.y;
+            k0 += __shfl_xor_sync(0xffffffffu, hi ? aA01.x : aB01.x, 2);
+            k1 += __shfl_xor_sync(0xffffffffu, hi ? aA01.y : aB01.y, 2);
+            k2 += __shfl_xor_sync(0xffffffffu, hi ? aA23.x : aB23.x, 2);
+            k3 += __shfl_xor_sync(0xffffffffu, hi ? aA23.y : aB23.y, 2);
+            float v0 = odd ? k2 : k0, v1 = odd ? k3 : k1;
+            v0 += __shfl_xor_sync(0xffffffffu, odd ? k0 : k2, 1);
+            v1 += __shfl_xor_sync(0xffffffffu, odd ? k1 : k3, 1);
+            if (s0 + j < S) st2(gx + ((s0 + j) & (RING - 1)) * 256 + gsl, make_float2(v0 + gbias.x, v1 + gbias.y));
         }
     };
 
-    float4 xpre = prefetch(0);
-    phase_a(0, xpre);
+    prefetch(0);
+    phase_a(0);
     __syncthreads();                                      // (P) xn of block 0 is complete
     x_part_group(0);
-    if (nblk > 1) xpre = prefetch(1);
+    if (nblk > 1) prefetch(1);
     __syncthreads();                                      // (Q) gx of group 0 is complete
     int next_c = 0;
     constexpr int GPB = SB / G;                           // groups per block
@@ -746,9 +773,8 @@ __global__ void __launch_bounds__(512, 1) lstm_ws_kernel(const SeqArgs a) {
         __syncthreads();                                  // group barrier
         const int blk = g / GPB, gb = g - blk * GPB;
         if (g + 1 < ngrp) x_part_group((g + 1) * G);      // needs xn of block (g+1)/GPB: written >= one group barrier ago
-        if (g > 0) project_group((g - 1) * G);
-        if (gb == GPB / 2 - 1 && blk + 1 < nblk) phase_a(blk + 1, xpre);
-        if (gb == GPB / 2 && blk + 2 < nblk) xpre = prefetch(blk + 2);
+        if (gb == GPB / 2 - 1 && blk + 1 < nblk) phase_a(blk + 1);
+        if (gb == GPB / 2 && blk + 2 < nblk) prefetch(blk + 2);
         if (gb == 2 && blk > 0) { phase_c(blk - 1); next_c = blk; }
     }
     __syncthreads();                                      // every projection is in outp
@@ -800,7 +826,7 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
         case SB_ALGO_LANE4:
             return launch("lstm_lane4", lstm_lane_kernel<C, 4, RAW_H>, dim3(ceil_div(a.n_rows, 4), a.n_dirs), dim3(256), 0, st, a);
         case SB_ALGO_WS:
-            return launch("lstm_ws", lstm_ws_kernel<C, RAW_H>, dim3(a.n_rows, a.n_dirs), dim3(512),
+            return launch("lstm_ws", lstm_ws_kernel<C, RAW_H>, dim3(a.n_rows, a.n_dirs), dim3(256),
                           WsCfg<C>::smem_floats * sizeof(float), st, a);
         default: break;
     }

@@ -112,24 +112,32 @@ def _lstm_dir(sd, prefix: str, sfx: str, H: int) -> Dict[str, torch.Tensor]:
     w_lane = w_slot.view(4 * H, K // 4, 4).permute(1, 0, 2).contiguous()     # [K/4][4H][4]
     b_lane = torch.empty(4 * H, dtype=torch.float32, device=w.device)
     b_lane[slot] = b
-    # warp-specialised kernel: thread t = 4u + kq owns the four gates of unit u over a quarter of K
+    # warp-specialised kernel: thread t = 4*ur + kq owns the four gates of units (ur, ur + 32) over a quarter of K
     C = K - H
     w_ih, w_hh = w[:, :C], w[:, C:]
-    w_rec = w_hh.reshape(4, H, 4, 16).permute(3, 1, 2, 0).reshape(16, 4 * H, 4).contiguous()          # [k][t][g]
-    w_xp = w_ih.reshape(4, H, 4, C // 4).permute(3, 1, 2, 0).reshape(C // 4, 4 * H, 4).contiguous()   # [k][t][g]
-    return {"w_tile": w_tile, "b_tile": b_tile, "w_lane": w_lane, "b_lane": b_lane, "w_rec": w_rec, "w_xp": w_xp}
+
+    def two_unit(m, kpt):                                   # m [4H, Kx] -> [kpt][2][128][4] = (k, A|B, thread, gate)
+        v = m.reshape(4, 2, H // 2, 4, kpt)                 # (g, ab, ur, kq, k): unit = ab*32 + ur, column = kq*kpt + k
+        return v.permute(4, 1, 2, 3, 0).reshape(kpt, 2, 2 * H, 4).contiguous()
+    return {"w_tile": w_tile, "b_tile": b_tile, "w_lane": w_lane, "b_lane": b_lane,
+            "w_rec": two_unit(w_hh, 16), "w_xp": two_unit(w_ih, C // 4)}
 
 
 def _proj_ws(lin: torch.Tensor, H: int) -> torch.Tensor:
-    """lin [C, H] -> w_prj [(KPT/4)][4H][4]: helper thread t holds lin[t // LPO][KPT*(t % LPO) + j], j < KPT, with
-    LPO = 4H / C lanes per output channel and KPT = H / LPO hidden units per lane (sb_lstm.cu, lstm_ws_kernel)."""
+    """lin [C, H] -> w_prj [4][128][4]: recurrence thread t = 4*ur + kq holds 16 weights for the h slice it has in
+    registers (k = 16kq + j): lin[ur % C][16kq + j] where j belongs to its plane ur // C, zero elsewhere (the 32/C
+    planes of an output channel are summed when the block is stored; sb_lstm.cu, lstm_ws_kernel)."""
     C = lin.shape[0]
-    lpo = 4 * H // C
-    kpt = H // lpo
-    t = torch.arange(4 * H)
-    col = (kpt * (t % lpo)).view(-1, 1) + torch.arange(kpt).view(1, -1)          # [4H, KPT]
-    p = lin.float()[(t // lpo).view(-1, 1).expand(-1, kpt), col]                # [4H, KPT]
-    return p.view(4 * H, kpt // 4, 4).permute(1, 0, 2).contiguous()
+    npl = 32 // C
+    kpl = 16 // npl
+    t = torch.arange(2 * H)
+    ur, kq = t // 4, t % 4
+    j = torch.arange(16)
+    col = (16 * kq).view(-1, 1) + j.view(1, -1)                                   # [128, 16]
+    p = lin.float()[(ur % C).view(-1, 1).expand(-1, 16), col]
+    mask = (j.view(1, -1) // kpl) == (ur // C).view(-1, 1)
+    p = p * mask.to(p.dtype)
+    return p.view(2 * H, 4, 4).permute(1, 0, 2).contiguous()
 
 
 class PackedWeights:
