@@ -46,6 +46,7 @@ extern "C" {
 #define SB_ALGO_LANE1 2         /* 1 sequence  per CTA, one gate column per thread, weights in registers        */
 #define SB_ALGO_LANE2 3         /* 2 sequences per CTA                                                           */
 #define SB_ALGO_LANE4 4         /* 4 sequences per CTA                                                           */
+#define SB_ALGO_TILE4 6         /* tile family with 4 sequences per warp (C = 32 only; chosen by TILE for 1-2 step calls) */
 #define SB_ALGO_WS    5         /* 1 sequence per CTA, warp-specialised: 8 recurrence warps (K split over 4 lanes, */
                                 /* packed FFMA2) + 8 helper warps (loads, LayerNorm, input gates, stores)          */
 

@@ -30,20 +30,22 @@ __device__ __forceinline__ long long row_base(const SeqArgs& a, int row) {
 // =============================================================================================================
 // tile kernel
 // =============================================================================================================
-template <int C>
+template <int C, int RW_>
 struct TileCfg {
-    static constexpr int H = 64, K = C + H, RW = 8;
+    static constexpr int H = 64, K = C + H, RW = RW_;
     static constexpr int AS = K + ((16 - K % 32 + 32) % 32);    // A row stride: == 16 (mod 32) -> conflict-free stores
     static constexpr int RS = (C == 32) ? 48 : 16;              // residual row stride
     static constexpr int warp_floats = RW * AS + 2 * RW * RS;
     static constexpr size_t smem_floats(int nwarps) { return (size_t)K * 256 + H * C + (size_t)nwarps * warp_floats; }
 };
 
-template <int C, bool RAW_H>
+template <int C, bool RAW_H, int RW_>
 __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
-    using Cfg = TileCfg<C>;
+    using Cfg = TileCfg<C, RW_>;
     constexpr int H = Cfg::H, K = Cfg::K, RW = Cfg::RW, AS = Cfg::AS, RS = Cfg::RS;
-    constexpr int NV = C / 16;              // float4 per lane in the load / LayerNorm mapping (4 lanes per row)
+    constexpr int LPR = 32 / RW;            // lanes per row in the load / LayerNorm mapping
+    constexpr int NV = C / (4 * LPR);       // float4 per lane there: channels (4*LPR)*v + 4*q .. +3
+    static_assert(NV >= 1, "RW = 4 needs C = 32");
     constexpr int ORW = RW * C / 32;        // rows per lane in the projection / output mapping (lane -> channel)
     static_assert(AS % 32 == 16 && AS % 4 == 0, "A stride");
     SB_DYN_SMEM(float, smem);
@@ -75,30 +77,30 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
     float* A = WlT + H * C + warp * Cfg::warp_floats;      // [RW][AS]: cols 0..C-1 = LN(x_s), C..K-1 = h_{s-1}
     float* res = A + RW * AS;                               // [2][RW][RS] x' kept for the residual
 
-    // ---- load / LayerNorm mapping: lane -> (row lr, channel group q): channels 16*v + 4*q .. +3 ------------------
-    const int lr = lane >> 2, q = lane & 3;
+    // ---- load / LayerNorm mapping: lane -> (row lr, channel group q): channels 4*LPR*v + 4*q .. +3 ---------------
+    const int lr = lane / LPR, q = lane % LPR;
     const int lrow = min(row0 + lr, a.n_rows - 1);
     const long long lbase = row_base(a, lrow) + 4 * q;
     const long long fbase = (long long)(lrow / a.film_row_div) * S * C + 4 * q;
     float4 g4[NV], b4[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-        g4[v] = __ldg(reinterpret_cast<const float4*>(w.ln_g + 16 * v) + q);
-        b4[v] = __ldg(reinterpret_cast<const float4*>(w.ln_b + 16 * v) + q);
+        g4[v] = __ldg(reinterpret_cast<const float4*>(w.ln_g + 4 * LPR * v) + q);
+        b4[v] = __ldg(reinterpret_cast<const float4*>(w.ln_b + 4 * LPR * v) + q);
     }
     auto load_x = [&](int step, float4 (&xv)[NV]) {
         const int pos = dir ? S - 1 - step : step;
         const long long off = lbase + (long long)pos * a.stride_pos;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            float4 t = ldg4_stream(a.x0 + off + 16 * v);
+            float4 t = ldg4_stream(a.x0 + off + 4 * LPR * v);
             if (a.x1) {
-                const float4 u = ldg4_stream(a.x1 + off + 16 * v);
+                const float4 u = ldg4_stream(a.x1 + off + 4 * LPR * v);
                 t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
             }
             if (a.film_scale) {
-                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + fbase + (long long)pos * C + 16 * v));
-                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + fbase + (long long)pos * C + 16 * v));
+                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + fbase + (long long)pos * C + 4 * LPR * v));
+                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + fbase + (long long)pos * C + 4 * LPR * v));
                 t.x = fmaf(t.x, fs.x, fb.x); t.y = fmaf(t.y, fs.y, fb.y);
                 t.z = fmaf(t.z, fs.z, fb.z); t.w = fmaf(t.w, fs.w, fb.w);
             }
@@ -109,14 +111,14 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
         float s1 = 0.f;
 #pragma unroll
         for (int v = 0; v < NV; ++v) s1 += (xv[v].x + xv[v].y) + (xv[v].z + xv[v].w);
-        const float mean = group_sum<4>(s1) * (1.0f / C);
+        const float mean = group_sum<LPR>(s1) * (1.0f / C);
         float s2 = 0.f;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const float dx = xv[v].x - mean, dy = xv[v].y - mean, dz = xv[v].z - mean, dw = xv[v].w - mean;
             s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
         }
-        const float rstd = rsqrtf(group_sum<4>(s2) * (1.0f / C) + kLnEps);
+        const float rstd = rsqrtf(group_sum<LPR>(s2) * (1.0f / C) + kLnEps);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             float4 n;
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
             n.y = fmaf((xv[v].y - mean) * rstd, g4[v].y, b4[v].y);
             n.z = fmaf((xv[v].z - mean) * rstd, g4[v].z, b4[v].z);
             n.w = fmaf((xv[v].w - mean) * rstd, g4[v].w, b4[v].w);
-            st4(A + lr * AS + 16 * v + 4 * q, n);
-            if (!RAW_H) st4(res + (slot * RW + lr) * RS + 16 * v + 4 * q, xv[v]);
+            st4(A + lr * AS + 4 * LPR * v + 4 * q, n);
+            if (!RAW_H) st4(res + (slot * RW + lr) * RS + 4 * LPR * v + 4 * q, xv[v]);
         }
     };
 
@@ -811,13 +813,24 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
     const int sms = sm_count();
     if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sms);
     switch (algo) {
+        case SB_ALGO_TILE4:
         case SB_ALGO_TILE: {
-            const int tasks = ceil_div(a.n_rows, 8);
+            // 8 sequences per warp; 4 when the call is a step or two long (streaming inter path) and rows are few enough
+            // that halving a warp's serial work beats the lower FMA : shared-memory-load ratio
+            const bool small = C == 32 && (algo == SB_ALGO_TILE4 ||
+                                          (a.n_steps <= 2 && ceil_div(a.n_rows, 4) * a.n_dirs <= 8 * sms));
+            const int rw = small ? 4 : 8;
+            const int tasks = ceil_div(a.n_rows, rw);
             int nw = ceil_div(tasks * a.n_dirs, sms);
             nw = nw < 1 ? 1 : (nw > 8 ? 8 : nw);
             dim3 grid(ceil_div(tasks, nw), a.n_dirs);
-            return launch("lstm_tile", lstm_tile_kernel<C, RAW_H>, grid, dim3(32 * nw),
-                          TileCfg<C>::smem_floats(nw) * sizeof(float), st, a);
+            if constexpr (C == 32) {
+                if (small)
+                    return launch("lstm_tile4", lstm_tile_kernel<C, RAW_H, 4>, grid, dim3(32 * nw),
+                                  TileCfg<C, 4>::smem_floats(nw) * sizeof(float), st, a);
+            }
+            return launch("lstm_tile", lstm_tile_kernel<C, RAW_H, 8>, grid, dim3(32 * nw),
+                          TileCfg<C, 8>::smem_floats(nw) * sizeof(float), st, a);
         }
         case SB_ALGO_LANE1:
             return launch("lstm_lane1", lstm_lane_kernel<C, 1, RAW_H>, dim3(a.n_rows, a.n_dirs), dim3(256), 0, st, a);

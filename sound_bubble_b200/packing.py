@@ -146,6 +146,8 @@ class PackedWeights:
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: ModelConfig, device):
         self.cfg = cfg
         pieces: List[Tuple[str, torch.Tensor]] = []
+        # re-pack on the host (0.5 M parameters, index plumbing only), then ship one flat buffer to the device
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
 
         def add(name: str, t: torch.Tensor):
             pieces.append((name, t.detach().to(torch.float32).contiguous().reshape(-1)))
