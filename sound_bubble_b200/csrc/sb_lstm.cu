@@ -573,75 +573,88 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
         __syncthreads();                                  // (P) pairs with the helpers' prologue barriers
         __syncthreads();                                  // (Q)
 
-        for (int g = 0; g <= ngrp; ++g) {
+        // projection of step sp from the h slice already in registers: 16 FMA, a quad reduction, one predicated store
+        auto project = [&](const float (&hr)[16], int sp, bool store) {
+            float p0 = wp[0] * hr[0], p1 = wp[1] * hr[1], p2 = wp[2] * hr[2], p3 = wp[3] * hr[3];
+#pragma unroll
+            for (int k = 4; k < 16; k += 4) {
+                p0 = fmaf(wp[k], hr[k], p0); p1 = fmaf(wp[k + 1], hr[k + 1], p1);
+                p2 = fmaf(wp[k + 2], hr[k + 2], p2); p3 = fmaf(wp[k + 3], hr[k + 3], p3);
+            }
+            float pp = (p0 + p1) + (p2 + p3);
+            pp += __shfl_xor_sync(0xffffffffu, pp, 1);
+            pp += __shfl_xor_sync(0xffffffffu, pp, 2);
+            if (store && kq == 0) {
+                const int bp = sp / SB;
+                outp[(((bp & 1) * NPL + ppl) * SB + (sp - bp * SB)) * C + pc] = pp;
+            }
+        };
+        auto load_h = [&](int s, float (&hr)[16]) {
+            const float* hs = hb + (s & (RING - 1)) * 4 * HS + kq * HS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = ld4(hs + 4 * i);
+                hr[4 * i] = v.x; hr[4 * i + 1] = v.y; hr[4 * i + 2] = v.z; hr[4 * i + 3] = v.w;
+            }
+        };
+
+        for (int g = 0; g < ngrp; ++g) {
             __syncthreads();                              // group barrier: gx of this group is ready
 #pragma unroll 1
             for (int j = 0; j < G; ++j) {
                 const int s = g * G + j;
-                if (s > S) break;
+                if (s >= S) break;
                 if (j > 0) bar_sync(1, 128);              // h_{s-1} of every unit is in the ring
-                const float* hs = hb + (s & (RING - 1)) * 4 * HS + kq * HS;
                 float hr[16];
+                load_h(s, hr);
+                const float2 g2 = ld2(gx + (s & (RING - 1)) * 256 + gsl);
+                float2 aA01[2], aA23[2], aB01[2], aB23[2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = ld4(hs + 4 * i);
-                    hr[4 * i] = v.x; hr[4 * i + 1] = v.y; hr[4 * i + 2] = v.z; hr[4 * i + 3] = v.w;
+                for (int e = 0; e < 2; ++e) {
+                    aA01[e] = make_float2(0.f, 0.f); aA23[e] = aA01[e]; aB01[e] = aA01[e]; aB23[e] = aA01[e];
                 }
-                if (!RAW_H) {                             // projection of step s-1 (h_{s-1} is what was just loaded)
-                    float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 16; k += 2) { p0 = fmaf(wp[k], hr[k], p0); p1 = fmaf(wp[k + 1], hr[k + 1], p1); }
-                    float pp = p0 + p1;
-                    pp += __shfl_xor_sync(0xffffffffu, pp, 1);
-                    pp += __shfl_xor_sync(0xffffffffu, pp, 2);
-                    if (kq == 0 && s > 0) {
-                        const int sp = s - 1, bp = sp / SB;
-                        outp[(((bp & 1) * NPL + ppl) * SB + (sp - bp * SB)) * C + pc] = pp;
-                    }
+                for (int k = 0; k < 16; ++k) {
+                    ffma2(aA01[k & 1], make_float2(wA[k].x, wA[k].y), hr[k]);
+                    ffma2(aA23[k & 1], make_float2(wA[k].z, wA[k].w), hr[k]);
+                    ffma2(aB01[k & 1], make_float2(wB[k].x, wB[k].y), hr[k]);
+                    ffma2(aB23[k & 1], make_float2(wB[k].z, wB[k].w), hr[k]);
                 }
-                if (s < S) {
-                    const float2 g2 = ld2(gx + (s & (RING - 1)) * 256 + gsl);
-                    float2 aA01[2], aA23[2], aB01[2], aB23[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        aA01[e] = make_float2(0.f, 0.f); aA23[e] = aA01[e]; aB01[e] = aA01[e]; aB23[e] = aA01[e];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        ffma2(aA01[k & 1], make_float2(wA[k].x, wA[k].y), hr[k]);
-                        ffma2(aA23[k & 1], make_float2(wA[k].z, wA[k].w), hr[k]);
-                        ffma2(aB01[k & 1], make_float2(wB[k].x, wB[k].y), hr[k]);
-                        ffma2(aB23[k & 1], make_float2(wB[k].z, wB[k].w), hr[k]);
-                    }
-                    const float A0 = aA01[0].x + aA01[1].x, A1 = aA01[0].y + aA01[1].y;
-                    const float A2 = aA23[0].x + aA23[1].x, A3 = aA23[0].y + aA23[1].y;
-                    const float B0 = aB01[0].x + aB01[1].x, B1 = aB01[0].y + aB01[1].y;
-                    const float B2 = aB23[0].x + aB23[1].x, B3 = aB23[0].y + aB23[1].y;
-                    // stage 1 (xor 2): low half of the quad keeps unit A, high half keeps unit B
-                    float k0 = hi ? B0 : A0, k1 = hi ? B1 : A1, k2 = hi ? B2 : A2, k3 = hi ? B3 : A3;
-                    k0 += __shfl_xor_sync(0xffffffffu, hi ? A0 : B0, 2);
-                    k1 += __shfl_xor_sync(0xffffffffu, hi ? A1 : B1, 2);
-                    k2 += __shfl_xor_sync(0xffffffffu, hi ? A2 : B2, 2);
-                    k3 += __shfl_xor_sync(0xffffffffu, hi ? A3 : B3, 2);
-                    // stage 2 (xor 1): even lane keeps (i, f), odd lane keeps (g, o)
-                    float v0 = odd ? k2 : k0, v1 = odd ? k3 : k1;
-                    v0 += __shfl_xor_sync(0xffffffffu, odd ? k0 : k2, 1);
-                    v1 += __shfl_xor_sync(0xffffffffu, odd ? k1 : k3, 1);
-                    const float act0 = fmaf(sigmoid_f((v0 + g2.x) * act_in), act_mul, act_add);   // sigma(i) | tanh(g)
-                    const float act1 = sigmoid_f(v1 + g2.y);                                      // sigma(f) | sigma(o)
-                    const float tg = __shfl_xor_sync(0xffffffffu, act0, 1);      // even lanes receive tanh(g), sigma(o)
-                    const float so = __shfl_xor_sync(0xffffffffu, act1, 1);
-                    c = fmaf(act1, c, act0 * tg);                                // even: c = sigma(f) c + sigma(i) tanh(g)
-                    hlast = so * tanh_f(c);
-                    if (!odd) {
-                        hb[((s + 1) & (RING - 1)) * 4 * HS + hslot] = hlast;
-                        if (RAW_H) {
-                            const int pos = dir ? S - 1 - s : s;
-                            outr[((long long)row * S + pos) * H + ux] = hlast;
-                        }
+                const float A0 = aA01[0].x + aA01[1].x, A1 = aA01[0].y + aA01[1].y;
+                const float A2 = aA23[0].x + aA23[1].x, A3 = aA23[0].y + aA23[1].y;
+                const float B0 = aB01[0].x + aB01[1].x, B1 = aB01[0].y + aB01[1].y;
+                const float B2 = aB23[0].x + aB23[1].x, B3 = aB23[0].y + aB23[1].y;
+                // stage 1 (xor 2): low half of the quad keeps unit A, high half keeps unit B
+                float k0 = hi ? B0 : A0, k1 = hi ? B1 : A1, k2 = hi ? B2 : A2, k3 = hi ? B3 : A3;
+                k0 += __shfl_xor_sync(0xffffffffu, hi ? A0 : B0, 2);
+                k1 += __shfl_xor_sync(0xffffffffu, hi ? A1 : B1, 2);
+                k2 += __shfl_xor_sync(0xffffffffu, hi ? A2 : B2, 2);
+                k3 += __shfl_xor_sync(0xffffffffu, hi ? A3 : B3, 2);
+                if (!RAW_H) project(hr, s - 1, s > 0);    // rides in the shadow of the gate shuffles
+                // stage 2 (xor 1): even lane keeps (i, f), odd lane keeps (g, o)
+                float v0 = odd ? k2 : k0, v1 = odd ? k3 : k1;
+                v0 += __shfl_xor_sync(0xffffffffu, odd ? k0 : k2, 1);
+                v1 += __shfl_xor_sync(0xffffffffu, odd ? k1 : k3, 1);
+                const float act0 = fmaf(sigmoid_f((v0 + g2.x) * act_in), act_mul, act_add);   // sigma(i) | tanh(g)
+                const float act1 = sigmoid_f(v1 + g2.y);                                      // sigma(f) | sigma(o)
+                const float tg = __shfl_xor_sync(0xffffffffu, act0, 1);      // even lanes receive tanh(g), sigma(o)
+                const float so = __shfl_xor_sync(0xffffffffu, act1, 1);
+                c = fmaf(act1, c, act0 * tg);                                // even: c = sigma(f) c + sigma(i) tanh(g)
+                hlast = so * tanh_f(c);
+                if (!odd) {
+                    hb[((s + 1) & (RING - 1)) * 4 * HS + hslot] = hlast;
+                    if (RAW_H) {
+                        const int pos = dir ? S - 1 - s : s;
+                        outr[((long long)row * S + pos) * H + ux] = hlast;
                     }
                 }
             }
+        }
+        __syncthreads();                                  // h_{S-1} is in the ring (pairs with the helpers' last group barrier)
+        if (!RAW_H) {
+            float hr[16];
+            load_h(S, hr);
+            project(hr, S - 1, true);
         }
         __syncthreads();                                  // pairs with the helpers' closing barrier
         if (!odd && a.hN) {
