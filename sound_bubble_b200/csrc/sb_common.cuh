@@ -180,20 +180,32 @@ __device__ __forceinline__ float ldg1_stream(const float* p) {
 // plain (coherent) loads for buffers an aliasing output of the same launch may point at
 __device__ __forceinline__ float ld_plain(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
 
-// Cooperative global -> shared copy of n4 float4 with 8 independent 16-byte loads in flight per thread (a plain
-// load/store loop leaves one L2 round trip per iteration on the critical path of every prologue).
+// Asynchronous global -> shared copies (LDGSTS): every copy of a staging loop is in flight at once instead of one L2
+// round trip per loop iteration; cp_async_wait_all() before the __syncthreads() that publishes the tile.
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gsrc) {
+#ifdef SB_EMU
+    *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gsrc);
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc) {
+#ifdef SB_EMU
+    *smem_dst = *gsrc;
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef SB_EMU
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// cooperative copy of n4 float4 (16-byte aligned both sides); complete after cp_async_wait_all() + a barrier
 __device__ __forceinline__ void stage_f4(float* dst, const float* src, int n4, int tid, int nthreads) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    int i = tid;
-    for (; i + 7 * nthreads < n4; i += 8 * nthreads) {
-        float4 v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(s4 + i + j * nthreads);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d4[i + j * nthreads] = v[j];
-    }
-    for (; i < n4; i += nthreads) d4[i] = __ldg(s4 + i);
+    for (int i = tid; i < n4; i += nthreads) cp_async_16(dst + 4 * i, src + 4 * i);
 }
 
 template <int WIDTH>

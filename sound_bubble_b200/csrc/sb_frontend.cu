@@ -35,57 +35,37 @@ __global__ void __launch_bounds__(128, 2) stft_features_kernel(const sb_stft_arg
     const int nvalid = min(kStftTT, a.T - t0);
     const int nf = min(kStftFC, F - f0);
 
-    // basis chunk (constant data), 4 independent 16-byte loads in flight per thread
+    // basis chunk (constant data): warp w stages rows w, w+4, ... with asynchronous 16-byte copies (all in flight)
     {
-        const int q = n_fft / 4, total = 2 * kStftFC * q;
-        for (int i0 = tid; i0 < total; i0 += 4 * 128) {
-            float4 v[4];
-            int dsti[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = i0 + j * 128;
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                dsti[j] = -1;
-                if (i < total) {
-                    const int row = i / q, k4 = i - row * q;
-                    const int ff = row & (kStftFC - 1);
-                    dsti[j] = row * BS + 4 * k4;
-                    if (ff < nf) {
-                        const int grow = (row < kStftFC) ? f0 + ff : F + f0 + ff;
-                        v[j] = __ldg(reinterpret_cast<const float4*>(a.filt + (size_t)grow * n_fft) + k4);
-                    }
-                }
+        const int q = n_fft / 4;
+        for (int row = warp; row < 2 * kStftFC; row += 4) {
+            const int ff = row & (kStftFC - 1);
+            float* dst = bs + row * BS;
+            if (ff < nf) {
+                const float* src = a.filt + (size_t)((row < kStftFC) ? f0 + ff : F + f0 + ff) * n_fft;
+                for (int k4 = lane; k4 < q; k4 += 32) cp_async_16(dst + 4 * k4, src + 4 * k4);
+            } else {
+                for (int k4 = lane; k4 < q; k4 += 32) st4(dst + 4 * k4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (dsti[j] >= 0) st4(bs + dsti[j], v[j]);
         }
     }
     pdl_trigger();
     pdl_wait();
-    {   // wave tile: only the samples the valid frames touch are read (float4 when the rows allow it), the rest is zeroed
+    {   // wave tile: only the samples the valid frames touch are read; what lies beyond feeds frames that are never
+        // stored, so it is left as is.  Warp w stages microphones w, w+4, ...
         const int wvalid = (nvalid - 1) * stride + n_fft;
         const float* wsrc = a.wave + (size_t)b * M * a.n_samples + (size_t)t0 * stride;
         const bool vec = ((a.n_samples & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.wave) & 15) == 0);
-        if (vec) {
-            const int q = wvalid / 4;                               // wvalid is a multiple of 4 (stride, n_fft are)
-            for (int i = tid; i < M * q; i += 128) {
-                const int m = i / q, n4 = i - m * q;
-                st4(ws + m * WT + 4 * n4, ldg4_stream(wsrc + (size_t)m * a.n_samples + 4 * n4));
-            }
-        } else {
-            for (int i = tid; i < M * wvalid; i += 128) {
-                const int m = i / wvalid, n = i - m * wvalid;
-                ws[m * WT + n] = ldg1_stream(wsrc + (size_t)m * a.n_samples + n);
+        for (int m = warp; m < M; m += 4) {
+            const float* src = wsrc + (size_t)m * a.n_samples;
+            float* dst = ws + m * WT;
+            if (vec) {
+                for (int n4 = lane; n4 < wvalid / 4; n4 += 32) cp_async_16(dst + 4 * n4, src + 4 * n4);
+            } else {
+                for (int n = lane; n < wvalid; n += 32) cp_async_4(dst + n, src + n);
             }
         }
-        if (wvalid < WT) {
-            const int rest = WT - wvalid;
-            for (int i = tid; i < M * rest; i += 128) {
-                const int m = i / rest, n = i - m * rest;
-                ws[m * WT + wvalid + n] = 0.0f;
-            }
-        }
+        cp_async_wait_all();
     }
     __syncthreads();
 
@@ -225,25 +205,32 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
 
     const int nfr = nvalid + 2;
     const int ncol = nf + 2;
-    for (int fr = 0; fr < nfr; ++fr) {
+    const int nwarps = blockDim.x >> 5, warp = tid >> 5, lane = tid & 31;
+    for (int fr = 0; fr < nfr; ++fr) {                          // asynchronous 4-byte copies: a transposing gather
         const int ft = t0 - 2 + fr;
         float* dst = in_s + fr * Cin * FP;
         if (ft >= 0) {
             const float* src = a.feats + (size_t)(b * a.T + ft) * F * Cin;
-            for (int i = tid; i < ncol * Cin; i += blockDim.x) {
-                const int j = i / Cin, c = i - j * Cin;
+            for (int j = warp; j < ncol; j += nwarps) {         // one bin (Cin contiguous floats in global) per warp pass
                 const int f = f0 - 1 + j;
-                dst[c * FP + j] = (f >= 0 && f < F) ? ldg1_stream(src + (size_t)f * Cin + c) : 0.0f;
+                if (f >= 0 && f < F) {
+                    for (int c = lane; c < Cin; c += 32) cp_async_4(dst + c * FP + j, src + (size_t)f * Cin + c);
+                } else {
+                    for (int c = lane; c < Cin; c += 32) dst[c * FP + j] = 0.0f;
+                }
             }
         } else {
             const float* src = a.conv_buf_in + (size_t)b * Cin * 2 * F + (size_t)(2 + ft) * F;
-            for (int i = tid; i < ncol * Cin; i += blockDim.x) {
-                const int c = i / ncol, j = i - c * ncol;
-                const int f = f0 - 1 + j;
-                dst[c * FP + j] = (f >= 0 && f < F) ? ldg1_stream(src + (size_t)c * 2 * F + f) : 0.0f;
+            for (int c = warp; c < Cin; c += nwarps) {          // one channel row (bins contiguous in global) per warp pass
+                for (int j = lane; j < ncol; j += 32) {
+                    const int f = f0 - 1 + j;
+                    if (f >= 0 && f < F) cp_async_4(dst + c * FP + j, src + (size_t)c * 2 * F + f);
+                    else dst[c * FP + j] = 0.0f;
+                }
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const int n_items = nvalid * nf * NOG;

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
         bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
     }
     pdl_trigger();
+    cp_async_wait_all();
     __syncthreads();                        // the only block-wide barrier
     pdl_wait();
 
@@ -497,13 +498,13 @@ __global__ void __launch_bounds__(256, 1) lstm_lane_kernel(const SeqArgs a) {
 // =============================================================================================================
 // One sequence (and direction) per CTA, 256 threads.  What bounds a one-sequence LSTM step on an SM is not FMA issue
 // but BYTES INTO REGISTERS: every gate column needs all 64 h values, and shared memory delivers 128 B/clk.  So:
-//   warps 0-3 (recurrence): thread (ur, kq) owns all four gates of TWO hidden units (ur, ur+32) over a quarter of the
+//   warps 4-7 (recurrence): thread (ur, kq) owns all four gates of TWO hidden units (ur, ur+32) over a quarter of the
 //     hidden state (k = 16kq..16kq+15): 128 weights in registers, 4 LDS.128 feed 64 packed FFMA2 (each loaded h value
 //     is used 8 times -> 8 KB per step instead of 64 KB for one column per thread).  A two-stage shuffle
 //     reduce-scatter over the quad leaves (i,f) of one unit on the even lane and (g,o) on the odd lane; two more
 //     shuffles and the even lane updates c and h.  The projection of step s-1 reuses the h slice already in
 //     registers (16 FMA, no loads).  One 128-thread named barrier per step.
-//   warps 4-7 (helpers), a GROUP of 4 steps at a time, off the critical path: global loads + FiLM + LayerNorm per
+//   warps 0-3 (helpers), a GROUP of 4 steps at a time, off the critical path: global loads + FiLM + LayerNorm per
 //     block of SB steps, the input part of the gates (x W_ih^T + b) for the next group with the same mapping, and
 //     the bias / residual / store of finished blocks.
 // The two sides meet at one full barrier per group; gate inputs and hidden states travel through 8-deep rings.
@@ -536,7 +537,8 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
     const int row = blockIdx.x;
     const int nblk = (S + SB - 1) / SB;
     const int ngrp = (S + G - 1) / G;
-    const bool recur = tid < 128;                        // warp-uniform role
+    const bool recur = tid >= 128;                       // warp-uniform role; the recurrence gets the higher warp ids,
+                                                         // which the issue arbiter favours when both sides are ready
     const int t7 = tid & 127;
     const int ur = t7 >> 2, kq = t7 & 3;
     const bool hi = (kq & 2) != 0, odd = (kq & 1) != 0;
@@ -624,17 +626,20 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
                 const float A2 = aA23[0].x + aA23[1].x, A3 = aA23[0].y + aA23[1].y;
                 const float B0 = aB01[0].x + aB01[1].x, B1 = aB01[0].y + aB01[1].y;
                 const float B2 = aB23[0].x + aB23[1].x, B3 = aB23[0].y + aB23[1].y;
-                // stage 1 (xor 2): low half of the quad keeps unit A, high half keeps unit B
-                float k0 = hi ? B0 : A0, k1 = hi ? B1 : A1, k2 = hi ? B2 : A2, k3 = hi ? B3 : A3;
-                k0 += __shfl_xor_sync(0xffffffffu, hi ? A0 : B0, 2);
-                k1 += __shfl_xor_sync(0xffffffffu, hi ? A1 : B1, 2);
-                k2 += __shfl_xor_sync(0xffffffffu, hi ? A2 : B2, 2);
-                k3 += __shfl_xor_sync(0xffffffffu, hi ? A3 : B3, 2);
+                // one-level reduce-scatter over the quad: this lane finishes (unit hi ? B : A, gates odd ? (g,o) : (i,f)); every
+                // partner sends the pair its reader wants: xor 1 = same unit / other pair, xor 2 = other unit / same pair,
+                // xor 3 = other unit / other pair.  Six independent shuffles, one latency level.
+                const float m0 = hi ? B0 : A0, m1 = hi ? B1 : A1, m2 = hi ? B2 : A2, m3 = hi ? B3 : A3;     // my unit
+                const float o0 = hi ? A0 : B0, o1 = hi ? A1 : B1, o2 = hi ? A2 : B2, o3 = hi ? A3 : B3;     // the other unit
+                const float r1a = __shfl_xor_sync(0xffffffffu, odd ? m0 : m2, 1);
+                const float r1b = __shfl_xor_sync(0xffffffffu, odd ? m1 : m3, 1);
+                const float r2a = __shfl_xor_sync(0xffffffffu, odd ? o2 : o0, 2);
+                const float r2b = __shfl_xor_sync(0xffffffffu, odd ? o3 : o1, 2);
+                const float r3a = __shfl_xor_sync(0xffffffffu, odd ? o0 : o2, 3);
+                const float r3b = __shfl_xor_sync(0xffffffffu, odd ? o1 : o3, 3);
                 if (!RAW_H) project(hr, s - 1, s > 0);    // rides in the shadow of the gate shuffles
-                // stage 2 (xor 1): even lane keeps (i, f), odd lane keeps (g, o)
-                float v0 = odd ? k2 : k0, v1 = odd ? k3 : k1;
-                v0 += __shfl_xor_sync(0xffffffffu, odd ? k0 : k2, 1);
-                v1 += __shfl_xor_sync(0xffffffffu, odd ? k1 : k3, 1);
+                const float v0 = ((odd ? m2 : m0) + r1a) + (r2a + r3a);
+                const float v1 = ((odd ? m3 : m1) + r1b) + (r2b + r3b);
                 const float act0 = fmaf(sigmoid_f((v0 + g2.x) * act_in), act_mul, act_add);   // sigma(i) | tanh(g)
                 const float act1 = sigmoid_f(v1 + g2.y);                                      // sigma(f) | sigma(o)
                 const float tg = __shfl_xor_sync(0xffffffffu, act0, 1);      // even lanes receive tanh(g), sigma(o)
