@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pdl", type=int, default=int(os.environ.get("SB_PDL", "0")))
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("SB_PDL", "1")))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(128, 2) stft_features_kernel(const sb_stft_arg
     const float eps = 1e-6f;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        if (!writer) continue;
         const int tt = 2 * fpair + j;
+        if (!writer || tt >= nvalid) continue;            // frames past the end of the call are never stored
         float* o = fs + (tt * kStftFC + lane) * Cin;
 #pragma unroll
         for (int m = 0; m < M; ++m) { o[m] = re[j][m]; o[M + m] = im[j][m]; }
@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
         for (int kt = 0; kt < 3; ++kt) {
             const float* ip = in_s + (tt + kt) * Cin * FP + fl;
             const float* wp = w_s + (kt * Cin * 3) * C + og * 8;
+#pragma unroll 3
             for (int c = 0; c < Cin; ++c) {
 #pragma unroll
                 for (int kf = 0; kf < 3; ++kf) {
