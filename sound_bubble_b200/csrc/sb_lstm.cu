@@ -835,15 +835,11 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
         case SB_ALGO_TILE: {
             // 8 sequences per warp; 4 when the call is a step or two long (streaming inter path) and rows are few enough
             // that halving a warp's serial work beats the lower FMA : shared-memory-load ratio
-            // Under programmatic dependent launch a one-step call prefers FEW fat CTAs (8 warps x 8 rows): they fit on the
-            // SMs the preceding single-sequence kernel leaves idle, so their weight staging overlaps it, and they leave
-            // SMs free for the next kernel's prologue in turn.
             const bool short_call = a.n_steps <= 2 && ceil_div(a.n_rows, 4) * a.n_dirs <= 8 * sms;
-            const bool small = C == 32 && (algo == SB_ALGO_TILE4 || (short_call && !pdl_enabled()));
+            const bool small = C == 32 && (algo == SB_ALGO_TILE4 || short_call);
             const int rw = small ? 4 : 8;
             const int tasks = ceil_div(a.n_rows, rw);
             int nw = ceil_div(tasks * a.n_dirs, sms);
-            if (short_call && pdl_enabled() && algo != SB_ALGO_TILE4) nw = 8;
             nw = nw < 1 ? 1 : (nw > 8 ? 8 : nw);
             dim3 grid(ceil_div(tasks, nw), a.n_dirs);
             if constexpr (C == 32) {
