@@ -47,6 +47,8 @@ extern "C" {
 #define SB_ALGO_LANE2 3         /* 2 sequences per CTA                                                           */
 #define SB_ALGO_LANE4 4         /* 4 sequences per CTA                                                           */
 #define SB_ALGO_TILE4 6         /* tile family with 4 sequences per warp (C = 32 only; chosen by TILE for 1-2 step calls) */
+#define SB_ALGO_TC    7         /* tcgen05: 128 sequences per CTA, gate GEMM on the tensor cores as a bf16 hi/lo split   */
+                                /* (3 products, fp32 accumulation in TMEM), cell update from TMEM (C = 32, projected mode) */
 #define SB_ALGO_WS    5         /* 1 sequence per CTA, warp-specialised: 8 recurrence warps (K split over 4 lanes, */
                                 /* packed FFMA2) + 8 helper warps (loads, LayerNorm, input gates, stores)          */
 
@@ -80,6 +82,9 @@ typedef struct sb_lstm_dir {
     const float* w_rec;     /* [16][2][2H] float4: thread t=(ur=t/4,kq=t%4), k, A|B -> W_hh[g*H+ur+32(A|B)][16kq+k], g=0..3 */
     const float* w_xp;      /* [C/4][2][2H] float4: same thread map, k -> W_ih[g*H+unit][(C/4)kq+k] for g = 0..3             */
     const float* w_prj;     /* [4][2H] float4: thread t -> lin[ur%C][16kq+j], j<16, zero outside its plane ur/C             */
+    const float* tc_w;      /* raw bf16 words: gate matrix (rows n = 4u+g, K = C+H) hi then lo, projection [C][H] hi then lo, */
+                            /* each as the no-swizzle K-major UMMA image [K/8][rows/8][8][8]  (lstm_tc_kernel, C = 32)     */
+    const float* tc_b;      /* [4H]       b_ih + b_hh in n = 4u+g order                                          */
     const float* lin_t;     /* [H][C]     output projection, transposed (this direction's half for the BiLSTM)  */
     const float* lin_n;     /* [C][H]     output projection, natural                                             */
     const float* lin_b;     /* [C]        projection bias (added by direction 0 only)                            */

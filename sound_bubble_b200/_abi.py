@@ -8,7 +8,7 @@ SB_VERSION = 100
 SB_MAX_BLOCKS = 16
 SB_MAX_MICS = 8
 
-SB_ALGO_AUTO, SB_ALGO_TILE, SB_ALGO_LANE1, SB_ALGO_LANE2, SB_ALGO_LANE4, SB_ALGO_WS, SB_ALGO_TILE4 = 0, 1, 2, 3, 4, 5, 6
+SB_ALGO_AUTO, SB_ALGO_TILE, SB_ALGO_LANE1, SB_ALGO_LANE2, SB_ALGO_LANE4, SB_ALGO_WS, SB_ALGO_TILE4, SB_ALGO_TC = 0, 1, 2, 3, 4, 5, 6, 7
 SB_FEAT_NONE, SB_FEAT_OMNI, SB_FEAT_DIRECTIONAL = 0, 1, 2
 SB_EMB_CONV, SB_EMB_LINEAR = 0, 1
 SB_CONVLSTM_PADCROP, SB_CONVLSTM_OUTPAD = 0, 1
@@ -19,7 +19,7 @@ fp = C.c_void_p          # device float* (raw address)
 
 
 class LstmDir(C.Structure):
-    _fields_ = [(n, fp) for n in ("w_tile", "b_tile", "w_lane", "b_lane", "w_rec", "w_xp", "w_prj", "lin_t", "lin_n", "lin_b", "ln_g", "ln_b")]
+    _fields_ = [(n, fp) for n in ("w_tile", "b_tile", "w_lane", "b_lane", "w_rec", "w_xp", "w_prj", "tc_w", "tc_b", "lin_t", "lin_n", "lin_b", "ln_g", "ln_b")]
 
 
 class StftArgs(C.Structure):

@@ -21,7 +21,14 @@ struct SeqArgs {
     int film_row_div;
 };
 
+__device__ __forceinline__ long long row_base(const SeqArgs& a, int row) {
+    const int o = row / a.rows_inner;
+    return (long long)o * a.stride_outer + (long long)(row - o * a.rows_inner) * a.stride_inner;
+}
+
 // raw_h = true: write h_t to out[dir] as [row][pos][H] instead of the projected, residual-added activation
 int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t st);
+// tcgen05 variant (sb_lstm_tc.cu): C = 32, H = 64, projected mode only
+int run_seq_tc(const SeqArgs& a, cudaStream_t st);
 
 }  // namespace sb

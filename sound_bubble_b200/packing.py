@@ -123,6 +123,36 @@ def _lstm_dir(sd, prefix: str, sfx: str, H: int) -> Dict[str, torch.Tensor]:
             "w_rec": two_unit(w_hh, 16), "w_xp": two_unit(w_ih, C // 4)}
 
 
+def _bf16_split(m: torch.Tensor):
+    """fp32 -> (hi, lo) bfloat16 pair with hi + lo == m to ~2^-17 relative (round-to-nearest both times)."""
+    hi = m.to(torch.bfloat16)
+    lo = (m - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _umma_kmajor(m: torch.Tensor) -> torch.Tensor:
+    """[R, K] bf16 -> the canonical no-swizzle K-major UMMA shared-memory image [K/8][R/8][8 rows][8 k] (one 128-byte
+    core matrix = 8 rows x 16 bytes; SBO = 128 B between 8-row groups, LBO = (R/8)*128 B between 8-element k chunks),
+    returned as raw 16-bit words."""
+    R, K = m.shape
+    assert R % 8 == 0 and K % 8 == 0
+    return m.view(R // 8, 8, K // 8, 8).permute(2, 0, 1, 3).contiguous().view(torch.int16).reshape(-1)
+
+
+def _tc_operands(w: torch.Tensor, b: torch.Tensor, lin: torch.Tensor, H: int) -> Dict[str, torch.Tensor]:
+    """Operands of lstm_tc_kernel (tcgen05): gate matrix [4H, K] with rows re-ordered unit-major (n = 4u + g), the
+    projection [C, H], both split into bf16 hi/lo and laid out for UMMA; biases fp32 in the same n order.
+    16-bit payloads are carried in the float32 weight buffer as raw bits."""
+    g = torch.arange(4).view(1, 4).expand(H, 4).reshape(-1)
+    u = torch.arange(H).view(H, 1).expand(H, 4).reshape(-1)
+    rows = g * H + u                                             # n = 4u + g  <-  weight row g*H + u
+    wn = w[rows].contiguous()
+    whi, wlo = _bf16_split(wn)
+    phi, plo = _bf16_split(lin.float().contiguous())
+    words = torch.cat([_umma_kmajor(whi), _umma_kmajor(wlo), _umma_kmajor(phi), _umma_kmajor(plo)])
+    return {"tc_w": words.view(torch.float32).clone(), "tc_b": b[rows].contiguous()}
+
+
 def _proj_ws(lin: torch.Tensor, H: int) -> torch.Tensor:
     """lin [C, H] -> w_prj [4][128][4]: recurrence thread t = 4*ur + kq holds 16 weights for the h slice it has in
     registers (k = 16kq + j): lin[ur % C][16kq + j] where j belongs to its plane ur // C, zero elsewhere (the 32/C
@@ -188,6 +218,8 @@ class PackedWeights:
                     add(f"b{i}.intra{d}.lin_n", lin)
                     add(f"b{i}.intra{d}.lin_t", lin.t())
                     add(f"b{i}.intra{d}.w_prj", _proj_ws(lin, H))
+                    for k, v in _tc_operands(*self._cat(sd, b + "intra_rnn.", sfx), lin, H).items():
+                        add(f"b{i}.intra{d}.{k}", v)
             if not cfg.conv_lstm:
                 add(f"b{i}.intra.lin_b", sd[b + "intra_linear.bias"])
             add(f"b{i}.intra.ln_g", sd[b + norm + "weight"])
@@ -197,6 +229,8 @@ class PackedWeights:
             add(f"b{i}.inter.lin_n", sd[b + "inter_linear.weight"])
             add(f"b{i}.inter.lin_t", sd[b + "inter_linear.weight"].t())
             add(f"b{i}.inter.w_prj", _proj_ws(sd[b + "inter_linear.weight"], H))
+            for k, v in _tc_operands(*self._cat(sd, b + "inter_rnn.", ""), sd[b + "inter_linear.weight"], H).items():
+                add(f"b{i}.inter.{k}", v)
             add(f"b{i}.inter.lin_b", sd[b + "inter_linear.bias"])
             add(f"b{i}.inter.ln_g", sd[b + "inter_norm.norm.weight"])
             add(f"b{i}.inter.ln_b", sd[b + "inter_norm.norm.bias"])
@@ -269,8 +303,14 @@ class PackedWeights:
                     setattr(fld, f, ptr(f"b{i}.attn_{nm}.{f}"))
         self.desc = d
 
+    @staticmethod
+    def _cat(sd, prefix: str, sfx: str):
+        w = torch.cat([sd[prefix + "weight_ih_l0" + sfx], sd[prefix + "weight_hh_l0" + sfx]], dim=1).float()
+        b = (sd[prefix + "bias_ih_l0" + sfx] + sd[prefix + "bias_hh_l0" + sfx]).float()
+        return w, b
+
     def _fill_dir(self, dst, own: str, shared: str):
-        for f in ("w_tile", "b_tile", "w_lane", "b_lane", "w_rec", "w_xp", "w_prj", "lin_t", "lin_n"):
+        for f in ("w_tile", "b_tile", "w_lane", "b_lane", "w_rec", "w_xp", "w_prj", "tc_w", "tc_b", "lin_t", "lin_n"):
             setattr(dst, f, self.ptr(own + f))
         for f in ("lin_b", "ln_g", "ln_b"):
             v = self.ptr(own + f)

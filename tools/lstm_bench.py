@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from bench import SYN  # noqa: E402
 from sound_bubble_b200 import Net, _abi as abi, _lib  # noqa: E402
 
-ALGO = {1: "tile", 2: "lane1", 3: "lane2", 4: "lane4", 5: "ws"}
+ALGO = {1: "tile", 2: "lane1", 3: "lane2", 4: "lane4", 5: "ws", 7: "tc"}
 
 
 def main():
@@ -20,6 +20,7 @@ def main():
     lib = _lib.load()
     if len(sys.argv) > 1 and sys.argv[1] == "pdl":
         _lib.set_pdl(True)
+    only_tc = len(sys.argv) > 1 and sys.argv[1] == "tc"
     torch.manual_seed(0)
     net = Net(**SYN).to(dev).eval()
     pk = net.engine().packed
@@ -38,16 +39,16 @@ def main():
         ts.sort()
         return ts[len(ts) // 2]
 
-    for (B, T) in ((32, 1), (8, 1), (128, 1), (32, 8), (4, 625), (32, 625)):
+    for (B, T) in (((4, 625), (32, 625)) if only_tc else ((32, 1), (8, 1), (128, 1), (32, 8), (4, 625), (32, 625))):
         x = torch.randn(B, T, F, C, device=dev)
         y0, y1 = torch.empty_like(x), torch.empty_like(x)
         h = torch.zeros(B * F, H, device=dev); c = torch.zeros(B * F, H, device=dev)
         film = torch.randn(2, B, F, C, device=dev)
         for kind in ("intra", "inter"):
-            for algo in (1, 2, 3, 4, 5):
+            for algo in ((1, 7) if only_tc else (1, 2, 3, 4, 5, 7)):
                 rows = B * T if kind == "intra" else B * F
                 steps = F if kind == "intra" else T
-                ctas = {1: rows / 8 / 8, 2: rows, 3: rows / 2, 4: rows / 4, 5: rows / 3}[algo] * (2 if kind == "intra" else 1)
+                ctas = {1: rows / 8 / 8, 2: rows, 3: rows / 2, 4: rows / 4, 5: rows / 3, 7: rows / 128}[algo] * (2 if kind == "intra" else 1)
                 if algo != 1 and ctas * steps > 148 * 145 * 80:
                     continue                                    # hopeless: skip the very long lane runs
                 if kind == "intra":
