@@ -214,21 +214,32 @@ def run_ours(args, rank, world, local_rank):
     launches_per_chunk = sess.launches_per_step()
     sess.reset()
     stream = torch.cuda.current_stream(dev)
+    # throughput mode: the same one-call-per-chunk protocol, calls asynchronous, consecutive chunks overlapping on two
+    # streams with per-unit dependencies (sound_bubble_b200/streaming.py::PipelinedSession)
+    pipe = net.streaming(BATCH, dis, pipelined=True, ranges=args.ranges or None, depth=args.depth) if args.pipeline else None
 
-    def pass_device():
+    def pass_in_order(win, out):
         sess.reset()
         for t in range(T_FRAMES):
-            sess.x.copy_(win_dev[t], non_blocking=True)
+            sess.x.copy_(win[t], non_blocking=True)
             sess.step()
-            out_dev[t].copy_(sess.y, non_blocking=True)
+            out[t].copy_(sess.y, non_blocking=True)
+
+    def pass_pipelined(win, out):
+        pipe.reset()
+        pipe.begin()
+        for t in range(T_FRAMES):
+            pipe.feed(win[t], out=out[t])
+        pipe.end()
+
+    one_pass = pass_pipelined if pipe is not None else pass_in_order
+
+    def pass_device():
+        one_pass(win_dev, out_dev)
         return out_dev.permute(1, 2, 0, 3).reshape(BATCH, 1, N_SAMPLES)
 
     def pass_host():
-        sess.reset()
-        for t in range(T_FRAMES):
-            sess.x.copy_(win_host[t], non_blocking=True)
-            sess.step()
-            out_host[t].copy_(sess.y, non_blocking=True)
+        one_pass(win_host, out_host)
         stream.synchronize()
         return out_host
 
@@ -261,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
         ms_dev = timed(pass_device, args.steps, args.warmup)
     clocks = clk.summary()
     ms_e2e = timed(pass_host, max(2, args.steps // 2), 1)
+    ms_in_order = timed(lambda: pass_in_order(win_dev, out_dev), 2, 1) if pipe is not None else ms_dev
     frames = BATCH * T_FRAMES * world
     value = frames / (ms_dev * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
@@ -334,11 +346,15 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "clip_seconds": 5.0, "frames_per_step": frames,
                    "chunks_per_step": T_FRAMES, "weights": "random init (seed 0) of the TFG_S architecture",
                    "l2": "256 MB buffer written between timed steps", "cuda_graph": not args.no_graph, "pdl": bool(args.pdl),
+                   "pipelined": pipe is not None, "unit_ranges": pipe.ranges if pipe is not None else None,
+                   "pipeline_depth": pipe.depth if pipe is not None else 1,
                    "parallelism": "dp%d (utterances sharded, no collective on the data path)" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(win_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
         "gpu_launches": int(launches_per_chunk * T_FRAMES * args.steps),
         "launches_per_chunk": int(launches_per_chunk),
+        "in_order": {"value": frames / (ms_in_order * 1e-3), "unit": UNIT, "ms_per_step": ms_in_order,
+                     "note": "one stream, chunk t+1 starts when chunk t has finished"},
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "offline": offline_info,
         "streaming_vs_offline_maxabs": stream_vs_offline,
     }), flush=True)
@@ -352,6 +368,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("SB_PDL", "1")))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=int(os.environ.get("SB_PIPELINE", "1")))
+    ap.add_argument("--ranges", type=int, default=0, help="pipelined session: number of unit ranges (0 = default)")
+    ap.add_argument("--depth", type=int, default=2, help="pipelined session: chunks in flight")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -81,9 +81,14 @@ extern "C" size_t sb_workspace_floats(const sb_net_desc* d, int B, int T) {
     return sb::carve(d, B, T, nullptr).total;
 }
 
-extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream) {
+// Units of the launch sequence: 0 = front-end (stft_features, conv_in, [film_params]), 1 .. n_blocks = GridNet block
+// i-1 (intra, inter, [attention]), n_blocks+1 = back-end.  sb_net_forward runs all of them; a pipelined streaming
+// session captures one CUDA graph per range so that consecutive chunks can overlap on two streams (streaming.py).
+extern "C" int sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first_unit, int last_unit, void* stream) {
     using namespace sb;
     SB_REQUIRE(d && io, SB_E_BADARG, "sb_net_forward: null descriptor");
+    SB_REQUIRE(first_unit >= 0 && first_unit <= last_unit && last_unit <= d->n_blocks + 1, SB_E_BADARG,
+               "sb_net_forward_range: bad unit range [%d, %d]", first_unit, last_unit);
     SB_REQUIRE(io->wave && io->wave_out && io->workspace, SB_E_BADARG, "sb_net_forward: null wave / wave_out / workspace");
     SB_REQUIRE(io->B > 0 && io->T > 0, SB_E_BADARG, "sb_net_forward: bad B/T");
     SB_REQUIRE(d->n_blocks > 0 && d->n_blocks <= SB_MAX_BLOCKS, SB_E_UNSUPP, "sb_net_forward: n_blocks=%d out of range", d->n_blocks);
@@ -92,6 +97,12 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     const int B = io->B, T = io->T;
     const Workspace w = carve(d, B, T, io->workspace);
 
+    const float* film = w.film;
+    if (io->film && d->film_din > 0 && d->n_blocks > 1) film = io->film;
+    SB_REQUIRE(first_unit == 0 || !w.film || film != w.film, SB_E_BADARG,
+               "sb_net_forward_range: a range that skips the front-end needs io->film (precomputed FiLM table)");
+
+    if (first_unit == 0) {
     sb_stft_args sa{};
     sa.wave = io->wave; sa.filt = d->enc_filt; sa.feats = w.feats; sa.spec = w.spec_in;
     sa.B = B; sa.M = d->M; sa.n_samples = d->stride * T + (d->n_fft - d->stride); sa.T = T;
@@ -105,10 +116,7 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     ca.x = w.x0; ca.B = B; ca.T = T; ca.F = d->F; ca.Cin = d->Cin; ca.C = d->C;
     { StageTimer tm(stream, SB_STAGE_CONV_IN); SB_CHECK(sb_conv_in_fwd(&ca, stream)); }
 
-    const float* film = w.film;
-    if (io->film && d->film_din > 0 && d->n_blocks > 1) {
-        film = io->film;
-    } else if (w.film) {
+    if (film == w.film && w.film) {
         sb_film_args fa{};
         fa.dis = io->dis_embed; fa.emb_w = d->emb_w; fa.emb_ln_g = d->emb_ln_g; fa.emb_ln_b = d->emb_ln_b;
         fa.w_w = d->film_w_w; fa.w_b = d->film_w_b; fa.b_w = d->film_b_w; fa.b_b = d->film_b_b;
@@ -116,9 +124,11 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
         fa.emb_mode = d->emb_mode;
         { StageTimer tm(stream, SB_STAGE_FILM); SB_CHECK(sb_film_params_fwd(&fa, stream)); }
     }
+    }   // front-end
 
     const size_t film_stride = (size_t)B * d->F * d->C;
     for (int i = 0; i < d->n_blocks; ++i) {
+        if (i + 1 < first_unit || i + 1 > last_unit) continue;
         const sb_block_desc& bd = d->blocks[i];
         const float* fscale = (film && i > 0) ? film + (size_t)(i - 1) * 2 * film_stride : nullptr;
         const float* fshift = fscale ? fscale + film_stride : nullptr;
@@ -156,6 +166,7 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
         }
     }
 
+    if (last_unit <= d->n_blocks) return 0;
     sb_backend_args ba{};
     ba.x = w.x0; ba.deconv_buf_in = io->deconv_buf_in; ba.deconv_buf_out = io->deconv_buf_out;
     ba.istft_buf_in = io->istft_buf_in; ba.istft_buf_out = io->istft_buf_out;
@@ -164,6 +175,11 @@ extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* s
     ba.B = B; ba.T = T; ba.F = d->F; ba.C = d->C; ba.n_src = d->n_src; ba.n_fft = d->n_fft; ba.stride = d->stride;
     StageTimer tm(stream, SB_STAGE_BACKEND);
     return sb_backend_fwd(&ba, stream);
+}
+
+extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream) {
+    SB_REQUIRE(d, SB_E_BADARG, "sb_net_forward: null descriptor");
+    return sb_net_forward_range(d, io, 0, d->n_blocks + 1, stream);
 }
 
 extern "C" int sb_profile_begin(void) {

@@ -92,12 +92,12 @@ class Engine:
         return film
 
     # -- the forward pass ------------------------------------------------------------------------------------
-    def forward(self, wave: torch.Tensor, dis_embed: Optional[torch.Tensor], state: dict,
+    def prepare(self, wave: torch.Tensor, dis_embed: Optional[torch.Tensor], state: dict,
                 out: Optional[torch.Tensor] = None, new_state: Optional[dict] = None,
-                film: Optional[torch.Tensor] = None):
-        """wave [B, M, stride*T + n_fft - stride] -> ([B, S, stride*T], state).  `state` is updated in place (the
-        dict, as the reference does, DE3:547-552) with freshly written tensors unless `new_state` supplies them."""
-        cfg, lib = self.cfg, self.lib
+                film: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> "PreparedCall":
+        """Validates one call and fills its sb_net_io (no launch).  wave [B, M, stride*T + n_fft - stride]; the result
+        goes to `out` [B, S, stride*T]; the next state is written into fresh tensors unless `new_state` supplies them."""
+        cfg = self.cfg
         B, M, N = wave.shape
         if M != cfg.num_ch:
             raise ValueError("mixture has %d channels, the model was built for num_ch=%d" % (M, cfg.num_ch))
@@ -122,6 +122,7 @@ class Engine:
             keep.append(dis)
             if film is not None:
                 io.film = film.data_ptr()
+                keep.append(film)
         if out is None:
             out = torch.empty(B, S, cfg.stft_chunk_size * T, dtype=torch.float32, device=dev)
         io.wave_out = out.data_ptr()
@@ -165,15 +166,51 @@ class Engine:
                 keep += [k_in, v_in]
                 o["K_buf"], o["V_buf"] = k_out, v_out
             outs[i] = o
-        ws = self.workspace(B, T, dev)
+        ws = workspace if workspace is not None else self.workspace(B, T, dev)
+        need_ws = int(self.lib.sb_workspace_floats(self.packed.desc_ref(), B, T))
+        if ws.numel() < need_ws or ws.dtype != torch.float32 or ws.device != dev:
+            raise ValueError("workspace must be %d float32 on %s" % (need_ws, dev))
         io.workspace = ws.data_ptr()
+        keep.append(ws)
+        return PreparedCall(self, io, keep, out, state, {"conv_buf": conv_out, "deconv_buf": deconv_out,
+                                                          "istft_buf": istft_out}, outs)
 
-        rc = lib.sb_net_forward(self.packed.desc_ref(), ctypes.byref(io), _stream_ptr(wave))
-        abi.check(lib, rc, "sb_net_forward")
+    def forward(self, wave: torch.Tensor, dis_embed: Optional[torch.Tensor], state: dict,
+                out: Optional[torch.Tensor] = None, new_state: Optional[dict] = None,
+                film: Optional[torch.Tensor] = None):
+        """wave [B, M, stride*T + n_fft - stride] -> ([B, S, stride*T], state).  `state` is updated in place (the
+        dict, as the reference does, DE3:547-552) with freshly written tensors unless `new_state` supplies them."""
+        call = self.prepare(wave, dis_embed, state, out=out, new_state=new_state, film=film)
+        call.launch()
+        return call.out, call.commit()
 
-        state["conv_buf"], state["deconv_buf"], state["istft_buf"] = conv_out, deconv_out, istft_out
-        for i in range(cfg.B):
-            buf = bufs[f"buf{i}"]
-            for k, v in outs[i].items():
-                buf[k] = v
-        return out, state
+
+class PreparedCall:
+    """One validated call of the forward pass: its sb_net_io and the tensors it points at.  `launch()` runs the whole
+    launch sequence (sb_net_forward) or a range of its units (sb_net_forward_range) on the current stream."""
+
+    def __init__(self, engine: Engine, io, keep, out, state, top, blocks):
+        self.engine, self.io, self.keep, self.out = engine, io, keep, out
+        self._state, self._top, self._blocks = state, top, blocks
+        self.n_units = engine.cfg.B + 2
+
+    def launch(self, first_unit: int = 0, last_unit: Optional[int] = None):
+        eng = self.engine
+        last = self.n_units - 1 if last_unit is None else last_unit
+        stream = _stream_ptr(self.keep[0])
+        if first_unit == 0 and last == self.n_units - 1:
+            rc = eng.lib.sb_net_forward(eng.packed.desc_ref(), ctypes.byref(self.io), stream)
+        else:
+            rc = eng.lib.sb_net_forward_range(eng.packed.desc_ref(), ctypes.byref(self.io), first_unit, last, stream)
+        abi.check(eng.lib, rc, "sb_net_forward")
+
+    def commit(self) -> dict:
+        """Point the caller's state dict at the tensors this call wrote (the reference mutates the dict it was given)."""
+        state = self._state
+        for k, v in self._top.items():
+            state[k] = v
+        bufs = state["gridnet_bufs"]
+        for i, o in self._blocks.items():
+            for k, v in o.items():
+                bufs[f"buf{i}"][k] = v
+        return state

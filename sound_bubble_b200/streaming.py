@@ -20,6 +20,11 @@ def _clone_state(st):
     return {k: (_clone_state(v) if isinstance(v, dict) else v.clone()) for k, v in st.items()}
 
 
+def _shallow(st):
+    """A throw-away copy of the dict structure (Engine.forward re-points the dict it is given at the new tensors)."""
+    return {k: (dict((kk, dict(vv)) for kk, vv in v.items()) if k == "gridnet_bufs" else v) for k, v in st.items()}
+
+
 class StreamingSession:
     def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, use_graph: bool = True,
                  frames_per_call: int = 1):
@@ -49,8 +54,7 @@ class StreamingSession:
     # ------------------------------------------------------------------------------------------------------
     def _step_eager(self, p: int):
         src, dst = self.states[p], self.states[p ^ 1]
-        work = {k: (dict((kk, dict(vv)) for kk, vv in v.items()) if k == "gridnet_bufs" else v) for k, v in src.items()}
-        self.engine.forward(self.x, self.dis, work, out=self.y, new_state=dst, film=self.film)
+        self.engine.forward(self.x, self.dis, _shallow(src), out=self.y, new_state=dst, film=self.film)
 
     def _capture(self):
         saved = [_clone_state(s) for s in self.states]
@@ -128,4 +132,162 @@ class StreamingSession:
         self._step_eager(self.parity)       # eager twin of the captured step, then restore parity bookkeeping
         torch.cuda.synchronize(self.device)
         self.parity ^= 1
+        return _lib.launch_count() - before
+
+
+class PipelinedSession:
+    """Throughput mode of the same protocol: one call per chunk, state carried, but the calls are ASYNCHRONOUS and
+    consecutive chunks overlap on the GPU.
+
+    A chunk at batch 32 fills 64 of the 148 SMs for most of its life (one CTA per (utterance, direction) of the
+    intra-frame BiLSTM, 145 dependent steps), so a single in-order stream leaves half of the GPU idle.  Every state
+    tensor of the reference belongs to exactly one unit of the launch sequence (conv_buf: front-end; h0/c0 [+K/V]: one
+    GridNet block; deconv_buf/istft_buf: back-end; DE3:403-421, 696-720), hence chunk t+1 depends on chunk t PER UNIT
+    only.  The session keeps `depth` slots (stream, window, result, workspace; chunk t uses slot t % depth and reads
+    state arena t % 2), captures one CUDA graph per (arena, slot, unit range) and links the streams with one event per
+    range: range j of chunk t+1 waits for range j of chunk t.  Results are identical to StreamingSession's (same
+    kernels, same order per unit).
+
+    Use: ``begin()`` once after the caller's stream has produced the windows, ``feed(window, out)`` per chunk (returns
+    immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
+
+    def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 2):
+        self.net = net
+        self.cfg = cfg = net.cfg
+        self.engine = eng = net.engine()
+        dev = eng.packed.flat.device
+        self.device = dev
+        self.B = batch_size
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.depth = depth
+        mk = lambda *shape: [torch.zeros(*shape, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.x = mk(batch_size, cfg.num_ch, cfg.n_fft)
+        self.y = mk(batch_size, cfg.num_src, cfg.stft_chunk_size)
+        n_ws = max(int(eng.lib.sb_workspace_floats(eng.packed.desc_ref(), batch_size, 1)), 1)
+        self.ws = [torch.empty(n_ws, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.dis = None
+        if cfg.variant == "dis_embed":
+            if dis_embed is None:
+                raise KeyError("dis_embed")
+            self.dis = dis_embed.to(dev, torch.float32).contiguous().clone()
+        self.film = eng.film_table(self.dis) if self.dis is not None else None
+        self.states = [init_state(cfg, batch_size, dev), init_state(cfg, batch_size, dev)]
+        n_units = cfg.B + 2
+        if ranges is None:
+            ranges = 2
+        if isinstance(ranges, int):                         # `ranges` near-equal groups of blocks
+            k = max(1, min(int(ranges), cfg.B))
+            cuts = [round(i * cfg.B / k) for i in range(k + 1)]
+            ranges = [(cuts[i] + 1, cuts[i + 1]) for i in range(k)]
+            ranges[0] = (0, ranges[0][1])
+            ranges[-1] = (ranges[-1][0], n_units - 1)
+        flat = [u for lo, hi in ranges for u in range(lo, hi + 1)]
+        if flat != list(range(n_units)):
+            raise ValueError("ranges must cover units 0..%d in order, got %r" % (n_units - 1, ranges))
+        self.ranges = [tuple(r) for r in ranges]
+        self.streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        self.events = [[torch.cuda.Event() for _ in self.ranges] for _ in range(depth)]
+        self._fork = torch.cuda.Event()
+        self.n_calls = 0
+        self._capture()
+
+    def _call(self, p: int, slot: int):
+        return self.engine.prepare(self.x[slot], self.dis, _shallow(self.states[p]), out=self.y[slot],
+                                   new_state=self.states[p ^ 1], film=self.film, workspace=self.ws[slot])
+
+    def _capture(self):
+        saved = [_clone_state(s) for s in self.states]
+        cur = torch.cuda.current_stream(self.device)
+        side = self.streams[0]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                       # warm-up eagerly (smem opt-ins, lazy module loading)
+            for p in (0, 1):
+                self._call(p, 0).launch()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graphs = {}
+        period = self.depth if self.depth % 2 == 0 else 2 * self.depth
+        for t in range(period):                             # every (arena, slot) pair that occurs
+            p, slot = t % 2, t % self.depth
+            call = self._call(p, slot)
+            gs = []
+            for lo, hi in self.ranges:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    call.launch(lo, hi)
+                gs.append(g)
+            self.graphs[(p, slot)] = gs
+        torch.cuda.synchronize(self.device)
+        for s, z in zip(self.states, saved):
+            StreamingSession._copy_state(s, z)
+
+    # ------------------------------------------------------------------------------------------------------
+    @property
+    def parity(self) -> int:
+        return self.n_calls % 2
+
+    def reset(self):
+        """Zero the state on the caller's stream (after an end(), so that nothing fed earlier is still running); call
+        begin() afterwards."""
+        for s in self.states:
+            for k, v in s.items():
+                if isinstance(v, dict):
+                    for b in v.values():
+                        for t in b.values():
+                            t.zero_()
+                else:
+                    v.zero_()
+        self.n_calls = 0
+
+    def begin(self):
+        """Order every slot stream after what the caller's current stream has enqueued so far (the windows, a
+        reset(), a load_state())."""
+        self._fork.record(torch.cuda.current_stream(self.device))
+        for s in self.streams:
+            s.wait_event(self._fork)
+
+    def feed(self, window: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Enqueue one chunk: window [B, M, chunk + lookahead] (host or device) -> `out` [B, S, chunk] (or the slot's
+        device buffer, valid until `depth` calls later).  Returns without waiting."""
+        t = self.n_calls
+        p, slot = t % 2, t % self.depth
+        s = self.streams[slot]
+        prev = self.events[(t - 1) % self.depth]
+        mine = self.events[slot]
+        with torch.cuda.stream(s):
+            self.x[slot].copy_(window, non_blocking=True)
+            for j, g in enumerate(self.graphs[(p, slot)]):
+                if t > 0 and self.depth > 1:
+                    s.wait_event(prev[j])                   # unit range j of the previous chunk (another stream)
+                g.replay()
+                mine[j].record(s)
+            res = self.y[slot]
+            if out is not None:
+                out.copy_(res, non_blocking=True)
+                res = out
+        self.n_calls += 1
+        return res
+
+    def end(self):
+        """Make the caller's current stream wait for every chunk fed so far."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    @property
+    def state(self) -> dict:
+        """The current state in the reference's schema (valid after end() + a synchronisation of the caller's stream)."""
+        return self.states[self.parity]
+
+    def load_state(self, state: dict):
+        StreamingSession._copy_state(self.states[self.parity], state)
+
+    def launches_per_step(self) -> int:
+        before = _lib.launch_count()
+        saved = [_clone_state(s) for s in self.states]
+        self._call(0, 0).launch()
+        torch.cuda.synchronize(self.device)
+        for s, z in zip(self.states, saved):
+            StreamingSession._copy_state(s, z)
         return _lib.launch_count() - before

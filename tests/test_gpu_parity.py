@@ -141,6 +141,43 @@ def test_streaming_session_equals_offline_and_reference():
         assert max(float((got[k] - v).abs().max()) for k, v in g.state.items()) <= pc.MAXABS_TIGHT
 
 
+@pytest.mark.parametrize("name,ranges,depth", [("syn_nopad", None, 2), ("syn_nopad", 6, 2), ("syn_nopad", 1, 2),
+                                               ("syn_nopad", 3, 3), ("syn_nopad", 6, 4), ("rpi_offline", None, 2),
+                                               ("rpi_offline", 3, 3), ("syn_attn", 3, 2)])
+def test_pipelined_session_is_bit_identical_to_the_in_order_session(name, ranges, depth):
+    """Throughput mode (two streams, per-unit events): same kernels in the same per-unit order, so the waveform and
+    the carried state must equal the in-order session's exactly, and the golden fixture's within the tight bar."""
+    g = Golden(name)
+    m = _net_for(g)
+    cfg = m.cfg
+    x = g.mixture.to(DEV)
+    if g.pad:
+        from sound_bubble_b200._net_base import mod_pad
+        x, _ = mod_pad(x, cfg.stft_chunk_size, (0, cfg.stft_pad_size))
+    dis = g.dis_embed.to(DEV) if g.dis_embed is not None else None
+    T = (x.shape[-1] - cfg.n_fft) // cfg.stft_chunk_size + 1
+    wins = [x[..., t * cfg.stft_chunk_size: t * cfg.stft_chunk_size + cfg.n_fft].contiguous() for t in range(T)]
+    seq = m.streaming(x.shape[0], dis)
+    ref = torch.cat([seq.feed(w).clone() for w in wins], dim=-1)
+    pipe = m.streaming(x.shape[0], dis, pipelined=True, ranges=ranges, depth=depth)
+    for rep in range(2):                                     # second pass: reset + reuse of the captured graphs
+        outs = [torch.empty_like(ref[..., : cfg.stft_chunk_size]) for _ in wins]
+        host = torch.empty(T, *outs[0].shape).pin_memory()
+        pipe.reset()
+        pipe.begin()
+        for t, w in enumerate(wins):
+            pipe.feed(w, out=outs[t] if rep == 0 else host[t])
+        pipe.end()
+        torch.cuda.synchronize()
+        y = torch.cat(outs, dim=-1) if rep == 0 else torch.cat(list(host.to(DEV)), dim=-1)
+        assert torch.equal(y, ref), (rep, float((y - ref).abs().max()))
+        a, b = flatten_state(pipe.state), flatten_state(seq.state)
+        assert all(torch.equal(a[k], b[k]) for k in b), rep
+    n = min(y.shape[-1], g.output.shape[-1])
+    r = pc.compare(y[..., :n], g.output[..., :n])
+    assert r["rms"] <= pc.RMS_TIGHT and r["maxabs"] <= pc.MAXABS_TIGHT, r
+
+
 def test_medium_clip_against_oracle():
     """1 s clips, batch 3, TFG_S config: ours vs the CPU oracle run here on the same seeded input."""
     ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q -x -k "pipelined or streaming" > gpurun_out/pytest_pipe.log 2>&1; tail -5 gpurun_out/pytest_pipe.log
+for cfg in "2 2" "2 3" "3 3" "6 3" "3 4" "6 4" "6 2"; do
+set -- $cfg; r=$1; d=$2
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --ranges $r --depth $d > gpurun_out/bench_pipe_r${r}_d$d.json 2> gpurun_out/bench_pipe_r${r}_d$d.err; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_pipe_r${r}_d$d.json").read().strip().splitlines()[-1])
+    print("ranges=$r depth=$d", "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "in_order", round(d["in_order"]["value"]), "ms", round(d["ms_per_step"],1), d["streaming_vs_offline_maxabs"])
+except Exception as e:
+    print("ranges=$r depth=$d failed", e); print(open("gpurun_out/bench_pipe_r${r}_d$d.err").read()[-2000:])
+PY
+done
