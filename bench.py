@@ -225,11 +225,15 @@ def run_ours(args, rank, world, local_rank):
             sess.step()
             out[t].copy_(sess.y, non_blocking=True)
 
+    enqueue_s = []
+
     def pass_pipelined(win, out):
         pipe.reset()
         pipe.begin()
+        t0 = time.perf_counter()
         for t in range(T_FRAMES):
             pipe.feed(win[t], out=out[t])
+        enqueue_s.append(time.perf_counter() - t0)
         pipe.end()
 
     one_pass = pass_pipelined if pipe is not None else pass_in_order
@@ -348,6 +352,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "256 MB buffer written between timed steps", "cuda_graph": not args.no_graph, "pdl": bool(args.pdl),
                    "pipelined": pipe is not None, "unit_ranges": pipe.ranges if pipe is not None else None,
                    "pipeline_depth": pipe.depth if pipe is not None else 1,
+                   "host_enqueue_ms_per_step": 1e3 * statistics.median(enqueue_s) if enqueue_s else None,
                    "parallelism": "dp%d (utterances sharded, no collective on the data path)" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(win_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},

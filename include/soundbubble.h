@@ -338,6 +338,26 @@ int    sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream);
 int    sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first_unit, int last_unit, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------- */
+/* Pipelined streaming (throughput mode of the edge/causal_infer.py:28-47 protocol): one sb_pipe_feed per 8 ms     */
+/* chunk, state carried, consecutive chunks overlapping on `depth` streams owned by the pipe.  Chunk t runs on      */
+/* stream t % depth as one CUDA graph per unit range (captured at creation from sb_net_forward_range); range j of   */
+/* chunk t waits for range j of chunk t-1.  The caller owns all device memory: ios[k] (k = t % n_ios, n_ios = depth */
+/* if even else 2*depth) holds the slot's wave / wave_out / workspace (shared by the entries of slot k % depth, T =  */
+/* 1) and reads the state arena t % 2 / writes the other one; io.film must be set for FiLM models.  Run one eager    */
+/* sb_net_forward per kernel configuration before sb_pipe_create (shared-memory opt-ins cannot happen in a capture). */
+/* The only entry points of the library that create CUDA objects (streams, events, graphs); not thread-safe per pipe.*/
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_pipe sb_pipe;
+int       sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_ios, int depth, const int* range_first,
+                         const int* range_last, int n_ranges, sb_pipe** out);
+int       sb_pipe_destroy(sb_pipe* p);
+int       sb_pipe_begin(sb_pipe* p, void* caller_stream);   /* pipe streams wait for the caller's stream            */
+int       sb_pipe_feed(sb_pipe* p, const float* window, float* out);  /* host (pinned) or device pointers, or NULL  */
+int       sb_pipe_end(sb_pipe* p, void* caller_stream);     /* the caller's stream waits for every chunk fed so far */
+int       sb_pipe_reset(sb_pipe* p);                        /* chunk counter back to 0 (caller resets the state)    */
+long long sb_pipe_calls(const sb_pipe* p);
+
+/* ---------------------------------------------------------------------------------------------------------- */
 /* Per-stage device timing of sb_net_forward with CUDA events on the launching stream (bench.py's roofline leg).  */
 /* sb_profile_begin() arms it; every sb_net_forward until sb_profile_end() brackets each stage with events (do    */
 /* not use while the stream is being captured into a graph).  sb_profile_end() synchronises the events and adds,  */

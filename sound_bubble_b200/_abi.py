@@ -133,6 +133,14 @@ PROTOTYPES = {
     "sb_workspace_floats": (C.c_size_t, [C.POINTER(NetDesc), C.c_int, C.c_int]),
     "sb_net_forward": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_void_p]),
     "sb_net_forward_range": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_int, C.c_int, C.c_void_p]),
+    "sb_pipe_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_int, C.c_int, C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "sb_pipe_destroy": (C.c_int, [C.c_void_p]),
+    "sb_pipe_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sb_pipe_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb_pipe_end": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sb_pipe_reset": (C.c_int, [C.c_void_p]),
+    "sb_pipe_calls": (C.c_longlong, [C.c_void_p]),
     "sb_profile_begin": (C.c_int, []),
     "sb_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "sb_version": (C.c_int, []),

@@ -1,0 +1,205 @@
+// Native runtime of the pipelined streaming session (throughput mode of the edge/causal_infer.py:28-47 protocol).
+//
+// One call per 8 ms chunk, state carried, but consecutive chunks overlap on the GPU: every state tensor of the
+// reference belongs to exactly one unit of the launch sequence (conv_buf: front-end; h0/c0 [+K/V]: one GridNet block;
+// deconv_buf/istft_buf: back-end; DE3:403-421, 696-720), so chunk t+1 depends on chunk t per unit only.  The pipe
+// owns `depth` streams; chunk t runs on stream t % depth as a few CUDA graphs (one per unit range, captured here from
+// sb_net_forward_range) and range j of chunk t waits for the event range j of chunk t-1 recorded on its own stream.
+// Per chunk the host issues 2 copies + n_ranges x (wait, graph launch, record): a few microseconds, no Python.
+//
+// All device memory (windows, results, workspaces, both state arenas) belongs to the caller and arrives inside the
+// sb_net_io array: entry k describes chunk numbers t with t % n_ios == k (n_ios = lcm(depth, 2): slot t % depth for
+// wave / wave_out / workspace, arena t % 2 for the state inputs, the other arena for the state outputs).
+#include <vector>
+
+#include "sb_common.cuh"
+
+struct sb_pipe {
+    const sb_net_desc* desc = nullptr;
+    int depth = 0, n_ranges = 0, n_ios = 0;
+    size_t window_bytes = 0, out_bytes = 0;
+    long long n_calls = 0;
+    std::vector<sb_net_io> io;
+    std::vector<int> first, last;
+#ifndef SB_EMU
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> events;            // [depth][n_ranges]
+    std::vector<cudaEvent_t> joins;             // [depth]
+    std::vector<cudaGraphExec_t> graphs;        // [n_ios][n_ranges]
+    cudaEvent_t fork = nullptr;
+#endif
+};
+
+#ifndef SB_EMU
+namespace sb {
+
+static int cuda_fail(const char* what, cudaError_t e) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return (int)e;
+}
+#define SB_CUDA(call)                                           \
+    do {                                                        \
+        const cudaError_t sb_e_ = (call);                       \
+        if (sb_e_ != cudaSuccess) return cuda_fail(#call, sb_e_); \
+    } while (0)
+
+static void destroy(sb_pipe* p) {
+    if (!p) return;
+    for (auto g : p->graphs) if (g) cudaGraphExecDestroy(g);
+    for (auto e : p->events) if (e) cudaEventDestroy(e);
+    for (auto e : p->joins) if (e) cudaEventDestroy(e);
+    if (p->fork) cudaEventDestroy(p->fork);
+    for (auto s : p->streams) if (s) cudaStreamDestroy(s);
+    delete p;
+}
+
+static int capture_range(sb_pipe* p, int k, int j, cudaStream_t st, cudaGraphExec_t* out) {
+    SB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = sb_net_forward_range(p->desc, &p->io[k], p->first[j], p->last[j], st);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != 0) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    if (e != cudaSuccess) return cuda_fail("cudaStreamEndCapture", e);
+    const cudaError_t e2 = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) return cuda_fail("cudaGraphInstantiate", e2);
+    return 0;
+}
+
+}  // namespace sb
+#endif
+
+extern "C" int sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_ios, int depth, const int* range_first,
+                              const int* range_last, int n_ranges, sb_pipe** out) {
+    using namespace sb;
+    SB_REQUIRE(d && ios && range_first && range_last && out, SB_E_BADARG, "sb_pipe_create: null pointer");
+    SB_REQUIRE(depth >= 1 && depth <= 16, SB_E_BADARG, "sb_pipe_create: depth %d out of range", depth);
+    const int period = depth % 2 == 0 ? depth : 2 * depth;
+    SB_REQUIRE(n_ios == period, SB_E_BADARG, "sb_pipe_create: need %d sb_net_io entries for depth %d, got %d", period, depth, n_ios);
+    SB_REQUIRE(n_ranges >= 1 && n_ranges <= SB_MAX_BLOCKS + 2, SB_E_BADARG, "sb_pipe_create: bad number of ranges %d", n_ranges);
+    int next = 0;
+    for (int j = 0; j < n_ranges; ++j) {
+        SB_REQUIRE(range_first[j] == next && range_last[j] >= range_first[j], SB_E_BADARG,
+                   "sb_pipe_create: ranges must cover units 0..%d in order", d->n_blocks + 1);
+        next = range_last[j] + 1;
+    }
+    SB_REQUIRE(next == d->n_blocks + 2, SB_E_BADARG, "sb_pipe_create: ranges must cover units 0..%d in order", d->n_blocks + 1);
+    for (int k = 0; k < n_ios; ++k) {
+        SB_REQUIRE(ios[k].T == 1 && ios[k].B == ios[0].B && ios[k].B > 0, SB_E_BADARG,
+                   "sb_pipe_create: every sb_net_io must describe one frame of the same batch");
+        SB_REQUIRE(ios[k].wave == ios[k % depth].wave && ios[k].wave_out == ios[k % depth].wave_out &&
+                   ios[k].workspace == ios[k % depth].workspace, SB_E_BADARG,
+                   "sb_pipe_create: entries of one slot must share wave / wave_out / workspace");
+    }
+#ifdef SB_EMU
+    set_error("sb_pipe_create: streams and graphs do not exist in the host-emulated test build");
+    return SB_E_UNSUPP;
+#else
+    sb_pipe* p = new sb_pipe();
+    p->desc = d; p->depth = depth; p->n_ranges = n_ranges; p->n_ios = n_ios;
+    p->io.assign(ios, ios + n_ios);
+    p->first.assign(range_first, range_first + n_ranges);
+    p->last.assign(range_last, range_last + n_ranges);
+    p->window_bytes = sizeof(float) * (size_t)ios[0].B * d->M * d->n_fft;
+    p->out_bytes = sizeof(float) * (size_t)ios[0].B * d->n_src * d->stride;
+    p->streams.assign(depth, nullptr);
+    p->events.assign((size_t)depth * n_ranges, nullptr);
+    p->joins.assign(depth, nullptr);
+    p->graphs.assign((size_t)n_ios * n_ranges, nullptr);
+    auto fail = [&](int rc) { destroy(p); return rc; };
+    cudaError_t e = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail(cuda_fail("cudaEventCreate", e));
+    for (int s = 0; s < depth; ++s) {
+        if ((e = cudaStreamCreateWithFlags(&p->streams[s], cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail("cudaStreamCreate", e));
+        if ((e = cudaEventCreateWithFlags(&p->joins[s], cudaEventDisableTiming)) != cudaSuccess) return fail(cuda_fail("cudaEventCreate", e));
+        for (int j = 0; j < n_ranges; ++j)
+            if ((e = cudaEventCreateWithFlags(&p->events[(size_t)s * n_ranges + j], cudaEventDisableTiming)) != cudaSuccess)
+                return fail(cuda_fail("cudaEventCreate", e));
+    }
+    for (int k = 0; k < n_ios; ++k)
+        for (int j = 0; j < n_ranges; ++j) {
+            const int rc = capture_range(p, k, j, p->streams[k % depth], &p->graphs[(size_t)k * n_ranges + j]);
+            if (rc != 0) return fail(rc);
+        }
+    *out = p;
+    return 0;
+#endif
+}
+
+extern "C" int sb_pipe_destroy(sb_pipe* p) {
+#ifndef SB_EMU
+    if (p) {
+        for (auto s : p->streams) if (s) cudaStreamSynchronize(s);
+        sb::destroy(p);
+    }
+#else
+    delete p;
+#endif
+    return 0;
+}
+
+/* Orders every stream of the pipe after what `caller_stream` has enqueued so far (the windows, a state reset). */
+extern "C" int sb_pipe_begin(sb_pipe* p, void* caller_stream) {
+    using namespace sb;
+    SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_begin: null pipe");
+#ifndef SB_EMU
+    SB_CUDA(cudaEventRecord(p->fork, (cudaStream_t)caller_stream));
+    for (auto s : p->streams) SB_CUDA(cudaStreamWaitEvent(s, p->fork, 0));
+#endif
+    return 0;
+}
+
+/* Restarts the chunk counter (the caller zeroes or reloads the state arena 0 on its own stream, then sb_pipe_begin). */
+extern "C" int sb_pipe_reset(sb_pipe* p) {
+    using namespace sb;
+    SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_reset: null pipe");
+    p->n_calls = 0;
+    return 0;
+}
+
+extern "C" long long sb_pipe_calls(const sb_pipe* p) { return p ? p->n_calls : -1; }
+
+/* Enqueues one chunk and returns.  window: [B][M][n_fft] floats, host (pinned for a truly asynchronous copy) or       */
+/* device, NULL = the slot's window buffer was filled by the caller; out: [B][S][stride], host or device, NULL = leave   */
+/* the result in the slot's wave_out buffer (valid until `depth` calls later).                                           */
+extern "C" int sb_pipe_feed(sb_pipe* p, const float* window, float* out) {
+    using namespace sb;
+    SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_feed: null pipe");
+#ifndef SB_EMU
+    const long long t = p->n_calls;
+    const int slot = (int)(t % p->depth), k = (int)(t % p->n_ios), R = p->n_ranges;
+    cudaStream_t st = p->streams[slot];
+    const sb_net_io& io = p->io[k];
+    if (window) SB_CUDA(cudaMemcpyAsync(const_cast<float*>(io.wave), window, p->window_bytes, cudaMemcpyDefault, st));
+    const cudaEvent_t* prev = &p->events[(size_t)((t + p->depth - 1) % p->depth) * R];
+    cudaEvent_t* mine = &p->events[(size_t)slot * R];
+    for (int j = 0; j < R; ++j) {
+        if (t > 0 && p->depth > 1) SB_CUDA(cudaStreamWaitEvent(st, prev[j], 0));   // unit range j of the previous chunk
+        SB_CUDA(cudaGraphLaunch(p->graphs[(size_t)k * R + j], st));
+        SB_CUDA(cudaEventRecord(mine[j], st));
+    }
+    if (out) SB_CUDA(cudaMemcpyAsync(out, io.wave_out, p->out_bytes, cudaMemcpyDefault, st));
+    p->n_calls = t + 1;
+    return 0;
+#else
+    (void)window; (void)out;
+    return SB_E_UNSUPP;
+#endif
+}
+
+/* Makes `caller_stream` wait for every chunk fed so far. */
+extern "C" int sb_pipe_end(sb_pipe* p, void* caller_stream) {
+    using namespace sb;
+    SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_end: null pipe");
+#ifndef SB_EMU
+    for (int s = 0; s < p->depth; ++s) {
+        SB_CUDA(cudaEventRecord(p->joins[s], p->streams[s]));
+        SB_CUDA(cudaStreamWaitEvent((cudaStream_t)caller_stream, p->joins[s], 0));
+    }
+#endif
+    return 0;
+}

@@ -8,10 +8,12 @@ into a CUDA graph, and a chunk costs one H2D copy, one graph launch and one D2H 
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
 
+from . import _abi as abi
 from . import _lib
 from .engine import init_state
 
@@ -143,10 +145,10 @@ class PipelinedSession:
     intra-frame BiLSTM, 145 dependent steps), so a single in-order stream leaves half of the GPU idle.  Every state
     tensor of the reference belongs to exactly one unit of the launch sequence (conv_buf: front-end; h0/c0 [+K/V]: one
     GridNet block; deconv_buf/istft_buf: back-end; DE3:403-421, 696-720), hence chunk t+1 depends on chunk t PER UNIT
-    only.  The session keeps `depth` slots (stream, window, result, workspace; chunk t uses slot t % depth and reads
-    state arena t % 2), captures one CUDA graph per (arena, slot, unit range) and links the streams with one event per
-    range: range j of chunk t+1 waits for range j of chunk t.  Results are identical to StreamingSession's (same
-    kernels, same order per unit).
+    only.  The session owns `depth` slots (window, result, workspace; chunk t uses slot t % depth, reads state arena
+    t % 2 and writes the other) and hands them to the library's native pipe (csrc/sb_pipe.cu), which runs chunk t on
+    stream t % depth as one CUDA graph per unit range, range j waiting for range j of chunk t-1.  Results are identical
+    to StreamingSession's (same kernels, same order per unit).
 
     Use: ``begin()`` once after the caller's stream has produced the windows, ``feed(window, out)`` per chunk (returns
     immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
@@ -186,41 +188,51 @@ class PipelinedSession:
         if flat != list(range(n_units)):
             raise ValueError("ranges must cover units 0..%d in order, got %r" % (n_units - 1, ranges))
         self.ranges = [tuple(r) for r in ranges]
-        self.streams = [torch.cuda.Stream(dev) for _ in range(depth)]
-        self.events = [[torch.cuda.Event() for _ in self.ranges] for _ in range(depth)]
-        self._fork = torch.cuda.Event()
         self.n_calls = 0
-        self._capture()
+        self._pipe = None
+        self._build()
 
     def _call(self, p: int, slot: int):
         return self.engine.prepare(self.x[slot], self.dis, _shallow(self.states[p]), out=self.y[slot],
                                    new_state=self.states[p ^ 1], film=self.film, workspace=self.ws[slot])
 
-    def _capture(self):
+    def _build(self):
+        """Warm up eagerly (shared-memory opt-ins, lazy module loading), then hand the per-(arena, slot) sb_net_io
+        blocks to the native pipe, which captures one CUDA graph per unit range on its own streams."""
+        lib = self.engine.lib
         saved = [_clone_state(s) for s in self.states]
-        cur = torch.cuda.current_stream(self.device)
-        side = self.streams[0]
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):                       # warm-up eagerly (smem opt-ins, lazy module loading)
+        with torch.cuda.device(self.device):
             for p in (0, 1):
                 self._call(p, 0).launch()
-        cur.wait_stream(side)
-        torch.cuda.synchronize(self.device)
-        self.graphs = {}
-        period = self.depth if self.depth % 2 == 0 else 2 * self.depth
-        for t in range(period):                             # every (arena, slot) pair that occurs
-            p, slot = t % 2, t % self.depth
-            call = self._call(p, slot)
-            gs = []
-            for lo, hi in self.ranges:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    call.launch(lo, hi)
-                gs.append(g)
-            self.graphs[(p, slot)] = gs
-        torch.cuda.synchronize(self.device)
+            torch.cuda.synchronize(self.device)
+            period = self.depth if self.depth % 2 == 0 else 2 * self.depth
+            self._calls = [self._call(t % 2, t % self.depth) for t in range(period)]     # keeps the tensors alive
+            ios = (abi.NetIO * period)(*[c.io for c in self._calls])
+            n = len(self.ranges)
+            first = (ctypes.c_int * n)(*[lo for lo, _ in self.ranges])
+            last = (ctypes.c_int * n)(*[hi for _, hi in self.ranges])
+            handle = ctypes.c_void_p()
+            rc = lib.sb_pipe_create(self.engine.packed.desc_ref(), ios, period, self.depth, first, last, n,
+                                    ctypes.byref(handle))
+            abi.check(lib, rc, "sb_pipe_create")
+            self._pipe = handle
+            torch.cuda.synchronize(self.device)
         for s, z in zip(self.states, saved):
             StreamingSession._copy_state(s, z)
+
+    def close(self):
+        if self._pipe is not None:
+            self.engine.lib.sb_pipe_destroy(self._pipe)
+            self._pipe = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _cur(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     # ------------------------------------------------------------------------------------------------------
     @property
@@ -239,41 +251,35 @@ class PipelinedSession:
                 else:
                     v.zero_()
         self.n_calls = 0
+        lib = self.engine.lib
+        abi.check(lib, lib.sb_pipe_reset(self._pipe), "sb_pipe_reset")
 
     def begin(self):
-        """Order every slot stream after what the caller's current stream has enqueued so far (the windows, a
+        """Order every stream of the pipe after what the caller's current stream has enqueued so far (the windows, a
         reset(), a load_state())."""
-        self._fork.record(torch.cuda.current_stream(self.device))
-        for s in self.streams:
-            s.wait_event(self._fork)
+        lib = self.engine.lib
+        abi.check(lib, lib.sb_pipe_begin(self._pipe, self._cur()), "sb_pipe_begin")
 
     def feed(self, window: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Enqueue one chunk: window [B, M, chunk + lookahead] (host or device) -> `out` [B, S, chunk] (or the slot's
-        device buffer, valid until `depth` calls later).  Returns without waiting."""
-        t = self.n_calls
-        p, slot = t % 2, t % self.depth
-        s = self.streams[slot]
-        prev = self.events[(t - 1) % self.depth]
-        mine = self.events[slot]
-        with torch.cuda.stream(s):
-            self.x[slot].copy_(window, non_blocking=True)
-            for j, g in enumerate(self.graphs[(p, slot)]):
-                if t > 0 and self.depth > 1:
-                    s.wait_event(prev[j])                   # unit range j of the previous chunk (another stream)
-                g.replay()
-                mine[j].record(s)
-            res = self.y[slot]
-            if out is not None:
-                out.copy_(res, non_blocking=True)
-                res = out
+        """Enqueue one chunk: window [B, M, chunk + lookahead] (pinned host or device) -> `out` [B, S, chunk] (or the
+        slot's device buffer, valid until `depth` calls later).  Returns without waiting."""
+        slot = self.n_calls % self.depth
+        if window.shape != self.x[slot].shape or window.dtype != torch.float32 or not window.is_contiguous():
+            raise ValueError("window must be a contiguous float32 tensor of shape %s" % (tuple(self.x[slot].shape),))
+        optr = None
+        if out is not None:
+            if out.shape != self.y[slot].shape or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous float32 tensor of shape %s" % (tuple(self.y[slot].shape),))
+            optr = out.data_ptr()
+        lib = self.engine.lib
+        abi.check(lib, lib.sb_pipe_feed(self._pipe, window.data_ptr(), optr), "sb_pipe_feed")
         self.n_calls += 1
-        return res
+        return out if out is not None else self.y[slot]
 
     def end(self):
         """Make the caller's current stream wait for every chunk fed so far."""
-        cur = torch.cuda.current_stream(self.device)
-        for s in self.streams:
-            cur.wait_stream(s)
+        lib = self.engine.lib
+        abi.check(lib, lib.sb_pipe_end(self._pipe, self._cur()), "sb_pipe_end")
 
     @property
     def state(self) -> dict:
@@ -281,6 +287,7 @@ class PipelinedSession:
         return self.states[self.parity]
 
     def load_state(self, state: dict):
+        """Adopt a reference-layout state dict as the state the next chunk starts from (on the caller's stream)."""
         StreamingSession._copy_state(self.states[self.parity], state)
 
     def launches_per_step(self) -> int:

@@ -7,7 +7,7 @@ timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --ranges $r --depth $d
 import json
 try:
     d=json.loads(open("gpurun_out/bench_pipe_r${r}_d$d.json").read().strip().splitlines()[-1])
-    print("ranges=$r depth=$d", "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "in_order", round(d["in_order"]["value"]), "ms", round(d["ms_per_step"],1), d["streaming_vs_offline_maxabs"])
+    print("ranges=$r depth=$d", "enq_ms", round(d["config"]["host_enqueue_ms_per_step"],1), "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "in_order", round(d["in_order"]["value"]), "ms", round(d["ms_per_step"],1), d["streaming_vs_offline_maxabs"])
 except Exception as e:
     print("ranges=$r depth=$d failed", e); print(open("gpurun_out/bench_pipe_r${r}_d$d.err").read()[-2000:])
 PY
