@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pipeline", type=int, default=int(os.environ.get("SB_PIPELINE", "1")))
     ap.add_argument("--ranges", type=int, default=0, help="pipelined session: number of unit ranges (0 = default)")
-    ap.add_argument("--depth", type=int, default=2, help="pipelined session: chunks in flight")
+    ap.add_argument("--depth", type=int, default=6, help="pipelined session: chunks in flight")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -800,16 +800,19 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
 // =============================================================================================================
 // host side
 // =============================================================================================================
-// Cost model in SM cycles per recurrent step, measured on B200 (profiles/r01_lstm_bench.txt):
-//   tile : a warp (8 sequences) needs ~24.5k cycles per step while <= 4 warps share an SM, ~32k with all 8 resident
-//   ws   : ~400 (one sequence per CTA, warp-specialised);  lane1/2/4 : 1360 / 2530 / 4950 (1/2/4 sequences per CTA)
+// Cost model in SM cycles per recurrent step, measured on B200 at 1965 MHz (profiles/r01_lstm_bench.txt):
+//   tile : one warp (8 sequences) per SMSP needs ~13.2k cycles per step, two warps per SMSP ~20.7k (the launch gives a
+//          CTA ceil(tasks / SMs) <= 8 warps); more tasks than 8 x SMs run in rounds
+//   ws   : ~600-790 (one sequence per CTA, warp-specialised);  lane1/2/4 : 1360 / 2530 / 4950 (1/2/4 sequences per CTA)
+//   tc   : ~15.5k per step for up to one wave of 128-sequence CTAs (tcgen05 gate GEMM + 256-thread cell update), ~10.8k
+//          per wave once several waves keep every SM busy; wins when the tile family needs several rounds (offline)
 // plus a launch + prologue constant; the cheapest family for (rows, dirs, steps) wins.
-static int pick_algo(int n_rows, int n_dirs, int S, int sms) {
-    const double tasks = (double)ceil_div(n_rows, 8) * n_dirs;
-    const double resident = sms * 8.0;
-    const double rounds = tasks <= resident ? 1.0 : (double)ceil_div((int)tasks, (int)resident);
-    const double wps = tasks / sms > 8.0 ? 8.0 : tasks / sms;
-    const double tile_step = wps <= 4.0 ? 9000.0 : 9000.0 + (wps - 4.0) * 1500.0;
+static int pick_algo(int n_rows, int n_dirs, int S, int sms, bool tc_ok) {
+    const int tasks = ceil_div(n_rows, 8) * n_dirs;
+    const int resident = sms * 8;
+    const double rounds = tasks <= resident ? 1.0 : (double)ceil_div(tasks, resident);
+    const int warps_per_cta = tasks >= resident ? 8 : ceil_div(tasks, sms);
+    const double tile_step = warps_per_cta <= 4 ? 13200.0 : 20700.0;
     const double tile = rounds * S * tile_step + 30000.0;
     auto per_cta = [&](int rl, double step, double fixed) {
         return (double)ceil_div(ceil_div(n_rows, rl) * n_dirs, sms) * (S * step + fixed);
@@ -819,14 +822,27 @@ static int pick_algo(int n_rows, int n_dirs, int S, int sms) {
     int best = SB_ALGO_TILE;
     for (int k = SB_ALGO_LANE1; k <= SB_ALGO_WS; ++k)
         if (cost[k] < cost[best]) best = k;
+    if (tc_ok) {
+        const double waves = (double)(ceil_div(n_rows, 128) * n_dirs) / sms;
+        const double tc = S * (waves <= 1.0 ? 15500.0 : waves * 10800.0) + 60000.0;
+        if (tc < cost[best]) return SB_ALGO_TC;
+    }
     return best;
 }
 
 template <int C, bool RAW_H>
 static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
     const int sms = sm_count();
-    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sms);
+#ifdef SB_EMU
+    constexpr bool tc_ok = false;           // tensor-core instructions cannot be emulated on the host
+#else
+    constexpr bool tc_ok = C == 32 && !RAW_H;
+#endif
+    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sms, tc_ok);
     switch (algo) {
+        case SB_ALGO_TC:
+            if constexpr (C == 32 && !RAW_H) return run_seq_tc(a, st);
+            break;
         case SB_ALGO_TILE4:
         case SB_ALGO_TILE: {
             // 8 sequences per warp; 4 when the call is a step or two long (streaming inter path) and rows are few enough

@@ -153,7 +153,7 @@ class PipelinedSession:
     Use: ``begin()`` once after the caller's stream has produced the windows, ``feed(window, out)`` per chunk (returns
     immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
 
-    def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 2):
+    def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 6):
         self.net = net
         self.cfg = cfg = net.cfg
         self.engine = eng = net.engine()
@@ -176,8 +176,8 @@ class PipelinedSession:
         self.film = eng.film_table(self.dis) if self.dis is not None else None
         self.states = [init_state(cfg, batch_size, dev), init_state(cfg, batch_size, dev)]
         n_units = cfg.B + 2
-        if ranges is None:
-            ranges = 2
+        if ranges is None:                                  # one range per GridNet block: measured best on B200 with
+            ranges = cfg.B                                  # depth >= 5 (profiles/r01_pipeline_sweep.txt)
         if isinstance(ranges, int):                         # `ranges` near-equal groups of blocks
             k = max(1, min(int(ranges), cfg.B))
             cuts = [round(i * cfg.B / k) for i in range(k + 1)]

@@ -60,6 +60,17 @@ def test_inter_lstm(lib, algo, variant, kw):
     _ok(kc.check_inter(lib, DEV, variant, kw, algo, B=1, T=1, alias_state=True, two_inputs=False))
 
 
+def test_tensor_core_lstm(lib):
+    """SB_ALGO_TC (tcgen05, bf16 hi/lo split with fp32 accumulation in TMEM): same bar as the fp32 SIMT families, rows
+    that do not fill a 128-row tile, several tiles, carried and aliased state."""
+    TC = abi.SB_ALGO_TC
+    _ok(kc.check_intra(lib, DEV, "dis_embed", SYN, TC, B=2, T=13, block=1))
+    _ok(kc.check_intra(lib, DEV, "dis_embed", SYN, TC, B=1, T=300, block=0))
+    _ok(kc.check_inter(lib, DEV, "dis_embed", SYN, TC, B=2, T=37, block=2))
+    _ok(kc.check_inter(lib, DEV, "dis_embed", SYN, TC, B=1, T=1, alias_state=True, two_inputs=False))
+    _ok(kc.check_intra(lib, DEV, "optim", dict(OPI, conv_lstm=False), TC, B=1, T=5, block=1))
+
+
 @pytest.mark.parametrize("variant,kw,B,T,mask", [("dis_embed", SYN, 2, 5, False), ("dis_embed", SYN, 2, 1, False),
                                                  ("dis_embed", SYN, 1, 11, True), ("optim", RPI, 1, 3, False),
                                                  ("dis_embed", SYN, 2, 3, True), ("dis_embed", SYN, 1, 8, False),
@@ -90,7 +101,8 @@ def test_golden_through_c_abi(lib, name):
 
 
 @pytest.mark.parametrize("intra,inter", [(abi.SB_ALGO_TILE, abi.SB_ALGO_TILE), (abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2),
-                                         (abi.SB_ALGO_LANE4, abi.SB_ALGO_LANE1), (abi.SB_ALGO_WS, abi.SB_ALGO_WS)])
+                                         (abi.SB_ALGO_LANE4, abi.SB_ALGO_LANE1), (abi.SB_ALGO_WS, abi.SB_ALGO_WS),
+                                         (abi.SB_ALGO_TC, abi.SB_ALGO_TC)])
 def test_golden_with_forced_lstm_algos(lib, intra, inter):
     pc.assert_parity(pc.run_golden(lib, DEV, "syn_offline", intra, inter))
 

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -k "pipelined or streaming" > gpurun_out/pytest_pipe.log 2>&1; tail -5 gpurun_out/pytest_pipe.log
-for cfg in "2 2" "2 3" "3 3" "6 3" "3 4" "6 4" "6 2"; do
+for cfg in "6 4" "6 5" "6 6" "6 8" "4 4" "3 6"; do
 set -- $cfg; r=$1; d=$2
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --ranges $r --depth $d > gpurun_out/bench_pipe_r${r}_d$d.json 2> gpurun_out/bench_pipe_r${r}_d$d.err; python - <<PY
 import json
