@@ -68,10 +68,11 @@ class NetBase(nn.Module):
             y = y[:, :, :-mod]
         return y, next_state
 
-    def streaming(self, batch_size: int, dis_embed=None, use_graph: bool = True, pipelined: bool = False, ranges=None, depth: int = 6):
+    def streaming(self, batch_size: int, dis_embed=None, use_graph: bool = True, pipelined: bool = False, ranges=None, depth: int = 6,
+                  intra_algo=None):
         """A chunk-by-chunk session with device-resident state and captured CUDA graphs (see streaming.py).
         pipelined=True: asynchronous feed() with consecutive chunks overlapping on two streams (throughput mode)."""
         from .streaming import PipelinedSession, StreamingSession
         if pipelined:
-            return PipelinedSession(self, batch_size, dis_embed, ranges=ranges, depth=depth)
+            return PipelinedSession(self, batch_size, dis_embed, ranges=ranges, depth=depth, intra_algo=intra_algo)
         return StreamingSession(self, batch_size, dis_embed, use_graph=use_graph)

@@ -94,7 +94,8 @@ class Engine:
     # -- the forward pass ------------------------------------------------------------------------------------
     def prepare(self, wave: torch.Tensor, dis_embed: Optional[torch.Tensor], state: dict,
                 out: Optional[torch.Tensor] = None, new_state: Optional[dict] = None,
-                film: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> "PreparedCall":
+                film: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                intra_algo: Optional[int] = None, inter_algo: Optional[int] = None) -> "PreparedCall":
         """Validates one call and fills its sb_net_io (no launch).  wave [B, M, stride*T + n_fft - stride]; the result
         goes to `out` [B, S, stride*T]; the next state is written into fresh tensors unless `new_state` supplies them."""
         cfg = self.cfg
@@ -111,7 +112,8 @@ class Engine:
 
         io = abi.NetIO()
         io.B, io.T = B, T
-        io.intra_algo, io.inter_algo = self.intra_algo, self.inter_algo
+        io.intra_algo = self.intra_algo if intra_algo is None else intra_algo
+        io.inter_algo = self.inter_algo if inter_algo is None else inter_algo
         io.wave = wave.data_ptr()
         keep = [wave]
         if cfg.variant == "dis_embed":

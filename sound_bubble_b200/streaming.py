@@ -153,7 +153,8 @@ class PipelinedSession:
     Use: ``begin()`` once after the caller's stream has produced the windows, ``feed(window, out)`` per chunk (returns
     immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
 
-    def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 6):
+    def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 6,
+                 intra_algo: Optional[int] = None):
         self.net = net
         self.cfg = cfg = net.cfg
         self.engine = eng = net.engine()
@@ -188,13 +189,15 @@ class PipelinedSession:
         if flat != list(range(n_units)):
             raise ValueError("ranges must cover units 0..%d in order, got %r" % (n_units - 1, ranges))
         self.ranges = [tuple(r) for r in ranges]
+        self.intra_algo = intra_algo          # None = the engine's choice (SB_ALGO_AUTO unless the caller forced one)
         self.n_calls = 0
         self._pipe = None
         self._build()
 
     def _call(self, p: int, slot: int):
         return self.engine.prepare(self.x[slot], self.dis, _shallow(self.states[p]), out=self.y[slot],
-                                   new_state=self.states[p ^ 1], film=self.film, workspace=self.ws[slot])
+                                   new_state=self.states[p ^ 1], film=self.film, workspace=self.ws[slot],
+                                   intra_algo=self.intra_algo)
 
     def _build(self):
         """Warm up eagerly (shared-memory opt-ins, lazy module loading), then hand the per-(arena, slot) sb_net_io
