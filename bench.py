@@ -217,7 +217,7 @@ def run_ours(args, rank, world, local_rank):
     # throughput mode: the same one-call-per-chunk protocol, calls asynchronous, consecutive chunks overlapping on two
     # streams with per-unit dependencies (sound_bubble_b200/streaming.py::PipelinedSession)
     pipe = net.streaming(BATCH, dis, pipelined=True, ranges=args.ranges or None, depth=args.depth,
-                         intra_algo=args.pipe_intra_algo or None) if args.pipeline else None
+                         intra_algo=args.pipe_intra_algo or None, inter_algo=args.pipe_inter_algo or None) if args.pipeline else None
 
     def pass_in_order(win, out):
         sess.reset()
@@ -354,6 +354,7 @@ def run_ours(args, rank, world, local_rank):
                    "pipelined": pipe is not None, "unit_ranges": pipe.ranges if pipe is not None else None,
                    "pipeline_depth": pipe.depth if pipe is not None else 1,
                    "pipeline_intra_algo": pipe.intra_algo if pipe is not None else None,
+                   "pipeline_inter_algo": pipe.inter_algo if pipe is not None else None,
                    "host_enqueue_ms_per_step": 1e3 * statistics.median(enqueue_s) if enqueue_s else None,
                    "parallelism": "dp%d (utterances sharded, no collective on the data path)" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(win_host.numel() * 4),
@@ -378,6 +379,7 @@ def main():
     ap.add_argument("--pipeline", type=int, default=int(os.environ.get("SB_PIPELINE", "1")))
     ap.add_argument("--ranges", type=int, default=0, help="pipelined session: number of unit ranges (0 = default)")
     ap.add_argument("--pipe-intra-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the intra path")
+    ap.add_argument("--pipe-inter-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the inter path")
     ap.add_argument("--depth", type=int, default=6, help="pipelined session: chunks in flight")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -69,10 +69,11 @@ class NetBase(nn.Module):
         return y, next_state
 
     def streaming(self, batch_size: int, dis_embed=None, use_graph: bool = True, pipelined: bool = False, ranges=None, depth: int = 6,
-                  intra_algo=None):
+                  intra_algo=None, inter_algo=None):
         """A chunk-by-chunk session with device-resident state and captured CUDA graphs (see streaming.py).
         pipelined=True: asynchronous feed() with consecutive chunks overlapping on two streams (throughput mode)."""
         from .streaming import PipelinedSession, StreamingSession
         if pipelined:
-            return PipelinedSession(self, batch_size, dis_embed, ranges=ranges, depth=depth, intra_algo=intra_algo)
+            return PipelinedSession(self, batch_size, dis_embed, ranges=ranges, depth=depth, intra_algo=intra_algo,
+                                    inter_algo=inter_algo)
         return StreamingSession(self, batch_size, dis_embed, use_graph=use_graph)

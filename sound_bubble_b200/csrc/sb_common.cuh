@@ -179,6 +179,15 @@ __device__ __forceinline__ float ldg1_stream(const float* p) {
 }
 // plain (coherent) loads for buffers an aliasing output of the same launch may point at
 __device__ __forceinline__ float ld_plain(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
+__device__ __forceinline__ float4 ld_plain4(const float* p) {
+#ifdef SB_EMU
+    return ld4(p);
+#else
+    float4 r;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#endif
+}
 
 // Asynchronous global -> shared copies (LDGSTS): every copy of a staging loop is in flight at once instead of one L2
 // round trip per loop iteration; cp_async_wait_all() before the __syncthreads() that publishes the tile.

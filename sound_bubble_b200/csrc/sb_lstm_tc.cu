@@ -34,7 +34,9 @@ constexpr int kAChunkBytes = (kRows / 8) * 128;            // LBO of A: 2048
 constexpr int kWChunkBytes = (kN / 8) * 128;               // LBO of the gate matrix: 4096
 constexpr int kPChunkBytes = (kC / 8) * 128;               // LBO of the projection: 512
 constexpr int kABytes = kRows * kK * 2, kWBytes = kN * kK * 2, kPBytes = kC * kH * 2;
-constexpr int kSmemBytes = 2 * kWBytes + 2 * kPBytes + 2 * kABytes + kN * 4 + 64;      // + bias + barriers
+constexpr int kStageStride = kH + 4;                       // floats per row of the (h | c) staging tile: conflict-free LDS.128
+constexpr int kStageBytes = kRows * kStageStride * 4;
+constexpr int kSmemBytes = 2 * kWBytes + 2 * kPBytes + 2 * kABytes + kN * 4 + 64 + 2 * kStageBytes;   // + bias + barriers + (h, c) staging
 constexpr uint32_t kTmemCols = 512;                        // 256 gate columns + 32 projection columns -> next power of 2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,6 +138,8 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     float* bias_s = reinterpret_cast<float*>(a_lo + kABytes);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bias_s + kN);         // [2]: units 0..31 (+ projection), units 32..63
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    float* stage_h = reinterpret_cast<float*>(mbar + 8);    // [kRows][kStageStride] each: the state tiles between their global
+    float* stage_c = stage_h + kRows * kStageStride;        // layout (row-contiguous, coalesced) and the (row, half) threads
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
@@ -171,18 +175,45 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     const long long xbase = row_base(a, crow);
     const long long fbase = (long long)(crow / a.film_row_div) * S * kC;
     float c[32];
-    {   // initial (h, c): thread (row, hf) owns units 32*hf .. 32*hf + 31
-        float h8[8];
+    // The tile's rows are consecutive in [n_rows][H]: the CTA moves them as one contiguous block (coalesced float4) through
+    // the staging tile; thread (row, hf) then owns units 32*hf .. 32*hf + 31 of its row.
+    const int tile_row0 = blockIdx.x * kRows;
+    auto stage_in = [&](float* stage, const float* src) {   // plain loads: hN / cN may alias h0 / c0
+        for (int i = tid; i < kRows * (kH / 4); i += 256) {
+            const int rr = i / (kH / 4), c4 = i % (kH / 4);
+            const int gr = min(tile_row0 + rr, a.n_rows - 1);
+            st4(stage + rr * kStageStride + 4 * c4, ld_plain4(src + (long long)gr * kH + 4 * c4));
+        }
+    };
+    auto stage_out = [&](const float* stage, float* dst) {
+        for (int i = tid; i < kRows * (kH / 4); i += 256) {
+            const int rr = i / (kH / 4), c4 = i % (kH / 4);
+            if (tile_row0 + rr < a.n_rows)
+                st4(dst + (long long)(tile_row0 + rr) * kH + 4 * c4, ld4(stage + rr * kStageStride + 4 * c4));
+        }
+    };
+    if (a.h0) {
+        stage_in(stage_c, a.c0);
+        stage_in(stage_h, a.h0);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = ld4(stage_c + r * kStageStride + 32 * hf + 4 * i);
+            c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int u = 32 * hf + 8 * ch + j;
-                h8[j] = a.h0 ? ld_plain(a.h0 + (long long)crow * kH + u) : 0.0f;
-                c[8 * ch + j] = a.c0 ? ld_plain(a.c0 + (long long)crow * kH + u) : 0.0f;
-            }
+            const float4 v0 = ld4(stage_h + r * kStageStride + 32 * hf + 8 * ch);
+            const float4 v1 = ld4(stage_h + r * kStageStride + 32 * hf + 8 * ch + 4);
+            const float h8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) c[j] = 0.0f;
+        const float h8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
     }
     float4 g4[4], b4[4];                                    // LayerNorm gain / bias of this thread's 16 channels
 #pragma unroll
@@ -362,12 +393,16 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     mbar_wait(mbar + 0, S & 1);
     fence_after();
     emit(S - 1, res_prev);
-    if (a.hN && rvalid) {
+    if (a.hN) {                                             // same staging tiles, the other way (the initial-state reads
+                                                            // were over before the first step's barrier)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            a.hN[(long long)grow * kH + 32 * hf + j] = hlast[j];
-            a.cN[(long long)grow * kH + 32 * hf + j] = c[j];
+        for (int i = 0; i < 8; ++i) {
+            st4(stage_h + r * kStageStride + 32 * hf + 4 * i, make_float4(hlast[4 * i], hlast[4 * i + 1], hlast[4 * i + 2], hlast[4 * i + 3]));
+            st4(stage_c + r * kStageStride + 32 * hf + 4 * i, make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]));
         }
+        __syncthreads();
+        stage_out(stage_h, a.hN);
+        stage_out(stage_c, a.cN);
     }
     fence_before();
     __syncthreads();

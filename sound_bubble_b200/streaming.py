@@ -154,7 +154,7 @@ class PipelinedSession:
     immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
 
     def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 6,
-                 intra_algo: Optional[int] = None):
+                 intra_algo: Optional[int] = None, inter_algo: Optional[int] = None):
         self.net = net
         self.cfg = cfg = net.cfg
         self.engine = eng = net.engine()
@@ -190,6 +190,11 @@ class PipelinedSession:
             raise ValueError("ranges must cover units 0..%d in order, got %r" % (n_units - 1, ranges))
         self.ranges = [tuple(r) for r in ranges]
         self.intra_algo = intra_algo          # None = the engine's choice (SB_ALGO_AUTO unless the caller forced one)
+        # Throughput mode pays in SM-time, not latency: the one-step inter-frame call as a tcgen05 GEMM occupies a quarter
+        # of the SMs the SIMT tile kernel needs (128-row tiles), which leaves room for the other chunks' recurrences.
+        if inter_algo is None and eng.inter_algo == abi.SB_ALGO_AUTO and cfg.D == 32 and batch_size * cfg.n_freqs >= 1024:
+            inter_algo = abi.SB_ALGO_TC
+        self.inter_algo = inter_algo
         self.n_calls = 0
         self._pipe = None
         self._build()
@@ -197,7 +202,7 @@ class PipelinedSession:
     def _call(self, p: int, slot: int):
         return self.engine.prepare(self.x[slot], self.dis, _shallow(self.states[p]), out=self.y[slot],
                                    new_state=self.states[p ^ 1], film=self.film, workspace=self.ws[slot],
-                                   intra_algo=self.intra_algo)
+                                   intra_algo=self.intra_algo, inter_algo=self.inter_algo)
 
     def _build(self):
         """Warm up eagerly (shared-memory opt-ins, lazy module loading), then hand the per-(arena, slot) sb_net_io
