@@ -192,6 +192,27 @@ def stage_profile(lib, fn):
     return {name: (ms[i], calls[i]) for i, name in enumerate(abi.SB_STAGES) if calls[i]}
 
 
+def ncu_dram_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of its
+    `ncu --set full` capture (profiles/rNN_prof_*.txt, written by tools/summarize_profiles.py).  None if there is none."""
+    import glob
+    import re
+    vals = []
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prof_*.txt"))):
+        cur = None
+        for line in open(path):
+            if line.startswith("== "):
+                cur = {"name": line, "r": None, "w": None}
+            m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if m and cur is not None and kernel_substr in cur["name"]:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
+                cur["r" if m.group(1) == "read" else "w"] = float(m.group(2)) * scale
+                if cur["r"] is not None and cur["w"] is not None:
+                    vals.append(cur["r"] + cur["w"])
+                    cur = None
+    return sum(vals) / len(vals) if vals else None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from sound_bubble_b200 import Net, _lib
@@ -310,7 +331,8 @@ def run_ours(args, rank, world, local_rank):
     peak_bw = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes.get(dom, 0) * BATCH / (dom_ms * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak_bw, "unit": "GB/s",
-                "frac": achieved / peak_bw, "traffic": None,
+                "frac": achieved / peak_bw,
+                "traffic": ncu_dram_traffic({"intra": "lstm_ws", "inter": "lstm_tile"}.get(dom, dom)),
                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                 "avg_launch_us": dom_ms * 1e3, "bytes_per_launch": alg_bytes.get(dom, 0) * BATCH,
                 "share_of_step": prof[dom][0] / tot,

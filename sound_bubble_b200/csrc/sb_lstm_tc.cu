@@ -36,7 +36,8 @@ constexpr int kPChunkBytes = (kC / 8) * 128;               // LBO of the project
 constexpr int kABytes = kRows * kK * 2, kWBytes = kN * kK * 2, kPBytes = kC * kH * 2;
 constexpr int kStageStride = kH + 4;                       // floats per row of the (h | c) staging tile: conflict-free LDS.128
 constexpr int kStageBytes = kRows * kStageStride * 4;
-constexpr int kSmemBytes = 2 * kWBytes + 2 * kPBytes + 2 * kABytes + kN * 4 + 64 + 2 * kStageBytes;   // + bias + barriers + (h, c) staging
+constexpr int kSmemBytes = 2 * kWBytes + 2 * kPBytes + 2 * kABytes + kN * 4 + 64;      // + bias + barriers
+static_assert(kStageBytes <= 2 * kABytes && 2 * kStageBytes <= 2 * kWBytes, "state staging tiles alias the operand images");
 constexpr uint32_t kTmemCols = 512;                        // 256 gate columns + 32 projection columns -> next power of 2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,8 +139,11 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     float* bias_s = reinterpret_cast<float*>(a_lo + kABytes);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bias_s + kN);         // [2]: units 0..31 (+ projection), units 32..63
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
-    float* stage_h = reinterpret_cast<float*>(mbar + 8);    // [kRows][kStageStride] each: the state tiles between their global
-    float* stage_c = stage_h + kRows * kStageStride;        // layout (row-contiguous, coalesced) and the (row, half) threads
+    // [kRows][kStageStride] staging tiles carry the state between its global layout (row-contiguous, coalesced) and the
+    // (row, half) threads.  They alias operand images that are idle at that moment (a bigger carve-out would cost L1):
+    float* stage_in_buf = reinterpret_cast<float*>(a_hi);   // prologue: before anything is written into A
+    float* stage_h = reinterpret_cast<float*>(w_hi);        // epilogue: after the last MMA has completed
+    float* stage_c = stage_h + kRows * kStageStride;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
@@ -178,13 +182,6 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     // The tile's rows are consecutive in [n_rows][H]: the CTA moves them as one contiguous block (coalesced float4) through
     // the staging tile; thread (row, hf) then owns units 32*hf .. 32*hf + 31 of its row.
     const int tile_row0 = blockIdx.x * kRows;
-    auto stage_in = [&](float* stage, const float* src) {   // plain loads: hN / cN may alias h0 / c0
-        for (int i = tid; i < kRows * (kH / 4); i += 256) {
-            const int rr = i / (kH / 4), c4 = i % (kH / 4);
-            const int gr = min(tile_row0 + rr, a.n_rows - 1);
-            st4(stage + rr * kStageStride + 4 * c4, ld_plain4(src + (long long)gr * kH + 4 * c4));
-        }
-    };
     auto stage_out = [&](const float* stage, float* dst) {
         for (int i = tid; i < kRows * (kH / 4); i += 256) {
             const int rr = i / (kH / 4), c4 = i % (kH / 4);
@@ -193,18 +190,40 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
         }
     };
     if (a.h0) {
-        stage_in(stage_c, a.c0);
-        stage_in(stage_h, a.h0);
+        // both tiles in flight at once (plain loads: hN / cN may alias h0 / c0), then through the one staging tile in turn
+        float4 cin[8], hin[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = tid + 256 * k, rr = i / (kH / 4), c4 = i % (kH / 4);
+            const long long off = (long long)min(tile_row0 + rr, a.n_rows - 1) * kH + 4 * c4;
+            cin[k] = ld_plain4(a.c0 + off);
+            hin[k] = ld_plain4(a.h0 + off);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = tid + 256 * k;
+            st4(stage_in_buf + (i / (kH / 4)) * kStageStride + 4 * (i % (kH / 4)), cin[k]);
+        }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 v = ld4(stage_c + r * kStageStride + 32 * hf + 4 * i);
+            const float4 v = ld4(stage_in_buf + r * kStageStride + 32 * hf + 4 * i);
             c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = tid + 256 * k;
+            st4(stage_in_buf + (i / (kH / 4)) * kStageStride + 4 * (i % (kH / 4)), hin[k]);
+        }
+        __syncthreads();
+        float4 hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hv[i] = ld4(stage_in_buf + r * kStageStride + 32 * hf + 4 * i);
+        __syncthreads();                                    // the staging tile is dead: A may be written
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            const float4 v0 = ld4(stage_h + r * kStageStride + 32 * hf + 8 * ch);
-            const float4 v1 = ld4(stage_h + r * kStageStride + 32 * hf + 8 * ch + 4);
+            const float4 v0 = hv[2 * ch], v1 = hv[2 * ch + 1];
             const float h8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
         }
