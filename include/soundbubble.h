@@ -49,8 +49,9 @@ extern "C" {
 #define SB_ALGO_TILE4 6         /* tile family with 4 sequences per warp (C = 32 only; chosen by TILE for 1-2 step calls) */
 #define SB_ALGO_TC    7         /* tcgen05: 128 sequences per CTA, gate GEMM on the tensor cores as a bf16 hi/lo split   */
                                 /* (3 products, fp32 accumulation in TMEM), cell update from TMEM (C = 32, projected mode) */
-#define SB_ALGO_WS    5         /* 1 sequence per CTA, warp-specialised: 8 recurrence warps (K split over 4 lanes, */
-                                /* packed FFMA2) + 8 helper warps (loads, LayerNorm, input gates, stores)          */
+#define SB_ALGO_WS    5         /* 1 sequence per CTA, warp-specialised: 4 recurrence warps (2 units x 4 gates x K/4 per   */
+                                /* thread, weights in registers, packed FFMA2) + 4 helper warps (loads, LayerNorm, input   */
+                                /* gates, stores)                                                                           */
 
 /* feature modes of the front-end (DE3:486-507) */
 #define SB_FEAT_NONE        0   /* merge_method "None": conv-in sees [Re, Im] only                               */

@@ -6,15 +6,17 @@
 // Both are the same fused "sequence" kernel: [FiLM] -> LayerNorm(C) -> x W_ih^T + h W_hh^T + b -> gates -> Linear ->
 // residual, one launch per (block, path); every activation is read once and written once.
 //
-// Two kernel families share one argument block:
-//   lstm_tile_kernel : throughput path.  [W_ih|W_hh]^T (K x 256 fp32) lives in shared memory; every WARP owns 8
+// The kernel families share one argument block; pick_algo() chooses per call:
+//   lstm_tile_kernel : throughput path.  [W_ih|W_hh]^T (K x 256 fp32) lives in shared memory; every WARP owns 8 (or 4)
 //                      sequences end to end (A operand, gates, cell state, projection), so the step loop has no block
 //                      barrier and the warps of an SM drift apart and overlap FMA / MUFU / LDS phases.  Each lane
 //                      holds an 8-row x 8-column accumulator tile = all four gates of two hidden units (no shuffles
 //                      for the cell update); the output projection of step s-1 rides in the h-part of step s's GEMM.
-//   lstm_lane_kernel : latency path.  1/2/4 sequences per CTA, one gate column per thread with its K weights in
-//                      registers, h broadcast from shared memory, quad shuffles for the cell update, one barrier per
-//                      step.  Used for streaming chunks (B sequences x 145 serial steps) and small batches.
+//   lstm_ws_kernel   : latency path for streaming chunks (B sequences x 145 serial steps).  One sequence per CTA,
+//                      warp-specialised: recurrence warps with the recurrent weights in registers, helper warps for
+//                      loads / LayerNorm / input gates / stores.
+//   lstm_lane_kernel : the earlier latency path (1/2/4 sequences per CTA, one gate column per thread); selectable.
+//   lstm_tc_kernel   : sb_lstm_tc.cu, tcgen05 gate GEMM for large batches of sequences.
 #include <type_traits>
 
 #include "sb_common.cuh"
