@@ -3,7 +3,7 @@
 from ._abi import SoundBubbleError  # noqa: F401
 from .packing import ModelConfig  # noqa: F401
 
-__all__ = ["SoundBubbleError", "ModelConfig", "Net", "NetOptim", "StreamingSession"]
+__all__ = ["SoundBubbleError", "ModelConfig", "Net", "NetOptim", "StreamingSession", "PipelinedSession"]
 
 
 def __getattr__(name):          # lazy: importing the package must not need torch.cuda or the built library
@@ -16,4 +16,7 @@ def __getattr__(name):          # lazy: importing the package must not need torc
     if name == "StreamingSession":
         from .streaming import StreamingSession
         return StreamingSession
+    if name == "PipelinedSession":
+        from .streaming import PipelinedSession
+        return PipelinedSession
     raise AttributeError(name)

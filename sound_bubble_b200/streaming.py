@@ -16,6 +16,7 @@ import torch
 from . import _abi as abi
 from . import _lib
 from .engine import init_state
+from .state_io import StateArena
 
 
 def _clone_state(st):
@@ -46,7 +47,9 @@ class StreamingSession:
                 raise KeyError("dis_embed")
             self.dis = dis_embed.to(dev, torch.float32).contiguous().clone()
         self.film = self.engine.film_table(self.dis) if self.dis is not None else None      # time-invariant: once
-        self.states = [init_state(cfg, batch_size, dev), init_state(cfg, batch_size, dev)]
+        # two state arenas that alternate; each is ONE flat device buffer with the reference-layout dict as views into it
+        self.arenas = [StateArena(init_state(cfg, batch_size, dev)) for _ in (0, 1)]
+        self.states = [a.state for a in self.arenas]
         self.parity = 0
         self.graphs = None
         self.n_calls = 0
@@ -88,14 +91,8 @@ class StreamingSession:
 
     # ------------------------------------------------------------------------------------------------------
     def reset(self):
-        for s in self.states:
-            for k, v in s.items():
-                if isinstance(v, dict):
-                    for b in v.values():
-                        for t in b.values():
-                            t.zero_()
-                else:
-                    v.zero_()
+        for a in self.arenas:
+            a.flat.zero_()
         self.parity = 0
 
     def load_state(self, state: dict):
@@ -175,7 +172,8 @@ class PipelinedSession:
                 raise KeyError("dis_embed")
             self.dis = dis_embed.to(dev, torch.float32).contiguous().clone()
         self.film = eng.film_table(self.dis) if self.dis is not None else None
-        self.states = [init_state(cfg, batch_size, dev), init_state(cfg, batch_size, dev)]
+        self.arenas = [StateArena(init_state(cfg, batch_size, dev)) for _ in (0, 1)]
+        self.states = [a.state for a in self.arenas]
         n_units = cfg.B + 2
         if ranges is None:                                  # one range per GridNet block: measured best on B200 with
             ranges = cfg.B                                  # depth >= 5 (profiles/r01_pipeline_sweep.txt)
@@ -250,14 +248,8 @@ class PipelinedSession:
     def reset(self):
         """Zero the state on the caller's stream (after an end(), so that nothing fed earlier is still running); call
         begin() afterwards."""
-        for s in self.states:
-            for k, v in s.items():
-                if isinstance(v, dict):
-                    for b in v.values():
-                        for t in b.values():
-                            t.zero_()
-                else:
-                    v.zero_()
+        for a in self.arenas:
+            a.flat.zero_()
         self.n_calls = 0
         lib = self.engine.lib
         abi.check(lib, lib.sb_pipe_reset(self._pipe), "sb_pipe_reset")
