@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--ranges", type=int, default=0, help="pipelined session: number of unit ranges (0 = default)")
     ap.add_argument("--pipe-intra-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the intra path")
     ap.add_argument("--pipe-inter-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the inter path")
-    ap.add_argument("--depth", type=int, default=6, help="pipelined session: chunks in flight")
+    ap.add_argument("--depth", type=int, default=8, help="pipelined session: chunks in flight")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

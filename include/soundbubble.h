@@ -330,12 +330,12 @@ typedef struct sb_net_io {
 
 size_t sb_workspace_floats(const sb_net_desc* d, int B, int T);
 int    sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream);
-/* A contiguous part of the same launch sequence.  Units: 0 = front-end (stft_features, conv_in, [film_params]),  */
-/* 1 .. n_blocks = GridNet block i-1, n_blocks+1 = back-end; sb_net_forward == range [0, n_blocks+1].  Activations   */
-/* travel between ranges through io->workspace, so the ranges of one call must use the same sb_net_io.  A range     */
-/* that skips unit 0 of a FiLM model needs io->film.  Used by the pipelined streaming session: consecutive chunks    */
-/* depend on each other per unit only (DE3:403-421, 696-720: every state tensor belongs to one unit), so chunk t+1   */
-/* unit u can run next to chunk t unit u+1 on a second stream.                                                       */
+/* A contiguous part of the same launch sequence.  Units: 0 = front-end (stft_features, conv_in, [film_params]); for */
+/* GridNet block i: 1 + 2i = intra-frame path, 2 + 2i = inter-frame path [+ attention]; 2 n_blocks + 1 = back-end;      */
+/* sb_net_forward == range [0, 2 n_blocks + 1].  Activations travel between ranges through io->workspace, so the ranges */
+/* of one call must use the same sb_net_io.  A range that skips unit 0 of a FiLM model needs io->film.  Used by the     */
+/* pipelined streaming session: consecutive chunks depend on each other per unit only (DE3:403-421, 696-720: every      */
+/* state tensor belongs to one unit), so chunk t+1 unit u can run next to chunk t unit u+1 on another stream.           */
 int    sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first_unit, int last_unit, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------- */

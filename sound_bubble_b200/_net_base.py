@@ -68,7 +68,7 @@ class NetBase(nn.Module):
             y = y[:, :, :-mod]
         return y, next_state
 
-    def streaming(self, batch_size: int, dis_embed=None, use_graph: bool = True, pipelined: bool = False, ranges=None, depth: int = 6,
+    def streaming(self, batch_size: int, dis_embed=None, use_graph: bool = True, pipelined: bool = False, ranges=None, depth: int = 8,
                   intra_algo=None, inter_algo=None):
         """A chunk-by-chunk session with device-resident state and captured CUDA graphs (see streaming.py).
         pipelined=True: asynchronous feed() with consecutive chunks overlapping on two streams (throughput mode)."""

@@ -81,13 +81,15 @@ extern "C" size_t sb_workspace_floats(const sb_net_desc* d, int B, int T) {
     return sb::carve(d, B, T, nullptr).total;
 }
 
-// Units of the launch sequence: 0 = front-end (stft_features, conv_in, [film_params]), 1 .. n_blocks = GridNet block
-// i-1 (intra, inter, [attention]), n_blocks+1 = back-end.  sb_net_forward runs all of them; a pipelined streaming
-// session captures one CUDA graph per range so that consecutive chunks can overlap on two streams (streaming.py).
+// Units of the launch sequence: 0 = front-end (stft_features, conv_in, [film_params]); for GridNet block i: 1 + 2i =
+// its intra-frame path, 2 + 2i = its inter-frame path [+ attention]; 2 n_blocks + 1 = back-end.  sb_net_forward runs all
+// of them; a pipelined streaming session captures one CUDA graph per range so that consecutive chunks can overlap on
+// several streams (sb_pipe.cu).  Carried state lives in units 0 (conv_buf), 2 + 2i (h, c, K/V) and the last (deconv /
+// iSTFT history); the intra units carry none.
 extern "C" int sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first_unit, int last_unit, void* stream) {
     using namespace sb;
     SB_REQUIRE(d && io, SB_E_BADARG, "sb_net_forward: null descriptor");
-    SB_REQUIRE(first_unit >= 0 && first_unit <= last_unit && last_unit <= d->n_blocks + 1, SB_E_BADARG,
+    SB_REQUIRE(first_unit >= 0 && first_unit <= last_unit && last_unit <= 2 * d->n_blocks + 1, SB_E_BADARG,
                "sb_net_forward_range: bad unit range [%d, %d]", first_unit, last_unit);
     SB_REQUIRE(io->wave && io->wave_out && io->workspace, SB_E_BADARG, "sb_net_forward: null wave / wave_out / workspace");
     SB_REQUIRE(io->B > 0 && io->T > 0, SB_E_BADARG, "sb_net_forward: bad B/T");
@@ -128,12 +130,14 @@ extern "C" int sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, i
 
     const size_t film_stride = (size_t)B * d->F * d->C;
     for (int i = 0; i < d->n_blocks; ++i) {
-        if (i + 1 < first_unit || i + 1 > last_unit) continue;
+        const bool do_intra = 1 + 2 * i >= first_unit && 1 + 2 * i <= last_unit;
+        const bool do_inter = 2 + 2 * i >= first_unit && 2 + 2 * i <= last_unit;
+        if (!do_intra && !do_inter) continue;
         const sb_block_desc& bd = d->blocks[i];
         const float* fscale = (film && i > 0) ? film + (size_t)(i - 1) * 2 * film_stride : nullptr;
         const float* fshift = fscale ? fscale + film_stride : nullptr;
-        const float* inter_x1 = nullptr;
-        if (d->conv_lstm) {
+        const float* inter_x1 = d->conv_lstm ? nullptr : w.x2;      // the second intra direction, added on load
+        if (do_intra && d->conv_lstm) {
             sb_intra_conv_args ia{};
             ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y = w.x1;
             ia.conv_w = bd.cl_conv_w; ia.conv_b = bd.cl_conv_b; ia.prelu = bd.cl_prelu;
@@ -142,14 +146,14 @@ extern "C" int sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, i
             ia.ws = w.extra; ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H;
             ia.down = d->lstm_down; ia.tail_mode = d->tail_mode; ia.algo = io->intra_algo;
             { StageTimer tm(stream, SB_STAGE_INTRA); SB_CHECK(sb_intra_convlstm_fwd(&ia, stream)); }
-        } else {
+        } else if (do_intra) {
             sb_intra_args ia{};
             ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y_fwd = w.x1; ia.y_bwd = w.x2;
             ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
             ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H; ia.algo = io->intra_algo;
             { StageTimer tm(stream, SB_STAGE_INTRA); SB_CHECK(sb_intra_lstm_fwd(&ia, stream)); }
-            inter_x1 = w.x2;
         }
+        if (!do_inter) continue;
         sb_inter_args na{};
         na.x0 = w.x1; na.x1 = inter_x1; na.y = w.x0;
         na.h0 = io->h_in[i]; na.c0 = io->c_in[i]; na.hN = io->h_out[i]; na.cN = io->c_out[i];
@@ -166,7 +170,7 @@ extern "C" int sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, i
         }
     }
 
-    if (last_unit <= d->n_blocks) return 0;
+    if (last_unit <= 2 * d->n_blocks) return 0;
     sb_backend_args ba{};
     ba.x = w.x0; ba.deconv_buf_in = io->deconv_buf_in; ba.deconv_buf_out = io->deconv_buf_out;
     ba.istft_buf_in = io->istft_buf_in; ba.istft_buf_out = io->istft_buf_out;
@@ -179,7 +183,7 @@ extern "C" int sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, i
 
 extern "C" int sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream) {
     SB_REQUIRE(d, SB_E_BADARG, "sb_net_forward: null descriptor");
-    return sb_net_forward_range(d, io, 0, d->n_blocks + 1, stream);
+    return sb_net_forward_range(d, io, 0, 2 * d->n_blocks + 1, stream);
 }
 
 extern "C" int sb_profile_begin(void) {

@@ -1,8 +1,8 @@
 // Native runtime of the pipelined streaming session (throughput mode of the edge/causal_infer.py:28-47 protocol).
 //
 // One call per 8 ms chunk, state carried, but consecutive chunks overlap on the GPU: every state tensor of the
-// reference belongs to exactly one unit of the launch sequence (conv_buf: front-end; h0/c0 [+K/V]: one GridNet block;
-// deconv_buf/istft_buf: back-end; DE3:403-421, 696-720), so chunk t+1 depends on chunk t per unit only.  The pipe
+// reference belongs to exactly one unit of the launch sequence (conv_buf: front-end; h0/c0 [+K/V]: the inter-frame path
+// of one GridNet block; deconv_buf/istft_buf: back-end; DE3:403-421, 696-720), so chunk t+1 depends on chunk t per unit only.  The pipe
 // owns `depth` streams; chunk t runs on stream t % depth as a few CUDA graphs (one per unit range, captured here from
 // sb_net_forward_range) and range j of chunk t waits for the event range j of chunk t-1 recorded on its own stream.
 // Per chunk the host issues 2 copies + n_ranges x (wait, graph launch, record): a few microseconds, no Python.
@@ -80,14 +80,14 @@ extern "C" int sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_
     SB_REQUIRE(depth >= 1 && depth <= 16, SB_E_BADARG, "sb_pipe_create: depth %d out of range", depth);
     const int period = depth % 2 == 0 ? depth : 2 * depth;
     SB_REQUIRE(n_ios == period, SB_E_BADARG, "sb_pipe_create: need %d sb_net_io entries for depth %d, got %d", period, depth, n_ios);
-    SB_REQUIRE(n_ranges >= 1 && n_ranges <= SB_MAX_BLOCKS + 2, SB_E_BADARG, "sb_pipe_create: bad number of ranges %d", n_ranges);
+    SB_REQUIRE(n_ranges >= 1 && n_ranges <= 2 * SB_MAX_BLOCKS + 2, SB_E_BADARG, "sb_pipe_create: bad number of ranges %d", n_ranges);
     int next = 0;
     for (int j = 0; j < n_ranges; ++j) {
         SB_REQUIRE(range_first[j] == next && range_last[j] >= range_first[j], SB_E_BADARG,
-                   "sb_pipe_create: ranges must cover units 0..%d in order", d->n_blocks + 1);
+                   "sb_pipe_create: ranges must cover units 0..%d in order", 2 * d->n_blocks + 1);
         next = range_last[j] + 1;
     }
-    SB_REQUIRE(next == d->n_blocks + 2, SB_E_BADARG, "sb_pipe_create: ranges must cover units 0..%d in order", d->n_blocks + 1);
+    SB_REQUIRE(next == 2 * d->n_blocks + 2, SB_E_BADARG, "sb_pipe_create: ranges must cover units 0..%d in order", 2 * d->n_blocks + 1);
     for (int k = 0; k < n_ios; ++k) {
         SB_REQUIRE(ios[k].T == 1 && ios[k].B == ios[0].B && ios[k].B > 0, SB_E_BADARG,
                    "sb_pipe_create: every sb_net_io must describe one frame of the same batch");

@@ -194,7 +194,7 @@ class PreparedCall:
     def __init__(self, engine: Engine, io, keep, out, state, top, blocks):
         self.engine, self.io, self.keep, self.out = engine, io, keep, out
         self._state, self._top, self._blocks = state, top, blocks
-        self.n_units = engine.cfg.B + 2
+        self.n_units = 2 * engine.cfg.B + 2           # front-end, (intra, inter) per block, back-end
 
     def launch(self, first_unit: int = 0, last_unit: Optional[int] = None):
         eng = self.engine

@@ -150,7 +150,7 @@ class PipelinedSession:
     Use: ``begin()`` once after the caller's stream has produced the windows, ``feed(window, out)`` per chunk (returns
     immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
 
-    def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 6,
+    def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 8,
                  intra_algo: Optional[int] = None, inter_algo: Optional[int] = None):
         self.net = net
         self.cfg = cfg = net.cfg
@@ -174,13 +174,19 @@ class PipelinedSession:
         self.film = eng.film_table(self.dis) if self.dis is not None else None
         self.arenas = [StateArena(init_state(cfg, batch_size, dev)) for _ in (0, 1)]
         self.states = [a.state for a in self.arenas]
-        n_units = cfg.B + 2
-        if ranges is None:                                  # one range per GridNet block: measured best on B200 with
-            ranges = cfg.B                                  # depth >= 5 (profiles/r01_pipeline_sweep.txt)
+        # units of sb_net_forward_range: 0 front-end, 1 + 2i / 2 + 2i intra / inter path of block i, 2B + 1 back-end
+        n_units = 2 * cfg.B + 2
+        if ranges is None:                                  # one range per unit: measured best on B200 with depth >= 8
+            ranges = n_units                                # (profiles/r01_pipeline_sweep.txt)
+        if isinstance(ranges, int) and ranges > cfg.B:
+            if ranges >= n_units:                           # every unit on its own
+                ranges = [(u, u) for u in range(n_units)]
+            else:                                           # front-end | one range per block | back-end
+                ranges = [(0, 0)] + [(1 + 2 * i, 2 + 2 * i) for i in range(cfg.B)] + [(n_units - 1, n_units - 1)]
         if isinstance(ranges, int):                         # `ranges` near-equal groups of blocks
             k = max(1, min(int(ranges), cfg.B))
             cuts = [round(i * cfg.B / k) for i in range(k + 1)]
-            ranges = [(cuts[i] + 1, cuts[i + 1]) for i in range(k)]
+            ranges = [(1 + 2 * cuts[i], 2 * cuts[i + 1]) for i in range(k)]
             ranges[0] = (0, ranges[0][1])
             ranges[-1] = (ranges[-1][0], n_units - 1)
         flat = [u for lo, hi in ranges for u in range(lo, hi + 1)]

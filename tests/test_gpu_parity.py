@@ -154,7 +154,7 @@ def test_streaming_session_equals_offline_and_reference():
 
 
 @pytest.mark.parametrize("name,ranges,depth", [("syn_nopad", None, 2), ("syn_nopad", 6, 2), ("syn_nopad", 1, 2),
-                                               ("syn_nopad", 3, 3), ("syn_nopad", 6, 4), ("rpi_offline", None, 2),
+                                               ("syn_nopad", 3, 3), ("syn_nopad", 6, 4), ("syn_nopad", 8, 5), ("rpi_offline", None, 2),
                                                ("rpi_offline", 3, 3), ("syn_attn", 3, 2)])
 def test_pipelined_session_is_bit_identical_to_the_in_order_session(name, ranges, depth):
     """Throughput mode (two streams, per-unit events): same kernels in the same per-unit order, so the waveform and
