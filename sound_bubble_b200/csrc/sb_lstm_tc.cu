@@ -36,7 +36,9 @@ constexpr int kPChunkBytes = (kC / 8) * 128;               // LBO of the project
 constexpr int kABytes = kRows * kK * 2, kWBytes = kN * kK * 2, kPBytes = kC * kH * 2;
 constexpr int kStageStride = kH + 4;                       // floats per row of the (h | c) staging tile: conflict-free LDS.128
 constexpr int kStageBytes = kRows * kStageStride * 4;
-constexpr int kSmemBytes = 2 * kWBytes + 2 * kPBytes + 2 * kABytes + kN * 4 + 64;      // + bias + barriers
+constexpr int kSlabStride = kC + 4;                         // floats per row of the x' slab of one step: conflict-free LDS.128
+constexpr int kSlabBytes = kRows * kSlabStride * 4;
+constexpr int kSmemBytes = 2 * kWBytes + 2 * kPBytes + 2 * kABytes + kN * 4 + 64 + 2 * kSlabBytes;  // + bias + barriers + in/out slabs
 static_assert(kStageBytes <= 2 * kABytes && 2 * kStageBytes <= 2 * kWBytes, "state staging tiles alias the operand images");
 constexpr uint32_t kTmemCols = 512;                        // 256 gate columns + 32 projection columns -> next power of 2
 
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
     // [kRows][kStageStride] staging tiles carry the state between its global layout (row-contiguous, coalesced) and the
     // (row, half) threads.  They alias operand images that are idle at that moment (a bigger carve-out would cost L1):
+    float* slab = reinterpret_cast<float*>(mbar + 8);       // [kRows][kSlabStride]: x' of the next step, loaded coalesced
+    float* oslab = slab + kRows * kSlabStride;              // [kRows][kSlabStride]: output of the previous step, stored coalesced
     float* stage_in_buf = reinterpret_cast<float*>(a_hi);   // prologue: before anything is written into A
     float* stage_h = reinterpret_cast<float*>(w_hi);        // epilogue: after the last MMA has completed
     float* stage_c = stage_h + kRows * kStageStride;
@@ -151,9 +155,6 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     const int S = a.n_steps;
     const int q = warp & 3, hf = warp >> 2;                 // TMEM lane quarter, unit half
     const int r = 32 * q + lane;                            // row of the tile
-    const int grow = blockIdx.x * kRows + r;
-    const bool rvalid = grow < a.n_rows;
-    const int crow = min(grow, a.n_rows - 1);
 
     // ---- constant operands: async copies of the packed images (hi/lo gate matrix, hi/lo projection), bias ----------
     {
@@ -176,8 +177,6 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     pdl_wait();
 
     // ---- per-thread state -----------------------------------------------------------------------------------------
-    const long long xbase = row_base(a, crow);
-    const long long fbase = (long long)(crow / a.film_row_div) * S * kC;
     float c[32];
     // The tile's rows are consecutive in [n_rows][H]: the CTA moves them as one contiguous block (coalesced float4) through
     // the staging tile; thread (row, hf) then owns units 32*hf .. 32*hf + 31 of its row.
@@ -244,24 +243,45 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) blin[i] = dir == 0 ? __ldg(reinterpret_cast<const float4*>(w.lin_b) + 4 * hf + i) : make_float4(0, 0, 0, 0);
 
-    // x' of one step: the whole row (for the LayerNorm statistics); FiLM and the second addend applied on arrival
-    auto load_row = [&](int step, float4 (&xv)[8]) {
-        const int pos = dir ? S - 1 - step : step;
-        const long long off = xbase + (long long)pos * a.stride_pos;
+    // x' of one step for the whole tile, COALESCED: item i = tid + 256 k is (row i / 8, channel quad i % 8), so a warp
+    // instruction touches 4 rows x 128 bytes instead of 32 rows x 16 bytes.  FiLM and the second addend are applied on
+    // arrival; the slab then goes through shared memory to the (row, half) threads, which need whole rows for LayerNorm.
+    long long sbase[4], sfilm[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 t = ldg4_stream(a.x0 + off + 4 * i);
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + 256 * k, rr = i >> 3, c4 = i & 7;
+        const int gr = min(tile_row0 + rr, a.n_rows - 1);
+        sbase[k] = row_base(a, gr) + 4 * c4;
+        sfilm[k] = (long long)(gr / a.film_row_div) * S * kC + 4 * c4;
+    }
+    auto load_slab = [&](int step, float4 (&xs)[4]) {
+        const int pos = dir ? S - 1 - step : step;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long off = sbase[k] + (long long)pos * a.stride_pos;
+            float4 t = ldg4_stream(a.x0 + off);
             if (a.x1) {
-                const float4 u4 = ldg4_stream(a.x1 + off + 4 * i);
+                const float4 u4 = ldg4_stream(a.x1 + off);
                 t.x += u4.x; t.y += u4.y; t.z += u4.z; t.w += u4.w;
             }
             if (a.film_scale) {
-                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + fbase + (long long)pos * kC) + i);
-                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + fbase + (long long)pos * kC) + i);
+                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + sfilm[k] + (long long)pos * kC));
+                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + sfilm[k] + (long long)pos * kC));
                 t.x = fmaf(t.x, fs.x, fb.x); t.y = fmaf(t.y, fs.y, fb.y); t.z = fmaf(t.z, fs.z, fb.z); t.w = fmaf(t.w, fs.w, fb.w);
             }
-            xv[i] = t;
+            xs[k] = t;
         }
+    };
+    auto store_slab = [&](const float4 (&xs)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + 256 * k;
+            st4(slab + (i >> 3) * kSlabStride + 4 * (i & 7), xs[k]);
+        }
+    };
+    auto read_row = [&](float4 (&xv)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = ld4(slab + r * kSlabStride + 4 * i);
     };
     // LayerNorm the row, write this thread's 16 channels (k = 16*hf ..) into the x part of A, keep them for the residual
     auto ln_store = [&](const float4 (&xv)[8], float4 (&keep)[4]) {
@@ -294,8 +314,11 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
 
     float4 res_cur[4], res_prev[4];                         // x' channels 16*hf .. of step s and s-1 (residual)
     {
-        float4 xv[8];
-        load_row(0, xv);
+        float4 xs[4], xv[8];
+        load_slab(0, xs);
+        store_slab(xs);
+        __syncthreads();
+        read_row(xv);
         ln_store(xv, res_cur);
     }
 #pragma unroll
@@ -340,21 +363,28 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
 
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;    // TMEM address = lane << 16 | column
     float* const outp = a.out[dir];
-    auto emit = [&](int step, const float4 (&resv)[4]) {    // projected + bias + residual -> global, 16 channels
+    // projected + bias + residual of one step: 16 channels per thread into the output slab; flush_out() then stores the
+    // slab coalesced (a warp instruction writes 4 rows x 128 bytes) once a barrier has published it
+    auto emit = [&](const float4 (&resv)[4]) {
         float pv[16];
         tmem_ld16(tmem + lane_base + 256 + 16 * hf, pv);
-        if (rvalid) {
-            const int pos = dir ? S - 1 - step : step;
-            float* dst = outp + xbase + (long long)pos * a.stride_pos + 16 * hf;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 o = make_float4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
-                if (dir == 0) {
-                    o.x += blin[i].x + resv[i].x; o.y += blin[i].y + resv[i].y;
-                    o.z += blin[i].z + resv[i].z; o.w += blin[i].w + resv[i].w;
-                }
-                st4(dst + 4 * i, o);
+        for (int i = 0; i < 4; ++i) {
+            float4 o = make_float4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+            if (dir == 0) {
+                o.x += blin[i].x + resv[i].x; o.y += blin[i].y + resv[i].y;
+                o.z += blin[i].z + resv[i].z; o.w += blin[i].w + resv[i].w;
             }
+            st4(oslab + r * kSlabStride + 16 * hf + 4 * i, o);
+        }
+    };
+    auto flush_out = [&](int step) {
+        const int pos = dir ? S - 1 - step : step;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + 256 * k, rr = i >> 3;
+            if (tile_row0 + rr < a.n_rows)
+                st4(outp + sbase[k] + (long long)pos * a.stride_pos, ld4(oslab + rr * kSlabStride + 4 * (i & 7)));
         }
     };
 
@@ -368,11 +398,11 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
             issue_gates(1);
             umma_commit(mbar + 1);
         }
-        float4 xnext[8];
-        if (s + 1 < S) load_row(s + 1, xnext);              // in flight while the tensor pipe works
+        float4 xnext[4];
+        if (s + 1 < S) load_slab(s + 1, xnext);             // in flight while the tensor pipe works
         mbar_wait(mbar + hf, s & 1);
         fence_after();
-        if (s > 0) emit(s - 1, res_prev);
+        if (s > 0) emit(res_prev);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {                    // 8 units = 32 TMEM columns at a time
             float gv[32];
@@ -398,7 +428,14 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) res_prev[i] = res_cur[i];
-        if (s + 1 < S) ln_store(xnext, res_cur);
+        if (s + 1 < S) store_slab(xnext);                   // the slab's previous readers finished before the last barrier
+        __syncthreads();                                    // publishes both slabs
+        if (s > 0) flush_out(s - 1);
+        if (s + 1 < S) {
+            float4 xv[8];
+            read_row(xv);
+            ln_store(xv, res_cur);
+        }
         fence_async_smem();
         fence_before();
         __syncthreads();
@@ -411,7 +448,9 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     }
     mbar_wait(mbar + 0, S & 1);
     fence_after();
-    emit(S - 1, res_prev);
+    emit(res_prev);
+    __syncthreads();
+    flush_out(S - 1);
     if (a.hN) {                                             // same staging tiles, the other way (the initial-state reads
                                                             // were over before the first step's barrier)
 #pragma unroll
