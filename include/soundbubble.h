@@ -343,9 +343,10 @@ int    sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first
 /* chunk, state carried, consecutive chunks overlapping on `depth` streams owned by the pipe.  Chunk t runs on      */
 /* stream t % depth as one CUDA graph per unit range (captured at creation from sb_net_forward_range); range j of   */
 /* chunk t waits for range j of chunk t-1.  The caller owns all device memory: ios[k] (k = t % n_ios, n_ios = depth */
-/* if even else 2*depth) holds the slot's wave / wave_out / workspace (shared by the entries of slot k % depth, T =  */
-/* 1) and reads the state arena t % 2 / writes the other one; io.film must be set for FiLM models.  Run one eager    */
-/* sb_net_forward per kernel configuration before sb_pipe_create (shared-memory opt-ins cannot happen in a capture). */
+/* if even else 2*depth) holds the slot's wave / wave_out / workspace (shared by the entries of slot k % depth; the  */
+/* same T >= 1 frames per chunk everywhere: T = 1 is the 8 ms protocol, larger T pipelines an offline utterance in    */
+/* time slices) and reads the state arena t % 2 / writes the other one; io.film must be set for FiLM models.  Run one */
+/* eager sb_net_forward per kernel configuration before sb_pipe_create (shared-memory opt-ins cannot happen in a capture). */
 /* The only entry points of the library that create CUDA objects (streams, events, graphs); not thread-safe per pipe.*/
 /* ---------------------------------------------------------------------------------------------------------- */
 typedef struct sb_pipe sb_pipe;

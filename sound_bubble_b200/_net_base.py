@@ -5,6 +5,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _abi as abi
 from . import _lib
 from ._modules import TFGridNetParams
 from .engine import Engine, init_state
@@ -37,6 +38,17 @@ class NetBase(nn.Module):
         self.tfgridnet = TFGridNetParams(cfg)
         self._engine = None
         self._engine_key = None
+        # Whole-utterance calls on large batches run as a pipeline of time slices (streaming.PipelinedSession with
+        # `offline_slice_frames` frames per call): the serial inter-frame recurrence of one slice overlaps the
+        # intra-frame work of the next.  Same kernels per frame, so results agree with the single call to fp32 rounding.
+        self.pipeline_offline = True
+        self.offline_slice_frames = 125
+        self.offline_min_rows = 4096              # batch * frames below which the single call is used
+        self._offline_pipes = {}
+        self.offline_intra_algo = None            # None = SB_ALGO_AUTO per slice
+        # the inter-frame path of a slice on the tcgen05 kernel: 37 CTAs instead of one per SM, so that the next slice's
+        # intra-frame work finds free SMs (27.5 ms instead of 45.5 ms per batch of 32 x 5 s; the single call takes 48.9 ms)
+        self.offline_inter_algo = abi.SB_ALGO_TC if cfg.D == 32 else None
 
     # -- engine (packed weights on the device of the parameters) ---------------------------------------------
     def _weights_key(self):
@@ -63,10 +75,63 @@ class NetBase(nn.Module):
             pad_size = (self.stft_back_pad, self.stft_pad_size) if self.lookahead else (0, 0)
             x, mod = mod_pad(x, chunk_size=self.stft_chunk_size, pad=pad_size)
         with torch.no_grad():
-            y, next_state = self.engine().forward(x, dis_embed, input_state)
+            y = self._forward_sliced(x, dis_embed, input_state)
+            if y is None:
+                y, _ = self.engine().forward(x, dis_embed, input_state)
+            next_state = input_state
         if mod != 0:
             y = y[:, :, :-mod]
         return y, next_state
+
+    def _forward_sliced(self, x, dis_embed, state):
+        """The whole-utterance call as K time slices through the native pipe (None = not applicable, use the single
+        call).  Updates `state` in place like Engine.forward does (the reference mutates the dict it was given)."""
+        cfg = self.cfg
+        eng = self.engine()
+        if not self.pipeline_offline or x.dim() != 3 or x.dtype != torch.float32:
+            return None
+        B, M, N = x.shape
+        hop, look = cfg.stft_chunk_size, cfg.n_fft - cfg.stft_chunk_size
+        T = eng.n_frames(N)
+        Tc = int(self.offline_slice_frames)
+        if M != cfg.num_ch or T < 2 * Tc or B * T < self.offline_min_rows or (cfg.variant == "dis_embed" and dis_embed is None):
+            return None
+        K = max(2, round(T / Tc))
+        Tc = T // K
+        rem = T - K * Tc
+        from .state_io import StateArena
+        from .streaming import PipelinedSession
+        key = (B, Tc, str(x.device), id(eng), self.offline_intra_algo, self.offline_inter_algo)
+        pipe = self._offline_pipes.get(key)
+        if pipe is None:
+            if len(self._offline_pipes) > 2:
+                for p in self._offline_pipes.values():
+                    p.close()
+                self._offline_pipes.clear()
+            dis0 = torch.zeros(B, 3, device=x.device) if cfg.variant == "dis_embed" else None
+            pipe = PipelinedSession(self, B, dis0, depth=min(K, 6), frames_per_call=Tc, intra_algo=self.offline_intra_algo,
+                                    inter_algo=self.offline_inter_algo)
+            self._offline_pipes[key] = pipe
+        n_in = hop * Tc + look
+        windows = x.unfold(-1, n_in, hop * Tc)[:, :, :K].permute(2, 0, 1, 3).contiguous()       # [K, B, M, n_in]
+        out = torch.empty(K, B, cfg.num_src, hop * Tc, dtype=torch.float32, device=x.device)
+        pipe.reset()
+        if cfg.variant == "dis_embed":
+            pipe.set_dis_embed(dis_embed)
+        pipe.load_state(state)
+        pipe.begin()
+        for c in range(K):
+            pipe.feed(windows[c], out[c])
+        pipe.end()
+        y = out.permute(1, 2, 0, 3).reshape(B, cfg.num_src, K * hop * Tc)
+        final = StateArena(pipe.state)                      # a private copy: the pipe's arenas are reused by the next call
+        for k, v in final.state.items():
+            state[k] = v
+        if rem > 0:                                         # the last few frames: one ordinary call on the carried state
+            tail = x[..., K * hop * Tc:].contiguous()
+            y_tail, _ = eng.forward(tail, dis_embed, state)
+            y = torch.cat([y, y_tail], dim=-1)
+        return y
 
     def streaming(self, batch_size: int, dis_embed=None, use_graph: bool = True, pipelined: bool = False, ranges=None, depth: int = 8,
                   intra_algo=None, inter_algo=None):

@@ -89,8 +89,8 @@ extern "C" int sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_
     }
     SB_REQUIRE(next == 2 * d->n_blocks + 2, SB_E_BADARG, "sb_pipe_create: ranges must cover units 0..%d in order", 2 * d->n_blocks + 1);
     for (int k = 0; k < n_ios; ++k) {
-        SB_REQUIRE(ios[k].T == 1 && ios[k].B == ios[0].B && ios[k].B > 0, SB_E_BADARG,
-                   "sb_pipe_create: every sb_net_io must describe one frame of the same batch");
+        SB_REQUIRE(ios[k].T >= 1 && ios[k].T == ios[0].T && ios[k].B == ios[0].B && ios[k].B > 0, SB_E_BADARG,
+                   "sb_pipe_create: every sb_net_io must describe the same number of frames of the same batch");
         SB_REQUIRE(ios[k].wave == ios[k % depth].wave && ios[k].wave_out == ios[k % depth].wave_out &&
                    ios[k].workspace == ios[k % depth].workspace, SB_E_BADARG,
                    "sb_pipe_create: entries of one slot must share wave / wave_out / workspace");
@@ -104,8 +104,8 @@ extern "C" int sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_
     p->io.assign(ios, ios + n_ios);
     p->first.assign(range_first, range_first + n_ranges);
     p->last.assign(range_last, range_last + n_ranges);
-    p->window_bytes = sizeof(float) * (size_t)ios[0].B * d->M * d->n_fft;
-    p->out_bytes = sizeof(float) * (size_t)ios[0].B * d->n_src * d->stride;
+    p->window_bytes = sizeof(float) * (size_t)ios[0].B * d->M * ((size_t)d->stride * ios[0].T + d->n_fft - d->stride);
+    p->out_bytes = sizeof(float) * (size_t)ios[0].B * d->n_src * d->stride * ios[0].T;
     p->streams.assign(depth, nullptr);
     p->events.assign((size_t)depth * n_ranges, nullptr);
     p->joins.assign(depth, nullptr);
@@ -163,9 +163,9 @@ extern "C" int sb_pipe_reset(sb_pipe* p) {
 
 extern "C" long long sb_pipe_calls(const sb_pipe* p) { return p ? p->n_calls : -1; }
 
-/* Enqueues one chunk and returns.  window: [B][M][n_fft] floats, host (pinned for a truly asynchronous copy) or       */
-/* device, NULL = the slot's window buffer was filled by the caller; out: [B][S][stride], host or device, NULL = leave   */
-/* the result in the slot's wave_out buffer (valid until `depth` calls later).                                           */
+/* Enqueues one chunk of T frames and returns.  window: [B][M][stride*T + n_fft - stride] floats, host (pinned for a     */
+/* truly asynchronous copy) or device, NULL = the slot's window buffer was filled by the caller; out: [B][S][stride*T],   */
+/* host or device, NULL = leave the result in the slot's wave_out buffer (valid until `depth` calls later).              */
 extern "C" int sb_pipe_feed(sb_pipe* p, const float* window, float* out) {
     using namespace sb;
     SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_feed: null pipe");

@@ -151,7 +151,7 @@ class PipelinedSession:
     immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
 
     def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 8,
-                 intra_algo: Optional[int] = None, inter_algo: Optional[int] = None):
+                 intra_algo: Optional[int] = None, inter_algo: Optional[int] = None, frames_per_call: int = 1):
         self.net = net
         self.cfg = cfg = net.cfg
         self.engine = eng = net.engine()
@@ -162,9 +162,10 @@ class PipelinedSession:
             raise ValueError("depth must be >= 1")
         self.depth = depth
         mk = lambda *shape: [torch.zeros(*shape, dtype=torch.float32, device=dev) for _ in range(depth)]
-        self.x = mk(batch_size, cfg.num_ch, cfg.n_fft)
-        self.y = mk(batch_size, cfg.num_src, cfg.stft_chunk_size)
-        n_ws = max(int(eng.lib.sb_workspace_floats(eng.packed.desc_ref(), batch_size, 1)), 1)
+        self.frames = frames_per_call
+        self.x = mk(batch_size, cfg.num_ch, cfg.stft_chunk_size * frames_per_call + cfg.n_fft - cfg.stft_chunk_size)
+        self.y = mk(batch_size, cfg.num_src, cfg.stft_chunk_size * frames_per_call)
+        n_ws = max(int(eng.lib.sb_workspace_floats(eng.packed.desc_ref(), batch_size, frames_per_call)), 1)
         self.ws = [torch.empty(n_ws, dtype=torch.float32, device=dev) for _ in range(depth)]
         self.dis = None
         if cfg.variant == "dis_embed":
@@ -196,7 +197,8 @@ class PipelinedSession:
         self.intra_algo = intra_algo          # None = the engine's choice (SB_ALGO_AUTO unless the caller forced one)
         # Throughput mode pays in SM-time, not latency: the one-step inter-frame call as a tcgen05 GEMM occupies a quarter
         # of the SMs the SIMT tile kernel needs (128-row tiles), which leaves room for the other chunks' recurrences.
-        if inter_algo is None and eng.inter_algo == abi.SB_ALGO_AUTO and cfg.D == 32 and batch_size * cfg.n_freqs >= 1024:
+        if inter_algo is None and eng.inter_algo == abi.SB_ALGO_AUTO and cfg.D == 32 and batch_size * cfg.n_freqs >= 1024 \
+                and frames_per_call == 1:
             inter_algo = abi.SB_ALGO_TC
         self.inter_algo = inter_algo
         self.n_calls = 0
@@ -295,6 +297,14 @@ class PipelinedSession:
     def load_state(self, state: dict):
         """Adopt a reference-layout state dict as the state the next chunk starts from (on the caller's stream)."""
         StreamingSession._copy_state(self.states[self.parity], state)
+
+    def set_dis_embed(self, dis_embed: torch.Tensor):
+        """New bubble radii for the rows of this session (on the caller's stream, before begin()): the FiLM table the
+        captured graphs read is recomputed in place."""
+        if self.dis is None:
+            return
+        self.dis.copy_(dis_embed.to(self.device, torch.float32))
+        self.film.copy_(self.engine.film_table(self.dis))
 
     def launches_per_step(self) -> int:
         before = _lib.launch_count()

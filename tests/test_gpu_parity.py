@@ -190,6 +190,35 @@ def test_pipelined_session_is_bit_identical_to_the_in_order_session(name, ranges
     assert r["rms"] <= pc.RMS_TIGHT and r["maxabs"] <= pc.MAXABS_TIGHT, r
 
 
+@pytest.mark.parametrize("name", ["syn_offline", "rpi_offline", "syn_attn"])
+def test_sliced_offline_call_equals_the_single_call(name):
+    """Net.forward on long inputs runs as time slices through the native pipe (ragged last slice, carried input state,
+    in-place update of the caller's state dict): same result as the single call and as the reference's golden output."""
+    g = Golden(name)
+    m = _net_for(g)
+    m.offline_min_rows, m.offline_slice_frames = 0, 5
+    inp = g.inputs(DEV)
+    st = m.init_buffers(g.mixture.shape[0], DEV)
+    r = m(inp, st, pad=g.pad)
+    assert len(m._offline_pipes) == 1, "the sliced path was not taken"
+    assert r["next_state"] is st
+    m.pipeline_offline = False
+    r1 = m(inp, pad=g.pad)
+    assert float((r["output"] - r1["output"]).abs().max()) <= 2e-5
+    a, b = flatten_state(r["next_state"]), flatten_state(r1["next_state"])
+    assert max(float((a[k] - b[k]).abs().max()) for k in b) <= 2e-5
+    res = {"out": pc.compare(r["output"], g.output)}
+    res["state_maxabs"] = max(float((a[k] - v).abs().max()) for k, v in g.state.items())
+    if g.mixture2 is not None:                                # second call on the carried state, sliced again
+        m.pipeline_offline = True
+        x2 = torch.cat([g.mixture2] * 12, dim=-1)[..., : 192 * 11 + 96].to(DEV).contiguous()
+        r2 = m({"mixture": x2, "dis_embed": g.dis_embed.to(DEV)}, r["next_state"], pad=False)
+        m.pipeline_offline = False
+        r3 = m({"mixture": x2, "dis_embed": g.dis_embed.to(DEV)}, r1["next_state"], pad=False)
+        assert float((r2["output"] - r3["output"]).abs().max()) <= 2e-5
+    pc.assert_parity(res)
+
+
 def test_medium_clip_against_oracle():
     """1 s clips, batch 3, TFG_S config: ours vs the CPU oracle run here on the same seeded input."""
     ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
