@@ -339,6 +339,30 @@ int    sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream);
 int    sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first_unit, int last_unit, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------- */
+/* Batch assembly on the device: src/datasets/general_multisrc_dataset_dis_embed.py:112-218 for PCM already in HBM  */
+/* (int16 -> float32, target = sum of the in-bubble voices at the reference microphone, one-hot radius) and the      */
+/* per-channel perturbations of src/datasets/perturbations (SampleShift = torch.roll, ChannelGain, ChannelDrop,      */
+/* PeakNorm); the random draws stay on the host.  Order: shift, gain, drop (they commute), then the peak scale.      */
+/* ---------------------------------------------------------------------------------------------------------- */
+typedef struct sb_prepare_args {
+    const int16_t* mix;         /* [B][M][N] PCM16 mixture                                                          */
+    const int16_t* voices;      /* [B][V][N] PCM16 solo voices at the reference microphone (mic 0), NULL if V == 0  */
+    const uint8_t* inside;      /* [B][V]    1 = voice within the bubble radius -> part of the target               */
+    const float*   gain;        /* [B][M]    linear channel gains or NULL                                           */
+    const int*     shift;       /* [B][M]    circular shifts in samples (torch.roll) or NULL                        */
+    const uint8_t* drop;        /* [B][M]    1 = channel zeroed (never channel 0) or NULL                           */
+    const float*   peak_scale;  /* [B]       PeakNorm's drawn scale, 0 = not applied to this row; or NULL           */
+    const int*     radius_idx;  /* [B]       0: 1 m, 1: 1.5 m, 2: 2 m; NULL = 1 m                                   */
+    float*         mixture;     /* [B][M][N] out                                                                    */
+    float*         target;      /* [B][1][N] out                                                                    */
+    float*         dis_embed;   /* [B][3]    out                                                                    */
+    float*         peak_ws;     /* sb_prepare_workspace_floats(B, M, N) floats (only read / written with peak_scale) */
+    int B, M, V, N;
+} sb_prepare_args;
+size_t sb_prepare_workspace_floats(int B, int M, int N);
+int    sb_prepare_batch_fwd(const sb_prepare_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------- */
 /* Pipelined streaming (throughput mode of the edge/causal_infer.py:28-47 protocol): one sb_pipe_feed per 8 ms     */
 /* chunk, state carried, consecutive chunks overlapping on `depth` streams owned by the pipe.  Chunk t runs on      */
 /* stream t % depth as one CUDA graph per unit range (captured at creation from sb_net_forward_range); range j of   */
@@ -383,7 +407,7 @@ const char* sb_last_error_string(void);
 uint64_t    sb_launch_count(void);
 /* sizeof() of the structs above as compiled, so the ctypes mirror can be checked without a GPU                 */
 /*   0 lstm_dir 1 stft 2 conv_in 3 film 4 intra 5 inter 6 backend 7 net_desc 8 net_io 9 intra_conv 10 attn_proj */
-/*   11 attn 12 block_desc                                                                                      */
+/*   11 attn 12 block_desc 13 prepare                                                                          */
 int         sb_abi_sizeof(int which);
 
 #ifdef __cplusplus

@@ -114,9 +114,16 @@ class NetIO(C.Structure):
                 ("B", C.c_int), ("T", C.c_int), ("intra_algo", C.c_int), ("inter_algo", C.c_int)]
 
 
+class PrepareArgs(C.Structure):
+    _fields_ = [("mix", C.c_void_p), ("voices", C.c_void_p), ("inside", C.c_void_p), ("gain", fp), ("shift", C.c_void_p),
+                ("drop", C.c_void_p), ("peak_scale", fp), ("radius_idx", C.c_void_p),
+                ("mixture", fp), ("target", fp), ("dis_embed", fp), ("peak_ws", fp),
+                ("B", C.c_int), ("M", C.c_int), ("V", C.c_int), ("N", C.c_int)]
+
+
 # index used by sb_abi_sizeof(which)
 ABI_STRUCTS = {0: LstmDir, 1: StftArgs, 2: ConvInArgs, 3: FilmArgs, 4: IntraArgs, 5: InterArgs, 6: BackendArgs,
-               7: NetDesc, 8: NetIO, 9: IntraConvArgs, 10: AttnProj, 11: AttnArgs, 12: BlockDesc}
+               7: NetDesc, 8: NetIO, 9: IntraConvArgs, 10: AttnProj, 11: AttnArgs, 12: BlockDesc, 13: PrepareArgs}
 
 # every symbol include/soundbubble.h declares: name -> (restype, argtypes)
 PROTOTYPES = {
@@ -133,6 +140,8 @@ PROTOTYPES = {
     "sb_workspace_floats": (C.c_size_t, [C.POINTER(NetDesc), C.c_int, C.c_int]),
     "sb_net_forward": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_void_p]),
     "sb_net_forward_range": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_int, C.c_int, C.c_void_p]),
+    "sb_prepare_workspace_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "sb_prepare_batch_fwd": (C.c_int, [C.POINTER(PrepareArgs), C.c_void_p]),
     "sb_pipe_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_int, C.c_int, C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "sb_pipe_destroy": (C.c_int, [C.c_void_p]),

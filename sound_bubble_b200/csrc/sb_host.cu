@@ -97,6 +97,7 @@ extern "C" int sb_abi_sizeof(int which) {
         case 10: return (int)sizeof(sb_attn_proj);
         case 11: return (int)sizeof(sb_attn_args);
         case 12: return (int)sizeof(sb_block_desc);
+        case 13: return (int)sizeof(sb_prepare_args);
         default: return -1;
     }
 }
