@@ -14,5 +14,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc -s 2 -c 1 -o gpurun_out/prof_tc python tools/profile_run.py --mode offline --batch 32 --frames 625 > gpurun_out/ncu4.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tile -s 2 -c 1 -o gpurun_out/prof_tile python tools/profile_run.py --mode offline --batch 8 --frames 200 --intra-algo 1 --inter-algo 1 > gpurun_out/ncu6.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_in|backend_small|stft_features' -s 9 -c 3 -o gpurun_out/prof_small python tools/profile_run.py --mode streaming --chunks 4 --graph 0 > gpurun_out/ncu5.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:prepare_batch -s 1 -c 1 -o gpurun_out/prof_prepare python tools/prepare_bench.py > gpurun_out/ncu7.log 2>&1
+timeout 300 python tools/prepare_bench.py > gpurun_out/prepare_bench.txt 2>&1; tail -3 gpurun_out/prepare_bench.txt
 timeout 600 python tools/lstm_bench.py > gpurun_out/lstm_bench.txt 2>&1; tail -4 gpurun_out/lstm_bench.txt
 ls -la gpurun_out | head -50
