@@ -16,7 +16,7 @@
 namespace sb {
 
 struct AttnWs {
-    float *Q, *Kc, *Vc, *AO;
+    float *Q, *Kc, *Vc, *AO, *P;
     size_t total;
 };
 
@@ -31,6 +31,7 @@ static AttnWs attn_carve(float* base, int B, int T, int F, int C, int L, int E, 
     w.Kc = take(BL * (T + W - 1) * DK);
     w.Vc = take(BL * (T + W - 1) * DV);
     w.AO = take(BL * T * DV);
+    w.P = take(BL * W);                     // streaming path: softmax probabilities of the one query per head-row
     w.total = off;
     return w;
 }
@@ -46,66 +47,66 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {      // re
     return t;
 }
 
-// ---- Q, K, V projections + per-head LayerNorm; one CTA per (t, b) ---------------------------------------------------
+// ---- Q, K, V projections + per-head LayerNorm; one CTA per (t, b, head) ---------------------------------------------
+// Head l needs output rows l*E.. of Q and K and l*Vd.. of V: NOH = 2E + Vd rows of C weights.  The weights sit in shared
+// memory TRANSPOSED ([c][NOH]: the threads of a warp differ in the output row, so they read consecutive words), x[f][:]
+// is a broadcast.  The three LayerNorms (F*E, F*E, F*Vd elements) are block-wide, every thread a few elements.
 __global__ void __launch_bounds__(256) attn_qkv_kernel(const sb_attn_args a, float* Q, float* Kc, float* Vc) {
     SB_DYN_SMEM(float, smem);
+    __shared__ float red[8];
     const int F = a.F, C = a.C, L = a.L, E = a.E, Vd = C / L, W = a.W, T = a.T;
-    const int LE = L * E, NO = 2 * LE + C, DK = F * E, DV = F * Vd;
+    const int NOH = 2 * E + Vd, DK = F * E, DV = F * Vd;
     float* xs = smem;                       // [F][C]
-    float* ws = xs + F * C;                 // [NO][C]  rows: Q (LE), K (LE), V (C)
-    float* bs = ws + NO * C;                // [NO]
-    float* st = bs + ((NO + 3) & ~3);       // staging: Q [L][DK], K [L][DK], V [L][DV]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = blockIdx.x, b = blockIdx.y;
-    for (int i = tid; i < NO * C; i += 256) {
+    float* wt = xs + F * C;                 // [C][NOH]  columns: Q (E), K (E), V (Vd) of this head
+    float* bs = wt + C * NOH;               // [NOH]
+    float* st = bs + ((NOH + 3) & ~3);      // staging: q [DK], k [DK], v [DV]
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x, b = blockIdx.y, l = blockIdx.z;
+    for (int i = tid; i < NOH * C; i += 256) {
         const int o = i / C, c = i - o * C;
-        ws[i] = o < LE ? __ldg(a.q.w + o * C + c) : (o < 2 * LE ? __ldg(a.k.w + (o - LE) * C + c) : __ldg(a.v.w + (o - 2 * LE) * C + c));
+        const float wv = o < E ? __ldg(a.q.w + (l * E + o) * C + c)
+                               : (o < 2 * E ? __ldg(a.k.w + (l * E + o - E) * C + c) : __ldg(a.v.w + (l * Vd + o - 2 * E) * C + c));
+        wt[c * NOH + o] = wv;
     }
-    for (int o = tid; o < NO; o += 256)
-        bs[o] = o < LE ? __ldg(a.q.b + o) : (o < 2 * LE ? __ldg(a.k.b + o - LE) : __ldg(a.v.b + o - 2 * LE));
+    for (int o = tid; o < NOH; o += 256)
+        bs[o] = o < E ? __ldg(a.q.b + l * E + o) : (o < 2 * E ? __ldg(a.k.b + l * E + o - E) : __ldg(a.v.b + l * Vd + o - 2 * E));
     const float sq = __ldg(a.q.prelu), sk = __ldg(a.k.prelu), sv = __ldg(a.v.prelu);
     pdl_trigger();
     pdl_wait();
     const float* xr = a.x + ((size_t)b * T + t) * F * C;
     for (int i = tid; i < F * C / 4; i += 256) st4(xs + 4 * i, ldg4_stream(xr + 4 * i));
     __syncthreads();
-    for (int i = tid; i < F * NO; i += 256) {
-        const int f = i / NO, o = i - f * NO;
+    for (int i = tid; i < F * NOH; i += 256) {
+        const int f = i / NOH, o = i - f * NOH;
         float acc = bs[o];
         const float* xp = xs + f * C;
-        const float* wp = ws + o * C;
-        for (int c = 0; c < C; ++c) acc = fmaf(xp[c], wp[c], acc);
-        if (o < LE) {
-            acc = acc > 0.f ? acc : sq * acc;
-            st[(o / E) * DK + f * E + (o % E)] = acc;
-        } else if (o < 2 * LE) {
-            const int oo = o - LE;
-            acc = acc > 0.f ? acc : sk * acc;
-            st[L * DK + (oo / E) * DK + f * E + (oo % E)] = acc;
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) acc = fmaf(xp[c], wt[c * NOH + o], acc);
+        if (o < E) {
+            st[f * E + o] = acc > 0.f ? acc : sq * acc;
+        } else if (o < 2 * E) {
+            st[DK + f * E + (o - E)] = acc > 0.f ? acc : sk * acc;
         } else {
-            const int oo = o - 2 * LE;
-            acc = acc > 0.f ? acc : sv * acc;
-            st[2 * L * DK + (oo / Vd) * DV + f * Vd + (oo % Vd)] = acc;
+            st[2 * DK + f * Vd + (o - 2 * E)] = acc > 0.f ? acc : sv * acc;
         }
     }
     __syncthreads();
-    // 3L rows to normalise: row r -> (tensor = r / L, head = r % L); one warp per row
-    for (int r = warp; r < 3 * L; r += 8) {
-        const int which = r / L, l = r - which * L;
+    for (int which = 0; which < 3; ++which) {               // q, k, v rows of this head
         const int n = which == 2 ? DV : DK;
-        float* row = st + (which == 2 ? 2 * L * DK + l * DV : (which * L + l) * DK);
+        const float* row = st + (which == 2 ? 2 * DK : which * DK);
         const sb_attn_proj& pj = which == 0 ? a.q : (which == 1 ? a.k : a.v);
         float s1 = 0.f;
-        for (int i = lane; i < n; i += 32) s1 += row[i];
-        const float mean = group_sum<32>(s1) / n;
+        for (int i = tid; i < n; i += 256) s1 += row[i];
+        const float mean = block_sum_256(s1, red) / n;
         float s2 = 0.f;
-        for (int i = lane; i < n; i += 32) { const float d = row[i] - mean; s2 = fmaf(d, d, s2); }
-        const float rstd = rsqrtf(group_sum<32>(s2) / n + kLnEps);
+        for (int i = tid; i < n; i += 256) { const float d = row[i] - mean; s2 = fmaf(d, d, s2); }
+        const float rstd = rsqrtf(block_sum_256(s2, red) / n + kLnEps);
         float* dst;
         if (which == 0) dst = Q + (((size_t)b * L + l) * T + t) * DK;
         else if (which == 1) dst = Kc + (((size_t)b * L + l) * (T + W - 1) + W - 1 + t) * DK;
         else dst = Vc + (((size_t)b * L + l) * (T + W - 1) + W - 1 + t) * DV;
-        for (int i = lane; i < n; i += 32) dst[i] = fmaf((row[i] - mean) * rstd, __ldg(pj.ln_g + i), __ldg(pj.ln_b + i));
+#pragma unroll 4
+        for (int i = tid; i < n; i += 256) dst[i] = fmaf((row[i] - mean) * rstd, __ldg(pj.ln_g + i), __ldg(pj.ln_b + i));
     }
 }
 
@@ -189,6 +190,117 @@ __global__ void __launch_bounds__(256) attn_core_kernel(const sb_attn_args a, co
     }
 }
 
+// =============================================================================================================
+// streaming path (T == 1): one query per head-row against its W-frame window
+// =============================================================================================================
+// A chunk's attention is a stream over the K / V history: (W-1) * (DK + DV) floats per head-row are read once, used for
+// one dot product / one weighted sum, and written back one row earlier (the reference's cat + slice, DE3:864-873).  The two
+// kernels below do exactly that and nothing else: HBM-bound, 2 * (W-1) * (DK + DV) * 4 bytes per head-row per chunk.
+
+// scores + softmax; the K history moves up one row on the way.  CTA = head-row bl, warp = key rows w, w + 8, ...
+__global__ void __launch_bounds__(256) attn_stream_scores_kernel(const sb_attn_args a, const float* Q, const float* Kc, float* P) {
+    SB_DYN_SMEM(float, smem);
+    const int F = a.F, E = a.E, W = a.W;
+    const int DK = F * E, DK2 = DK / 2;
+    float* qs = smem;                       // [DK]
+    float* ps = qs + ((DK + 3) & ~3);       // [W]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bl = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    for (int i = tid; i < DK; i += 256) qs[i] = ldg1_stream(Q + (size_t)bl * DK + i);
+    __syncthreads();
+    const float scale = 1.0f / sqrtf((float)DK);
+    const float* hist = a.K_buf_in + (size_t)bl * (W - 1) * DK;
+    const float* knew = Kc + ((size_t)bl * W + (W - 1)) * DK;
+    float* hout = a.K_buf_out + (size_t)bl * (W - 1) * DK;
+    constexpr int KI = 5;                                   // float2 per lane and row held in registers (DK <= 320)
+    for (int r0 = warp; r0 < W; r0 += 16) {                 // two key rows per warp at a time, every load issued before use
+        const int r1 = r0 + 8;
+        const bool two = r1 < W;
+        const float* src0 = r0 < W - 1 ? hist + (size_t)r0 * DK : knew;
+        const float* src1 = !two ? knew : (r1 < W - 1 ? hist + (size_t)r1 * DK : knew);
+        float* dst0 = r0 >= 1 ? hout + (size_t)(r0 - 1) * DK : nullptr;
+        float* dst1 = two ? hout + (size_t)(r1 - 1) * DK : nullptr;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int kb = 0; kb < DK2; kb += 32 * KI) {
+            float2 v0[KI], v1[KI];
+#pragma unroll
+            for (int i = 0; i < KI; ++i) {
+                const int k = kb + 32 * i + lane;
+                v0[i] = k < DK2 ? ldg2_stream(src0 + 2 * k) : make_float2(0.f, 0.f);
+                v1[i] = k < DK2 ? ldg2_stream(src1 + 2 * k) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < KI; ++i) {
+                const int k = kb + 32 * i + lane;
+                if (k < DK2) {
+                    const float2 q2 = ld2(qs + 2 * k);
+                    acc0 = fmaf(q2.x, v0[i].x, acc0); acc0 = fmaf(q2.y, v0[i].y, acc0);
+                    acc1 = fmaf(q2.x, v1[i].x, acc1); acc1 = fmaf(q2.y, v1[i].y, acc1);
+                    if (dst0) st2(dst0 + 2 * k, v0[i]);
+                    if (dst1) st2(dst1 + 2 * k, v1[i]);
+                }
+            }
+        }
+        acc0 = group_sum<32>(acc0);
+        acc1 = group_sum<32>(acc1);
+        if (lane == 0) {
+            ps[r0] = acc0 * scale;
+            if (two) ps[r1] = acc1 * scale;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float m = -INFINITY;
+        for (int w = lane; w < W; w += 32) m = fmaxf(m, ps[w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int w = lane; w < W; w += 32) { const float e = expf(ps[w] - m); ps[w] = e; s += e; }
+        const float inv = 1.0f / group_sum<32>(s);
+        for (int w = lane; w < W; w += 32) P[(size_t)bl * W + w] = ps[w] * inv;
+    }
+}
+
+// out = P V; the V history moves up one row on the way.  grid (column chunks, head-rows), thread = one float4 column
+__global__ void __launch_bounds__(128) attn_stream_pv_kernel(const sb_attn_args a, const float* Vc, const float* P, float* AO) {
+    SB_DYN_SMEM(float, smem);               // [W] probabilities
+    const int W = a.W, DV = a.F * (a.C / a.L), DV4 = DV / 4;
+    const int bl = blockIdx.y, c4 = blockIdx.x * 128 + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    for (int w = threadIdx.x; w < W; w += 128) smem[w] = P[(size_t)bl * W + w];
+    __syncthreads();
+    if (c4 >= DV4) return;
+    const float4* hist = reinterpret_cast<const float4*>(a.V_buf_in + (size_t)bl * (W - 1) * DV) + c4;
+    const float4* vnew = reinterpret_cast<const float4*>(Vc + ((size_t)bl * W + (W - 1)) * DV) + c4;
+    float4* hout = reinterpret_cast<float4*>(a.V_buf_out + (size_t)bl * (W - 1) * DV) + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 8;                    // rows in flight per thread
+    int r = 0;
+    for (; r + U <= W - 1; r += U) {
+        float4 v[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) v[i] = ldg4_stream(reinterpret_cast<const float*>(hist + (size_t)(r + i) * DV4));
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            const float p = smem[r + i];
+            acc.x = fmaf(p, v[i].x, acc.x); acc.y = fmaf(p, v[i].y, acc.y);
+            acc.z = fmaf(p, v[i].z, acc.z); acc.w = fmaf(p, v[i].w, acc.w);
+            if (r + i >= 1) hout[(size_t)(r + i - 1) * DV4] = v[i];
+        }
+    }
+    for (; r < W; ++r) {
+        const float4 v = r < W - 1 ? ldg4_stream(reinterpret_cast<const float*>(hist + (size_t)r * DV4)) : *vnew;
+        const float p = smem[r];
+        acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
+        acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+        if (r >= 1) hout[(size_t)(r - 1) * DV4] = v;
+    }
+    st4(AO + (size_t)bl * DV + 4 * c4, acc);
+}
+
 // ---- head regroup + output projection + LayerNorm(F*C) + residual; one CTA per (t, b) --------------------------------
 __global__ void __launch_bounds__(256) attn_out_kernel(const sb_attn_args a, const float* AO) {
     SB_DYN_SMEM(float, smem);
@@ -199,7 +311,7 @@ __global__ void __launch_bounds__(256) attn_out_kernel(const sb_attn_args a, con
     float* ws = ys + n;                     // [C][C]
     const int tid = threadIdx.x;
     const int t = blockIdx.x, b = blockIdx.y;
-    for (int i = tid; i < C * C; i += 256) ws[i] = __ldg(a.o.w + i);
+    for (int i = tid; i < C * C; i += 256) ws[(i % C) * C + i / C] = __ldg(a.o.w + i);     // transposed: [c][o]
     const float slope = __ldg(a.o.prelu);
     pdl_trigger();
     pdl_wait();
@@ -211,9 +323,10 @@ __global__ void __launch_bounds__(256) attn_out_kernel(const sb_attn_args a, con
     __syncthreads();
     float s1 = 0.f;
     for (int i = tid; i < n; i += 256) {
-        const int f = i / C, o = i - f * C;
+        const int f = i / C, o = i - f * C;                 // a warp: one f (broadcast), 32 consecutive o (conflict-free)
         float acc = __ldg(a.o.b + o);
-        for (int c = 0; c < C; ++c) acc = fmaf(os[f * C + c], ws[o * C + c], acc);
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) acc = fmaf(os[f * C + c], ws[c * C + o], acc);
         acc = acc > 0.f ? acc : slope * acc;
         ys[i] = acc;
         s1 += acc;
@@ -224,6 +337,7 @@ __global__ void __launch_bounds__(256) attn_out_kernel(const sb_attn_args a, con
     const float rstd = rsqrtf(block_sum_256(s2, red) / n + kLnEps);
     const float* xr = a.x + ((size_t)b * T + t) * n;
     float* yr = a.y + ((size_t)b * T + t) * n;
+#pragma unroll 4
     for (int i = tid; i < n; i += 256)
         yr[i] = xr[i] + fmaf((ys[i] - mean) * rstd, __ldg(a.o.ln_g + i), __ldg(a.o.ln_b + i));
 }
@@ -247,15 +361,26 @@ extern "C" int sb_attn_fwd(const sb_attn_args* p, void* stream) {
     const int B = p->B, T = p->T, F = p->F, C = p->C, L = p->L, E = p->E, W = p->W, Vd = C / L;
     const int BL = B * L, DK = F * E, DV = F * Vd, TT = T + W - 1;
     const AttnWs w = attn_carve(p->ws, B, T, F, C, L, E, W);
+    if (T == 1 && DK % 2 == 0) {            // streaming chunk: stream the history once, shifting it on the way
+        const int NOH1 = 2 * E + Vd;
+        const size_t smem_qkv1 = ((size_t)F * C + (size_t)NOH1 * C + ((NOH1 + 3) & ~3) + (size_t)2 * DK + DV) * sizeof(float);
+        SB_CHECK(launch("attn_qkv", attn_qkv_kernel, dim3(T, B, L), dim3(256), smem_qkv1, st, *p, w.Q, w.Kc, w.Vc));
+        SB_CHECK(launch("attn_stream_scores", attn_stream_scores_kernel, dim3(BL), dim3(256),
+                        (size_t)(((DK + 3) & ~3) + W) * sizeof(float), st, *p, (const float*)w.Q, (const float*)w.Kc, w.P));
+        SB_CHECK(launch("attn_stream_pv", attn_stream_pv_kernel, dim3(ceil_div(DV / 4, 128), BL), dim3(128),
+                        (size_t)W * sizeof(float), st, *p, (const float*)w.Vc, (const float*)w.P, w.AO));
+        const size_t smem_out1 = ((size_t)2 * F * C + (size_t)C * C) * sizeof(float);
+        return launch("attn_out", attn_out_kernel, dim3(T, B), dim3(256), smem_out1, st, *p, (const float*)w.AO);
+    }
     const int cgrid = 2 * sm_count();
     // history -> first W-1 rows of the concatenated K / V
     SB_CHECK(launch("attn_copy", attn_copy_kernel, dim3(cgrid), dim3(256), 0, st, p->K_buf_in, w.Kc, BL,
                     (long long)(W - 1) * DK, (long long)TT * DK, 0LL, 0LL, (long long)(W - 1) * DK));
     SB_CHECK(launch("attn_copy", attn_copy_kernel, dim3(cgrid), dim3(256), 0, st, p->V_buf_in, w.Vc, BL,
                     (long long)(W - 1) * DV, (long long)TT * DV, 0LL, 0LL, (long long)(W - 1) * DV));
-    const int NO = 2 * L * E + C;
-    const size_t smem_qkv = ((size_t)F * C + (size_t)NO * C + ((NO + 3) & ~3) + (size_t)2 * L * DK + (size_t)L * DV) * sizeof(float);
-    SB_CHECK(launch("attn_qkv", attn_qkv_kernel, dim3(T, B), dim3(256), smem_qkv, st, *p, w.Q, w.Kc, w.Vc));
+    const int NOH = 2 * E + Vd;
+    const size_t smem_qkv = ((size_t)F * C + (size_t)NOH * C + ((NOH + 3) & ~3) + (size_t)2 * DK + DV) * sizeof(float);
+    SB_CHECK(launch("attn_qkv", attn_qkv_kernel, dim3(T, B, L), dim3(256), smem_qkv, st, *p, w.Q, w.Kc, w.Vc));
     const size_t smem_core = ((size_t)kAttnTQ * DK + (size_t)kAttnTQ * (W + 1)) * sizeof(float);
     SB_CHECK(launch("attn_core", attn_core_kernel, dim3(ceil_div(T, kAttnTQ), BL), dim3(256), smem_core, st, *p,
                     (const float*)w.Q, (const float*)w.Kc, (const float*)w.Vc, w.AO));

@@ -168,6 +168,15 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
     return r;
 #endif
 }
+__device__ __forceinline__ float2 ldg2_stream(const float* p) {
+#ifdef SB_EMU
+    return ld2(p);
+#else
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#endif
+}
 __device__ __forceinline__ float ldg1_stream(const float* p) {
 #ifdef SB_EMU
     return *p;

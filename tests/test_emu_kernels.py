@@ -40,5 +40,11 @@ def test_lstm_kernels(lib, algo):
     _ok(kc.check_intra(lib, "cpu", "optim", dict(OPI, D=16), algo, B=1, T=2))
 
 
+def test_streaming_attention_path(lib):
+    """T == 1: scores / weighted sum streamed over the K / V history, which moves up one row on the way."""
+    _ok(kc.check_attn(lib, "cpu", "dis_embed", dict(SYN, use_attn=True, local_atten_len=7), B=2, T=1))
+    _ok(kc.check_attn(lib, "cpu", "optim", dict(RPI, use_attn=True, local_atten_len=10, conv_lstm=False), B=1, T=1, block=1))
+
+
 def test_whole_path_golden_plain(lib):
     pc.assert_parity(pc.run_golden(lib, "cpu", "syn_plain"))

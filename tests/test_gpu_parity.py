@@ -92,6 +92,7 @@ def test_intra_convlstm(lib, variant, kw, algo):
                                         ("dis_embed", dict(SYN, use_attn=True, local_atten_len=100))])
 def test_attention(lib, variant, kw):
     _ok(kc.check_attn(lib, DEV, variant, kw, B=2, T=21), tol=5e-5)
+    _ok(kc.check_attn(lib, DEV, variant, kw, B=3, T=1, block=1), tol=5e-5)       # streaming path: one query per head-row
 
 
 # ---- whole path against the outputs of the unmodified reference ---------------------------------------------
