@@ -321,15 +321,37 @@ __global__ void __launch_bounds__(256) attn_out_kernel(const sb_attn_args a, con
         os[f * C + l * Vd + vd] = ldg1_stream(AO + (((size_t)b * L + l) * T + t) * DV + r);
     }
     __syncthreads();
+    // thread = output channel o (tid % C) for the frequencies f = tid / C, tid / C + 256 / C, ...: its weight column stays in
+    // registers and every os[f][:] row arrives as broadcast LDS.128, so the projection costs 1/4 shared-memory load per FMA
     float s1 = 0.f;
-    for (int i = tid; i < n; i += 256) {
-        const int f = i / C, o = i - f * C;                 // a warp: one f (broadcast), 32 consecutive o (conflict-free)
-        float acc = __ldg(a.o.b + o);
+    if (C == 32) {
+        const int o = tid & 31;
+        float wcol[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) wcol[c] = ws[c * 32 + o];
+        const float bo = __ldg(a.o.b + o);
+        for (int f = tid >> 5; f < F; f += 8) {
+            float acc = bo;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 v = ld4(os + f * 32 + 4 * c4);
+                acc = fmaf(v.x, wcol[4 * c4], acc); acc = fmaf(v.y, wcol[4 * c4 + 1], acc);
+                acc = fmaf(v.z, wcol[4 * c4 + 2], acc); acc = fmaf(v.w, wcol[4 * c4 + 3], acc);
+            }
+            acc = acc > 0.f ? acc : slope * acc;
+            ys[f * 32 + o] = acc;
+            s1 += acc;
+        }
+    } else {
+        for (int i = tid; i < n; i += 256) {
+            const int f = i / C, o = i - f * C;             // a warp: one or two f (broadcast), consecutive o (conflict-free)
+            float acc = __ldg(a.o.b + o);
 #pragma unroll 8
-        for (int c = 0; c < C; ++c) acc = fmaf(os[f * C + c], ws[c * C + o], acc);
-        acc = acc > 0.f ? acc : slope * acc;
-        ys[i] = acc;
-        s1 += acc;
+            for (int c = 0; c < C; ++c) acc = fmaf(os[f * C + c], ws[c * C + o], acc);
+            acc = acc > 0.f ? acc : slope * acc;
+            ys[i] = acc;
+            s1 += acc;
+        }
     }
     const float mean = block_sum_256(s1, red) / n;
     float s2 = 0.f;
