@@ -68,6 +68,8 @@ extern "C" {
 
 /* process-wide options */
 #define SB_OPT_PDL 1            /* 1 = launch kernels with programmatic dependent launch (prologue overlap)       */
+#define SB_OPT_ATTN_TC 2        /* 0 = keep the attention core of whole-utterance calls on the SIMT kernel (default 1:  */
+                                /* tcgen05 core for T >= 64, W <= 129, F*E <= 320)                                    */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

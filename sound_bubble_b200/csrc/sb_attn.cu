@@ -15,6 +15,10 @@
 
 namespace sb {
 
+// sb_attn_tc.cu: the same core on the tensor cores (tcgen05) for T >= 64
+bool attn_core_tc_supported(const sb_attn_args& a);
+int attn_core_tc(const sb_attn_args& a, const float* Q, const float* Kc, const float* Vc, float* AO, cudaStream_t st);
+
 struct AttnWs {
     float *Q, *Kc, *Vc, *AO, *P;
     size_t total;
@@ -403,9 +407,13 @@ extern "C" int sb_attn_fwd(const sb_attn_args* p, void* stream) {
     const int NOH = 2 * E + Vd;
     const size_t smem_qkv = ((size_t)F * C + (size_t)NOH * C + ((NOH + 3) & ~3) + (size_t)2 * DK + DV) * sizeof(float);
     SB_CHECK(launch("attn_qkv", attn_qkv_kernel, dim3(T, B, L), dim3(256), smem_qkv, st, *p, w.Q, w.Kc, w.Vc));
-    const size_t smem_core = ((size_t)kAttnTQ * DK + (size_t)kAttnTQ * (W + 1)) * sizeof(float);
-    SB_CHECK(launch("attn_core", attn_core_kernel, dim3(ceil_div(T, kAttnTQ), BL), dim3(256), smem_core, st, *p,
-                    (const float*)w.Q, (const float*)w.Kc, (const float*)w.Vc, w.AO));
+    if (attn_tc_enabled() && attn_core_tc_supported(*p)) {
+        SB_CHECK(attn_core_tc(*p, w.Q, w.Kc, w.Vc, w.AO, st));
+    } else {
+        const size_t smem_core = ((size_t)kAttnTQ * DK + (size_t)kAttnTQ * (W + 1)) * sizeof(float);
+        SB_CHECK(launch("attn_core", attn_core_kernel, dim3(ceil_div(T, kAttnTQ), BL), dim3(256), smem_core, st, *p,
+                        (const float*)w.Q, (const float*)w.Kc, (const float*)w.Vc, w.AO));
+    }
     // last W-1 rows of the concatenated K / V -> new history
     SB_CHECK(launch("attn_copy", attn_copy_kernel, dim3(cgrid), dim3(256), 0, st, (const float*)w.Kc, p->K_buf_out, BL,
                     (long long)TT * DK, (long long)(W - 1) * DK, (long long)T * DK, 0LL, (long long)(W - 1) * DK));

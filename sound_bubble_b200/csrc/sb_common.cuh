@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...);
 void count_launch();
 int  check_launch(const char* what);        // cudaGetLastError() -> 0 / cudaError_t, records the message
 bool pdl_enabled();                         // programmatic dependent launch (sb_set_option(SB_OPT_PDL, 1))
+bool attn_tc_enabled();                     // tcgen05 attention core for T >= 64 (sb_set_option(SB_OPT_ATTN_TC, 0) turns it off)
 int  sm_count();
 int  ensure_smem(const void* func, size_t bytes, const char* name);
 

@@ -48,6 +48,7 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert lib.sb_inter_lstm_fwd(ctypes.byref(a), None) == -1
     assert lib.sb_set_option(12345, 1) == -1
     assert lib.sb_set_option(abi.SB_OPT_PDL, 0) == 0
+    assert lib.sb_set_option(abi.SB_OPT_ATTN_TC, 1) == 0
 
 
 def test_product_path_refuses_cpu_tensors():

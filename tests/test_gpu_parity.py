@@ -91,11 +91,30 @@ def test_intra_convlstm(lib, variant, kw, algo):
                                         ("optim", dict(RPI, use_attn=True, local_atten_len=7)),
                                         ("dis_embed", dict(SYN, use_attn=True, local_atten_len=100))])
 def test_attention(lib, variant, kw):
-    _ok(kc.check_attn(lib, DEV, variant, kw, B=2, T=21), tol=5e-5)
+    _ok(kc.check_attn(lib, DEV, variant, kw, B=2, T=21), tol=5e-5)                # SIMT core (T < 64)
     _ok(kc.check_attn(lib, DEV, variant, kw, B=3, T=1, block=1), tol=5e-5)       # streaming path: one query per head-row
 
 
 # ---- whole path against the outputs of the unmodified reference ---------------------------------------------
+def test_attention_tensor_core_path(lib):
+    """T >= 64 runs the attention core on tcgen05 (fp32 -> bf16 hi/lo operands, four MMAs per k-step, fp32 accumulation
+    in TMEM): 16-bit operand mantissas, so the stage bar is 1e-4 max-abs on O(1) data (measured 3-4e-5; the SIMT core
+    gives 5-8e-6); tiles that are not full, several tiles, a narrow and a full window, the C = 16 variant."""
+    try:
+        for kw, var, B, T, blk in ((dict(SYN, use_attn=True), "dis_embed", 2, 130, 0),
+                                   (dict(SYN, use_attn=True, local_atten_len=10), "dis_embed", 1, 64, 2),
+                                   (dict(SYN, use_attn=True), "dis_embed", 1, 300, 1),
+                                   (dict(RPI, use_attn=True), "optim", 1, 200, 0)):
+            abi.check(lib, lib.sb_set_option(abi.SB_OPT_ATTN_TC, 1), "opt")
+            tc = kc.check_attn(lib, DEV, var, kw, B=B, T=T, block=blk)
+            abi.check(lib, lib.sb_set_option(abi.SB_OPT_ATTN_TC, 0), "opt")
+            simt = kc.check_attn(lib, DEV, var, kw, B=B, T=T, block=blk)
+            _ok(tc, tol=1e-4)
+            _ok(simt, tol=2e-5)
+    finally:
+        abi.check(lib, lib.sb_set_option(abi.SB_OPT_ATTN_TC, 1), "opt")
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_through_c_abi(lib, name):
     pc.assert_parity(pc.run_golden(lib, DEV, name))
