@@ -99,8 +99,14 @@ class NetBase(nn.Module):
         K = max(2, round(T / Tc))
         Tc = T // K
         rem = T - K * Tc
-        from .state_io import StateArena
+        from .state_io import StateArena, flatten_state
         from .streaming import PipelinedSession
+        try:                                                # anything unusual about the state: let the single call report it
+            names, _ = flatten_state(state)
+        except (TypeError, AttributeError):
+            return None
+        if names != flatten_state(self.init_buffers(1, "meta"))[0]:
+            return None
         key = (B, Tc, str(x.device), id(eng), self.offline_intra_algo, self.offline_inter_algo)
         pipe = self._offline_pipes.get(key)
         if pipe is None:
