@@ -227,6 +227,55 @@ __device__ __forceinline__ void stage_f4(float* dst, const float* src, int n4, i
     for (int i = tid; i < n4; i += nthreads) cp_async_16(dst + 4 * i, src + 4 * i);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP): one thread hands a contiguous global -> shared copy of any multiple of
+// 16 bytes to the copy engine and the consumers wait on an mbarrier that counts the arriving bytes.  Used to stage the
+// packed weight images (up to 106 KB per CTA) with one instruction instead of thousands of 16-byte LDGSTS.
+// ------------------------------------------------------------------------------------------------------------
+struct alignas(8) BulkBarrier { unsigned long long v; };
+
+__device__ __forceinline__ void bulk_barrier_init(BulkBarrier* bar) {           // one thread, then a block barrier
+#ifndef SB_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    bar->v = 0;
+#endif
+}
+// one thread: announce `total_bytes`, then issue the copies (each a multiple of 16 bytes, 16-byte aligned on both sides)
+__device__ __forceinline__ void bulk_expect(BulkBarrier* bar, unsigned total_bytes) {
+#ifndef SB_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(total_bytes) : "memory");
+#else
+    (void)bar; (void)total_bytes;
+#endif
+}
+__device__ __forceinline__ void bulk_copy_g2s(float* smem_dst, const float* gsrc, unsigned bytes, BulkBarrier* bar) {
+#ifndef SB_EMU
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+#else
+    (void)bar;
+    for (unsigned i = 0; i < bytes / 4; ++i) smem_dst[i] = gsrc[i];
+#endif
+}
+// every consumer thread: wait for phase `parity` of the barrier (the copies have landed and are visible)
+__device__ __forceinline__ void bulk_wait(BulkBarrier* bar, unsigned parity) {
+#ifndef SB_EMU
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SB_BULK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra SB_BULK_WAIT_%=;\n\t}\n" ::"r"(a), "r"(parity) : "memory");
+#else
+    (void)bar; (void)parity;
+#endif
+}
+
 template <int WIDTH>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll

@@ -58,7 +58,10 @@ int ensure_smem(const void* func, size_t bytes, const char* name) {
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
     if (done.count({dev, func})) return 0;
-    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncAttributes fa{};
+    size_t stat = 0;                        // static shared memory counts against the same 227 KB
+    if (cudaFuncGetAttributes(&fa, func) == cudaSuccess) stat = fa.sharedSizeBytes;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - stat));
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("%s: cannot opt in to %zu bytes of shared memory: %s", name, bytes, cudaGetErrorString(e));

@@ -55,9 +55,15 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
     const sb_lstm_dir& w = a.w[dir];
     const int S = a.n_steps;
 
-    // stage the weights once per CTA (constant data: allowed before pdl_wait)
-    stage_f4(Wt, w.w_tile, K * 64, tid, blockDim.x);
-    if (!RAW_H) stage_f4(WlT, w.lin_t, H * C / 4, tid, blockDim.x);
+    // stage the weights once per CTA with TMA bulk copies (constant data: allowed before pdl_wait)
+    __shared__ BulkBarrier wbar;
+    if (tid == 0) bulk_barrier_init(&wbar);
+    __syncthreads();
+    if (tid == 0) {
+        bulk_expect(&wbar, (unsigned)((K * 256 + (RAW_H ? 0 : H * C)) * sizeof(float)));
+        bulk_copy_g2s(Wt, w.w_tile, K * 256 * sizeof(float), &wbar);
+        if (!RAW_H) bulk_copy_g2s(WlT, w.lin_t, H * C * sizeof(float), &wbar);
+    }
     float bias[8];
     {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(w.b_tile) + lane);
@@ -66,8 +72,10 @@ __global__ void __launch_bounds__(256, 1) lstm_tile_kernel(const SeqArgs a) {
         bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
     }
     pdl_trigger();
-    cp_async_wait_all();
-    __syncthreads();                        // the only block-wide barrier
+#ifdef SB_EMU
+    __syncthreads();                        // the host-emulated copy above is an ordinary store by thread 0
+#endif
+    bulk_wait(&wbar, 0);                    // the weights have landed; no block-wide barrier in the step loop either
     pdl_wait();
 
     const int row0 = (blockIdx.x * (blockDim.x >> 5) + warp) * RW;

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     unsigned char* a_lo = a_hi + kABytes;
     float* bias_s = reinterpret_cast<float*>(a_lo + kABytes);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bias_s + kN);         // [2]: units 0..31 (+ projection), units 32..63
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3);
     // [kRows][kStageStride] staging tiles carry the state between its global layout (row-contiguous, coalesced) and the
     // (row, half) threads.  They alias operand images that are idle at that moment (a bigger carve-out would cost L1):
     float* slab = reinterpret_cast<float*>(mbar + 8);       // [kRows][kSlabStride]: x' of the next step, loaded coalesced
@@ -158,20 +158,20 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
 
     // ---- constant operands: async copies of the packed images (hi/lo gate matrix, hi/lo projection), bias ----------
     {
-        const float* src = w.tc_w;
-        float* dst = reinterpret_cast<float*>(sm);
-        const int n4 = (2 * kWBytes + 2 * kPBytes) / 16;
-        for (int i = tid; i < n4; i += 256) cp_async_16(dst + 4 * i, src + 4 * i);
         for (int i = tid; i < kN; i += 256) bias_s[i] = __ldg(w.tc_b + i);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(mbar + 2);
     if (tid == 0) {
         mbar_init(mbar + 0, 1);
         mbar_init(mbar + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        bulk_barrier_init(wbar);
+        // the packed operand images (hi / lo gate matrix, hi / lo projection: 106 KB) in one TMA bulk copy
+        bulk_expect(wbar, 2 * kWBytes + 2 * kPBytes);
+        bulk_copy_g2s(reinterpret_cast<float*>(sm), w.tc_w, 2 * kWBytes + 2 * kPBytes, wbar);
     }
     pdl_trigger();
     pdl_wait();
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const SeqArgs a) {
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) res_prev[i] = res_cur[i];
-    cp_async_wait_all();
+    bulk_wait(wbar, 0);                                     // the operand images have landed (async proxy wrote them)
     fence_async_smem();
     fence_before();
     __syncthreads();
