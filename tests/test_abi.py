@@ -69,3 +69,13 @@ def test_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "emu_lib" not in text and "libsoundbubble_emu" not in text, f
+
+
+def test_integration_doc_shows_the_current_lstm_dir_layout():
+    """INTEGRATION.md's reference-side ctypes stub must name the fields of sb_lstm_dir in header order."""
+    hdr = open(os.path.join(ROOT, "include", "soundbubble.h")).read()
+    body = hdr[hdr.index("typedef struct sb_lstm_dir"):hdr.index("} sb_lstm_dir;")]
+    fields = re.findall(r"const float\*\s+(\w+);", body)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = doc[doc.index("class sb_lstm_dir"):doc.index("class sb_inter_args")]
+    assert re.findall(r'"(\w+)"', stub) == fields == [n for n, _ in abi.LstmDir._fields_]
