@@ -16,5 +16,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_in|backend_small|stft_features' -s 9 -c 3 -o gpurun_out/prof_small python tools/profile_run.py --mode streaming --chunks 4 --graph 0 > gpurun_out/ncu5.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:prepare_batch -s 1 -c 1 -o gpurun_out/prof_prepare python tools/prepare_bench.py > gpurun_out/ncu7.log 2>&1
 timeout 300 python tools/prepare_bench.py > gpurun_out/prepare_bench.txt 2>&1; tail -3 gpurun_out/prepare_bench.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_core_tc -s 2 -c 1 -o gpurun_out/prof_attn_tc python tools/profile_attn_offline.py > gpurun_out/ncu8.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_stream_pv -s 2 -c 1 -o gpurun_out/prof_attn_pv python tools/profile_attn.py > gpurun_out/ncu9.log 2>&1
+timeout 300 python tools/variants_bench.py > gpurun_out/variants_bench.txt 2>&1; cat gpurun_out/variants_bench.txt
 timeout 600 python tools/lstm_bench.py > gpurun_out/lstm_bench.txt 2>&1; tail -4 gpurun_out/lstm_bench.txt
 ls -la gpurun_out | head -50

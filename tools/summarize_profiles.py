@@ -96,7 +96,7 @@ if __name__ == "__main__":
     for r in sorted(os.listdir(OUT)):
         if r.endswith(".ncu-rep"):
             report(r, tag)
-    for n in ("ubench.txt", "lstm_bench.txt", "bench.json", "bench_pdl.json", "gpu.txt", "host.txt", "prepare_bench.txt"):
+    for n in ("ubench.txt", "lstm_bench.txt", "bench.json", "bench_pdl.json", "gpu.txt", "host.txt", "prepare_bench.txt", "variants_bench.txt"):
         p = os.path.join(OUT, n)
         if os.path.exists(p):
             open(os.path.join(PROF, "%s_%s" % (tag, n)), "w").write(open(p).read())
