@@ -49,6 +49,8 @@ extern "C" {
 #define SB_ALGO_TILE4 6         /* tile family with 4 sequences per warp (C = 32 only; chosen by TILE for 1-2 step calls) */
 #define SB_ALGO_TC    7         /* tcgen05: 128 sequences per CTA, gate GEMM on the tensor cores as a bf16 hi/lo split   */
                                 /* (3 products, fp32 accumulation in TMEM), cell update from TMEM (C = 32, projected mode) */
+#define SB_ALGO_WS2   8         /* the WS kernel with 2 sequences per CTA sharing the weights in registers, their steps     */
+                                /* interleaved phase by phase: 1.6x the latency, 0.81x the SM-time per sequence             */
 #define SB_ALGO_WS    5         /* 1 sequence per CTA, warp-specialised: 4 recurrence warps (2 units x 4 gates x K/4 per   */
                                 /* thread, weights in registers, packed FFMA2) + 4 helper warps (loads, LayerNorm, input   */
                                 /* gates, stores)                                                                           */

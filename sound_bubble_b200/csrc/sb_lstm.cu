@@ -514,23 +514,29 @@ __global__ void __launch_bounds__(256, 1) lstm_lane_kernel(const SeqArgs a) {
 //     block of SB steps, the input part of the gates (x W_ih^T + b) for the next group with the same mapping, and
 //     the bias / residual / store of finished blocks.
 // The two sides meet at one full barrier per group; gate inputs and hidden states travel through 8-deep rings.
-template <int C>
+template <int C, int NQ>
 struct WsCfg {
     static constexpr int H = 64, LPP = C / 4, SB = 256 / LPP, XK = C / 4, HS = 20, G = 4, RING = 8;
     static constexpr int NPL = 32 / C;                      // projection planes (threads per output channel and quad)
+    // per sequence of the CTA:
     static constexpr int xn_off = 0, res_off = 2 * SB * C, outp_off = 4 * SB * C;
     static constexpr int gx_off = outp_off + 2 * NPL * SB * C, hb_off = gx_off + RING * 256;
-    static constexpr int smem_floats = hb_off + RING * 4 * HS;
+    static constexpr int seq_floats = hb_off + RING * 4 * HS;
+    static constexpr int smem_floats = NQ * seq_floats;
     static_assert(SB >= 32 && SB % (2 * G) == 0 && XK % 4 == 0, "block / slice sizes");
 };
 
-template <int C, bool RAW_H>
+// NQ sequences per CTA (rows NQ*blockIdx.x ..): the recurrence warps run the step of every sequence with the SAME weights
+// in registers, phase by phase, so the shuffles, MUFU round trips and stores of one sequence sit in the shadow of the
+// other's FMAs.  NQ = 1 is the lowest-latency shape (one sequence per SM); NQ = 2 (SB_ALGO_WS2) costs 1.6x the latency
+// for 0.81x the SM-time per sequence, which is what a saturated pipelined session pays for.
+template <int C, bool RAW_H, int NQ>
 __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
-    using Cfg = WsCfg<C>;
+    using Cfg = WsCfg<C, NQ>;
     constexpr int H = Cfg::H, LPP = Cfg::LPP, SB = Cfg::SB, XK = Cfg::XK, HS = Cfg::HS, NPL = Cfg::NPL;
-    constexpr int G = Cfg::G, RING = Cfg::RING;
+    constexpr int G = Cfg::G, RING = Cfg::RING, SQ = Cfg::seq_floats;
     SB_DYN_SMEM(float, smem);
-    float* xn = smem + Cfg::xn_off;         // [2][SB][C]        LayerNorm(x') of the current / next block
+    float* xn = smem + Cfg::xn_off;         // [2][SB][C]        LayerNorm(x') of the current / next block   (+ q * SQ)
     float* res = smem + Cfg::res_off;       // [2][SB][C]        x' (residual)
     float* outp = smem + Cfg::outp_off;     // [2][NPL][SB][C]   (partial) projections of finished steps
     float* gx = smem + Cfg::gx_off;         // [RING][64][4]     x W_ih^T + b of step s in slot s % RING: unit, gate
@@ -540,7 +546,6 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
     const int dir = blockIdx.y;
     const sb_lstm_dir& w = a.w[dir];
     const int S = a.n_steps;
-    const int row = blockIdx.x;
     const int nblk = (S + SB - 1) / SB;
     const int ngrp = (S + G - 1) / G;
     const bool recur = tid >= 128;                       // warp-uniform role; the recurrence gets the higher warp ids,
@@ -550,6 +555,13 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
     const bool hi = (kq & 2) != 0, odd = (kq & 1) != 0;
     const int ux = hi ? ur + 32 : ur;                     // the unit this lane ends up with after the reduce-scatter
     const int gsl = 4 * ux + (odd ? 2 : 0);               // its two gates: (i,f) on even lanes, (g,o) on odd lanes
+    int row[NQ];
+    bool rok[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        rok[q] = blockIdx.x * NQ + q < a.n_rows;          // a ragged last CTA computes its missing row on a copy
+        row[q] = min(blockIdx.x * NQ + q, a.n_rows - 1);  // of the last one and stores nothing for it
+    }
 
     if (recur) {
         // ---------------------------------------------------------------------------------------- recurrence warps
@@ -571,10 +583,14 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
         pdl_trigger();
         pdl_wait();
         const bool has0 = a.h0 != nullptr;
-        float c = has0 ? ld_plain(a.c0 + (long long)row * H + ux) : 0.0f;       // meaningful on even lanes
-        float hlast = has0 ? ld_plain(a.h0 + (long long)row * H + ux) : 0.0f;
         const int hslot = (ux >> 4) * HS + (ux & 15);
-        if (!odd) hb[hslot] = hlast;
+        float c[NQ], hlast[NQ];                           // meaningful on even lanes
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            c[q] = has0 ? ld_plain(a.c0 + (long long)row[q] * H + ux) : 0.0f;
+            hlast[q] = has0 ? ld_plain(a.h0 + (long long)row[q] * H + ux) : 0.0f;
+            if (!odd) hb[q * SQ + hslot] = hlast[q];
+        }
         float* const outr = a.out[dir];
         const float act_in = odd ? 2.0f : 1.0f;           // odd lanes: value 0 is the cell gate -> tanh(x) = 2 sigmoid(2x) - 1
         const float act_mul = odd ? 2.0f : 1.0f, act_add = odd ? -1.0f : 0.0f;
@@ -582,7 +598,7 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
         __syncthreads();                                  // (Q)
 
         // projection of step sp from the h slice already in registers: 16 FMA, a quad reduction, one predicated store
-        auto project = [&](const float (&hr)[16], int sp, bool store) {
+        auto project = [&](const float (&hr)[16], int q, int sp, bool store) {
             float p0 = wp[0] * hr[0], p1 = wp[1] * hr[1], p2 = wp[2] * hr[2], p3 = wp[3] * hr[3];
 #pragma unroll
             for (int k = 4; k < 16; k += 4) {
@@ -592,13 +608,13 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
             float pp = (p0 + p1) + (p2 + p3);
             pp += __shfl_xor_sync(0xffffffffu, pp, 1);
             pp += __shfl_xor_sync(0xffffffffu, pp, 2);
-            if (store && kq == 0) {
-                const int bp = sp / SB;
-                outp[(((bp & 1) * NPL + ppl) * SB + (sp - bp * SB)) * C + pc] = pp;
-            }
+            const int spc = sp < 0 ? 0 : sp;
+            const int bp = spc / SB;
+            float* dst = outp + q * SQ + (((bp & 1) * NPL + ppl) * SB + (spc - bp * SB)) * C + pc;
+            if (store && kq == 0) *dst = pp;
         };
-        auto load_h = [&](int s, float (&hr)[16]) {
-            const float* hs = hb + (s & (RING - 1)) * 4 * HS + kq * HS;
+        auto load_h = [&](int s, int q, float (&hr)[16]) {
+            const float* hs = hb + q * SQ + (s & (RING - 1)) * 4 * HS + kq * HS;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 v = ld4(hs + 4 * i);
@@ -613,64 +629,95 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
                 const int s = g * G + j;
                 if (s >= S) break;
                 if (j > 0) bar_sync(1, 128);              // h_{s-1} of every unit is in the ring
-                float hr[16];
-                load_h(s, hr);
-                const float2 g2 = ld2(gx + (s & (RING - 1)) * 256 + gsl);
-                float2 aA01[2], aA23[2], aB01[2], aB23[2];
+                // the step of the NQ sequences, phase by phase
+                float hr[NQ][16];
+                float2 g2[NQ];
+                float mine0[NQ], mine1[NQ], r1a[NQ], r1b[NQ], r2a[NQ], r2b[NQ], r3a[NQ], r3b[NQ];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    aA01[e] = make_float2(0.f, 0.f); aA23[e] = aA01[e]; aB01[e] = aA01[e]; aB23[e] = aA01[e];
+                for (int q = 0; q < NQ; ++q) {
+                    load_h(s, q, hr[q]);
+                    g2[q] = ld2(gx + q * SQ + (s & (RING - 1)) * 256 + gsl);
                 }
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    ffma2(aA01[k & 1], make_float2(wA[k].x, wA[k].y), hr[k]);
-                    ffma2(aA23[k & 1], make_float2(wA[k].z, wA[k].w), hr[k]);
-                    ffma2(aB01[k & 1], make_float2(wB[k].x, wB[k].y), hr[k]);
-                    ffma2(aB23[k & 1], make_float2(wB[k].z, wB[k].w), hr[k]);
+                for (int q = 0; q < NQ; ++q) {
+                    float2 aA01[2], aA23[2], aB01[2], aB23[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        aA01[e] = make_float2(0.f, 0.f); aA23[e] = aA01[e]; aB01[e] = aA01[e]; aB23[e] = aA01[e];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        ffma2(aA01[k & 1], make_float2(wA[k].x, wA[k].y), hr[q][k]);
+                        ffma2(aA23[k & 1], make_float2(wA[k].z, wA[k].w), hr[q][k]);
+                        ffma2(aB01[k & 1], make_float2(wB[k].x, wB[k].y), hr[q][k]);
+                        ffma2(aB23[k & 1], make_float2(wB[k].z, wB[k].w), hr[q][k]);
+                    }
+                    const float A0 = aA01[0].x + aA01[1].x, A1 = aA01[0].y + aA01[1].y;
+                    const float A2 = aA23[0].x + aA23[1].x, A3 = aA23[0].y + aA23[1].y;
+                    const float B0 = aB01[0].x + aB01[1].x, B1 = aB01[0].y + aB01[1].y;
+                    const float B2 = aB23[0].x + aB23[1].x, B3 = aB23[0].y + aB23[1].y;
+                    // one-level reduce-scatter over the quad: this lane finishes (unit hi ? B : A, gates odd ? (g,o) : (i,f)); every
+                    // partner sends the pair its reader wants: xor 1 = same unit / other pair, xor 2 = other unit / same pair,
+                    // xor 3 = other unit / other pair.  Six independent shuffles, one latency level.
+                    const float m0 = hi ? B0 : A0, m1 = hi ? B1 : A1, m2 = hi ? B2 : A2, m3 = hi ? B3 : A3;     // my unit
+                    const float o0 = hi ? A0 : B0, o1 = hi ? A1 : B1, o2 = hi ? A2 : B2, o3 = hi ? A3 : B3;     // the other unit
+                    mine0[q] = odd ? m2 : m0; mine1[q] = odd ? m3 : m1;
+                    r1a[q] = __shfl_xor_sync(0xffffffffu, odd ? m0 : m2, 1);
+                    r1b[q] = __shfl_xor_sync(0xffffffffu, odd ? m1 : m3, 1);
+                    r2a[q] = __shfl_xor_sync(0xffffffffu, odd ? o2 : o0, 2);
+                    r2b[q] = __shfl_xor_sync(0xffffffffu, odd ? o3 : o1, 2);
+                    r3a[q] = __shfl_xor_sync(0xffffffffu, odd ? o0 : o2, 3);
+                    r3b[q] = __shfl_xor_sync(0xffffffffu, odd ? o1 : o3, 3);
                 }
-                const float A0 = aA01[0].x + aA01[1].x, A1 = aA01[0].y + aA01[1].y;
-                const float A2 = aA23[0].x + aA23[1].x, A3 = aA23[0].y + aA23[1].y;
-                const float B0 = aB01[0].x + aB01[1].x, B1 = aB01[0].y + aB01[1].y;
-                const float B2 = aB23[0].x + aB23[1].x, B3 = aB23[0].y + aB23[1].y;
-                // one-level reduce-scatter over the quad: this lane finishes (unit hi ? B : A, gates odd ? (g,o) : (i,f)); every
-                // partner sends the pair its reader wants: xor 1 = same unit / other pair, xor 2 = other unit / same pair,
-                // xor 3 = other unit / other pair.  Six independent shuffles, one latency level.
-                const float m0 = hi ? B0 : A0, m1 = hi ? B1 : A1, m2 = hi ? B2 : A2, m3 = hi ? B3 : A3;     // my unit
-                const float o0 = hi ? A0 : B0, o1 = hi ? A1 : B1, o2 = hi ? A2 : B2, o3 = hi ? A3 : B3;     // the other unit
-                const float r1a = __shfl_xor_sync(0xffffffffu, odd ? m0 : m2, 1);
-                const float r1b = __shfl_xor_sync(0xffffffffu, odd ? m1 : m3, 1);
-                const float r2a = __shfl_xor_sync(0xffffffffu, odd ? o2 : o0, 2);
-                const float r2b = __shfl_xor_sync(0xffffffffu, odd ? o3 : o1, 2);
-                const float r3a = __shfl_xor_sync(0xffffffffu, odd ? o0 : o2, 3);
-                const float r3b = __shfl_xor_sync(0xffffffffu, odd ? o1 : o3, 3);
-                if (!RAW_H) project(hr, s - 1, s > 0);    // rides in the shadow of the gate shuffles
-                const float v0 = ((odd ? m2 : m0) + r1a) + (r2a + r3a);
-                const float v1 = ((odd ? m3 : m1) + r1b) + (r2b + r3b);
-                const float act0 = fmaf(sigmoid_f((v0 + g2.x) * act_in), act_mul, act_add);   // sigma(i) | tanh(g)
-                const float act1 = sigmoid_f(v1 + g2.y);                                      // sigma(f) | sigma(o)
-                const float tg = __shfl_xor_sync(0xffffffffu, act0, 1);      // even lanes receive tanh(g), sigma(o)
-                const float so = __shfl_xor_sync(0xffffffffu, act1, 1);
-                c = fmaf(act1, c, act0 * tg);                                // even: c = sigma(f) c + sigma(i) tanh(g)
-                hlast = so * tanh_f(c);
-                if (!odd) {
-                    hb[((s + 1) & (RING - 1)) * 4 * HS + hslot] = hlast;
-                    if (RAW_H) {
+                if (!RAW_H) {                             // rides in the shadow of the gate shuffles
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) project(hr[q], q, s - 1, s > 0);
+                }
+                float act0[NQ], act1[NQ], tg[NQ], so[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const float v0 = (mine0[q] + r1a[q]) + (r2a[q] + r3a[q]);
+                    const float v1 = (mine1[q] + r1b[q]) + (r2b[q] + r3b[q]);
+                    act0[q] = fmaf(sigmoid_f((v0 + g2[q].x) * act_in), act_mul, act_add);   // sigma(i) | tanh(g)
+                    act1[q] = sigmoid_f(v1 + g2[q].y);                                      // sigma(f) | sigma(o)
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    tg[q] = __shfl_xor_sync(0xffffffffu, act0[q], 1);            // even lanes receive tanh(g), sigma(o)
+                    so[q] = __shfl_xor_sync(0xffffffffu, act1[q], 1);
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    c[q] = fmaf(act1[q], c[q], act0[q] * tg[q]);                 // even: c = sigma(f) c + sigma(i) tanh(g)
+                    hlast[q] = so[q] * tanh_f(c[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if (!odd) hb[q * SQ + ((s + 1) & (RING - 1)) * 4 * HS + hslot] = hlast[q];
+                    if (RAW_H && !odd && rok[q]) {
                         const int pos = dir ? S - 1 - s : s;
-                        outr[((long long)row * S + pos) * H + ux] = hlast;
+                        outr[((long long)row[q] * S + pos) * H + ux] = hlast[q];
                     }
                 }
             }
         }
         __syncthreads();                                  // h_{S-1} is in the ring (pairs with the helpers' last group barrier)
         if (!RAW_H) {
-            float hr[16];
-            load_h(S, hr);
-            project(hr, S - 1, true);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float hr[16];
+                load_h(S, q, hr);
+                project(hr, q, S - 1, true);
+            }
         }
         __syncthreads();                                  // pairs with the helpers' closing barrier
         if (!odd && a.hN) {
-            a.hN[(long long)row * H + ux] = hlast;
-            a.cN[(long long)row * H + ux] = c;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (rok[q]) {
+                    a.hN[(long long)row[q] * H + ux] = hlast[q];
+                    a.cN[(long long)row[q] * H + ux] = c[q];
+                }
         }
         return;
     }
@@ -689,101 +736,116 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.ln_b) + c4);
     float4 blin4 = make_float4(0, 0, 0, 0);
     if (!RAW_H && dir == 0) blin4 = __ldg(reinterpret_cast<const float4*>(w.lin_b) + c4);
-    const long long p_base = row_base(a, row) + 4 * c4;
-    const long long p_fbase = (long long)(row / a.film_row_div) * S * C + 4 * c4;
+    long long p_base[NQ], p_fbase[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        p_base[q] = row_base(a, row[q]) + 4 * c4;
+        p_fbase[q] = (long long)(row[q] / a.film_row_div) * S * C + 4 * c4;
+    }
     float* const outp_g = a.out[dir];
     pdl_trigger();
     pdl_wait();
 
-    auto prefetch1 = [&](int s) -> float4 {
+    auto prefetch1 = [&](int q, int s) -> float4 {
         float4 v = make_float4(0, 0, 0, 0);
         if (s < S) {
             const int pos = dir ? S - 1 - s : s;
-            const long long off = p_base + (long long)pos * a.stride_pos;
+            const long long off = p_base[q] + (long long)pos * a.stride_pos;
             v = ldg4_stream(a.x0 + off);
             if (a.x1) {
                 const float4 t = ldg4_stream(a.x1 + off);
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
             if (a.film_scale) {
-                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + p_fbase + (long long)pos * C));
-                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + p_fbase + (long long)pos * C));
+                const float4 fs = __ldg(reinterpret_cast<const float4*>(a.film_scale + p_fbase[q] + (long long)pos * C));
+                const float4 fb = __ldg(reinterpret_cast<const float4*>(a.film_shift + p_fbase[q] + (long long)pos * C));
                 v.x = fmaf(v.x, fs.x, fb.x); v.y = fmaf(v.y, fs.y, fb.y);
                 v.z = fmaf(v.z, fs.z, fb.z); v.w = fmaf(v.w, fs.w, fb.w);
             }
         }
         return v;
     };
-    float4 xpre[2];
+    float4 xpre[NQ][2];
     auto prefetch = [&](int blk) {
-        xpre[0] = prefetch1(blk * SB + pq);
-        xpre[1] = prefetch1(blk * SB + pq + SB / 2);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            xpre[q][0] = prefetch1(q, blk * SB + pq);
+            xpre[q][1] = prefetch1(q, blk * SB + pq + SB / 2);
+        }
     };
     auto phase_a = [&](int blk) {                         // LayerNorm(C) of one step by LPP adjacent lanes
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float4 v = xpre[e];
-            const int st = pq + e * (SB / 2);
-            const float mean = group_sum<LPP>((v.x + v.y) + (v.z + v.w)) * (1.0f / C);
-            const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-            const float var = group_sum<LPP>((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / C);
-            const float rstd = rsqrtf(var + kLnEps);
-            st4(xn + ((blk & 1) * SB + st) * C + 4 * c4, make_float4(fmaf(dx * rstd, g4.x, b4.x), fmaf(dy * rstd, g4.y, b4.y),
-                                                                      fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w)));
-            if (!RAW_H) st4(res + ((blk & 1) * SB + st) * C + 4 * c4, v);
-        }
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float4 v = xpre[q][e];
+                const int st = pq + e * (SB / 2);
+                const float mean = group_sum<LPP>((v.x + v.y) + (v.z + v.w)) * (1.0f / C);
+                const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+                const float var = group_sum<LPP>((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / C);
+                const float rstd = rsqrtf(var + kLnEps);
+                st4(xn + q * SQ + ((blk & 1) * SB + st) * C + 4 * c4,
+                    make_float4(fmaf(dx * rstd, g4.x, b4.x), fmaf(dy * rstd, g4.y, b4.y),
+                                fmaf(dz * rstd, g4.z, b4.z), fmaf(dw * rstd, g4.w, b4.w)));
+                if (!RAW_H) st4(res + q * SQ + ((blk & 1) * SB + st) * C + 4 * c4, v);
+            }
     };
     auto phase_c = [&](int blk) {                         // finished block: projection + bias + residual -> global
         if (RAW_H) return;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int st = pq + e * (SB / 2);
-            const int s = blk * SB + st;
-            if (s < S) {
-                float4 v = make_float4(0, 0, 0, 0);
+        for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                for (int q = 0; q < NPL; ++q) {
-                    const float4 t = ld4(outp + (((blk & 1) * NPL + q) * SB + st) * C + 4 * c4);
-                    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            for (int e = 0; e < 2; ++e) {
+                const int st = pq + e * (SB / 2);
+                const int s = blk * SB + st;
+                if (s < S && rok[q]) {
+                    float4 v = make_float4(0, 0, 0, 0);
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl) {
+                        const float4 t = ld4(outp + q * SQ + (((blk & 1) * NPL + pl) * SB + st) * C + 4 * c4);
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    }
+                    if (dir == 0) {
+                        const float4 r = ld4(res + q * SQ + ((blk & 1) * SB + st) * C + 4 * c4);
+                        v.x += blin4.x + r.x; v.y += blin4.y + r.y; v.z += blin4.z + r.z; v.w += blin4.w + r.w;
+                    }
+                    const int pos = dir ? S - 1 - s : s;
+                    st4(outp_g + p_base[q] + (long long)pos * a.stride_pos, v);
                 }
-                if (dir == 0) {
-                    const float4 r = ld4(res + ((blk & 1) * SB + st) * C + 4 * c4);
-                    v.x += blin4.x + r.x; v.y += blin4.y + r.y; v.z += blin4.z + r.z; v.w += blin4.w + r.w;
-                }
-                const int pos = dir ? S - 1 - s : s;
-                st4(outp_g + p_base + (long long)pos * a.stride_pos, v);
             }
-        }
     };
     // gx[s] = LN(x_s) W_ih^T + b for the G steps of a group: same (two units, K quarter) mapping as the recurrence
     auto x_part_group = [&](int s0) {
         const int blk = s0 / SB;
-        const float* xr = xn + ((blk & 1) * SB + (s0 - blk * SB)) * C + XK * kq;
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            float xv[XK];
+        for (int q = 0; q < NQ; ++q) {
+            const float* xr = xn + q * SQ + ((blk & 1) * SB + (s0 - blk * SB)) * C + XK * kq;
 #pragma unroll
-            for (int i = 0; i < XK / 4; ++i) {
-                const float4 v = ld4(xr + j * C + 4 * i);
-                xv[4 * i] = v.x; xv[4 * i + 1] = v.y; xv[4 * i + 2] = v.z; xv[4 * i + 3] = v.w;
+            for (int j = 0; j < G; ++j) {
+                float xv[XK];
+#pragma unroll
+                for (int i = 0; i < XK / 4; ++i) {
+                    const float4 v = ld4(xr + j * C + 4 * i);
+                    xv[4 * i] = v.x; xv[4 * i + 1] = v.y; xv[4 * i + 2] = v.z; xv[4 * i + 3] = v.w;
+                }
+                float2 aA01 = make_float2(0.f, 0.f), aA23 = aA01, aB01 = aA01, aB23 = aA01;
+#pragma unroll
+                for (int k = 0; k < XK; ++k) {
+                    ffma2(aA01, make_float2(xA[k].x, xA[k].y), xv[k]);
+                    ffma2(aA23, make_float2(xA[k].z, xA[k].w), xv[k]);
+                    ffma2(aB01, make_float2(xB[k].x, xB[k].y), xv[k]);
+                    ffma2(aB23, make_float2(xB[k].z, xB[k].w), xv[k]);
+                }
+                float k0 = hi ? aB01.x : aA01.x, k1 = hi ? aB01.y : aA01.y, k2 = hi ? aB23.x : aA23.x, k3 = hi ? aB23.y : aA23.y;
+                k0 += __shfl_xor_sync(0xffffffffu, hi ? aA01.x : aB01.x, 2);
+                k1 += __shfl_xor_sync(0xffffffffu, hi ? aA01.y : aB01.y, 2);
+                k2 += __shfl_xor_sync(0xffffffffu, hi ? aA23.x : aB23.x, 2);
+                k3 += __shfl_xor_sync(0xffffffffu, hi ? aA23.y : aB23.y, 2);
+                float v0 = odd ? k2 : k0, v1 = odd ? k3 : k1;
+                v0 += __shfl_xor_sync(0xffffffffu, odd ? k0 : k2, 1);
+                v1 += __shfl_xor_sync(0xffffffffu, odd ? k1 : k3, 1);
+                if (s0 + j < S) st2(gx + q * SQ + ((s0 + j) & (RING - 1)) * 256 + gsl, make_float2(v0 + gbias.x, v1 + gbias.y));
             }
-            float2 aA01 = make_float2(0.f, 0.f), aA23 = aA01, aB01 = aA01, aB23 = aA01;
-#pragma unroll
-            for (int k = 0; k < XK; ++k) {
-                ffma2(aA01, make_float2(xA[k].x, xA[k].y), xv[k]);
-                ffma2(aA23, make_float2(xA[k].z, xA[k].w), xv[k]);
-                ffma2(aB01, make_float2(xB[k].x, xB[k].y), xv[k]);
-                ffma2(aB23, make_float2(xB[k].z, xB[k].w), xv[k]);
-            }
-            float k0 = hi ? aB01.x : aA01.x, k1 = hi ? aB01.y : aA01.y, k2 = hi ? aB23.x : aA23.x, k3 = hi ? aB23.y : aA23.y;
-            k0 += __shfl_xor_sync(0xffffffffu, hi ? aA01.x : aB01.x, 2);
-            k1 += __shfl_xor_sync(0xffffffffu, hi ? aA01.y : aB01.y, 2);
-            k2 += __shfl_xor_sync(0xffffffffu, hi ? aA23.x : aB23.x, 2);
-            k3 += __shfl_xor_sync(0xffffffffu, hi ? aA23.y : aB23.y, 2);
-            float v0 = odd ? k2 : k0, v1 = odd ? k3 : k1;
-            v0 += __shfl_xor_sync(0xffffffffu, odd ? k0 : k2, 1);
-            v1 += __shfl_xor_sync(0xffffffffu, odd ? k1 : k3, 1);
-            if (s0 + j < S) st2(gx + ((s0 + j) & (RING - 1)) * 256 + gsl, make_float2(v0 + gbias.x, v1 + gbias.y));
         }
     };
 
@@ -814,6 +876,7 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
 //   tile : one warp (8 sequences) per SMSP needs ~13.2k cycles per step, two warps per SMSP ~20.7k (the launch gives a
 //          CTA ceil(tasks / SMs) <= 8 warps); more tasks than 8 x SMs run in rounds
 //   ws   : ~600-790 (one sequence per CTA, warp-specialised);  lane1/2/4 : 1360 / 2530 / 4950 (1/2/4 sequences per CTA)
+//   ws2  : ~1260 for the two sequences of a CTA
 //   tc   : ~15.5k per step for up to one wave of 128-sequence CTAs (tcgen05 gate GEMM + 256-thread cell update), ~10.8k
 //          per wave once several waves keep every SM busy; wins when the tile family needs several rounds (offline)
 // plus a launch + prologue constant; the cheapest family for (rows, dirs, steps) wins.
@@ -832,10 +895,13 @@ static int pick_algo(int n_rows, int n_dirs, int S, int sms, bool tc_ok) {
     int best = SB_ALGO_TILE;
     for (int k = SB_ALGO_LANE1; k <= SB_ALGO_WS; ++k)
         if (cost[k] < cost[best]) best = k;
+    double best_cost = cost[best];
+    const double ws2 = per_cta(2, 1260.0, 14000.0);        // two sequences per CTA: wins when it saves a round of CTAs
+    if (ws2 < best_cost) { best = SB_ALGO_WS2; best_cost = ws2; }
     if (tc_ok) {
         const double waves = (double)(ceil_div(n_rows, 128) * n_dirs) / sms;
         const double tc = S * (waves <= 1.0 ? 15500.0 : waves * 10800.0) + 60000.0;
-        if (tc < cost[best]) return SB_ALGO_TC;
+        if (tc < best_cost) return SB_ALGO_TC;
     }
     return best;
 }
@@ -879,8 +945,11 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
         case SB_ALGO_LANE4:
             return launch("lstm_lane4", lstm_lane_kernel<C, 4, RAW_H>, dim3(ceil_div(a.n_rows, 4), a.n_dirs), dim3(256), 0, st, a);
         case SB_ALGO_WS:
-            return launch("lstm_ws", lstm_ws_kernel<C, RAW_H>, dim3(a.n_rows, a.n_dirs), dim3(256),
-                          WsCfg<C>::smem_floats * sizeof(float), st, a);
+            return launch("lstm_ws", lstm_ws_kernel<C, RAW_H, 1>, dim3(a.n_rows, a.n_dirs), dim3(256),
+                          WsCfg<C, 1>::smem_floats * sizeof(float), st, a);
+        case SB_ALGO_WS2:
+            return launch("lstm_ws2", lstm_ws_kernel<C, RAW_H, 2>, dim3(ceil_div(a.n_rows, 2), a.n_dirs), dim3(256),
+                          WsCfg<C, 2>::smem_floats * sizeof(float), st, a);
         default: break;
     }
     set_error("unknown LSTM algo %d", algo);

@@ -194,6 +194,11 @@ class PipelinedSession:
         if flat != list(range(n_units)):
             raise ValueError("ranges must cover units 0..%d in order, got %r" % (n_units - 1, ranges))
         self.ranges = [tuple(r) for r in ranges]
+        # Throughput mode pays in SM-time, not latency.  With every SM busy (14 unit ranges, 8 chunks in flight) the
+        # intra-frame recurrence with two sequences per CTA wins: 0.81x the SM-time per sequence at 1.6x the latency
+        # (212k instead of 192k frames/s at batch 32).
+        if intra_algo is None and eng.intra_algo == abi.SB_ALGO_AUTO and batch_size >= 8 and frames_per_call == 1:
+            intra_algo = abi.SB_ALGO_WS2
         self.intra_algo = intra_algo          # None = the engine's choice (SB_ALGO_AUTO unless the caller forced one)
         # Throughput mode pays in SM-time, not latency: the one-step inter-frame call as a tcgen05 GEMM occupies a quarter
         # of the SMs the SIMT tile kernel needs (128-row tiles), which leaves room for the other chunks' recurrences.

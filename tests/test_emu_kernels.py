@@ -33,11 +33,16 @@ def test_frontend_backend_kernels(lib):
     _ok(kc.check_backend(lib, "cpu", "dis_embed", dict(SYN, num_src=2), B=1, T=10))
 
 
-@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE4, abi.SB_ALGO_WS])
+@pytest.mark.parametrize("algo", [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE4, abi.SB_ALGO_WS, abi.SB_ALGO_WS2])
 def test_lstm_kernels(lib, algo):
     _ok(kc.check_inter(lib, "cpu", "dis_embed", SYN, algo, B=1, T=3, alias_state=True))
     _ok(kc.check_intra(lib, "cpu", "dis_embed", SYN, algo, B=1, T=2))
     _ok(kc.check_intra(lib, "cpu", "optim", dict(OPI, D=16), algo, B=1, T=2))
+
+
+def test_two_sequences_per_cta_with_a_ragged_last_cta(lib):
+    """SB_ALGO_WS2 pairs rows (2i, 2i+1): an odd number of rows leaves the last CTA with one real sequence."""
+    _ok(kc.check_intra(lib, "cpu", "dis_embed", SYN, abi.SB_ALGO_WS2, B=1, T=3))
 
 
 def test_streaming_attention_path(lib):

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = 2e-5          # max-abs for single stages on O(1) data (fp32 both sides, different summation order)
 C16 = dict(OPI, D=16)
-ALGOS = [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2, abi.SB_ALGO_LANE4, abi.SB_ALGO_WS, abi.SB_ALGO_AUTO]
+ALGOS = [abi.SB_ALGO_TILE, abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2, abi.SB_ALGO_LANE4, abi.SB_ALGO_WS, abi.SB_ALGO_WS2,
+         abi.SB_ALGO_AUTO]
 
 
 @pytest.fixture(scope="module")
@@ -58,6 +59,14 @@ def test_intra_lstm(lib, algo, variant, kw):
 def test_inter_lstm(lib, algo, variant, kw):
     _ok(kc.check_inter(lib, DEV, variant, kw, algo, B=2, T=37, block=2))
     _ok(kc.check_inter(lib, DEV, variant, kw, algo, B=1, T=1, alias_state=True, two_inputs=False))
+
+
+def test_ws2_ragged_rows(lib):
+    """Two sequences per CTA: odd row counts (last CTA half empty), carried and aliased state, conv-LSTM raw-h mode."""
+    W2 = abi.SB_ALGO_WS2
+    _ok(kc.check_intra(lib, DEV, "dis_embed", SYN, W2, B=1, T=13, block=1))
+    _ok(kc.check_inter(lib, DEV, "dis_embed", SYN, W2, B=1, T=40, block=2, alias_state=True))
+    _ok(kc.check_intra(lib, DEV, "optim", RPI, W2, B=1, T=3, block=1))
 
 
 def test_tensor_core_lstm(lib):
@@ -122,7 +131,7 @@ def test_golden_through_c_abi(lib, name):
 
 @pytest.mark.parametrize("intra,inter", [(abi.SB_ALGO_TILE, abi.SB_ALGO_TILE), (abi.SB_ALGO_LANE1, abi.SB_ALGO_LANE2),
                                          (abi.SB_ALGO_LANE4, abi.SB_ALGO_LANE1), (abi.SB_ALGO_WS, abi.SB_ALGO_WS),
-                                         (abi.SB_ALGO_TC, abi.SB_ALGO_TC)])
+                                         (abi.SB_ALGO_TC, abi.SB_ALGO_TC), (abi.SB_ALGO_WS2, abi.SB_ALGO_WS2)])
 def test_golden_with_forced_lstm_algos(lib, intra, inter):
     pc.assert_parity(pc.run_golden(lib, DEV, "syn_offline", intra, inter))
 

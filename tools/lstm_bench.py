@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from bench import SYN  # noqa: E402
 from sound_bubble_b200 import Net, _abi as abi, _lib  # noqa: E402
 
-ALGO = {1: "tile", 2: "lane1", 3: "lane2", 4: "lane4", 5: "ws", 7: "tc"}
+ALGO = {1: "tile", 2: "lane1", 3: "lane2", 4: "lane4", 5: "ws", 8: "ws2", 7: "tc"}
 
 
 def main():
@@ -47,10 +47,10 @@ def main():
         h = torch.zeros(B * F, H, device=dev); c = torch.zeros(B * F, H, device=dev)
         film = torch.randn(2, B, F, C, device=dev)
         for kind in ("intra", "inter"):
-            for algo in ((1, 7) if only_tc else (1, 2, 3, 4, 5, 7)):
+            for algo in ((1, 7) if only_tc else (1, 2, 3, 4, 5, 8, 7)):
                 rows = B * T if kind == "intra" else B * F
                 steps = F if kind == "intra" else T
-                ctas = {1: rows / 8 / 8, 2: rows, 3: rows / 2, 4: rows / 4, 5: rows / 3, 7: rows / 128}[algo] * (2 if kind == "intra" else 1)
+                ctas = {1: rows / 8 / 8, 2: rows, 3: rows / 2, 4: rows / 4, 5: rows / 3, 8: rows / 6, 7: rows / 128}[algo] * (2 if kind == "intra" else 1)
                 if algo != 1 and ctas * steps > 148 * 145 * 80:
                     continue                                    # hopeless: skip the very long lane runs
                 if kind == "intra":
