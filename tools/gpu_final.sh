@@ -11,6 +11,7 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_streaming.csv python tools/profile_run.py --mode streaming --chunks 12 --graph 0 > gpurun_out/ncu1.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_offline.csv python tools/profile_run.py --mode offline > gpurun_out/ncu2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_ws -s 12 -c 2 -o gpurun_out/prof_ws python tools/profile_run.py --mode streaming --chunks 4 --graph 0 > gpurun_out/ncu3.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_ws -s 12 -c 2 -o gpurun_out/prof_ws2 python tools/profile_run.py --mode streaming --chunks 4 --graph 0 --intra-algo 8 > gpurun_out/ncu3b.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc -s 2 -c 1 -o gpurun_out/prof_tc python tools/profile_run.py --mode offline --batch 32 --frames 625 > gpurun_out/ncu4.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tile -s 2 -c 1 -o gpurun_out/prof_tile python tools/profile_run.py --mode offline --batch 8 --frames 200 --intra-algo 1 --inter-algo 1 > gpurun_out/ncu6.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'conv_in|backend_small|stft_features' -s 9 -c 3 -o gpurun_out/prof_small python tools/profile_run.py --mode streaming --chunks 4 --graph 0 > gpurun_out/ncu5.log 2>&1
