@@ -43,7 +43,8 @@ class NetBase(nn.Module):
         # intra-frame work of the next.  Same kernels per frame, so results agree with the single call to fp32 rounding.
         self.pipeline_offline = True
         self.offline_slice_frames = 125
-        self.offline_min_rows = 4096              # batch * frames below which the single call is used
+        self.offline_min_rows = 12000             # batch * frames below which the single call is used (measured crossover:
+                                                  # batch 16 x 625 frames, profiles/r01_offline_slices.txt)
         self._offline_pipes = {}
         self.offline_intra_algo = None            # None = SB_ALGO_AUTO per slice
         # the inter-frame path of a slice on the tcgen05 kernel: 37 CTAs instead of one per SM, so that the next slice's
