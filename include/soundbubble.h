@@ -342,6 +342,116 @@ int    sb_net_forward(const sb_net_desc* d, const sb_net_io* io, void* stream);
 /* state tensor belongs to one unit), so chunk t+1 unit u can run next to chunk t unit u+1 on another stream.           */
 int    sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first_unit, int last_unit, void* stream);
 
+/* ========================================================================================================== */
+/* TRAINING PATH (the *_bwd twins of the stages above; configs 4, 5: src/train_pt.py -> PLModule._step ->           */
+/* self.model(inputs) -> loss.backward(), src/hl_modules/distance_based_hl_module.py:303-330, 437-441).              */
+/* Training calls run from zero state (the reference trains with input_state=None, DE3/net.py:84-93), read the       */
+/* parameters in their CHECKPOINT layouts (they change every step, so nothing is re-packed), keep what the backward  */
+/* pass needs in a caller-owned `saved` buffer and ACCUMULATE (+=) into the caller's gradient buffers with fp32      */
+/* atomics (zero them first; summation order, hence the last bits, vary from run to run).  Plain BiLSTM / LSTM       */
+/* blocks only: conv_lstm and use_attn models have no backward kernels yet.                                          */
+/* ========================================================================================================== */
+
+/* One recurrent path of a GridNet block:  y = x + Linear(LSTM(LayerNorm_C(x))).                                     */
+/*   inter = 0: intra-frame path (DE3:794-827): rows (b,t), F steps, two directions, lin_w [C][2H]                   */
+/*   inter = 1: inter-frame path (DE3:829-849): rows (b,f), T steps, one direction from zero (h0, c0), lin_w [C][H]  */
+/*   w_ih [4H][C], w_hh [4H][H], b_ih/b_hh [4H] exactly as nn.LSTM stores them (gate order i, f, g, o).               */
+/*   saved: sb_path_train_saved_floats() floats = normalised input, LayerNorm output, 1/std, and per direction the    */
+/*   activated gates, c_t and h_t of every step (sequence-major [row][step][.]).  The backward call CONSUMES it (the   */
+/*   gate slots are overwritten with the pre-activation gradients).                                                   */
+typedef struct sb_path_train_args {
+    const float* x;             /* [B][T][F][C] */
+    float*       y;             /* [B][T][F][C]; must not alias x */
+    const float* ln_g;
+    const float* ln_b;
+    const float* w_ih[2];
+    const float* w_hh[2];
+    const float* b_ih[2];
+    const float* b_hh[2];
+    const float* lin_w;
+    const float* lin_b;
+    float*       saved;
+    int B, T, F, C, H;
+    int inter;
+} sb_path_train_args;
+size_t sb_path_train_saved_floats(int B, int T, int F, int C, int H, int inter);
+int    sb_intra_lstm_train_fwd(const sb_path_train_args* a, void* stream);     /* requires inter == 0 */
+int    sb_inter_lstm_train_fwd(const sb_path_train_args* a, void* stream);     /* requires inter == 1 */
+
+typedef struct sb_path_bwd_args {
+    sb_path_train_args f;       /* the forward call's arguments (y unused) */
+    const float* gy;            /* [B][T][F][C] dL/dy */
+    float*       gx;            /* [B][T][F][C] dL/dx (written; may alias gy) */
+    float* g_ln_g;  float* g_ln_b;
+    float* g_w_ih[2]; float* g_w_hh[2]; float* g_b_ih[2]; float* g_b_hh[2];
+    float* g_lin_w; float* g_lin_b;
+    float* ws;                  /* sb_path_bwd_workspace_floats() floats */
+} sb_path_bwd_args;
+size_t sb_path_bwd_workspace_floats(int B, int T, int F, int C, int H, int inter);
+int    sb_intra_lstm_bwd(const sb_path_bwd_args* a, void* stream);
+int    sb_inter_lstm_bwd(const sb_path_bwd_args* a, void* stream);
+
+/* FilmLayer.forward (DE3:51-68, :509-513) as its own stage: y = x * scale[b,f,c] + shift[b,f,c]; the backward also    */
+/* accumulates dL/dscale, dL/dshift [B][F][C] (sums over frames), which sb_film_params_bwd turns into parameter grads.*/
+typedef struct sb_film_apply_args {
+    const float* x;             /* [B][T][F][C] */
+    const float* film_scale;    /* [B][F][C] */
+    const float* film_shift;
+    float*       y;             /* fwd: output.  bwd: unused */
+    const float* gy;            /* bwd only */
+    float*       gx;            /* bwd only; may alias gy */
+    float*       g_scale;       /* bwd only, [B][F][C], accumulated */
+    float*       g_shift;
+    int B, T, F, C;
+} sb_film_apply_args;
+int sb_film_apply_fwd(const sb_film_apply_args* a, void* stream);
+int sb_film_apply_bwd(const sb_film_apply_args* a, void* stream);
+
+/* Backward of sb_film_params_fwd (Dis_Embed_Conv only, emb_mode SB_EMB_CONV): g_film [n_layers][2][B][F][C] ->        */
+/* gradients of embeds.j.{weight,bias}.{weight,bias}, embed_net.dis_norm, embed_net.dis_embedding.0.weight.           */
+typedef struct sb_film_bwd_args {
+    sb_film_args f;             /* forward arguments (film unused) */
+    const float* g_film;
+    float* g_emb_w; float* g_emb_ln_g; float* g_emb_ln_b;
+    float* g_w_w; float* g_w_b; float* g_b_w; float* g_b_b;
+} sb_film_bwd_args;
+int sb_film_params_bwd(const sb_film_bwd_args* a, void* stream);
+
+/* a6 for training: Conv2d(Cin -> C, (3,3), pad (0,1)) from zero history + LayerNorm(C); w [C][Cin][3][3] as stored.  */
+/*   saved: B*T*F*(2C+1) floats (conv output, normalised conv output, 1/std) when ln_g != NULL, else unused.         */
+typedef struct sb_conv_in_train_args {
+    const float* feats;         /* [B][T][F][Cin] */
+    const float* w;
+    const float* bias;
+    const float* ln_g;          /* NULL if use_first_ln is false */
+    const float* ln_b;
+    float*       x;             /* [B][T][F][C] */
+    float*       saved;
+    const float* gx;            /* bwd only: dL/dx */
+    float* g_w; float* g_bias; float* g_ln_g; float* g_ln_b;    /* bwd only, accumulated */
+    float*       ws;            /* bwd only: B*T*F*C floats */
+    int B, T, F, Cin, C;
+} sb_conv_in_train_args;
+int sb_conv_in_train_fwd(const sb_conv_in_train_args* a, void* stream);
+int sb_conv_in_bwd(const sb_conv_in_train_args* a, void* stream);
+
+/* Backward of sb_backend_fwd from zero history (DE3:517-542): g_wave [B][S][stride*T] -> gx [B][T][F][C], g_w, g_bias. */
+/*   ws: B*T*S*2F floats (the spectrum gradient).  mask_spec as in the forward call or NULL.                           */
+typedef struct sb_backend_bwd_args {
+    const float* x;             /* [B][T][F][C] the forward input */
+    const float* g_wave;
+    const float* w;             /* [C][2S][3][3] */
+    const float* filt;          /* [2F][n_fft] */
+    const float* mask_spec;
+    float*       gx;
+    float*       g_w;
+    float*       g_bias;
+    float*       ws;
+    int B, T, F, C, n_src;
+    int n_fft, stride;
+} sb_backend_bwd_args;
+int sb_backend_bwd(const sb_backend_bwd_args* a, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------- */
 /* Batch assembly on the device: src/datasets/general_multisrc_dataset_dis_embed.py:112-218 for PCM already in HBM  */
 /* (int16 -> float32, target = sum of the in-bubble voices at the reference microphone, one-hot radius) and the      */
@@ -411,7 +521,8 @@ const char* sb_last_error_string(void);
 uint64_t    sb_launch_count(void);
 /* sizeof() of the structs above as compiled, so the ctypes mirror can be checked without a GPU                 */
 /*   0 lstm_dir 1 stft 2 conv_in 3 film 4 intra 5 inter 6 backend 7 net_desc 8 net_io 9 intra_conv 10 attn_proj */
-/*   11 attn 12 block_desc 13 prepare                                                                          */
+/*   11 attn 12 block_desc 13 prepare 14 path_train 15 path_bwd 16 film_apply 17 film_bwd 18 conv_in_train     */
+/*   19 backend_bwd                                                                                            */
 int         sb_abi_sizeof(int which);
 
 #ifdef __cplusplus

@@ -123,9 +123,47 @@ class PrepareArgs(C.Structure):
                 ("B", C.c_int), ("M", C.c_int), ("V", C.c_int), ("N", C.c_int)]
 
 
+class PathTrainArgs(C.Structure):
+    _fields_ = [("x", fp), ("y", fp), ("ln_g", fp), ("ln_b", fp),
+                ("w_ih", fp * 2), ("w_hh", fp * 2), ("b_ih", fp * 2), ("b_hh", fp * 2),
+                ("lin_w", fp), ("lin_b", fp), ("saved", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("H", C.c_int), ("inter", C.c_int)]
+
+
+class PathBwdArgs(C.Structure):
+    _fields_ = [("f", PathTrainArgs), ("gy", fp), ("gx", fp), ("g_ln_g", fp), ("g_ln_b", fp),
+                ("g_w_ih", fp * 2), ("g_w_hh", fp * 2), ("g_b_ih", fp * 2), ("g_b_hh", fp * 2),
+                ("g_lin_w", fp), ("g_lin_b", fp), ("ws", fp)]
+
+
+class FilmApplyArgs(C.Structure):
+    _fields_ = [("x", fp), ("film_scale", fp), ("film_shift", fp), ("y", fp), ("gy", fp), ("gx", fp),
+                ("g_scale", fp), ("g_shift", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int)]
+
+
+class FilmBwdArgs(C.Structure):
+    _fields_ = [("f", FilmArgs), ("g_film", fp), ("g_emb_w", fp), ("g_emb_ln_g", fp), ("g_emb_ln_b", fp),
+                ("g_w_w", fp), ("g_w_b", fp), ("g_b_w", fp), ("g_b_b", fp)]
+
+
+class ConvInTrainArgs(C.Structure):
+    _fields_ = [("feats", fp), ("w", fp), ("bias", fp), ("ln_g", fp), ("ln_b", fp), ("x", fp), ("saved", fp),
+                ("gx", fp), ("g_w", fp), ("g_bias", fp), ("g_ln_g", fp), ("g_ln_b", fp), ("ws", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("Cin", C.c_int), ("C", C.c_int)]
+
+
+class BackendBwdArgs(C.Structure):
+    _fields_ = [("x", fp), ("g_wave", fp), ("w", fp), ("filt", fp), ("mask_spec", fp), ("gx", fp), ("g_w", fp),
+                ("g_bias", fp), ("ws", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("n_src", C.c_int),
+                ("n_fft", C.c_int), ("stride", C.c_int)]
+
+
 # index used by sb_abi_sizeof(which)
 ABI_STRUCTS = {0: LstmDir, 1: StftArgs, 2: ConvInArgs, 3: FilmArgs, 4: IntraArgs, 5: InterArgs, 6: BackendArgs,
-               7: NetDesc, 8: NetIO, 9: IntraConvArgs, 10: AttnProj, 11: AttnArgs, 12: BlockDesc, 13: PrepareArgs}
+               7: NetDesc, 8: NetIO, 9: IntraConvArgs, 10: AttnProj, 11: AttnArgs, 12: BlockDesc, 13: PrepareArgs,
+               14: PathTrainArgs, 15: PathBwdArgs, 16: FilmApplyArgs, 17: FilmBwdArgs, 18: ConvInTrainArgs, 19: BackendBwdArgs}
 
 # every symbol include/soundbubble.h declares: name -> (restype, argtypes)
 PROTOTYPES = {
@@ -144,6 +182,18 @@ PROTOTYPES = {
     "sb_net_forward_range": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_int, C.c_int, C.c_void_p]),
     "sb_prepare_workspace_floats": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "sb_prepare_batch_fwd": (C.c_int, [C.POINTER(PrepareArgs), C.c_void_p]),
+    "sb_path_train_saved_floats": (C.c_size_t, [C.c_int] * 6),
+    "sb_path_bwd_workspace_floats": (C.c_size_t, [C.c_int] * 6),
+    "sb_intra_lstm_train_fwd": (C.c_int, [C.POINTER(PathTrainArgs), C.c_void_p]),
+    "sb_inter_lstm_train_fwd": (C.c_int, [C.POINTER(PathTrainArgs), C.c_void_p]),
+    "sb_intra_lstm_bwd": (C.c_int, [C.POINTER(PathBwdArgs), C.c_void_p]),
+    "sb_inter_lstm_bwd": (C.c_int, [C.POINTER(PathBwdArgs), C.c_void_p]),
+    "sb_film_apply_fwd": (C.c_int, [C.POINTER(FilmApplyArgs), C.c_void_p]),
+    "sb_film_apply_bwd": (C.c_int, [C.POINTER(FilmApplyArgs), C.c_void_p]),
+    "sb_film_params_bwd": (C.c_int, [C.POINTER(FilmBwdArgs), C.c_void_p]),
+    "sb_conv_in_train_fwd": (C.c_int, [C.POINTER(ConvInTrainArgs), C.c_void_p]),
+    "sb_conv_in_bwd": (C.c_int, [C.POINTER(ConvInTrainArgs), C.c_void_p]),
+    "sb_backend_bwd": (C.c_int, [C.POINTER(BackendBwdArgs), C.c_void_p]),
     "sb_pipe_create": (C.c_int, [C.POINTER(NetDesc), C.POINTER(NetIO), C.c_int, C.c_int, C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "sb_pipe_destroy": (C.c_int, [C.c_void_p]),

@@ -107,6 +107,12 @@ extern "C" int sb_abi_sizeof(int which) {
         case 11: return (int)sizeof(sb_attn_args);
         case 12: return (int)sizeof(sb_block_desc);
         case 13: return (int)sizeof(sb_prepare_args);
+        case 14: return (int)sizeof(sb_path_train_args);
+        case 15: return (int)sizeof(sb_path_bwd_args);
+        case 16: return (int)sizeof(sb_film_apply_args);
+        case 17: return (int)sizeof(sb_film_bwd_args);
+        case 18: return (int)sizeof(sb_conv_in_train_args);
+        case 19: return (int)sizeof(sb_backend_bwd_args);
         default: return -1;
     }
 }

@@ -1,0 +1,1030 @@
+// Training path: forward kernels that keep what back-propagation needs, and the backward kernels (the *_bwd twins).
+//
+// Reference spans (DE3 = src/models/tfgridnet_realtime_clean_dis_embd3/tfgridnet_causal.py); what is differentiated is
+// exactly what PLModule._step runs under autograd (src/hl_modules/distance_based_hl_module.py:303-330, 437-441):
+//   conv-in + LayerNorm      :332-354, 499-507     conv_in_train_kernel, ln_fwd_kernel / ln_bwd_kernel, conv_in_wgrad_kernel
+//   FilmLayer                :51-68, 509-513       film_apply_*_kernel, film_params_bwd_kernel (Dis_Embed_Conv :150-173)
+//   intra / inter LSTM paths :794-827, 829-849     ln_fwd -> lstm_train_fwd -> rowgemm (Linear + residual);
+//                                                  rowgemm (dL/dh) -> lstm_train_bwd (BPTT, serial part only: the cell
+//                                                  derivatives and W_hh^T dz) -> rowgemm (dL/dLN(x)) -> ln_bwd, and the
+//                                                  weight gradients as one reduction over all (row, step) pairs (outer_kernel)
+//   deconv + iSTFT/OLA       :401, 517-542         istft_bwd_kernel, deconv_bwd_x_kernel, deconv_wgrad_kernel
+// The STFT basis buffers and the input features carry no gradient (no parameter upstream of conv-in).
+//
+// Layout: the LSTM-side buffers are sequence-major, n = row * S + step ("[row][step][.]"); the activations stay in
+// X[B][T][F][C].  For the intra-frame path the two orders coincide (row = (b,t), step = f); for the inter-frame path
+// (row = (b,f), step = t) RowMap converts.  Gradients are accumulated with fp32 atomics.
+#include "sb_common.cuh"
+
+namespace sb {
+
+constexpr int kH = 64;
+
+struct RowMap {
+    int S, F, inter;
+};
+// sequence-major index n -> index of the same (b, t, f) position in X[B][T][F][.]
+__device__ __forceinline__ long long map_pos(const RowMap& m, long long n) {
+    if (!m.inter) return n;
+    const long long row = n / m.S;
+    const int s = (int)(n - row * m.S);
+    const long long b = row / m.F;
+    const int f = (int)(row - b * m.F);
+    return (b * m.S + s) * m.F + f;
+}
+
+#ifdef SB_EMU
+__device__ __forceinline__ void atomic_add(float* p, float v) { emu_atomic_add(p, v); }
+#else
+__device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v); }
+#endif
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm over C, one position per thread.  in: rows of C floats at map_pos(n) (or n); out: xhat[n], xn[n], rstd[n].
+// ------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* x, RowMap map, const float* g, const float* bta,
+                                                     float* xhat, float* xn, float* rstd, long long N, float eps) {
+    pdl_wait();
+    const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const float* xr = x + map_pos(map, n) * C;
+    float v[C];
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+        const float4 t = ldg4_stream(xr + 4 * i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        mean += (t.x + t.y) + (t.z + t.w);
+    }
+    mean *= 1.0f / C;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) { v[i] -= mean; var = fmaf(v[i], v[i], var); }
+    const float r = rsqrtf(var * (1.0f / C) + eps);
+    rstd[n] = r;
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+        float4 h, o;
+        h.x = v[4 * i] * r; h.y = v[4 * i + 1] * r; h.z = v[4 * i + 2] * r; h.w = v[4 * i + 3] * r;
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i), bb = __ldg(reinterpret_cast<const float4*>(bta) + i);
+        o.x = fmaf(h.x, gg.x, bb.x); o.y = fmaf(h.y, gg.y, bb.y); o.z = fmaf(h.z, gg.z, bb.z); o.w = fmaf(h.w, gg.w, bb.w);
+        st4(xhat + n * C + 4 * i, h);
+        st4(xn + n * C + 4 * i, o);
+    }
+}
+
+// dL/dLN-output (dxn[n]) -> dL/dx at map_pos(n) (+ the residual branch's gradient gy), and the gain / bias gradients.
+template <int C>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* dxn, const float* xhat, const float* rstd, const float* g,
+                                                     const float* gy, float* gx, RowMap map, float* g_g, float* g_b,
+                                                     long long N) {
+    __shared__ float red[2 * C];
+    pdl_wait();
+    if (threadIdx.x < 2 * C) red[threadIdx.x] = 0.f;
+    __syncthreads();
+    float ag[C], ab[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+    for (long long n = (long long)blockIdx.x * 256 + threadIdx.x; n < N; n += (long long)gridDim.x * 256) {
+        float d[C], h[C];
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+            const float4 t = ldg4_stream(dxn + n * C + 4 * i), u = ldg4_stream(xhat + n * C + 4 * i);
+            d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
+            h[4 * i] = u.x; h[4 * i + 1] = u.y; h[4 * i + 2] = u.z; h[4 * i + 3] = u.w;
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            ag[i] = fmaf(d[i], h[i], ag[i]);
+            ab[i] += d[i];
+            d[i] *= __ldg(g + i);
+            m1 += d[i];
+            m2 = fmaf(d[i], h[i], m2);
+        }
+        m1 *= 1.0f / C;
+        m2 *= 1.0f / C;
+        const float r = rstd[n];
+        const long long p = map_pos(map, n) * C;
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+            float4 o;
+            o.x = r * (d[4 * i] - m1 - h[4 * i] * m2);
+            o.y = r * (d[4 * i + 1] - m1 - h[4 * i + 1] * m2);
+            o.z = r * (d[4 * i + 2] - m1 - h[4 * i + 2] * m2);
+            o.w = r * (d[4 * i + 3] - m1 - h[4 * i + 3] * m2);
+            if (gy) {
+                const float4 t = ld_plain4(gy + p + 4 * i);
+                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            st4(gx + p + 4 * i, o);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        float a = ag[i], b = ab[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if ((threadIdx.x & 31) == 0) { atomic_add(&red[i], a); atomic_add(&red[C + i], b); }
+    }
+    __syncthreads();
+    if (threadIdx.x < C) atomic_add(g_g + threadIdx.x, red[threadIdx.x]);
+    else if (threadIdx.x < 2 * C) atomic_add(g_b + threadIdx.x - C, red[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LSTM forward that stores the activated gates, c_t and h_t of every step.  CTA = 4 sequences of one direction; thread j
+// owns gate column j (row j of [W_ih | W_hh], in registers) for the four sequences; [x_t | h_{t-1}] of the four sequences
+// sits in shared memory as one float4 per k (a broadcast LDS.128 feeds four FMAs); threads (q, u) do the cell update.
+// ------------------------------------------------------------------------------------------------------------
+struct LstmTrain {
+    const float* xn;                    // [N][C]
+    const float* w_ih[2];
+    const float* w_hh[2];
+    const float* b_ih[2];
+    const float* b_hh[2];
+    float* gates[2];                    // [N][4H]  fwd: i, f, g, o (activated)   bwd: overwritten with dL/dz
+    float* c[2];                        // [N][H]
+    float* h[2];                        // [N][H]
+    const float* dh[2];                 // bwd: dL/dh_t from the projection, [N][H]
+    int R, S;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) lstm_train_fwd_kernel(const LstmTrain a) {
+    constexpr int H = kH, NS = 4, K = C + H;
+    __shared__ float4 a_s[K];
+    __shared__ float z_s[NS][4 * H];
+    const int tid = threadIdx.x, d = blockIdx.y, r0 = blockIdx.x * NS, S = a.S;
+    float w[K];
+#pragma unroll
+    for (int k = 0; k < C; k += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.w_ih[d] + (size_t)tid * C + k));
+        w[k] = t.x; w[k + 1] = t.y; w[k + 2] = t.z; w[k + 3] = t.w;
+    }
+#pragma unroll
+    for (int k = 0; k < H; k += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.w_hh[d] + (size_t)tid * H + k));
+        w[C + k] = t.x; w[C + k + 1] = t.y; w[C + k + 2] = t.z; w[C + k + 3] = t.w;
+    }
+    const float bias = __ldg(a.b_ih[d] + tid) + __ldg(a.b_hh[d] + tid);
+    const int gate = tid / H;
+    // x loader role (tid < NS*C): sequence xq, channel xc.  cell role: sequence q, unit u.
+    const int xq = tid / C, xc = tid - xq * C;
+    const bool loader = tid < NS * C;
+    const long long xrow = min(r0 + (loader ? xq : 0), a.R - 1);
+    const int q = tid / H, u = tid - q * H;
+    const bool valid = r0 + q < a.R;
+    const long long crow = min(r0 + q, a.R - 1);
+    reinterpret_cast<float*>(&a_s[C + u])[q] = 0.f;
+    float c_reg = 0.f;
+    pdl_wait();
+    float xv = 0.f;
+    if (loader) xv = ldg1_stream(a.xn + (xrow * S + (d ? S - 1 : 0)) * C + xc);
+    for (int s = 0; s < S; ++s) {
+        const int se = d ? S - 1 - s : s;
+        if (loader) reinterpret_cast<float*>(&a_s[xc])[xq] = xv;
+        __syncthreads();
+        if (loader && s + 1 < S) xv = ldg1_stream(a.xn + (xrow * S + (d ? se - 1 : se + 1)) * C + xc);
+        float acc0 = bias, acc1 = bias, acc2 = bias, acc3 = bias;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 v = a_s[k];
+            acc0 = fmaf(w[k], v.x, acc0); acc1 = fmaf(w[k], v.y, acc1); acc2 = fmaf(w[k], v.z, acc2); acc3 = fmaf(w[k], v.w, acc3);
+        }
+        if (gate == 2) { acc0 = tanh_f(acc0); acc1 = tanh_f(acc1); acc2 = tanh_f(acc2); acc3 = tanh_f(acc3); }
+        else { acc0 = sigmoid_f(acc0); acc1 = sigmoid_f(acc1); acc2 = sigmoid_f(acc2); acc3 = sigmoid_f(acc3); }
+        z_s[0][tid] = acc0; z_s[1][tid] = acc1; z_s[2][tid] = acc2; z_s[3][tid] = acc3;
+        {
+            float* gp = a.gates[d] + ((long long)r0 * S + se) * (4 * H) + tid;
+            const long long seq = (long long)S * 4 * H;
+            if (r0 + 0 < a.R) gp[0] = acc0;
+            if (r0 + 1 < a.R) gp[seq] = acc1;
+            if (r0 + 2 < a.R) gp[2 * seq] = acc2;
+            if (r0 + 3 < a.R) gp[3 * seq] = acc3;
+        }
+        __syncthreads();
+        const float gi = z_s[q][u], gf = z_s[q][H + u], gg = z_s[q][2 * H + u], go = z_s[q][3 * H + u];
+        c_reg = fmaf(gf, c_reg, gi * gg);
+        const float hh = go * tanh_f(c_reg);
+        reinterpret_cast<float*>(&a_s[C + u])[q] = hh;
+        if (valid) {
+            const long long n = crow * S + se;
+            a.c[d][n * H + u] = c_reg;
+            a.h[d][n * H + u] = hh;
+        }
+    }
+}
+
+// BPTT, serial part: per step the cell derivatives (dz, written over the stored gates) and dh_{t-1} += W_hh^T dz.
+// Thread (q, u) differentiates the cell of sequence q, unit u; thread (quarter, k) then sums its quarter of the 4H gate
+// rows of column k of W_hh (64 weights in registers) for the four sequences.
+__global__ void __launch_bounds__(256) lstm_train_bwd_kernel(const LstmTrain a) {
+    constexpr int H = kH, NS = 4;
+    __shared__ float4 dz_s[4 * H];
+    __shared__ float part_s[4][NS][H];
+    const int tid = threadIdx.x, d = blockIdx.y, r0 = blockIdx.x * NS, S = a.S;
+    const int q = tid / H, u = tid - q * H;
+    float wq[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) wq[j] = __ldg(a.w_hh[d] + (size_t)(q * H + j) * H + u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) part_s[i][q][u] = 0.f;
+    const bool valid = r0 + q < a.R;
+    const long long row = min(r0 + q, a.R - 1);
+    float* gates = a.gates[d];
+    const float* cc = a.c[d];
+    const float* dh = a.dh[d];
+    pdl_wait();
+    __syncthreads();
+    float dc = 0.f;
+    // software pipeline: the loads of step s+1 are issued before the W_hh^T product of step s
+    int se = d ? 0 : S - 1;
+    long long n = row * S + se;
+    float gi = gates[n * 4 * H + u], gf = gates[n * 4 * H + H + u], gg = gates[n * 4 * H + 2 * H + u], go = gates[n * 4 * H + 3 * H + u];
+    float ct = cc[n * H + u], dhv = dh[n * H + u];
+    float cp = S > 1 ? cc[(d ? n + 1 : n - 1) * H + u] : 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float dht = dhv + ((part_s[0][q][u] + part_s[1][q][u]) + (part_s[2][q][u] + part_s[3][q][u]));
+        const float tc = tanh_f(ct);
+        const float dcv = fmaf(dht * go, 1.f - tc * tc, dc);
+        const float dzi = dcv * gg * gi * (1.f - gi);
+        const float dzf = dcv * cp * gf * (1.f - gf);
+        const float dzg = dcv * gi * (1.f - gg * gg);
+        const float dzo = dht * tc * go * (1.f - go);
+        dc = dcv * gf;
+        reinterpret_cast<float*>(&dz_s[u])[q] = dzi;
+        reinterpret_cast<float*>(&dz_s[H + u])[q] = dzf;
+        reinterpret_cast<float*>(&dz_s[2 * H + u])[q] = dzg;
+        reinterpret_cast<float*>(&dz_s[3 * H + u])[q] = dzo;
+        if (valid) {
+            gates[n * 4 * H + u] = dzi; gates[n * 4 * H + H + u] = dzf; gates[n * 4 * H + 2 * H + u] = dzg; gates[n * 4 * H + 3 * H + u] = dzo;
+        }
+        if (s + 1 < S) {
+            se = d ? se + 1 : se - 1;
+            n = row * S + se;
+            gi = gates[n * 4 * H + u]; gf = gates[n * 4 * H + H + u]; gg = gates[n * 4 * H + 2 * H + u]; go = gates[n * 4 * H + 3 * H + u];
+            ct = cp;
+            dhv = dh[n * H + u];
+            cp = s + 2 < S ? cc[(d ? n + 1 : n - 1) * H + u] : 0.f;
+        }
+        __syncthreads();
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float4 v = dz_s[q * H + j];
+            p0 = fmaf(wq[j], v.x, p0); p1 = fmaf(wq[j], v.y, p1); p2 = fmaf(wq[j], v.z, p2); p3 = fmaf(wq[j], v.w, p3);
+        }
+        part_s[q][0][u] = p0; part_s[q][1][u] = p1; part_s[q][2][u] = p2; part_s[q][3][u] = p3;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// out[o(n)][0..P) = bias + res[o(n)] + sum_a sum_k A_a[i(n)][k] * W_a(k, p)       (tall-skinny GEMM, W in shared memory)
+// ------------------------------------------------------------------------------------------------------------
+struct RowGemm {
+    const float* A[2];
+    const float* W[2];
+    int nA, K, lda, ldw, w_trans;       // W(k, p) = w_trans ? W[p*ldw + k] : W[k*ldw + p]
+    const float* bias;
+    const float* res;
+    float* out;
+    RowMap map;
+    int a_mapped, o_mapped;
+    long long N;
+};
+
+template <int P>
+__global__ void __launch_bounds__(256) rowgemm_kernel(const RowGemm g) {
+    SB_DYN_SMEM(float, ws);                         // [nA][K][P]
+    constexpr int TPR = P / 8, ROWS = 256 / TPR;
+    const int tid = threadIdx.x, K = g.K;
+    for (int a = 0; a < g.nA; ++a)
+        for (int i = tid; i < K * P; i += 256) {
+            const int k = i / P, p = i - k * P;
+            ws[(a * K + k) * P + p] = __ldg(g.W[a] + (g.w_trans ? (size_t)p * g.ldw + k : (size_t)k * g.ldw + p));
+        }
+    pdl_wait();
+    __syncthreads();
+    const long long n = (long long)blockIdx.x * ROWS + tid / TPR;
+    if (n >= g.N) return;
+    const int p0 = (tid % TPR) * 8;
+    const long long pos = map_pos(g.map, n);
+    const long long na = g.a_mapped ? pos : n, no = g.o_mapped ? pos : n;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = g.bias ? __ldg(g.bias + p0 + i) : 0.f;
+    if (g.res) {
+        const float4 r0 = ldg4_stream(g.res + no * P + p0), r1 = ldg4_stream(g.res + no * P + p0 + 4);
+        acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w; acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+    }
+    for (int a = 0; a < g.nA; ++a) {
+        const float* ar = g.A[a] + na * g.lda;
+        const float* wa = ws + (size_t)a * K * P + p0;
+        for (int k = 0; k < K; k += 4) {
+            const float4 av = ld4(ar + k);
+            const float avv[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 w0 = ld4(wa + (k + kk) * P), w1 = ld4(wa + (k + kk) * P + 4);
+                acc[0] = fmaf(avv[kk], w0.x, acc[0]); acc[1] = fmaf(avv[kk], w0.y, acc[1]);
+                acc[2] = fmaf(avv[kk], w0.z, acc[2]); acc[3] = fmaf(avv[kk], w0.w, acc[3]);
+                acc[4] = fmaf(avv[kk], w1.x, acc[4]); acc[5] = fmaf(avv[kk], w1.y, acc[5]);
+                acc[6] = fmaf(avv[kk], w1.z, acc[6]); acc[7] = fmaf(avv[kk], w1.w, acc[7]);
+            }
+        }
+    }
+    st4(g.out + no * P + p0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(g.out + no * P + p0 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dW[j][k] += sum_n A[n][j] * B[n'][k],  db[j] += sum_n A[n][j]          (reduction over all (row, step) pairs)
+//   b_mode 0: n' = n;  1: n' = map_pos(n) (A mapped the same way if a_mapped);  2: n' = the previous step of the same
+//   sequence in processing order (n - 1, or n + 1 for the reverse direction), a zero row at the sequence start.
+// Each CTA walks a contiguous range of n in slabs of 16 rows staged in shared memory; thread tile TJ x TK in registers.
+// ------------------------------------------------------------------------------------------------------------
+struct Outer {
+    const float* A;
+    const float* Bm;
+    float* dW;
+    float* db;
+    float* db2;
+    RowMap map;
+    int a_mapped, b_mode, reverse, ldw;
+    long long N, rows_per_cta;
+};
+
+template <int J, int KC, int TJ, int TK>
+__global__ void __launch_bounds__(256) outer_kernel(const Outer o) {
+    constexpr int RB = 16, NTJ = J / TJ, NTK = KC / TK;
+    static_assert(NTJ * NTK <= 256, "tile");
+    __shared__ __align__(16) float As[RB][J];
+    __shared__ __align__(16) float Bs[RB][KC];
+    const int tid = threadIdx.x;
+    const int tj = tid % NTJ, tk = tid / NTJ;
+    const bool worker = tk < NTK;
+    float acc[TJ][TK], accb[TJ];
+#pragma unroll
+    for (int i = 0; i < TJ; ++i) {
+        accb[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < TK; ++k) acc[i][k] = 0.f;
+    }
+    const long long n_begin = (long long)blockIdx.x * o.rows_per_cta;
+    const long long n_end = n_begin + o.rows_per_cta < o.N ? n_begin + o.rows_per_cta : o.N;
+    pdl_wait();
+    for (long long n0 = n_begin; n0 < n_end; n0 += RB) {
+        for (int i = tid; i < RB * (J / 4); i += 256) {
+            const int r = i / (J / 4), c4 = i - r * (J / 4);
+            const long long n = n0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < n_end) v = ldg4_stream(o.A + (o.a_mapped ? map_pos(o.map, n) : n) * J + 4 * c4);
+            st4(&As[r][4 * c4], v);
+        }
+        for (int i = tid; i < RB * (KC / 4); i += 256) {
+            const int r = i / (KC / 4), c4 = i - r * (KC / 4);
+            const long long n = n0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < n_end) {
+                long long nb = n;
+                bool zero = false;
+                if (o.b_mode == 1) nb = map_pos(o.map, n);
+                else if (o.b_mode == 2) {
+                    const int s = (int)(n % o.map.S);
+                    if (o.reverse) { zero = s == o.map.S - 1; nb = n + 1; }
+                    else { zero = s == 0; nb = n - 1; }
+                }
+                if (!zero) v = ldg4_stream(o.Bm + nb * KC + 4 * c4);
+            }
+            st4(&Bs[r][4 * c4], v);
+        }
+        __syncthreads();
+        if (worker) {
+#pragma unroll 4
+            for (int r = 0; r < RB; ++r) {
+                float av[TJ], bv[TK];
+#pragma unroll
+                for (int i = 0; i < TJ; ++i) av[i] = As[r][tj * TJ + i];
+#pragma unroll
+                for (int k = 0; k < TK; ++k) bv[k] = Bs[r][tk * TK + k];
+#pragma unroll
+                for (int i = 0; i < TJ; ++i) {
+                    if (tk == 0) accb[i] += av[i];
+#pragma unroll
+                    for (int k = 0; k < TK; ++k) acc[i][k] = fmaf(av[i], bv[k], acc[i][k]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (worker) {
+#pragma unroll
+        for (int i = 0; i < TJ; ++i) {
+#pragma unroll
+            for (int k = 0; k < TK; ++k) atomic_add(o.dW + (size_t)(tj * TJ + i) * o.ldw + tk * TK + k, acc[i][k]);
+            if (tk == 0) {
+                if (o.db) atomic_add(o.db + tj * TJ + i, accb[i]);
+                if (o.db2) atomic_add(o.db2 + tj * TJ + i, accb[i]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FiLM apply
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) film_apply_fwd_kernel(const sb_film_apply_args a) {
+    pdl_wait();
+    const long long n4 = (long long)a.B * a.T * a.F * a.C / 4, fc4 = (long long)a.F * a.C / 4, tfc4 = fc4 * a.T;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const long long b = i / tfc4, r = i % fc4;
+        const float4 v = ldg4_stream(a.x + 4 * i);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(a.film_scale) + b * fc4 + r);
+        const float4 h = __ldg(reinterpret_cast<const float4*>(a.film_shift) + b * fc4 + r);
+        st4(a.y + 4 * i, make_float4(fmaf(v.x, s.x, h.x), fmaf(v.y, s.y, h.y), fmaf(v.z, s.z, h.z), fmaf(v.w, s.w, h.w)));
+    }
+}
+
+// thread (b, f, c) walks the frames: dL/dx = g * scale; dL/dscale += sum_t g * x; dL/dshift += sum_t g
+__global__ void __launch_bounds__(256) film_apply_bwd_kernel(const sb_film_apply_args a) {
+    pdl_wait();
+    const long long fc = (long long)a.F * a.C, total = fc * a.B;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const long long b = i / fc, r = i - b * fc;
+    const float sc = __ldg(a.film_scale + i);
+    float gs = 0.f, gh = 0.f;
+    for (int t = 0; t < a.T; ++t) {
+        const long long p = (b * a.T + t) * fc + r;
+        const float g = ld_plain(a.gy + p), x = ldg1_stream(a.x + p);
+        gs = fmaf(g, x, gs);
+        gh += g;
+        a.gx[p] = g * sc;
+    }
+    a.g_scale[i] += gs;
+    a.g_shift[i] += gh;
+}
+
+// Dis_Embed_Conv + the 1x1 convs of every FilmLayer, backward.  CTA = one utterance.
+__global__ void __launch_bounds__(256) film_params_bwd_kernel(const sb_film_bwd_args a) {
+    SB_DYN_SMEM(float, sm);
+    const sb_film_args& f = a.f;
+    const int F = f.F, C = f.C, Din = f.Din, L = f.n_layers, b = blockIdx.x, tid = threadIdx.x;
+    float* e_s = sm;                                // [F][Din]  embedding (LayerNorm output)
+    float* eh_s = e_s + F * Din;                    // [F][Din]  normalised
+    float* rs_s = eh_s + F * Din;                   // [F]
+    float* de_s = rs_s + F;                         // [F][Din]
+    pdl_wait();
+    const float d0 = __ldg(f.dis + b * 3), d1 = __ldg(f.dis + b * 3 + 1), d2 = __ldg(f.dis + b * 3 + 2);
+    for (int fq = tid; fq < F; fq += 256) {
+        float mean = 0.f;
+        for (int i = 0; i < Din; ++i) {
+            const float* w = f.emb_w + (size_t)(fq * Din + i) * 3;
+            const float v = fmaf(__ldg(w + 2), d2, fmaf(__ldg(w + 1), d1, __ldg(w) * d0));
+            eh_s[fq * Din + i] = v;
+            mean += v;
+        }
+        mean /= Din;
+        float var = 0.f;
+        for (int i = 0; i < Din; ++i) { const float v = eh_s[fq * Din + i] - mean; eh_s[fq * Din + i] = v; var = fmaf(v, v, var); }
+        const float r = rsqrtf(var / Din + 1e-5f);
+        rs_s[fq] = r;
+        for (int i = 0; i < Din; ++i) {
+            const float h = eh_s[fq * Din + i] * r;
+            eh_s[fq * Din + i] = h;
+            e_s[fq * Din + i] = fmaf(h, __ldg(f.emb_ln_g + i), __ldg(f.emb_ln_b + i));
+            de_s[fq * Din + i] = 0.f;
+        }
+    }
+    __syncthreads();
+    const size_t plane = (size_t)f.B * F * C;
+    // (1) thread (layer, c): gradients of the two 1x1 convs, summed over f
+    for (int lc = tid; lc < L * C; lc += 256) {
+        const int l = lc / C, c = lc - l * C;
+        const float* gs = a.g_film + ((size_t)(2 * l) * f.B + b) * F * C + c;
+        const float* gh = gs + plane;
+        float sw = 0.f, sb_ = 0.f;
+        for (int i = 0; i < Din; ++i) {
+            float aw = 0.f, ab = 0.f;
+            for (int fq = 0; fq < F; ++fq) {
+                const float e = e_s[fq * Din + i];
+                aw = fmaf(__ldg(gs + (size_t)fq * C), e, aw);
+                ab = fmaf(__ldg(gh + (size_t)fq * C), e, ab);
+            }
+            atomic_add(a.g_w_w + (size_t)lc * Din + i, aw);
+            atomic_add(a.g_b_w + (size_t)lc * Din + i, ab);
+        }
+        for (int fq = 0; fq < F; ++fq) { sw += __ldg(gs + (size_t)fq * C); sb_ += __ldg(gh + (size_t)fq * C); }
+        atomic_add(a.g_w_b + lc, sw);
+        atomic_add(a.g_b_b + lc, sb_);
+    }
+    // (2) thread f: dL/de, LayerNorm(Din) backward, dL/d(embedding weight)
+    for (int fq = tid; fq < F; fq += 256) {
+        for (int l = 0; l < L; ++l) {
+            const float* gs = a.g_film + (((size_t)(2 * l) * f.B + b) * F + fq) * C;
+            const float* gh = gs + plane;
+            for (int c = 0; c < C; ++c) {
+                const float s = __ldg(gs + c), h = __ldg(gh + c);
+                for (int i = 0; i < Din; ++i)
+                    de_s[fq * Din + i] += s * __ldg(f.w_w + (size_t)(l * C + c) * Din + i) + h * __ldg(f.b_w + (size_t)(l * C + c) * Din + i);
+            }
+        }
+        float m1 = 0.f, m2 = 0.f;
+        for (int i = 0; i < Din; ++i) {
+            const float de = de_s[fq * Din + i], h = eh_s[fq * Din + i];
+            atomic_add(a.g_emb_ln_g + i, de * h);
+            atomic_add(a.g_emb_ln_b + i, de);
+            const float dg = de * __ldg(f.emb_ln_g + i);
+            de_s[fq * Din + i] = dg;
+            m1 += dg;
+            m2 = fmaf(dg, h, m2);
+        }
+        m1 /= Din;
+        m2 /= Din;
+        for (int i = 0; i < Din; ++i) {
+            const float dl = rs_s[fq] * (de_s[fq * Din + i] - m1 - eh_s[fq * Din + i] * m2);
+            float* gw = a.g_emb_w + (size_t)(fq * Din + i) * 3;
+            atomic_add(gw, dl * d0);
+            atomic_add(gw + 1, dl * d1);
+            atomic_add(gw + 2, dl * d2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// conv-in for training (zero history): y[b,t,f,o] = bias[o] + sum_{c,kt,kf} w[o][c][kt][kf] * feats[b, t+kt-2, f+kf-1, c]
+// ------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) conv_in_train_kernel(const sb_conv_in_train_args a, float* y) {
+    SB_DYN_SMEM(float, w_s);                        // [kt][kf][cin][o]
+    const int Cin = a.Cin, F = a.F, T = a.T, tid = threadIdx.x;
+    for (int i = tid; i < 9 * Cin * C; i += 256) {
+        const int o = i % C, c = (i / C) % Cin, tap = i / (C * Cin);
+        w_s[i] = __ldg(a.w + ((size_t)o * Cin + c) * 9 + tap);
+    }
+    pdl_wait();
+    __syncthreads();
+    constexpr int TPR = C / 8, ROWS = 256 / TPR;
+    const long long N = (long long)a.B * T * F;
+    const long long n = (long long)blockIdx.x * ROWS + tid / TPR;
+    if (n >= N) return;
+    const int o0 = (tid % TPR) * 8;
+    const int fq = (int)(n % F), t = (int)((n / F) % T);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = __ldg(a.bias + o0 + i);
+    for (int kt = 0; kt < 3; ++kt) {
+        if (t + kt - 2 < 0) continue;
+        for (int kf = 0; kf < 3; ++kf) {
+            const int ff = fq + kf - 1;
+            if (ff < 0 || ff >= F) continue;
+            const float* xr = a.feats + (n + (long long)(kt - 2) * F + (kf - 1)) * Cin;
+            const float* wr = w_s + (size_t)(kt * 3 + kf) * Cin * C + o0;
+            for (int c = 0; c < Cin; ++c) {
+                const float v = __ldg(xr + c);
+                const float4 w0 = ld4(wr + c * C), w1 = ld4(wr + c * C + 4);
+                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+            }
+        }
+    }
+    st4(y + n * C + o0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(y + n * C + o0 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// dL/dw[o][c][kt][kf] += sum_n g[n][o] * feats[n shifted by (kt-2, kf-1)][c];  dL/dbias[o] += sum_n g[n][o].
+// Thread = one (tap, c) pair with C accumulators; the g rows of 32 positions are staged in shared memory.
+template <int C>
+__global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const sb_conv_in_train_args a, const float* g, long long rows_per_cta) {
+    constexpr int RB = 32;
+    __shared__ __align__(16) float g_s[RB][C];
+    const int Cin = a.Cin, F = a.F, T = a.T, tid = threadIdx.x;
+    const long long N = (long long)a.B * T * F;
+    const long long n_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long n_end = n_begin + rows_per_cta < N ? n_begin + rows_per_cta : N;
+    pdl_wait();
+    for (int pair0 = 0; pair0 < 9 * Cin; pair0 += 256) {
+        const int pair = pair0 + tid;
+        const bool worker = pair < 9 * Cin;
+        const int tap = worker ? pair / Cin : 0, c = worker ? pair - tap * Cin : 0, kt = tap / 3, kf = tap - kt * 3;
+        float acc[C], accb = 0.f;
+#pragma unroll
+        for (int o = 0; o < C; ++o) acc[o] = 0.f;
+        for (long long n0 = n_begin; n0 < n_end; n0 += RB) {
+            __syncthreads();
+            for (int i = tid; i < RB * C / 4; i += 256) {
+                const long long n = n0 + i / (C / 4);
+                st4(&g_s[0][0] + 4 * i, n < n_end ? ldg4_stream(g + n * C + 4 * (i % (C / 4))) : make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            __syncthreads();
+            if (worker) {
+                for (int r = 0; r < RB; ++r) {
+                    const long long n = n0 + r;
+                    if (n >= n_end) break;
+                    const int fq = (int)(n % F), t = (int)((n / F) % T), ff = fq + kf - 1;
+                    if (t + kt - 2 < 0 || ff < 0 || ff >= F) continue;
+                    const float v = __ldg(a.feats + (n + (long long)(kt - 2) * F + (kf - 1)) * Cin + c);
+#pragma unroll
+                    for (int o = 0; o < C; ++o) acc[o] = fmaf(v, g_s[r][o], acc[o]);
+                }
+            }
+            if (pair0 == 0 && tid < C)
+                for (int r = 0; r < RB; ++r) accb += g_s[r][tid];
+        }
+        if (worker)
+#pragma unroll
+            for (int o = 0; o < C; ++o) atomic_add(a.g_w + ((size_t)o * Cin + c) * 9 + tap, acc[o]);
+        if (pair0 == 0 && tid < C) atomic_add(a.g_bias + tid, accb);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// back-end, backward.  Forward (zero history): spec[o=(s,ri)][t][f] = bias[o] + sum_{c,kt,kf} x[c][t-kt][f+1-kf] w[c][o][kt][kf],
+// wave[192 t' + r] += sum_k spec_k[t'] filt[k][r] over frames t' in {t, t-1} (iSTFT/OLA, first `stride` samples dropped).
+// ------------------------------------------------------------------------------------------------------------
+// g_spec[b][t][s][k] = sum_r filt[k][r] * g_wave[b][s][stride*t + r]   (samples past stride*T are the cropped look-ahead)
+__global__ void __launch_bounds__(320) istft_bwd_kernel(const sb_backend_bwd_args a) {
+    constexpr int TT = 8;
+    SB_DYN_SMEM(float, g_s);                        // [(TT-1)*stride + n_fft]
+    const int F2 = 2 * a.F, S = a.n_src, t0 = blockIdx.x * TT, bs = blockIdx.y, tid = threadIdx.x;
+    const int span = (TT - 1) * a.stride + a.n_fft, len = a.stride * a.T;
+    pdl_wait();
+    const float* gw = a.g_wave + (size_t)bs * len;
+    for (int i = tid; i < span; i += 320) {
+        const long long p = (long long)t0 * a.stride + i;
+        g_s[i] = p < len ? ldg1_stream(gw + p) : 0.f;
+    }
+    __syncthreads();
+    const int b = bs / S, s = bs - b * S;
+    for (int k = tid; k < F2; k += 320) {
+        float acc[TT];
+#pragma unroll
+        for (int j = 0; j < TT; ++j) acc[j] = 0.f;
+        const float* fr = a.filt + (size_t)k * a.n_fft;
+        for (int r = 0; r < a.n_fft; ++r) {
+            const float w = __ldg(fr + r);
+#pragma unroll
+            for (int j = 0; j < TT; ++j) acc[j] = fmaf(w, g_s[j * a.stride + r], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < TT; ++j) {
+            const int t = t0 + j;
+            if (t >= a.T) break;
+            const size_t idx = (((size_t)b * a.T + t) * S + s) * F2 + k;
+            a.ws[idx] = a.mask_spec ? acc[j] * __ldg(a.mask_spec + idx) : acc[j];
+        }
+    }
+}
+
+// dL/dx[b][t][f][c] = sum_{o,kt,kf} g_spec_o[t+kt][f-1+kf] * w[c][o][kt][kf]; one thread per (position, channel)
+template <int C>
+__global__ void __launch_bounds__(256) deconv_bwd_x_kernel(const sb_backend_bwd_args a) {
+    __shared__ float w_s[4 * 9 * C];                // [o][tap][c]
+    const int O = 2 * a.n_src, F = a.F, T = a.T, tid = threadIdx.x;
+    for (int i = tid; i < O * 9 * C; i += 256) {
+        const int c = i % C, tap = (i / C) % 9, o = i / (9 * C);
+        w_s[i] = __ldg(a.w + ((size_t)c * O + o) * 9 + tap);
+    }
+    pdl_wait();
+    __syncthreads();
+    const long long N = (long long)a.B * T * F;
+    const long long n = (long long)blockIdx.x * (256 / C) + tid / C;
+    if (n >= N) return;
+    const int c = tid % C, fq = (int)(n % F), t = (int)((n / F) % T);
+    const long long b = n / ((long long)F * T);
+    float acc = 0.f;
+    for (int o = 0; o < O; ++o) {
+        const int s = o >> 1, ri = o & 1;
+        for (int kt = 0; kt < 3; ++kt) {
+            if (t + kt >= T) break;
+            const float* gr = a.ws + (((size_t)b * T + t + kt) * a.n_src + s) * 2 * F + ri * F;
+            for (int kf = 0; kf < 3; ++kf) {
+                const int ff = fq - 1 + kf;
+                if (ff < 0 || ff >= F) continue;
+                acc = fmaf(__ldg(gr + ff), w_s[(o * 9 + kt * 3 + kf) * C + c], acc);
+            }
+        }
+    }
+    a.gx[n * C + c] = acc;
+}
+
+// dL/dw[c][o][kt][kf] += sum x[b][t-kt][f+1-kf][c] * g_spec_o[b][t][f];  dL/dbias[o] += sum g_spec_o.  Thread = (tap, c).
+template <int C>
+__global__ void __launch_bounds__(320) deconv_wgrad_kernel(const sb_backend_bwd_args a, long long rows_per_cta) {
+    const int O = 2 * a.n_src, F = a.F, T = a.T, tid = threadIdx.x;
+    if (tid >= 9 * C) return;
+    const int tap = tid / C, c = tid - tap * C, kt = tap / 3, kf = tap - kt * 3;
+    const long long N = (long long)a.B * T * F;
+    const long long n_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long n_end = n_begin + rows_per_cta < N ? n_begin + rows_per_cta : N;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+    pdl_wait();
+    for (long long n = n_begin; n < n_end; ++n) {
+        const int fq = (int)(n % F), t = (int)((n / F) % T), ff = fq + 1 - kf;
+        const long long b = n / ((long long)F * T);
+        const bool in = t - kt >= 0 && ff >= 0 && ff < F;
+        const float v = in ? __ldg(a.x + (n + (long long)(-kt) * F + (1 - kf)) * C + c) : 0.f;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (o < O) {
+                const float g = __ldg(a.ws + (((size_t)b * T + t) * a.n_src + (o >> 1)) * 2 * F + (o & 1) * F + fq);
+                acc[o] = fmaf(v, g, acc[o]);
+                accb[o] += g;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        if (o < O) {
+            atomic_add(a.g_w + ((size_t)c * O + o) * 9 + tap, acc[o]);
+            if (tid == 0) atomic_add(a.g_bias + o, accb[o]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct PathDims {
+    long long N, R;
+    int S, nd;
+    RowMap map;
+};
+static PathDims path_dims(const sb_path_train_args& a) {
+    PathDims d;
+    d.nd = a.inter ? 1 : 2;
+    d.S = a.inter ? a.T : a.F;
+    d.R = a.inter ? (long long)a.B * a.F : (long long)a.B * a.T;
+    d.N = d.R * d.S;
+    d.map = RowMap{d.S, a.F, a.inter};
+    return d;
+}
+struct SavedView {
+    float *xhat, *xn, *rstd, *gates[2], *c[2], *h[2];
+};
+static SavedView saved_view(const sb_path_train_args& a, const PathDims& d) {
+    SavedView v{};
+    float* p = a.saved;
+    v.xhat = p; p += d.N * a.C;
+    v.xn = p; p += d.N * a.C;
+    v.rstd = p; p += (d.N + 3) / 4 * 4;
+    for (int k = 0; k < d.nd; ++k) {
+        v.gates[k] = p; p += d.N * 4 * a.H;
+        v.c[k] = p; p += d.N * a.H;
+        v.h[k] = p; p += d.N * a.H;
+    }
+    return v;
+}
+
+static int check_path(const sb_path_train_args* p, int inter, const char* who) {
+    SB_REQUIRE(p && p->x && p->ln_g && p->ln_b && p->lin_w && p->lin_b && p->saved, SB_E_BADARG, "%s: null pointer", who);
+    SB_REQUIRE(p->inter == inter, SB_E_BADARG, "%s: args.inter must be %d", who, inter);
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0, SB_E_BADARG, "%s: bad sizes", who);
+    SB_REQUIRE(p->C == 16 || p->C == 32, SB_E_UNSUPP, "%s: C must be 16 or 32 (got %d)", who, p->C);
+    SB_REQUIRE(p->H == kH, SB_E_UNSUPP, "%s: H must be 64 (got %d)", who, p->H);
+    for (int d = 0; d < (inter ? 1 : 2); ++d)
+        SB_REQUIRE(p->w_ih[d] && p->w_hh[d] && p->b_ih[d] && p->b_hh[d], SB_E_BADARG, "%s: null LSTM parameter", who);
+    return 0;
+}
+
+template <int P>
+static int run_rowgemm(const RowGemm& g, cudaStream_t st, const char* name) {
+    constexpr int ROWS = 256 / (P / 8);
+    const size_t smem = (size_t)g.nA * g.K * P * sizeof(float);
+    return launch(name, rowgemm_kernel<P>, dim3((unsigned)ceil_div_ll(g.N, ROWS)), dim3(256), smem, st, g);
+}
+static int rowgemm(const RowGemm& g, int P, cudaStream_t st, const char* name) {
+    switch (P) {
+        case 16: return run_rowgemm<16>(g, st, name);
+        case 32: return run_rowgemm<32>(g, st, name);
+        case 64: return run_rowgemm<64>(g, st, name);
+    }
+    set_error("%s: unsupported width %d", name, P);
+    return SB_E_UNSUPP;
+}
+
+static long long reduction_rows(long long N, int rb) {
+    const long long ctas = 2LL * sm_count();
+    long long rows = ceil_div_ll(N, ctas);
+    rows = ceil_div_ll(rows, rb) * rb;
+    return rows < rb ? rb : rows;
+}
+template <int J, int KC, int TJ, int TK>
+static int run_outer(Outer o, cudaStream_t st, const char* name) {
+    o.rows_per_cta = reduction_rows(o.N, 16);
+    return launch(name, outer_kernel<J, KC, TJ, TK>, dim3((unsigned)ceil_div_ll(o.N, o.rows_per_cta)), dim3(256), 0, st, o);
+}
+
+static int path_train_fwd(const sb_path_train_args& a, cudaStream_t st) {
+    const PathDims d = path_dims(a);
+    const SavedView v = saved_view(a, d);
+    const unsigned gN = (unsigned)ceil_div_ll(d.N, 256);
+    if (a.C == 32) SB_CHECK(launch("ln_fwd", ln_fwd_kernel<32>, dim3(gN), dim3(256), 0, st, a.x, d.map, a.ln_g, a.ln_b, v.xhat, v.xn, v.rstd, d.N, 1e-5f));
+    else SB_CHECK(launch("ln_fwd", ln_fwd_kernel<16>, dim3(gN), dim3(256), 0, st, a.x, d.map, a.ln_g, a.ln_b, v.xhat, v.xn, v.rstd, d.N, 1e-5f));
+    LstmTrain l{};
+    l.xn = v.xn;
+    for (int k = 0; k < d.nd; ++k) {
+        l.w_ih[k] = a.w_ih[k]; l.w_hh[k] = a.w_hh[k]; l.b_ih[k] = a.b_ih[k]; l.b_hh[k] = a.b_hh[k];
+        l.gates[k] = v.gates[k]; l.c[k] = v.c[k]; l.h[k] = v.h[k];
+    }
+    l.R = (int)d.R; l.S = d.S;
+    const dim3 grid((unsigned)ceil_div_ll(d.R, 4), d.nd);
+    if (a.C == 32) SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd_kernel<32>, grid, dim3(256), 0, st, l));
+    else SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd_kernel<16>, grid, dim3(256), 0, st, l));
+    RowGemm g{};
+    g.nA = d.nd; g.K = a.H; g.lda = a.H; g.ldw = d.nd * a.H; g.w_trans = 1;
+    for (int k = 0; k < d.nd; ++k) { g.A[k] = v.h[k]; g.W[k] = a.lin_w + k * a.H; }
+    g.bias = a.lin_b; g.res = a.x; g.out = a.y; g.map = d.map; g.a_mapped = 0; g.o_mapped = 1; g.N = d.N;
+    return rowgemm(g, a.C, st, "path_linear");
+}
+
+static int path_bwd(const sb_path_bwd_args& b, cudaStream_t st) {
+    const sb_path_train_args& a = b.f;
+    const PathDims d = path_dims(a);
+    const SavedView v = saved_view(a, d);
+    float* dh[2] = {b.ws, b.ws + d.N * a.H};
+    float* dxn = b.ws + (long long)d.nd * d.N * a.H;
+    // (1) projection: dL/dh per direction, dL/dlin_w, dL/dlin_b
+    for (int k = 0; k < d.nd; ++k) {
+        RowGemm g{};
+        g.nA = 1; g.K = a.C; g.lda = a.C; g.ldw = d.nd * a.H; g.w_trans = 0;
+        g.A[0] = b.gy; g.W[0] = a.lin_w + k * a.H;
+        g.out = dh[k]; g.map = d.map; g.a_mapped = 1; g.o_mapped = 0; g.N = d.N;
+        SB_CHECK(rowgemm(g, a.H, st, "path_linear_bwd"));
+        Outer o{};
+        o.A = b.gy; o.Bm = v.h[k]; o.dW = b.g_lin_w + k * a.H; o.ldw = d.nd * a.H;
+        o.db = k == 0 ? b.g_lin_b : nullptr; o.db2 = nullptr;
+        o.map = d.map; o.a_mapped = 1; o.b_mode = 0; o.reverse = 0; o.N = d.N;
+        if (a.C == 32) SB_CHECK((run_outer<32, 64, 4, 2>(o, st, "path_linear_wgrad")));
+        else SB_CHECK((run_outer<16, 64, 2, 2>(o, st, "path_linear_wgrad")));
+    }
+    // (2) BPTT: gates -> dz in place
+    LstmTrain l{};
+    for (int k = 0; k < d.nd; ++k) { l.w_hh[k] = a.w_hh[k]; l.gates[k] = v.gates[k]; l.c[k] = v.c[k]; l.dh[k] = dh[k]; }
+    l.R = (int)d.R; l.S = d.S;
+    SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd_kernel, dim3((unsigned)ceil_div_ll(d.R, 4), d.nd), dim3(256), 0, st, l));
+    // (3) weight gradients: dW_ih = dz^T LN(x), dW_hh = dz^T h_prev, db = sum dz
+    for (int k = 0; k < d.nd; ++k) {
+        Outer o{};
+        o.A = v.gates[k]; o.map = d.map; o.a_mapped = 0; o.reverse = k; o.N = d.N;
+        o.Bm = v.xn; o.b_mode = 0; o.dW = b.g_w_ih[k]; o.ldw = a.C; o.db = b.g_b_ih[k]; o.db2 = b.g_b_hh[k];
+        if (a.C == 32) SB_CHECK((run_outer<256, 32, 8, 4>(o, st, "lstm_wgrad_ih")));
+        else SB_CHECK((run_outer<256, 16, 8, 2>(o, st, "lstm_wgrad_ih")));
+        o.Bm = v.h[k]; o.b_mode = 2; o.dW = b.g_w_hh[k]; o.ldw = a.H; o.db = nullptr; o.db2 = nullptr;
+        SB_CHECK((run_outer<256, 64, 8, 8>(o, st, "lstm_wgrad_hh")));
+    }
+    // (4) dL/dLN(x) = sum_dir dz W_ih, then LayerNorm backward + the residual branch
+    RowGemm g{};
+    g.nA = d.nd; g.K = 4 * a.H; g.lda = 4 * a.H; g.ldw = a.C; g.w_trans = 0;
+    for (int k = 0; k < d.nd; ++k) { g.A[k] = v.gates[k]; g.W[k] = a.w_ih[k]; }
+    g.out = dxn; g.map = d.map; g.a_mapped = 0; g.o_mapped = 0; g.N = d.N;
+    SB_CHECK(rowgemm(g, a.C, st, "lstm_dx"));
+    const unsigned grid = (unsigned)(ceil_div_ll(d.N, 256) < 2LL * sm_count() ? ceil_div_ll(d.N, 256) : 2LL * sm_count());
+    if (a.C == 32) return launch("ln_bwd", ln_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, (const float*)dxn, (const float*)v.xhat, (const float*)v.rstd, a.ln_g, b.gy, b.gx, d.map, b.g_ln_g, b.g_ln_b, d.N);
+    return launch("ln_bwd", ln_bwd_kernel<16>, dim3(grid), dim3(256), 0, st, (const float*)dxn, (const float*)v.xhat, (const float*)v.rstd, a.ln_g, b.gy, b.gx, d.map, b.g_ln_g, b.g_ln_b, d.N);
+}
+
+static int check_path_bwd(const sb_path_bwd_args* p, int inter, const char* who) {
+    SB_REQUIRE(p, SB_E_BADARG, "%s: null pointer", who);
+    SB_CHECK(check_path(&p->f, inter, who));
+    SB_REQUIRE(p->gy && p->gx && p->g_ln_g && p->g_ln_b && p->g_lin_w && p->g_lin_b && p->ws, SB_E_BADARG, "%s: null pointer", who);
+    for (int d = 0; d < (inter ? 1 : 2); ++d)
+        SB_REQUIRE(p->g_w_ih[d] && p->g_w_hh[d] && p->g_b_ih[d] && p->g_b_hh[d], SB_E_BADARG, "%s: null gradient buffer", who);
+    return 0;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" size_t sb_path_train_saved_floats(int B, int T, int F, int C, int H, int inter) {
+    const long long N = (long long)B * T * F;
+    const int nd = inter ? 1 : 2;
+    return (size_t)(2 * N * C + (N + 3) / 4 * 4 + nd * N * 6 * H);
+}
+extern "C" size_t sb_path_bwd_workspace_floats(int B, int T, int F, int C, int H, int inter) {
+    const long long N = (long long)B * T * F;
+    return (size_t)((inter ? 1 : 2) * N * H + N * C);
+}
+extern "C" int sb_intra_lstm_train_fwd(const sb_path_train_args* p, void* stream) {
+    SB_CHECK(check_path(p, 0, "sb_intra_lstm_train_fwd"));
+    SB_REQUIRE(p->y && p->y != p->x, SB_E_BADARG, "sb_intra_lstm_train_fwd: y must be a separate buffer");
+    return path_train_fwd(*p, (cudaStream_t)stream);
+}
+extern "C" int sb_inter_lstm_train_fwd(const sb_path_train_args* p, void* stream) {
+    SB_CHECK(check_path(p, 1, "sb_inter_lstm_train_fwd"));
+    SB_REQUIRE(p->y && p->y != p->x, SB_E_BADARG, "sb_inter_lstm_train_fwd: y must be a separate buffer");
+    return path_train_fwd(*p, (cudaStream_t)stream);
+}
+extern "C" int sb_intra_lstm_bwd(const sb_path_bwd_args* p, void* stream) {
+    SB_CHECK(check_path_bwd(p, 0, "sb_intra_lstm_bwd"));
+    return path_bwd(*p, (cudaStream_t)stream);
+}
+extern "C" int sb_inter_lstm_bwd(const sb_path_bwd_args* p, void* stream) {
+    SB_CHECK(check_path_bwd(p, 1, "sb_inter_lstm_bwd"));
+    return path_bwd(*p, (cudaStream_t)stream);
+}
+
+static int check_film_apply(const sb_film_apply_args* p, const char* who) {
+    SB_REQUIRE(p && p->x && p->film_scale && p->film_shift, SB_E_BADARG, "%s: null pointer", who);
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0 && p->C > 0 && p->C % 4 == 0, SB_E_BADARG, "%s: bad sizes", who);
+    return 0;
+}
+extern "C" int sb_film_apply_fwd(const sb_film_apply_args* p, void* stream) {
+    SB_CHECK(check_film_apply(p, "sb_film_apply_fwd"));
+    SB_REQUIRE(p->y, SB_E_BADARG, "sb_film_apply_fwd: null output");
+    const long long n4 = (long long)p->B * p->T * p->F * p->C / 4;
+    const long long blocks = ceil_div_ll(n4, 256);
+    const unsigned grid = (unsigned)(blocks < 8LL * sm_count() ? blocks : 8LL * sm_count());
+    return launch("film_apply_fwd", film_apply_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, *p);
+}
+extern "C" int sb_film_apply_bwd(const sb_film_apply_args* p, void* stream) {
+    SB_CHECK(check_film_apply(p, "sb_film_apply_bwd"));
+    SB_REQUIRE(p->gy && p->gx && p->g_scale && p->g_shift, SB_E_BADARG, "sb_film_apply_bwd: null pointer");
+    const long long total = (long long)p->B * p->F * p->C;
+    return launch("film_apply_bwd", film_apply_bwd_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, (cudaStream_t)stream, *p);
+}
+
+extern "C" int sb_film_params_bwd(const sb_film_bwd_args* p, void* stream) {
+    SB_REQUIRE(p && p->g_film && p->f.dis && p->f.emb_w && p->f.emb_ln_g && p->f.emb_ln_b && p->f.w_w && p->f.b_w, SB_E_BADARG,
+               "sb_film_params_bwd: null pointer");
+    SB_REQUIRE(p->g_emb_w && p->g_emb_ln_g && p->g_emb_ln_b && p->g_w_w && p->g_w_b && p->g_b_w && p->g_b_b, SB_E_BADARG,
+               "sb_film_params_bwd: null gradient buffer");
+    SB_REQUIRE(p->f.emb_mode == SB_EMB_CONV, SB_E_UNSUPP, "sb_film_params_bwd: only Dis_Embed_Conv (dis_type conv*) has a backward kernel");
+    SB_REQUIRE(p->f.B > 0 && p->f.F > 0 && p->f.C > 0 && p->f.Din > 0 && p->f.n_layers > 0, SB_E_BADARG, "sb_film_params_bwd: bad sizes");
+    const size_t smem = ((size_t)3 * p->f.F * p->f.Din + p->f.F) * sizeof(float);
+    return launch("film_params_bwd", film_params_bwd_kernel, dim3(p->f.B), dim3(256), smem, (cudaStream_t)stream, *p);
+}
+
+static int check_conv_in_train(const sb_conv_in_train_args* p, const char* who) {
+    SB_REQUIRE(p && p->feats && p->w && p->bias, SB_E_BADARG, "%s: null pointer", who);
+    SB_REQUIRE((p->ln_g == nullptr) == (p->ln_b == nullptr), SB_E_BADARG, "%s: LayerNorm gain and bias must come together", who);
+    SB_REQUIRE(!p->ln_g || p->saved, SB_E_BADARG, "%s: saved buffer missing", who);
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0 && p->Cin > 0, SB_E_BADARG, "%s: bad sizes", who);
+    SB_REQUIRE(p->C == 16 || p->C == 32, SB_E_UNSUPP, "%s: C must be 16 or 32 (got %d)", who, p->C);
+    return 0;
+}
+extern "C" int sb_conv_in_train_fwd(const sb_conv_in_train_args* p, void* stream) {
+    SB_CHECK(check_conv_in_train(p, "sb_conv_in_train_fwd"));
+    SB_REQUIRE(p->x, SB_E_BADARG, "sb_conv_in_train_fwd: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = (long long)p->B * p->T * p->F;
+    const int C = p->C;
+    // with the LayerNorm the raw conv output goes to the head of `saved` and ln_fwd writes x from it
+    float* raw = p->ln_g ? p->saved : p->x;
+    const size_t smem = (size_t)9 * p->Cin * C * sizeof(float);
+    const unsigned grid = (unsigned)ceil_div_ll(N, 256 / (C / 8));
+    if (C == 32) SB_CHECK(launch("conv_in_train", conv_in_train_kernel<32>, dim3(grid), dim3(256), smem, st, *p, raw));
+    else SB_CHECK(launch("conv_in_train", conv_in_train_kernel<16>, dim3(grid), dim3(256), smem, st, *p, raw));
+    if (!p->ln_g) return 0;
+    float* xhat = p->saved + N * C;
+    float* rstd = p->saved + 2 * N * C;
+    const RowMap map{1, p->F, 0};
+    const unsigned gN = (unsigned)ceil_div_ll(N, 256);
+    if (C == 32) return launch("ln_fwd", ln_fwd_kernel<32>, dim3(gN), dim3(256), 0, st, (const float*)raw, map, p->ln_g, p->ln_b, xhat, p->x, rstd, N, 1e-5f);
+    return launch("ln_fwd", ln_fwd_kernel<16>, dim3(gN), dim3(256), 0, st, (const float*)raw, map, p->ln_g, p->ln_b, xhat, p->x, rstd, N, 1e-5f);
+}
+extern "C" int sb_conv_in_bwd(const sb_conv_in_train_args* p, void* stream) {
+    SB_CHECK(check_conv_in_train(p, "sb_conv_in_bwd"));
+    SB_REQUIRE(p->gx && p->g_w && p->g_bias && p->ws, SB_E_BADARG, "sb_conv_in_bwd: null pointer");
+    SB_REQUIRE(!p->ln_g || (p->g_ln_g && p->g_ln_b), SB_E_BADARG, "sb_conv_in_bwd: null LayerNorm gradient buffer");
+    SB_REQUIRE(9 * p->Cin <= 512, SB_E_UNSUPP, "sb_conv_in_bwd: too many input channels (%d)", p->Cin);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long N = (long long)p->B * p->T * p->F;
+    const int C = p->C;
+    const float* g = p->gx;
+    if (p->ln_g) {
+        const RowMap map{1, p->F, 0};
+        const unsigned grid = (unsigned)(ceil_div_ll(N, 256) < 2LL * sm_count() ? ceil_div_ll(N, 256) : 2LL * sm_count());
+        const float* xhat = p->saved + N * C;
+        const float* rstd = p->saved + 2 * N * C;
+        if (C == 32) SB_CHECK(launch("ln_bwd", ln_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, p->gx, xhat, rstd, p->ln_g, (const float*)nullptr, p->ws, map, p->g_ln_g, p->g_ln_b, N));
+        else SB_CHECK(launch("ln_bwd", ln_bwd_kernel<16>, dim3(grid), dim3(256), 0, st, p->gx, xhat, rstd, p->ln_g, (const float*)nullptr, p->ws, map, p->g_ln_g, p->g_ln_b, N));
+        g = p->ws;
+    }
+    const long long rows = reduction_rows(N, 32);
+    const unsigned grid = (unsigned)ceil_div_ll(N, rows);
+    if (C == 32) return launch("conv_in_wgrad", conv_in_wgrad_kernel<32>, dim3(grid), dim3(256), 0, st, *p, g, rows);
+    return launch("conv_in_wgrad", conv_in_wgrad_kernel<16>, dim3(grid), dim3(256), 0, st, *p, g, rows);
+}
+
+extern "C" int sb_backend_bwd(const sb_backend_bwd_args* p, void* stream) {
+    SB_REQUIRE(p && p->x && p->g_wave && p->w && p->filt && p->gx && p->g_w && p->g_bias && p->ws, SB_E_BADARG, "sb_backend_bwd: null pointer");
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0 && p->n_fft > 0 && p->stride > 0 && p->n_fft >= p->stride, SB_E_BADARG, "sb_backend_bwd: bad sizes");
+    SB_REQUIRE(p->C == 16 || p->C == 32, SB_E_UNSUPP, "sb_backend_bwd: C must be 16 or 32 (got %d)", p->C);
+    SB_REQUIRE(p->n_src == 1 || p->n_src == 2, SB_E_UNSUPP, "sb_backend_bwd: 1 or 2 sources (got %d)", p->n_src);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = ((size_t)7 * p->stride + p->n_fft) * sizeof(float);
+    SB_CHECK(launch("istft_bwd", istft_bwd_kernel, dim3(ceil_div(p->T, 8), p->B * p->n_src), dim3(320), smem, st, *p));
+    const long long N = (long long)p->B * p->T * p->F;
+    const long long rows = reduction_rows(N, 1);
+    if (p->C == 32) {
+        SB_CHECK(launch("deconv_bwd_x", deconv_bwd_x_kernel<32>, dim3((unsigned)ceil_div_ll(N, 8)), dim3(256), 0, st, *p));
+        return launch("deconv_wgrad", deconv_wgrad_kernel<32>, dim3((unsigned)ceil_div_ll(N, rows)), dim3(288), 0, st, *p, rows);
+    }
+    SB_CHECK(launch("deconv_bwd_x", deconv_bwd_x_kernel<16>, dim3((unsigned)ceil_div_ll(N, 16)), dim3(256), 0, st, *p));
+    return launch("deconv_wgrad", deconv_wgrad_kernel<16>, dim3((unsigned)ceil_div_ll(N, rows)), dim3(160), 0, st, *p, rows);
+}

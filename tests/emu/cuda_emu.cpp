@@ -6,6 +6,7 @@ dim3 blockDim, gridDim;
 
 namespace emu {
 Block* g_block = nullptr;
+std::mutex g_atomic_mu;
 thread_local unsigned t_lane = 0, t_warp = 0;
 
 // Runs the grid one block at a time on a pool of `blockDim` OS threads.  Kernels of this library never let a thread

@@ -127,6 +127,8 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int d, int widt
 }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+namespace emu { extern std::mutex g_atomic_mu; }
+static inline void emu_atomic_add(float* p, float v) { std::lock_guard<std::mutex> lock(emu::g_atomic_mu); *p += v; }
 #define __expf(x) expf(x)
 static inline float __frcp_rn(float x) { return 1.0f / x; }
 static inline float __fdividef(float a, float b) { return a / b; }

@@ -1,0 +1,127 @@
+"""Gradient parity checks of the training entry points (sb_*_train_fwd / sb_*_bwd) against autograd through the CPU
+oracle's restatement of the same reference spans.  TEST INFRASTRUCTURE (see kernel_cases.py): every function takes a
+bound CDLL and a device; the GPU tests pass the sm_100a library, the emu tests the host-emulated test build.
+
+Errors are reported relative to the largest entry of the reference tensor (gradients span several orders of magnitude).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from oracle import tfgridnet_oracle as orc
+from oracle.weights import make_state_dict, synthetic_mixture
+from sound_bubble_b200 import _abi as abi
+from sound_bubble_b200.packing import ModelConfig
+from sound_bubble_b200.training import TrainGraph, differentiable_forward
+
+from kernel_cases import _stream, _sync
+
+
+def relerr(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _model(variant, kwargs, seed=0):
+    ocfg = orc.OracleConfig.from_kwargs(variant, **kwargs)
+    sd = make_state_dict(ocfg, seed)
+    cfg = ModelConfig(variant=variant, **kwargs)
+    return ocfg, sd, cfg
+
+
+def _leaf_sd(sd):
+    out = {}
+    for k, v in sd.items():
+        t = v.clone().float()
+        if "_filters" not in k:
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+def check_path(lib, device, variant, kwargs, inter, B=1, T=2, block=1, seed=7):
+    """One recurrent path (a9 / a10): forward value, dL/dx and every parameter gradient for L = sum(y * R)."""
+    ocfg, sd, cfg = _model(variant, kwargs)
+    lsd = _leaf_sd(sd)
+    g = torch.Generator().manual_seed(seed)
+    Fq, C, H = cfg.n_freqs, cfg.D, cfg.H
+    x = torch.randn(B, T, Fq, C, generator=g).requires_grad_(True)
+    R = torch.randn(B, T, Fq, C, generator=g)
+    if inter:
+        ref, _, _ = orc.inter_path(lsd, ocfg, block, x, torch.zeros(1, B * Fq, H), torch.zeros(1, B * Fq, H))
+    else:
+        ref = orc.intra_path(lsd, ocfg, block, x)
+    (ref * R).sum().backward()
+
+    P = {k: v.detach().to(device).contiguous() for k, v in sd.items()}
+    tg = TrainGraph(lib, cfg)
+    xd, Rd = x.detach().to(device), R.to(device)
+    y = torch.full_like(xd, float("nan"))
+    saved = torch.empty(int(lib.sb_path_train_saved_floats(B, T, Fq, C, H, int(inter))), device=device)
+    pa = tg._path_args(P, block, inter, B, T)
+    pa.x, pa.y, pa.saved = xd.data_ptr(), y.data_ptr(), saved.data_ptr()
+    fwd = lib.sb_inter_lstm_train_fwd if inter else lib.sb_intra_lstm_train_fwd
+    abi.check(lib, fwd(ctypes.byref(pa), _stream(device)), "path train fwd")
+    _sync(device)
+    errs = {"y": relerr(y, ref)}
+
+    kind = "inter" if inter else "intra"
+    b = f"tfgridnet.blocks.{block}."
+    names = [b + kind + "_norm.norm.weight", b + kind + "_norm.norm.bias", b + kind + "_linear.weight", b + kind + "_linear.bias"]
+    sfxs = ("",) if inter else ("", "_reverse")
+    for sfx in sfxs:
+        names += [b + kind + "_rnn." + n + sfx for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")]
+    G = {n: torch.zeros_like(P[n]) for n in names}
+    pb = abi.PathBwdArgs()
+    pb.f = pa
+    gx = torch.full_like(xd, float("nan"))
+    ws = torch.empty(int(lib.sb_path_bwd_workspace_floats(B, T, Fq, C, H, int(inter))), device=device)
+    pb.gy, pb.gx, pb.ws = Rd.data_ptr(), gx.data_ptr(), ws.data_ptr()
+    pb.g_ln_g, pb.g_ln_b, pb.g_lin_w, pb.g_lin_b = (G[n].data_ptr() for n in names[:4])
+    for d, sfx in enumerate(sfxs):
+        r = b + kind + "_rnn."
+        pb.g_w_ih[d], pb.g_w_hh[d] = G[r + "weight_ih_l0" + sfx].data_ptr(), G[r + "weight_hh_l0" + sfx].data_ptr()
+        pb.g_b_ih[d], pb.g_b_hh[d] = G[r + "bias_ih_l0" + sfx].data_ptr(), G[r + "bias_hh_l0" + sfx].data_ptr()
+    bwd = lib.sb_inter_lstm_bwd if inter else lib.sb_intra_lstm_bwd
+    abi.check(lib, bwd(ctypes.byref(pb), _stream(device)), "path bwd")
+    _sync(device)
+    errs["gx"] = relerr(gx, x.grad)
+    for n in names:
+        errs[n.split("blocks.%d." % block)[1]] = relerr(G[n], lsd[n].grad)
+    return errs
+
+
+def oracle_gradients(variant, kwargs, wave, dis, R, seed=0):
+    """autograd through the oracle's whole path: L = sum(output * R) -> (output, {name: grad})."""
+    ocfg, sd, cfg = _model(variant, kwargs, seed)
+    lsd = _leaf_sd(sd)
+    out, _ = orc.core_forward(lsd, ocfg, wave, dis, orc.init_state(ocfg, wave.shape[0]))
+    (out * R).sum().backward()
+    return out.detach(), {k: v.grad for k, v in lsd.items() if v.requires_grad}
+
+
+def check_net(lib, device, variant, kwargs, B=1, T=3, seed=11, golden=None):
+    """The whole differentiable forward (SeparatorFunction) against the oracle: output and every parameter gradient."""
+    ocfg, sd, cfg = _model(variant, kwargs)
+    n = cfg.stft_chunk_size * T + cfg.n_fft - cfg.stft_chunk_size
+    wave = synthetic_mixture(B, cfg.num_ch, n, seed=seed)
+    dis = torch.tensor([[0., 0., 1.], [0., 1., 0.], [1., 0., 0.]])[torch.arange(B) % 3] if variant == "dis_embed" else None
+    R = torch.randn(B, cfg.num_src, cfg.stft_chunk_size * T, generator=torch.Generator().manual_seed(seed + 1))
+    ref_out, ref_g = oracle_gradients(variant, kwargs, wave, dis, R) if golden is None else golden
+
+    named = {}
+    for k, v in sd.items():
+        t = v.detach().clone().float().to(device)
+        if "_filters" not in k:
+            t.requires_grad_(True)
+        named[k] = t
+    out = differentiable_forward(lib, cfg, named, wave.to(device), None if dis is None else dis.to(device))
+    (out * R.to(device)).sum().backward()
+    _sync(device)
+    errs = {"output": relerr(out, ref_out)}
+    for k, g in ref_g.items():
+        assert named[k].grad is not None, k
+        errs[k.replace("tfgridnet.", "")] = relerr(named[k].grad, g)
+    return errs
