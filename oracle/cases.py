@@ -46,3 +46,11 @@ CASES = {
     "wav_syn_1m": dict(variant="dis_embed", kwargs=SYN, wav="test_samples/syn_1m/00002/mixture.wav",
                        n_samples=12000, radius=[0.0, 0.0, 1.0]),
 }
+
+# gradient fixtures (oracle/make_golden_grads.py): the reference module in train() mode, L = sum(output * R)
+GRAD_CASES = {
+    # TFG_S architecture with 2 blocks (FiLM + distance embedding, first LayerNorm, mod-pad path of Net.forward)
+    "grad_syn_b2": dict(variant="dis_embed", kwargs=_with(SYN, B=2), batch=2, n_samples=192 * 4 - 30, loss_seed=77),
+    # the OPT variant (no distance embedding) at D = 16 with plain BiLSTM blocks
+    "grad_opi_d16": dict(variant="optim", kwargs=_with(OPI, B=1, D=16), batch=1, n_samples=192 * 3, loss_seed=78),
+}

@@ -84,6 +84,36 @@ class NetBase(nn.Module):
             y = y[:, :, :-mod]
         return y, next_state
 
+    # -- training (autograd) ------------------------------------------------------------------------------------
+    def _wants_grad(self, input_state) -> bool:
+        """The differentiable path is taken exactly where the reference trains: module in train() mode, autograd on, no
+        carried state (PLModule._step calls self.model(inputs), hl_module.py:309), for the configurations that have
+        backward kernels.  Everything else runs the inference kernels under no_grad, so a backward() on their output
+        fails loudly instead of training nothing."""
+        if not (self.training and torch.is_grad_enabled() and input_state is None):
+            return False
+        from .training import check_trainable
+        try:
+            check_trainable(self.cfg)
+        except NotImplementedError:
+            return False
+        return any(p.requires_grad for p in self.parameters())
+
+    def _train_forward(self, x, dis_embed, pad=True):
+        """Net.forward for a training step: same padding / cropping as _predict, gradients to every parameter through
+        SeparatorFunction (training.py).  'next_state' is None: a training call starts from and discards zero state."""
+        from .training import differentiable_forward
+        _lib.require_cuda(x)
+        mod = 0
+        if pad:
+            pad_size = (self.stft_back_pad, self.stft_pad_size) if self.lookahead else (0, 0)
+            x, mod = mod_pad(x, chunk_size=self.stft_chunk_size, pad=pad_size)
+        named = dict(self.state_dict(keep_vars=True))
+        y = differentiable_forward(_lib.load(), self.cfg, named, x, dis_embed)
+        if mod != 0:
+            y = y[:, :, :-mod]
+        return {'output': y, 'next_state': None}
+
     def _forward_sliced(self, x, dis_embed, state):
         """The whole-utterance call as K time slices through the native pipe (None = not applicable, use the single
         call).  Updates `state` in place like Engine.forward does (the reference mutates the dict it was given)."""

@@ -29,6 +29,8 @@ class Net(NetBase):
     def forward(self, inputs, input_state=None, pad=True):
         x = inputs['mixture']
         dis_embed = inputs['dis_embed']
+        if self._wants_grad(input_state):
+            return self._train_forward(x, dis_embed, pad)
         if input_state is None:
             input_state = self.init_buffers(x.shape[0], x.device)
         x, next_state = self.predict(x, dis_embed, input_state, pad)

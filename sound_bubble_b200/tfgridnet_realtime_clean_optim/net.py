@@ -28,6 +28,8 @@ class Net(NetBase):
 
     def forward(self, inputs, input_state=None, pad=True):
         x = inputs['mixture']
+        if self._wants_grad(input_state):
+            return self._train_forward(x, None, pad)
         if input_state is None:
             input_state = self.init_buffers(x.shape[0], x.device)
         x, next_state = self.predict(x, input_state, pad)

@@ -1,0 +1,118 @@
+"""Training path on a B200 (run with `-m gpu`): gradients of the hand-written backward kernels, through the C ABI and
+through the drop-in ``Net`` module in train() mode, against the gradients of the UNMODIFIED reference (fixtures) and
+against autograd through the oracle; size-independent properties at larger sizes."""
+import pytest
+import torch
+
+import train_cases as tc
+from oracle.cases import GRAD_CASES, OPI, SYN
+from oracle.weights import make_state_dict, radius_one_hot, synthetic_mixture
+from oracle import tfgridnet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRAD_TOL = 1e-4          # relative to the largest entry of each gradient tensor (fp32 both sides; atomics reorder the sums,
+                         # sigmoid / tanh are ex2.approx + rcp.approx on the device)
+C16 = dict(OPI, D=16)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sound_bubble_b200 import _lib
+    return _lib.load()
+
+
+def _ok(errs, tol=GRAD_TOL):
+    assert all(v <= tol for v in errs.values()), {k: v for k, v in errs.items() if v > tol}
+
+
+@pytest.mark.parametrize("inter", [False, True])
+@pytest.mark.parametrize("variant,kw,B,T", [("dis_embed", SYN, 2, 5), ("optim", C16, 1, 3), ("dis_embed", SYN, 1, 31)])
+def test_recurrent_path_gradients(lib, inter, variant, kw, B, T):
+    _ok(tc.check_path(lib, DEV, variant, kw, inter, B=B, T=T))
+
+
+@pytest.mark.parametrize("name", sorted(GRAD_CASES))
+def test_module_gradients_match_the_reference(lib, name):
+    _ok(tc.check_golden_grads(lib, DEV, name))
+
+
+def test_tfg_s_gradients_against_oracle_autograd(lib):
+    """the benchmark architecture (6 blocks, FiLM on 5 of them), every parameter"""
+    _ok(tc.check_net(lib, DEV, "dis_embed", SYN, B=3, T=6))
+
+
+def test_variants_against_oracle_autograd(lib):
+    _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=1, num_src=2, spectral_masking=True), B=2, T=4))
+    _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=2, merge_method="None", use_first_ln=False), B=1, T=9))
+    _ok(tc.check_net(lib, DEV, "optim", dict(OPI, B=2), B=2, T=5))
+
+
+def _net(kw=SYN, seed=0):
+    from sound_bubble_b200 import Net
+    net = Net(**kw)
+    net.load_state_dict(make_state_dict(orc.OracleConfig.from_kwargs("dis_embed", **kw), seed), strict=True)
+    return net.to(DEV)
+
+
+def _grads(net, mix, dis, R):
+    net.zero_grad(set_to_none=True)
+    out = net({"mixture": mix, "dis_embed": dis})["output"]
+    (out * R).sum().backward()
+    return out.detach(), {k: p.grad.clone() for k, p in net.named_parameters()}
+
+
+def test_gradients_add_over_utterances_at_one_second_clips():
+    """size-independent property: for a sum loss, grad(batch of 4) = grad(first 2) + grad(last 2); 1 s clips (125 frames)"""
+    net = _net().train()
+    mix = synthetic_mixture(4, 6, 24000, seed=5).to(DEV)
+    dis = radius_one_hot(4).to(DEV)
+    R = torch.randn(4, 1, 24000, generator=torch.Generator().manual_seed(6)).to(DEV)
+    out, g_all = _grads(net, mix, dis, R)
+    out_a, g_a = _grads(net, mix[:2], dis[:2], R[:2])
+    out_b, g_b = _grads(net, mix[2:], dis[2:], R[2:])
+    assert float((out[:2] - out_a).abs().max()) <= 1e-6 and float((out[2:] - out_b).abs().max()) <= 1e-6   # utterances never mix
+    for k in g_all:
+        assert tc.relerr(g_a[k] + g_b[k], g_all[k]) <= 1e-4, k
+    # and the inference kernels agree with the training forward
+    with torch.no_grad():
+        ref = net.eval()({"mixture": mix, "dis_embed": dis})["output"]
+    assert float((ref - out).abs().max()) <= 3e-4
+
+
+def test_mode_switches():
+    net = _net(dict(SYN, B=2))
+    mix, dis = synthetic_mixture(1, 6, 192 * 4, seed=1).to(DEV), radius_one_hot(1).to(DEV)
+    out = net.train()({"mixture": mix, "dis_embed": dis})
+    assert out["output"].requires_grad and out["next_state"] is None
+    out = net.eval()({"mixture": mix, "dis_embed": dis})
+    assert not out["output"].requires_grad and out["next_state"] is not None
+    with torch.no_grad():
+        assert not net.train()({"mixture": mix, "dis_embed": dis})["output"].requires_grad
+    st = net.init_buffers(1, DEV)                      # carried state: the inference kernels, no autograd graph
+    assert not net.train()({"mixture": mix, "dis_embed": dis}, st)["output"].requires_grad
+    from sound_bubble_b200 import Net
+    rpi = Net(**dict(SYN, B=1, conv_lstm=True)).to(DEV).train()      # no backward kernels: forward-only, backward fails loudly
+    y = rpi({"mixture": mix, "dis_embed": dis})["output"]
+    with pytest.raises(RuntimeError):
+        y.sum().backward()
+
+
+def test_a_few_optimizer_steps_reduce_the_loss():
+    """train_pt.py's inner loop in miniature: negative SNR loss, clip_grad_norm_(1), Adam (hl_module.py:321, 437-441)"""
+    net = _net(dict(SYN, B=2)).train()
+    mix = synthetic_mixture(2, 6, 192 * 20, seed=9).to(DEV)
+    dis = radius_one_hot(2).to(DEV)
+    target = mix[:, :1] * 0.5
+    opt = torch.optim.Adam(net.parameters(), lr=2e-3)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad(set_to_none=True)
+        est = net({"mixture": mix, "dis_embed": dis})["output"]
+        loss = -(10 * torch.log10(target.pow(2).sum(-1) / ((est - target).pow(2).sum(-1) + 1e-8))).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        losses.append(float(loss))
+    # the same loop through the oracle port on the CPU gives 16.543, 11.697, ..., 4.959
+    assert abs(losses[0] - 16.5427) <= 2e-3 and losses[-1] < 7.0, losses

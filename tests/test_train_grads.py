@@ -1,0 +1,65 @@
+"""Training path without a GPU: (1) autograd through the oracle is pinned to the gradients of the UNMODIFIED reference
+(tests/golden/grad_*.npz); (2) the backward kernels are checked on the host-emulated TEST build of the same .cu sources
+(tests/emu) against those fixtures and against oracle autograd.  The product library has no CPU path."""
+import pytest
+import torch
+
+import train_cases as tc
+from oracle import tfgridnet_oracle as orc
+from oracle.cases import GRAD_CASES, OPI, SYN
+
+GRAD_TOL = 2e-5          # relative to the largest entry of each gradient tensor
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from emu.emu_lib import load
+    return load()
+
+
+def _ok(errs, tol=GRAD_TOL):
+    assert all(v <= tol for v in errs.values()), {k: v for k, v in errs.items() if v > tol}
+
+
+@pytest.mark.parametrize("name", sorted(GRAD_CASES))
+def test_oracle_autograd_matches_reference_gradients(name):
+    meta, mix, dis, ref_out, ref_g = tc.load_grad_fixture(name)
+    ocfg, sd, cfg = tc._model(meta["variant"], meta["kwargs"], meta["seed"])
+    leaf = {k: (v.clone().requires_grad_(True) if k in ref_g else v) for k, v in sd.items()}
+    out = orc.net_forward(leaf, ocfg, {"mixture": mix, "dis_embed": dis})["output"]
+    (out * tc.loss_weights(out.shape, meta["loss_seed"])).sum().backward()
+    assert tc.relerr(out, ref_out) <= 2e-6
+    for k, g in ref_g.items():
+        assert tc.relerr(leaf[k].grad, g) <= GRAD_TOL, k
+
+
+def test_fixture_covers_every_parameter():
+    meta, _, _, _, ref_g = tc.load_grad_fixture("grad_syn_b2")
+    shapes = orc.param_shapes(orc.OracleConfig.from_kwargs(meta["variant"], **meta["kwargs"]))
+    assert set(ref_g) == {k for k in shapes if "_filters" not in k}
+
+
+@pytest.mark.parametrize("inter", [False, True])
+def test_recurrent_path_gradients(lib, inter):
+    _ok(tc.check_path(lib, "cpu", "dis_embed", SYN, inter, B=1, T=2))
+    _ok(tc.check_path(lib, "cpu", "optim", dict(OPI, D=16), inter, B=1, T=3))      # ragged last CTA (3 / 435 rows)
+
+
+def test_whole_path_gradients_against_the_reference_fixtures(lib):
+    _ok(tc.check_golden_grads(lib, "cpu", "grad_opi_d16"))
+    _ok(tc.check_golden_grads(lib, "cpu", "grad_syn_b2"))
+
+
+def test_variants_against_oracle_autograd(lib):
+    """two sources + spectral masking, and the plain front-end (no spatial features, no first LayerNorm)"""
+    _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, B=1, num_src=2, spectral_masking=True), B=1, T=2))
+    _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, B=2, merge_method="None", use_first_ln=False), B=1, T=2))
+
+
+def test_untrainable_configurations_raise():
+    from sound_bubble_b200.packing import ModelConfig
+    from sound_bubble_b200.training import check_trainable
+    check_trainable(ModelConfig(variant="dis_embed", **SYN))
+    for kw in (dict(SYN, conv_lstm=True), dict(SYN, use_attn=True), dict(SYN, dis_type="linear2")):
+        with pytest.raises(NotImplementedError):
+            check_trainable(ModelConfig(variant="dis_embed", **kw))

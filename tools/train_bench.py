@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Training step of the TFG_S separator on one B200: forward + backward through the hand-written kernels, timed with CUDA
+events, next to autograd through the CPU oracle port on a bounded sample (BASELINE config 4's per-GPU work: the reference
+trains with global batch 8 on 5 s clips, syn_experiments/pretrain_stage.json).
+
+    python tools/train_bench.py [--batch 8] [--seconds 5] [--steps 3] [--cpu 1]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import SYN, radius_one_hot  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--seconds", type=float, default=5.0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--cpu", type=int, default=1)
+    args = ap.parse_args()
+    from sound_bubble_b200 import Net, _lib
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    net = Net(**SYN).to(dev).train()
+    n = int(args.seconds * 24000) // 192 * 192
+    g = torch.Generator().manual_seed(1)
+    mix = (0.1 * torch.randn(args.batch, 6, n, generator=g)).to(dev)
+    tgt = (0.1 * torch.randn(args.batch, 1, n, generator=g)).to(dev)
+    dis = radius_one_hot(args.batch).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        est = net({"mixture": mix, "dis_embed": dis})["output"]
+        loss = -(10 * torch.log10(tgt.pow(2).sum(-1) / ((est - tgt).pow(2).sum(-1) + 1e-8))).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    frames = args.batch * (n // 192)
+    res = {"what": "training step (forward + backward + clip + Adam), TFG_S, fp32", "batch": args.batch, "seconds": args.seconds,
+           "ms_per_step": ms, "train_frames_per_s": frames / ms * 1e3, "clips_per_s": args.batch / ms * 1e3,
+           "launches_per_step": (_lib.launch_count() - l0) / args.steps,
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": float(loss)}
+    # forward-only and backward-only split
+    torch.cuda.synchronize()
+    e0.record()
+    est = net({"mixture": mix, "dis_embed": dis})["output"]
+    e1.record()
+    l = est.pow(2).mean()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    l.backward()
+    e3.record()
+    torch.cuda.synchronize()
+    res["fwd_ms"], res["bwd_ms"] = e0.elapsed_time(e1), e2.elapsed_time(e3)
+    if args.cpu:
+        # the oracle port under autograd on the host cores, bounded sample: 1 clip x 1 s
+        from oracle import tfgridnet_oracle as orc
+        from oracle.weights import make_state_dict
+        ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
+        sd = {k: (v.clone().requires_grad_("_filters" not in k)) for k, v in make_state_dict(ocfg, 0).items()}
+        torch.set_num_threads(os.cpu_count())
+        cm = mix[:1, :, :24000].cpu()
+        t0 = time.time()
+        out = orc.net_forward(sd, ocfg, {"mixture": cm, "dis_embed": dis[:1].cpu()})["output"]
+        out.pow(2).mean().backward()
+        dt = time.time() - t0
+        res["cpu_port"] = {"sample": "1 clip x 1 s, forward + backward, oracle port under torch autograd", "cores": os.cpu_count(),
+                           "s": dt, "train_frames_per_s": 125 / dt}
+        res["speedup_vs_cpu_port"] = res["train_frames_per_s"] / res["cpu_port"]["train_frames_per_s"]
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
