@@ -64,7 +64,7 @@ def flatten_state(st, prefix="state"):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("grad_"))   # grad_*: train_cases.py
 
 
 @pytest.fixture(scope="session")
