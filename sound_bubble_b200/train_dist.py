@@ -9,8 +9,9 @@
     (:433-441), so the order is reduce -> clip -> optimizer step.
   * ``dump_state / load_state``: the checkpoint layout of PLModule (:115-156) with the model saved WITHOUT a wrapper
     prefix, so run directories stay interchangeable with the reference's.
-This repository's CUDA path is forward-only: the reducer is exercised here with autograd models such as
-the reference ``Net``; it does not make the B200 kernels trainable.
+It serves any autograd module: the drop-in ``Net`` in train() mode (whose backward pass is the hand-written kernels of
+csrc/sb_train.cu behind training.SeparatorFunction; ``tools/train_ddp.py`` runs that over NCCL) as well as the reference
+``Net`` (``tests/test_train_dist.py``, Gloo).
 """
 from __future__ import annotations
 
