@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(256) lstm_train_bwd_kernel(const LstmTrain a) 
 
 // ------------------------------------------------------------------------------------------------------------
 // out[o(n)][0..P) = bias + res[o(n)] + sum_a sum_k A_a[i(n)][k] * W_a(k, p)       (tall-skinny GEMM, W in shared memory)
+// CTA tile = ROWS x P with an 8 x 8 register tile per thread; A is staged k-major through shared memory in chunks of KB
+// columns (coalesced float4 loads, the next chunk prefetched into registers while the current one is multiplied), so one
+// k costs 2 + 2 LDS.128 for 64 FMA.
 // ------------------------------------------------------------------------------------------------------------
 struct RowGemm {
     const float* A[2];
@@ -297,70 +300,118 @@ struct RowGemm {
 };
 
 template <int P>
-__global__ void __launch_bounds__(256) rowgemm_kernel(const RowGemm g) {
+struct RowGemmCfg {
+    static constexpr int CG = P / 8, RG = 256 / CG, ROWS = RG * 8, KB = 8;
+    static constexpr int AS = ROWS + 4, LPT = ROWS * KB / 4 / 256;
+    static size_t smem_bytes(int nA, int K) { return ((size_t)nA * K * P + (size_t)KB * AS) * sizeof(float); }
+};
+
+template <int P>
+__global__ void __launch_bounds__(256, 2) rowgemm_kernel(const RowGemm g) {
+    using Cfg = RowGemmCfg<P>;
+    constexpr int CG = Cfg::CG, ROWS = Cfg::ROWS, KB = Cfg::KB, AS = Cfg::AS, LPT = Cfg::LPT;
     SB_DYN_SMEM(float, ws);                         // [nA][K][P]
-    constexpr int TPR = P / 8, ROWS = 256 / TPR;
     const int tid = threadIdx.x, K = g.K;
-    for (int a = 0; a < g.nA; ++a)
+    float* As = ws + (size_t)g.nA * K * P;          // [KB][AS]
+    for (int a = 0; a < g.nA; ++a) {
+        const float* wsrc = a ? g.W[1] : g.W[0];
         for (int i = tid; i < K * P; i += 256) {
             const int k = i / P, p = i - k * P;
-            ws[(a * K + k) * P + p] = __ldg(g.W[a] + (g.w_trans ? (size_t)p * g.ldw + k : (size_t)k * g.ldw + p));
+            ws[(a * K + k) * P + p] = __ldg(wsrc + (g.w_trans ? (size_t)p * g.ldw + k : (size_t)k * g.ldw + p));
         }
+    }
+    const long long row_base = (long long)blockIdx.x * ROWS;
+    // loader role: float4 number tid + 256 i of the chunk = (row lrow, columns 4*lk4 .. +3)
+    long long aoff[LPT];
+    auto lrow = [&](int i) { return (tid + 256 * i) / (KB / 4); };
+    auto lk = [&](int i) { return 4 * ((tid + 256 * i) % (KB / 4)); };
+#pragma unroll
+    for (int i = 0; i < LPT; ++i) {
+        const long long n = row_base + lrow(i);
+        aoff[i] = n < g.N ? (g.a_mapped ? map_pos(g.map, n) : n) * g.lda + lk(i) : -1;
+    }
+    const int p0 = (tid % CG) * 8, r0 = (tid / CG) * 8;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     pdl_wait();
-    __syncthreads();
-    const long long n = (long long)blockIdx.x * ROWS + tid / TPR;
-    if (n >= g.N) return;
-    const int p0 = (tid % TPR) * 8;
-    const long long pos = map_pos(g.map, n);
-    const long long na = g.a_mapped ? pos : n, no = g.o_mapped ? pos : n;
-    float acc[8];
+    const int chunks = K / KB, total = g.nA * chunks;
+    float4 v[LPT];
+    auto fetch = [&](int c) {
+        const float* base = (c >= chunks ? g.A[1] : g.A[0]) + (c % chunks) * KB;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = g.bias ? __ldg(g.bias + p0 + i) : 0.f;
-    if (g.res) {
-        const float4 r0 = ldg4_stream(g.res + no * P + p0), r1 = ldg4_stream(g.res + no * P + p0 + 4);
-        acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w; acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
-    }
-    for (int a = 0; a < g.nA; ++a) {
-        const float* ar = g.A[a] + na * g.lda;
-        const float* wa = ws + (size_t)a * K * P + p0;
-        for (int k = 0; k < K; k += 4) {
-            const float4 av = ld4(ar + k);
-            const float avv[4] = {av.x, av.y, av.z, av.w};
+        for (int i = 0; i < LPT; ++i) v[i] = aoff[i] >= 0 ? ld4(base + aoff[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch(0);
+    for (int c = 0; c < total; ++c) {
+        __syncthreads();                            // the previous chunk has been consumed (and W is staged)
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const float4 w0 = ld4(wa + (k + kk) * P), w1 = ld4(wa + (k + kk) * P + 4);
-                acc[0] = fmaf(avv[kk], w0.x, acc[0]); acc[1] = fmaf(avv[kk], w0.y, acc[1]);
-                acc[2] = fmaf(avv[kk], w0.z, acc[2]); acc[3] = fmaf(avv[kk], w0.w, acc[3]);
-                acc[4] = fmaf(avv[kk], w1.x, acc[4]); acc[5] = fmaf(avv[kk], w1.y, acc[5]);
-                acc[6] = fmaf(avv[kk], w1.z, acc[6]); acc[7] = fmaf(avv[kk], w1.w, acc[7]);
-            }
+        for (int i = 0; i < LPT; ++i) {
+            float* d = As + lk(i) * AS + lrow(i);
+            d[0] = v[i].x; d[AS] = v[i].y; d[2 * AS] = v[i].z; d[3 * AS] = v[i].w;
+        }
+        __syncthreads();
+        if (c + 1 < total) fetch(c + 1);
+        const float* wa = ws + ((size_t)(c / chunks) * K + (c % chunks) * KB) * P + p0;
+#pragma unroll 2
+        for (int k = 0; k < KB; ++k) {
+            const float4 a0 = ld4(As + k * AS + r0), a1 = ld4(As + k * AS + r0 + 4);
+            const float4 w0 = ld4(wa + k * P), w1 = ld4(wa + k * P + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
         }
     }
-    st4(g.out + no * P + p0, make_float4(acc[0], acc[1], acc[2], acc[3]));
-    st4(g.out + no * P + p0 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    float bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = g.bias ? __ldg(g.bias + p0 + j) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long n = row_base + r0 + i;
+        if (n >= g.N) break;
+        const long long no = (g.o_mapped ? map_pos(g.map, n) : n) * P + p0;
+        float4 o0 = make_float4(acc[i][0] + bv[0], acc[i][1] + bv[1], acc[i][2] + bv[2], acc[i][3] + bv[3]);
+        float4 o1 = make_float4(acc[i][4] + bv[4], acc[i][5] + bv[5], acc[i][6] + bv[6], acc[i][7] + bv[7]);
+        if (g.res) {
+            const float4 q0 = ldg4_stream(g.res + no), q1 = ldg4_stream(g.res + no + 4);
+            o0.x += q0.x; o0.y += q0.y; o0.z += q0.z; o0.w += q0.w; o1.x += q1.x; o1.y += q1.y; o1.z += q1.z; o1.w += q1.w;
+        }
+        st4(g.out + no, o0);
+        st4(g.out + no + 4, o1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // dW[j][k] += sum_n A[n][j] * B[n'][k],  db[j] += sum_n A[n][j]          (reduction over all (row, step) pairs)
-//   b_mode 0: n' = n;  1: n' = map_pos(n) (A mapped the same way if a_mapped);  2: n' = the previous step of the same
-//   sequence in processing order (n - 1, or n + 1 for the reverse direction), a zero row at the sequence start.
-// Each CTA walks a contiguous range of n in slabs of 16 rows staged in shared memory; thread tile TJ x TK in registers.
+//   columns k < kc0 of B come from Bm:  b_mode 0: n' = n;  1: n' = map_pos(n) (A mapped the same way if a_mapped);
+//   columns k >= kc0 come from Bm2 at the previous step of the same sequence in processing order (n - 1, or n + 1 for
+//   the reverse direction; a zero row at the sequence start) and go to dW2: one pass over dz yields dW_ih and dW_hh.
+// Each CTA walks a contiguous range of n in slabs of 16 rows staged in shared memory (the next slab is prefetched into
+// registers while the current one is multiplied); thread tile TJ x TK in registers.
 // ------------------------------------------------------------------------------------------------------------
 struct Outer {
     const float* A;
     const float* Bm;
+    const float* Bm2;
     float* dW;
+    float* dW2;
     float* db;
     float* db2;
     RowMap map;
-    int a_mapped, b_mode, reverse, ldw;
+    int a_mapped, b_mode, reverse, ldw, ldw2, kc0;
     long long N, rows_per_cta;
 };
 
 template <int J, int KC, int TJ, int TK>
 __global__ void __launch_bounds__(256) outer_kernel(const Outer o) {
     constexpr int RB = 16, NTJ = J / TJ, NTK = KC / TK;
-    static_assert(NTJ * NTK <= 256, "tile");
+    constexpr int NA = (RB * J / 4 + 255) / 256, NB = (RB * KC / 4 + 255) / 256;
+    static_assert(NTJ * NTK <= 256 && TJ % 2 == 0 && TK % 2 == 0, "tile");
     __shared__ __align__(16) float As[RB][J];
     __shared__ __align__(16) float Bs[RB][KC];
     const int tid = threadIdx.x;
@@ -375,41 +426,56 @@ __global__ void __launch_bounds__(256) outer_kernel(const Outer o) {
     }
     const long long n_begin = (long long)blockIdx.x * o.rows_per_cta;
     const long long n_end = n_begin + o.rows_per_cta < o.N ? n_begin + o.rows_per_cta : o.N;
+    const int kc0 = o.kc0;
     pdl_wait();
-    for (long long n0 = n_begin; n0 < n_end; n0 += RB) {
-        for (int i = tid; i < RB * (J / 4); i += 256) {
-            const int r = i / (J / 4), c4 = i - r * (J / 4);
+    float4 va[NA], vb[NB];
+    auto fetch = [&](long long n0) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            const int i = tid + 256 * q, r = i / (J / 4), c4 = i - r * (J / 4);
             const long long n = n0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < n_end) v = ldg4_stream(o.A + (o.a_mapped ? map_pos(o.map, n) : n) * J + 4 * c4);
-            st4(&As[r][4 * c4], v);
+            va[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < RB * (J / 4) && n < n_end) va[q] = ldg4_stream(o.A + (o.a_mapped ? map_pos(o.map, n) : n) * J + 4 * c4);
         }
-        for (int i = tid; i < RB * (KC / 4); i += 256) {
-            const int r = i / (KC / 4), c4 = i - r * (KC / 4);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int i = tid + 256 * q, r = i / (KC / 4), col = 4 * (i - r * (KC / 4));
             const long long n = n0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < n_end) {
-                long long nb = n;
-                bool zero = false;
-                if (o.b_mode == 1) nb = map_pos(o.map, n);
-                else if (o.b_mode == 2) {
+            vb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < RB * (KC / 4) && n < n_end) {
+                if (col < kc0) {
+                    vb[q] = ldg4_stream(o.Bm + (o.b_mode == 1 ? map_pos(o.map, n) : n) * kc0 + col);
+                } else {
                     const int s = (int)(n % o.map.S);
-                    if (o.reverse) { zero = s == o.map.S - 1; nb = n + 1; }
-                    else { zero = s == 0; nb = n - 1; }
+                    const bool zero = o.reverse ? s == o.map.S - 1 : s == 0;
+                    if (!zero) vb[q] = ldg4_stream(o.Bm2 + (o.reverse ? n + 1 : n - 1) * (KC - kc0) + (col - kc0));
                 }
-                if (!zero) v = ldg4_stream(o.Bm + nb * KC + 4 * c4);
             }
-            st4(&Bs[r][4 * c4], v);
+        }
+    };
+    if (n_begin < n_end) fetch(n_begin);
+    for (long long n0 = n_begin; n0 < n_end; n0 += RB) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            const int i = tid + 256 * q;
+            if (i < RB * (J / 4)) st4(&As[0][0] + 4 * i, va[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int i = tid + 256 * q;
+            if (i < RB * (KC / 4)) st4(&Bs[0][0] + 4 * i, vb[q]);
         }
         __syncthreads();
+        if (n0 + RB < n_end) fetch(n0 + RB);
         if (worker) {
 #pragma unroll 4
             for (int r = 0; r < RB; ++r) {
                 float av[TJ], bv[TK];
 #pragma unroll
-                for (int i = 0; i < TJ; ++i) av[i] = As[r][tj * TJ + i];
+                for (int i = 0; i < TJ; i += 2) { const float2 t = ld2(&As[r][tj * TJ + i]); av[i] = t.x; av[i + 1] = t.y; }
 #pragma unroll
-                for (int k = 0; k < TK; ++k) bv[k] = Bs[r][tk * TK + k];
+                for (int k = 0; k < TK; k += 2) { const float2 t = ld2(&Bs[r][tk * TK + k]); bv[k] = t.x; bv[k + 1] = t.y; }
 #pragma unroll
                 for (int i = 0; i < TJ; ++i) {
                     if (tk == 0) accb[i] += av[i];
@@ -418,16 +484,20 @@ __global__ void __launch_bounds__(256) outer_kernel(const Outer o) {
                 }
             }
         }
-        __syncthreads();
     }
     if (worker) {
 #pragma unroll
         for (int i = 0; i < TJ; ++i) {
+            const int j = tj * TJ + i;
 #pragma unroll
-            for (int k = 0; k < TK; ++k) atomic_add(o.dW + (size_t)(tj * TJ + i) * o.ldw + tk * TK + k, acc[i][k]);
+            for (int k = 0; k < TK; ++k) {
+                const int col = tk * TK + k;
+                if (col < kc0) atomic_add(o.dW + (size_t)j * o.ldw + col, acc[i][k]);
+                else atomic_add(o.dW2 + (size_t)j * o.ldw2 + (col - kc0), acc[i][k]);
+            }
             if (tk == 0) {
-                if (o.db) atomic_add(o.db + tj * TJ + i, accb[i]);
-                if (o.db2) atomic_add(o.db2 + tj * TJ + i, accb[i]);
+                if (o.db) atomic_add(o.db + j, accb[i]);
+                if (o.db2) atomic_add(o.db2 + j, accb[i]);
             }
         }
     }
@@ -792,9 +862,12 @@ static int check_path(const sb_path_train_args* p, int inter, const char* who) {
 
 template <int P>
 static int run_rowgemm(const RowGemm& g, cudaStream_t st, const char* name) {
-    constexpr int ROWS = 256 / (P / 8);
-    const size_t smem = (size_t)g.nA * g.K * P * sizeof(float);
-    return launch(name, rowgemm_kernel<P>, dim3((unsigned)ceil_div_ll(g.N, ROWS)), dim3(256), smem, st, g);
+    using Cfg = RowGemmCfg<P>;
+    if (g.K % Cfg::KB != 0) {
+        set_error("%s: K = %d is not a multiple of %d", name, g.K, Cfg::KB);
+        return SB_E_UNSUPP;
+    }
+    return launch(name, rowgemm_kernel<P>, dim3((unsigned)ceil_div_ll(g.N, Cfg::ROWS)), dim3(256), Cfg::smem_bytes(g.nA, g.K), st, g);
 }
 static int rowgemm(const RowGemm& g, int P, cudaStream_t st, const char* name) {
     switch (P) {
@@ -855,7 +928,7 @@ static int path_bwd(const sb_path_bwd_args& b, cudaStream_t st) {
         g.out = dh[k]; g.map = d.map; g.a_mapped = 1; g.o_mapped = 0; g.N = d.N;
         SB_CHECK(rowgemm(g, a.H, st, "path_linear_bwd"));
         Outer o{};
-        o.A = b.gy; o.Bm = v.h[k]; o.dW = b.g_lin_w + k * a.H; o.ldw = d.nd * a.H;
+        o.A = b.gy; o.Bm = v.h[k]; o.kc0 = a.H; o.dW = b.g_lin_w + k * a.H; o.ldw = d.nd * a.H;
         o.db = k == 0 ? b.g_lin_b : nullptr; o.db2 = nullptr;
         o.map = d.map; o.a_mapped = 1; o.b_mode = 0; o.reverse = 0; o.N = d.N;
         if (a.C == 32) SB_CHECK((run_outer<32, 64, 4, 2>(o, st, "path_linear_wgrad")));
@@ -866,15 +939,14 @@ static int path_bwd(const sb_path_bwd_args& b, cudaStream_t st) {
     for (int k = 0; k < d.nd; ++k) { l.w_hh[k] = a.w_hh[k]; l.gates[k] = v.gates[k]; l.c[k] = v.c[k]; l.dh[k] = dh[k]; }
     l.R = (int)d.R; l.S = d.S;
     SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd_kernel, dim3((unsigned)ceil_div_ll(d.R, 4), d.nd), dim3(256), 0, st, l));
-    // (3) weight gradients: dW_ih = dz^T LN(x), dW_hh = dz^T h_prev, db = sum dz
+    // (3) weight gradients in one pass over dz: dW_ih = dz^T LN(x), dW_hh = dz^T h_prev, db = sum dz
     for (int k = 0; k < d.nd; ++k) {
         Outer o{};
         o.A = v.gates[k]; o.map = d.map; o.a_mapped = 0; o.reverse = k; o.N = d.N;
-        o.Bm = v.xn; o.b_mode = 0; o.dW = b.g_w_ih[k]; o.ldw = a.C; o.db = b.g_b_ih[k]; o.db2 = b.g_b_hh[k];
-        if (a.C == 32) SB_CHECK((run_outer<256, 32, 8, 4>(o, st, "lstm_wgrad_ih")));
-        else SB_CHECK((run_outer<256, 16, 8, 2>(o, st, "lstm_wgrad_ih")));
-        o.Bm = v.h[k]; o.b_mode = 2; o.dW = b.g_w_hh[k]; o.ldw = a.H; o.db = nullptr; o.db2 = nullptr;
-        SB_CHECK((run_outer<256, 64, 8, 8>(o, st, "lstm_wgrad_hh")));
+        o.Bm = v.xn; o.b_mode = 0; o.kc0 = a.C; o.dW = b.g_w_ih[k]; o.ldw = a.C; o.db = b.g_b_ih[k]; o.db2 = b.g_b_hh[k];
+        o.Bm2 = v.h[k]; o.dW2 = b.g_w_hh[k]; o.ldw2 = a.H;
+        if (a.C == 32) SB_CHECK((run_outer<256, 96, 8, 12>(o, st, "lstm_wgrad")));
+        else SB_CHECK((run_outer<256, 80, 8, 10>(o, st, "lstm_wgrad")));
     }
     // (4) dL/dLN(x) = sum_dir dz W_ih, then LayerNorm backward + the residual branch
     RowGemm g{};
