@@ -213,6 +213,65 @@ def ncu_dram_traffic(kernel_substr):
     return sum(vals) / len(vals) if vals else None
 
 
+def training_leg(dev, rank, world, batch=8, steps=3):
+    """BASELINE config 4's shape, for context next to the headline: one data-parallel training step of the same TFG_S
+    model (forward + hand-written backward kernels + ONE NCCL all-reduce of the flat gradient + clip + Adam) on `batch`
+    5 s clips per GPU, fp32.  Device-timed, max over ranks.  A failure is reported in the line, never hidden."""
+    import torch.distributed as dist
+    from sound_bubble_b200 import Net
+    from sound_bubble_b200.train_dist import FlatGradReducer, backprop
+    ok, err, step = 1, "", None
+    try:
+        torch.manual_seed(0)
+        tnet = Net(**SYN).to(dev).train()
+        g = torch.Generator().manual_seed(99 + rank)
+        mix = (0.1 * torch.randn(batch, MICS, N_SAMPLES, generator=g)).to(dev)
+        tgt = (0.1 * torch.randn(batch, 1, N_SAMPLES, generator=g)).to(dev)
+        dis = radius_one_hot(batch).to(dev)
+        red = FlatGradReducer(tnet.parameters())
+        opt = torch.optim.Adam(tnet.parameters(), lr=1e-3)
+
+        def local_grads():
+            red.zero_grad()
+            est = tnet({"mixture": mix, "dis_embed": dis})["output"]
+            loss = -(10 * torch.log10(tgt.pow(2).sum(-1) / ((est - tgt).pow(2).sum(-1) + 1e-8))).mean()
+            loss.backward()
+            return loss
+
+        def step():
+            loss = local_grads()
+            backprop(red, opt, grad_clip=1.0)                      # all-reduce (mean) -> clip -> Adam
+            return loss
+        local_grads()                                              # warm-up without a collective
+        torch.cuda.synchronize(dev)
+    except Exception as e:                                         # noqa: BLE001 - reported in the JSON line
+        ok, err = 0, "%s: %s" % (type(e).__name__, str(e)[:200])
+    flag = torch.tensor([ok], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                # every rank takes the same branch below
+    if int(flag.item()) == 0:
+        return {"error": err or "a peer rank failed"}
+    step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    b.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    frames = batch * T_FRAMES * world
+    return {"value": frames / (ms * 1e-3), "unit": "training frames/s", "ms_per_step": ms, "global_batch": batch * world,
+            "clip_seconds": 5.0, "dtype": "f32", "steps": steps, "loss": float(loss.detach()),
+            "collective": "one all-reduce of %d fp32 gradients per step (NCCL)" % red.numel if world > 1 else "none (1 GPU)",
+            "note": "forward + backward through csrc/sb_train.cu, clip after the reduction, Adam; see tools/train_bench.py"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from sound_bubble_b200 import Net, _lib
@@ -302,6 +361,8 @@ def run_ours(args, rank, world, local_rank):
     frames = BATCH * T_FRAMES * world
     value = frames / (ms_dev * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
+
+    train_info = None if args.no_train else training_leg(dev, rank, world)
 
     if rank != 0:
         return
@@ -398,7 +459,7 @@ def run_ours(args, rank, world, local_rank):
         "in_order": {"value": frames / (ms_in_order * 1e-3), "unit": UNIT, "ms_per_step": ms_in_order,
                      "note": "one stream, chunk t+1 starts when chunk t has finished"},
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "offline": offline_info,
-        "streaming_vs_offline_maxabs": stream_vs_offline,
+        "streaming_vs_offline_maxabs": stream_vs_offline, "train": train_info,
     }), flush=True)
 
 
@@ -416,6 +477,7 @@ def main():
     ap.add_argument("--pipe-inter-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the inter path")
     ap.add_argument("--depth", type=int, default=8, help="pipelined session: chunks in flight")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

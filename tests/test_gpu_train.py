@@ -116,3 +116,14 @@ def test_a_few_optimizer_steps_reduce_the_loss():
         losses.append(float(loss))
     # the same loop through the oracle port on the CPU gives 16.543, 11.697, ..., 4.959
     assert abs(losses[0] - 16.5427) <= 2e-3 and losses[-1] < 7.0, losses
+
+
+def test_gradients_with_programmatic_dependent_launch(lib):
+    """bench.py runs the library with SB_OPT_PDL on: every training kernel must wait before it reads a predecessor's output"""
+    from sound_bubble_b200 import _lib
+    _lib.set_pdl(True)
+    try:
+        _ok(tc.check_golden_grads(lib, DEV, "grad_syn_b2"))
+        _ok(tc.check_net(lib, DEV, "dis_embed", SYN, B=2, T=20))
+    finally:
+        _lib.set_pdl(False)
