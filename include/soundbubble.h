@@ -72,6 +72,8 @@ extern "C" {
 #define SB_OPT_PDL 1            /* 1 = launch kernels with programmatic dependent launch (prologue overlap)       */
 #define SB_OPT_ATTN_TC 2        /* 0 = keep the attention core of whole-utterance calls on the SIMT kernel (default 1:  */
                                 /* tcgen05 core for T >= 64, W <= 129, F*E <= 320)                                    */
+#define SB_OPT_TRAIN_ONE_ROW 3  /* 1 = training LSTM kernels with one gate row (forward) / one W_hh column (BPTT) per thread  */
+                                /* and 256 threads (the first version, kept for comparison; default 0: two per thread, 128) */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

@@ -14,6 +14,7 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_pdl{0};
 static std::atomic<int> g_attn_tc{1};
+static std::atomic<int> g_train_one_row{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -33,6 +34,7 @@ int check_launch(const char* what) {
 
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 bool attn_tc_enabled() { return g_attn_tc.load(std::memory_order_relaxed) != 0; }
+bool train_one_row_enabled() { return g_train_one_row.load(std::memory_order_relaxed) != 0; }
 
 int sm_count() {
     static thread_local int dev_cached = -1, sms = 0;
@@ -85,6 +87,10 @@ extern "C" int sb_set_option(int option, int value) {
     }
     if (option == SB_OPT_ATTN_TC) {
         sb::g_attn_tc.store(value ? 1 : 0);
+        return 0;
+    }
+    if (option == SB_OPT_TRAIN_ONE_ROW) {
+        sb::g_train_one_row.store(value ? 1 : 0);
         return 0;
     }
     sb::set_error("sb_set_option: unknown option %d", option);

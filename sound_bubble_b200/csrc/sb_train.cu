@@ -217,6 +217,87 @@ __global__ void __launch_bounds__(256) lstm_train_fwd_kernel(const LstmTrain a) 
     }
 }
 
+// Same computation with TWO gate rows per thread (rows t and t + 2H: an (i|f) row and a (g|o) row), 128 threads: one
+// broadcast LDS.128 now feeds 8 FMAs, which halves the shared-memory traffic that bounds the one-row version (C = 32).
+template <int C>
+__global__ void __launch_bounds__(128) lstm_train_fwd2_kernel(const LstmTrain a) {
+    constexpr int H = kH, NS = 4, K = C + H;
+    static_assert(NS * C <= 128, "x loader");
+    __shared__ float4 a_s[K];
+    __shared__ float z_s[NS][4 * H];
+    const int tid = threadIdx.x, d = blockIdx.y, r0 = blockIdx.x * NS, S = a.S;
+    float w0[K], w1[K];
+#pragma unroll
+    for (int k = 0; k < C; k += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.w_ih[d] + (size_t)tid * C + k));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(a.w_ih[d] + (size_t)(tid + 2 * H) * C + k));
+        w0[k] = t.x; w0[k + 1] = t.y; w0[k + 2] = t.z; w0[k + 3] = t.w;
+        w1[k] = u.x; w1[k + 1] = u.y; w1[k + 2] = u.z; w1[k + 3] = u.w;
+    }
+#pragma unroll
+    for (int k = 0; k < H; k += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(a.w_hh[d] + (size_t)tid * H + k));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(a.w_hh[d] + (size_t)(tid + 2 * H) * H + k));
+        w0[C + k] = t.x; w0[C + k + 1] = t.y; w0[C + k + 2] = t.z; w0[C + k + 3] = t.w;
+        w1[C + k] = u.x; w1[C + k + 1] = u.y; w1[C + k + 2] = u.z; w1[C + k + 3] = u.w;
+    }
+    const float bias0 = __ldg(a.b_ih[d] + tid) + __ldg(a.b_hh[d] + tid);
+    const float bias1 = __ldg(a.b_ih[d] + tid + 2 * H) + __ldg(a.b_hh[d] + tid + 2 * H);
+    const bool row1_tanh = tid < H;                 // row tid + 2H is a g row for tid < H, an o row otherwise
+    const int xq = tid / C, xc = tid - xq * C;
+    const bool loader = tid < NS * C;
+    const long long xrow = min(r0 + (loader ? xq : 0), a.R - 1);
+    // cell role: unit u of sequences q0 and q0 + 2
+    const int q0 = tid / H, u = tid - q0 * H;
+    reinterpret_cast<float*>(&a_s[C + u])[q0] = 0.f;
+    reinterpret_cast<float*>(&a_s[C + u])[q0 + 2] = 0.f;
+    float c_reg[2] = {0.f, 0.f};
+    pdl_wait();
+    float xv = 0.f;
+    if (loader) xv = ldg1_stream(a.xn + (xrow * S + (d ? S - 1 : 0)) * C + xc);
+    for (int s = 0; s < S; ++s) {
+        const int se = d ? S - 1 - s : s;
+        if (loader) reinterpret_cast<float*>(&a_s[xc])[xq] = xv;
+        __syncthreads();
+        if (loader && s + 1 < S) xv = ldg1_stream(a.xn + (xrow * S + (d ? se - 1 : se + 1)) * C + xc);
+        float acc[2][4] = {{bias0, bias0, bias0, bias0}, {bias1, bias1, bias1, bias1}};
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 v = a_s[k];
+            acc[0][0] = fmaf(w0[k], v.x, acc[0][0]); acc[0][1] = fmaf(w0[k], v.y, acc[0][1]);
+            acc[0][2] = fmaf(w0[k], v.z, acc[0][2]); acc[0][3] = fmaf(w0[k], v.w, acc[0][3]);
+            acc[1][0] = fmaf(w1[k], v.x, acc[1][0]); acc[1][1] = fmaf(w1[k], v.y, acc[1][1]);
+            acc[1][2] = fmaf(w1[k], v.z, acc[1][2]); acc[1][3] = fmaf(w1[k], v.w, acc[1][3]);
+        }
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            acc[0][q] = sigmoid_f(acc[0][q]);
+            acc[1][q] = row1_tanh ? tanh_f(acc[1][q]) : sigmoid_f(acc[1][q]);
+            z_s[q][tid] = acc[0][q];
+            z_s[q][tid + 2 * H] = acc[1][q];
+            if (r0 + q < a.R) {
+                float* gp = a.gates[d] + ((long long)(r0 + q) * S + se) * (4 * H) + tid;
+                gp[0] = acc[0][q];
+                gp[2 * H] = acc[1][q];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = q0 + 2 * i;
+            const float gi = z_s[q][u], gf = z_s[q][H + u], gg = z_s[q][2 * H + u], go = z_s[q][3 * H + u];
+            c_reg[i] = fmaf(gf, c_reg[i], gi * gg);
+            const float hh = go * tanh_f(c_reg[i]);
+            reinterpret_cast<float*>(&a_s[C + u])[q] = hh;
+            if (r0 + q < a.R) {
+                const long long n = (long long)(r0 + q) * S + se;
+                a.c[d][n * H + u] = c_reg[i];
+                a.h[d][n * H + u] = hh;
+            }
+        }
+    }
+}
+
 // BPTT, serial part: per step the cell derivatives (dz, written over the stored gates) and dh_{t-1} += W_hh^T dz.
 // Thread (q, u) differentiates the cell of sequence q, unit u; thread (quarter, k) then sums its quarter of the 4H gate
 // rows of column k of W_hh (64 weights in registers) for the four sequences.
@@ -277,6 +358,91 @@ __global__ void __launch_bounds__(256) lstm_train_bwd_kernel(const LstmTrain a) 
             p0 = fmaf(wq[j], v.x, p0); p1 = fmaf(wq[j], v.y, p1); p2 = fmaf(wq[j], v.z, p2); p3 = fmaf(wq[j], v.w, p3);
         }
         part_s[q][0][u] = p0; part_s[q][1][u] = p1; part_s[q][2][u] = p2; part_s[q][3][u] = p3;
+        __syncthreads();
+    }
+}
+
+// BPTT with TWO columns of W_hh per thread (k and k + 32) and 128 threads: one broadcast LDS.128 of dz feeds 8 FMAs.
+// Thread (quarter, kp) sums its quarter of the 4H gate rows for columns kp and kp + 32; thread (q0, u) differentiates the
+// cells of unit u for sequences q0 and q0 + 2.
+__global__ void __launch_bounds__(128) lstm_train_bwd2_kernel(const LstmTrain a) {
+    constexpr int H = kH, NS = 4;
+    __shared__ float4 dz_s[4 * H];
+    __shared__ float part_s[4][NS][H];
+    const int tid = threadIdx.x, d = blockIdx.y, r0 = blockIdx.x * NS, S = a.S;
+    const int qtr = tid / 32, kp = tid % 32;
+    float wq[2][H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        wq[0][j] = __ldg(a.w_hh[d] + (size_t)(qtr * H + j) * H + kp);
+        wq[1][j] = __ldg(a.w_hh[d] + (size_t)(qtr * H + j) * H + kp + 32);
+    }
+    const int q0 = tid / H, u = tid - q0 * H;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { part_s[i][q0][u] = 0.f; part_s[i][q0 + 2][u] = 0.f; }
+    float* gates = a.gates[d];
+    const float* cc = a.c[d];
+    const float* dh = a.dh[d];
+    bool valid[2];
+    long long row[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { valid[i] = r0 + q0 + 2 * i < a.R; row[i] = min(r0 + q0 + 2 * i, a.R - 1); }
+    pdl_wait();
+    __syncthreads();
+    float dc[2] = {0.f, 0.f};
+    int se = d ? 0 : S - 1;
+    float gi[2], gf[2], gg[2], go[2], ct[2], cp[2], dhv[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const long long n = row[i] * S + se;
+        gi[i] = gates[n * 4 * H + u]; gf[i] = gates[n * 4 * H + H + u]; gg[i] = gates[n * 4 * H + 2 * H + u]; go[i] = gates[n * 4 * H + 3 * H + u];
+        ct[i] = cc[n * H + u]; dhv[i] = dh[n * H + u];
+        cp[i] = S > 1 ? cc[(d ? n + 1 : n - 1) * H + u] : 0.f;
+    }
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = q0 + 2 * i;
+            const long long n = row[i] * S + se;
+            const float dht = dhv[i] + ((part_s[0][q][u] + part_s[1][q][u]) + (part_s[2][q][u] + part_s[3][q][u]));
+            const float tc = tanh_f(ct[i]);
+            const float dcv = fmaf(dht * go[i], 1.f - tc * tc, dc[i]);
+            const float dzi = dcv * gg[i] * gi[i] * (1.f - gi[i]);
+            const float dzf = dcv * cp[i] * gf[i] * (1.f - gf[i]);
+            const float dzg = dcv * gi[i] * (1.f - gg[i] * gg[i]);
+            const float dzo = dht * tc * go[i] * (1.f - go[i]);
+            dc[i] = dcv * gf[i];
+            reinterpret_cast<float*>(&dz_s[u])[q] = dzi;
+            reinterpret_cast<float*>(&dz_s[H + u])[q] = dzf;
+            reinterpret_cast<float*>(&dz_s[2 * H + u])[q] = dzg;
+            reinterpret_cast<float*>(&dz_s[3 * H + u])[q] = dzo;
+            if (valid[i]) {
+                gates[n * 4 * H + u] = dzi; gates[n * 4 * H + H + u] = dzf; gates[n * 4 * H + 2 * H + u] = dzg; gates[n * 4 * H + 3 * H + u] = dzo;
+            }
+        }
+        if (s + 1 < S) {
+            se = d ? se + 1 : se - 1;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const long long n = row[i] * S + se;
+                gi[i] = gates[n * 4 * H + u]; gf[i] = gates[n * 4 * H + H + u]; gg[i] = gates[n * 4 * H + 2 * H + u]; go[i] = gates[n * 4 * H + 3 * H + u];
+                ct[i] = cp[i];
+                dhv[i] = dh[n * H + u];
+                cp[i] = s + 2 < S ? cc[(d ? n + 1 : n - 1) * H + u] : 0.f;
+            }
+        }
+        __syncthreads();
+        float p[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float4 v = dz_s[qtr * H + j];
+            p[0][0] = fmaf(wq[0][j], v.x, p[0][0]); p[0][1] = fmaf(wq[0][j], v.y, p[0][1]);
+            p[0][2] = fmaf(wq[0][j], v.z, p[0][2]); p[0][3] = fmaf(wq[0][j], v.w, p[0][3]);
+            p[1][0] = fmaf(wq[1][j], v.x, p[1][0]); p[1][1] = fmaf(wq[1][j], v.y, p[1][1]);
+            p[1][2] = fmaf(wq[1][j], v.z, p[1][2]); p[1][3] = fmaf(wq[1][j], v.w, p[1][3]);
+        }
+#pragma unroll
+        for (int q = 0; q < NS; ++q) { part_s[qtr][q][kp] = p[0][q]; part_s[qtr][q][kp + 32] = p[1][q]; }
         __syncthreads();
     }
 }
@@ -905,7 +1071,8 @@ static int path_train_fwd(const sb_path_train_args& a, cudaStream_t st) {
     }
     l.R = (int)d.R; l.S = d.S;
     const dim3 grid((unsigned)ceil_div_ll(d.R, 4), d.nd);
-    if (a.C == 32) SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd_kernel<32>, grid, dim3(256), 0, st, l));
+    if (a.C == 32 && !train_one_row_enabled()) SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd2_kernel<32>, grid, dim3(128), 0, st, l));
+    else if (a.C == 32) SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd_kernel<32>, grid, dim3(256), 0, st, l));
     else SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd_kernel<16>, grid, dim3(256), 0, st, l));
     RowGemm g{};
     g.nA = d.nd; g.K = a.H; g.lda = a.H; g.ldw = d.nd * a.H; g.w_trans = 1;
@@ -938,7 +1105,8 @@ static int path_bwd(const sb_path_bwd_args& b, cudaStream_t st) {
     LstmTrain l{};
     for (int k = 0; k < d.nd; ++k) { l.w_hh[k] = a.w_hh[k]; l.gates[k] = v.gates[k]; l.c[k] = v.c[k]; l.dh[k] = dh[k]; }
     l.R = (int)d.R; l.S = d.S;
-    SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd_kernel, dim3((unsigned)ceil_div_ll(d.R, 4), d.nd), dim3(256), 0, st, l));
+    if (train_one_row_enabled()) SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd_kernel, dim3((unsigned)ceil_div_ll(d.R, 4), d.nd), dim3(256), 0, st, l));
+    else SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd2_kernel, dim3((unsigned)ceil_div_ll(d.R, 4), d.nd), dim3(128), 0, st, l));
     // (3) weight gradients in one pass over dz: dW_ih = dz^T LN(x), dW_hh = dz^T h_prev, db = sum dz
     for (int k = 0; k < d.nd; ++k) {
         Outer o{};

@@ -127,3 +127,13 @@ def test_gradients_with_programmatic_dependent_launch(lib):
         _ok(tc.check_net(lib, DEV, "dis_embed", SYN, B=2, T=20))
     finally:
         _lib.set_pdl(False)
+
+
+def test_first_version_lstm_training_kernels(lib):
+    from sound_bubble_b200 import _abi as abi
+    assert lib.sb_set_option(abi.SB_OPT_TRAIN_ONE_ROW, 1) == 0
+    try:
+        for inter in (False, True):
+            _ok(tc.check_path(lib, DEV, "dis_embed", SYN, inter, B=2, T=7))
+    finally:
+        lib.sb_set_option(abi.SB_OPT_TRAIN_ONE_ROW, 0)

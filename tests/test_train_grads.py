@@ -63,3 +63,14 @@ def test_untrainable_configurations_raise():
     for kw in (dict(SYN, conv_lstm=True), dict(SYN, use_attn=True), dict(SYN, dis_type="linear2")):
         with pytest.raises(NotImplementedError):
             check_trainable(ModelConfig(variant="dis_embed", **kw))
+
+
+def test_first_version_lstm_training_kernels(lib):
+    """SB_OPT_TRAIN_ONE_ROW: the one-gate-row / one-column-per-thread kernels stay selectable and correct"""
+    from sound_bubble_b200 import _abi as abi
+    assert lib.sb_set_option(abi.SB_OPT_TRAIN_ONE_ROW, 1) == 0
+    try:
+        _ok(tc.check_path(lib, "cpu", "dis_embed", SYN, False, B=1, T=2))
+        _ok(tc.check_path(lib, "cpu", "dis_embed", SYN, True, B=1, T=2))
+    finally:
+        lib.sb_set_option(abi.SB_OPT_TRAIN_ONE_ROW, 0)

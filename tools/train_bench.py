@@ -25,9 +25,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--cpu", type=int, default=1)
+    ap.add_argument("--one-row", type=int, default=0, help="1 = the first LSTM training kernels (SB_OPT_TRAIN_ONE_ROW)")
     args = ap.parse_args()
     from sound_bubble_b200 import Net, _lib
     dev = torch.device("cuda", 0)
+    if args.one_row:
+        _lib.load().sb_set_option(3, 1)
     torch.manual_seed(0)
     net = Net(**SYN).to(dev).train()
     n = int(args.seconds * 24000) // 192 * 192
@@ -59,7 +62,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     frames = args.batch * (n // 192)
-    res = {"what": "training step (forward + backward + clip + Adam), TFG_S, fp32", "batch": args.batch, "seconds": args.seconds,
+    res = {"what": "training step (forward + backward + clip + Adam), TFG_S, fp32", "batch": args.batch, "seconds": args.seconds, "one_row_kernels": bool(args.one_row),
            "ms_per_step": ms, "train_frames_per_s": frames / ms * 1e3, "clips_per_s": args.batch / ms * 1e3,
            "launches_per_step": (_lib.launch_count() - l0) / args.steps,
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": float(loss)}
