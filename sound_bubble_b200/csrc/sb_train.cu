@@ -260,15 +260,16 @@ __global__ void __launch_bounds__(128) lstm_train_fwd2_kernel(const LstmTrain a)
         if (loader) reinterpret_cast<float*>(&a_s[xc])[xq] = xv;
         __syncthreads();
         if (loader && s + 1 < S) xv = ldg1_stream(a.xn + (xrow * S + (d ? se - 1 : se + 1)) * C + xc);
-        float acc[2][4] = {{bias0, bias0, bias0, bias0}, {bias1, bias1, bias1, bias1}};
+        float2 acc2[2][2] = {{make_float2(bias0, bias0), make_float2(bias0, bias0)}, {make_float2(bias1, bias1), make_float2(bias1, bias1)}};
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+        for (int k = 0; k < K; ++k) {               // one broadcast LDS.128 -> 4 packed FFMA2 = 8 FMA
             const float4 v = a_s[k];
-            acc[0][0] = fmaf(w0[k], v.x, acc[0][0]); acc[0][1] = fmaf(w0[k], v.y, acc[0][1]);
-            acc[0][2] = fmaf(w0[k], v.z, acc[0][2]); acc[0][3] = fmaf(w0[k], v.w, acc[0][3]);
-            acc[1][0] = fmaf(w1[k], v.x, acc[1][0]); acc[1][1] = fmaf(w1[k], v.y, acc[1][1]);
-            acc[1][2] = fmaf(w1[k], v.z, acc[1][2]); acc[1][3] = fmaf(w1[k], v.w, acc[1][3]);
+            ffma2(acc2[0][0], make_float2(v.x, v.y), w0[k]);
+            ffma2(acc2[0][1], make_float2(v.z, v.w), w0[k]);
+            ffma2(acc2[1][0], make_float2(v.x, v.y), w1[k]);
+            ffma2(acc2[1][1], make_float2(v.z, v.w), w1[k]);
         }
+        float acc[2][4] = {{acc2[0][0].x, acc2[0][0].y, acc2[0][1].x, acc2[0][1].y}, {acc2[1][0].x, acc2[1][0].y, acc2[1][1].x, acc2[1][1].y}};
 #pragma unroll
         for (int q = 0; q < NS; ++q) {
             acc[0][q] = sigmoid_f(acc[0][q]);
@@ -389,29 +390,40 @@ __global__ void __launch_bounds__(128) lstm_train_bwd2_kernel(const LstmTrain a)
     for (int i = 0; i < 2; ++i) { valid[i] = r0 + q0 + 2 * i < a.R; row[i] = min(r0 + q0 + 2 * i, a.R - 1); }
     pdl_wait();
     __syncthreads();
-    float dc[2] = {0.f, 0.f};
-    int se = d ? 0 : S - 1;
-    float gi[2], gf[2], gg[2], go[2], ct[2], cp[2], dhv[2];
+    // processed step p (p = 0 is the last step of the forward recurrence) sits at position se(p) of its sequence.
+    // Register pipeline two steps deep: the loads of step p + 2 are issued while step p is worked on.
+    auto nof = [&](int i, int p) { return row[i] * S + (d ? p : S - 1 - p); };
+    struct Stage { float gi, gf, gg, go, dh; };
+    Stage cur[2], nxt[2];
+    float c0[2], c1[2], c2[2], dc[2] = {0.f, 0.f};
+    auto load_stage = [&](Stage& st, int i, int p) {
+        const long long n = nof(i, p);
+        st.gi = gates[n * 4 * H + u]; st.gf = gates[n * 4 * H + H + u]; st.gg = gates[n * 4 * H + 2 * H + u]; st.go = gates[n * 4 * H + 3 * H + u];
+        st.dh = dh[n * H + u];
+    };
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const long long n = row[i] * S + se;
-        gi[i] = gates[n * 4 * H + u]; gf[i] = gates[n * 4 * H + H + u]; gg[i] = gates[n * 4 * H + 2 * H + u]; go[i] = gates[n * 4 * H + 3 * H + u];
-        ct[i] = cc[n * H + u]; dhv[i] = dh[n * H + u];
-        cp[i] = S > 1 ? cc[(d ? n + 1 : n - 1) * H + u] : 0.f;
+        load_stage(cur[i], i, 0);
+        nxt[i] = cur[i];
+        if (S > 1) load_stage(nxt[i], i, 1);
+        c0[i] = cc[nof(i, 0) * H + u];
+        c1[i] = S > 1 ? cc[nof(i, 1) * H + u] : 0.f;
+        c2[i] = S > 2 ? cc[nof(i, 2) * H + u] : 0.f;
     }
     for (int s = 0; s < S; ++s) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int q = q0 + 2 * i;
-            const long long n = row[i] * S + se;
-            const float dht = dhv[i] + ((part_s[0][q][u] + part_s[1][q][u]) + (part_s[2][q][u] + part_s[3][q][u]));
-            const float tc = tanh_f(ct[i]);
-            const float dcv = fmaf(dht * go[i], 1.f - tc * tc, dc[i]);
-            const float dzi = dcv * gg[i] * gi[i] * (1.f - gi[i]);
-            const float dzf = dcv * cp[i] * gf[i] * (1.f - gf[i]);
-            const float dzg = dcv * gi[i] * (1.f - gg[i] * gg[i]);
-            const float dzo = dht * tc * go[i] * (1.f - go[i]);
-            dc[i] = dcv * gf[i];
+            const long long n = nof(i, s);
+            const Stage g = cur[i];
+            const float dht = g.dh + ((part_s[0][q][u] + part_s[1][q][u]) + (part_s[2][q][u] + part_s[3][q][u]));
+            const float tc = tanh_f(c0[i]);
+            const float dcv = fmaf(dht * g.go, 1.f - tc * tc, dc[i]);
+            const float dzi = dcv * g.gg * g.gi * (1.f - g.gi);
+            const float dzf = dcv * c1[i] * g.gf * (1.f - g.gf);
+            const float dzg = dcv * g.gi * (1.f - g.gg * g.gg);
+            const float dzo = dht * tc * g.go * (1.f - g.go);
+            dc[i] = dcv * g.gf;
             reinterpret_cast<float*>(&dz_s[u])[q] = dzi;
             reinterpret_cast<float*>(&dz_s[H + u])[q] = dzf;
             reinterpret_cast<float*>(&dz_s[2 * H + u])[q] = dzg;
@@ -419,30 +431,24 @@ __global__ void __launch_bounds__(128) lstm_train_bwd2_kernel(const LstmTrain a)
             if (valid[i]) {
                 gates[n * 4 * H + u] = dzi; gates[n * 4 * H + H + u] = dzf; gates[n * 4 * H + 2 * H + u] = dzg; gates[n * 4 * H + 3 * H + u] = dzo;
             }
-        }
-        if (s + 1 < S) {
-            se = d ? se + 1 : se - 1;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const long long n = row[i] * S + se;
-                gi[i] = gates[n * 4 * H + u]; gf[i] = gates[n * 4 * H + H + u]; gg[i] = gates[n * 4 * H + 2 * H + u]; go[i] = gates[n * 4 * H + 3 * H + u];
-                ct[i] = cp[i];
-                dhv[i] = dh[n * H + u];
-                cp[i] = s + 2 < S ? cc[(d ? n + 1 : n - 1) * H + u] : 0.f;
-            }
+            cur[i] = nxt[i];
+            c0[i] = c1[i];
+            c1[i] = c2[i];
+            if (s + 2 < S) load_stage(nxt[i], i, s + 2);
+            c2[i] = s + 3 < S ? cc[nof(i, s + 3) * H + u] : 0.f;
         }
         __syncthreads();
-        float p[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float2 p[2][2] = {{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}};
 #pragma unroll
-        for (int j = 0; j < H; ++j) {
+        for (int j = 0; j < H; ++j) {               // one broadcast LDS.128 -> 4 packed FFMA2 = 8 FMA
             const float4 v = dz_s[qtr * H + j];
-            p[0][0] = fmaf(wq[0][j], v.x, p[0][0]); p[0][1] = fmaf(wq[0][j], v.y, p[0][1]);
-            p[0][2] = fmaf(wq[0][j], v.z, p[0][2]); p[0][3] = fmaf(wq[0][j], v.w, p[0][3]);
-            p[1][0] = fmaf(wq[1][j], v.x, p[1][0]); p[1][1] = fmaf(wq[1][j], v.y, p[1][1]);
-            p[1][2] = fmaf(wq[1][j], v.z, p[1][2]); p[1][3] = fmaf(wq[1][j], v.w, p[1][3]);
+            ffma2(p[0][0], make_float2(v.x, v.y), wq[0][j]);
+            ffma2(p[0][1], make_float2(v.z, v.w), wq[0][j]);
+            ffma2(p[1][0], make_float2(v.x, v.y), wq[1][j]);
+            ffma2(p[1][1], make_float2(v.z, v.w), wq[1][j]);
         }
-#pragma unroll
-        for (int q = 0; q < NS; ++q) { part_s[qtr][q][kp] = p[0][q]; part_s[qtr][q][kp + 32] = p[1][q]; }
+        part_s[qtr][0][kp] = p[0][0].x; part_s[qtr][1][kp] = p[0][0].y; part_s[qtr][2][kp] = p[0][1].x; part_s[qtr][3][kp] = p[0][1].y;
+        part_s[qtr][0][kp + 32] = p[1][0].x; part_s[qtr][1][kp + 32] = p[1][0].y; part_s[qtr][2][kp + 32] = p[1][1].x; part_s[qtr][3][kp + 32] = p[1][1].y;
         __syncthreads();
     }
 }
