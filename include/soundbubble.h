@@ -351,7 +351,7 @@ int    sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first
 /* parameters in their CHECKPOINT layouts (they change every step, so nothing is re-packed), keep what the backward  */
 /* pass needs in a caller-owned `saved` buffer and ACCUMULATE (+=) into the caller's gradient buffers with fp32      */
 /* atomics (zero them first; summation order, hence the last bits, vary from run to run).  Plain BiLSTM / LSTM       */
-/* blocks only: conv_lstm and use_attn models have no backward kernels yet.                                          */
+/* blocks and the conv-LSTM intra path; use_attn models have no backward kernels yet.                                 */
 /* ========================================================================================================== */
 
 /* One recurrent path of a GridNet block:  y = x + Linear(LSTM(LayerNorm_C(x))).                                     */
@@ -392,6 +392,43 @@ typedef struct sb_path_bwd_args {
 size_t sb_path_bwd_workspace_floats(int B, int T, int F, int C, int H, int inter);
 int    sb_intra_lstm_bwd(const sb_path_bwd_args* a, void* stream);
 int    sb_inter_lstm_bwd(const sb_path_bwd_args* a, void* stream);
+
+/* The conv-LSTM intra-frame path (a9', DE3:800-815 / OPT:684-697, 494-510) for training:                              */
+/*   y = x + tail(ConvTranspose1d(BiLSTM(LayerNorm(PReLU(Conv1d(x))))))   with k = s = down over frequency.               */
+/*   conv_w [C][C][down], deconv_w [2H][C][down], prelu [1], ln_* = blocks.i.norm.norm, all as stored in the checkpoint.  */
+/*   saved: sb_convpath_train_saved_floats(); the backward call consumes it.  FiLM is applied before (sb_film_apply_*).  */
+typedef struct sb_convpath_train_args {
+    const float* x;             /* [B][T][F][C] */
+    float*       y;             /* [B][T][F][C]; must not alias x */
+    const float* conv_w;
+    const float* conv_b;
+    const float* prelu;
+    const float* ln_g;
+    const float* ln_b;
+    const float* w_ih[2];
+    const float* w_hh[2];
+    const float* b_ih[2];
+    const float* b_hh[2];
+    const float* deconv_w;
+    const float* deconv_b;
+    float*       saved;
+    int B, T, F, C, H;
+    int down, tail_mode;        /* SB_CONVLSTM_PADCROP / SB_CONVLSTM_OUTPAD */
+} sb_convpath_train_args;
+size_t sb_convpath_train_saved_floats(int B, int T, int F, int C, int H, int down);
+int    sb_intra_convlstm_train_fwd(const sb_convpath_train_args* a, void* stream);
+
+typedef struct sb_convpath_bwd_args {
+    sb_convpath_train_args f;   /* the forward call's arguments (x = the forward input, y unused) */
+    const float* gy;            /* [B][T][F][C] */
+    float*       gx;            /* [B][T][F][C]; may alias gy */
+    float* g_conv_w; float* g_conv_b; float* g_prelu; float* g_ln_g; float* g_ln_b;
+    float* g_w_ih[2]; float* g_w_hh[2]; float* g_b_ih[2]; float* g_b_hh[2];
+    float* g_deconv_w; float* g_deconv_b;
+    float* ws;                  /* sb_convpath_bwd_workspace_floats() floats */
+} sb_convpath_bwd_args;
+size_t sb_convpath_bwd_workspace_floats(int B, int T, int F, int C, int H, int down);
+int    sb_intra_convlstm_bwd(const sb_convpath_bwd_args* a, void* stream);
 
 /* FilmLayer.forward (DE3:51-68, :509-513) as its own stage: y = x * scale[b,f,c] + shift[b,f,c]; the backward also    */
 /* accumulates dL/dscale, dL/dshift [B][F][C] (sums over frames), which sb_film_params_bwd turns into parameter grads.*/
@@ -524,7 +561,7 @@ uint64_t    sb_launch_count(void);
 /* sizeof() of the structs above as compiled, so the ctypes mirror can be checked without a GPU                 */
 /*   0 lstm_dir 1 stft 2 conv_in 3 film 4 intra 5 inter 6 backend 7 net_desc 8 net_io 9 intra_conv 10 attn_proj */
 /*   11 attn 12 block_desc 13 prepare 14 path_train 15 path_bwd 16 film_apply 17 film_bwd 18 conv_in_train     */
-/*   19 backend_bwd                                                                                            */
+/*   19 backend_bwd 20 convpath_train 21 convpath_bwd                                                          */
 int         sb_abi_sizeof(int which);
 
 #ifdef __cplusplus

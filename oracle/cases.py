@@ -54,3 +54,9 @@ GRAD_CASES = {
     # the OPT variant (no distance embedding) at D = 16 with plain BiLSTM blocks
     "grad_opi_d16": dict(variant="optim", kwargs=_with(OPI, B=1, D=16), batch=1, n_samples=192 * 3, loss_seed=78),
 }
+GRAD_CASES.update({
+    # the Raspberry-Pi model (conv-LSTM intra path with output_padding, k = 5, D = 16, 3 blocks): BASELINE config 5's model
+    "grad_rpi": dict(variant="optim", kwargs=RPI, batch=2, n_samples=192 * 3 - 11, loss_seed=79),
+    # DE3 conv-LSTM (pad-and-crop tail, k = 4, D = 32) with FiLM, 2 blocks
+    "grad_syn_convlstm": dict(variant="dis_embed", kwargs=_with(SYN, conv_lstm=True, B=2), batch=1, n_samples=192 * 3, loss_seed=80),
+})

@@ -161,10 +161,26 @@ class BackendBwdArgs(C.Structure):
                 ("n_fft", C.c_int), ("stride", C.c_int)]
 
 
+class ConvPathTrainArgs(C.Structure):
+    _fields_ = [("x", fp), ("y", fp), ("conv_w", fp), ("conv_b", fp), ("prelu", fp), ("ln_g", fp), ("ln_b", fp),
+                ("w_ih", fp * 2), ("w_hh", fp * 2), ("b_ih", fp * 2), ("b_hh", fp * 2),
+                ("deconv_w", fp), ("deconv_b", fp), ("saved", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("H", C.c_int),
+                ("down", C.c_int), ("tail_mode", C.c_int)]
+
+
+class ConvPathBwdArgs(C.Structure):
+    _fields_ = [("f", ConvPathTrainArgs), ("gy", fp), ("gx", fp),
+                ("g_conv_w", fp), ("g_conv_b", fp), ("g_prelu", fp), ("g_ln_g", fp), ("g_ln_b", fp),
+                ("g_w_ih", fp * 2), ("g_w_hh", fp * 2), ("g_b_ih", fp * 2), ("g_b_hh", fp * 2),
+                ("g_deconv_w", fp), ("g_deconv_b", fp), ("ws", fp)]
+
+
 # index used by sb_abi_sizeof(which)
 ABI_STRUCTS = {0: LstmDir, 1: StftArgs, 2: ConvInArgs, 3: FilmArgs, 4: IntraArgs, 5: InterArgs, 6: BackendArgs,
                7: NetDesc, 8: NetIO, 9: IntraConvArgs, 10: AttnProj, 11: AttnArgs, 12: BlockDesc, 13: PrepareArgs,
-               14: PathTrainArgs, 15: PathBwdArgs, 16: FilmApplyArgs, 17: FilmBwdArgs, 18: ConvInTrainArgs, 19: BackendBwdArgs}
+               14: PathTrainArgs, 15: PathBwdArgs, 16: FilmApplyArgs, 17: FilmBwdArgs, 18: ConvInTrainArgs, 19: BackendBwdArgs,
+               20: ConvPathTrainArgs, 21: ConvPathBwdArgs}
 
 # every symbol include/soundbubble.h declares: name -> (restype, argtypes)
 PROTOTYPES = {
@@ -189,6 +205,10 @@ PROTOTYPES = {
     "sb_inter_lstm_train_fwd": (C.c_int, [C.POINTER(PathTrainArgs), C.c_void_p]),
     "sb_intra_lstm_bwd": (C.c_int, [C.POINTER(PathBwdArgs), C.c_void_p]),
     "sb_inter_lstm_bwd": (C.c_int, [C.POINTER(PathBwdArgs), C.c_void_p]),
+    "sb_convpath_train_saved_floats": (C.c_size_t, [C.c_int] * 6),
+    "sb_convpath_bwd_workspace_floats": (C.c_size_t, [C.c_int] * 6),
+    "sb_intra_convlstm_train_fwd": (C.c_int, [C.POINTER(ConvPathTrainArgs), C.c_void_p]),
+    "sb_intra_convlstm_bwd": (C.c_int, [C.POINTER(ConvPathBwdArgs), C.c_void_p]),
     "sb_film_apply_fwd": (C.c_int, [C.POINTER(FilmApplyArgs), C.c_void_p]),
     "sb_film_apply_bwd": (C.c_int, [C.POINTER(FilmApplyArgs), C.c_void_p]),
     "sb_film_params_bwd": (C.c_int, [C.POINTER(FilmBwdArgs), C.c_void_p]),

@@ -119,6 +119,8 @@ extern "C" int sb_abi_sizeof(int which) {
         case 17: return (int)sizeof(sb_film_bwd_args);
         case 18: return (int)sizeof(sb_conv_in_train_args);
         case 19: return (int)sizeof(sb_backend_bwd_args);
+        case 20: return (int)sizeof(sb_convpath_train_args);
+        case 21: return (int)sizeof(sb_convpath_bwd_args);
         default: return -1;
     }
 }

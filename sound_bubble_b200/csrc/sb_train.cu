@@ -988,6 +988,292 @@ __global__ void __launch_bounds__(320) deconv_wgrad_kernel(const sb_backend_bwd_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// conv-LSTM intra-frame path for training (a9': DE3 :800-815, OPT :684-697 with the deconv of :494-510):
+//   x -> Conv1d(C -> C, k = s = down) over frequency -> PReLU -> LayerNorm(C) -> BiLSTM over J steps
+//     -> ConvTranspose1d(2H -> C, k = s = down) -> (pad & crop | output_padding) -> + x
+// k = s: the convolution is a per-group linear map, group n' = (b, t, j) covering bins j*k .. j*k + k - 1.
+// ------------------------------------------------------------------------------------------------------------
+struct ConvPath {
+    const float* x;             // [B*T][F][C]
+    const float* conv_w;        // [C][C][k]   (o, c, tap) as stored
+    const float* conv_b;
+    const float* deconv_w;      // [2H][C][k]  (d*H + u, c, tap) as stored
+    const float* deconv_b;
+    int BT, F, C, J, k, outpad;
+};
+
+// zraw[n'][o] = conv_b[o] + sum_{tap, c} x[bt][j*k + tap][c] * conv_w[o][c][tap]; thread = (group, 8 outputs)
+template <int C>
+__global__ void __launch_bounds__(256) convpre_train_kernel(const ConvPath a, float* zraw) {
+    SB_DYN_SMEM(float, w_s);                        // [tap][c][o]
+    const int k = a.k, tid = threadIdx.x;
+    for (int i = tid; i < k * C * C; i += 256) {
+        const int o = i % C, c = (i / C) % C, tap = i / (C * C);
+        w_s[i] = __ldg(a.conv_w + ((size_t)o * C + c) * k + tap);
+    }
+    pdl_wait();
+    __syncthreads();
+    constexpr int TPR = C / 8;
+    const long long N = (long long)a.BT * a.J;
+    const long long n = (long long)blockIdx.x * (256 / TPR) + tid / TPR;
+    if (n >= N) return;
+    const int o0 = (tid % TPR) * 8;
+    const long long bt = n / a.J;
+    const int j = (int)(n - bt * a.J);
+    const float* xr = a.x + ((size_t)bt * a.F + (size_t)j * k) * C;       // k*C contiguous floats
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = __ldg(a.conv_b + o0 + i);
+    for (int q = 0; q < k * C; ++q) {
+        const float v = __ldg(xr + q);
+        const float4 w0 = ld4(w_s + q * C + o0), w1 = ld4(w_s + q * C + o0 + 4);
+        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    }
+    st4(zraw + n * C + o0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(zraw + n * C + o0 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+__global__ void __launch_bounds__(256) prelu_fwd_kernel(const float* z, const float* slope, float* out, long long n4) {
+    pdl_wait();
+    const float a = __ldg(slope);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        float4 v = ldg4_stream(z + 4 * i);
+        v.x = v.x > 0.f ? v.x : a * v.x; v.y = v.y > 0.f ? v.y : a * v.y; v.z = v.z > 0.f ? v.z : a * v.z; v.w = v.w > 0.f ? v.w : a * v.w;
+        st4(out + 4 * i, v);
+    }
+}
+
+// in place: g <- g * (z > 0 ? 1 : slope);  dL/dslope += sum g * z over z <= 0
+__global__ void __launch_bounds__(256) prelu_bwd_kernel(float* g, const float* z, const float* slope, float* g_slope, long long n) {
+    __shared__ float red[8];
+    pdl_wait();
+    const float a = __ldg(slope);
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float zv = z[i], gv = g[i];
+        if (zv > 0.f) continue;
+        acc = fmaf(gv, zv, acc);
+        g[i] = gv * a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        atomic_add(g_slope, t);
+    }
+}
+
+// y[bt][f][c] = x + (f < J*k ? deconv_b[c] + sum_{d,u} h_d[n'][u] * deconv_w[d*H+u][c][tap] : tail); thread = (position, 8 channels)
+template <int C>
+__global__ void __launch_bounds__(256) convpost_train_kernel(const ConvPath a, const float* h0, const float* h1, float* y) {
+    SB_DYN_SMEM(float, w_s);                        // [tap][2H][c]
+    constexpr int H = kH;
+    const int k = a.k, tid = threadIdx.x;
+    for (int i = tid; i < k * 2 * H * C; i += 256) {
+        const int c = i % C, du = (i / C) % (2 * H), tap = i / (C * 2 * H);
+        w_s[i] = __ldg(a.deconv_w + ((size_t)du * C + c) * k + tap);
+    }
+    pdl_wait();
+    __syncthreads();
+    constexpr int TPR = C / 8;
+    const long long N = (long long)a.BT * a.F;
+    const long long n = (long long)blockIdx.x * (256 / TPR) + tid / TPR;
+    if (n >= N) return;
+    const int c0 = (tid % TPR) * 8;
+    const long long bt = n / a.F;
+    const int f = (int)(n - bt * a.F);
+    float acc[8];
+    const float4 x0 = ldg4_stream(a.x + n * C + c0), x1 = ldg4_stream(a.x + n * C + c0 + 4);
+    acc[0] = x0.x; acc[1] = x0.y; acc[2] = x0.z; acc[3] = x0.w; acc[4] = x1.x; acc[5] = x1.y; acc[6] = x1.z; acc[7] = x1.w;
+    if (f < a.J * k || a.outpad) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __ldg(a.deconv_b + c0 + i);
+    }
+    if (f < a.J * k) {
+        const int j = f / k, tap = f - j * k;
+        const long long np = bt * a.J + j;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const float* hr = (d ? h1 : h0) + np * H;
+            const float* wr = w_s + ((size_t)tap * 2 * H + d * H) * C + c0;
+            for (int u = 0; u < H; ++u) {
+                const float v = hr[u];
+                const float4 w0 = ld4(wr + u * C), w1 = ld4(wr + u * C + 4);
+                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+            }
+        }
+    }
+    st4(y + n * C + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(y + n * C + c0 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// dL/dh_d[n'][u] = sum_{tap, c} gy[bt][j*k + tap][c] * deconv_w[d*H+u][c][tap]; thread = (group, 8 of the 2H units)
+template <int C>
+__global__ void __launch_bounds__(256) convpost_dh_kernel(const ConvPath a, const float* gy, float* dh0, float* dh1) {
+    SB_DYN_SMEM(float, w_s);                        // [tap][c][2H]
+    constexpr int H = kH;
+    const int k = a.k, tid = threadIdx.x;
+    for (int i = tid; i < k * C * 2 * H; i += 256) {
+        const int du = i % (2 * H), c = (i / (2 * H)) % C, tap = i / (2 * H * C);
+        w_s[i] = __ldg(a.deconv_w + ((size_t)du * C + c) * k + tap);
+    }
+    pdl_wait();
+    __syncthreads();
+    const long long N = (long long)a.BT * a.J;
+    const long long n = (long long)blockIdx.x * 16 + tid / 16;
+    if (n >= N) return;
+    const int u0 = (tid % 16) * 8;                  // 0 .. 127 over both directions
+    const long long bt = n / a.J;
+    const int j = (int)(n - bt * a.J);
+    const float* gr = gy + ((size_t)bt * a.F + (size_t)j * k) * C;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < k * C; ++q) {
+        const float v = gr[q];
+        const float4 w0 = ld4(w_s + q * 2 * H + u0), w1 = ld4(w_s + q * 2 * H + u0 + 4);
+        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    }
+    float* out = (u0 < H ? dh0 + n * H + u0 : dh1 + n * H + (u0 - H));
+    st4(out, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(out + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// dL/ddeconv_w[du][c][tap] += sum_{n'} h[n'][du] * gy[bt][j*k+tap][c];  dL/ddeconv_b[c] += sum over the bins that receive
+// the bias.  Thread = (tap, c) with 2H accumulators; the h rows of 8 groups are staged in shared memory.
+template <int C>
+__global__ void __launch_bounds__(256) convpost_wgrad_kernel(const ConvPath a, const float* gy, const float* h0, const float* h1,
+                                                            float* g_w, float* g_b, long long groups_per_cta) {
+    constexpr int H = kH, RB = 8;
+    __shared__ __align__(16) float h_s[RB][2 * H];
+    const int k = a.k, tid = threadIdx.x;
+    const bool worker = tid < k * C;
+    const int tap = worker ? tid / C : 0, c = worker ? tid - tap * C : 0;
+    const long long N = (long long)a.BT * a.J;
+    const long long n_begin = (long long)blockIdx.x * groups_per_cta;
+    const long long n_end = n_begin + groups_per_cta < N ? n_begin + groups_per_cta : N;
+    float acc[2 * H], accb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * H; ++i) acc[i] = 0.f;
+    pdl_wait();
+    for (long long n0 = n_begin; n0 < n_end; n0 += RB) {
+        __syncthreads();
+        for (int i = tid; i < RB * 2 * H / 4; i += 256) {
+            const int r = i / (2 * H / 4), q = i - r * (2 * H / 4);
+            const long long n = n0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < n_end) v = q < H / 4 ? ldg4_stream(h0 + n * H + 4 * q) : ldg4_stream(h1 + n * H + 4 * (q - H / 4));
+            st4(&h_s[r][4 * q], v);
+        }
+        __syncthreads();
+        if (worker) {
+            for (int r = 0; r < RB; ++r) {
+                const long long n = n0 + r;
+                if (n >= n_end) break;
+                const long long bt = n / a.J;
+                const int j = (int)(n - bt * a.J);
+                const float g = __ldg(gy + ((size_t)bt * a.F + (size_t)j * k + tap) * C + c);
+                accb += g;
+                if (a.outpad && tap == 0 && j == a.J - 1)          // output_padding bins receive the bias only
+                    for (int f = a.J * k; f < a.F; ++f) accb += __ldg(gy + ((size_t)bt * a.F + f) * C + c);
+#pragma unroll
+                for (int i = 0; i < 2 * H; i += 4) {
+                    const float4 hv = ld4(&h_s[r][i]);
+                    acc[i] = fmaf(g, hv.x, acc[i]); acc[i + 1] = fmaf(g, hv.y, acc[i + 1]);
+                    acc[i + 2] = fmaf(g, hv.z, acc[i + 2]); acc[i + 3] = fmaf(g, hv.w, acc[i + 3]);
+                }
+            }
+        }
+    }
+    if (worker) {
+#pragma unroll
+        for (int i = 0; i < 2 * H; ++i) atomic_add(g_w + ((size_t)i * C + c) * k + tap, acc[i]);
+        atomic_add(g_b + c, accb);
+    }
+}
+
+// dL/dx[bt][f][c] = gy + (f < J*k ? sum_o dz[n'][o] * conv_w[o][c][tap] : 0); thread = (position, 8 channels)
+template <int C>
+__global__ void __launch_bounds__(256) convpre_bwd_x_kernel(const ConvPath a, const float* gy, const float* dz, float* gx) {
+    SB_DYN_SMEM(float, w_s);                        // [tap][o][c]
+    const int k = a.k, tid = threadIdx.x;
+    for (int i = tid; i < k * C * C; i += 256) {
+        const int c = i % C, o = (i / C) % C, tap = i / (C * C);
+        w_s[i] = __ldg(a.conv_w + ((size_t)o * C + c) * k + tap);
+    }
+    pdl_wait();
+    __syncthreads();
+    constexpr int TPR = C / 8;
+    const long long N = (long long)a.BT * a.F;
+    const long long n = (long long)blockIdx.x * (256 / TPR) + tid / TPR;
+    if (n >= N) return;
+    const int c0 = (tid % TPR) * 8;
+    const long long bt = n / a.F;
+    const int f = (int)(n - bt * a.F);
+    const float4 g0 = ld_plain4(gy + n * C + c0), g1 = ld_plain4(gy + n * C + c0 + 4);
+    float acc[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    if (f < a.J * k) {
+        const int j = f / k, tap = f - j * k;
+        const float* zr = dz + (bt * a.J + j) * C;
+        const float* wr = w_s + (size_t)tap * C * C + c0;
+        for (int o = 0; o < C; ++o) {
+            const float v = zr[o];
+            const float4 w0 = ld4(wr + o * C), w1 = ld4(wr + o * C + 4);
+            acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+            acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+    }
+    st4(gx + n * C + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    st4(gx + n * C + c0 + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// dL/dconv_w[o][c][tap] += sum_{n'} dz[n'][o] * x[bt][j*k+tap][c];  dL/dconv_b[o] += sum dz[n'][o].  Thread = (tap, c).
+template <int C>
+__global__ void __launch_bounds__(256) convpre_wgrad_kernel(const ConvPath a, const float* dz, float* g_w, float* g_b, long long groups_per_cta) {
+    constexpr int RB = 32;
+    __shared__ __align__(16) float g_s[RB][C];
+    const int k = a.k, tid = threadIdx.x;
+    const bool worker = tid < k * C;
+    const int tap = worker ? tid / C : 0, c = worker ? tid - tap * C : 0;
+    const long long N = (long long)a.BT * a.J;
+    const long long n_begin = (long long)blockIdx.x * groups_per_cta;
+    const long long n_end = n_begin + groups_per_cta < N ? n_begin + groups_per_cta : N;
+    float acc[C], accb = 0.f;
+#pragma unroll
+    for (int o = 0; o < C; ++o) acc[o] = 0.f;
+    pdl_wait();
+    for (long long n0 = n_begin; n0 < n_end; n0 += RB) {
+        __syncthreads();
+        for (int i = tid; i < RB * C / 4; i += 256) {
+            const long long n = n0 + i / (C / 4);
+            st4(&g_s[0][0] + 4 * i, n < n_end ? ldg4_stream(dz + n * C + 4 * (i % (C / 4))) : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        __syncthreads();
+        if (worker) {
+            for (int r = 0; r < RB; ++r) {
+                const long long n = n0 + r;
+                if (n >= n_end) break;
+                const long long bt = n / a.J;
+                const int j = (int)(n - bt * a.J);
+                const float v = __ldg(a.x + ((size_t)bt * a.F + (size_t)j * k + tap) * C + c);
+#pragma unroll
+                for (int o = 0; o < C; ++o) acc[o] = fmaf(v, g_s[r][o], acc[o]);
+            }
+        }
+        if (tid < C)
+            for (int r = 0; r < RB; ++r) accb += g_s[r][tid];
+    }
+    if (worker)
+#pragma unroll
+        for (int o = 0; o < C; ++o) atomic_add(g_w + ((size_t)o * C + c) * k + tap, acc[o]);
+    if (tid < C) atomic_add(g_b + tid, accb);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 struct PathDims {
@@ -1142,6 +1428,123 @@ static int check_path_bwd(const sb_path_bwd_args* p, int inter, const char* who)
     return 0;
 }
 
+// ---- conv-LSTM intra path ---------------------------------------------------------------------------------
+struct ConvSaved {
+    float *zraw, *pz, *xhat, *xn, *rstd, *gates[2], *c[2], *h[2];
+};
+static ConvSaved conv_saved_view(const sb_convpath_train_args& a, long long NP) {
+    ConvSaved v{};
+    float* p = a.saved;
+    v.zraw = p; p += NP * a.C;
+    v.pz = p; p += NP * a.C;
+    v.xhat = p; p += NP * a.C;
+    v.xn = p; p += NP * a.C;
+    v.rstd = p; p += (NP + 3) / 4 * 4;
+    for (int k = 0; k < 2; ++k) {
+        v.gates[k] = p; p += NP * 4 * a.H;
+        v.c[k] = p; p += NP * a.H;
+        v.h[k] = p; p += NP * a.H;
+    }
+    return v;
+}
+static ConvPath conv_path_of(const sb_convpath_train_args& a) {
+    ConvPath c{};
+    c.x = a.x; c.conv_w = a.conv_w; c.conv_b = a.conv_b; c.deconv_w = a.deconv_w; c.deconv_b = a.deconv_b;
+    c.BT = a.B * a.T; c.F = a.F; c.C = a.C; c.k = a.down; c.J = (a.F - a.down) / a.down + 1;
+    c.outpad = a.tail_mode == SB_CONVLSTM_OUTPAD;
+    return c;
+}
+static int check_convpath(const sb_convpath_train_args* p, const char* who) {
+    SB_REQUIRE(p && p->x && p->conv_w && p->conv_b && p->prelu && p->ln_g && p->ln_b && p->deconv_w && p->deconv_b && p->saved,
+               SB_E_BADARG, "%s: null pointer", who);
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0, SB_E_BADARG, "%s: bad sizes", who);
+    SB_REQUIRE(p->C == 16 || p->C == 32, SB_E_UNSUPP, "%s: C must be 16 or 32 (got %d)", who, p->C);
+    SB_REQUIRE(p->H == kH, SB_E_UNSUPP, "%s: H must be 64 (got %d)", who, p->H);
+    SB_REQUIRE(p->down >= 1 && p->down <= p->F && p->down * p->C <= 256, SB_E_UNSUPP, "%s: unsupported lstm_down %d", who, p->down);
+    const int J = (p->F - p->down) / p->down + 1;
+    SB_REQUIRE(p->tail_mode == SB_CONVLSTM_OUTPAD || p->F - J * p->down <= 3, SB_E_UNSUPP,
+               "%s: pad-and-crop tail covers at most 3 bins (F=%d, down=%d)", who, p->F, p->down);
+    for (int d = 0; d < 2; ++d)
+        SB_REQUIRE(p->w_ih[d] && p->w_hh[d] && p->b_ih[d] && p->b_hh[d], SB_E_BADARG, "%s: null LSTM parameter", who);
+    return 0;
+}
+
+template <int C>
+static int convpath_fwd(const sb_convpath_train_args& a, cudaStream_t st) {
+    const ConvPath cp = conv_path_of(a);
+    const long long NP = (long long)cp.BT * cp.J, N = (long long)cp.BT * cp.F;
+    const ConvSaved v = conv_saved_view(a, NP);
+    constexpr int RPC = 256 / (C / 8);
+    SB_CHECK(launch("convpre_train", convpre_train_kernel<C>, dim3((unsigned)ceil_div_ll(NP, RPC)), dim3(256),
+                    (size_t)cp.k * C * C * sizeof(float), st, cp, v.zraw));
+    const long long n4 = NP * C / 4;
+    const unsigned ge = (unsigned)(ceil_div_ll(n4, 256) < 8LL * sm_count() ? ceil_div_ll(n4, 256) : 8LL * sm_count());
+    SB_CHECK(launch("prelu_fwd", prelu_fwd_kernel, dim3(ge), dim3(256), 0, st, (const float*)v.zraw, a.prelu, v.pz, n4));
+    const RowMap ident{cp.J, cp.F, 0};
+    SB_CHECK(launch("ln_fwd", ln_fwd_kernel<C>, dim3((unsigned)ceil_div_ll(NP, 256)), dim3(256), 0, st, (const float*)v.pz, ident, a.ln_g,
+                    a.ln_b, v.xhat, v.xn, v.rstd, NP, 1e-5f));
+    LstmTrain l{};
+    l.xn = v.xn;
+    for (int k = 0; k < 2; ++k) {
+        l.w_ih[k] = a.w_ih[k]; l.w_hh[k] = a.w_hh[k]; l.b_ih[k] = a.b_ih[k]; l.b_hh[k] = a.b_hh[k];
+        l.gates[k] = v.gates[k]; l.c[k] = v.c[k]; l.h[k] = v.h[k];
+    }
+    l.R = cp.BT; l.S = cp.J;
+    const dim3 grid((unsigned)ceil_div(cp.BT, 4), 2);
+    if (C == 32 && !train_one_row_enabled()) SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd2_kernel<32>, grid, dim3(128), 0, st, l));
+    else SB_CHECK(launch("lstm_train_fwd", lstm_train_fwd_kernel<C>, grid, dim3(256), 0, st, l));
+    return launch("convpost_train", convpost_train_kernel<C>, dim3((unsigned)ceil_div_ll(N, RPC)), dim3(256),
+                  (size_t)cp.k * 2 * kH * C * sizeof(float), st, cp, (const float*)v.h[0], (const float*)v.h[1], a.y);
+}
+
+template <int C>
+static int convpath_bwd(const sb_convpath_bwd_args& b, cudaStream_t st) {
+    const sb_convpath_train_args& a = b.f;
+    const ConvPath cp = conv_path_of(a);
+    const long long NP = (long long)cp.BT * cp.J, N = (long long)cp.BT * cp.F;
+    const ConvSaved v = conv_saved_view(a, NP);
+    float* dh[2] = {b.ws, b.ws + NP * a.H};
+    float* dxn = b.ws + 2 * NP * a.H;
+    const size_t smem_d = (size_t)cp.k * 2 * kH * C * sizeof(float);
+    SB_CHECK(launch("convpost_dh", convpost_dh_kernel<C>, dim3((unsigned)ceil_div_ll(NP, 16)), dim3(256), smem_d, st, cp, b.gy, dh[0], dh[1]));
+    const long long gpc = reduction_rows(NP, 8);
+    SB_CHECK(launch("convpost_wgrad", convpost_wgrad_kernel<C>, dim3((unsigned)ceil_div_ll(NP, gpc)), dim3(256), 0, st, cp, b.gy,
+                    (const float*)v.h[0], (const float*)v.h[1], b.g_deconv_w, b.g_deconv_b, gpc));
+    LstmTrain l{};
+    for (int k = 0; k < 2; ++k) { l.w_hh[k] = a.w_hh[k]; l.gates[k] = v.gates[k]; l.c[k] = v.c[k]; l.dh[k] = dh[k]; }
+    l.R = cp.BT; l.S = cp.J;
+    const dim3 grid((unsigned)ceil_div(cp.BT, 4), 2);
+    if (train_one_row_enabled()) SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd_kernel, grid, dim3(256), 0, st, l));
+    else SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd2_kernel, grid, dim3(128), 0, st, l));
+    const RowMap ident{cp.J, cp.F, 0};
+    for (int k = 0; k < 2; ++k) {
+        Outer o{};
+        o.A = v.gates[k]; o.map = ident; o.a_mapped = 0; o.reverse = k; o.N = NP;
+        o.Bm = v.xn; o.b_mode = 0; o.kc0 = C; o.dW = b.g_w_ih[k]; o.ldw = C; o.db = b.g_b_ih[k]; o.db2 = b.g_b_hh[k];
+        o.Bm2 = v.h[k]; o.dW2 = b.g_w_hh[k]; o.ldw2 = a.H;
+        if (C == 32) SB_CHECK((run_outer<256, 96, 8, 12>(o, st, "lstm_wgrad")));
+        else SB_CHECK((run_outer<256, 80, 8, 10>(o, st, "lstm_wgrad")));
+    }
+    RowGemm g{};
+    g.nA = 2; g.K = 4 * a.H; g.lda = 4 * a.H; g.ldw = C; g.w_trans = 0;
+    for (int k = 0; k < 2; ++k) { g.A[k] = v.gates[k]; g.W[k] = a.w_ih[k]; }
+    g.out = dxn; g.map = ident; g.a_mapped = 0; g.o_mapped = 0; g.N = NP;
+    SB_CHECK(rowgemm(g, C, st, "lstm_dx"));
+    // LayerNorm backward -> gradient of the PReLU output (written over the PReLU output slot), PReLU backward in place
+    const unsigned gl = (unsigned)(ceil_div_ll(NP, 256) < 2LL * sm_count() ? ceil_div_ll(NP, 256) : 2LL * sm_count());
+    SB_CHECK(launch("ln_bwd", ln_bwd_kernel<C>, dim3(gl), dim3(256), 0, st, (const float*)dxn, (const float*)v.xhat, (const float*)v.rstd, a.ln_g,
+                    (const float*)nullptr, v.pz, ident, b.g_ln_g, b.g_ln_b, NP));
+    const long long ne = NP * C;
+    const unsigned ge = (unsigned)(ceil_div_ll(ne, 256) < 4LL * sm_count() ? ceil_div_ll(ne, 256) : 4LL * sm_count());
+    SB_CHECK(launch("prelu_bwd", prelu_bwd_kernel, dim3(ge), dim3(256), 0, st, v.pz, (const float*)v.zraw, a.prelu, b.g_prelu, ne));
+    const long long gpc2 = reduction_rows(NP, 32);
+    SB_CHECK(launch("convpre_wgrad", convpre_wgrad_kernel<C>, dim3((unsigned)ceil_div_ll(NP, gpc2)), dim3(256), 0, st, cp, (const float*)v.pz,
+                    b.g_conv_w, b.g_conv_b, gpc2));
+    constexpr int RPC = 256 / (C / 8);
+    return launch("convpre_bwd_x", convpre_bwd_x_kernel<C>, dim3((unsigned)ceil_div_ll(N, RPC)), dim3(256), (size_t)cp.k * C * C * sizeof(float),
+                  st, cp, b.gy, (const float*)v.pz, b.gx);
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -1273,4 +1676,27 @@ extern "C" int sb_backend_bwd(const sb_backend_bwd_args* p, void* stream) {
     }
     SB_CHECK(launch("deconv_bwd_x", deconv_bwd_x_kernel<16>, dim3((unsigned)ceil_div_ll(N, 16)), dim3(256), 0, st, *p));
     return launch("deconv_wgrad", deconv_wgrad_kernel<16>, dim3((unsigned)ceil_div_ll(N, rows)), dim3(160), 0, st, *p, rows);
+}
+
+extern "C" size_t sb_convpath_train_saved_floats(int B, int T, int F, int C, int H, int down) {
+    const long long NP = (long long)B * T * ((F - down) / down + 1);
+    return (size_t)(4 * NP * C + (NP + 3) / 4 * 4 + 2 * NP * 6 * H);
+}
+extern "C" size_t sb_convpath_bwd_workspace_floats(int B, int T, int F, int C, int H, int down) {
+    const long long NP = (long long)B * T * ((F - down) / down + 1);
+    return (size_t)(2 * NP * H + NP * C);
+}
+extern "C" int sb_intra_convlstm_train_fwd(const sb_convpath_train_args* p, void* stream) {
+    SB_CHECK(check_convpath(p, "sb_intra_convlstm_train_fwd"));
+    SB_REQUIRE(p->y && p->y != p->x, SB_E_BADARG, "sb_intra_convlstm_train_fwd: y must be a separate buffer");
+    return p->C == 32 ? convpath_fwd<32>(*p, (cudaStream_t)stream) : convpath_fwd<16>(*p, (cudaStream_t)stream);
+}
+extern "C" int sb_intra_convlstm_bwd(const sb_convpath_bwd_args* p, void* stream) {
+    SB_REQUIRE(p, SB_E_BADARG, "sb_intra_convlstm_bwd: null pointer");
+    SB_CHECK(check_convpath(&p->f, "sb_intra_convlstm_bwd"));
+    SB_REQUIRE(p->gy && p->gx && p->ws && p->g_conv_w && p->g_conv_b && p->g_prelu && p->g_ln_g && p->g_ln_b && p->g_deconv_w && p->g_deconv_b,
+               SB_E_BADARG, "sb_intra_convlstm_bwd: null pointer");
+    for (int d = 0; d < 2; ++d)
+        SB_REQUIRE(p->g_w_ih[d] && p->g_w_hh[d] && p->g_b_ih[d] && p->g_b_hh[d], SB_E_BADARG, "sb_intra_convlstm_bwd: null gradient buffer");
+    return p->f.C == 32 ? convpath_bwd<32>(*p, (cudaStream_t)stream) : convpath_bwd<16>(*p, (cudaStream_t)stream);
 }

@@ -7,8 +7,8 @@ through the training entry points of include/soundbubble.h (``*_train_fwd`` keep
 the twins); ``SeparatorFunction`` is the ``torch.autograd.Function`` that puts it behind ``Net.forward`` when the module is
 in training mode with gradients enabled.  Parameters are read in their checkpoint layouts - nothing is re-packed per step.
 
-Supported: the plain BiLSTM / LSTM blocks every shipped training config except the conv-LSTM ones uses (conv_lstm=False,
-use_attn=False), FiLM with Dis_Embed_Conv (dis_type conv*), 1-2 sources, optional spectral masking and first LayerNorm.
+Supported: plain BiLSTM and conv-LSTM intra-frame paths, the inter-frame LSTM (use_attn=False), FiLM with Dis_Embed_Conv
+(dis_type conv*), 1-2 sources, optional spectral masking and first LayerNorm - i.e. every shipped training config.
 Anything else raises ``NotImplementedError`` rather than training a different model.  No CPU path: the library handed in
 is the sm_100a build (the tests' host-emulated build goes through the same code on tiny shapes).
 """
@@ -34,8 +34,8 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def check_trainable(cfg: ModelConfig):
-    if cfg.conv_lstm:
-        raise NotImplementedError("training: conv_lstm=True has no backward kernels yet (forward-only configuration)")
+    if cfg.conv_lstm and cfg.lstm_down * cfg.D > 256:
+        raise NotImplementedError("training: conv-LSTM backward kernels need lstm_down * D <= 256")
     if cfg.use_attn:
         raise NotImplementedError("training: use_attn=True has no backward kernels yet (forward-only configuration)")
     if cfg.variant == "dis_embed" and cfg.B > 1 and not cfg.dis_type.startswith("conv"):
@@ -67,6 +67,21 @@ class TrainGraph:
             a.w_ih[d], a.w_hh[d], a.b_ih[d], a.b_hh[d] = w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr()
         a.lin_w, a.lin_b = P[b + kind + "_linear.weight"].data_ptr(), P[b + kind + "_linear.bias"].data_ptr()
         a.B, a.T, a.F, a.C, a.H, a.inter = B, T, cfg.n_freqs, cfg.D, cfg.H, int(inter)
+        return a
+
+    def _convpath_args(self, P, i: int, B: int, T: int) -> abi.ConvPathTrainArgs:
+        cfg = self.cfg
+        b = f"tfgridnet.blocks.{i}."
+        a = abi.ConvPathTrainArgs()
+        a.conv_w, a.conv_b, a.prelu = P[b + "conv.weight"].data_ptr(), P[b + "conv.bias"].data_ptr(), P[b + "act.weight"].data_ptr()
+        a.ln_g, a.ln_b = P[b + "norm.norm.weight"].data_ptr(), P[b + "norm.norm.bias"].data_ptr()
+        for d, sfx in enumerate(("", "_reverse")):
+            w_ih, w_hh, b_ih, b_hh = (P[b + "intra_rnn." + n + sfx] for n in _LSTM)
+            a.w_ih[d], a.w_hh[d], a.b_ih[d], a.b_hh[d] = w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr()
+        a.deconv_w, a.deconv_b = P[b + "deconv.weight"].data_ptr(), P[b + "deconv.bias"].data_ptr()
+        a.B, a.T, a.F, a.C, a.H = B, T, cfg.n_freqs, cfg.D, cfg.H
+        a.down = cfg.lstm_down
+        a.tail_mode = abi.SB_CONVLSTM_OUTPAD if cfg.variant == "optim" else abi.SB_CONVLSTM_PADCROP
         return a
 
     def _film_args(self, P, dis: torch.Tensor, stacks: Dict[str, torch.Tensor]) -> abi.FilmArgs:
@@ -144,7 +159,10 @@ class TrainGraph:
 
         # blocks
         n_saved = [int(lib.sb_path_train_saved_floats(B, T, Fq, C, cfg.H, k)) for k in (0, 1)]
+        if cfg.conv_lstm:
+            n_saved[0] = int(lib.sb_convpath_train_saved_floats(B, T, Fq, C, cfg.H, cfg.lstm_down))
         ctx["saved"] = []
+        ctx["intra_in"] = []
         for i in range(cfg.B):
             if i > 0 and film is not None:
                 y = new(B, T, Fq, C)
@@ -156,12 +174,18 @@ class TrainGraph:
                 x = y
             per_block = []
             for inter in (False, True):
-                pa = self._path_args(P, i, inter, B, T)
                 saved = new(n_saved[int(inter)])
                 y = new(B, T, Fq, C)
-                pa.x, pa.y, pa.saved = x.data_ptr(), y.data_ptr(), saved.data_ptr()
-                fn = lib.sb_inter_lstm_train_fwd if inter else lib.sb_intra_lstm_train_fwd
-                self._call(fn, pa, wave, "sb_%s_lstm_train_fwd" % ("inter" if inter else "intra"))
+                if cfg.conv_lstm and not inter:
+                    ca = self._convpath_args(P, i, B, T)
+                    ca.x, ca.y, ca.saved = x.data_ptr(), y.data_ptr(), saved.data_ptr()
+                    self._call(lib.sb_intra_convlstm_train_fwd, ca, wave, "sb_intra_convlstm_train_fwd")
+                    ctx["intra_in"].append(x)           # the conv weight gradient needs the path input
+                else:
+                    pa = self._path_args(P, i, inter, B, T)
+                    pa.x, pa.y, pa.saved = x.data_ptr(), y.data_ptr(), saved.data_ptr()
+                    fn = lib.sb_inter_lstm_train_fwd if inter else lib.sb_intra_lstm_train_fwd
+                    self._call(fn, pa, wave, "sb_%s_lstm_train_fwd" % ("inter" if inter else "intra"))
                 per_block.append(saved)
                 x = y
             ctx["saved"].append(per_block)
@@ -209,12 +233,32 @@ class TrainGraph:
 
         # blocks, last to first
         n_ws = [int(lib.sb_path_bwd_workspace_floats(B, T, Fq, C, cfg.H, k)) for k in (0, 1)]
+        n_ws.append(B * T * Fq * C)
+        if cfg.conv_lstm:
+            n_ws.append(int(lib.sb_convpath_bwd_workspace_floats(B, T, Fq, C, cfg.H, cfg.lstm_down)))
         wsp = new(max(n_ws))
         g_film = torch.zeros(cfg.B - 1, 2, B, Fq, C, dtype=torch.float32, device=dev) if self.has_film else None
         for i in reversed(range(cfg.B)):
             b = f"tfgridnet.blocks.{i}."
             for inter in (True, False):
                 kind = "inter" if inter else "intra"
+                if cfg.conv_lstm and not inter:
+                    cb = abi.ConvPathBwdArgs()
+                    cb.f = self._convpath_args(P, i, B, T)
+                    saved = ctx["saved"][i][0]
+                    cb.f.saved, cb.f.x = saved.data_ptr(), ctx["intra_in"][i].data_ptr()
+                    cb.gy, cb.gx, cb.ws = gx.data_ptr(), gx.data_ptr(), wsp.data_ptr()
+                    cb.g_conv_w, cb.g_conv_b, cb.g_prelu = (grad(b + n).data_ptr() for n in ("conv.weight", "conv.bias", "act.weight"))
+                    cb.g_ln_g, cb.g_ln_b = grad(b + "norm.norm.weight").data_ptr(), grad(b + "norm.norm.bias").data_ptr()
+                    for d, sfx in enumerate(("", "_reverse")):
+                        g4 = [grad(b + "intra_rnn." + n + sfx) for n in _LSTM]
+                        cb.g_w_ih[d], cb.g_w_hh[d], cb.g_b_ih[d], cb.g_b_hh[d] = (t.data_ptr() for t in g4)
+                    cb.g_deconv_w, cb.g_deconv_b = grad(b + "deconv.weight").data_ptr(), grad(b + "deconv.bias").data_ptr()
+                    self._call(lib.sb_intra_convlstm_bwd, cb, g_out, "sb_intra_convlstm_bwd")
+                    ctx["saved"][i][0] = None
+                    ctx["intra_in"][i] = None
+                    del saved
+                    continue
                 pb = abi.PathBwdArgs()
                 pb.f = self._path_args(P, i, inter, B, T)
                 saved = ctx["saved"][i][int(inter)]

@@ -92,7 +92,7 @@ def test_mode_switches():
     st = net.init_buffers(1, DEV)                      # carried state: the inference kernels, no autograd graph
     assert not net.train()({"mixture": mix, "dis_embed": dis}, st)["output"].requires_grad
     from sound_bubble_b200 import Net
-    rpi = Net(**dict(SYN, B=1, conv_lstm=True)).to(DEV).train()      # no backward kernels: forward-only, backward fails loudly
+    rpi = Net(**dict(SYN, B=1, use_attn=True)).to(DEV).train()       # no backward kernels: forward-only, backward fails loudly
     y = rpi({"mixture": mix, "dis_embed": dis})["output"]
     with pytest.raises(RuntimeError):
         y.sum().backward()

@@ -50,6 +50,12 @@ def test_whole_path_gradients_against_the_reference_fixtures(lib):
     _ok(tc.check_golden_grads(lib, "cpu", "grad_syn_b2"))
 
 
+def test_conv_lstm_gradients_against_the_reference_fixtures(lib):
+    """a9': the Raspberry-Pi model (OPT, k = 5, D = 16, output_padding tail) and the DE3 variant (k = 4, D = 32, pad-and-crop)"""
+    _ok(tc.check_golden_grads(lib, "cpu", "grad_rpi"))
+    _ok(tc.check_golden_grads(lib, "cpu", "grad_syn_convlstm"))
+
+
 def test_variants_against_oracle_autograd(lib):
     """two sources + spectral masking, and the plain front-end (no spatial features, no first LayerNorm)"""
     _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, B=1, num_src=2, spectral_masking=True), B=1, T=2))
@@ -60,7 +66,8 @@ def test_untrainable_configurations_raise():
     from sound_bubble_b200.packing import ModelConfig
     from sound_bubble_b200.training import check_trainable
     check_trainable(ModelConfig(variant="dis_embed", **SYN))
-    for kw in (dict(SYN, conv_lstm=True), dict(SYN, use_attn=True), dict(SYN, dis_type="linear2")):
+    check_trainable(ModelConfig(variant="dis_embed", **dict(SYN, conv_lstm=True)))
+    for kw in (dict(SYN, use_attn=True), dict(SYN, dis_type="linear2")):
         with pytest.raises(NotImplementedError):
             check_trainable(ModelConfig(variant="dis_embed", **kw))
 

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--cpu", type=int, default=1)
+    ap.add_argument("--config", default="syn", choices=["syn", "rpi"], help="syn = TFG_S (config 4), rpi = Raspberry-Pi conv-LSTM model (config 5)")
     ap.add_argument("--one-row", type=int, default=0, help="1 = the first LSTM training kernels (SB_OPT_TRAIN_ONE_ROW)")
     args = ap.parse_args()
     from sound_bubble_b200 import Net, _lib
@@ -32,7 +33,12 @@ def main():
     if args.one_row:
         _lib.load().sb_set_option(3, 1)
     torch.manual_seed(0)
-    net = Net(**SYN).to(dev).train()
+    if args.config == "rpi":
+        from oracle.cases import RPI
+        from sound_bubble_b200.tfgridnet_realtime_clean_optim.net import Net as NetOPT
+        net = NetOPT(**RPI).to(dev).train()
+    else:
+        net = Net(**SYN).to(dev).train()
     n = int(args.seconds * 24000) // 192 * 192
     g = torch.Generator().manual_seed(1)
     mix = (0.1 * torch.randn(args.batch, 6, n, generator=g)).to(dev)
@@ -62,7 +68,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     frames = args.batch * (n // 192)
-    res = {"what": "training step (forward + backward + clip + Adam), TFG_S, fp32", "batch": args.batch, "seconds": args.seconds, "one_row_kernels": bool(args.one_row),
+    res = {"what": "training step (forward + backward + clip + Adam), %s, fp32" % ("TFG_S" if args.config == "syn" else "Raspberry-Pi conv-LSTM model"), "batch": args.batch, "seconds": args.seconds, "one_row_kernels": bool(args.one_row),
            "ms_per_step": ms, "train_frames_per_s": frames / ms * 1e3, "clips_per_s": args.batch / ms * 1e3,
            "launches_per_step": (_lib.launch_count() - l0) / args.steps,
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": float(loss)}
@@ -78,7 +84,7 @@ def main():
     e3.record()
     torch.cuda.synchronize()
     res["fwd_ms"], res["bwd_ms"] = e0.elapsed_time(e1), e2.elapsed_time(e3)
-    if args.cpu:
+    if args.cpu and args.config == "syn":
         # the oracle port under autograd on the host cores, bounded sample: 1 clip x 1 s
         from oracle import tfgridnet_oracle as orc
         from oracle.weights import make_state_dict
