@@ -6,7 +6,7 @@ import torch
 
 import train_cases as tc
 from oracle import tfgridnet_oracle as orc
-from oracle.cases import GRAD_CASES, OPI, SYN
+from oracle.cases import GRAD_CASES, OPI, RPI, SYN
 
 GRAD_TOL = 2e-5          # relative to the largest entry of each gradient tensor
 
@@ -81,3 +81,13 @@ def test_first_version_lstm_training_kernels(lib):
         _ok(tc.check_path(lib, "cpu", "dis_embed", SYN, True, B=1, T=2))
     finally:
         lib.sb_set_option(abi.SB_OPT_TRAIN_ONE_ROW, 0)
+
+
+def test_other_geometries(lib):
+    """the constructor defaults' STFT sizes (n_fft 280, F = 141), 2-3 microphones, single frames, ragged row counts"""
+    kw = dict(stft_chunk_size=160, stft_pad_size=120, num_ch=2, D=16, B=2, H=64, L=4, E=2, use_attn=False, lookahead=True,
+              use_first_ln=False, merge_method="None", conv_lstm=False, dis_type="conv3")
+    _ok(tc.check_net(lib, "cpu", "dis_embed", kw, B=3, T=1))
+    _ok(tc.check_net(lib, "cpu", "dis_embed", dict(kw, conv_lstm=True, use_first_ln=True, merge_method="early_cat"), B=1, T=2))
+    _ok(tc.check_net(lib, "cpu", "optim", dict(RPI, lstm_down=4, B=1), B=5, T=1))
+    _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, num_ch=3, B=1), B=1, T=2))
