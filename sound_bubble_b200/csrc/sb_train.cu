@@ -478,7 +478,7 @@ struct RowGemmCfg {
     static size_t smem_bytes(int nA, int K) { return ((size_t)nA * K * P + (size_t)KB * AS) * sizeof(float); }
 };
 
-template <int P>
+template <int P, bool PACK>
 __global__ void __launch_bounds__(256, 2) rowgemm_kernel(const RowGemm g) {
     using Cfg = RowGemmCfg<P>;
     constexpr int CG = Cfg::CG, ROWS = Cfg::ROWS, KB = Cfg::KB, AS = Cfg::AS, LPT = Cfg::LPT;
@@ -503,11 +503,11 @@ __global__ void __launch_bounds__(256, 2) rowgemm_kernel(const RowGemm g) {
         aoff[i] = n < g.N ? (g.a_mapped ? map_pos(g.map, n) : n) * g.lda + lk(i) : -1;
     }
     const int p0 = (tid % CG) * 8, r0 = (tid / CG) * 8;
-    float acc[8][8];
+    float2 acc2[8][4];                              // [row][column pair]
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
     pdl_wait();
     const int chunks = K / KB, total = g.nA * chunks;
     float4 v[LPT];
@@ -536,9 +536,17 @@ __global__ void __launch_bounds__(256, 2) rowgemm_kernel(const RowGemm g) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) {
+                    if (PACK) ffma2(acc2[i][j], make_float2(wv[2 * j], wv[2 * j + 1]), av[i]);
+                    else { acc2[i][j].x = fmaf(av[i], wv[2 * j], acc2[i][j].x); acc2[i][j].y = fmaf(av[i], wv[2 * j + 1], acc2[i][j].y); }
+                }
         }
     }
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][2 * j] = acc2[i][j].x; acc[i][2 * j + 1] = acc2[i][j].y; }
     float bv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) bv[j] = g.bias ? __ldg(g.bias + p0 + j) : 0.f;
@@ -579,7 +587,7 @@ struct Outer {
     long long N, rows_per_cta;
 };
 
-template <int J, int KC, int TJ, int TK>
+template <int J, int KC, int TJ, int TK, bool PACK>
 __global__ void __launch_bounds__(256) outer_kernel(const Outer o) {
     constexpr int RB = 16, NTJ = J / TJ, NTK = KC / TK;
     constexpr int NA = (RB * J / 4 + 255) / 256, NB = (RB * KC / 4 + 255) / 256;
@@ -589,12 +597,13 @@ __global__ void __launch_bounds__(256) outer_kernel(const Outer o) {
     const int tid = threadIdx.x;
     const int tj = tid % NTJ, tk = tid / NTJ;
     const bool worker = tk < NTK;
-    float acc[TJ][TK], accb[TJ];
+    float2 acc2[TJ][TK / 2];
+    float accb[TJ];
 #pragma unroll
     for (int i = 0; i < TJ; ++i) {
         accb[i] = 0.f;
 #pragma unroll
-        for (int k = 0; k < TK; ++k) acc[i][k] = 0.f;
+        for (int k = 0; k < TK / 2; ++k) acc2[i][k] = make_float2(0.f, 0.f);
     }
     const long long n_begin = (long long)blockIdx.x * o.rows_per_cta;
     const long long n_end = n_begin + o.rows_per_cta < o.N ? n_begin + o.rows_per_cta : o.N;
@@ -652,11 +661,19 @@ __global__ void __launch_bounds__(256) outer_kernel(const Outer o) {
                 for (int i = 0; i < TJ; ++i) {
                     if (tk == 0) accb[i] += av[i];
 #pragma unroll
-                    for (int k = 0; k < TK; ++k) acc[i][k] = fmaf(av[i], bv[k], acc[i][k]);
+                    for (int k = 0; k < TK / 2; ++k) {
+                        if (PACK) ffma2(acc2[i][k], make_float2(bv[2 * k], bv[2 * k + 1]), av[i]);
+                        else { acc2[i][k].x = fmaf(av[i], bv[2 * k], acc2[i][k].x); acc2[i][k].y = fmaf(av[i], bv[2 * k + 1], acc2[i][k].y); }
+                    }
                 }
             }
         }
     }
+    float acc[TJ][TK];
+#pragma unroll
+    for (int i = 0; i < TJ; ++i)
+#pragma unroll
+        for (int k = 0; k < TK / 2; ++k) { acc[i][2 * k] = acc2[i][k].x; acc[i][2 * k + 1] = acc2[i][k].y; }
     if (worker) {
 #pragma unroll
         for (int i = 0; i < TJ; ++i) {
@@ -1325,7 +1342,9 @@ static int run_rowgemm(const RowGemm& g, cudaStream_t st, const char* name) {
         set_error("%s: K = %d is not a multiple of %d", name, g.K, Cfg::KB);
         return SB_E_UNSUPP;
     }
-    return launch(name, rowgemm_kernel<P>, dim3((unsigned)ceil_div_ll(g.N, Cfg::ROWS)), dim3(256), Cfg::smem_bytes(g.nA, g.K), st, g);
+    if (train_ffma2_enabled())
+        return launch(name, rowgemm_kernel<P, true>, dim3((unsigned)ceil_div_ll(g.N, Cfg::ROWS)), dim3(256), Cfg::smem_bytes(g.nA, g.K), st, g);
+    return launch(name, rowgemm_kernel<P, false>, dim3((unsigned)ceil_div_ll(g.N, Cfg::ROWS)), dim3(256), Cfg::smem_bytes(g.nA, g.K), st, g);
 }
 static int rowgemm(const RowGemm& g, int P, cudaStream_t st, const char* name) {
     switch (P) {
@@ -1346,7 +1365,9 @@ static long long reduction_rows(long long N, int rb) {
 template <int J, int KC, int TJ, int TK>
 static int run_outer(Outer o, cudaStream_t st, const char* name) {
     o.rows_per_cta = reduction_rows(o.N, 16);
-    return launch(name, outer_kernel<J, KC, TJ, TK>, dim3((unsigned)ceil_div_ll(o.N, o.rows_per_cta)), dim3(256), 0, st, o);
+    if (train_ffma2_enabled())
+        return launch(name, outer_kernel<J, KC, TJ, TK, true>, dim3((unsigned)ceil_div_ll(o.N, o.rows_per_cta)), dim3(256), 0, st, o);
+    return launch(name, outer_kernel<J, KC, TJ, TK, false>, dim3((unsigned)ceil_div_ll(o.N, o.rows_per_cta)), dim3(256), 0, st, o);
 }
 
 static int path_train_fwd(const sb_path_train_args& a, cudaStream_t st) {

@@ -137,3 +137,14 @@ def test_first_version_lstm_training_kernels(lib):
             _ok(tc.check_path(lib, DEV, "dis_embed", SYN, inter, B=2, T=7))
     finally:
         lib.sb_set_option(abi.SB_OPT_TRAIN_ONE_ROW, 0)
+
+
+@pytest.mark.parametrize("on", [0, 1])
+def test_packed_fma_variants_of_the_gemm_kernels(lib, on):
+    from sound_bubble_b200 import _abi as abi
+    assert lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, on) == 0
+    try:
+        _ok(tc.check_golden_grads(lib, DEV, "grad_syn_b2"))
+        _ok(tc.check_path(lib, DEV, "optim", C16, True, B=2, T=9))
+    finally:
+        lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 0)

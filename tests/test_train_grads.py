@@ -91,3 +91,14 @@ def test_other_geometries(lib):
     _ok(tc.check_net(lib, "cpu", "dis_embed", dict(kw, conv_lstm=True, use_first_ln=True, merge_method="early_cat"), B=1, T=2))
     _ok(tc.check_net(lib, "cpu", "optim", dict(RPI, lstm_down=4, B=1), B=5, T=1))
     _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, num_ch=3, B=1), B=1, T=2))
+
+
+def test_packed_fma_variants_of_the_gemm_kernels(lib):
+    """SB_OPT_TRAIN_FFMA2: same arithmetic (two fmaf per packed instruction), other instruction stream"""
+    from sound_bubble_b200 import _abi as abi
+    assert lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 1) == 0
+    try:
+        _ok(tc.check_path(lib, "cpu", "dis_embed", SYN, False, B=1, T=2))
+        _ok(tc.check_path(lib, "cpu", "optim", dict(OPI, D=16), True, B=1, T=3))
+    finally:
+        lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 0)
