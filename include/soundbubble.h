@@ -74,7 +74,7 @@ extern "C" {
                                 /* tcgen05 core for T >= 64, W <= 129, F*E <= 320)                                    */
 #define SB_OPT_TRAIN_ONE_ROW 3  /* 1 = training LSTM kernels with one gate row (forward) / one W_hh column (BPTT) per thread  */
                                 /* and 256 threads (the first version, kept for comparison; default 0: two per thread, 128) */
-#define SB_OPT_TRAIN_FFMA2 4    /* packed fp32x2 FMAs in the training GEMM kernels (rowgemm / outer)                                     */
+#define SB_OPT_TRAIN_FFMA2 4    /* packed fp32x2 FMAs in the training GEMM kernels (rowgemm / outer); default 1 (measured 2.7 % per step) */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

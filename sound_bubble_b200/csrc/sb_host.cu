@@ -15,7 +15,7 @@ static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_pdl{0};
 static std::atomic<int> g_attn_tc{1};
 static std::atomic<int> g_train_one_row{0};
-static std::atomic<int> g_train_ffma2{0};
+static std::atomic<int> g_train_ffma2{1};
 
 void set_error(const char* fmt, ...) {
     va_list ap;

@@ -147,4 +147,4 @@ def test_packed_fma_variants_of_the_gemm_kernels(lib, on):
         _ok(tc.check_golden_grads(lib, DEV, "grad_syn_b2"))
         _ok(tc.check_path(lib, DEV, "optim", C16, True, B=2, T=9))
     finally:
-        lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 0)
+        lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 1)

@@ -96,9 +96,9 @@ def test_other_geometries(lib):
 def test_packed_fma_variants_of_the_gemm_kernels(lib):
     """SB_OPT_TRAIN_FFMA2: same arithmetic (two fmaf per packed instruction), other instruction stream"""
     from sound_bubble_b200 import _abi as abi
-    assert lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 1) == 0
+    assert lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 0) == 0          # the default is 1: this is the unpacked variant
     try:
         _ok(tc.check_path(lib, "cpu", "dis_embed", SYN, False, B=1, T=2))
         _ok(tc.check_path(lib, "cpu", "optim", dict(OPI, D=16), True, B=1, T=3))
     finally:
-        lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 0)
+        lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 1)
