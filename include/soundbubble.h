@@ -447,8 +447,8 @@ typedef struct sb_film_apply_args {
 int sb_film_apply_fwd(const sb_film_apply_args* a, void* stream);
 int sb_film_apply_bwd(const sb_film_apply_args* a, void* stream);
 
-/* Backward of sb_film_params_fwd (Dis_Embed_Conv only, emb_mode SB_EMB_CONV): g_film [n_layers][2][B][F][C] ->        */
-/* gradients of embeds.j.{weight,bias}.{weight,bias}, embed_net.dis_norm, embed_net.dis_embedding.0.weight.           */
+/* Backward of sb_film_params_fwd (both emb_modes): g_film [n_layers][2][B][F][C] -> gradients of                       */
+/* embeds.j.{weight,bias}.{weight,bias}, the embedding LayerNorm (dis_norm / dis_embedding.1) and dis_embedding.0.weight */
 typedef struct sb_film_bwd_args {
     sb_film_args f;             /* forward arguments (film unused) */
     const float* g_film;

@@ -8,6 +8,7 @@
 //                                                  rowgemm (dL/dh) -> lstm_train_bwd (BPTT, serial part only: the cell
 //                                                  derivatives and W_hh^T dz) -> rowgemm (dL/dLN(x)) -> ln_bwd, and the
 //                                                  weight gradients as one reduction over all (row, step) pairs (outer_kernel)
+//   conv-LSTM intra path     :800-815 (OPT :684-697, 494-510)   convpre_* / prelu_* / convpost_* around the same LSTM kernels
 //   deconv + iSTFT/OLA       :401, 517-542         istft_bwd_kernel, deconv_bwd_x_kernel, deconv_wgrad_kernel
 // The STFT basis buffers and the input features carry no gradient (no parameter upstream of conv-in).
 //
@@ -727,35 +728,66 @@ __global__ void __launch_bounds__(256) film_apply_bwd_kernel(const sb_film_apply
     a.g_shift[i] += gh;
 }
 
-// Dis_Embed_Conv + the 1x1 convs of every FilmLayer, backward.  CTA = one utterance.
+// Dis_Embed_Conv / Dis_Embed_Linear + the 1x1 convs of every FilmLayer, backward.  CTA = one utterance.
+// Embedding entry (f, i) lives at flat index pos = f*Din + i (conv: view [B,F,Din], LayerNorm over Din) or i*F + f
+// (linear: LayerNorm over the whole F*Din vector, view [B,Din,F]); pos is also its row of the embedding weight.
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+}
+
 __global__ void __launch_bounds__(256) film_params_bwd_kernel(const sb_film_bwd_args a) {
     SB_DYN_SMEM(float, sm);
+    __shared__ float red[8];
     const sb_film_args& f = a.f;
-    const int F = f.F, C = f.C, Din = f.Din, L = f.n_layers, b = blockIdx.x, tid = threadIdx.x;
-    float* e_s = sm;                                // [F][Din]  embedding (LayerNorm output)
-    float* eh_s = e_s + F * Din;                    // [F][Din]  normalised
-    float* rs_s = eh_s + F * Din;                   // [F]
-    float* de_s = rs_s + F;                         // [F][Din]
+    const int F = f.F, C = f.C, Din = f.Din, L = f.n_layers, b = blockIdx.x, tid = threadIdx.x, n = F * Din;
+    const bool conv = f.emb_mode == SB_EMB_CONV;
+    float* e_s = sm;                                // [n]  embedding (LayerNorm output)
+    float* eh_s = e_s + n;                          // [n]  normalised
+    float* rs_s = eh_s + n;                         // [F]  1/std per bin (conv mode)
+    float* de_s = rs_s + F;                         // [n]
+    auto pos = [&](int fq, int i) { return conv ? fq * Din + i : i * F + fq; };
     pdl_wait();
     const float d0 = __ldg(f.dis + b * 3), d1 = __ldg(f.dis + b * 3 + 1), d2 = __ldg(f.dis + b * 3 + 2);
-    for (int fq = tid; fq < F; fq += 256) {
-        float mean = 0.f;
-        for (int i = 0; i < Din; ++i) {
-            const float* w = f.emb_w + (size_t)(fq * Din + i) * 3;
-            const float v = fmaf(__ldg(w + 2), d2, fmaf(__ldg(w + 1), d1, __ldg(w) * d0));
-            eh_s[fq * Din + i] = v;
-            mean += v;
+    for (int i = tid; i < n; i += 256) {
+        const float* w = f.emb_w + (size_t)i * 3;
+        eh_s[i] = fmaf(__ldg(w + 2), d2, fmaf(__ldg(w + 1), d1, __ldg(w) * d0));
+        de_s[i] = 0.f;
+    }
+    __syncthreads();
+    float rstd_all = 0.f;
+    if (conv) {
+        for (int fq = tid; fq < F; fq += 256) {
+            float mean = 0.f;
+            for (int i = 0; i < Din; ++i) mean += eh_s[fq * Din + i];
+            mean /= Din;
+            float var = 0.f;
+            for (int i = 0; i < Din; ++i) { const float v = eh_s[fq * Din + i] - mean; eh_s[fq * Din + i] = v; var = fmaf(v, v, var); }
+            const float r = rsqrtf(var / Din + 1e-5f);
+            rs_s[fq] = r;
+            for (int i = 0; i < Din; ++i) {
+                const float h = eh_s[fq * Din + i] * r;
+                eh_s[fq * Din + i] = h;
+                e_s[fq * Din + i] = fmaf(h, __ldg(f.emb_ln_g + i), __ldg(f.emb_ln_b + i));
+            }
         }
-        mean /= Din;
-        float var = 0.f;
-        for (int i = 0; i < Din; ++i) { const float v = eh_s[fq * Din + i] - mean; eh_s[fq * Din + i] = v; var = fmaf(v, v, var); }
-        const float r = rsqrtf(var / Din + 1e-5f);
-        rs_s[fq] = r;
-        for (int i = 0; i < Din; ++i) {
-            const float h = eh_s[fq * Din + i] * r;
-            eh_s[fq * Din + i] = h;
-            e_s[fq * Din + i] = fmaf(h, __ldg(f.emb_ln_g + i), __ldg(f.emb_ln_b + i));
-            de_s[fq * Din + i] = 0.f;
+    } else {
+        float s1 = 0.f;
+        for (int i = tid; i < n; i += 256) s1 += eh_s[i];
+        const float mean = block_sum_256(s1, red) / n;
+        float s2 = 0.f;
+        for (int i = tid; i < n; i += 256) { const float v = eh_s[i] - mean; s2 = fmaf(v, v, s2); }
+        rstd_all = rsqrtf(block_sum_256(s2, red) / n + 1e-5f);
+        for (int i = tid; i < n; i += 256) {
+            const float h = (eh_s[i] - mean) * rstd_all;
+            eh_s[i] = h;
+            e_s[i] = fmaf(h, __ldg(f.emb_ln_g + i), __ldg(f.emb_ln_b + i));
         }
     }
     __syncthreads();
@@ -769,7 +801,7 @@ __global__ void __launch_bounds__(256) film_params_bwd_kernel(const sb_film_bwd_
         for (int i = 0; i < Din; ++i) {
             float aw = 0.f, ab = 0.f;
             for (int fq = 0; fq < F; ++fq) {
-                const float e = e_s[fq * Din + i];
+                const float e = e_s[pos(fq, i)];
                 aw = fmaf(__ldg(gs + (size_t)fq * C), e, aw);
                 ab = fmaf(__ldg(gh + (size_t)fq * C), e, ab);
             }
@@ -780,7 +812,7 @@ __global__ void __launch_bounds__(256) film_params_bwd_kernel(const sb_film_bwd_
         atomic_add(a.g_w_b + lc, sw);
         atomic_add(a.g_b_b + lc, sb_);
     }
-    // (2) thread f: dL/de, LayerNorm(Din) backward, dL/d(embedding weight)
+    // (2) thread f: dL/de
     for (int fq = tid; fq < F; fq += 256) {
         for (int l = 0; l < L; ++l) {
             const float* gs = a.g_film + (((size_t)(2 * l) * f.B + b) * F + fq) * C;
@@ -788,24 +820,50 @@ __global__ void __launch_bounds__(256) film_params_bwd_kernel(const sb_film_bwd_
             for (int c = 0; c < C; ++c) {
                 const float s = __ldg(gs + c), h = __ldg(gh + c);
                 for (int i = 0; i < Din; ++i)
-                    de_s[fq * Din + i] += s * __ldg(f.w_w + (size_t)(l * C + c) * Din + i) + h * __ldg(f.b_w + (size_t)(l * C + c) * Din + i);
+                    de_s[pos(fq, i)] += s * __ldg(f.w_w + (size_t)(l * C + c) * Din + i) + h * __ldg(f.b_w + (size_t)(l * C + c) * Din + i);
             }
         }
+    }
+    __syncthreads();
+    // (3) LayerNorm backward and dL/d(embedding weight)
+    if (conv) {
+        for (int fq = tid; fq < F; fq += 256) {
+            float m1 = 0.f, m2 = 0.f;
+            for (int i = 0; i < Din; ++i) {
+                const float de = de_s[fq * Din + i], h = eh_s[fq * Din + i];
+                atomic_add(a.g_emb_ln_g + i, de * h);
+                atomic_add(a.g_emb_ln_b + i, de);
+                const float dg = de * __ldg(f.emb_ln_g + i);
+                de_s[fq * Din + i] = dg;
+                m1 += dg;
+                m2 = fmaf(dg, h, m2);
+            }
+            m1 /= Din;
+            m2 /= Din;
+            for (int i = 0; i < Din; ++i) {
+                const float dl = rs_s[fq] * (de_s[fq * Din + i] - m1 - eh_s[fq * Din + i] * m2);
+                float* gw = a.g_emb_w + (size_t)(fq * Din + i) * 3;
+                atomic_add(gw, dl * d0);
+                atomic_add(gw + 1, dl * d1);
+                atomic_add(gw + 2, dl * d2);
+            }
+        }
+    } else {
         float m1 = 0.f, m2 = 0.f;
-        for (int i = 0; i < Din; ++i) {
-            const float de = de_s[fq * Din + i], h = eh_s[fq * Din + i];
+        for (int i = tid; i < n; i += 256) {
+            const float de = de_s[i], h = eh_s[i];
             atomic_add(a.g_emb_ln_g + i, de * h);
             atomic_add(a.g_emb_ln_b + i, de);
             const float dg = de * __ldg(f.emb_ln_g + i);
-            de_s[fq * Din + i] = dg;
+            de_s[i] = dg;
             m1 += dg;
             m2 = fmaf(dg, h, m2);
         }
-        m1 /= Din;
-        m2 /= Din;
-        for (int i = 0; i < Din; ++i) {
-            const float dl = rs_s[fq] * (de_s[fq * Din + i] - m1 - eh_s[fq * Din + i] * m2);
-            float* gw = a.g_emb_w + (size_t)(fq * Din + i) * 3;
+        m1 = block_sum_256(m1, red) / n;
+        m2 = block_sum_256(m2, red) / n;
+        for (int i = tid; i < n; i += 256) {
+            const float dl = rstd_all * (de_s[i] - m1 - eh_s[i] * m2);
+            float* gw = a.g_emb_w + (size_t)i * 3;
             atomic_add(gw, dl * d0);
             atomic_add(gw + 1, dl * d1);
             atomic_add(gw + 2, dl * d2);
@@ -1623,7 +1681,7 @@ extern "C" int sb_film_params_bwd(const sb_film_bwd_args* p, void* stream) {
                "sb_film_params_bwd: null pointer");
     SB_REQUIRE(p->g_emb_w && p->g_emb_ln_g && p->g_emb_ln_b && p->g_w_w && p->g_w_b && p->g_b_w && p->g_b_b, SB_E_BADARG,
                "sb_film_params_bwd: null gradient buffer");
-    SB_REQUIRE(p->f.emb_mode == SB_EMB_CONV, SB_E_UNSUPP, "sb_film_params_bwd: only Dis_Embed_Conv (dis_type conv*) has a backward kernel");
+    SB_REQUIRE(p->f.emb_mode == SB_EMB_CONV || p->f.emb_mode == SB_EMB_LINEAR, SB_E_BADARG, "sb_film_params_bwd: unknown emb_mode %d", p->f.emb_mode);
     SB_REQUIRE(p->f.B > 0 && p->f.F > 0 && p->f.C > 0 && p->f.Din > 0 && p->f.n_layers > 0, SB_E_BADARG, "sb_film_params_bwd: bad sizes");
     const size_t smem = ((size_t)3 * p->f.F * p->f.Din + p->f.F) * sizeof(float);
     return launch("film_params_bwd", film_params_bwd_kernel, dim3(p->f.B), dim3(256), smem, (cudaStream_t)stream, *p);

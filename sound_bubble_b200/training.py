@@ -7,8 +7,8 @@ through the training entry points of include/soundbubble.h (``*_train_fwd`` keep
 the twins); ``SeparatorFunction`` is the ``torch.autograd.Function`` that puts it behind ``Net.forward`` when the module is
 in training mode with gradients enabled.  Parameters are read in their checkpoint layouts - nothing is re-packed per step.
 
-Supported: plain BiLSTM and conv-LSTM intra-frame paths, the inter-frame LSTM (use_attn=False), FiLM with Dis_Embed_Conv
-(dis_type conv*), 1-2 sources, optional spectral masking and first LayerNorm - i.e. every shipped training config.
+Supported: plain BiLSTM and conv-LSTM intra-frame paths, the inter-frame LSTM (use_attn=False), FiLM with either distance
+embedding (dis_type conv* / linear*), 1-2 sources, optional spectral masking and first LayerNorm - i.e. every shipped training config.
 Anything else raises ``NotImplementedError`` rather than training a different model.  No CPU path: the library handed in
 is the sm_100a build (the tests' host-emulated build goes through the same code on tiny shapes).
 """
@@ -38,8 +38,6 @@ def check_trainable(cfg: ModelConfig):
         raise NotImplementedError("training: conv-LSTM backward kernels need lstm_down * D <= 256")
     if cfg.use_attn:
         raise NotImplementedError("training: use_attn=True has no backward kernels yet (forward-only configuration)")
-    if cfg.variant == "dis_embed" and cfg.B > 1 and not cfg.dis_type.startswith("conv"):
-        raise NotImplementedError("training: only Dis_Embed_Conv (dis_type conv*) has a backward kernel")
     if cfg.H != 64 or cfg.D not in (16, 32):
         raise NotImplementedError("training: kernels are instantiated for H = 64 and D in {16, 32}")
 
@@ -89,11 +87,18 @@ class TrainGraph:
         a = abi.FilmArgs()
         a.dis = dis.data_ptr()
         a.emb_w = P["tfgridnet.embed_net.dis_embedding.0.weight"].data_ptr()
-        a.emb_ln_g = P["tfgridnet.embed_net.dis_norm.weight"].data_ptr()
-        a.emb_ln_b = P["tfgridnet.embed_net.dis_norm.bias"].data_ptr()
+        a.emb_ln_g, a.emb_ln_b = (P[n].data_ptr() for n in self._emb_ln_names())
         a.w_w, a.w_b, a.b_w, a.b_b = (stacks[k].data_ptr() for k in ("w_w", "w_b", "b_w", "b_b"))
-        a.B, a.F, a.C, a.Din, a.n_layers, a.emb_mode = dis.shape[0], cfg.n_freqs, cfg.D, cfg.film_in, cfg.B - 1, abi.SB_EMB_CONV
+        a.B, a.F, a.C, a.Din, a.n_layers = dis.shape[0], cfg.n_freqs, cfg.D, cfg.film_in, cfg.B - 1
+        a.emb_mode = abi.SB_EMB_CONV if cfg.dis_type.startswith("conv") else abi.SB_EMB_LINEAR
         return a
+
+    def _emb_ln_names(self):
+        """Dis_Embed_Conv keeps its LayerNorm(Din) as dis_norm (DE3:150-173), Dis_Embed_Linear as dis_embedding.1 (:114-147)"""
+        e = "tfgridnet.embed_net."
+        if self.cfg.dis_type.startswith("conv"):
+            return e + "dis_norm.weight", e + "dis_norm.bias"
+        return e + "dis_embedding.1.weight", e + "dis_embedding.1.bias"
 
     def _film_stacks(self, P) -> Dict[str, torch.Tensor]:
         L = self.cfg.B - 1
@@ -292,7 +297,7 @@ class TrainGraph:
             fb.f = self._film_args(P, ctx["dis"], st)
             fb.g_film = g_film.data_ptr()
             fb.g_emb_w = grad("tfgridnet.embed_net.dis_embedding.0.weight").data_ptr()
-            fb.g_emb_ln_g, fb.g_emb_ln_b = grad("tfgridnet.embed_net.dis_norm.weight").data_ptr(), grad("tfgridnet.embed_net.dis_norm.bias").data_ptr()
+            fb.g_emb_ln_g, fb.g_emb_ln_b = (grad(n).data_ptr() for n in self._emb_ln_names())
             fb.g_w_w, fb.g_w_b, fb.g_b_w, fb.g_b_b = (gs[k].data_ptr() for k in ("w_w", "w_b", "b_w", "b_b"))
             self._call(lib.sb_film_params_bwd, fb, g_out, "sb_film_params_bwd")
             e = "tfgridnet.embeds.%d."

@@ -67,7 +67,8 @@ def test_untrainable_configurations_raise():
     from sound_bubble_b200.training import check_trainable
     check_trainable(ModelConfig(variant="dis_embed", **SYN))
     check_trainable(ModelConfig(variant="dis_embed", **dict(SYN, conv_lstm=True)))
-    for kw in (dict(SYN, use_attn=True), dict(SYN, dis_type="linear2")):
+    check_trainable(ModelConfig(variant="dis_embed", **dict(SYN, dis_type="linear2")))
+    for kw in (dict(SYN, use_attn=True),):
         with pytest.raises(NotImplementedError):
             check_trainable(ModelConfig(variant="dis_embed", **kw))
 
@@ -102,3 +103,9 @@ def test_packed_fma_variants_of_the_gemm_kernels(lib):
         _ok(tc.check_path(lib, "cpu", "optim", dict(OPI, D=16), True, B=1, T=3))
     finally:
         lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 1)
+
+
+def test_every_distance_embedding_type(lib):
+    """Dis_Embed_Linear (LayerNorm over the whole F*Din vector, DE3:114-147) and the other Dis_Embed_Conv widths"""
+    for dt in ("linear1", "linear2", "conv2"):
+        _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, B=2, dis_type=dt), B=2, T=2))
