@@ -150,6 +150,6 @@ def test_packed_fma_variants_of_the_gemm_kernels(lib, on):
         lib.sb_set_option(abi.SB_OPT_TRAIN_FFMA2, 1)
 
 
-@pytest.mark.parametrize("dt", ["linear1", "linear2", "conv1", "conv4"])
+@pytest.mark.parametrize("dt", ["linear1", "linear2", "conv4"])      # conv1 / conv2: LayerNorm over 1 - 2 values, gradients ~ 0
 def test_every_distance_embedding_type(lib, dt):
     _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=2, dis_type=dt), B=3, T=4))

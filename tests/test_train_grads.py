@@ -107,5 +107,5 @@ def test_packed_fma_variants_of_the_gemm_kernels(lib):
 
 def test_every_distance_embedding_type(lib):
     """Dis_Embed_Linear (LayerNorm over the whole F*Din vector, DE3:114-147) and the other Dis_Embed_Conv widths"""
-    for dt in ("linear1", "linear2", "conv2"):
+    for dt in ("linear1", "linear2", "conv4"):       # conv1 / conv2 normalise 1 - 2 values: embedding gradients vanish
         _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, B=2, dis_type=dt), B=2, T=2))
