@@ -111,3 +111,73 @@ def test_views_survive_steps_and_checkpoint_layout(tmp_path):
     rest = load_state(path, m2, opt2)
     assert rest["current_epoch"] == 3 and rest["metric_values"] == {"val/loss": {"epoch": 1.0}}
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+# ---- the separator's own backward kernels under data parallelism (host-emulated TEST build of the .cu sources) ----------
+def _sep_case():
+    import torch.nn.functional as F  # noqa: F401
+    from oracle import tfgridnet_oracle as orc
+    from oracle.cases import SYN
+    from oracle.weights import make_state_dict, radius_one_hot, synthetic_mixture
+    from sound_bubble_b200.packing import ModelConfig
+    kw = dict(SYN, B=1)
+    ocfg = orc.OracleConfig.from_kwargs("dis_embed", **kw)
+    sd = make_state_dict(ocfg, 0)
+    n = 4
+    mix = synthetic_mixture(n, 6, 192 * 2 + 96, seed=21)
+    tgt = 0.1 * torch.randn(n, 1, 192 * 2, generator=torch.Generator().manual_seed(22))
+    return orc, ocfg, ModelConfig(variant="dis_embed", **kw), sd, mix, radius_one_hot(n), tgt
+
+
+def _sep_loss(est, tgt):                    # mean over the batch of a per-utterance loss (hl_module.py:321)
+    return ((est - tgt) ** 2).mean(dim=(1, 2)).mean()
+
+
+def _sep_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from emu.emu_lib import load
+        from sound_bubble_b200.training import differentiable_forward
+        lib = load(build=False)
+        orc, ocfg, cfg, sd, mix, dis, tgt = _sep_case()
+        named = {k: v.clone().requires_grad_("_filters" not in k) for k, v in sd.items()}
+        params = [v for v in named.values() if v.requires_grad]
+        red = FlatGradReducer(params)
+        lo, hi = shard_bounds(mix.shape[0], world, rank)
+        red.zero_grad()
+        est = differentiable_forward(lib, cfg, named, mix[lo:hi], dis[lo:hi])
+        _sep_loss(est, tgt[lo:hi]).backward()
+        red.all_reduce_mean()
+        q.put((rank, red.flat.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_separator_backward_kernels_under_data_parallelism():
+    """2 gloo ranks, each back-propagating its shard through the training kernels (host-emulated build), one all-reduce:
+    the result is the gradient of the global-batch mean loss as autograd through the oracle computes it."""
+    from emu.emu_lib import load
+    load()                                                      # build once, before the ranks start
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    orc, ocfg, cfg, sd, mix, dis, tgt = _sep_case()
+    leaf = {k: v.clone().requires_grad_("_filters" not in k) for k, v in sd.items()}
+    out, _ = orc.core_forward(leaf, ocfg, mix, dis, orc.init_state(ocfg, mix.shape[0]))
+    _sep_loss(out, tgt).backward()
+    ref = torch.cat([(v.grad if v.grad is not None else torch.zeros_like(v)).reshape(-1)       # unused parameters: zeros in the flat buffer
+                     for v in leaf.values() if v.requires_grad])
+    for rank, flat in res:
+        flat = torch.tensor(flat)
+        assert flat.shape == ref.shape
+        assert float((flat - ref).abs().max() / ref.abs().max()) <= 2e-5, rank
