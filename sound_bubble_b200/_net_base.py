@@ -101,18 +101,19 @@ class NetBase(nn.Module):
 
     def _train_forward(self, x, dis_embed, pad=True):
         """Net.forward for a training step: same padding / cropping as _predict, gradients to every parameter through
-        SeparatorFunction (training.py).  'next_state' is None: a training call starts from and discards zero state."""
-        from .training import differentiable_forward
+        SeparatorFunction (training.py).  'next_state' has the reference's schema; its tensors are detached (the reference's
+        carry the graph, which nothing in its training loop uses)."""
+        from .training import differentiable_forward_with_state
         _lib.require_cuda(x)
         mod = 0
         if pad:
             pad_size = (self.stft_back_pad, self.stft_pad_size) if self.lookahead else (0, 0)
             x, mod = mod_pad(x, chunk_size=self.stft_chunk_size, pad=pad_size)
         named = dict(self.state_dict(keep_vars=True))
-        y = differentiable_forward(_lib.load(), self.cfg, named, x, dis_embed)
+        y, next_state = differentiable_forward_with_state(_lib.load(), self.cfg, named, x, dis_embed)
         if mod != 0:
             y = y[:, :, :-mod]
-        return {'output': y, 'next_state': None}
+        return {'output': y, 'next_state': next_state}
 
     def _forward_sliced(self, x, dis_embed, state):
         """The whole-utterance call as K time slices through the native pipe (None = not applicable, use the single

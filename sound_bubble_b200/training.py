@@ -208,6 +208,19 @@ class TrainGraph:
         ba.B, ba.T, ba.F, ba.C, ba.n_src, ba.n_fft, ba.stride = B, T, Fq, C, S, cfg.n_fft, hop
         self._call(lib.sb_backend_fwd, ba, wave, "sb_backend_fwd")
         ctx["x_last"] = x
+
+        # the state a streaming call would carry on from (TFGridNet.forward returns it in training too, DE3:547-552): same
+        # keys / shapes / order as init_buffers; detached copies (the backward pass consumes the saved buffers)
+        NI, H = B * Fq * T, cfg.H
+        feats2 = feats if T >= 2 else torch.cat([torch.zeros(B, 2 - T, Fq, cfg.conv_in_ch, device=dev), feats], dim=1)
+        state = {"conv_buf": feats2[:, -2:].permute(0, 3, 1, 2).contiguous(), "deconv_buf": dbo, "istft_buf": ibo.view(B, S, 2 * Fq, 1),
+                 "gridnet_bufs": {}}
+        off_c = 2 * NI * C + (NI + 3) // 4 * 4 + NI * 4 * H            # layout of sb_path_train_args.saved (inter: one direction)
+        for i in range(cfg.B):
+            sv = ctx["saved"][i][1]
+            last = lambda o: sv[o:o + NI * H].view(B * Fq, T, H)[:, -1].clone().unsqueeze(0)
+            state["gridnet_bufs"][f"buf{i}"] = {"c0": last(off_c), "h0": last(off_c + NI * H)}
+        ctx["next_state"] = state
         return out, ctx
 
     # -- backward --------------------------------------------------------------------------------------------
@@ -330,6 +343,7 @@ class SeparatorFunction(torch.autograd.Function):
     def forward(ctx, graph: TrainGraph, names: List[str], wave, dis, *tensors):
         P = {n: (t.detach() if t.is_contiguous() else t.detach().contiguous()) for n, t in zip(names, tensors)}
         out, saved = graph.forward(P, wave.detach(), None if dis is None else dis.detach())
+        graph.last_state = saved.pop("next_state")
         ctx.graph, ctx.names, ctx.saved = graph, names, saved
         ctx.needs = [t.requires_grad for t in tensors]
         return out
@@ -343,7 +357,14 @@ class SeparatorFunction(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
-def differentiable_forward(lib, cfg: ModelConfig, named_tensors: Dict[str, torch.Tensor], wave, dis):
-    """``named_tensors``: every state_dict entry (parameters with requires_grad, buffers without) by reference name."""
+def differentiable_forward_with_state(lib, cfg: ModelConfig, named_tensors: Dict[str, torch.Tensor], wave, dis):
+    """``named_tensors``: every state_dict entry (parameters with requires_grad, buffers without) by reference name.
+    Returns (output with an autograd graph, next_state as detached tensors in the reference's schema)."""
     names = list(named_tensors.keys())
-    return SeparatorFunction.apply(TrainGraph(lib, cfg), names, wave, dis, *[named_tensors[n] for n in names])
+    graph = TrainGraph(lib, cfg)
+    out = SeparatorFunction.apply(graph, names, wave, dis, *[named_tensors[n] for n in names])
+    return out, graph.last_state
+
+
+def differentiable_forward(lib, cfg: ModelConfig, named_tensors: Dict[str, torch.Tensor], wave, dis):
+    return differentiable_forward_with_state(lib, cfg, named_tensors, wave, dis)[0]

@@ -84,7 +84,9 @@ def test_mode_switches():
     net = _net(dict(SYN, B=2))
     mix, dis = synthetic_mixture(1, 6, 192 * 4, seed=1).to(DEV), radius_one_hot(1).to(DEV)
     out = net.train()({"mixture": mix, "dis_embed": dis})
-    assert out["output"].requires_grad and out["next_state"] is None
+    assert out["output"].requires_grad
+    from conftest import flatten_state
+    assert list(flatten_state(out["next_state"])) == list(flatten_state(net.init_buffers(1, DEV)))
     out = net.eval()({"mixture": mix, "dis_embed": dis})
     assert not out["output"].requires_grad and out["next_state"] is not None
     with torch.no_grad():
@@ -153,3 +155,8 @@ def test_packed_fma_variants_of_the_gemm_kernels(lib, on):
 @pytest.mark.parametrize("dt", ["linear1", "linear2", "conv4"])      # conv1 / conv2: LayerNorm over 1 - 2 values, gradients ~ 0
 def test_every_distance_embedding_type(lib, dt):
     _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=2, dis_type=dt), B=3, T=4))
+
+
+def test_training_call_returns_the_next_state(lib):
+    _ok(tc.check_next_state(lib, DEV, "dis_embed", dict(SYN, B=2), B=2, T=7))
+    _ok(tc.check_next_state(lib, DEV, "optim", dict(OPI, B=1), B=1, T=1))

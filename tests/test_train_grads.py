@@ -109,3 +109,8 @@ def test_every_distance_embedding_type(lib):
     """Dis_Embed_Linear (LayerNorm over the whole F*Din vector, DE3:114-147) and the other Dis_Embed_Conv widths"""
     for dt in ("linear1", "linear2", "conv4"):       # conv1 / conv2 normalise 1 - 2 values: embedding gradients vanish
         _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, B=2, dis_type=dt), B=2, T=2))
+
+
+def test_training_call_returns_the_next_state(lib):
+    _ok(tc.check_next_state(lib, "cpu", "dis_embed", dict(SYN, B=2), B=2, T=3))
+    _ok(tc.check_next_state(lib, "cpu", "optim", dict(RPI, B=1), B=1, T=1))          # single frame: conv_buf keeps a zero frame

@@ -183,3 +183,31 @@ def check_golden_grads(lib, device, name):
         assert got[k] is not None, k
         errs[k.replace("tfgridnet.", "")] = relerr(got[k], g)
     return errs
+
+
+def check_next_state(lib, device, variant, kwargs, B=2, T=3, seed=13):
+    """The state a training call returns (same schema as init_buffers) against the oracle's after the same call."""
+    from sound_bubble_b200.training import differentiable_forward_with_state
+    ocfg, sd, cfg = _model(variant, kwargs)
+    n = cfg.stft_chunk_size * T + cfg.n_fft - cfg.stft_chunk_size
+    wave = synthetic_mixture(B, cfg.num_ch, n, seed=seed)
+    dis = torch.tensor([[0., 0., 1.], [0., 1., 0.], [1., 0., 0.]])[torch.arange(B) % 3] if variant == "dis_embed" else None
+    with torch.no_grad():
+        ref_out, ref_state = orc.core_forward(sd, ocfg, wave, dis, orc.init_state(ocfg, B))
+    named = {k: v.detach().clone().float().to(device).requires_grad_("_filters" not in k) for k, v in sd.items()}
+    out, state = differentiable_forward_with_state(lib, cfg, named, wave.to(device), None if dis is None else dis.to(device))
+    _sync(device)
+
+    def flat(st, prefix=""):
+        o = {}
+        for k, v in st.items():
+            o.update(flat(v, prefix + k + "::") if isinstance(v, dict) else {prefix + k: v})
+        return o
+    got, ref = flat(state), flat(ref_state)
+    assert list(got) == list(ref), (list(got), list(ref))                      # same keys in the same order
+    errs = {"output": relerr(out, ref_out)}
+    for k in ref:
+        assert tuple(got[k].shape) == tuple(ref[k].shape), k
+        assert not got[k].requires_grad
+        errs[k] = relerr(got[k], ref[k])
+    return errs
