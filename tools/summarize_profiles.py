@@ -91,12 +91,14 @@ def report(rep, tag):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
-    for n in ("launches_streaming.csv", "launches_offline.csv"):
+    for n in ("launches_streaming.csv", "launches_offline.csv", "launches_train.csv"):
         launches(n, tag)
     for r in sorted(os.listdir(OUT)):
         if r.endswith(".ncu-rep"):
             report(r, tag)
-    for n in ("ubench.txt", "lstm_bench.txt", "bench.json", "bench_pdl.json", "gpu.txt", "host.txt", "prepare_bench.txt", "variants_bench.txt"):
+    for n in ("ubench.txt", "lstm_bench.txt", "bench.json", "bench_pdl.json", "gpu.txt", "host.txt", "prepare_bench.txt", "variants_bench.txt",
+              "train_bench.json", "train_bench_one_row.json", "train_bench_ffma2_0.json", "train_bench_rpi.json", "train_ddp_n2.json",
+              "smoke.log"):
         p = os.path.join(OUT, n)
         if os.path.exists(p):
             open(os.path.join(PROF, "%s_%s" % (tag, n)), "w").write(open(p).read())
