@@ -352,7 +352,7 @@ int    sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, int first
 /* parameters in their CHECKPOINT layouts (they change every step, so nothing is re-packed), keep what the backward  */
 /* pass needs in a caller-owned `saved` buffer and ACCUMULATE (+=) into the caller's gradient buffers with fp32      */
 /* atomics (zero them first; summation order, hence the last bits, vary from run to run).  Plain BiLSTM / LSTM       */
-/* blocks and the conv-LSTM intra path; use_attn models have no backward kernels yet.                                 */
+/* blocks, the conv-LSTM intra path and (first version) the attention.                                                */
 /* ========================================================================================================== */
 
 /* One recurrent path of a GridNet block:  y = x + Linear(LSTM(LayerNorm_C(x))).                                     */
@@ -430,6 +430,31 @@ typedef struct sb_convpath_bwd_args {
 } sb_convpath_bwd_args;
 size_t sb_convpath_bwd_workspace_floats(int B, int T, int F, int C, int H, int down);
 int    sb_intra_convlstm_bwd(const sb_convpath_bwd_args* a, void* stream);
+
+/* a11 for training, from zero K / V history (DE3:639-684, 856-898): y = x + LN(PReLU(Linear(attention(x)))).           */
+/*   Projection parameters as in sb_attn_fwd.  saved: sb_attn_train_saved_floats(); the backward call consumes it.       */
+/*   First version (plain loops, one CTA per head-row): the attention is dormant in every shipped configuration.         */
+typedef struct sb_attn_train_args {
+    const float* x;             /* [B][T][F][C] */
+    float*       y;             /* [B][T][F][C]; must not alias x */
+    sb_attn_proj q, k, v, o;
+    float*       saved;
+    int B, T, F, C, L, E, W;
+} sb_attn_train_args;
+typedef struct sb_attn_proj_grad {
+    float* w; float* b; float* prelu; float* ln_g; float* ln_b;
+} sb_attn_proj_grad;
+typedef struct sb_attn_bwd_args {
+    sb_attn_train_args f;       /* the forward call's arguments (y unused) */
+    const float* gy;
+    float*       gx;            /* may alias gy */
+    sb_attn_proj_grad gq, gk, gv, go;
+    float*       ws;            /* sb_attn_bwd_workspace_floats() floats */
+} sb_attn_bwd_args;
+size_t sb_attn_train_saved_floats(const sb_attn_train_args* a);
+size_t sb_attn_bwd_workspace_floats(const sb_attn_train_args* a);
+int    sb_attn_train_fwd(const sb_attn_train_args* a, void* stream);
+int    sb_attn_bwd(const sb_attn_bwd_args* a, void* stream);
 
 /* FilmLayer.forward (DE3:51-68, :509-513) as its own stage: y = x * scale[b,f,c] + shift[b,f,c]; the backward also    */
 /* accumulates dL/dscale, dL/dshift [B][F][C] (sums over frames), which sb_film_params_bwd turns into parameter grads.*/
@@ -562,7 +587,7 @@ uint64_t    sb_launch_count(void);
 /* sizeof() of the structs above as compiled, so the ctypes mirror can be checked without a GPU                 */
 /*   0 lstm_dir 1 stft 2 conv_in 3 film 4 intra 5 inter 6 backend 7 net_desc 8 net_io 9 intra_conv 10 attn_proj */
 /*   11 attn 12 block_desc 13 prepare 14 path_train 15 path_bwd 16 film_apply 17 film_bwd 18 conv_in_train     */
-/*   19 backend_bwd 20 convpath_train 21 convpath_bwd                                                          */
+/*   19 backend_bwd 20 convpath_train 21 convpath_bwd 22 attn_train 23 attn_proj_grad 24 attn_bwd              */
 int         sb_abi_sizeof(int which);
 
 #ifdef __cplusplus

@@ -60,3 +60,8 @@ GRAD_CASES.update({
     # DE3 conv-LSTM (pad-and-crop tail, k = 4, D = 32) with FiLM, 2 blocks
     "grad_syn_convlstm": dict(variant="dis_embed", kwargs=_with(SYN, conv_lstm=True, B=2), batch=1, n_samples=192 * 3, loss_seed=80),
 })
+GRAD_CASES.update({
+    # TFG_S block with the sliding-window attention switched on (dormant in the shipped configs), window 5 over 6 frames
+    "grad_syn_attn": dict(variant="dis_embed", kwargs=_with(SYN, use_attn=True, local_atten_len=5, B=2), batch=2, n_samples=192 * 6,
+                          loss_seed=81),
+})

@@ -177,11 +177,25 @@ class ConvPathBwdArgs(C.Structure):
                 ("g_deconv_w", fp), ("g_deconv_b", fp), ("ws", fp)]
 
 
+class AttnTrainArgs(C.Structure):
+    _fields_ = [("x", fp), ("y", fp), ("q", AttnProj), ("k", AttnProj), ("v", AttnProj), ("o", AttnProj), ("saved", fp),
+                ("B", C.c_int), ("T", C.c_int), ("F", C.c_int), ("C", C.c_int), ("L", C.c_int), ("E", C.c_int), ("W", C.c_int)]
+
+
+class AttnProjGrad(C.Structure):
+    _fields_ = [(n, fp) for n in ("w", "b", "prelu", "ln_g", "ln_b")]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("f", AttnTrainArgs), ("gy", fp), ("gx", fp),
+                ("gq", AttnProjGrad), ("gk", AttnProjGrad), ("gv", AttnProjGrad), ("go", AttnProjGrad), ("ws", fp)]
+
+
 # index used by sb_abi_sizeof(which)
 ABI_STRUCTS = {0: LstmDir, 1: StftArgs, 2: ConvInArgs, 3: FilmArgs, 4: IntraArgs, 5: InterArgs, 6: BackendArgs,
                7: NetDesc, 8: NetIO, 9: IntraConvArgs, 10: AttnProj, 11: AttnArgs, 12: BlockDesc, 13: PrepareArgs,
                14: PathTrainArgs, 15: PathBwdArgs, 16: FilmApplyArgs, 17: FilmBwdArgs, 18: ConvInTrainArgs, 19: BackendBwdArgs,
-               20: ConvPathTrainArgs, 21: ConvPathBwdArgs}
+               20: ConvPathTrainArgs, 21: ConvPathBwdArgs, 22: AttnTrainArgs, 23: AttnProjGrad, 24: AttnBwdArgs}
 
 # every symbol include/soundbubble.h declares: name -> (restype, argtypes)
 PROTOTYPES = {
@@ -210,6 +224,10 @@ PROTOTYPES = {
     "sb_convpath_bwd_workspace_floats": (C.c_size_t, [C.c_int] * 6),
     "sb_intra_convlstm_train_fwd": (C.c_int, [C.POINTER(ConvPathTrainArgs), C.c_void_p]),
     "sb_intra_convlstm_bwd": (C.c_int, [C.POINTER(ConvPathBwdArgs), C.c_void_p]),
+    "sb_attn_train_saved_floats": (C.c_size_t, [C.POINTER(AttnTrainArgs)]),
+    "sb_attn_bwd_workspace_floats": (C.c_size_t, [C.POINTER(AttnTrainArgs)]),
+    "sb_attn_train_fwd": (C.c_int, [C.POINTER(AttnTrainArgs), C.c_void_p]),
+    "sb_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), C.c_void_p]),
     "sb_film_apply_fwd": (C.c_int, [C.POINTER(FilmApplyArgs), C.c_void_p]),
     "sb_film_apply_bwd": (C.c_int, [C.POINTER(FilmApplyArgs), C.c_void_p]),
     "sb_film_params_bwd": (C.c_int, [C.POINTER(FilmBwdArgs), C.c_void_p]),

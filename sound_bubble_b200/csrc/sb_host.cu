@@ -127,6 +127,9 @@ extern "C" int sb_abi_sizeof(int which) {
         case 19: return (int)sizeof(sb_backend_bwd_args);
         case 20: return (int)sizeof(sb_convpath_train_args);
         case 21: return (int)sizeof(sb_convpath_bwd_args);
+        case 22: return (int)sizeof(sb_attn_train_args);
+        case 23: return (int)sizeof(sb_attn_proj_grad);
+        case 24: return (int)sizeof(sb_attn_bwd_args);
         default: return -1;
     }
 }

@@ -1349,6 +1349,278 @@ __global__ void __launch_bounds__(256) convpre_wgrad_kernel(const ConvPath a, co
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Sliding-window attention for training (a11: DE3 :639-684, 856-898, 722-744) from zero K / V history.  First version:
+// one CTA per head-row, every contraction a plain loop (the attention is dormant in every shipped configuration).
+//   head-row r = (b*L + l)*T + t;  element i of a head-row <-> bin f = i / ed, channel l*ed + e of position (b, t, f)
+// ------------------------------------------------------------------------------------------------------------
+struct AttnDims {
+    int B, T, F, C, L, E, W, Vd;
+};
+
+// zq/zk [n][L*E], zv [n][C] = Linear(x[n]) before the PReLU; thread = position
+template <int C>
+__global__ void __launch_bounds__(128) attn_proj_train_kernel(const float* x, const float* wq, const float* bq, const float* wk, const float* bk,
+                                                              const float* wv, const float* bv, float* zq, float* zk, float* zv, int LE, long long N) {
+    __shared__ float w_s[(2 * 32 + C) * C];
+    __shared__ float b_s[2 * 32 + C];
+    const int tid = threadIdx.x, O = 2 * LE + C;
+    for (int i = tid; i < O * C; i += 128) {
+        const int o = i / C, c = i - o * C;
+        w_s[i] = o < LE ? __ldg(wq + o * C + c) : o < 2 * LE ? __ldg(wk + (o - LE) * C + c) : __ldg(wv + (o - 2 * LE) * C + c);
+    }
+    for (int o = tid; o < O; o += 128) b_s[o] = o < LE ? __ldg(bq + o) : o < 2 * LE ? __ldg(bk + o - LE) : __ldg(bv + o - 2 * LE);
+    pdl_wait();
+    __syncthreads();
+    const long long n = (long long)blockIdx.x * 128 + tid;
+    if (n >= N) return;
+    float xv[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 4) { const float4 t = ldg4_stream(x + n * C + c); xv[c] = t.x; xv[c + 1] = t.y; xv[c + 2] = t.z; xv[c + 3] = t.w; }
+    for (int o = 0; o < O; ++o) {
+        float acc = b_s[o];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc = fmaf(xv[c], w_s[o * C + c], acc);
+        if (o < LE) zq[n * LE + o] = acc;
+        else if (o < 2 * LE) zk[n * LE + o - LE] = acc;
+        else zv[n * C + o - 2 * LE] = acc;
+    }
+}
+
+// rows of D elements: PReLU -> LayerNorm(D).  head = 1: row r is a head-row, element i comes from z[pos(b,t,f)][l*ed + e];
+// head = 0: row = (b, t), element i = z[row*D + i] and the result is added to res (the block's residual).
+struct RowLn {
+    const float* z;             // pre-PReLU values
+    const float* slope;
+    const float* g;
+    const float* b;
+    const float* res;           // head = 0 only
+    float* out;                 // [row][D]
+    float* stats;               // [row][2] mean, 1/std
+    const float* gout;          // bwd: dL/d(out)
+    float* dz;                  // bwd: dL/dz, same addressing as z
+    float* g_g; float* g_b; float* g_slope;
+    int D, head, ed, zstride, L, T, F;
+};
+__device__ __forceinline__ long long rowln_src(const RowLn& a, long long row, int i) {
+    if (!a.head) return row * a.D + i;
+    const long long b = row / ((long long)a.L * a.T);
+    const int l = (int)((row / a.T) % a.L), t = (int)(row % a.T);
+    const int f = i / a.ed, e = i - f * a.ed;
+    return ((b * a.T + t) * a.F + f) * a.zstride + l * a.ed + e;
+}
+__global__ void __launch_bounds__(256) prelu_ln_rows_fwd_kernel(const RowLn a) {
+    __shared__ float red[8];
+    pdl_wait();
+    const long long row = blockIdx.x;
+    const float sl = __ldg(a.slope);
+    float s1 = 0.f;
+    for (int i = threadIdx.x; i < a.D; i += 256) { const float v = a.z[rowln_src(a, row, i)]; s1 += v > 0.f ? v : sl * v; }
+    const float mean = block_sum_256(s1, red) / a.D;
+    float s2 = 0.f;
+    for (int i = threadIdx.x; i < a.D; i += 256) {
+        float v = a.z[rowln_src(a, row, i)];
+        v = (v > 0.f ? v : sl * v) - mean;
+        s2 = fmaf(v, v, s2);
+    }
+    const float rstd = rsqrtf(block_sum_256(s2, red) / a.D + 1e-5f);
+    if (threadIdx.x == 0) { a.stats[2 * row] = mean; a.stats[2 * row + 1] = rstd; }
+    for (int i = threadIdx.x; i < a.D; i += 256) {
+        float v = a.z[rowln_src(a, row, i)];
+        v = ((v > 0.f ? v : sl * v) - mean) * rstd;
+        v = fmaf(v, __ldg(a.g + i), __ldg(a.b + i));
+        if (a.res) v += a.res[row * a.D + i];
+        a.out[row * a.D + i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) prelu_ln_rows_bwd_kernel(const RowLn a) {
+    __shared__ float red[8];
+    pdl_wait();
+    const long long row = blockIdx.x;
+    const float sl = __ldg(a.slope), mean = a.stats[2 * row], rstd = a.stats[2 * row + 1];
+    float m1 = 0.f, m2 = 0.f;
+    for (int i = threadIdx.x; i < a.D; i += 256) {
+        const float z = a.z[rowln_src(a, row, i)];
+        const float h = ((z > 0.f ? z : sl * z) - mean) * rstd;
+        const float g = a.gout[row * a.D + i];
+        atomic_add(a.g_g + i, g * h);
+        atomic_add(a.g_b + i, g);
+        const float dh = g * __ldg(a.g + i);
+        m1 += dh;
+        m2 = fmaf(dh, h, m2);
+    }
+    m1 = block_sum_256(m1, red) / a.D;
+    m2 = block_sum_256(m2, red) / a.D;
+    float ds = 0.f;
+    for (int i = threadIdx.x; i < a.D; i += 256) {
+        const long long src = rowln_src(a, row, i);
+        const float z = a.z[src];
+        const float h = ((z > 0.f ? z : sl * z) - mean) * rstd;
+        const float dp = rstd * (a.gout[row * a.D + i] * __ldg(a.g + i) - m1 - h * m2);
+        if (z > 0.f) a.dz[src] = dp;
+        else { a.dz[src] = dp * sl; ds = fmaf(dp, z, ds); }
+    }
+    ds = block_sum_256(ds, red);
+    if (threadIdx.x == 0) atomic_add(a.g_slope, ds);
+}
+
+// forward core: att[r][w] = softmax_w(q_r . k_{s(w)} / sqrt(DQ)), s(w) = t - W + 1 + w (frames < 0: zero key and value,
+// NOT masked: they take part in the softmax with logit 0); o = sum_w att[w] v_{s(w)} written in [B][T][F][C] order
+__global__ void __launch_bounds__(128) attn_core_train_fwd_kernel(const AttnDims d, const float* qn, const float* kn, const float* vn,
+                                                                  float* att, float* ob) {
+    SB_DYN_SMEM(float, sm);
+    const int DQ = d.F * d.E, DV = d.F * d.Vd, W = d.W, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* q_s = sm;                        // [DQ]
+    float* l_s = q_s + DQ;                  // [W]
+    pdl_wait();
+    const long long r = blockIdx.x;
+    const long long bl = r / d.T;
+    const int t = (int)(r - bl * d.T);
+    for (int i = tid; i < DQ; i += 128) q_s[i] = qn[r * DQ + i];
+    __syncthreads();
+    const float scale = rsqrtf((float)DQ);
+    for (int w = warp; w < W; w += 4) {
+        const int s = t - W + 1 + w;
+        float acc = 0.f;
+        if (s >= 0) {
+            const float* kr = kn + (bl * d.T + s) * DQ;
+            for (int i = lane; i < DQ; i += 32) acc = fmaf(q_s[i], kr[i], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) l_s[w] = acc * scale;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -3.4e38f;
+        for (int w = lane; w < W; w += 32) mx = fmaxf(mx, l_s[w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int w = lane; w < W; w += 32) { const float e = __expf(l_s[w] - mx); l_s[w] = e; sum += e; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        for (int w = lane; w < W; w += 32) { const float p = l_s[w] * inv; l_s[w] = p; att[r * W + w] = p; }
+    }
+    __syncthreads();
+    const long long b = bl / d.L;
+    const int l = (int)(bl - b * d.L);
+    const int w0 = t - W + 1 < 0 ? W - 1 - t : 0;      // first window slot that holds a real frame
+    for (int i = tid; i < DV; i += 128) {
+        float acc = 0.f;
+        for (int w = w0; w < W; ++w) acc = fmaf(l_s[w], vn[(bl * d.T + (t - W + 1 + w)) * DV + i], acc);
+        const int f = i / d.Vd, v = i - f * d.Vd;
+        ob[((b * d.T + t) * d.F + f) * d.C + l * d.Vd + v] = acc;
+    }
+}
+
+// backward, query side: dl[r][w] = att (datt - sum att datt), datt[w] = dO_r . v_s;  dq_r = sum_w dl[w] k_s / sqrt(DQ)
+__global__ void __launch_bounds__(128) attn_core_bwd_q_kernel(const AttnDims d, const float* kn, const float* vn, const float* att,
+                                                              const float* dob, float* dl, float* dqn) {
+    SB_DYN_SMEM(float, sm);
+    __shared__ float red[4];
+    const int DQ = d.F * d.E, DV = d.F * d.Vd, W = d.W, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* do_s = sm;                       // [DV]
+    float* l_s = do_s + DV;                 // [W]
+    pdl_wait();
+    const long long r = blockIdx.x;
+    const long long bl = r / d.T;
+    const int t = (int)(r - bl * d.T);
+    const long long b = bl / d.L;
+    const int l = (int)(bl - b * d.L);
+    for (int i = tid; i < DV; i += 128) {
+        const int f = i / d.Vd, v = i - f * d.Vd;
+        do_s[i] = dob[((b * d.T + t) * d.F + f) * d.C + l * d.Vd + v];
+    }
+    __syncthreads();
+    for (int w = warp; w < W; w += 4) {
+        const int s = t - W + 1 + w;
+        float acc = 0.f;
+        if (s >= 0) {
+            const float* vr = vn + (bl * d.T + s) * DV;
+            for (int i = lane; i < DV; i += 32) acc = fmaf(do_s[i], vr[i], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) l_s[w] = acc;
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int w = tid; w < W; w += 128) part = fmaf(att[r * W + w], l_s[w], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    const float dot = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    for (int w = tid; w < W; w += 128) {
+        const float v = att[r * W + w] * (l_s[w] - dot);
+        l_s[w] = v;
+        dl[r * W + w] = v;
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)DQ);
+    const int w0 = t - W + 1 < 0 ? W - 1 - t : 0;
+    for (int i = tid; i < DQ; i += 128) {
+        float acc = 0.f;
+        for (int w = w0; w < W; ++w) acc = fmaf(l_s[w], kn[(bl * d.T + (t - W + 1 + w)) * DQ + i], acc);
+        dqn[r * DQ + i] = acc * scale;
+    }
+}
+
+// backward, key / value side: frame s is slot w = s - t + W - 1 of the queries t = s .. min(s + W - 1, T - 1)
+__global__ void __launch_bounds__(128) attn_core_bwd_kv_kernel(const AttnDims d, const float* qn, const float* att, const float* dl,
+                                                               const float* dob, float* dkn, float* dvn) {
+    const int DQ = d.F * d.E, DV = d.F * d.Vd, W = d.W, tid = threadIdx.x;
+    pdl_wait();
+    const long long r = blockIdx.x;
+    const long long bl = r / d.T;
+    const int s = (int)(r - bl * d.T);
+    const long long b = bl / d.L;
+    const int l = (int)(bl - b * d.L);
+    const int t_end = s + W - 1 < d.T - 1 ? s + W - 1 : d.T - 1;
+    const float scale = rsqrtf((float)DQ);
+    for (int i = tid; i < DQ; i += 128) {
+        float acc = 0.f;
+        for (int t = s; t <= t_end; ++t) acc = fmaf(dl[(bl * d.T + t) * W + (s - t + W - 1)], qn[(bl * d.T + t) * DQ + i], acc);
+        dkn[r * DQ + i] = acc * scale;
+    }
+    for (int i = tid; i < DV; i += 128) {
+        const int f = i / d.Vd, v = i - f * d.Vd;
+        float acc = 0.f;
+        for (int t = s; t <= t_end; ++t)
+            acc = fmaf(att[(bl * d.T + t) * W + (s - t + W - 1)], dob[((b * d.T + t) * d.F + f) * d.C + l * d.Vd + v], acc);
+        dvn[r * DV + i] = acc;
+    }
+}
+
+// dL/dx[n] = gy[n] + dzq[n] Wq + dzk[n] Wk + dzv[n] Wv; thread = position
+template <int C>
+__global__ void __launch_bounds__(128) attn_proj_bwd_x_kernel(const float* gy, const float* dzq, const float* dzk, const float* dzv,
+                                                              const float* wq, const float* wk, const float* wv, float* gx, int LE, long long N) {
+    __shared__ float w_s[(2 * 32 + C) * C];
+    const int tid = threadIdx.x, O = 2 * LE + C;
+    for (int i = tid; i < O * C; i += 128) {
+        const int o = i / C, c = i - o * C;
+        w_s[i] = o < LE ? __ldg(wq + o * C + c) : o < 2 * LE ? __ldg(wk + (o - LE) * C + c) : __ldg(wv + (o - 2 * LE) * C + c);
+    }
+    pdl_wait();
+    __syncthreads();
+    const long long n = (long long)blockIdx.x * 128 + tid;
+    if (n >= N) return;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 4) { const float4 t = ld_plain4(gy + n * C + c); acc[c] = t.x; acc[c + 1] = t.y; acc[c + 2] = t.z; acc[c + 3] = t.w; }
+    for (int o = 0; o < O; ++o) {
+        const float g = o < LE ? dzq[n * LE + o] : o < 2 * LE ? dzk[n * LE + o - LE] : dzv[n * C + o - 2 * LE];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(g, w_s[o * C + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; c += 4) st4(gx + n * C + c, make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 struct PathDims {
@@ -1624,6 +1896,143 @@ static int convpath_bwd(const sb_convpath_bwd_args& b, cudaStream_t st) {
                   st, cp, b.gy, (const float*)v.pz, b.gx);
 }
 
+// ---- attention (training) -----------------------------------------------------------------------------------
+static long long al4(long long n) { return (n + 3) / 4 * 4; }
+struct AttnSaved {
+    float *zq, *zk, *zv, *qn, *kn, *vn, *att, *ob, *zo, *st_q, *st_k, *st_v, *st_o;
+};
+struct AttnSizes {
+    long long N, R, BT;
+    int LE, DQ, DV;
+};
+static AttnSizes attn_sizes(const sb_attn_train_args& a) {
+    AttnSizes z;
+    z.N = (long long)a.B * a.T * a.F; z.R = (long long)a.B * a.L * a.T; z.BT = (long long)a.B * a.T;
+    z.LE = a.L * a.E; z.DQ = a.F * a.E; z.DV = a.F * (a.C / a.L);
+    return z;
+}
+static AttnSaved attn_saved_view(const sb_attn_train_args& a, const AttnSizes& z) {
+    AttnSaved v{};
+    float* p = a.saved;
+    v.zq = p; p += al4(z.N * z.LE);
+    v.zk = p; p += al4(z.N * z.LE);
+    v.zv = p; p += al4(z.N * a.C);
+    v.qn = p; p += al4(z.N * z.LE);
+    v.kn = p; p += al4(z.N * z.LE);
+    v.vn = p; p += al4(z.N * a.C);
+    v.att = p; p += al4(z.R * a.W);
+    v.ob = p; p += al4(z.N * a.C);
+    v.zo = p; p += al4(z.N * a.C);
+    v.st_q = p; p += al4(2 * z.R);
+    v.st_k = p; p += al4(2 * z.R);
+    v.st_v = p; p += al4(2 * z.R);
+    v.st_o = p; p += al4(2 * z.BT);
+    return v;
+}
+static size_t attn_saved_floats(const sb_attn_train_args& a) {
+    const AttnSizes z = attn_sizes(a);
+    return (size_t)(4 * al4(z.N * z.LE) + 4 * al4(z.N * a.C) + al4(z.R * a.W) + 3 * al4(2 * z.R) + al4(2 * z.BT));
+}
+static int check_attn_train(const sb_attn_train_args* p, const char* who) {
+    SB_REQUIRE(p && p->x && p->saved, SB_E_BADARG, "%s: null pointer", who);
+    const sb_attn_proj* pr[4] = {&p->q, &p->k, &p->v, &p->o};
+    for (int i = 0; i < 4; ++i)
+        SB_REQUIRE(pr[i]->w && pr[i]->b && pr[i]->prelu && pr[i]->ln_g && pr[i]->ln_b, SB_E_BADARG, "%s: null projection parameter", who);
+    SB_REQUIRE(p->B > 0 && p->T > 0 && p->F > 0 && p->L > 0 && p->E > 0 && p->W > 0, SB_E_BADARG, "%s: bad sizes", who);
+    SB_REQUIRE(p->C == 16 || p->C == 32, SB_E_UNSUPP, "%s: C must be 16 or 32 (got %d)", who, p->C);
+    SB_REQUIRE(p->C % p->L == 0, SB_E_BADARG, "%s: C must be a multiple of L", who);
+    SB_REQUIRE(p->L * p->E == 8 || p->L * p->E == 16, SB_E_UNSUPP, "%s: L*E must be 8 or 16 (got %d)", who, p->L * p->E);
+    SB_REQUIRE((size_t)(p->F * (p->C / p->L) + p->W) * sizeof(float) <= 200 * 1024, SB_E_UNSUPP, "%s: head-row too long", who);
+    return 0;
+}
+static AttnDims attn_dims(const sb_attn_train_args& a) { return AttnDims{a.B, a.T, a.F, a.C, a.L, a.E, a.W, a.C / a.L}; }
+
+static RowLn rowln_head(const sb_attn_train_args& a, const sb_attn_proj& pr, float* z, int ed, int zstride, float* out, float* stats) {
+    RowLn r{};
+    r.z = z; r.slope = pr.prelu; r.g = pr.ln_g; r.b = pr.ln_b; r.out = out; r.stats = stats;
+    r.D = a.F * ed; r.head = 1; r.ed = ed; r.zstride = zstride; r.L = a.L; r.T = a.T; r.F = a.F;
+    return r;
+}
+
+template <int C>
+static int attn_train_fwd(const sb_attn_train_args& a, cudaStream_t st) {
+    const AttnSizes z = attn_sizes(a);
+    const AttnSaved v = attn_saved_view(a, z);
+    const AttnDims d = attn_dims(a);
+    SB_CHECK(launch("attn_proj_train", attn_proj_train_kernel<C>, dim3((unsigned)ceil_div_ll(z.N, 128)), dim3(128), 0, st, a.x, a.q.w, a.q.b,
+                    a.k.w, a.k.b, a.v.w, a.v.b, v.zq, v.zk, v.zv, z.LE, z.N));
+    SB_CHECK(launch("attn_head_ln", prelu_ln_rows_fwd_kernel, dim3((unsigned)z.R), dim3(256), 0, st, rowln_head(a, a.q, v.zq, a.E, z.LE, v.qn, v.st_q)));
+    SB_CHECK(launch("attn_head_ln", prelu_ln_rows_fwd_kernel, dim3((unsigned)z.R), dim3(256), 0, st, rowln_head(a, a.k, v.zk, a.E, z.LE, v.kn, v.st_k)));
+    SB_CHECK(launch("attn_head_ln", prelu_ln_rows_fwd_kernel, dim3((unsigned)z.R), dim3(256), 0, st, rowln_head(a, a.v, v.zv, d.Vd, a.C, v.vn, v.st_v)));
+    SB_CHECK(launch("attn_core_train_fwd", attn_core_train_fwd_kernel, dim3((unsigned)z.R), dim3(128), (size_t)(z.DQ + a.W) * sizeof(float), st, d,
+                    (const float*)v.qn, (const float*)v.kn, (const float*)v.vn, v.att, v.ob));
+    RowGemm g{};
+    g.nA = 1; g.K = C; g.lda = C; g.ldw = C; g.w_trans = 1;
+    g.A[0] = v.ob; g.W[0] = a.o.w; g.bias = a.o.b; g.out = v.zo; g.map = RowMap{1, a.F, 0}; g.N = z.N;
+    SB_CHECK(rowgemm(g, C, st, "attn_out_proj"));
+    RowLn r{};
+    r.z = v.zo; r.slope = a.o.prelu; r.g = a.o.ln_g; r.b = a.o.ln_b; r.res = a.x; r.out = a.y; r.stats = v.st_o; r.D = a.F * C; r.head = 0;
+    return launch("attn_out_ln", prelu_ln_rows_fwd_kernel, dim3((unsigned)z.BT), dim3(256), 0, st, r);
+}
+
+template <int J, int KC>
+static int attn_wgrad(const float* A, const float* Bm, float* dW, float* db, long long N, cudaStream_t st) {
+    Outer o{};
+    o.A = A; o.Bm = Bm; o.kc0 = KC; o.dW = dW; o.ldw = KC; o.db = db; o.map = RowMap{1, 1, 0}; o.N = N;
+    return run_outer<J, KC, (J >= 32 ? 4 : 2), 2>(o, st, "attn_wgrad");
+}
+
+template <int C>
+static int attn_train_bwd(const sb_attn_bwd_args& b, cudaStream_t st) {
+    const sb_attn_train_args& a = b.f;
+    const AttnSizes z = attn_sizes(a);
+    const AttnSaved v = attn_saved_view(a, z);
+    const AttnDims d = attn_dims(a);
+    float* p = b.ws;
+    float* dob = p; p += al4(z.N * C);
+    float* dqn = p; p += al4(z.N * z.LE);
+    float* dkn = p; p += al4(z.N * z.LE);
+    float* dvn = p; p += al4(z.N * C);
+    float* dl = p;
+    // output LayerNorm + PReLU (dz over zo in place), output projection
+    RowLn r{};
+    r.z = v.zo; r.slope = a.o.prelu; r.g = a.o.ln_g; r.stats = v.st_o; r.D = a.F * C; r.head = 0;
+    r.gout = b.gy; r.dz = v.zo; r.g_g = b.go.ln_g; r.g_b = b.go.ln_b; r.g_slope = b.go.prelu;
+    SB_CHECK(launch("attn_out_ln_bwd", prelu_ln_rows_bwd_kernel, dim3((unsigned)z.BT), dim3(256), 0, st, r));
+    RowGemm g{};
+    g.nA = 1; g.K = C; g.lda = C; g.ldw = C; g.w_trans = 0;
+    g.A[0] = v.zo; g.W[0] = a.o.w; g.out = dob; g.map = RowMap{1, a.F, 0}; g.N = z.N;
+    SB_CHECK(rowgemm(g, C, st, "attn_out_proj_bwd"));
+    SB_CHECK((attn_wgrad<C, C>(v.zo, v.ob, b.go.w, b.go.b, z.N, st)));
+    // attention core
+    SB_CHECK(launch("attn_core_bwd_q", attn_core_bwd_q_kernel, dim3((unsigned)z.R), dim3(128), (size_t)(z.DV + a.W) * sizeof(float), st, d,
+                    (const float*)v.kn, (const float*)v.vn, (const float*)v.att, (const float*)dob, dl, dqn));
+    SB_CHECK(launch("attn_core_bwd_kv", attn_core_bwd_kv_kernel, dim3((unsigned)z.R), dim3(128), 0, st, d, (const float*)v.qn, (const float*)v.att,
+                    (const float*)dl, (const float*)dob, dkn, dvn));
+    // head LayerNorms + PReLUs (dz over zq / zk / zv in place)
+    const sb_attn_proj* pr[3] = {&a.q, &a.k, &a.v};
+    const sb_attn_proj_grad* gr[3] = {&b.gq, &b.gk, &b.gv};
+    float* zs[3] = {v.zq, v.zk, v.zv};
+    float* gs[3] = {dqn, dkn, dvn};
+    float* sts[3] = {v.st_q, v.st_k, v.st_v};
+    for (int i = 0; i < 3; ++i) {
+        RowLn h = rowln_head(a, *pr[i], zs[i], i < 2 ? a.E : d.Vd, i < 2 ? z.LE : C, nullptr, sts[i]);
+        h.gout = gs[i]; h.dz = zs[i]; h.g_g = gr[i]->ln_g; h.g_b = gr[i]->ln_b; h.g_slope = gr[i]->prelu;
+        SB_CHECK(launch("attn_head_ln_bwd", prelu_ln_rows_bwd_kernel, dim3((unsigned)z.R), dim3(256), 0, st, h));
+    }
+    // projections
+    if (z.LE == 8) {
+        SB_CHECK((attn_wgrad<8, C>(v.zq, a.x, b.gq.w, b.gq.b, z.N, st)));
+        SB_CHECK((attn_wgrad<8, C>(v.zk, a.x, b.gk.w, b.gk.b, z.N, st)));
+    } else {
+        SB_CHECK((attn_wgrad<16, C>(v.zq, a.x, b.gq.w, b.gq.b, z.N, st)));
+        SB_CHECK((attn_wgrad<16, C>(v.zk, a.x, b.gk.w, b.gk.b, z.N, st)));
+    }
+    SB_CHECK((attn_wgrad<C, C>(v.zv, a.x, b.gv.w, b.gv.b, z.N, st)));
+    return launch("attn_proj_bwd_x", attn_proj_bwd_x_kernel<C>, dim3((unsigned)ceil_div_ll(z.N, 128)), dim3(128), 0, st, b.gy, (const float*)v.zq,
+                  (const float*)v.zk, (const float*)v.zv, a.q.w, a.k.w, a.v.w, b.gx, z.LE, z.N);
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -1778,4 +2187,25 @@ extern "C" int sb_intra_convlstm_bwd(const sb_convpath_bwd_args* p, void* stream
     for (int d = 0; d < 2; ++d)
         SB_REQUIRE(p->g_w_ih[d] && p->g_w_hh[d] && p->g_b_ih[d] && p->g_b_hh[d], SB_E_BADARG, "sb_intra_convlstm_bwd: null gradient buffer");
     return p->f.C == 32 ? convpath_bwd<32>(*p, (cudaStream_t)stream) : convpath_bwd<16>(*p, (cudaStream_t)stream);
+}
+
+extern "C" size_t sb_attn_train_saved_floats(const sb_attn_train_args* p) { return p ? attn_saved_floats(*p) : 0; }
+extern "C" size_t sb_attn_bwd_workspace_floats(const sb_attn_train_args* p) {
+    if (!p) return 0;
+    const AttnSizes z = attn_sizes(*p);
+    return (size_t)(2 * al4(z.N * p->C) + 2 * al4(z.N * z.LE) + al4(z.R * p->W));
+}
+extern "C" int sb_attn_train_fwd(const sb_attn_train_args* p, void* stream) {
+    SB_CHECK(check_attn_train(p, "sb_attn_train_fwd"));
+    SB_REQUIRE(p->y && p->y != p->x, SB_E_BADARG, "sb_attn_train_fwd: y must be a separate buffer");
+    return p->C == 32 ? attn_train_fwd<32>(*p, (cudaStream_t)stream) : attn_train_fwd<16>(*p, (cudaStream_t)stream);
+}
+extern "C" int sb_attn_bwd(const sb_attn_bwd_args* p, void* stream) {
+    SB_REQUIRE(p, SB_E_BADARG, "sb_attn_bwd: null pointer");
+    SB_CHECK(check_attn_train(&p->f, "sb_attn_bwd"));
+    SB_REQUIRE(p->gy && p->gx && p->ws, SB_E_BADARG, "sb_attn_bwd: null pointer");
+    const sb_attn_proj_grad* gr[4] = {&p->gq, &p->gk, &p->gv, &p->go};
+    for (int i = 0; i < 4; ++i)
+        SB_REQUIRE(gr[i]->w && gr[i]->b && gr[i]->prelu && gr[i]->ln_g && gr[i]->ln_b, SB_E_BADARG, "sb_attn_bwd: null gradient buffer");
+    return p->f.C == 32 ? attn_train_bwd<32>(*p, (cudaStream_t)stream) : attn_train_bwd<16>(*p, (cudaStream_t)stream);
 }

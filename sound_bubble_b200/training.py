@@ -33,11 +33,18 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# The attention backward kernels are a first version that has been checked on the host-emulated test build only (no B200
+# run yet): they stay behind this switch, so that ``Net`` in train() mode keeps treating use_attn models as forward-only.
+EXPERIMENTAL_ATTENTION = False
+
+
 def check_trainable(cfg: ModelConfig):
     if cfg.conv_lstm and cfg.lstm_down * cfg.D > 256:
         raise NotImplementedError("training: conv-LSTM backward kernels need lstm_down * D <= 256")
-    if cfg.use_attn:
-        raise NotImplementedError("training: use_attn=True has no backward kernels yet (forward-only configuration)")
+    if cfg.use_attn and not EXPERIMENTAL_ATTENTION:
+        raise NotImplementedError("training: the attention backward kernels are experimental (training.EXPERIMENTAL_ATTENTION)")
+    if cfg.use_attn and cfg.L * cfg.attn_E not in (8, 16):
+        raise NotImplementedError("training: attention backward kernels need L * E in {8, 16}")
     if cfg.H != 64 or cfg.D not in (16, 32):
         raise NotImplementedError("training: kernels are instantiated for H = 64 and D in {16, 32}")
 
@@ -80,6 +87,19 @@ class TrainGraph:
         a.B, a.T, a.F, a.C, a.H = B, T, cfg.n_freqs, cfg.D, cfg.H
         a.down = cfg.lstm_down
         a.tail_mode = abi.SB_CONVLSTM_OUTPAD if cfg.variant == "optim" else abi.SB_CONVLSTM_PADCROP
+        return a
+
+    _ATTN = (("q", "attn_conv_Q."), ("k", "attn_conv_K."), ("v", "attn_conv_V."), ("o", "attn_concat_proj."))
+    _ATTN_P = (("w", "0.weight"), ("b", "0.bias"), ("prelu", "1.weight"), ("ln_g", "3.norm.weight"), ("ln_b", "3.norm.bias"))
+
+    def _attn_args(self, P, i: int, B: int, T: int) -> abi.AttnTrainArgs:
+        cfg = self.cfg
+        a = abi.AttnTrainArgs()
+        for field, mod in self._ATTN:
+            pr = getattr(a, field)
+            for f2, name in self._ATTN_P:
+                setattr(pr, f2, P[f"tfgridnet.blocks.{i}." + mod + name].data_ptr())
+        a.B, a.T, a.F, a.C, a.L, a.E, a.W = B, T, cfg.n_freqs, cfg.D, cfg.L, cfg.attn_E, cfg.local_atten_len
         return a
 
     def _film_args(self, P, dis: torch.Tensor, stacks: Dict[str, torch.Tensor]) -> abi.FilmArgs:
@@ -193,6 +213,15 @@ class TrainGraph:
                     self._call(fn, pa, wave, "sb_%s_lstm_train_fwd" % ("inter" if inter else "intra"))
                 per_block.append(saved)
                 x = y
+            if cfg.use_attn:
+                aa = self._attn_args(P, i, B, T)
+                saved = new(int(lib.sb_attn_train_saved_floats(ctypes.byref(aa))))
+                y = new(B, T, Fq, C)
+                aa.x, aa.y, aa.saved = x.data_ptr(), y.data_ptr(), saved.data_ptr()
+                self._call(lib.sb_attn_train_fwd, aa, wave, "sb_attn_train_fwd")
+                per_block.append(saved)
+                ctx.setdefault("attn_in", []).append(x)
+                x = y
             ctx["saved"].append(per_block)
 
         # a13-a15 from zero history (the inference entry point; nothing has to be kept but its input)
@@ -219,7 +248,18 @@ class TrainGraph:
         for i in range(cfg.B):
             sv = ctx["saved"][i][1]
             last = lambda o: sv[o:o + NI * H].view(B * Fq, T, H)[:, -1].clone().unsqueeze(0)
-            state["gridnet_bufs"][f"buf{i}"] = {"c0": last(off_c), "h0": last(off_c + NI * H)}
+            buf = {}
+            if cfg.use_attn:                        # layout of sb_attn_train_args.saved: zq, zk, zv, qn, kn, vn, ... (each padded to 4 floats)
+                al4 = lambda n: (n + 3) // 4 * 4
+                LE, W1, sa = cfg.L * cfg.attn_E, cfg.local_atten_len - 1, ctx["saved"][i][2]
+                o_kn = 2 * al4(NP * LE) + al4(NP * C) + al4(NP * LE)
+                o_vn = o_kn + al4(NP * LE)
+                for key, o, width in (("K_buf", o_kn, Fq * cfg.attn_E), ("V_buf", o_vn, Fq * (C // cfg.L))):
+                    rows = sa[o:o + B * cfg.L * T * width].view(B * cfg.L, T, width)
+                    buf[key] = torch.cat([torch.zeros(B * cfg.L, W1, width, device=dev), rows], dim=1)[:, -W1:].contiguous() if W1 > 0 \
+                        else rows[:, :0].contiguous()
+            buf["c0"], buf["h0"] = last(off_c), last(off_c + NI * H)
+            state["gridnet_bufs"][f"buf{i}"] = buf
         ctx["next_state"] = state
         return out, ctx
 
@@ -258,6 +298,21 @@ class TrainGraph:
         g_film = torch.zeros(cfg.B - 1, 2, B, Fq, C, dtype=torch.float32, device=dev) if self.has_film else None
         for i in reversed(range(cfg.B)):
             b = f"tfgridnet.blocks.{i}."
+            if cfg.use_attn:
+                ab = abi.AttnBwdArgs()
+                ab.f = self._attn_args(P, i, B, T)
+                saved = ctx["saved"][i][2]
+                ab.f.saved, ab.f.x = saved.data_ptr(), ctx["attn_in"][i].data_ptr()
+                wsa = new(int(lib.sb_attn_bwd_workspace_floats(ctypes.byref(ab.f))))
+                ab.gy, ab.gx, ab.ws = gx.data_ptr(), gx.data_ptr(), wsa.data_ptr()
+                for field, mod in self._ATTN:
+                    gp = getattr(ab, "g" + field)
+                    for f2, name in self._ATTN_P:
+                        setattr(gp, f2, grad(b + mod + name).data_ptr())
+                self._call(lib.sb_attn_bwd, ab, g_out, "sb_attn_bwd")
+                ctx["saved"][i][2] = None
+                ctx["attn_in"][i] = None
+                del saved, wsa
             for inter in (True, False):
                 kind = "inter" if inter else "intra"
                 if cfg.conv_lstm and not inter:
