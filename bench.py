@@ -143,6 +143,23 @@ def cpu_streaming_sample(sd, n_chunks, warm=2, seed=1234):
     return time.perf_counter() - t0
 
 
+def cpu_training_sample(sd, seconds=1.0, seed=77):
+    """One training step (forward + backward under torch autograd) of ONE clip of `seconds` through the oracle port on the
+    host cores: the CPU figure beside the "train" leg.  Returns (seconds of wall time, frames)."""
+    from oracle import tfgridnet_oracle as orc
+    ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
+    torch.set_num_threads(os.cpu_count() or 1)
+    leaf = {k: v.detach().clone().requires_grad_("_filters" not in k) for k, v in sd.items()}
+    n = int(seconds * 24000) // CHUNK * CHUNK
+    g = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(1, MICS, n, generator=g)
+    tgt = 0.1 * torch.randn(1, 1, n, generator=g)
+    t0 = time.perf_counter()
+    est = orc.net_forward(leaf, ocfg, {"mixture": x, "dis_embed": radius_one_hot(1)})["output"]
+    (-(10 * torch.log10(tgt.pow(2).sum(-1) / ((est - tgt).pow(2).sum(-1) + 1e-8))).mean()).backward()
+    return time.perf_counter() - t0, n // CHUNK
+
+
 def reference_weights():
     from oracle import tfgridnet_oracle as orc
     from oracle.weights import make_state_dict
@@ -437,6 +454,10 @@ def run_ours(args, rank, world, local_rank):
         dt = cpu_streaming_sample(sd, n_cpu, warm=2)
         cpu = {"value": BATCH * n_cpu / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "first %d of %d chunks of the batch-32 streaming pass (%.1f s of CPU work)" % (n_cpu, T_FRAMES, dt)}
+        if train_info is not None and "error" not in train_info:
+            dt_t, fr_t = cpu_training_sample(sd)
+            cpu["train"] = {"value": fr_t / dt_t, "unit": "training frames/s", "kind": "port", "cores": os.cpu_count() or 1,
+                            "sample": "forward + backward of 1 clip x 1 s under torch autograd (%.2f s of CPU work)" % dt_t}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

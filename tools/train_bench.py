@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Training step of the TFG_S separator on one B200: forward + backward through the hand-written kernels, timed with CUDA
-events, next to autograd through the CPU oracle port on a bounded sample (BASELINE config 4's per-GPU work: the reference
-trains with global batch 8 on 5 s clips, syn_experiments/pretrain_stage.json).
+events (BASELINE config 4's per-GPU work: the reference trains with global batch 8 on 5 s clips,
+syn_experiments/pretrain_stage.json).  The CPU figure beside it is bench.py's cpu_baseline.train.
 
     python tools/train_bench.py [--batch 8] [--seconds 5] [--steps 3] [--cpu 1]
 """
@@ -9,7 +9,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 import torch
 
@@ -24,7 +23,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--cpu", type=int, default=1)
+    ap.add_argument("--cpu", type=int, default=0, help="ignored (the CPU figure beside the training step is bench.py's cpu_baseline.train)")
     ap.add_argument("--config", default="syn", choices=["syn", "rpi"], help="syn = TFG_S (config 4), rpi = Raspberry-Pi conv-LSTM model (config 5)")
     ap.add_argument("--ffma2", type=int, default=-1, help="0 / 1 = SB_OPT_TRAIN_FFMA2 (packed FMAs in the training GEMM kernels); -1 = library default")
     ap.add_argument("--one-row", type=int, default=0, help="1 = the first LSTM training kernels (SB_OPT_TRAIN_ONE_ROW)")
@@ -37,7 +36,7 @@ def main():
         _lib.load().sb_set_option(4, args.ffma2)
     torch.manual_seed(0)
     if args.config == "rpi":
-        from oracle.cases import RPI
+        from oracle.cases import RPI          # configuration dictionary only
         from sound_bubble_b200.tfgridnet_realtime_clean_optim.net import Net as NetOPT
         net = NetOPT(**RPI).to(dev).train()
     else:
@@ -87,21 +86,6 @@ def main():
     e3.record()
     torch.cuda.synchronize()
     res["fwd_ms"], res["bwd_ms"] = e0.elapsed_time(e1), e2.elapsed_time(e3)
-    if args.cpu and args.config == "syn":
-        # the oracle port under autograd on the host cores, bounded sample: 1 clip x 1 s
-        from oracle import tfgridnet_oracle as orc
-        from oracle.weights import make_state_dict
-        ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
-        sd = {k: (v.clone().requires_grad_("_filters" not in k)) for k, v in make_state_dict(ocfg, 0).items()}
-        torch.set_num_threads(os.cpu_count())
-        cm = mix[:1, :, :24000].cpu()
-        t0 = time.time()
-        out = orc.net_forward(sd, ocfg, {"mixture": cm, "dis_embed": dis[:1].cpu()})["output"]
-        out.pow(2).mean().backward()
-        dt = time.time() - t0
-        res["cpu_port"] = {"sample": "1 clip x 1 s, forward + backward, oracle port under torch autograd", "cores": os.cpu_count(),
-                           "s": dt, "train_frames_per_s": 125 / dt}
-        res["speedup_vs_cpu_port"] = res["train_frames_per_s"] / res["cpu_port"]["train_frames_per_s"]
     print(json.dumps(res))
 
 
