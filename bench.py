@@ -455,9 +455,12 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": BATCH * n_cpu / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "first %d of %d chunks of the batch-32 streaming pass (%.1f s of CPU work)" % (n_cpu, T_FRAMES, dt)}
         if train_info is not None and "error" not in train_info:
-            dt_t, fr_t = cpu_training_sample(sd)
-            cpu["train"] = {"value": fr_t / dt_t, "unit": "training frames/s", "kind": "port", "cores": os.cpu_count() or 1,
-                            "sample": "forward + backward of 1 clip x 1 s under torch autograd (%.2f s of CPU work)" % dt_t}
+            try:
+                dt_t, fr_t = cpu_training_sample(sd)
+                cpu["train"] = {"value": fr_t / dt_t, "unit": "training frames/s", "kind": "port", "cores": os.cpu_count() or 1,
+                                "sample": "forward + backward of 1 clip x 1 s under torch autograd (%.2f s of CPU work)" % dt_t}
+            except Exception as e:                                 # noqa: BLE001 - an extra figure must not cost the headline line
+                cpu["train"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
