@@ -65,3 +65,7 @@ GRAD_CASES.update({
     "grad_syn_attn": dict(variant="dis_embed", kwargs=_with(SYN, use_attn=True, local_atten_len=5, B=2), batch=2, n_samples=192 * 6,
                           loss_seed=81),
 })
+GRAD_CASES.update({
+    # the benchmark architecture itself (TFG_S: 6 blocks, FiLM on 5 of them), every one of its 149 parameter tensors
+    "grad_tfg_s": dict(variant="dis_embed", kwargs=SYN, batch=1, n_samples=192 * 3 - 50, loss_seed=82),
+})

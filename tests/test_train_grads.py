@@ -48,6 +48,7 @@ def test_recurrent_path_gradients(lib, inter):
 def test_whole_path_gradients_against_the_reference_fixtures(lib):
     _ok(tc.check_golden_grads(lib, "cpu", "grad_opi_d16"))
     _ok(tc.check_golden_grads(lib, "cpu", "grad_syn_b2"))
+    _ok(tc.check_golden_grads(lib, "cpu", "grad_tfg_s"))           # the benchmark architecture, all 149 tensors
 
 
 def test_conv_lstm_gradients_against_the_reference_fixtures(lib):
