@@ -550,6 +550,10 @@ int    sb_prepare_batch_fwd(const sb_prepare_args* a, void* stream);
 /* same T >= 1 frames per chunk everywhere: T = 1 is the 8 ms protocol, larger T pipelines an offline utterance in    */
 /* time slices) and reads the state arena t % 2 / writes the other one; io.film must be set for FiLM models.  Run one */
 /* eager sb_net_forward per kernel configuration before sb_pipe_create (shared-memory opt-ins cannot happen in a capture). */
+/* A range made of one intra-frame unit carries no state (DE3:819-827) and does not wait for its predecessor.           */
+/* Grouped throughput mode: with T = G > 1 frames per sb_net_io the caller may still feed ONE 8 ms window per call        */
+/* (sb_pipe_feed_chunk); the pipe gathers G consecutive windows of the rolling protocol (edge/causal_infer.py:39-40)     */
+/* into the slot's wave buffer and launches them as one T = G call; sb_pipe_flush / sb_pipe_end run a partial group.      */
 /* The only entry points of the library that create CUDA objects (streams, events, graphs); not thread-safe per pipe.*/
 /* ---------------------------------------------------------------------------------------------------------- */
 typedef struct sb_pipe sb_pipe;
@@ -558,7 +562,9 @@ int       sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_ios, 
 int       sb_pipe_destroy(sb_pipe* p);
 int       sb_pipe_begin(sb_pipe* p, void* caller_stream);   /* pipe streams wait for the caller's stream            */
 int       sb_pipe_feed(sb_pipe* p, const float* window, float* out);  /* host (pinned) or device pointers, or NULL  */
-int       sb_pipe_end(sb_pipe* p, void* caller_stream);     /* the caller's stream waits for every chunk fed so far */
+int       sb_pipe_feed_chunk(sb_pipe* p, const float* window, float* out);  /* one [B][M][n_fft] window of a group of T */
+int       sb_pipe_flush(sb_pipe* p);                        /* launch the chunks of a partial group now             */
+int       sb_pipe_end(sb_pipe* p, void* caller_stream);     /* flush + the caller's stream waits for every chunk fed */
 int       sb_pipe_reset(sb_pipe* p);                        /* chunk counter back to 0 (caller resets the state)    */
 long long sb_pipe_calls(const sb_pipe* p);
 

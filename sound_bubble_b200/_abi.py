@@ -239,6 +239,8 @@ PROTOTYPES = {
     "sb_pipe_destroy": (C.c_int, [C.c_void_p]),
     "sb_pipe_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sb_pipe_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb_pipe_feed_chunk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sb_pipe_flush": (C.c_int, [C.c_void_p]),
     "sb_pipe_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sb_pipe_reset": (C.c_int, [C.c_void_p]),
     "sb_pipe_calls": (C.c_longlong, [C.c_void_p]),

@@ -9,7 +9,7 @@ tfgridnet_causal.py (:271-401 TFGridNet.__init__, :566-684 GridNetBlock.__init__
 import torch
 import torch.nn as nn
 
-from .filterbank import stft_filters
+from .filterbank import stft_filters, stft_window
 from .packing import ModelConfig
 
 
@@ -24,10 +24,28 @@ def _wrapped_ln(n: int) -> nn.Module:          # LayerNormalization4D / 4DCF add
     return m
 
 
+class _STFTFBParams(_Bag):
+    """Buffers of asteroid_filterbanks.STFTFB.  Published releases register ``_filters`` and (0.3.x onwards) the analysis
+    window as ``torch_window``; the package is absent here, so a checkpoint may or may not carry ``torch_window``.  Both
+    load strictly: a missing window is filled with the closed form (nothing reads it - the kernels take ``_filters``)."""
+
+    def __init__(self, n_fft: int, hop: int):
+        super().__init__()
+        self.register_buffer("_filters", stft_filters(n_fft, hop))
+        self.register_buffer("torch_window", stft_window(n_fft))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        key = prefix + "torch_window"
+        if key not in state_dict:
+            state_dict[key] = self.torch_window.detach().clone()
+        elif state_dict[key].dtype != self.torch_window.dtype:          # some releases stored the numpy float64 window
+            state_dict[key] = state_dict[key].to(self.torch_window.dtype)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
 def _filterbank(n_fft: int, hop: int) -> nn.Module:
-    m, fb = _Bag(), _Bag()
-    fb.register_buffer("_filters", stft_filters(n_fft, hop))
-    m.filterbank = fb
+    m = _Bag()
+    m.filterbank = _STFTFBParams(n_fft, hop)
     return m
 
 

@@ -36,6 +36,10 @@ class NetBase(nn.Module):
         self.E = cfg.E
         self.nfft = cfg.n_fft
         self.tfgridnet = TFGridNetParams(cfg)
+        # state_dict() keys, recorded once: nn.DataParallel replicas (the reference harness wraps the model when
+        # use_dp=true, hl_module.py:34-35) keep their weights as plain attributes, not in _parameters, so state_dict() on a
+        # replica is nearly empty - _named_weights() walks these names instead
+        self._weight_names = list(self.state_dict().keys())
         self._engine = None
         self._engine_key = None
         # Whole-utterance calls on large batches run as a pipeline of time slices (streaming.PipelinedSession with
@@ -52,13 +56,25 @@ class NetBase(nn.Module):
         self.offline_inter_algo = abi.SB_ALGO_TC if cfg.D == 32 else None
 
     # -- engine (packed weights on the device of the parameters) ---------------------------------------------
-    def _weights_key(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+    def _named_weights(self) -> dict:
+        """name -> tensor for every state_dict() key, by attribute walk (works on nn.DataParallel replicas too, whose
+        tensors are autograd-connected broadcast copies held as plain attributes)."""
+        out = {}
+        for name in self._weight_names:
+            obj = self
+            for part in name.split("."):
+                obj = getattr(obj, part)
+            out[name] = obj
+        return out
+
+    def _weights_key(self, named):
+        return tuple((t.data_ptr(), t._version) for t in named.values())
 
     def engine(self) -> Engine:
-        key = self._weights_key()
+        named = self._named_weights()
+        key = self._weights_key(named)
         if self._engine is None or key != self._engine_key:
-            sd = {k: v.detach() for k, v in self.state_dict(keep_vars=True).items()}
+            sd = {k: v.detach() for k, v in named.items()}
             dev = next(iter(sd.values())).device
             _lib.require_cuda(next(iter(sd.values())))
             self._engine = Engine(_lib.load(), self.cfg, PackedWeights(sd, self.cfg, dev))
@@ -97,7 +113,7 @@ class NetBase(nn.Module):
             check_trainable(self.cfg)
         except NotImplementedError:
             return False
-        return any(p.requires_grad for p in self.parameters())
+        return any(t.requires_grad for t in self._named_weights().values())
 
     def _train_forward(self, x, dis_embed, pad=True):
         """Net.forward for a training step: same padding / cropping as _predict, gradients to every parameter through
@@ -109,7 +125,7 @@ class NetBase(nn.Module):
         if pad:
             pad_size = (self.stft_back_pad, self.stft_pad_size) if self.lookahead else (0, 0)
             x, mod = mod_pad(x, chunk_size=self.stft_chunk_size, pad=pad_size)
-        named = dict(self.state_dict(keep_vars=True))
+        named = self._named_weights()
         y, next_state = differentiable_forward_with_state(_lib.load(), self.cfg, named, x, dis_embed)
         if mod != 0:
             y = y[:, :, :-mod]
@@ -120,8 +136,8 @@ class NetBase(nn.Module):
         call).  Updates `state` in place like Engine.forward does (the reference mutates the dict it was given)."""
         cfg = self.cfg
         eng = self.engine()
-        if not self.pipeline_offline or x.dim() != 3 or x.dtype != torch.float32:
-            return None
+        if not self.pipeline_offline or x.dim() != 3 or x.dtype != torch.float32 or getattr(self, "_is_replica", False):
+            return None                                     # (DataParallel replicas live for one call: no cached pipes)
         B, M, N = x.shape
         hop, look = cfg.stft_chunk_size, cfg.n_fft - cfg.stft_chunk_size
         T = eng.n_frames(N)
@@ -172,11 +188,11 @@ class NetBase(nn.Module):
         return y
 
     def streaming(self, batch_size: int, dis_embed=None, use_graph: bool = True, pipelined: bool = False, ranges=None, depth: int = 8,
-                  intra_algo=None, inter_algo=None):
+                  intra_algo=None, inter_algo=None, frames_per_call: int = 1, group: int = 1):
         """A chunk-by-chunk session with device-resident state and captured CUDA graphs (see streaming.py).
         pipelined=True: asynchronous feed() with consecutive chunks overlapping on two streams (throughput mode)."""
         from .streaming import PipelinedSession, StreamingSession
         if pipelined:
             return PipelinedSession(self, batch_size, dis_embed, ranges=ranges, depth=depth, intra_algo=intra_algo,
-                                    inter_algo=inter_algo)
-        return StreamingSession(self, batch_size, dis_embed, use_graph=use_graph)
+                                    inter_algo=inter_algo, frames_per_call=frames_per_call, group=group)
+        return StreamingSession(self, batch_size, dis_embed, use_graph=use_graph, frames_per_call=frames_per_call)

@@ -6,6 +6,14 @@
 // owns `depth` streams; chunk t runs on stream t % depth as a few CUDA graphs (one per unit range, captured here from
 // sb_net_forward_range) and range j of chunk t waits for the event range j of chunk t-1 recorded on its own stream.
 // Per chunk the host issues 2 copies + n_ranges x (wait, graph launch, record): a few microseconds, no Python.
+// The intra-frame units carry no state (DE3:819-827 starts every frame's BiLSTM from zeros), so a range made of one
+// intra unit does not wait for its predecessor: the intra work of all chunks in flight runs side by side.
+//
+// Grouped throughput mode (sb_pipe_feed_chunk): when the sb_net_io entries describe G > 1 frames, the caller still feeds
+// ONE 8 ms window per call; the pipe gathers G consecutive windows into the slot's wave buffer (the windows of the
+// rolling protocol overlap by n_fft - stride samples, edge/causal_infer.py:39-40) and launches the group as one T = G
+// call, so that the intra-frame recurrences of G chunks share tcgen05 tiles (G x B rows per direction) and the
+// inter-frame kernel walks G steps per launch.  A partial last group is run eagerly with T = the number of pending chunks.
 //
 // All device memory (windows, results, workspaces, both state arenas) belongs to the caller and arrives inside the
 // sb_net_io array: entry k describes chunk numbers t with t % n_ios == k (n_ios = lcm(depth, 2): slot t % depth for
@@ -21,6 +29,10 @@ struct sb_pipe {
     long long n_calls = 0;
     std::vector<sb_net_io> io;
     std::vector<int> first, last;
+    std::vector<char> stateless;                // per range: 1 = a single intra-frame unit (no carried state)
+    std::vector<const float*> pend_win;         // grouped mode: windows / results of the chunks gathered so far
+    std::vector<float*> pend_out;
+    int B = 0, G = 0;
 #ifndef SB_EMU
     std::vector<cudaStream_t> streams;
     std::vector<cudaEvent_t> events;            // [depth][n_ranges]
@@ -77,7 +89,7 @@ extern "C" int sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_
                               const int* range_last, int n_ranges, sb_pipe** out) {
     using namespace sb;
     SB_REQUIRE(d && ios && range_first && range_last && out, SB_E_BADARG, "sb_pipe_create: null pointer");
-    SB_REQUIRE(depth >= 1 && depth <= 16, SB_E_BADARG, "sb_pipe_create: depth %d out of range", depth);
+    SB_REQUIRE(depth >= 1 && depth <= 64, SB_E_BADARG, "sb_pipe_create: depth %d out of range", depth);
     const int period = depth % 2 == 0 ? depth : 2 * depth;
     SB_REQUIRE(n_ios == period, SB_E_BADARG, "sb_pipe_create: need %d sb_net_io entries for depth %d, got %d", period, depth, n_ios);
     SB_REQUIRE(n_ranges >= 1 && n_ranges <= 2 * SB_MAX_BLOCKS + 2, SB_E_BADARG, "sb_pipe_create: bad number of ranges %d", n_ranges);
@@ -104,6 +116,10 @@ extern "C" int sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_
     p->io.assign(ios, ios + n_ios);
     p->first.assign(range_first, range_first + n_ranges);
     p->last.assign(range_last, range_last + n_ranges);
+    p->stateless.assign(n_ranges, 0);
+    for (int j = 0; j < n_ranges; ++j)          // units 1 + 2i are the intra-frame paths
+        p->stateless[j] = range_first[j] == range_last[j] && (range_first[j] & 1) && range_first[j] <= 2 * d->n_blocks - 1;
+    p->B = ios[0].B; p->G = ios[0].T;
     p->window_bytes = sizeof(float) * (size_t)ios[0].B * d->M * ((size_t)d->stride * ios[0].T + d->n_fft - d->stride);
     p->out_bytes = sizeof(float) * (size_t)ios[0].B * d->n_src * d->stride * ios[0].T;
     p->streams.assign(depth, nullptr);
@@ -158,10 +174,87 @@ extern "C" int sb_pipe_reset(sb_pipe* p) {
     using namespace sb;
     SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_reset: null pipe");
     p->n_calls = 0;
+    p->pend_win.clear();
+    p->pend_out.clear();
     return 0;
 }
 
 extern "C" long long sb_pipe_calls(const sb_pipe* p) { return p ? p->n_calls : -1; }
+
+#ifndef SB_EMU
+namespace sb {
+// one call of the launch sequence on the slot's stream: per range (wait for the same range of the previous call unless
+// it is stateless, run, record).  n_frames == 0: replay the captured graphs; otherwise an eager T = n_frames call.
+static int run_ranges(sb_pipe* p, long long t, int n_frames) {
+    const int slot = (int)(t % p->depth), k = (int)(t % p->n_ios), R = p->n_ranges;
+    cudaStream_t st = p->streams[slot];
+    const cudaEvent_t* prev = &p->events[(size_t)((t + p->depth - 1) % p->depth) * R];
+    cudaEvent_t* mine = &p->events[(size_t)slot * R];
+    sb_net_io tail = p->io[k];
+    if (n_frames > 0) tail.T = n_frames;
+    for (int j = 0; j < R; ++j) {
+        if (t > 0 && p->depth > 1 && !p->stateless[j]) SB_CUDA(cudaStreamWaitEvent(st, prev[j], 0));
+        if (n_frames > 0) SB_CHECK(sb_net_forward_range(p->desc, &tail, p->first[j], p->last[j], st));
+        else SB_CUDA(cudaGraphLaunch(p->graphs[(size_t)k * R + j], st));
+        if (!p->stateless[j]) SB_CUDA(cudaEventRecord(mine[j], st));
+    }
+    return 0;
+}
+
+// launches the chunks gathered so far as one call of n = pend_win.size() frames (n == G: the captured graphs)
+static int launch_group(sb_pipe* p) {
+    const int n = (int)p->pend_win.size();
+    if (n == 0) return 0;
+    const long long t = p->n_calls;
+    const int slot = (int)(t % p->depth), k = (int)(t % p->n_ios);
+    cudaStream_t st = p->streams[slot];
+    const sb_net_io& io = p->io[k];
+    const sb_net_desc* d = p->desc;
+    const size_t hop = (size_t)d->stride, nfft = (size_t)d->n_fft;
+    const size_t in_pitch = sizeof(float) * (hop * n + nfft - hop), out_pitch = sizeof(float) * hop * n;
+    for (int c = 0; c < n; ++c)                 // window c covers samples [c*hop, c*hop + n_fft) of the group's wave
+        SB_CUDA(cudaMemcpy2DAsync(const_cast<float*>(io.wave) + c * hop, in_pitch, p->pend_win[c], sizeof(float) * nfft,
+                                  sizeof(float) * nfft, (size_t)p->B * d->M, cudaMemcpyDefault, st));
+    SB_CHECK(run_ranges(p, t, n == p->G ? 0 : n));
+    for (int c = 0; c < n; ++c)
+        if (p->pend_out[c])
+            SB_CUDA(cudaMemcpy2DAsync(p->pend_out[c], sizeof(float) * hop, io.wave_out + c * hop, out_pitch,
+                                      sizeof(float) * hop, (size_t)p->B * d->n_src, cudaMemcpyDefault, st));
+    p->pend_win.clear();
+    p->pend_out.clear();
+    p->n_calls = t + 1;
+    return 0;
+}
+}  // namespace sb
+#endif
+
+/* Grouped mode: one 8 ms window [B][M][n_fft] per call (host, pinned for asynchronous copies, or device); the result    */
+/* [B][S][stride] lands in `out` (may be NULL) once the chunk's group of G = ios[].T frames has run.  The window must stay  */
+/* untouched until its group has been launched (G calls later, or sb_pipe_flush / sb_pipe_end).                          */
+extern "C" int sb_pipe_feed_chunk(sb_pipe* p, const float* window, float* out) {
+    using namespace sb;
+    SB_REQUIRE(p && window, SB_E_BADARG, "sb_pipe_feed_chunk: null pipe / window");
+#ifndef SB_EMU
+    p->pend_win.push_back(window);
+    p->pend_out.push_back(out);
+    if ((int)p->pend_win.size() == p->G) return launch_group(p);
+    return 0;
+#else
+    (void)out;
+    return SB_E_UNSUPP;
+#endif
+}
+
+/* Runs the chunks of a partial group now (eager T = pending call on the slot's stream). */
+extern "C" int sb_pipe_flush(sb_pipe* p) {
+    using namespace sb;
+    SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_flush: null pipe");
+#ifndef SB_EMU
+    return launch_group(p);
+#else
+    return 0;
+#endif
+}
 
 /* Enqueues one chunk of T frames and returns.  window: [B][M][stride*T + n_fft - stride] floats, host (pinned for a     */
 /* truly asynchronous copy) or device, NULL = the slot's window buffer was filled by the caller; out: [B][S][stride*T],   */
@@ -170,18 +263,13 @@ extern "C" int sb_pipe_feed(sb_pipe* p, const float* window, float* out) {
     using namespace sb;
     SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_feed: null pipe");
 #ifndef SB_EMU
+    SB_REQUIRE(p->pend_win.empty(), SB_E_BADARG, "sb_pipe_feed: chunks of a group are pending (sb_pipe_feed_chunk); flush first");
     const long long t = p->n_calls;
-    const int slot = (int)(t % p->depth), k = (int)(t % p->n_ios), R = p->n_ranges;
+    const int slot = (int)(t % p->depth), k = (int)(t % p->n_ios);
     cudaStream_t st = p->streams[slot];
     const sb_net_io& io = p->io[k];
     if (window) SB_CUDA(cudaMemcpyAsync(const_cast<float*>(io.wave), window, p->window_bytes, cudaMemcpyDefault, st));
-    const cudaEvent_t* prev = &p->events[(size_t)((t + p->depth - 1) % p->depth) * R];
-    cudaEvent_t* mine = &p->events[(size_t)slot * R];
-    for (int j = 0; j < R; ++j) {
-        if (t > 0 && p->depth > 1) SB_CUDA(cudaStreamWaitEvent(st, prev[j], 0));   // unit range j of the previous chunk
-        SB_CUDA(cudaGraphLaunch(p->graphs[(size_t)k * R + j], st));
-        SB_CUDA(cudaEventRecord(mine[j], st));
-    }
+    SB_CHECK(run_ranges(p, t, 0));
     if (out) SB_CUDA(cudaMemcpyAsync(out, io.wave_out, p->out_bytes, cudaMemcpyDefault, st));
     p->n_calls = t + 1;
     return 0;
@@ -196,6 +284,7 @@ extern "C" int sb_pipe_end(sb_pipe* p, void* caller_stream) {
     using namespace sb;
     SB_REQUIRE(p, SB_E_BADARG, "sb_pipe_end: null pipe");
 #ifndef SB_EMU
+    SB_CHECK(launch_group(p));
     for (int s = 0; s < p->depth; ++s) {
         SB_CUDA(cudaEventRecord(p->joins[s], p->streams[s]));
         SB_CUDA(cudaStreamWaitEvent((cudaStream_t)caller_stream, p->joins[s], 0));

@@ -54,8 +54,8 @@ class Engine:
         ws = self._ws.get(key)
         if ws is None:
             n = self.lib.sb_workspace_floats(self.packed.desc_ref(), B, T)
-            if len(self._ws) > 4:
-                self._ws.clear()
+            if len(self._ws) > 4:                           # eager calls only: sessions own their workspaces (a captured
+                self._ws.clear()                            # graph keeps raw pointers, so it must never read this cache)
             ws = torch.empty(max(int(n), 1), dtype=torch.float32, device=device)
             self._ws[key] = ws
         return ws
@@ -179,10 +179,10 @@ class Engine:
 
     def forward(self, wave: torch.Tensor, dis_embed: Optional[torch.Tensor], state: dict,
                 out: Optional[torch.Tensor] = None, new_state: Optional[dict] = None,
-                film: Optional[torch.Tensor] = None):
+                film: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
         """wave [B, M, stride*T + n_fft - stride] -> ([B, S, stride*T], state).  `state` is updated in place (the
         dict, as the reference does, DE3:547-552) with freshly written tensors unless `new_state` supplies them."""
-        call = self.prepare(wave, dis_embed, state, out=out, new_state=new_state, film=film)
+        call = self.prepare(wave, dis_embed, state, out=out, new_state=new_state, film=film, workspace=workspace)
         call.launch()
         return call.out, call.commit()
 

@@ -12,6 +12,11 @@ import numpy as np
 import torch
 
 
+def stft_window(n_fft: int) -> torch.Tensor:
+    """STFTFB's default analysis window, ``sqrt(hanning(n_fft + 1)[:-1])``, as its ``torch_window`` buffer holds it."""
+    return torch.from_numpy(np.hanning(n_fft + 1)[:-1] ** 0.5).float()
+
+
 def stft_filters(n_fft: int, hop: int) -> torch.Tensor:
     window = np.hanning(n_fft + 1)[:-1] ** 0.5
     basis = np.fft.fft(np.eye(n_fft)) / (0.5 * np.sqrt(n_fft * n_fft / hop))

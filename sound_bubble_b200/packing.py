@@ -56,6 +56,13 @@ class ModelConfig:
             raise NotImplementedError("stft_back_pad > 0 (causal_decoder, DE3:423-431) is not implemented")
         if self.merge_method not in ("None", "early_cat"):
             raise NotImplementedError("merge_method %r (DE3:334-347 knows 'None' and 'early_cat')" % self.merge_method)
+        if self.H != 64 or self.D not in (16, 32):
+            raise NotImplementedError(
+                "the sm_100a kernels are built for H=64 and D in {16, 32} (every shipped reference config: "
+                "syn_experiments/*.json D=32, real_experiments/*.json D=16/32, all H=64); got D=%d, H=%d" % (self.D, self.H))
+        if not (1 <= self.num_ch <= 8) or not (1 <= self.num_src <= 2):
+            raise NotImplementedError("1..8 microphones and 1..2 sources are supported, got num_ch=%d, num_src=%d"
+                                      % (self.num_ch, self.num_src))
         assert self.n_fft % 2 == 0                                  # DE3:307
         if self.use_attn:
             assert self.D % self.L == 0                             # DE3:641
@@ -120,7 +127,7 @@ def _lstm_dir(sd, prefix: str, sfx: str, H: int) -> Dict[str, torch.Tensor]:
         v = m.reshape(4, 2, H // 2, 4, kpt)                 # (g, ab, ur, kq, k): unit = ab*32 + ur, column = kq*kpt + k
         return v.permute(4, 1, 2, 3, 0).reshape(kpt, 2, 2 * H, 4).contiguous()
     return {"w_tile": w_tile, "b_tile": b_tile, "w_lane": w_lane, "b_lane": b_lane,
-            "w_rec": two_unit(w_hh, 16), "w_xp": two_unit(w_ih, C // 4)}
+            "w_rec": two_unit(w_hh, H // 4), "w_xp": two_unit(w_ih, C // 4)}
 
 
 def _bf16_split(m: torch.Tensor):

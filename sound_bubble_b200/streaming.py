@@ -47,6 +47,10 @@ class StreamingSession:
                 raise KeyError("dis_embed")
             self.dis = dis_embed.to(dev, torch.float32).contiguous().clone()
         self.film = self.engine.film_table(self.dis) if self.dis is not None else None      # time-invariant: once
+        # the session's own workspace: the captured graphs hold its raw pointer, so it must not come from (and be evicted
+        # with) the engine's cache of eager-call workspaces
+        n_ws = max(int(self.engine.lib.sb_workspace_floats(self.engine.packed.desc_ref(), batch_size, frames_per_call)), 1)
+        self.ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
         # two state arenas that alternate; each is ONE flat device buffer with the reference-layout dict as views into it
         self.arenas = [StateArena(init_state(cfg, batch_size, dev)) for _ in (0, 1)]
         self.states = [a.state for a in self.arenas]
@@ -59,7 +63,7 @@ class StreamingSession:
     # ------------------------------------------------------------------------------------------------------
     def _step_eager(self, p: int):
         src, dst = self.states[p], self.states[p ^ 1]
-        self.engine.forward(self.x, self.dis, _shallow(src), out=self.y, new_state=dst, film=self.film)
+        self.engine.forward(self.x, self.dis, _shallow(src), out=self.y, new_state=dst, film=self.film, workspace=self.ws)
 
     def _capture(self):
         saved = [_clone_state(s) for s in self.states]
@@ -151,7 +155,17 @@ class PipelinedSession:
     immediately; `out` may be a pinned host tensor), ``end()`` to make the caller's stream wait for everything fed."""
 
     def __init__(self, net, batch_size: int, dis_embed: Optional[torch.Tensor] = None, ranges=None, depth: int = 8,
-                 intra_algo: Optional[int] = None, inter_algo: Optional[int] = None, frames_per_call: int = 1):
+                 intra_algo: Optional[int] = None, inter_algo: Optional[int] = None, frames_per_call: int = 1,
+                 group: int = 1):
+        """group = G > 1: grouped throughput mode.  feed() still takes ONE 8 ms window per call, the native pipe gathers G
+        consecutive windows and launches them as one G-frame call (`depth` groups in flight), so the intra-frame
+        recurrences of G chunks share 128-row tcgen05 tiles.  The result of a chunk lands in its `out` once its group has
+        run; a window must stay untouched until then (G calls later, flush() or end())."""
+        if group < 1 or (group > 1 and frames_per_call != 1):
+            raise ValueError("group must be >= 1 and excludes frames_per_call > 1")
+        self.group = group
+        if group > 1:
+            frames_per_call = group
         self.net = net
         self.cfg = cfg = net.cfg
         self.engine = eng = net.engine()
@@ -199,14 +213,21 @@ class PipelinedSession:
         # (212k instead of 192k frames/s at batch 32).
         if intra_algo is None and eng.intra_algo == abi.SB_ALGO_AUTO and batch_size >= 8 and frames_per_call == 1:
             intra_algo = abi.SB_ALGO_WS2
+        # grouped mode: G x B rows per direction on the tcgen05 kernel (a fifth of the SM-time of the SIMT recurrence per
+        # sequence) once they fill most of a 128-row tile
+        if intra_algo is None and eng.intra_algo == abi.SB_ALGO_AUTO and group > 1 and cfg.D == 32 and not cfg.conv_lstm \
+                and batch_size * group >= 96:
+            intra_algo = abi.SB_ALGO_TC
         self.intra_algo = intra_algo          # None = the engine's choice (SB_ALGO_AUTO unless the caller forced one)
         # Throughput mode pays in SM-time, not latency: the one-step inter-frame call as a tcgen05 GEMM occupies a quarter
         # of the SMs the SIMT tile kernel needs (128-row tiles), which leaves room for the other chunks' recurrences.
         if inter_algo is None and eng.inter_algo == abi.SB_ALGO_AUTO and cfg.D == 32 and batch_size * cfg.n_freqs >= 1024 \
-                and frames_per_call == 1:
+                and (frames_per_call == 1 or group > 1):
             inter_algo = abi.SB_ALGO_TC
         self.inter_algo = inter_algo
         self.n_calls = 0
+        self.n_chunks = 0
+        self._pending = []
         self._pipe = None
         self._build()
 
@@ -264,6 +285,8 @@ class PipelinedSession:
         for a in self.arenas:
             a.flat.zero_()
         self.n_calls = 0
+        self.n_chunks = 0
+        self._pending.clear()
         lib = self.engine.lib
         abi.check(lib, lib.sb_pipe_reset(self._pipe), "sb_pipe_reset")
 
@@ -276,6 +299,8 @@ class PipelinedSession:
     def feed(self, window: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Enqueue one chunk: window [B, M, chunk + lookahead] (pinned host or device) -> `out` [B, S, chunk] (or the
         slot's device buffer, valid until `depth` calls later).  Returns without waiting."""
+        if self.group > 1:
+            return self._feed_chunk(window, out)
         slot = self.n_calls % self.depth
         if window.shape != self.x[slot].shape or window.dtype != torch.float32 or not window.is_contiguous():
             raise ValueError("window must be a contiguous float32 tensor of shape %s" % (tuple(self.x[slot].shape),))
@@ -289,8 +314,36 @@ class PipelinedSession:
         self.n_calls += 1
         return out if out is not None else self.y[slot]
 
+    def _feed_chunk(self, window: torch.Tensor, out: Optional[torch.Tensor]):
+        cfg = self.cfg
+        wshape, oshape = (self.B, cfg.num_ch, cfg.n_fft), (self.B, cfg.num_src, cfg.stft_chunk_size)
+        if tuple(window.shape) != wshape or window.dtype != torch.float32 or not window.is_contiguous():
+            raise ValueError("window must be a contiguous float32 tensor of shape %s" % (wshape,))
+        if out is None:
+            raise ValueError("grouped mode needs an `out` tensor per chunk (the slot's buffer holds the whole group)")
+        if tuple(out.shape) != oshape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 tensor of shape %s" % (oshape,))
+        lib = self.engine.lib
+        abi.check(lib, lib.sb_pipe_feed_chunk(self._pipe, window.data_ptr(), out.data_ptr()), "sb_pipe_feed_chunk")
+        self._pending.append((window, out))                 # keep the tensors alive until their group is launched
+        self.n_chunks += 1
+        if len(self._pending) == self.group:
+            self._pending.clear()
+            self.n_calls += 1
+        return out
+
+    def flush(self):
+        """Grouped mode: run the chunks of a partial group now."""
+        lib = self.engine.lib
+        abi.check(lib, lib.sb_pipe_flush(self._pipe), "sb_pipe_flush")
+        if self._pending:
+            self._pending.clear()
+            self.n_calls += 1
+
     def end(self):
-        """Make the caller's current stream wait for every chunk fed so far."""
+        """Make the caller's current stream wait for every chunk fed so far (a partial group is run first)."""
+        if self._pending:
+            self.flush()
         lib = self.engine.lib
         abi.check(lib, lib.sb_pipe_end(self._pipe, self._cur()), "sb_pipe_end")
 

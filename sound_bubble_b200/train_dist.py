@@ -4,7 +4,9 @@
   * ``FlatGradReducer``: every parameter's ``.grad`` is a view into ONE flat fp32 buffer (2.0 MB for the TFG_S model), so
     the gradient exchange of a step is a single ``all_reduce`` (NCCL over NVLink on a GPU box, Gloo in the CPU tests),
     followed by the division by the world size: the reference's loss is the mean over the GLOBAL batch (:321), so
-    per-rank mean-loss gradients are averaged, not summed.
+    per-rank mean-loss gradients are averaged, not summed.  With ragged shards (a last partial batch, fewer items than
+    ranks) pass each rank's item count: the gradients are then weighted by it and the count travels in the same
+    collective (one extra float), which reproduces the global-batch mean exactly; an empty shard contributes zero.
   * ``clip_grad_norm_`` on the reduced flat buffer: the reference clips the already-reduced DataParallel gradients
     (:433-441), so the order is reduce -> clip -> optimizer step.
   * ``dump_state / load_state``: the checkpoint layout of PLModule (:115-156) with the model saved WITHOUT a wrapper
@@ -29,7 +31,8 @@ class FlatGradReducer:
         dev, dt = self.params[0].device, torch.float32
         self.group = group
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
+        self._buf = torch.zeros(self.numel + 1, dtype=dt, device=dev)      # + one slot for the item count
+        self.flat = self._buf[:self.numel]
         off = 0
         for p in self.params:
             if p.dtype != dt or p.device != dev:
@@ -49,14 +52,25 @@ class FlatGradReducer:
                 raise RuntimeError("a parameter's .grad no longer aliases the flat buffer (zero_grad(set_to_none=True)?)")
             off += p.numel()
 
-    def all_reduce_mean(self):
-        """ONE collective for the whole model, then the mean over ranks."""
+    def all_reduce_mean(self, n_local: Optional[int] = None):
+        """ONE collective for the whole model, then the mean over ranks (equal shards), or - with `n_local` = the number of
+        items this rank's mean loss was taken over - the item-weighted mean, i.e. the gradient of the global-batch mean
+        loss whatever the shard sizes.  A rank with n_local == 0 contributes nothing (its local loss is NaN: 0 / 0)."""
         self.check_views()
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size(self.group)
             if world > 1:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-                self.flat.div_(world)
+                if n_local is None:
+                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                    self.flat.div_(world)
+                    return
+                if n_local > 0:
+                    self.flat.mul_(float(n_local))
+                else:
+                    self.flat.zero_()
+                self._buf[self.numel] = float(n_local)
+                dist.all_reduce(self._buf, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.div_(self._buf[self.numel].clamp_min(1.0))
 
     def clip_grad_norm_(self, max_norm: Optional[float]) -> torch.Tensor:
         """torch.nn.utils.clip_grad_norm_ semantics (2-norm, coefficient clamped to 1) on the flat buffer."""
@@ -67,9 +81,11 @@ class FlatGradReducer:
         return total
 
 
-def backprop(reducer: FlatGradReducer, optimizer, grad_clip: Optional[float] = None) -> torch.Tensor:
-    """PLModule.backprop (:433-441) for one rank of a data-parallel job: reduce -> clip -> step."""
-    reducer.all_reduce_mean()
+def backprop(reducer: FlatGradReducer, optimizer, grad_clip: Optional[float] = None,
+             n_local: Optional[int] = None) -> torch.Tensor:
+    """PLModule.backprop (:433-441) for one rank of a data-parallel job: reduce -> clip -> step.  `n_local`: see
+    FlatGradReducer.all_reduce_mean (needed when the ranks' shards differ in size)."""
+    reducer.all_reduce_mean(n_local)
     norm = reducer.clip_grad_norm_(grad_clip)
     optimizer.step()
     return norm

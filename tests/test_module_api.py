@@ -47,9 +47,54 @@ def test_state_dict_layout_matches_reference_checkpoint(name):
     ocfg = OracleConfig.from_kwargs(case["variant"], **case["kwargs"])
     want = param_shapes(ocfg)
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    # asteroid_filterbanks.STFTFB also registers its analysis window (`torch_window`); nothing on the path reads it
+    windows = {k: got.pop(k) for k in list(got) if k.endswith("filterbank.torch_window")}
+    assert windows == {"tfgridnet.enc.filterbank.torch_window": (ocfg.n_fft,), "tfgridnet.dec.filterbank.torch_window": (ocfg.n_fft,)}
     assert list(got) == list(want)
     assert got == want
-    m.load_state_dict(make_state_dict(ocfg, 0), strict=True)
+    sd = make_state_dict(ocfg, 0)
+    m.load_state_dict(sd, strict=True)                      # a checkpoint written without torch_window
+    with_window = dict(sd)
+    for k in windows:
+        with_window[k] = torch.hann_window(ocfg.n_fft, periodic=True, dtype=torch.float64).sqrt()
+    m.load_state_dict(with_window, strict=True)             # ... and one written with it (float64 in some releases)
+    assert m.state_dict()["tfgridnet.enc.filterbank.torch_window"].dtype == torch.float32
+    assert torch.allclose(m.state_dict()["tfgridnet.enc.filterbank.torch_window"], with_window[list(windows)[0]].float(), atol=1e-6)
+
+
+def test_unsupported_sizes_are_rejected_in_the_constructor():
+    """The reference's own constructor defaults (D=64, H=128; DE3/net.py:21-26) are outside what the kernels are built
+    for: that must be a clear error at construction, not a shape error at the first forward."""
+    for cls in (Net, NetOptim):
+        with pytest.raises(NotImplementedError, match="H=64"):
+            cls()
+    for bad in (dict(D=64), dict(D=24), dict(H=128), dict(num_ch=9), dict(stft_back_pad=32)):
+        with pytest.raises(NotImplementedError):
+            Net(**dict(SYN, **bad))
+
+
+def test_weights_are_found_on_data_parallel_replicas():
+    """PLModule wraps the model in nn.DataParallel when use_dp=true (hl_module.py:34-35); replicas hold their weights as
+    plain attributes, so state_dict() on them is nearly empty.  The drop-in gathers weights by name instead."""
+    m = Net(**SYN)
+    names = list(m.state_dict().keys())
+    # what torch.nn.parallel.replicate does, on one device
+    mods, reps = list(m.modules()), [x._replicate_for_data_parallel() for x in m.modules()]
+    idx = {mod: i for i, mod in enumerate(mods)}
+    for i, mod in enumerate(mods):
+        r = reps[i]
+        for key, child in mod._modules.items():
+            r._modules[key] = reps[idx[child]] if child is not None else None
+        for key, p in mod._parameters.items():
+            setattr(r, key, p.detach().clone().requires_grad_(p.requires_grad) if p is not None else None)
+        for key, b in mod._buffers.items():
+            r._buffers[key] = b
+    rep = reps[0]
+    assert len(rep.state_dict()) < len(names)               # the situation the walk exists for
+    got = rep._named_weights()
+    assert list(got) == names
+    assert all(torch.equal(got[k], v) for k, v in m.state_dict().items())
+    assert rep._wants_grad(None) == m._wants_grad(None)
 
 
 def test_filterbank_buffer_is_bit_identical_to_the_oracle_basis():

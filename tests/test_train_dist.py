@@ -89,6 +89,48 @@ def test_one_all_reduce_gives_the_global_batch_gradients():
     assert float(torch.linalg.vector_norm(ref)) <= clip * 1.0001        # the clip was active in this case
 
 
+def _ragged_worker(rank, world, port, n, clip, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        m = Tiny()
+        red = FlatGradReducer(m.parameters())
+        opt = torch.optim.SGD(m.parameters(), lr=0.0)
+        x, y = _data(n)
+        lo, hi = shard_bounds(n, world, rank)
+        red.zero_grad()
+        if hi > lo:
+            ((m(x[lo:hi]) - y[lo:hi]) ** 2).mean(dim=(1, 2)).mean().backward()
+        else:
+            red.flat.fill_(float("nan"))                        # what a mean over an empty shard would leave behind
+        backprop(red, opt, grad_clip=clip, n_local=hi - lo)
+        q.put((rank, hi - lo, red.flat.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ragged_and_empty_shards_still_give_the_global_batch_mean():
+    for n in (3, 1):                                            # 2 + 1 items, and 1 + 0 (an empty shard)
+        world, clip = 2, 10.0
+        port = _free_port()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_ragged_worker, args=(r, world, port, n, clip, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=180) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+        assert sorted(r[1] for r in res) == sorted([n - n // 2, n // 2]) or sum(r[1] for r in res) == n
+        ref = _single_process_reference(n, clip)
+        for rank, _, flat in res:
+            flat = torch.tensor(flat)
+            assert torch.isfinite(flat).all()
+            assert torch.allclose(flat, ref, atol=1e-6, rtol=1e-5), (n, float((flat - ref).abs().max()))
+
+
 def test_views_survive_steps_and_checkpoint_layout(tmp_path):
     torch.manual_seed(1)
     m = Tiny()
