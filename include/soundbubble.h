@@ -48,6 +48,9 @@ extern "C" {
 #define SB_ALGO_LANE4 4         /* 4 sequences per CTA                                                           */
 #define SB_ALGO_TILE4 6         /* tile family with 4 sequences per warp (C = 32 only; chosen by TILE for 1-2 step calls) */
 #define SB_ALGO_TC    7         /* tcgen05: 128 sequences per CTA, gate GEMM on the tensor cores as a bf16 hi/lo split   */
+#define SB_ALGO_TCP   9         /* the same arithmetic as a warp-specialised pipeline: TMA tensor loads of the TF grid   */
+                                /* (cp.async.bulk.tensor), LayerNorm / output warps, one MMA-issuing thread, 8 cell-update */
+                                /* warps, mbarriers instead of block barriers (sb_lstm_tcp.cu; C = 32, projected mode)     */
                                 /* (3 products, fp32 accumulation in TMEM), cell update from TMEM (C = 32, projected mode) */
 #define SB_ALGO_WS2   8         /* the WS kernel with 2 sequences per CTA sharing the weights in registers, their steps     */
                                 /* interleaved phase by phase: 1.6x the latency, 0.81x the SM-time per sequence             */

@@ -30,5 +30,8 @@ __device__ __forceinline__ long long row_base(const SeqArgs& a, int row) {
 int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t st);
 // tcgen05 variant (sb_lstm_tc.cu): C = 32, H = 64, projected mode only
 int run_seq_tc(const SeqArgs& a, cudaStream_t st);
+// warp-specialised tcgen05 + TMA variant (sb_lstm_tcp.cu): same conditions, plus a TMA-addressable activation layout
+int run_seq_tcp(const SeqArgs& a, cudaStream_t st);
+bool seq_tcp_supported(const SeqArgs& a);
 
 }  // namespace sb

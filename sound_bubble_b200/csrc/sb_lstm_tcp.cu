@@ -1,0 +1,594 @@
+// Warp-specialised tcgen05 / TMEM / TMA sequence kernel (SB_ALGO_TCP): the pipelined successor of lstm_tc_kernel.
+//
+// Same arithmetic, operand images and summation order as lstm_tc_kernel (sb_lstm_tc.cu): [FiLM] -> LayerNorm(C) ->
+// [LN(x) | h] W^T + b as the three-term bf16 hi/lo split on the 5th-generation tensor cores -> cell -> Linear -> residual.
+// Reference: GridNetBlock.forward intra / inter branches, DE3 tfgridnet_causal.py:794-849.
+//
+// What changed is WHO does what, so that the 145 (intra) / T (inter) dependent steps carry as little as possible:
+//
+//   warps 0-3  "stream" group, thread = tile row:
+//        * lane 0 of warp 0 is the TMA producer: the [128 rows x C] fp32 slab of every step is pulled from the TF grid
+//          with cp.async.bulk.tensor (4-D tensor map over [outer][pos|row][row|pos][C], 128-byte swizzle, SASS UTMALDG)
+//          into a ring of 16 KB stages, several steps ahead of its use; completion is counted by an mbarrier.
+//        * every thread turns its row of the NEXT step into LayerNorm(FiLM(x0 [+ x1])) as bf16 hi/lo in the x part of the
+//          A operand while the cell update of the current step runs, keeps x' for the residual, and - once the projection
+//          of h_{s-1} (issued with step s) has landed in TMEM - stores y_{s-1} = x' + b + lin h_{s-1} as full 128-byte rows.
+//        * lane 0 of warp 1 issues the tcgen05.mma of a step the moment the 8 cell-update warps have published h:
+//          18 MMAs (N = 128) for units 0..31 + commit, 18 for units 32..63, 12 (N = 32) for the projection + commit.
+//   warps 4-11 cell-update group, thread = (row, half of the units): tcgen05.ld of its 128 gate columns in four chunks
+//          (the load of chunk k+1 in flight while chunk k is evaluated), bias, sigmoid / tanh, c in registers for the
+//          whole sequence, h back into the A operand as bf16 hi/lo, fence.proxy.async, ONE mbarrier arrive per warp.
+//
+// No __syncthreads in the step loop: full[] (TMA bytes), gates[2] (tcgen05.commit) and hready (8 warp arrivals) are
+// mbarriers; the stream group uses one 128-thread named barrier per step.  Every wait is bounded and traps.
+//
+// Rows are tiled so that a TMA box never straddles an outer index (utterance): per outer index floor(rows_inner / 128)
+// full tiles, and the remaining rows_inner % 128 rows of floor(128 / tail) consecutive outer indices share one tile
+// (F = 145: one full tile per utterance + 17-row tails of 7 utterances per tile; 37 tiles at batch 32, as before).
+#include "sb_common.cuh"
+#include "sb_lstm.cuh"
+
+#ifndef SB_EMU
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+#endif
+
+namespace sb {
+
+#ifndef SB_EMU
+
+namespace tcp {
+
+constexpr int kRows = 128, kC = 32, kH = 64, kK = kC + kH, kN = 4 * kH;
+constexpr int kThreads = 384;
+constexpr int kAChunkBytes = (kRows / 8) * 128;            // LBO of A: 2048
+constexpr int kWChunkBytes = (kN / 8) * 128;               // LBO of the gate matrix: 4096
+constexpr int kPChunkBytes = (kC / 8) * 128;               // LBO of the projection: 512
+constexpr int kABytes = kRows * kK * 2, kWBytes = kN * kK * 2, kPBytes = kC * kH * 2;
+constexpr int kSlabBytes = kRows * kC * 4;                 // one [128][32] fp32 stage = one TMA box
+constexpr int kSlabs = 4;
+constexpr int kOffW = kSlabs * kSlabBytes;                 // packed operand images: gate hi, gate lo, proj hi, proj lo
+constexpr int kOffA = kOffW + 2 * kWBytes + 2 * kPBytes;   // A hi, A lo
+constexpr int kOffBias = kOffA + 2 * kABytes;
+constexpr int kOffLn = kOffBias + kN * 4;                  // LayerNorm gain, bias, projection bias: 3 x [C]
+constexpr int kOffBar = kOffLn + 3 * kC * 4;
+constexpr int kSmemBytes = kOffBar + 256 + 1024;           // + barriers + slack for the 1024-byte alignment of the stages
+constexpr uint32_t kTmemCols = 512;                        // 256 gate columns + 32 projection columns -> next power of 2
+
+struct Geom {
+    int mode;           // 0: pos is dim 1, rows are dim 2 (intra: rows (b,t), steps f); 1: rows dim 1, pos dim 2 (inter)
+    int n_outer;        // n_rows / rows_inner
+    int nfull;          // full 128-row tiles per outer index
+    int tail;           // rows_inner % 128
+    int P;              // outer indices whose tails share a tile
+    int n_full_tiles;   // n_outer * nfull
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;                                         // SmemDescriptor: no swizzle, K-major
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // f32 acc, bf16 x bf16
+}
+__device__ __forceinline__ void umma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error must end in a trap, not in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (long long spin = 0; spin < (1ll << 26); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// issue only; the registers are valid after tmem_wait_ld() + pin()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// keeps the compiler from using registers of an asynchronous tcgen05.ld before the wait that precedes this call
+__device__ __forceinline__ void pin(uint32_t (&r)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
+}
+
+// 8 consecutive k of one row -> one 16-byte core-matrix row in the hi image and one in the lo image
+__device__ __forceinline__ void store_split8(unsigned char* a_hi, unsigned char* a_lo, int row, int chunk, const float (&v)[8]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const float r0 = v[2 * i] - __bfloat162float(h2.x), r1 = v[2 * i + 1] - __bfloat162float(h2.y);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    const int off = ((chunk * (kRows / 8) + (row >> 3)) * 8 + (row & 7)) * 16;
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+}  // namespace tcp
+
+__global__ void __launch_bounds__(tcp::kThreads, 1)
+lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUtensorMap map_x0,
+                const __grid_constant__ CUtensorMap map_x0_tail, const __grid_constant__ CUtensorMap map_x1,
+                const __grid_constant__ CUtensorMap map_x1_tail) {
+    using namespace tcp;
+    extern __shared__ unsigned char sm_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* slabs = sm;
+    unsigned char* w_hi = sm + kOffW;
+    unsigned char* w_lo = w_hi + kWBytes;
+    unsigned char* p_hi = w_lo + kWBytes;
+    unsigned char* p_lo = p_hi + kPBytes;
+    unsigned char* a_hi = sm + kOffA;
+    unsigned char* a_lo = a_hi + kABytes;
+    float* bias_s = reinterpret_cast<float*>(sm + kOffBias);
+    float* ln_s = reinterpret_cast<float*>(sm + kOffLn);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kOffBar);
+    uint64_t* full = bars;                                  // [kSlabs]  TMA bytes of a step's stage(s)
+    uint64_t* gates = bars + kSlabs;                        // [2]       tcgen05.commit: units 0..31 | everything
+    uint64_t* hready = bars + kSlabs + 2;                   //           8 cell-update warps have published h
+    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(bars + kSlabs + 3);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kSlabs + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const sb_lstm_dir& w = a.w[dir];
+    const int S = a.n_steps;
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+    const int r = 32 * q + lane;                            // tile row of this thread
+    const int nld = a.x1 ? 2 : 1;                           // stages per step
+    const int nslots = kSlabs / nld;
+
+    // ---- tile geometry: which (outer, inner) row this thread owns ----------------------------------------------------
+    const int tile = blockIdx.x;
+    const bool tail_tile = tile >= g.n_full_tiles;
+    int outer0, inner0;                                     // first row of the tile (full tile) / first outer index (tail tile)
+    int o_row, i_row;
+    bool valid;
+    if (!tail_tile) {
+        outer0 = tile / g.nfull;
+        inner0 = (tile - outer0 * g.nfull) * kRows;
+        o_row = outer0; i_row = inner0 + r; valid = true;
+    } else {
+        outer0 = (tile - g.n_full_tiles) * g.P;
+        inner0 = g.nfull * kRows;
+        const int qq = r / g.tail;
+        o_row = outer0 + qq; i_row = inner0 + (r - qq * g.tail);
+        valid = qq < g.P && o_row < g.n_outer;
+    }
+    const int grow = valid ? o_row * a.rows_inner + i_row : 0;                 // global row: state and FiLM index
+    const long long rbase = valid ? (long long)o_row * a.stride_outer + (long long)i_row * a.stride_inner : 0;
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------------
+    for (int i = tid; i < kN; i += kThreads) bias_s[i] = __ldg(w.tc_b + i);
+    if (tid < kC) {
+        ln_s[tid] = __ldg(w.ln_g + tid);
+        ln_s[kC + tid] = __ldg(w.ln_b + tid);
+        ln_s[2 * kC + tid] = dir == 0 ? __ldg(w.lin_b + tid) : 0.0f;       // direction 0 adds the projection bias
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < kSlabs; ++i) mbar_init(full + i, 1);
+        mbar_init(gates + 0, 1);
+        mbar_init(gates + 1, 1);
+        mbar_init(hready, 8);
+        bulk_barrier_init(wbar);                            // includes fence.mbarrier_init
+        // the packed operand images (hi / lo gate matrix, hi / lo projection: 106 KB) in one TMA bulk copy (constant data)
+        bulk_expect(wbar, 2 * kWBytes + 2 * kPBytes);
+        bulk_copy_g2s(reinterpret_cast<float*>(w_hi), w.tc_w, 2 * kWBytes + 2 * kPBytes, wbar);
+    }
+    pdl_trigger();
+    pdl_wait();                                             // nothing a predecessor wrote is touched before this line
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;    // TMEM address = lane << 16 | column
+
+    if (warp < 4) {
+        // =============================================================================================================
+        // stream group: TMA producer, LayerNorm / operand builder, MMA issuer, output writer
+        // =============================================================================================================
+        auto issue_loads = [&](int step) {                  // one thread
+            const int pos = dir ? S - 1 - step : step;
+            const int slot = step % nslots;
+            unsigned char* dst = slabs + (size_t)slot * nld * kSlabBytes;
+            uint64_t* bar = full + slot;
+            if (!tail_tile) {
+                mbar_expect(bar, (uint32_t)(nld * kSlabBytes));
+                const int c1 = g.mode == 0 ? pos : inner0, c2 = g.mode == 0 ? inner0 : pos;
+                tma_load_4d(dst, &map_x0, bar, 0, c1, c2, outer0);
+                if (nld == 2) tma_load_4d(dst + kSlabBytes, &map_x1, bar, 0, c1, c2, outer0);
+            } else {
+                int nq = g.n_outer - outer0;
+                nq = nq < g.P ? nq : g.P;
+                mbar_expect(bar, (uint32_t)(nld * nq * g.tail * kC * 4));
+                const int c1 = g.mode == 0 ? pos : inner0, c2 = g.mode == 0 ? inner0 : pos;
+                for (int qq = 0; qq < nq; ++qq) {
+                    tma_load_4d(dst + (size_t)qq * g.tail * kC * 4, &map_x0_tail, bar, 0, c1, c2, outer0 + qq);
+                    if (nld == 2) tma_load_4d(dst + kSlabBytes + (size_t)qq * g.tail * kC * 4, &map_x1_tail, bar, 0, c1, c2, outer0 + qq);
+                }
+            }
+        };
+        if (tid == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x0) : "memory");
+            const int n0 = S < nslots ? S : nslots;
+            for (int j = 0; j < n0; ++j) issue_loads(j);
+        }
+
+        const long long film_row = (long long)(grow / a.film_row_div) * S * kC;
+
+        // the row of step `step` out of its stage (128-byte swizzle: 16-byte chunk j of row r sits at chunk j ^ (r & 7)),
+        // second addend and FiLM on the way; LayerNorm; bf16 hi/lo into the x part of A; x' (+ projection bias) kept
+        auto build = [&](int step, float4 (&keep)[8]) {
+            const int pos = dir ? S - 1 - step : step;
+            const int slot = step % nslots;
+            mbar_wait(full + slot, (uint32_t)((step / nslots) & 1));
+            const unsigned char* base = slabs + (size_t)slot * nld * kSlabBytes + (size_t)r * (kC * 4);
+            float4 xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(base + ((i ^ (r & 7)) << 4));
+            if (nld == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 u4 = *reinterpret_cast<const float4*>(base + kSlabBytes + ((i ^ (r & 7)) << 4));
+                    xv[i].x += u4.x; xv[i].y += u4.y; xv[i].z += u4.z; xv[i].w += u4.w;
+                }
+            }
+            if (a.film_scale) {
+                const float4* fs = reinterpret_cast<const float4*>(a.film_scale + film_row + (long long)pos * kC);
+                const float4* fb = reinterpret_cast<const float4*>(a.film_shift + film_row + (long long)pos * kC);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 s4 = __ldg(fs + i), h4 = __ldg(fb + i);
+                    xv[i].x = fmaf(xv[i].x, s4.x, h4.x); xv[i].y = fmaf(xv[i].y, s4.y, h4.y);
+                    xv[i].z = fmaf(xv[i].z, s4.z, h4.z); xv[i].w = fmaf(xv[i].w, s4.w, h4.w);
+                }
+            }
+            float s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s1 += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+            const float mean = s1 * (1.0f / kC);
+            float s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dx = xv[i].x - mean, dy = xv[i].y - mean, dz = xv[i].z - mean, dw = xv[i].w - mean;
+                s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+            const float rstd = rsqrtf(s2 * (1.0f / kC) + kLnEps);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 t = xv[2 * ch + i];
+                    const float4 gg = ld4(ln_s + 4 * (2 * ch + i)), bb = ld4(ln_s + kC + 4 * (2 * ch + i));
+                    v[4 * i + 0] = fmaf((t.x - mean) * rstd, gg.x, bb.x); v[4 * i + 1] = fmaf((t.y - mean) * rstd, gg.y, bb.y);
+                    v[4 * i + 2] = fmaf((t.z - mean) * rstd, gg.z, bb.z); v[4 * i + 3] = fmaf((t.w - mean) * rstd, gg.w, bb.w);
+                }
+                store_split8(a_hi, a_lo, r, ch, v);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) keep[i] = xv[i];
+        };
+
+        // ---- MMA issue (one thread) ---------------------------------------------------------------------------------
+        const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), w_hi_s = smem_u32(w_hi), w_lo_s = smem_u32(w_lo);
+        const uint32_t p_hi_s = smem_u32(p_hi), p_lo_s = smem_u32(p_lo);
+        constexpr uint32_t idesc_g = make_idesc(128, 128), idesc_p = make_idesc(128, 32);
+        auto issue_proj = [&]() {                           // proj[128 x 32] = h (k chunks 4..11 of A) . lin^T
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ab = pass == 2 ? a_lo_s : a_hi_s, pb = pass == 1 ? p_lo_s : p_hi_s;
+#pragma unroll
+                for (int ks = 0; ks < kH / 16; ++ks) {
+                    umma(tmem + 256, make_desc(ab + (4 + 2 * ks) * kAChunkBytes, kAChunkBytes, 128),
+                         make_desc(pb + 2 * ks * kPChunkBytes, kPChunkBytes, 128), idesc_p, acc);
+                    acc = 1;
+                }
+            }
+        };
+        auto issue_gates = [&](int half) {                  // gates[128 x 128] for units 32*half .. : rows n of the image
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ab = pass == 2 ? a_lo_s : a_hi_s, wb = (pass == 1 ? w_lo_s : w_hi_s) + half * 16 * 128;
+#pragma unroll
+                for (int ks = 0; ks < kK / 16; ++ks) {
+                    umma(tmem + 128 * half, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
+                         make_desc(wb + 2 * ks * kWChunkBytes, kWChunkBytes, 128), idesc_g, acc);
+                    acc = 1;
+                }
+            }
+        };
+
+        float* const outp = a.out[dir] + rbase;
+        auto emit = [&](int step, const float4 (&resv)[8]) {                  // y_step = lin h_step [+ b + x'_step]
+            uint32_t pr[32];
+            tmem_ld32_issue(tmem + lane_base + 256, pr);
+            tmem_wait_ld();
+            pin(pr);
+            if (!valid) return;
+            const int pos = dir ? S - 1 - step : step;
+            float* dst = outp + (long long)pos * a.stride_pos;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 o = make_float4(__uint_as_float(pr[4 * i]), __uint_as_float(pr[4 * i + 1]), __uint_as_float(pr[4 * i + 2]),
+                                       __uint_as_float(pr[4 * i + 3]));
+                if (dir == 0) {                             // direction 0 adds bias and residual
+                    const float4 bl = ld4(ln_s + 2 * kC + 4 * i);
+                    o.x += bl.x + resv[i].x; o.y += bl.y + resv[i].y;
+                    o.z += bl.z + resv[i].z; o.w += bl.w + resv[i].w;
+                }
+                st4(dst + 4 * i, o);
+            }
+        };
+
+        float4 res_prev[8], res_cur[8];
+        build(0, res_cur);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res_prev[i] = res_cur[i];
+        fence_async_smem();
+        for (int s = 0; s < S; ++s) {
+            fence_before();
+            bar_sync(1, 128);                               // x part of step s complete, its stage read by all four warps
+            if (tid == 0 && s + nslots < S) issue_loads(s + nslots);
+            if (tid == 32) {
+                if (s == 0) bulk_wait(wbar, 0);             // the operand images have landed
+                mbar_wait(hready, (uint32_t)(s & 1));       // h_{s-1} (or h0) is in A, the gate columns have been read
+                fence_after();
+                issue_gates(0);
+                umma_commit(gates + 0);
+                issue_gates(1);
+                if (s > 0) issue_proj();
+                umma_commit(gates + 1);
+            }
+            __syncwarp();
+            mbar_wait(gates + 1, (uint32_t)(s & 1));        // every MMA of step s is done: A may be rewritten, proj is ready
+            fence_after();
+            if (s > 0) emit(s - 1, res_prev);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res_prev[i] = res_cur[i];
+            if (s + 1 < S) build(s + 1, res_cur);
+            fence_async_smem();
+        }
+        // ---- drain: projection of the last step ------------------------------------------------------------------------
+        fence_before();
+        bar_sync(1, 128);
+        if (tid == 32) {
+            mbar_wait(hready, (uint32_t)(S & 1));
+            fence_after();
+            issue_proj();
+            umma_commit(gates + 1);
+        }
+        __syncwarp();
+        mbar_wait(gates + 1, (uint32_t)(S & 1));
+        fence_after();
+        emit(S - 1, res_prev);
+    } else {
+        // =============================================================================================================
+        // cell-update group: thread (row, half) owns units 32*hf .. 32*hf + 31 of its row
+        // =============================================================================================================
+        const int hf = (warp - 4) >> 2;
+        float c[32];
+        if (a.h0 && valid) {
+            const float* cp = a.c0 + (long long)grow * kH + 32 * hf;
+            const float* hp = a.h0 + (long long)grow * kH + 32 * hf;
+            float4 hv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = ld_plain4(cp + 4 * i);     // plain loads: hN / cN may alias h0 / c0
+                c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+                hv[i] = ld_plain4(hp + 4 * i);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const float4 v0 = hv[2 * ch], v1 = hv[2 * ch + 1];
+                const float h8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c[j] = 0.0f;
+            const float h8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hready);
+
+        float* const hN = (a.hN && valid) ? a.hN + (long long)grow * kH + 32 * hf : nullptr;
+        const uint32_t gcol = tmem + lane_base + 128 * hf;
+        for (int s = 0; s < S; ++s) {
+            mbar_wait(gates + hf, (uint32_t)(s & 1));
+            fence_after();
+            uint32_t ga[32], gb[32];
+            tmem_ld32_issue(gcol, ga);
+            tmem_wait_ld();
+            pin(ga);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {                // 8 units = 32 TMEM columns at a time
+                uint32_t (&cur)[32] = (ch & 1) ? gb : ga;
+                uint32_t (&nxt)[32] = (ch & 1) ? ga : gb;
+                if (ch < 3) tmem_ld32_issue(gcol + 32 * (ch + 1), nxt);
+                float h8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = ld4(bias_s + 4 * (32 * hf + 8 * ch + j));
+                    const float ig = sigmoid_f(__uint_as_float(cur[4 * j + 0]) + bb.x), fg = sigmoid_f(__uint_as_float(cur[4 * j + 1]) + bb.y);
+                    const float gg = tanh_f(__uint_as_float(cur[4 * j + 2]) + bb.z), og = sigmoid_f(__uint_as_float(cur[4 * j + 3]) + bb.w);
+                    c[8 * ch + j] = fmaf(fg, c[8 * ch + j], ig * gg);
+                    h8[j] = og * tanh_f(c[8 * ch + j]);
+                }
+                // The first half's warps get here while the second half's MMAs may still be READING A: nothing may be
+                // written into A before gates[1] has fired.
+                if (hf == 0 && ch == 0) mbar_wait(gates + 1, (uint32_t)(s & 1));
+                store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
+                if (s == S - 1 && hN) {
+                    st4(hN + 8 * ch, make_float4(h8[0], h8[1], h8[2], h8[3]));
+                    st4(hN + 8 * ch + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
+                }
+                if (ch < 3) {
+                    tmem_wait_ld();
+                    pin(nxt);
+                }
+            }
+            fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hready);
+        }
+        if (a.cN && valid) {
+            float* cp = a.cN + (long long)grow * kH + 32 * hf;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st4(cp + 4 * i, make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]));
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+// ---- host: tensor maps ------------------------------------------------------------------------------------------
+namespace tcp {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+// 4-D fp32 map over the activation grid as this call addresses it; the box is [C][1][rows][1] (mode 0) or [C][rows][1][1]
+static int make_map(CUtensorMap* m, const float* base, const SeqArgs& a, const Geom& g, int box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    SB_REQUIRE(enc, SB_E_UNSUPP, "SB_ALGO_TCP: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t outer_stride = g.n_outer > 1 ? (cuuint64_t)a.stride_outer : (cuuint64_t)a.rows_inner * a.stride_inner;
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    dims[0] = kC;
+    if (g.mode == 0) {
+        dims[1] = (cuuint64_t)a.n_steps; dims[2] = (cuuint64_t)a.rows_inner;
+        strides[0] = (cuuint64_t)a.stride_pos * 4; strides[1] = (cuuint64_t)a.stride_inner * 4;
+        box[0] = kC; box[1] = 1; box[2] = (cuuint32_t)box_rows; box[3] = 1;
+    } else {
+        dims[1] = (cuuint64_t)a.rows_inner; dims[2] = (cuuint64_t)a.n_steps;
+        strides[0] = (cuuint64_t)a.stride_inner * 4; strides[1] = (cuuint64_t)a.stride_pos * 4;
+        box[0] = kC; box[1] = (cuuint32_t)box_rows; box[2] = 1; box[3] = 1;
+    }
+    dims[3] = (cuuint64_t)g.n_outer;
+    strides[2] = outer_stride * 4;
+    const CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SB_REQUIRE(rc == CUDA_SUCCESS, SB_E_BADARG, "SB_ALGO_TCP: cuTensorMapEncodeTiled failed (%d): base %p, strides %lld / %lld / %lld",
+               (int)rc, (const void*)base, (long long)strides[0], (long long)strides[1], (long long)strides[2]);
+    return 0;
+}
+
+}  // namespace tcp
+
+bool seq_tcp_supported(const SeqArgs& a) {
+    if (a.n_rows % a.rows_inner != 0) return false;
+    const bool al = ((uintptr_t)a.x0 & 15) == 0 && (!a.x1 || ((uintptr_t)a.x1 & 15) == 0);
+    const bool strides = a.stride_pos % 4 == 0 && a.stride_inner % 4 == 0 && a.stride_outer % 4 == 0;
+    const bool ordered = a.stride_pos < a.stride_inner ? a.stride_pos >= tcp::kC : a.stride_inner >= tcp::kC;
+    return al && strides && ordered && tcp::encode_fn() != nullptr;
+}
+
+int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
+    using namespace tcp;
+    SB_REQUIRE(seq_tcp_supported(a), SB_E_UNSUPP, "SB_ALGO_TCP: activation layout not addressable by a TMA tensor map");
+    Geom g{};
+    g.mode = a.stride_pos < a.stride_inner ? 0 : 1;
+    g.n_outer = a.n_rows / a.rows_inner;
+    g.nfull = a.rows_inner / kRows;
+    g.tail = a.rows_inner % kRows;
+    g.P = g.tail ? kRows / g.tail : 1;
+    g.n_full_tiles = g.n_outer * g.nfull;
+    const int n_tiles = g.n_full_tiles + (g.tail ? ceil_div(g.n_outer, g.P) : 0);
+    CUtensorMap m0, m0t, m1, m1t;
+    SB_CHECK(make_map(&m0, a.x0, a, g, kRows));
+    SB_CHECK(make_map(&m0t, a.x0, a, g, g.tail ? g.tail : kRows));
+    SB_CHECK(make_map(&m1, a.x1 ? a.x1 : a.x0, a, g, kRows));
+    SB_CHECK(make_map(&m1t, a.x1 ? a.x1 : a.x0, a, g, g.tail ? g.tail : kRows));
+    dim3 grid(n_tiles, a.n_dirs);
+    return launch("lstm_tcp", lstm_tcp_kernel, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m0, m0t, m1, m1t);
+}
+
+#else   // SB_EMU: tensor-core / TMA instructions cannot be emulated on the host
+
+bool seq_tcp_supported(const SeqArgs&) { return false; }
+
+int run_seq_tcp(const SeqArgs&, cudaStream_t) {
+    set_error("SB_ALGO_TCP (tcgen05 + TMA) is not available in the host-emulated test build");
+    return SB_E_UNSUPP;
+}
+
+#endif
+
+}  // namespace sb
