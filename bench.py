@@ -27,7 +27,10 @@ import sys
 import tempfile
 import time
 
-import torch
+# 16-32 streams of the pipelined session must not alias onto the default 8 hardware work queues (read at context creation)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -56,6 +59,13 @@ def synthetic_clips(batch, seed):
         d = (3 * m + 1) % 9
         out[:, m] = gains[:, m:m + 1] * src[:, d:d + N_SAMPLES]
     return out + noise
+
+
+def synthetic_target(batch, seed):
+    """The clean source as the reference microphone (mic 0, delay 1) sees it: the synthetic target of the SI-SDR figures."""
+    g = torch.Generator().manual_seed(seed)
+    src = 0.1 * torch.randn(batch, N_SAMPLES + 8, generator=g)
+    return src[:, 1:1 + N_SAMPLES].clone()
 
 
 def radius_one_hot(batch):
@@ -124,14 +134,29 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # the reference arm / CPU baseline: oracle port of the reference on the host cores
 # ---------------------------------------------------------------------------------------------------------------
+def cpu_engine():
+    """("reference", description) when oracle/_ref holds the unmodified reference module (oracle/build_ref.py), else
+    ("port", description): the oracle restatement, which dispatches to the same aten CPU kernels."""
+    from oracle import ref_runner
+    if ref_runner.available():
+        return "reference", ("UNMODIFIED reference module (oracle/_ref copy of src/models/tfgridnet_realtime_clean_dis_embd3, "
+                             "asteroid/espnet stand-ins from oracle/shims) on PyTorch CPU (torch %s)" % torch.__version__)
+    return "port", "oracle port of the reference on PyTorch CPU (torch %s)" % torch.__version__
+
+
 def cpu_streaming_sample(sd, n_chunks, warm=2, seed=1234):
-    """Times `n_chunks` streaming calls at batch 32 through the oracle (PyTorch CPU).  Returns seconds."""
-    from oracle import tfgridnet_oracle as orc
-    ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
+    """Times `n_chunks` streaming calls at batch 32 (edge/causal_infer.py:28-47 protocol) on the host cores through the
+    unmodified reference module when oracle/_ref is present, else through the oracle port.  Returns seconds."""
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(seed)
     x = 0.1 * torch.randn(BATCH, MICS, CHUNK * (n_chunks + warm) + LOOK, generator=g)
     dis = radius_one_hot(BATCH)
+    from oracle import ref_runner
+    if ref_runner.available():
+        net = ref_runner.reference_net(SYN, sd)
+        return ref_runner.streaming_sample(net, x, dis, CHUNK, LOOK, n_chunks, warm)[0]
+    from oracle import tfgridnet_oracle as orc
+    ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
     st = orc.init_state(ocfg, BATCH)
     t0 = None
     with torch.no_grad():
@@ -182,14 +207,15 @@ def run_reference(args, rank):
     total = sum(times)
     value = BATCH * n * len(times) / total
     sample = "first %d of %d chunks of the batch-32 streaming pass per step" % (n, T_FRAMES)
+    kind, engine = cpu_engine()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "rtf": (total / len(times)) / (BATCH * n * CHUNK / 24000.0),
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "clip_seconds": 5.0, "frames_per_step": BATCH * n,
-                   "sample": sample, "engine": "oracle port of the reference on PyTorch CPU (torch %s)" % torch.__version__},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                   "sample": sample, "engine": engine},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -289,6 +315,103 @@ def training_leg(dev, rank, world, batch=8, steps=3):
             "note": "forward + backward through csrc/sb_train.cu, clip after the reduction, Adam; see tools/train_bench.py"}
 
 
+def library_baseline(net, mix, dis, dev, n_chunks=40):
+    """Context, never the product path: the UNMODIFIED reference module (oracle/_ref; else the oracle port) on the SAME
+    B200 through stock PyTorch (cuDNN LSTM, cuBLAS, aten) - the library bar SURVEY.md section 2b names.  Whole-clip call at
+    batch 32 and a sample of the chunk-by-chunk protocol; device-timed."""
+    from oracle import ref_runner
+    out = {"engine": "stock PyTorch %s / cuDNN %s on the same GPU" % (torch.__version__, torch.backends.cudnn.version())}
+    try:
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        if ref_runner.available():
+            ref = ref_runner.reference_net(SYN, sd).to(dev).eval()
+            out["kind"] = "reference"
+            fwd = lambda x, st=None, pad=True: ref({"mixture": x, "dis_embed": dis}, st, pad=pad)       # noqa: E731
+            init = lambda: ref.init_buffers(BATCH, dev)                                                # noqa: E731
+        else:
+            from oracle import tfgridnet_oracle as orc
+            ocfg = orc.OracleConfig.from_kwargs("dis_embed", **SYN)
+            sdd = {k: v.to(dev) for k, v in sd.items()}
+            out["kind"] = "port"
+            fwd = lambda x, st=None, pad=True: orc.net_forward(sdd, ocfg, {"mixture": x, "dis_embed": dis}, st, pad=pad)   # noqa: E731
+
+            def init():
+                st = orc.init_state(ocfg, BATCH)
+                mv = lambda d: {k: (mv(v) if isinstance(v, dict) else v.to(dev)) for k, v in d.items()}  # noqa: E731
+                return mv(st)
+        x = mix.to(dev)
+        ev = lambda: torch.cuda.Event(enable_timing=True)      # noqa: E731
+        with torch.no_grad():
+            y = fwd(x)["output"]
+            torch.cuda.synchronize(dev)
+            t0, t1 = ev(), ev()
+            t0.record()
+            for _ in range(2):
+                y = fwd(x)["output"]
+            t1.record(); t1.synchronize()
+            ms_off = t0.elapsed_time(t1) / 2
+            xp = torch.nn.functional.pad(x, (0, LOOK))
+            st = init()
+            for t in range(3):
+                st = fwd(xp[..., t * CHUNK: t * CHUNK + NFFT], st, pad=False)["next_state"]
+            torch.cuda.synchronize(dev)
+            t0, t1 = ev(), ev()
+            t0.record()
+            for t in range(3, 3 + n_chunks):
+                st = fwd(xp[..., t * CHUNK: t * CHUNK + NFFT], st, pad=False)["next_state"]
+            t1.record(); t1.synchronize()
+            ms_chunk = t0.elapsed_time(t1) / n_chunks
+        out.update({"offline": {"value": BATCH * T_FRAMES / (ms_off * 1e-3), "unit": UNIT, "ms_per_step": ms_off},
+                    "streaming": {"value": BATCH / (ms_chunk * 1e-3), "unit": UNIT, "us_per_chunk": 1e3 * ms_chunk,
+                                  "sample": "%d chunks of the batch-32 streaming pass" % n_chunks},
+                    "output_rms": float(y.float().pow(2).mean().sqrt())})
+        out["_y"] = y
+    except Exception as e:                                         # noqa: BLE001 - context figure, reported not hidden
+        out["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+    return out
+
+
+def strong_leg(net, dev, rank, world, global_batch=256):
+    """BASELINE config 3: a FIXED job of 256 synthetic 6-mic 5 s clips (radii 1 / 1.5 / 2 m), sharded over the ranks
+    (256 / N per GPU, whole-clip calls, no collective).  Device-timed, max over ranks: the driver's per-N lines give the
+    strong-scaling curve."""
+    import torch.distributed as dist
+    nb = global_batch // world
+    try:
+        g = torch.Generator().manual_seed(4321 + rank)
+        x = (0.1 * torch.randn(nb, MICS, N_SAMPLES, generator=g)).to(dev)
+        dis = radius_one_hot(global_batch)[rank * nb:(rank + 1) * nb].to(dev).contiguous()
+        inputs = {"mixture": x, "dis_embed": dis}
+        with torch.no_grad():
+            for _ in range(2):
+                y = net(inputs)["output"]
+        torch.cuda.synchronize(dev)
+        ok = 1
+    except Exception as e:                                         # noqa: BLE001
+        ok, err = 0, "%s: %s" % (type(e).__name__, str(e)[:200])
+    flag = torch.tensor([ok], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return {"error": err if not ok else "a peer rank failed"}
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 3
+    a.record()
+    with torch.no_grad():
+        for _ in range(steps):
+            y = net(inputs)["output"]
+    b.record(); b.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"global_batch": global_batch, "batch_per_gpu": nb, "ms_per_job": ms, "value": global_batch * T_FRAMES / (ms * 1e-3),
+            "unit": UNIT, "scaling": "strong", "finite": bool(torch.isfinite(y).all()),
+            "note": "Net.forward on whole 5 s clips, %d per GPU; speed-up over the N=1 line of the same key = strong scaling" % nb}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from sound_bubble_b200 import Net, _lib
@@ -308,13 +431,16 @@ def run_ours(args, rank, world, local_rank):
     out_host = torch.empty(T_FRAMES, BATCH, 1, CHUNK).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)        # > 126 MB L2
     sess = net.streaming(BATCH, dis, use_graph=not args.no_graph)
-    launches_per_chunk = sess.launches_per_step()
     sess.reset()
     stream = torch.cuda.current_stream(dev)
-    # throughput mode: the same one-call-per-chunk protocol, calls asynchronous, consecutive chunks overlapping on two
-    # streams with per-unit dependencies (sound_bubble_b200/streaming.py::PipelinedSession)
-    pipe = net.streaming(BATCH, dis, pipelined=True, ranges=args.ranges or None, depth=args.depth,
+    # throughput mode: the same one-call-per-8-ms-chunk protocol, calls asynchronous; the native pipe gathers `group`
+    # consecutive chunks per launch and keeps `depth` groups in flight with per-unit dependencies
+    # (sound_bubble_b200/streaming.py::PipelinedSession, csrc/sb_pipe.cu)
+    pipe = net.streaming(BATCH, dis, pipelined=True, ranges=args.ranges or None, depth=args.depth, group=args.group,
                          intra_algo=args.pipe_intra_algo or None, inter_algo=args.pipe_inter_algo or None) if args.pipeline else None
+    G = pipe.group if pipe is not None else 1
+    launches_per_call = pipe.launches_per_step() if pipe is not None else sess.launches_per_step()
+    sess.reset()
 
     def pass_in_order(win, out):
         sess.reset()
@@ -338,12 +464,13 @@ def run_ours(args, rank, world, local_rank):
 
     def pass_device():
         one_pass(win_dev, out_dev)
-        return out_dev.permute(1, 2, 0, 3).reshape(BATCH, 1, N_SAMPLES)
 
     def pass_host():
         one_pass(win_host, out_host)
         stream.synchronize()
-        return out_host
+
+    def as_wave(o):
+        return o.permute(1, 2, 0, 3).reshape(BATCH, 1, N_SAMPLES)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -373,57 +500,113 @@ def run_ours(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clk:
         ms_dev = timed(pass_device, args.steps, args.warmup)
     clocks = clk.summary()
+    y_timed = as_wave(out_dev).clone()                             # the output of the LAST TIMED step (parity below)
     ms_e2e = timed(pass_host, max(2, args.steps // 2), 1)
+    y_e2e = as_wave(out_host.to(dev))
     ms_in_order = timed(lambda: pass_in_order(win_dev, out_dev), 2, 1) if pipe is not None else ms_dev
     frames = BATCH * T_FRAMES * world
     value = frames / (ms_dev * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
 
     train_info = None if args.no_train else training_leg(dev, rank, world)
+    strong_info = None if args.no_strong else strong_leg(net, dev, rank, world)
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel, timed live with CUDA events (eager replay of the same per-chunk sequence) ----
-    n_prof = 100
-    eng = net.engine()
-    saved_algos = (eng.intra_algo, eng.inter_algo)
-    if pipe is not None:                                           # the kernel families the timed region ran
-        eng.intra_algo = pipe.intra_algo if pipe.intra_algo is not None else eng.intra_algo
-        eng.inter_algo = pipe.inter_algo if pipe.inter_algo is not None else eng.inter_algo
-    sess_e = net.streaming(BATCH, dis, use_graph=False)
-
-    def eager_chunks():
-        for t in range(n_prof):
-            sess_e.x.copy_(win_dev[t], non_blocking=True)
-            sess_e.step()
-    eager_chunks()
-    prof = stage_profile(lib, eager_chunks)
-    eng.intra_algo, eng.inter_algo = saved_algos
-    tot = sum(v[0] for v in prof.values())
-    dom = max(prof, key=lambda k: prof[k][0])
-    dom_ms = prof[dom][0] / prof[dom][1]
-    F, C, H = NFFT // 2 + 1, SYN["D"], SYN["H"]
-    act = F * C * 4                                                # one [F][C] fp32 slab = 18 560 B (SURVEY.md §8d)
-    alg_bytes = {"intra": 2 * act, "inter": 2 * act + 2 * 2 * F * H * 4, "stft_features": MICS * CHUNK * 4 + F * 27 * 4,
-                 "conv_in": F * 27 * 4 + act, "backend": act + CHUNK * 4, "film_params": 0}
-    alg_flops = {"intra": 2 * (2 * F * (4 * H * (C + H)) + F * 2 * H * C), "inter": 2 * (F * 4 * H * (C + H) + F * H * C)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_bw = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes.get(dom, 0) * BATCH / (dom_ms * 1e-3) / 1e9
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak_bw, "unit": "GB/s",
-                "frac": achieved / peak_bw,
-                "traffic": ncu_dram_traffic({"intra": "lstm_ws_kernel<32, 0, 2>" if pipe is not None and pipe.intra_algo == 8
-                                             else "lstm_ws_kernel<32, 0, 1>", "inter": "lstm_t"}.get(dom, dom)),
-                "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
-                "avg_launch_us": dom_ms * 1e3, "bytes_per_launch": alg_bytes.get(dom, 0) * BATCH,
-                "share_of_step": prof[dom][0] / tot,
-                "fp32_tflops": alg_flops.get(dom, 0) * BATCH / (dom_ms * 1e-3) / 1e12,
-                "note": "latency-bound: 145 dependent LSTM steps per launch (two sequences per CTA in the pipelined session); see DESIGN.md",
-                "stage_us_per_chunk": {k: 1e3 * v[0] / n_prof for k, v in prof.items()}}
+
+    # ---- parity of the timed run's own output against the CPU oracle (checker only) -------------------------------
+    parity = None
+    if not args.no_parity:
+        from oracle.headline import compare_with_oracle
+        rows = [0, 13, 29]                                         # one utterance per bubble radius
+        sd_cpu = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        parity = compare_with_oracle(sd_cpu, SYN, mix, dis.cpu(), y_timed, rows, target=synthetic_target(BATCH, 1234 + rank))
+        parity["e2e_vs_device_maxabs"] = float((y_e2e - y_timed).abs().max())
+        parity["path"] = "output of the last timed step (pipelined session, group %d, depth %d)" % (G, pipe.depth if pipe else 1)
+        parity["bar"] = "north_star: rms <= 1e-3 and |SI-SDR delta| <= 0.05 dB"
+
+    # ---- roofline: the launch sequence of ONE group exactly as the timed region runs it (same T = G call, same kernel
+    # families), replayed eagerly in order on one stream with CUDA events around every stage (sb_profile_*) ----------
+    n_prof = 12
+    F, C, H, NB = NFFT // 2 + 1, SYN["D"], SYN["H"], SYN["B"]
+    if pipe is not None:
+        call = pipe._call(0, 0)
+        arena_saved = [a.flat.clone() for a in pipe.arenas]
+
+        def replay():
+            for _ in range(n_prof):
+                call.launch()
+    else:
+        arena_saved = None
+
+        def replay():
+            for t in range(n_prof):
+                sess.x.copy_(win_dev[t], non_blocking=True)
+                sess._step_eager(sess.parity)
+    replay()
+    prof = stage_profile(lib, replay)
+    if arena_saved is not None:
+        for a, z in zip(pipe.arenas, arena_saved):
+            a.flat.copy_(z)
+    calls_per_step = T_FRAMES / G                                   # launches of each stage's sequence per step
+    per_call_ms = {k: v[0] / n_prof for k, v in prof.items()}       # one group's stage time (all 6 blocks)
+    tot = sum(per_call_ms.values())
+    dom = max(per_call_ms, key=lambda k: per_call_ms[k])
+    dom_ms = prof[dom][0] / prof[dom][1]                            # average duration of ONE launch of the dominant stage
+    act = F * C * 4                                                # one [F][C] fp32 slab = 18 560 B (SURVEY.md section 8d)
+    alg_bytes = {"intra": 2 * act, "inter": 2 * act + 2 * 2 * F * H * 4 / G, "stft_features": MICS * CHUNK * 4 + F * 27 * 4,
+                 "conv_in": F * 27 * 4 + act, "backend": act + CHUNK * 4, "film_params": 0}       # per (utterance, frame)
+    alg_flops = {"intra": 2 * (2 * F * (4 * H * (C + H)) + F * 2 * H * C), "inter": 2 * (F * 4 * H * (C + H) + F * H * C)}
+    units = BATCH * G                                              # (utterance, frame) pairs one launch processes
+    fl, by = alg_flops.get(dom, 0) * units, alg_bytes.get(dom, 0) * units
+    t_s = dom_ms * 1e-3
+    tc_family = pipe is not None and dom in ("intra", "inter") and \
+        (pipe.intra_algo if dom == "intra" else pipe.inter_algo) in (7, 9)
+    bw_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tensor_peak = float(peaks.get("bf16_tflops", 1684.0))           # burst figure: the kernel is timed alone
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                      # 74.4 TFLOP/s fp32 FMA (tools/ubench: 72.7 measured)
+    fracs = {"hbm": by / t_s / 1e9 / bw_peak, "tensor": (3 * fl / t_s / 1e12 / tensor_peak) if tc_family else 0.0,
+             "fp32_fma": 0.0 if tc_family else fl / t_s / 1e12 / fp32_peak}
+    kernel_name = {"intra": "lstm_tcp_kernel" if tc_family else "lstm_ws_kernel", "inter": "lstm_tcp_kernel" if tc_family else "lstm_tile_kernel"}.get(dom, dom)
+    if tc_family:
+        bound, achieved, peak, unit = "tensor", fl / t_s / 1e12, tensor_peak, "TFLOP/s"
+    elif dom in alg_flops:
+        bound, achieved, peak, unit = "fp32_fma", fl / t_s / 1e12, fp32_peak, "TFLOP/s"
+    else:
+        bound, achieved, peak, unit = "hbm", by / t_s / 1e9, bw_peak, "GB/s"
+    n_tiles = {"intra": 2 * -(-units // 128), "inter": BATCH * (F // 128) + -(-BATCH // (128 // (F % 128)))} if tc_family else {}
+    step_flops = (sum(alg_flops.values())) * NB * BATCH * T_FRAMES
+    step_bytes = (alg_bytes["stft_features"] + alg_bytes["conv_in"] + alg_bytes["backend"] + NB * (alg_bytes["intra"] + alg_bytes["inter"])) * BATCH * T_FRAMES
+    sm_ms = sum(per_call_ms[k] * (min(n_tiles.get(k, 148), 148) / 148.0) for k in per_call_ms) * calls_per_step
+    roofline = {
+        "kernel": "%s (%s stage)" % (kernel_name, dom), "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+        "frac": achieved / peak,
+        "traffic": ncu_dram_traffic("lstm_tcp_kernel" if tc_family else {"intra": "lstm_ws_kernel<32, 0, 2>", "inter": "lstm_t"}.get(dom, dom)),
+        "peak_source": ("MEASURED_PEAKS.json (measured)" if peaks else "fallback of B200_PROFILING.md") + (
+            "; fp32 FMA peak = 148 SMs x 128 FMA/clk x 1.965 GHz (tools/ubench measured 72.7)" if bound == "fp32_fma" else ""),
+        "avg_launch_us": dom_ms * 1e3, "launch_units": "%d utterances x %d frames" % (BATCH, G),
+        "flops_per_launch": fl, "bytes_per_launch": by,
+        "timing": "CUDA events on the launching stream around every stage (sb_profile_*), eager in-order replay of the SAME "
+                  "T = %d launch sequence the timed region runs as graphs; share checked against profiles/r02_launches_bench.txt" % G,
+        "share_of_group": per_call_ms[dom] / tot,
+        "all_roofs": {"hbm_frac": fracs["hbm"], "tensor_frac_executed_3term": fracs["tensor"], "fp32_fma_frac": fracs["fp32_fma"],
+                      "max": max(fracs.values()),
+                      "note": "tcgen05 path: algorithmic 2*MAC FLOPs in `achieved`; the bf16 hi/lo three-term split executes 3x that on "
+                              "the tensor pipe.  ncu (profiles/r02_prof_tcp.txt): XU (MUFU: 10 ex2/rcp per cell) 54 %, tensor pipe 26 %, "
+                              "issue 34 % of active cycles - the serial cell update, not a memory or tensor roof, bounds the kernel"},
+        "stage_us_per_group": {k: 1e3 * v for k, v in per_call_ms.items()},
+        "step": {"alg_tflop": step_flops / 1e12, "alg_gbyte": step_bytes / 1e9, "tflops": step_flops / (ms_dev * 1e-3) / 1e12,
+                 "frac_of_fp32_fma_peak": step_flops / (ms_dev * 1e-3) / 1e12 / fp32_peak,
+                 "gbs": step_bytes / (ms_dev * 1e-3) / 1e9, "frac_of_hbm_peak": step_bytes / (ms_dev * 1e-3) / 1e9 / bw_peak,
+                 "sm_time_ms": sm_ms, "packing": sm_ms / ms_dev,
+                 "note": "sm_time = sum over stages of (serial duration x CTAs / 148) x %.1f groups: the share of ms_per_step "
+                         "the kernels occupy when perfectly packed; packing = sm_time / ms_per_step" % calls_per_step},
+    }
 
     # ---- offline (whole-utterance) pass of the same clips, for context ----
     x_dev = mix.to(dev)
@@ -432,8 +615,7 @@ def run_ours(args, rank, world, local_rank):
     def offline():
         return net(inputs)["output"]
     y_off = offline()
-    y_str = pass_device()
-    stream_vs_offline = float((y_str - y_off).abs().max())
+    stream_vs_offline = float((y_timed - y_off).abs().max())
     ms_off = timed(offline, 3, 1) if world == 1 else None
     offline_info = None
     if ms_off is not None:
@@ -447,12 +629,23 @@ def run_ours(args, rank, world, local_rank):
                         "single_call": {"value": BATCH * T_FRAMES / (ms_single * 1e-3), "ms_per_step": ms_single,
                                         "stage_ms": {k: v[0] for k, v in oprof.items()}}}
 
+    lib_base = None
+    if world == 1 and not args.no_library:
+        lib_base = library_baseline(net, mix, dis, dev)
+        y_lib = lib_base.pop("_y", None)
+        if y_lib is not None:
+            lib_base["ours_vs_library_maxabs"] = float((y_off - y_lib).abs().max())
+            lib_base["speedup_streaming_value"] = value / lib_base["streaming"]["value"]
+            if offline_info is not None:
+                lib_base["speedup_offline"] = offline_info["value"] / lib_base["offline"]["value"]
+
     cpu = None
     if world == 1 and not args.no_cpu:
         sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
         n_cpu = 300
         dt = cpu_streaming_sample(sd, n_cpu, warm=2)
-        cpu = {"value": BATCH * n_cpu / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        kind, engine = cpu_engine()
+        cpu = {"value": BATCH * n_cpu / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "engine": engine,
                "sample": "first %d of %d chunks of the batch-32 streaming pass (%.1f s of CPU work)" % (n_cpu, T_FRAMES, dt)}
         if train_info is not None and "error" not in train_info:
             try:
@@ -462,6 +655,7 @@ def run_ours(args, rank, world, local_rank):
             except Exception as e:                                 # noqa: BLE001 - an extra figure must not cost the headline line
                 cpu["train"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
+    calls = -(-T_FRAMES // G)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -471,19 +665,22 @@ def run_ours(args, rank, world, local_rank):
                    "chunks_per_step": T_FRAMES, "weights": "random init (seed 0) of the TFG_S architecture",
                    "l2": "256 MB buffer written between timed steps", "cuda_graph": not args.no_graph, "pdl": bool(args.pdl),
                    "pipelined": pipe is not None, "unit_ranges": pipe.ranges if pipe is not None else None,
-                   "pipeline_depth": pipe.depth if pipe is not None else 1,
+                   "pipeline_group": G, "pipeline_depth": pipe.depth if pipe is not None else 1,
+                   "protocol": "one feed() per 8 ms chunk with the state carried; the native pipe launches %d consecutive chunks "
+                               "as one call (buffering %d ms) and keeps %d groups in flight" % (G, 8 * G, pipe.depth if pipe else 1),
                    "pipeline_intra_algo": pipe.intra_algo if pipe is not None else None,
                    "pipeline_inter_algo": pipe.inter_algo if pipe is not None else None,
+                   "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                    "host_enqueue_ms_per_step": 1e3 * statistics.median(enqueue_s) if enqueue_s else None,
                    "parallelism": "dp%d (utterances sharded, no collective on the data path)" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(win_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
-        "gpu_launches": int(launches_per_chunk * T_FRAMES * args.steps),
-        "launches_per_chunk": int(launches_per_chunk),
+        "gpu_launches": int(launches_per_call * calls * args.steps),
+        "launches_per_call": int(launches_per_call), "calls_per_step": calls,
         "in_order": {"value": frames / (ms_in_order * 1e-3), "unit": UNIT, "ms_per_step": ms_in_order,
-                     "note": "one stream, chunk t+1 starts when chunk t has finished"},
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "offline": offline_info,
-        "streaming_vs_offline_maxabs": stream_vs_offline, "train": train_info,
+                     "note": "latency mode: one stream, one chunk per launch sequence, chunk t+1 starts when chunk t has finished"},
+        "clocks": clocks, "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "gpu_library_baseline": lib_base,
+        "offline": offline_info, "streaming_vs_offline_maxabs": stream_vs_offline, "strong": strong_info, "train": train_info,
     }), flush=True)
 
 
@@ -499,7 +696,11 @@ def main():
     ap.add_argument("--ranges", type=int, default=0, help="pipelined session: number of unit ranges (0 = default)")
     ap.add_argument("--pipe-intra-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the intra path")
     ap.add_argument("--pipe-inter-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the inter path")
-    ap.add_argument("--depth", type=int, default=8, help="pipelined session: chunks in flight")
+    ap.add_argument("--group", type=int, default=int(os.environ.get("SB_GROUP", "32")), help="pipelined session: chunks per launch")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("SB_DEPTH", "16")), help="pipelined session: groups in flight")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed output")
+    ap.add_argument("--no-library", action="store_true", help="skip the stock-PyTorch-on-GPU context baseline")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 256-clip strong-scaling leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg")
     args = ap.parse_args()

@@ -78,6 +78,8 @@ extern "C" {
 #define SB_OPT_TRAIN_ONE_ROW 3  /* 1 = training LSTM kernels with one gate row (forward) / one W_hh column (BPTT) per thread  */
                                 /* and 256 threads (the first version, kept for comparison; default 0: two per thread, 128) */
 #define SB_OPT_TRAIN_FFMA2 4    /* packed fp32x2 FMAs in the training GEMM kernels (rowgemm / outer); default 1 (measured 2.7 % per step) */
+#define SB_OPT_TC_V1 5          /* 1 = SB_ALGO_TC runs the first tcgen05 kernel (lstm_tc_kernel, LDG operand loads); default 0: the   */
+                                /* warp-specialised TMA pipeline lstm_tcp_kernel whenever a tensor map can address the grid (A/B knob) */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

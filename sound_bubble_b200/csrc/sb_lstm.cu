@@ -17,6 +17,7 @@
 //                      loads / LayerNorm / input gates / stores.
 //   lstm_lane_kernel : the earlier latency path (1/2/4 sequences per CTA, one gate column per thread); selectable.
 //   lstm_tc_kernel   : sb_lstm_tc.cu, tcgen05 gate GEMM for large batches of sequences.
+#include <cmath>
 #include <type_traits>
 
 #include "sb_common.cuh"
@@ -900,7 +901,9 @@ static int pick_algo(int n_rows, int n_dirs, int S, int sms, bool tc_ok) {
     if (ws2 < best_cost) { best = SB_ALGO_WS2; best_cost = ws2; }
     if (tc_ok) {
         const double waves = (double)(ceil_div(n_rows, 128) * n_dirs) / sms;
-        const double tc = S * (waves <= 1.0 ? 15500.0 : waves * 10800.0) + 60000.0;
+        // lstm_tcp_kernel (profiles/r02_tcp_time.txt): 5.25 us = 10.3k cycles per step and round of CTAs, one CTA per SM
+        const double tc = tc_v1_enabled() ? S * (waves <= 1.0 ? 15500.0 : waves * 10800.0) + 60000.0
+                                          : S * ceil(waves) * 10300.0 + 40000.0;
         if (tc < best_cost) return SB_ALGO_TC;
     }
     return best;
@@ -917,7 +920,8 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
     if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sms, tc_ok);
     switch (algo) {
         case SB_ALGO_TC:
-            if constexpr (C == 32 && !RAW_H) return run_seq_tc(a, st);
+            if constexpr (C == 32 && !RAW_H)
+                return (!tc_v1_enabled() && seq_tcp_supported(a)) ? run_seq_tcp(a, st) : run_seq_tc(a, st);
             break;
         case SB_ALGO_TILE4:
         case SB_ALGO_TILE: {
@@ -962,7 +966,8 @@ int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t s
     SB_REQUIRE(a.n_rows > 0 && a.n_steps > 0, SB_E_BADARG, "empty LSTM problem (%d rows, %d steps)", a.n_rows, a.n_steps);
     if (algo == SB_ALGO_TC || algo == SB_ALGO_TCP) {
         SB_REQUIRE(C == 32 && !raw_h, SB_E_UNSUPP, "SB_ALGO_TC / SB_ALGO_TCP support C=32 in projected mode only");
-        return algo == SB_ALGO_TCP ? run_seq_tcp(a, st) : run_seq_tc(a, st);
+        if (algo == SB_ALGO_TCP) return run_seq_tcp(a, st);
+        return (!tc_v1_enabled() && seq_tcp_supported(a)) ? run_seq_tcp(a, st) : run_seq_tc(a, st);
     }
     if (C == 32) return raw_h ? run_seq_c<32, true>(a, algo, st) : run_seq_c<32, false>(a, algo, st);
     return raw_h ? run_seq_c<16, true>(a, algo, st) : run_seq_c<16, false>(a, algo, st);

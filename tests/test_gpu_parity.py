@@ -299,3 +299,49 @@ def test_launches_are_counted():
     m(g.inputs(DEV), pad=g.pad)
     torch.cuda.synchronize()
     assert _lib.launch_count() - before == 2 + 1 + 2 * 2 + 1      # stft, conv_in, film, 2 x (intra, inter), fused backend
+
+
+@pytest.mark.parametrize("mode", ["grouped", "per_chunk", "offline_sliced"])
+def test_headline_configuration_against_oracle(mode):
+    """BASELINE config 2 at FULL size - batch 32 x 5 s = 625 recurrent steps per inter-frame LSTM - through the very
+    sessions bench.py times (grouped throughput mode: 32 chunks per launch, 16 groups in flight, tcgen05 + TMA LSTM
+    kernels on both paths; per-chunk pipelined mode: WS2 intra, tcgen05 inter, 14 unit ranges, depth 8; whole-clip call
+    as 125-frame slices), compared with the CPU oracle on three utterances (one per bubble radius) over all 625 frames.
+    Bars (north_star): waveform RMS error <= 1e-3, |SI-SDR(ours, target) - SI-SDR(oracle, target)| <= 0.05 dB; the
+    engineering bound asserted here is 20x tighter and the error must not grow along the clip."""
+    import bench
+    from oracle.headline import compare_with_oracle
+    from sound_bubble_b200 import Net
+    torch.manual_seed(0)
+    m = Net(**bench.SYN).to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    mix = bench.synthetic_clips(bench.BATCH, 1234)
+    dis = bench.radius_one_hot(bench.BATCH)
+    tgt = bench.synthetic_target(bench.BATCH, 1234)
+    if mode == "offline_sliced":
+        y = m({"mixture": mix.to(DEV), "dis_embed": dis.to(DEV)})["output"]
+        assert len(m._offline_pipes) == 1, "the sliced path was not taken"
+    else:
+        win = bench.windows_of(mix).to(DEV)
+        out = torch.empty(bench.T_FRAMES, bench.BATCH, 1, bench.CHUNK, device=DEV)
+        kw = dict(group=32, depth=16) if mode == "grouped" else dict(depth=8)
+        pipe = m.streaming(bench.BATCH, dis.to(DEV), pipelined=True, **kw)
+        if mode == "grouped":
+            assert pipe.intra_algo == 7 and pipe.inter_algo == 7
+        else:
+            assert pipe.intra_algo == 8 and pipe.inter_algo == 7 and len(pipe.ranges) == 14
+        for rep in range(2):                                  # the second pass reuses the captured graphs after a reset
+            pipe.reset()
+            pipe.begin()
+            for t in range(bench.T_FRAMES):
+                pipe.feed(win[t], out=out[t])
+            pipe.end()
+            torch.cuda.synchronize()
+        y = out.permute(1, 2, 0, 3).reshape(bench.BATCH, 1, bench.N_SAMPLES)
+        pipe.close()
+    r = compare_with_oracle(sd, bench.SYN, mix, dis, y, [0, 13, 29], target=tgt)
+    print(mode, r)
+    assert r["frames_per_row"] == 625
+    assert r["rms"] <= 5e-5 and r["rel_rms"] <= 1e-4 and r["rms"] <= pc.RMS_BAR, r
+    assert r["worst_second_rms"] <= 1e-4, r
+    assert r["si_sdr_vs_oracle_db"] >= 60.0 and r["si_sdr_delta_db"] <= 0.05, r

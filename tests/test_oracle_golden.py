@@ -81,3 +81,25 @@ def test_si_sdr_definition():
     noisy = t + 0.1 * torch.randn(2, 1000)
     assert torch.all((si_sdr(noisy, t) - 20).abs() < 1.5)
     assert rms(torch.ones(4)) == 1.0
+
+
+def test_reference_copy_in_oracle_ref_equals_the_port():
+    """oracle/_ref (oracle/build_ref.py: byte-for-byte copy of the reference's model files, present where the recipe has
+    run) through the reference's own streaming protocol == the oracle port's whole-clip call; and the headline checker
+    reports a perfect score for the reference's own output."""
+    from oracle import ref_runner
+    from oracle.headline import compare_with_oracle
+    from oracle.cases import SYN
+    from oracle.weights import radius_one_hot, synthetic_mixture
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref has not been built (python oracle/build_ref.py in the build container)")
+    cfg = OracleConfig.from_kwargs("dis_embed", **SYN)
+    sd = make_state_dict(cfg, 0)
+    net = ref_runner.reference_net(SYN, sd)
+    mix = synthetic_mixture(3, 6, 192 * 12 + 96)
+    mix[..., 192 * 12:] = 0.0                                 # the look-ahead of the last chunk = the offline call's zero pad
+    dis = radius_one_hot(3)
+    _, y = ref_runner.streaming_sample(net, mix, dis, 192, 96, 11, warm=1)
+    r = compare_with_oracle(sd, SYN, mix[..., : 192 * 12], dis, y, [0, 2], target=mix[:, 0, : 192 * 12])
+    assert y.shape == (3, 1, 192 * 12)
+    assert r["rms"] <= 1e-6 and r["si_sdr_delta_db"] <= 1e-3 and r["ok"], r

@@ -19,6 +19,7 @@ from sound_bubble_b200 import Net, _lib  # noqa: E402
 def main():
     combos = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(1, 8), (2, 8), (4, 8), (8, 8), (4, 16), (8, 16), (16, 8)]
     dev = torch.device("cuda", 0)
+    print("CUDA_DEVICE_MAX_CONNECTIONS=%s" % os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "(default 8)"), flush=True)
     _lib.load()
     _lib.set_pdl(True)
     torch.manual_seed(0)
@@ -31,7 +32,7 @@ def main():
     outs = torch.empty(T_FRAMES, BATCH, 1, CHUNK, device=dev)
     ref = None
     for G, depth in combos:
-        for ia, ea in ([(None, None)] if G == 1 else [(None, None), (8, 7)]):
+        for ia, ea in ([(None, None)] if G == 1 or not os.environ.get("SWEEP_WS2") else [(None, None), (8, 7)]):
             pipe = net.streaming(BATCH, dis, pipelined=True, depth=depth, group=G, intra_algo=ia, inter_algo=ea)
 
             def one_pass():

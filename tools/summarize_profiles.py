@@ -40,7 +40,9 @@ def launches(name, tag):
         agg[k].append(v)
         order.append((k, v))
     tot = sum(sum(v) for v in agg.values())
-    with open(os.path.join(PROF, "%s_%s.txt" % (tag, name.replace(".csv", ""))), "w") as f:
+    base = name.replace(".csv", "")
+    base = base[len(tag) + 1:] if base.startswith(tag + "_") else base
+    with open(os.path.join(PROF, "%s_%s.txt" % (tag, base)), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (serialised, cold-cache: compare SHARES)\n")
         f.write("# %d launches, %.1f us total\n" % (len(order), tot))
         f.write("%-110s %6s %10s %8s\n" % ("kernel", "n", "avg_us", "share"))
@@ -58,7 +60,9 @@ def report(rep, tag):
         return
     hdr, units = rows[0], rows[1]
     src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    with open(os.path.join(PROF, "%s_%s.txt" % (tag, rep.replace(".ncu-rep", ""))), "w") as f:
+    base = rep.replace(".ncu-rep", "")
+    base = base[len(tag) + 1:] if base.startswith(tag + "_") else base
+    with open(os.path.join(PROF, "%s_%s.txt" % (tag, base)), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on ; %s\n" % rep)
         for r in rows[2:]:
             d = dict(zip(hdr, r))
@@ -91,10 +95,11 @@ def report(rep, tag):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
-    for n in ("launches_streaming.csv", "launches_offline.csv", "launches_train.csv"):
-        launches(n, tag)
+    for n in sorted(os.listdir(OUT)):
+        if "launches" in n and n.endswith(".csv"):
+            launches(n, tag)
     for r in sorted(os.listdir(OUT)):
-        if r.endswith(".ncu-rep"):
+        if r.endswith(".ncu-rep") and (r.startswith(tag + "_") or tag == "r01"):
             report(r, tag)
     for n in ("ubench.txt", "lstm_bench.txt", "bench.json", "bench_pdl.json", "gpu.txt", "host.txt", "prepare_bench.txt", "variants_bench.txt",
               "train_bench.json", "train_bench_one_row.json", "train_bench_ffma2_0.json", "train_bench_rpi.json", "train_ddp_n2.json",
