@@ -80,6 +80,8 @@ extern "C" {
 #define SB_OPT_TRAIN_FFMA2 4    /* packed fp32x2 FMAs in the training GEMM kernels (rowgemm / outer); default 1 (measured 2.7 % per step) */
 #define SB_OPT_TC_V1 5          /* 1 = SB_ALGO_TC runs the first tcgen05 kernel (lstm_tc_kernel, LDG operand loads); default 0: the   */
                                 /* warp-specialised TMA pipeline lstm_tcp_kernel whenever a tensor map can address the grid (A/B knob) */
+#define SB_OPT_TC_CELL7 6       /* lstm_tcp_kernel's cell update with shared reciprocals (5 ex2 + 2 rcp per cell instead of 5 + 5;  */
+                                /* the kernel is bound by the XU pipe).  Default set from the measured A/B, see DESIGN.md section 4.  */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

@@ -187,11 +187,16 @@ static int launch_stft(const sb_stft_args& a, cudaStream_t st) {
 // shared memory as [frame][c][F+2] with zero columns for the frequency padding; the packed weights [kt][c][kf][C]
 // follow.  One thread computes 8 output channels of one (t, f): per input value 1 LDS + 2 broadcast LDS.128 + 8 FMA.
 // The C/8 threads of a (t, f) are adjacent lanes, so LayerNorm(C) is two quad shuffles and the store is coalesced.
-template <int C>
-__global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a, const int TT, const int FC) {
+//
+// PP = 4 (whole-utterance and grouped calls): a thread owns 8 output channels of FOUR adjacent bins, so the two weight
+// LDS.128 of a tap feed 4 x 8 FMAs and the six input values of a (frame, channel) row arrive as two LDS.128: 8 shared-memory
+// loads per 96 FMAs instead of 9 per 24 (the PP = 1 form was bound by the shared-memory pipe at 18 % of the FMA rate and had
+// grown to 18 % of the grouped step's SM-time, profiles/r02_launches_bench.txt).  Same summation order: bit-identical.
+template <int C, int PP>
+__global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a, const int TT, const int FC, const int FP) {
     constexpr int NOG = C / 8;
     SB_DYN_SMEM(float, smem);
-    const int F = a.F, Cin = a.Cin, FP = FC + 2;
+    const int F = a.F, Cin = a.Cin;
     float* w_s = smem;                                          // [3][Cin][3][C]
     float* in_s = w_s + 9 * Cin * C;                            // [TT+2][Cin][FP]; column j <-> bin f0 - 1 + j
     const int tid = threadIdx.x;
@@ -230,9 +235,79 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
             }
         }
     }
+    if (PP > 1) {                                               // columns past the tile: read by the last bin group, never stored
+        const int npad = FP - ncol;
+        for (int i = tid; i < nfr * Cin * npad; i += blockDim.x) {
+            const int row = i / npad;
+            in_s[row * FP + ncol + (i - row * npad)] = 0.0f;
+        }
+    }
     cp_async_wait_all();
     __syncthreads();
 
+    if constexpr (PP == 4) {
+        const int NFG = (nf + 3) >> 2;
+        const int n_items4 = nvalid * NFG * NOG;
+        for (int base = 0; base < n_items4; base += blockDim.x) {
+            const int item = base + tid;
+            const bool valid = item < n_items4;
+            const int it = valid ? item : 0;
+            const int og = it % NOG, pf = it / NOG;
+            const int tt = pf / NFG, fl0 = (pf - tt * NFG) << 2;
+            float2 acc[4][4];
+            {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias) + 2 * og);
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias) + 2 * og + 1);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    acc[p][0] = make_float2(b0.x, b0.y); acc[p][1] = make_float2(b0.z, b0.w);
+                    acc[p][2] = make_float2(b1.x, b1.y); acc[p][3] = make_float2(b1.z, b1.w);
+                }
+            }
+            for (int kt = 0; kt < 3; ++kt) {
+                const float* ip = in_s + (tt + kt) * Cin * FP + fl0;
+                const float* wp = w_s + (kt * Cin * 3) * C + og * 8;
+#pragma unroll 3
+                for (int c = 0; c < Cin; ++c) {
+                    const float4 a0 = ld4(ip + c * FP), a1 = ld4(ip + c * FP + 4);
+                    const float v[6] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
+#pragma unroll
+                    for (int kf = 0; kf < 3; ++kf) {
+                        const float4 w0 = ld4(wp + (c * 3 + kf) * C);
+                        const float4 w1 = ld4(wp + (c * 3 + kf) * C + 4);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            ffma2(acc[p][0], make_float2(w0.x, w0.y), v[p + kf]);
+                            ffma2(acc[p][1], make_float2(w0.z, w0.w), v[p + kf]);
+                            ffma2(acc[p][2], make_float2(w1.x, w1.y), v[p + kf]);
+                            ffma2(acc[p][3], make_float2(w1.z, w1.w), v[p + kf]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float o[8] = {acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y, acc[p][2].x, acc[p][2].y, acc[p][3].x, acc[p][3].y};
+                if (a.ln_g) {
+                    float s1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s1 += o[j];
+                    const float mean = group_sum<NOG>(s1) * (1.0f / C);
+                    float s2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { o[j] -= mean; s2 = fmaf(o[j], o[j], s2); }
+                    const float rstd = rsqrtf(group_sum<NOG>(s2) * (1.0f / C) + kLnEps);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j] * rstd, __ldg(a.ln_g + og * 8 + j), __ldg(a.ln_b + og * 8 + j));
+                }
+                if (valid && fl0 + p < nf) {
+                    float* dst = a.x + ((size_t)(b * a.T + t0 + tt) * F + f0 + fl0 + p) * C + og * 8;
+                    st4(dst, make_float4(o[0], o[1], o[2], o[3]));
+                    st4(dst + 4, make_float4(o[4], o[5], o[6], o[7]));
+                }
+            }
+        }
+    } else {
     const int n_items = nvalid * nf * NOG;
     for (int base = 0; base < n_items; base += blockDim.x) {
         const int item = base + tid;
@@ -283,6 +358,8 @@ __global__ void __launch_bounds__(640, 1) conv_in_kernel(const sb_conv_in_args a
             st4(dst + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
         }
     }
+
+    }   // PP == 1
 
     if (t0 + nvalid == a.T) {           // this CTA holds the last two frames of [history ; feats]: new conv_buf
         float* dst = a.conv_buf_out + (size_t)b * Cin * 2 * F;
@@ -402,15 +479,21 @@ extern "C" int sb_conv_in_fwd(const sb_conv_in_args* p, void* stream) {
     SB_REQUIRE(p->conv_buf_in != p->conv_buf_out, SB_E_BADARG, "sb_conv_in_fwd: conv_buf_in and conv_buf_out must not alias");
     // offline: 4 frames x all bins per CTA; streaming-sized calls: 1 frame x 16 bins per CTA so the few frames still
     // spread over the whole chip (B * T * ceil(F/16) CTAs)
-    const int TT = p->T >= 4 ? 4 : 1;
-    const int FC = p->T >= 4 ? p->F : 16;
-    const int threads = p->T >= 4 ? 640 : 128;
-    const size_t smem = ((size_t)9 * p->Cin * p->C + (size_t)(TT + 2) * p->Cin * (FC + 2)) * sizeof(float);
+    const bool big = p->T >= 4;
+    const int TT = big ? 4 : 1;
+    const int FC = big ? p->F : 16;
+    const int FP = big ? (FC + 3) / 4 * 4 + 8 : FC + 2;        // PP = 4 reads columns fl0 .. fl0 + 7 of a 16-byte aligned row
+    const int threads = big ? 640 : 128;
+    const size_t smem = ((size_t)9 * p->Cin * p->C + (size_t)(TT + 2) * p->Cin * FP) * sizeof(float);
     SB_REQUIRE(smem <= 227 * 1024, SB_E_SMEM, "sb_conv_in_fwd: Cin=%d F=%d needs %zu bytes of shared memory", p->Cin, p->F, smem);
     dim3 grid(ceil_div(p->T, TT), p->B, ceil_div(p->F, FC));
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->C == 32) return launch("conv_in", conv_in_kernel<32>, grid, dim3(threads), smem, st, *p, TT, FC);
-    return launch("conv_in", conv_in_kernel<16>, grid, dim3(threads), smem, st, *p, TT, FC);
+    if (big) {
+        if (p->C == 32) return launch("conv_in", conv_in_kernel<32, 4>, grid, dim3(threads), smem, st, *p, TT, FC, FP);
+        return launch("conv_in", conv_in_kernel<16, 4>, grid, dim3(threads), smem, st, *p, TT, FC, FP);
+    }
+    if (p->C == 32) return launch("conv_in", conv_in_kernel<32, 1>, grid, dim3(threads), smem, st, *p, TT, FC, FP);
+    return launch("conv_in", conv_in_kernel<16, 1>, grid, dim3(threads), smem, st, *p, TT, FC, FP);
 }
 
 extern "C" int sb_film_params_fwd(const sb_film_args* p, void* stream) {

@@ -153,8 +153,32 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
+// LSTM cell with shared reciprocals.  With e_x = 2^(-x log2 e):  sigmoid(x) = 1 / (1 + e_x),  tanh(x) = (1 - e_2x) / (1 + e_2x), so
+//   f     = (1 + e_i)(1 + e_2g) / D,   i * tanh(g) = (1 + e_f)(1 - e_2g) / D,   D = (1 + e_i)(1 + e_f)(1 + e_2g)
+//   h     = o * tanh(c) = (1 - e_2c) / ((1 + e_o)(1 + e_2c))
+// i.e. 5 ex2 + 2 rcp on the XU pipe instead of 5 ex2 + 5 rcp: the cell update is bound by that pipe (profiles/r02_prof_tcp.txt:
+// XU 54 % of active cycles at 10 MUFU per cell).  Exponent arguments are clamped (40 / 60) so that the products stay finite: the
+// clamped gates differ from the exact ones by < 1e-12.  zs = the gate pre-activations WITHOUT bias, nb = the biases pre-multiplied
+// by -log2 e (-2 log2 e for g).  Relative error ~4 ulp, the same order as the one-reciprocal-per-gate form.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float cell7(float zi, float zf, float zg, float zo, const float4 nb, float& c) {
+    const float ei = fast_ex2(fminf(fmaf(zi, -kLog2e, nb.x), 40.0f));
+    const float ef = fast_ex2(fminf(fmaf(zf, -kLog2e, nb.y), 40.0f));
+    const float eg = fast_ex2(fminf(fmaf(zg, -2.0f * kLog2e, nb.z), 40.0f));
+    const float eo = fast_ex2(fminf(fmaf(zo, -kLog2e, nb.w), 60.0f));
+    const float pi = 1.0f + ei, pf = 1.0f + ef, pg = 1.0f + eg;
+    const float r = fast_rcp(pi * pf * pg);
+    const float f = r * (pi * pg);
+    const float ig = r * (pf * (1.0f - eg));
+    c = fmaf(f, c, ig);
+    const float ec = fast_ex2(fminf(c * (-2.0f * kLog2e), 60.0f));
+    return (1.0f - ec) * fast_rcp((1.0f + eo) * (1.0f + ec));
+}
+
 }  // namespace tcp
 
+// CELL7: the cell update with shared reciprocals (7 MUFU operations per cell instead of 10, see cell7 below)
+template <bool CELL7>
 __global__ void __launch_bounds__(tcp::kThreads, 1)
 lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUtensorMap map_x0,
                 const __grid_constant__ CUtensorMap map_x0_tail, const __grid_constant__ CUtensorMap map_x1,
@@ -208,7 +232,9 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
     const long long rbase = valid ? (long long)o_row * a.stride_outer + (long long)i_row * a.stride_inner : 0;
 
     // ---- one-time setup ---------------------------------------------------------------------------------------------
-    for (int i = tid; i < kN; i += kThreads) bias_s[i] = __ldg(w.tc_b + i);
+    // CELL7 folds the bias into the exponent argument: columns are (i, f, g, o) per unit, the g column feeds tanh
+    for (int i = tid; i < kN; i += kThreads)
+        bias_s[i] = CELL7 ? __ldg(w.tc_b + i) * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e) : __ldg(w.tc_b + i);
     if (tid < kC) {
         ln_s[tid] = __ldg(w.ln_g + tid);
         ln_s[kC + tid] = __ldg(w.ln_b + tid);
@@ -468,10 +494,15 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 bb = ld4(bias_s + 4 * (32 * hf + 8 * ch + j));
-                    const float ig = sigmoid_f(__uint_as_float(cur[4 * j + 0]) + bb.x), fg = sigmoid_f(__uint_as_float(cur[4 * j + 1]) + bb.y);
-                    const float gg = tanh_f(__uint_as_float(cur[4 * j + 2]) + bb.z), og = sigmoid_f(__uint_as_float(cur[4 * j + 3]) + bb.w);
-                    c[8 * ch + j] = fmaf(fg, c[8 * ch + j], ig * gg);
-                    h8[j] = og * tanh_f(c[8 * ch + j]);
+                    if (CELL7) {
+                        h8[j] = cell7(__uint_as_float(cur[4 * j + 0]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
+                                      __uint_as_float(cur[4 * j + 3]), bb, c[8 * ch + j]);
+                    } else {
+                        const float ig = sigmoid_f(__uint_as_float(cur[4 * j + 0]) + bb.x), fg = sigmoid_f(__uint_as_float(cur[4 * j + 1]) + bb.y);
+                        const float gg = tanh_f(__uint_as_float(cur[4 * j + 2]) + bb.z), og = sigmoid_f(__uint_as_float(cur[4 * j + 3]) + bb.w);
+                        c[8 * ch + j] = fmaf(fg, c[8 * ch + j], ig * gg);
+                        h8[j] = og * tanh_f(c[8 * ch + j]);
+                    }
                 }
                 // The first half's warps get here while the second half's MMAs may still be READING A: nothing may be
                 // written into A before gates[1] has fired.
@@ -577,7 +608,9 @@ int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
     SB_CHECK(make_map(&m1, a.x1 ? a.x1 : a.x0, a, g, kRows));
     SB_CHECK(make_map(&m1t, a.x1 ? a.x1 : a.x0, a, g, g.tail ? g.tail : kRows));
     dim3 grid(n_tiles, a.n_dirs);
-    return launch("lstm_tcp", lstm_tcp_kernel, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m0, m0t, m1, m1t);
+    if (tc_cell7_enabled())
+        return launch("lstm_tcp", lstm_tcp_kernel<true>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m0, m0t, m1, m1t);
+    return launch("lstm_tcp", lstm_tcp_kernel<false>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m0, m0t, m1, m1t);
 }
 
 #else   // SB_EMU: tensor-core / TMA instructions cannot be emulated on the host

@@ -7,8 +7,9 @@ through the training entry points of include/soundbubble.h (``*_train_fwd`` keep
 the twins); ``SeparatorFunction`` is the ``torch.autograd.Function`` that puts it behind ``Net.forward`` when the module is
 in training mode with gradients enabled.  Parameters are read in their checkpoint layouts - nothing is re-packed per step.
 
-Supported: plain BiLSTM and conv-LSTM intra-frame paths, the inter-frame LSTM (use_attn=False), FiLM with either distance
-embedding (dis_type conv* / linear*), 1-2 sources, optional spectral masking and first LayerNorm - i.e. every shipped training config.
+Supported: plain BiLSTM and conv-LSTM intra-frame paths, the inter-frame LSTM, the windowed self-attention unit
+(use_attn=True, DE3:856-898; L*E in {8, 16}), FiLM with either distance embedding (dis_type conv* / linear*), 1-2 sources,
+optional spectral masking and first LayerNorm - i.e. every shipped training config and the attention the constructor offers.
 Anything else raises ``NotImplementedError`` rather than training a different model.  No CPU path: the library handed in
 is the sm_100a build (the tests' host-emulated build goes through the same code on tiny shapes).
 """
@@ -33,16 +34,11 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-# The attention backward kernels are a first version that has been checked on the host-emulated test build only (no B200
-# run yet): they stay behind this switch, so that ``Net`` in train() mode keeps treating use_attn models as forward-only.
-EXPERIMENTAL_ATTENTION = False
 
 
 def check_trainable(cfg: ModelConfig):
     if cfg.conv_lstm and cfg.lstm_down * cfg.D > 256:
         raise NotImplementedError("training: conv-LSTM backward kernels need lstm_down * D <= 256")
-    if cfg.use_attn and not EXPERIMENTAL_ATTENTION:
-        raise NotImplementedError("training: the attention backward kernels are experimental (training.EXPERIMENTAL_ATTENTION)")
     if cfg.use_attn and cfg.L * cfg.attn_E not in (8, 16):
         raise NotImplementedError("training: attention backward kernels need L * E in {8, 16}")
     if cfg.H != 64 or cfg.D not in (16, 32):

@@ -37,6 +37,16 @@ def test_module_gradients_match_the_reference(lib, name):
     _ok(tc.check_golden_grads(lib, DEV, name))
 
 
+def test_attention_gradients(lib):
+    """a11 under autograd on the B200 (DE3:856-898): the reference's own gradients for a windowed-attention model through
+    ``Net`` in train() mode, the attention unit alone at 7 250 positions with five windows' worth of frames, and a small
+    whole network with more frames than the window."""
+    _ok(tc.check_golden_grads(lib, DEV, "grad_syn_attn"))
+    _ok(tc.check_attn_stage(lib, DEV, "dis_embed", dict(SYN, B=1, use_attn=True, local_atten_len=10), B=2, T=25))
+    _ok(tc.check_attn_stage(lib, DEV, "optim", dict(C16, B=1, use_attn=True, local_atten_len=100), B=1, T=40))
+    _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=1, use_attn=True, local_atten_len=5), B=2, T=12))
+
+
 def test_tfg_s_gradients_against_oracle_autograd(lib):
     """the benchmark architecture (6 blocks, FiLM on 5 of them), every parameter"""
     _ok(tc.check_net(lib, DEV, "dis_embed", SYN, B=3, T=6))
@@ -94,7 +104,7 @@ def test_mode_switches():
     st = net.init_buffers(1, DEV)                      # carried state: the inference kernels, no autograd graph
     assert not net.train()({"mixture": mix, "dis_embed": dis}, st)["output"].requires_grad
     from sound_bubble_b200 import Net
-    rpi = Net(**dict(SYN, B=1, use_attn=True)).to(DEV).train()       # no backward kernels: forward-only, backward fails loudly
+    rpi = Net(**dict(SYN, B=1, use_attn=True, E=3)).to(DEV).train()  # L*E = 12: no backward kernels, forward-only, backward fails loudly
     y = rpi({"mixture": mix, "dis_embed": dis})["output"]
     with pytest.raises(RuntimeError):
         y.sum().backward()

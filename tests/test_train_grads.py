@@ -117,15 +117,11 @@ def test_training_call_returns_the_next_state(lib):
     _ok(tc.check_next_state(lib, "cpu", "optim", dict(RPI, B=1), B=1, T=1))          # single frame: conv_buf keeps a zero frame
 
 
-def test_experimental_attention_backward(lib, monkeypatch):
-    """a11 under autograd (training.EXPERIMENTAL_ATTENTION): the reference's gradients for a windowed-attention model, the
-    K / V history a training call hands back, and the D = 16 / E = 4 instantiations against oracle autograd"""
-    from sound_bubble_b200 import training
-    from sound_bubble_b200.packing import ModelConfig
-    with pytest.raises(NotImplementedError):
-        training.check_trainable(ModelConfig(variant="dis_embed", **dict(SYN, use_attn=True)))
-    monkeypatch.setattr(training, "EXPERIMENTAL_ATTENTION", True)
+def test_attention_backward(lib):
+    """a11 under autograd: the reference's gradients for a windowed-attention model, the K / V history a training call hands
+    back, the D = 16 / E = 4 instantiations against oracle autograd, and the unit alone with more frames than the window"""
     _ok(tc.check_golden_grads(lib, "cpu", "grad_syn_attn"))
     _ok(tc.check_next_state(lib, "cpu", "dis_embed", dict(SYN, B=1, use_attn=True, local_atten_len=3), B=1, T=5))
     _ok(tc.check_net(lib, "cpu", "optim", dict(RPI, B=1, conv_lstm=False, use_attn=True, local_atten_len=3), B=1, T=4))
     _ok(tc.check_net(lib, "cpu", "dis_embed", dict(SYN, B=1, E=4, use_attn=True, local_atten_len=9), B=1, T=3))
+    _ok(tc.check_attn_stage(lib, "cpu", "dis_embed", dict(SYN, B=1, use_attn=True, local_atten_len=4), B=2, T=9))

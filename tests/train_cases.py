@@ -130,6 +130,54 @@ def check_net(lib, device, variant, kwargs, B=1, T=3, seed=11, golden=None):
     return errs
 
 
+def check_attn_stage(lib, device, variant, kwargs, B=1, T=12, block=0, seed=5):
+    """a11 under autograd at stage level (sb_attn_train_fwd / sb_attn_bwd through the C ABI) on the SAME input and output
+    gradient as autograd through the oracle's attention_path (zero K / V history, as every training call has).  A stage
+    check is robust where a whole-network one is not: four PReLUs sit in the attention unit, and with ~10^5 pre-activations
+    one of them can land within rounding distance of the kink, where the two sides' 1e-6 different inputs pick different
+    slopes and a whole weight gradient moves by ~1/sqrt(N) (observed: 3e-3 at 7 250 positions, kernels correct)."""
+    ocfg, sd, cfg = _model(variant, kwargs)
+    Fq, C, W = cfg.n_freqs, cfg.D, cfg.local_atten_len
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, Fq, C, generator=g)
+    gy = torch.randn(B, T, Fq, C, generator=g)
+    pre = "tfgridnet.blocks.%d." % block
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(pre + "attn")}
+    xs = x.clone().requires_grad_(True)
+    full = dict(sd)
+    full.update(leaf)
+    Kb = torch.zeros(B * cfg.L, W - 1, cfg.attn_E * Fq)
+    Vb = torch.zeros(B * cfg.L, W - 1, (C // cfg.L) * Fq)
+    y, newK, newV = orc.attention_path(full, ocfg, block, xs, Kb, Vb)
+    (y * gy).sum().backward()
+
+    tg = TrainGraph(lib, cfg)
+    P = {k: v.clone().float().to(device) for k, v in sd.items()}
+    xd, gx = x.to(device), gy.clone().to(device)
+    nan = lambda n: torch.full((int(n),), float("nan"), device=device)      # uninitialised reads would surface
+    aa = tg._attn_args(P, block, B, T)
+    saved, yo = nan(lib.sb_attn_train_saved_floats(ctypes.byref(aa))), nan(B * T * Fq * C).view(B, T, Fq, C)
+    aa.x, aa.y, aa.saved = xd.data_ptr(), yo.data_ptr(), saved.data_ptr()
+    abi.check(lib, lib.sb_attn_train_fwd(ctypes.byref(aa), _stream(device)), "sb_attn_train_fwd")
+    ab = abi.AttnBwdArgs()
+    ab.f = tg._attn_args(P, block, B, T)
+    ab.f.saved, ab.f.x = saved.data_ptr(), xd.data_ptr()
+    wsa = nan(lib.sb_attn_bwd_workspace_floats(ctypes.byref(ab.f)))
+    ab.gy, ab.gx, ab.ws = gx.data_ptr(), gx.data_ptr(), wsa.data_ptr()           # in place, as TrainGraph.backward calls it
+    G = {}
+    for field, mod in tg._ATTN:
+        gp = getattr(ab, "g" + field)
+        for f2, name in tg._ATTN_P:
+            G[mod + name] = torch.zeros_like(P[pre + mod + name])
+            setattr(gp, f2, G[mod + name].data_ptr())
+    abi.check(lib, lib.sb_attn_bwd(ctypes.byref(ab), _stream(device)), "sb_attn_bwd")
+    _sync(device)
+    errs = {"y": relerr(yo, y), "gx": relerr(gx, xs.grad)}
+    for k, v in G.items():
+        errs[k] = relerr(v, leaf[pre + k].grad)
+    return errs
+
+
 def load_grad_fixture(name):
     import json
     import os
