@@ -119,13 +119,18 @@ __global__ void __launch_bounds__(1024) istft_ola_kernel(const sb_backend_args a
         sp[k * NFP + fr] = v;
     }
     __syncthreads();
-    if (tid < n_fft) {
+    // the k loop is a chain of dependent basis loads: KS thread groups (blockDim = KS x n_fft rounded to warps) take a
+    // slice of k each and meet in shared memory (ola [KS][NF][n_fft])
+    const int nth = (n_fft + 31) & ~31, KS = blockDim.x / nth;
+    const int grp = tid / nth, r0 = tid - grp * nth;
+    if (grp < KS && r0 < n_fft) {
         float acc[NF];
 #pragma unroll
         for (int i = 0; i < NF; ++i) acc[i] = 0.f;
-        const float* bp = a.filt + tid;
+        const float* bp = a.filt + r0;
+        const int kper = (F2 + KS - 1) / KS, k0 = grp * kper, k1 = min(F2, k0 + kper);
 #pragma unroll 16
-        for (int k = 0; k < F2; ++k) {
+        for (int k = k0; k < k1; ++k) {
             const float bv = __ldg(bp + (size_t)k * n_fft);
             const float4 s0 = ld4(sp + k * NFP), s1 = ld4(sp + k * NFP + 4);
             const float s8 = sp[k * NFP + 8];
@@ -136,15 +141,18 @@ __global__ void __launch_bounds__(1024) istft_ola_kernel(const sb_backend_args a
             acc[8] = fmaf(s8, bv, acc[8]);
         }
 #pragma unroll
-        for (int i = 0; i < NF; ++i) ola[i * n_fft + tid] = acc[i];
+        for (int i = 0; i < NF; ++i) ola[(grp * NF + i) * n_fft + r0] = acc[i];
     }
     __syncthreads();
     const int look = n_fft - hop;
     float* dst = a.wave_out + (size_t)bs * a.T * hop + (size_t)t0 * hop;
     for (int i = tid; i < nv * hop; i += blockDim.x) {
         const int fr = i / hop, r = i - fr * hop;
-        float v = ola[(fr + 1) * n_fft + r];
-        if (r < look) v += ola[fr * n_fft + hop + r];
+        float v = 0.f;
+        for (int g2 = 0; g2 < KS; ++g2) {
+            v += ola[(g2 * NF + fr + 1) * n_fft + r];
+            if (r < look) v += ola[(g2 * NF + fr) * n_fft + hop + r];
+        }
         dst[i] = v;
     }
 }
@@ -282,8 +290,10 @@ static int launch_backend(const sb_backend_args& a, cudaStream_t st) {
     }
     const int LPP = C / 4, PPB = 256 / LPP;
     const int n_pos = a.T * a.F;
+    // every CTA first pulls its 72 weights into registers: give it several 32-position passes to amortise that over (one pass
+    // per CTA made the launch 25x slower than its L1 traffic allows, profiles/r02_launches_bench.txt) - about four CTAs per SM
     int gx = ceil_div(n_pos, PPB);
-    const int cap = 8 * sm_count();
+    const int cap = ceil_div(4 * sm_count(), a.B);
     if (gx > cap) gx = cap;
     dim3 grid(gx, a.B);
     switch (a.n_src) {
@@ -293,8 +303,10 @@ static int launch_backend(const sb_backend_args& a, cudaStream_t st) {
             set_error("sb_backend_fwd: n_src must be 1 or 2 (got %d)", a.n_src);
             return SB_E_UNSUPP;
     }
-    const int threads = ceil_div(a.n_fft, 32) * 32;
-    const size_t smem = ((size_t)2 * a.F * 12 + (size_t)(kIstftTT + 1) * a.n_fft) * sizeof(float);
+    const int nth = ceil_div(a.n_fft, 32) * 32;
+    const int KS = nth * 3 <= 1024 ? 3 : (nth * 2 <= 1024 ? 2 : 1);
+    const int threads = nth * KS;
+    const size_t smem = ((size_t)2 * a.F * 12 + (size_t)KS * (kIstftTT + 1) * a.n_fft) * sizeof(float);
     return launch("istft_ola", istft_ola_kernel, dim3(ceil_div(a.T, kIstftTT), a.B * a.n_src), dim3(threads), smem, st, a);
 }
 

@@ -14,12 +14,16 @@
 //          A operand while the cell update of the current step runs, keeps x' for the residual, and - once the projection
 //          of h_{s-1} (issued with step s) has landed in TMEM - stores y_{s-1} = x' + b + lin h_{s-1} as full 128-byte rows.
 //        * lane 0 of warp 1 issues the tcgen05.mma of a step the moment the 8 cell-update warps have published h:
-//          18 MMAs (N = 128) for units 0..31 + commit, 18 for units 32..63, 12 (N = 32) for the projection + commit.
+//          18 MMAs (N = 128) for units 0..31 + commit, 18 for units 32..63, 12 (N = 32) for the projection + a commit that
+//          means "every MMA of this step has finished".  (Four N = 64 quarters, so that all eight cell warps start on the
+//          first commit, were measured SLOWER - 858 vs 722 us per 145 steps: every MMA re-reads its 4 KB slice of A from
+//          shared memory whatever N is, and at N = 64 that read, not the math, sets the MMA time.)
 //   warps 4-11 cell-update group, thread = (row, half of the units): tcgen05.ld of its 128 gate columns in four chunks
-//          (the load of chunk k+1 in flight while chunk k is evaluated), bias, sigmoid / tanh, c in registers for the
-//          whole sequence, h back into the A operand as bf16 hi/lo, fence.proxy.async, ONE mbarrier arrive per warp.
+//          (the load of chunk k+1 in flight while chunk k is evaluated), bias, cell, c in registers for the whole
+//          sequence, h back into the A operand as bf16 hi/lo one chunk late (A may only be rewritten once every MMA has
+//          read it), fence.proxy.async, ONE mbarrier arrive per warp.
 //
-// No __syncthreads in the step loop: full[] (TMA bytes), gates[2] (tcgen05.commit) and hready (8 warp arrivals) are
+// No __syncthreads in the step loop: full[] (TMA bytes), gates[2] + alldone (tcgen05.commit) and hready (8 warp arrivals) are
 // mbarriers; the stream group uses one 128-thread named barrier per step.  Every wait is bounded and traps.
 //
 // Rows are tiled so that a TMA box never straddles an outer index (utterance): per outer index floor(rows_inner / 128)
@@ -99,6 +103,7 @@ __device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
 // bounded wait: a protocol error must end in a trap, not in a hung GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (long long spin = 0; spin < (1ll << 26); ++spin) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
@@ -130,8 +135,28 @@ __device__ __forceinline__ void pin(uint32_t (&r)[32]) {
     for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
 }
 
+// Explicit shared-space accesses.  The working set sits behind a pointer that was aligned by integer arithmetic, so the
+// compiler cannot prove the address space and emits generic LD.E / ST.E for plain dereferences (r02 SASS: the bias loads of
+// the cell update and the operand stores were generic, their consumers waited on the long scoreboard).
+__device__ __forceinline__ float4 lds4(const void* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+// Constants written in the prologue (biases, LayerNorm gain / bias): volatile keeps the load below the prologue's barrier and
+// in program order (a free-floating load was hoisted across whole chunks and spilled), no memory clobber so that arithmetic
+// may move around it; callers issue it one cell ahead of its use.
+__device__ __forceinline__ float4 lds4_ro(const void* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void sts16(void* p, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // 8 consecutive k of one row -> one 16-byte core-matrix row in the hi image and one in the lo image
-__device__ __forceinline__ void store_split8(unsigned char* a_hi, unsigned char* a_lo, int row, int chunk, const float (&v)[8]) {
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi4, uint4& lo4) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -141,9 +166,18 @@ __device__ __forceinline__ void store_split8(unsigned char* a_hi, unsigned char*
         hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
         lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
     }
+    hi4 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    lo4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void store_pair(unsigned char* a_hi, unsigned char* a_lo, int row, int chunk, const uint4 hi4, const uint4 lo4) {
     const int off = ((chunk * (kRows / 8) + (row >> 3)) * 8 + (row & 7)) * 16;
-    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    sts16(a_hi + off, hi4);
+    sts16(a_lo + off, lo4);
+}
+__device__ __forceinline__ void store_split8(unsigned char* a_hi, unsigned char* a_lo, int row, int chunk, const float (&v)[8]) {
+    uint4 hi4, lo4;
+    split8(v, hi4, lo4);
+    store_pair(a_hi, a_lo, row, chunk, hi4, lo4);
 }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -197,10 +231,11 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
     float* ln_s = reinterpret_cast<float*>(sm + kOffLn);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kOffBar);
     uint64_t* full = bars;                                  // [kSlabs]  TMA bytes of a step's stage(s)
-    uint64_t* gates = bars + kSlabs;                        // [2]       tcgen05.commit: units 0..31 | everything
-    uint64_t* hready = bars + kSlabs + 2;                   //           8 cell-update warps have published h
-    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(bars + kSlabs + 3);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kSlabs + 4);
+    uint64_t* gates = bars + kSlabs;                        // [2]       tcgen05.commit: the gate columns of units 32h .. 32h + 31
+    uint64_t* alldone = bars + kSlabs + 4;                  //           tcgen05.commit: every MMA of the step (incl. the projection)
+    uint64_t* hready = bars + kSlabs + 5;                   //           8 cell-update warps have published h
+    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(bars + kSlabs + 6);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kSlabs + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
@@ -246,8 +281,8 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
     }
     if (tid == 32) {
         for (int i = 0; i < kSlabs; ++i) mbar_init(full + i, 1);
-        mbar_init(gates + 0, 1);
-        mbar_init(gates + 1, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(gates + i, 1);
+        mbar_init(alldone, 1);
         mbar_init(hready, 8);
         bulk_barrier_init(wbar);                            // includes fence.mbarrier_init
         // the packed operand images (hi / lo gate matrix, hi / lo projection: 106 KB) in one TMA bulk copy (constant data)
@@ -304,11 +339,11 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
             const unsigned char* base = slabs + (size_t)slot * nld * kSlabBytes + (size_t)r * (kC * 4);
             float4 xv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(base + ((i ^ (r & 7)) << 4));
+            for (int i = 0; i < 8; ++i) xv[i] = lds4(base + ((i ^ (r & 7)) << 4));
             if (nld == 2) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 u4 = *reinterpret_cast<const float4*>(base + kSlabBytes + ((i ^ (r & 7)) << 4));
+                    const float4 u4 = lds4(base + kSlabBytes + ((i ^ (r & 7)) << 4));
                     xv[i].x += u4.x; xv[i].y += u4.y; xv[i].z += u4.z; xv[i].w += u4.w;
                 }
             }
@@ -339,7 +374,7 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const float4 t = xv[2 * ch + i];
-                    const float4 gg = ld4(ln_s + 4 * (2 * ch + i)), bb = ld4(ln_s + kC + 4 * (2 * ch + i));
+                    const float4 gg = lds4_ro(ln_s + 4 * (2 * ch + i)), bb = lds4_ro(ln_s + kC + 4 * (2 * ch + i));
                     v[4 * i + 0] = fmaf((t.x - mean) * rstd, gg.x, bb.x); v[4 * i + 1] = fmaf((t.y - mean) * rstd, gg.y, bb.y);
                     v[4 * i + 2] = fmaf((t.z - mean) * rstd, gg.z, bb.z); v[4 * i + 3] = fmaf((t.w - mean) * rstd, gg.w, bb.w);
                 }
@@ -366,14 +401,14 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
                 }
             }
         };
-        auto issue_gates = [&](int half) {                  // gates[128 x 128] for units 32*half .. : rows n of the image
+        auto issue_gates = [&](int q) {                     // gates[128 x 128] for units 32q .. 32q + 31: rows 128q .. of the image
             uint32_t acc = 0;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t ab = pass == 2 ? a_lo_s : a_hi_s, wb = (pass == 1 ? w_lo_s : w_hi_s) + half * 16 * 128;
+                const uint32_t ab = pass == 2 ? a_lo_s : a_hi_s, wb = (pass == 1 ? w_lo_s : w_hi_s) + q * 16 * 128;
 #pragma unroll
                 for (int ks = 0; ks < kK / 16; ++ks) {
-                    umma(tmem + 128 * half, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
+                    umma(tmem + 128 * q, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
                          make_desc(wb + 2 * ks * kWChunkBytes, kWChunkBytes, 128), idesc_g, acc);
                     acc = 1;
                 }
@@ -394,7 +429,7 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
                 float4 o = make_float4(__uint_as_float(pr[4 * i]), __uint_as_float(pr[4 * i + 1]), __uint_as_float(pr[4 * i + 2]),
                                        __uint_as_float(pr[4 * i + 3]));
                 if (dir == 0) {                             // direction 0 adds bias and residual
-                    const float4 bl = ld4(ln_s + 2 * kC + 4 * i);
+                    const float4 bl = lds4_ro(ln_s + 2 * kC + 4 * i);
                     o.x += bl.x + resv[i].x; o.y += bl.y + resv[i].y;
                     o.z += bl.z + resv[i].z; o.w += bl.w + resv[i].w;
                 }
@@ -415,14 +450,16 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
                 if (s == 0) bulk_wait(wbar, 0);             // the operand images have landed
                 mbar_wait(hready, (uint32_t)(s & 1));       // h_{s-1} (or h0) is in A, the gate columns have been read
                 fence_after();
-                issue_gates(0);
-                umma_commit(gates + 0);
-                issue_gates(1);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    issue_gates(q);
+                    umma_commit(gates + q);
+                }
                 if (s > 0) issue_proj();
-                umma_commit(gates + 1);
+                umma_commit(alldone);
             }
             __syncwarp();
-            mbar_wait(gates + 1, (uint32_t)(s & 1));        // every MMA of step s is done: A may be rewritten, proj is ready
+            mbar_wait(alldone, (uint32_t)(s & 1));          // every MMA of step s is done: A may be rewritten, proj is ready
             fence_after();
             if (s > 0) emit(s - 1, res_prev);
 #pragma unroll
@@ -437,31 +474,27 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
             mbar_wait(hready, (uint32_t)(S & 1));
             fence_after();
             issue_proj();
-            umma_commit(gates + 1);
+            umma_commit(alldone);
         }
         __syncwarp();
-        mbar_wait(gates + 1, (uint32_t)(S & 1));
+        mbar_wait(alldone, (uint32_t)(S & 1));
         fence_after();
         emit(S - 1, res_prev);
     } else {
         // =============================================================================================================
-        // cell-update group: thread (row, half) owns units 32*hf .. 32*hf + 31 of its row
+        // cell-update group: thread (row, hf) owns units 32hf + 8k .. + 7 for k = 0..3 (register c[8k + j])
         // =============================================================================================================
         const int hf = (warp - 4) >> 2;
         float c[32];
         if (a.h0 && valid) {
             const float* cp = a.c0 + (long long)grow * kH + 32 * hf;
             const float* hp = a.h0 + (long long)grow * kH + 32 * hf;
-            float4 hv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v = ld_plain4(cp + 4 * i);     // plain loads: hN / cN may alias h0 / c0
-                c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
-                hv[i] = ld_plain4(hp + 4 * i);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const float4 v0 = hv[2 * ch], v1 = hv[2 * ch + 1];
+            for (int ch = 0; ch < 4; ++ch) {                // plain loads: hN / cN may alias h0 / c0
+                const float4 c0 = ld_plain4(cp + 8 * ch), c1 = ld_plain4(cp + 8 * ch + 4);
+                c[8 * ch] = c0.x; c[8 * ch + 1] = c0.y; c[8 * ch + 2] = c0.z; c[8 * ch + 3] = c0.w;
+                c[8 * ch + 4] = c1.x; c[8 * ch + 5] = c1.y; c[8 * ch + 6] = c1.z; c[8 * ch + 7] = c1.w;
+                const float4 v0 = ld_plain4(hp + 8 * ch), v1 = ld_plain4(hp + 8 * ch + 4);
                 const float h8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                 store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
             }
@@ -479,7 +512,9 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         float* const hN = (a.hN && valid) ? a.hN + (long long)grow * kH + 32 * hf : nullptr;
         const uint32_t gcol = tmem + lane_base + 128 * hf;
         for (int s = 0; s < S; ++s) {
-            mbar_wait(gates + hf, (uint32_t)(s & 1));
+            const uint32_t par = (uint32_t)(s & 1);
+            uint4 p_hi = make_uint4(0u, 0u, 0u, 0u), p_lo = p_hi;    // chunk k - 1 as operand rows, stored one chunk late
+            mbar_wait(gates + hf, par);
             fence_after();
             uint32_t ga[32], gb[32];
             tmem_ld32_issue(gcol, ga);
@@ -490,33 +525,38 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
                 uint32_t (&cur)[32] = (ch & 1) ? gb : ga;
                 uint32_t (&nxt)[32] = (ch & 1) ? ga : gb;
                 if (ch < 3) tmem_ld32_issue(gcol + 32 * (ch + 1), nxt);
+                const float* bp = bias_s + 4 * (32 * hf + 8 * ch);
+                float4 nb_next = lds4_ro(bp);
                 float h8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 bb = ld4(bias_s + 4 * (32 * hf + 8 * ch + j));
+                    const float4 nb = nb_next;
+                    if (j < 7) nb_next = lds4_ro(bp + 4 * (j + 1));
                     if (CELL7) {
                         h8[j] = cell7(__uint_as_float(cur[4 * j + 0]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
-                                      __uint_as_float(cur[4 * j + 3]), bb, c[8 * ch + j]);
+                                      __uint_as_float(cur[4 * j + 3]), nb, c[8 * ch + j]);
                     } else {
-                        const float ig = sigmoid_f(__uint_as_float(cur[4 * j + 0]) + bb.x), fg = sigmoid_f(__uint_as_float(cur[4 * j + 1]) + bb.y);
-                        const float gg = tanh_f(__uint_as_float(cur[4 * j + 2]) + bb.z), og = sigmoid_f(__uint_as_float(cur[4 * j + 3]) + bb.w);
+                        const float ig = sigmoid_f(__uint_as_float(cur[4 * j + 0]) + nb.x), fg = sigmoid_f(__uint_as_float(cur[4 * j + 1]) + nb.y);
+                        const float gg = tanh_f(__uint_as_float(cur[4 * j + 2]) + nb.z), og = sigmoid_f(__uint_as_float(cur[4 * j + 3]) + nb.w);
                         c[8 * ch + j] = fmaf(fg, c[8 * ch + j], ig * gg);
                         h8[j] = og * tanh_f(c[8 * ch + j]);
                     }
                 }
-                // The first half's warps get here while the second half's MMAs may still be READING A: nothing may be
-                // written into A before gates[1] has fired.
-                if (hf == 0 && ch == 0) mbar_wait(gates + 1, (uint32_t)(s & 1));
-                store_split8(a_hi, a_lo, r, 4 + 4 * hf + ch, h8);
                 if (s == S - 1 && hN) {
                     st4(hN + 8 * ch, make_float4(h8[0], h8[1], h8[2], h8[3]));
                     st4(hN + 8 * ch + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
                 }
+                // Nothing may be written into A before every MMA of the step has read it (the first half's warps get here while
+                // the second half's MMAs may still be reading A): chunk k goes out after chunk k + 1 has been evaluated.
+                if (ch == 1) mbar_wait(alldone, par);
+                if (ch > 0) store_pair(a_hi, a_lo, r, 4 + 4 * hf + ch - 1, p_hi, p_lo);
+                split8(h8, p_hi, p_lo);
                 if (ch < 3) {
                     tmem_wait_ld();
                     pin(nxt);
                 }
             }
+            store_pair(a_hi, a_lo, r, 4 + 4 * hf + 3, p_hi, p_lo);
             fence_before();
             fence_async_smem();
             __syncwarp();
@@ -525,7 +565,10 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         if (a.cN && valid) {
             float* cp = a.cN + (long long)grow * kH + 32 * hf;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) st4(cp + 4 * i, make_float4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]));
+            for (int ch = 0; ch < 4; ++ch) {
+                st4(cp + 8 * ch, make_float4(c[8 * ch], c[8 * ch + 1], c[8 * ch + 2], c[8 * ch + 3]));
+                st4(cp + 8 * ch + 4, make_float4(c[8 * ch + 4], c[8 * ch + 5], c[8 * ch + 6], c[8 * ch + 7]));
+            }
         }
     }
     fence_before();

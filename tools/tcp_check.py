@@ -109,3 +109,36 @@ if which in ("all", "golden"):
     import parity_cases as pc
     for name in ("syn_offline", "syn_nopad", "wav_syn_1m", "opi_offline"):
         print(name, pc.run_golden(lib, "cuda:0", name, TCP, TCP), flush=True)
+
+if which == "cell7":
+    # A/B of the shared-reciprocal cell update (SB_OPT_TC_CELL7): values against the one-reciprocal-per-gate form on the same
+    # inputs (also with pre-activations driven far into saturation: the exponent clamps) and time per launch
+    torch.manual_seed(0)
+    net = Net(**SYN).to(dev).eval()
+    pk = net.engine().packed
+    F, C, H = 145, 32, 64
+
+    def opt(v):
+        abi.check(lib, lib.sb_set_option(abi.SB_OPT_TC_CELL7, v), "sb_set_option")
+    for (B, T, scale) in ((32, 8, 1.0), (32, 32, 1.0), (32, 32, 40.0), (32, 125, 1.0), (32, 625, 1.0)):
+        g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
+        x = (scale * torch.randn(B, T, F, C, generator=g)).to(dev)
+        x1 = torch.randn(B, T, F, C, generator=g).to(dev)
+        film = (scale * torch.randn(2, B, F, C, generator=g)).to(dev)
+        h = (0.3 * torch.randn(B * F, H, generator=g)).to(dev)
+        c = (scale * 0.3 * torch.randn(B * F, H, generator=g)).to(dev)
+        opt(0)
+        rf, rb, f_old = intra_call(pk, x, film, TCP)
+        t_old = timeit(f_old)
+        ry, rh, rc, g_old = inter_call(pk, x, x1, h, c, TCP)
+        u_old = timeit(g_old)
+        opt(1)
+        nf, nb, f_new = intra_call(pk, x, film, TCP)
+        t_new = timeit(f_new)
+        ny, nh, nc, g_new = inter_call(pk, x, x1, h, c, TCP)
+        u_new = timeit(g_new)
+        d_intra = max(float((rf - nf).abs().max()), float((rb - nb).abs().max()))
+        d_inter = max(float((ry - ny).abs().max()), float((rh - nh).abs().max()), float((rc - nc).abs().max() / max(1.0, float(rc.abs().max()))))
+        nan = bool(torch.isnan(nf).any() or torch.isnan(nb).any() or torch.isnan(ny).any() or torch.isnan(nh).any() or torch.isnan(nc).any())
+        print("B=%3d T=%3d scale=%4.0f  intra maxabs %.2e  %8.1f -> %8.1f us   inter maxabs %.2e  %8.1f -> %8.1f us  nan=%s"
+              % (B, T, scale, d_intra, t_old, t_new, d_inter, u_old, u_new, nan), flush=True)
