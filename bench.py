@@ -294,6 +294,28 @@ def training_leg(dev, rank, world, batch=8, steps=3):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)                # every rank takes the same branch below
     if int(flag.item()) == 0:
         return {"error": err or "a peer rank failed"}
+    # the reduced gradient is the gradient of the GLOBAL-batch mean loss: 2 clips x 1 s per rank through the kernels and the
+    # NCCL all-reduce, against the same world x 2 clips in one batch on rank 0
+    grad_relerr = None
+    if world > 1:
+        n1 = 24000 // CHUNK * CHUNK
+        gg = torch.Generator().manual_seed(4242)
+        mix_g = 0.1 * torch.randn(2 * world, MICS, n1, generator=gg)
+        tgt_g = 0.1 * torch.randn(2 * world, 1, n1, generator=gg)
+        dis_g = radius_one_hot(2 * world)
+
+        def snr_grads(lo, hi):
+            red.zero_grad()
+            est = tnet({"mixture": mix_g[lo:hi].to(dev), "dis_embed": dis_g[lo:hi].to(dev)})["output"]
+            t = tgt_g[lo:hi].to(dev)
+            (-(10 * torch.log10(t.pow(2).sum(-1) / ((est - t).pow(2).sum(-1) + 1e-8))).mean()).backward()
+        snr_grads(2 * rank, 2 * rank + 2)
+        red.all_reduce_mean(2)
+        reduced = red.flat.clone()
+        if rank == 0:
+            snr_grads(0, 2 * world)
+            grad_relerr = float((red.flat - reduced).abs().max() / red.flat.abs().max())
+        dist.barrier()
     step()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -311,6 +333,7 @@ def training_leg(dev, rank, world, batch=8, steps=3):
     frames = batch * T_FRAMES * world
     return {"value": frames / (ms * 1e-3), "unit": "training frames/s", "ms_per_step": ms, "global_batch": batch * world,
             "clip_seconds": 5.0, "dtype": "f32", "steps": steps, "loss": float(loss.detach()),
+            "grad_relerr_vs_global_batch": grad_relerr,
             "collective": "one all-reduce of %d fp32 gradients per step (NCCL)" % red.numel if world > 1 else "none (1 GPU)",
             "note": "forward + backward through csrc/sb_train.cu, clip after the reduction, Adam; see tools/train_bench.py"}
 

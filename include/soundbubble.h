@@ -82,6 +82,8 @@ extern "C" {
                                 /* warp-specialised TMA pipeline lstm_tcp_kernel whenever a tensor map can address the grid (A/B knob) */
 #define SB_OPT_TC_CELL7 6       /* lstm_tcp_kernel's cell update with shared reciprocals (5 ex2 + 2 rcp per cell instead of 5 + 5;  */
                                 /* the kernel is bound by the XU pipe).  Default set from the measured A/B, see DESIGN.md section 4.  */
+#define SB_OPT_TRAIN_TC 7       /* 1 (default) = LSTM weight gradients (dW_ih, dW_hh, db) of the C = 32 paths as a tcgen05 reduction GEMM */
+                                /* with bf16 hi/lo three-term operands (sb_train_tc.cu); 0 = the fp32 SIMT outer_kernel                 */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

@@ -25,6 +25,7 @@ int  check_launch(const char* what);        // cudaGetLastError() -> 0 / cudaErr
 bool pdl_enabled();                         // programmatic dependent launch (sb_set_option(SB_OPT_PDL, 1))
 bool attn_tc_enabled();                     // tcgen05 attention core for T >= 64 (sb_set_option(SB_OPT_ATTN_TC, 0) turns it off)
 bool train_one_row_enabled();                // training LSTM kernels with one gate row / one W_hh column per thread (sb_set_option(SB_OPT_TRAIN_ONE_ROW, 1))
+bool train_tc_enabled();                     // LSTM weight gradients on tcgen05 (sb_train_tc.cu; sb_set_option(SB_OPT_TRAIN_TC, v))
 bool tc_cell7_enabled();                     // shared-reciprocal cell update in lstm_tcp_kernel (sb_set_option(SB_OPT_TC_CELL7, v))
 bool tc_v1_enabled();                        // SB_ALGO_TC on the first tcgen05 kernel instead of the TMA pipeline (sb_set_option(SB_OPT_TC_V1, 1))
 bool train_ffma2_enabled();                  // packed FFMA2 in the training GEMM kernels (sb_set_option(SB_OPT_TRAIN_FFMA2, v))
@@ -47,6 +48,20 @@ int  ensure_smem(const void* func, size_t bytes, const char* name);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// sb_train_tc.cu: dW_ih / dW_hh / db of one LSTM direction as one tcgen05 reduction GEMM over the n = (row, step) pairs
+struct WgradTc {
+    const float* dz;        // [N][4H]
+    const float* xn;        // [N][C]   LayerNorm output (the LSTM's input)
+    const float* h;         // [N][H]   hidden states; row n pairs with h[n - 1] (n + 1 for the reverse direction)
+    float* dW_ih;           // [4H][C]  accumulated with atomics
+    float* dW_hh;           // [4H][H]
+    float* db;              // [4H] or NULL
+    float* db2;             // [4H] or NULL (b_hh receives the same sum as b_ih)
+    int S, reverse;
+    long long N, rows_per_cta;
+};
+int run_wgrad_tc(const WgradTc& w, cudaStream_t st);
 
 // One place through which every kernel of the library is launched: opt-in shared memory, optional programmatic
 // dependent launch (the kernel then calls pdl_wait() before it touches anything a predecessor wrote), accounting.

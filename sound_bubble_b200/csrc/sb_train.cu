@@ -1752,6 +1752,16 @@ static int path_bwd(const sb_path_bwd_args& b, cudaStream_t st) {
     else SB_CHECK(launch("lstm_train_bwd", lstm_train_bwd2_kernel, dim3((unsigned)ceil_div_ll(d.R, 4), d.nd), dim3(128), 0, st, l));
     // (3) weight gradients in one pass over dz: dW_ih = dz^T LN(x), dW_hh = dz^T h_prev, db = sum dz
     for (int k = 0; k < d.nd; ++k) {
+#ifndef SB_EMU
+        if (a.C == 32 && train_tc_enabled()) {              // tcgen05 reduction GEMM (sb_train_tc.cu)
+            WgradTc w{};
+            w.dz = v.gates[k]; w.xn = v.xn; w.h = v.h[k];
+            w.dW_ih = b.g_w_ih[k]; w.dW_hh = b.g_w_hh[k]; w.db = b.g_b_ih[k]; w.db2 = b.g_b_hh[k];
+            w.S = d.S; w.reverse = k; w.N = d.N;
+            SB_CHECK(run_wgrad_tc(w, st));
+            continue;
+        }
+#endif
         Outer o{};
         o.A = v.gates[k]; o.map = d.map; o.a_mapped = 0; o.reverse = k; o.N = d.N;
         o.Bm = v.xn; o.b_mode = 0; o.kc0 = a.C; o.dW = b.g_w_ih[k]; o.ldw = a.C; o.db = b.g_b_ih[k]; o.db2 = b.g_b_hh[k];

@@ -170,3 +170,59 @@ def test_every_distance_embedding_type(lib, dt):
 def test_training_call_returns_the_next_state(lib):
     _ok(tc.check_next_state(lib, DEV, "dis_embed", dict(SYN, B=2), B=2, T=7))
     _ok(tc.check_next_state(lib, DEV, "optim", dict(OPI, B=1), B=1, T=1))
+
+
+def test_pretrain_stage_three_optimizer_steps_reproduce_the_oracle_loss_curve():
+    """syn_experiments/pretrain_stage.json as src/train_pt.py runs it (PLModule args from the fixture: TFG_S model, SNRLPLoss
+    ('snr', neg_weight 100), Adam lr 1.2e-3, grad_clip 1), driven through train_dist.TrainModule on the B200 for three
+    optimizer steps with train_epoch's call order, against the same three steps of oracle autograd on the CPU (same
+    initial weights, same loss restatement, torch Adam + clip_grad_norm_).  One clip of the batch has a silent target, so
+    both branches of the loss are on the path."""
+    import json
+    import os
+    from sound_bubble_b200.losses import SNRLPLoss
+    from sound_bubble_b200.train_dist import TrainModule
+    exp = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "experiments.json")))["syn_experiments/pretrain_stage.json"]
+    args = dict(exp["pl_module_args"], grad_clip=exp["grad_clip"])
+    ocfg = orc.OracleConfig.from_kwargs("dis_embed", **args["model_params"])
+    sd = make_state_dict(ocfg, 0)
+    B, n = 3, 192 * 40
+    mix = synthetic_mixture(B, 6, n, seed=21)
+    tgt = 0.6 * mix[:, :1].clone()
+    tgt[1] = 0.0
+    dis = radius_one_hot(B)
+    nspk = torch.tensor([1, 0, 2])
+
+    # oracle: the reference's arithmetic under torch autograd
+    leaf = {k: v.clone().requires_grad_("_filters" not in k) for k, v in sd.items()}
+    params = [v for v in leaf.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, **args["optimizer_params"])
+    loss_fn = SNRLPLoss(**args["loss_params"])
+    want = []
+    for _ in range(3):
+        opt.zero_grad()
+        est = orc.net_forward(leaf, ocfg, {"mixture": mix, "dis_embed": dis})["output"]
+        loss = loss_fn(est=est, gt=tgt).mean()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, args["grad_clip"])
+        opt.step()
+        want.append(float(loss.detach()))
+
+    m = TrainModule(**args)
+    m.model.load_state_dict(sd, strict=True)
+    m.model.to(DEV)
+    m.optimizer = torch.optim.Adam(m.model.parameters(), **args["optimizer_params"])      # after .to(), as PLModule.load_state re-creates it
+    m.train()
+    batch = ({"mixture": mix.to(DEV), "dis_embed": dis.to(DEV)}, {"target": tgt.to(DEV), "num_target_speakers": nspk})
+    got = []
+    for i in range(3):
+        m.reset_grad()
+        loss, nb = m.training_step(batch, i)
+        loss.backward()
+        m.backprop()
+        got.append(float(loss.detach()))
+    print("loss curve  ours %s  oracle %s" % (got, want))
+    assert nb == B and m.get_avg_metric_at_epoch("train/loss") == pytest.approx(sum(got) / 3, rel=1e-5)
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (got, want)
+    assert want[2] < want[0]                                           # and the curve goes down

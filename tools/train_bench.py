@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--config", default="syn", choices=["syn", "rpi"], help="syn = TFG_S (config 4), rpi = Raspberry-Pi conv-LSTM model (config 5)")
     ap.add_argument("--ffma2", type=int, default=-1, help="0 / 1 = SB_OPT_TRAIN_FFMA2 (packed FMAs in the training GEMM kernels); -1 = library default")
     ap.add_argument("--one-row", type=int, default=0, help="1 = the first LSTM training kernels (SB_OPT_TRAIN_ONE_ROW)")
+    ap.add_argument("--train-tc", type=int, default=-1, help="0 / 1 = SB_OPT_TRAIN_TC (LSTM weight gradients on tcgen05); -1 = library default")
     args = ap.parse_args()
     from sound_bubble_b200 import Net, _lib
     dev = torch.device("cuda", 0)
@@ -34,6 +35,8 @@ def main():
         _lib.load().sb_set_option(3, 1)
     if args.ffma2 >= 0:
         _lib.load().sb_set_option(4, args.ffma2)
+    if args.train_tc >= 0:
+        _lib.load().sb_set_option(7, args.train_tc)
     torch.manual_seed(0)
     if args.config == "rpi":
         from oracle.cases import RPI          # configuration dictionary only
@@ -70,7 +73,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     frames = args.batch * (n // 192)
-    res = {"what": "training step (forward + backward + clip + Adam), %s, fp32" % ("TFG_S" if args.config == "syn" else "Raspberry-Pi conv-LSTM model"), "batch": args.batch, "seconds": args.seconds, "one_row_kernels": bool(args.one_row), "ffma2_gemms": args.ffma2,
+    res = {"what": "training step (forward + backward + clip + Adam), %s, fp32" % ("TFG_S" if args.config == "syn" else "Raspberry-Pi conv-LSTM model"), "batch": args.batch, "seconds": args.seconds, "one_row_kernels": bool(args.one_row), "ffma2_gemms": args.ffma2, "train_tc": args.train_tc,
            "ms_per_step": ms, "train_frames_per_s": frames / ms * 1e3, "clips_per_s": args.batch / ms * 1e3,
            "launches_per_step": (_lib.launch_count() - l0) / args.steps,
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": float(loss)}
