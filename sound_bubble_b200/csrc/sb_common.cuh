@@ -60,6 +60,8 @@ struct WgradTc {
     float* db2;             // [4H] or NULL (b_hh receives the same sum as b_ih)
     int S, reverse;
     long long N, rows_per_cta;
+    float* scratch;         // optional: per-CTA partial sums [ctas][4H * (C + H) + 4H]; a second kernel adds them up (no atomics)
+    long long scratch_floats;
 };
 int run_wgrad_tc(const WgradTc& w, cudaStream_t st);
 

@@ -1758,6 +1758,8 @@ static int path_bwd(const sb_path_bwd_args& b, cudaStream_t st) {
             w.dz = v.gates[k]; w.xn = v.xn; w.h = v.h[k];
             w.dW_ih = b.g_w_ih[k]; w.dW_hh = b.g_w_hh[k]; w.db = b.g_b_ih[k]; w.db2 = b.g_b_hh[k];
             w.S = d.S; w.reverse = k; w.N = d.N;
+            w.scratch = b.ws;                               // the workspace is idle between BPTT (dh consumed) and lstm_dx (dxn written)
+            w.scratch_floats = (long long)d.nd * d.N * a.H + d.N * a.C;
             SB_CHECK(run_wgrad_tc(w, st));
             continue;
         }
