@@ -69,7 +69,8 @@ def test_untrainable_configurations_raise():
     check_trainable(ModelConfig(variant="dis_embed", **SYN))
     check_trainable(ModelConfig(variant="dis_embed", **dict(SYN, conv_lstm=True)))
     check_trainable(ModelConfig(variant="dis_embed", **dict(SYN, dis_type="linear2")))
-    for kw in (dict(SYN, use_attn=True),):
+    check_trainable(ModelConfig(variant="dis_embed", **dict(SYN, use_attn=True)))           # L * E = 8: backward kernels exist
+    for kw in (dict(SYN, use_attn=True, E=3),):                                                # L * E = 12: none
         with pytest.raises(NotImplementedError):
             check_trainable(ModelConfig(variant="dis_embed", **kw))
 
