@@ -14,8 +14,11 @@
 //          A operand while the cell update of the current step runs, keeps x' for the residual, and - once the projection
 //          of h_{s-1} (issued with step s) has landed in TMEM - stores y_{s-1} = x' + b + lin h_{s-1} as full 128-byte rows.
 //        * lane 0 of warp 1 issues the tcgen05.mma of a step the moment the 8 cell-update warps have published h:
-//          18 MMAs (N = 128) for units 0..31 + commit, 18 for units 32..63, 12 (N = 32) for the projection + a commit that
-//          means "every MMA of this step has finished".  (Four N = 64 quarters, so that all eight cell warps start on the
+//          12 MMAs (N = 256: the h part of the contraction, three terms x four k steps) + commit, 12 (N = 32) for the
+//          projection + a commit that means "every MMA of this step has finished"; the 6 MMAs of the x part do not depend on
+//          h and were issued a step earlier into the other of two TMEM gate buffers, while the cell warps were busy.
+//          Measured (profiles/r02_tcp_*.txt, us per 145 steps): two N = 128 halves with a commit each 674, + x part ahead 681,
+//          one N = 256 MMA per k step 688, + x part ahead 641: per-MMA overhead, not tensor throughput, sits on the serial path.  (Four N = 64 quarters, so that all eight cell warps start on the
 //          first commit, were measured SLOWER - 858 vs 722 us per 145 steps: every MMA re-reads its 4 KB slice of A from
 //          shared memory whatever N is, and at N = 64 that read, not the math, sets the MMA time.)
 //   warps 4-11 cell-update group, thread = (row, half of the units): tcgen05.ld of its 128 gate columns in four chunks
@@ -46,6 +49,8 @@ namespace tcp {
 
 constexpr int kRows = 128, kC = 32, kH = 64, kK = kC + kH, kN = 4 * kH;
 constexpr int kThreads = 384;
+constexpr bool kPreX = true;                                // x part of the contraction issued one step ahead (688 -> 641 us per 145 steps)
+constexpr int kGateN = 256;                                 // gate columns per MMA: 256 = one MMA per k step, 128 = two halves with a commit each
 constexpr int kAChunkBytes = (kRows / 8) * 128;            // LBO of A: 2048
 constexpr int kWChunkBytes = (kN / 8) * 128;               // LBO of the gate matrix: 4096
 constexpr int kPChunkBytes = (kC / 8) * 128;               // LBO of the projection: 512
@@ -387,38 +392,43 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         // ---- MMA issue (one thread) ---------------------------------------------------------------------------------
         const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), w_hi_s = smem_u32(w_hi), w_lo_s = smem_u32(w_lo);
         const uint32_t p_hi_s = smem_u32(p_hi), p_lo_s = smem_u32(p_lo);
-        constexpr uint32_t idesc_g = make_idesc(128, 128), idesc_p = make_idesc(128, 32);
-        auto issue_proj = [&]() {                           // proj[128 x 32] = h (k chunks 4..11 of A) . lin^T
+        constexpr uint32_t idesc_g = make_idesc(128, kGateN), idesc_p = make_idesc(128, 32);
+        // TMEM: two gate buffers of 256 columns (step s accumulates into buffer s & 1); the projection of h_{s-1}, issued with
+        // step s, lands in columns 0..31 of the OTHER buffer - the one step s - 1 used, which every cell warp has finished
+        // reading - and is read back by this group before the x part of step s + 1 overwrites that buffer.
+        auto issue_proj = [&](uint32_t col) {               // proj[128 x 32] = h (k chunks 4..11 of A) . lin^T
             uint32_t acc = 0;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
                 const uint32_t ab = pass == 2 ? a_lo_s : a_hi_s, pb = pass == 1 ? p_lo_s : p_hi_s;
 #pragma unroll
                 for (int ks = 0; ks < kH / 16; ++ks) {
-                    umma(tmem + 256, make_desc(ab + (4 + 2 * ks) * kAChunkBytes, kAChunkBytes, 128),
+                    umma(tmem + col, make_desc(ab + (4 + 2 * ks) * kAChunkBytes, kAChunkBytes, 128),
                          make_desc(pb + 2 * ks * kPChunkBytes, kPChunkBytes, 128), idesc_p, acc);
                     acc = 1;
                 }
             }
         };
-        auto issue_gates = [&](int q) {                     // gates[128 x 128] for units 32q .. 32q + 31: rows 128q .. of the image
-            uint32_t acc = 0;
+        // gates[128 x 128] for units 32q .. 32q + 31 (rows 128q .. of the image), k steps [ks0, ks1) of the K = 96 contraction:
+        // the x part (k steps 0, 1) does not depend on h and is issued one step ahead, the h part (2..5) accumulates onto it
+        auto issue_gates = [&](uint32_t col, int q, int ks0, int ks1, bool fresh) {
+            uint32_t acc = fresh ? 0u : 1u;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
                 const uint32_t ab = pass == 2 ? a_lo_s : a_hi_s, wb = (pass == 1 ? w_lo_s : w_hi_s) + q * 16 * 128;
-#pragma unroll
-                for (int ks = 0; ks < kK / 16; ++ks) {
-                    umma(tmem + 128 * q, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
+                for (int ks = ks0; ks < ks1; ++ks) {
+                    umma(tmem + col + 128 * q, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
                          make_desc(wb + 2 * ks * kWChunkBytes, kWChunkBytes, 128), idesc_g, acc);
                     acc = 1;
                 }
             }
         };
+        constexpr int kXs = kPreX ? kC / 16 : 0, kKs = kK / 16;  // k steps issued ahead (the x part) / of the whole contraction
 
         float* const outp = a.out[dir] + rbase;
-        auto emit = [&](int step, const float4 (&resv)[8]) {                  // y_step = lin h_step [+ b + x'_step]
+        auto emit = [&](int step, const float4 (&resv)[8], uint32_t col) {    // y_step = lin h_step [+ b + x'_step]
             uint32_t pr[32];
-            tmem_ld32_issue(tmem + lane_base + 256, pr);
+            tmem_ld32_issue(tmem + lane_base + col, pr);
             tmem_wait_ld();
             pin(pr);
             if (!valid) return;
@@ -443,43 +453,59 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         for (int i = 0; i < 8; ++i) res_prev[i] = res_cur[i];
         fence_async_smem();
         for (int s = 0; s < S; ++s) {
+            const uint32_t gbuf = 256u * (uint32_t)(s & 1), obuf = 256u - gbuf;
             fence_before();
             bar_sync(1, 128);                               // x part of step s complete, its stage read by all four warps
             if (tid == 0 && s + nslots < S) issue_loads(s + nslots);
             if (tid == 32) {
-                if (s == 0) bulk_wait(wbar, 0);             // the operand images have landed
+                if (s == 0) {
+                    bulk_wait(wbar, 0);                     // the operand images have landed
+                    fence_after();
+                    if (kPreX)
+                        for (int q = 0; q < 256 / kGateN; ++q) issue_gates(gbuf, q, 0, kXs, true);     // x part of step 0 (later: one step ahead)
+                }
                 mbar_wait(hready, (uint32_t)(s & 1));       // h_{s-1} (or h0) is in A, the gate columns have been read
                 fence_after();
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    issue_gates(q);
+                for (int q = 0; q < 256 / kGateN; ++q) {
+                    issue_gates(gbuf, q, kXs, kKs, !kPreX);
                     umma_commit(gates + q);
                 }
-                if (s > 0) issue_proj();
+                if (kGateN == 256) umma_commit(gates + 1);
+                if (s > 0) issue_proj(obuf);
                 umma_commit(alldone);
             }
             __syncwarp();
             mbar_wait(alldone, (uint32_t)(s & 1));          // every MMA of step s is done: A may be rewritten, proj is ready
             fence_after();
-            if (s > 0) emit(s - 1, res_prev);
+            if (s > 0) emit(s - 1, res_prev, obuf);
 #pragma unroll
             for (int i = 0; i < 8; ++i) res_prev[i] = res_cur[i];
-            if (s + 1 < S) build(s + 1, res_cur);
-            fence_async_smem();
+            if (s + 1 < S) {
+                build(s + 1, res_cur);
+                fence_async_smem();
+                fence_before();
+                bar_sync(2, 128);                           // x part of step s + 1 in A; every warp has read the projection
+                if (kPreX && tid == 32) {                   // ... so the other buffer may take the x part of step s + 1 now,
+                    fence_after();                          // while the cell warps are still busy with step s
+                    for (int q = 0; q < 256 / kGateN; ++q) issue_gates(obuf, q, 0, kXs, true);
+                }
+            }
         }
         // ---- drain: projection of the last step ------------------------------------------------------------------------
+        const uint32_t dbuf = 256u - 256u * (uint32_t)(S & 1);
         fence_before();
         bar_sync(1, 128);
         if (tid == 32) {
             mbar_wait(hready, (uint32_t)(S & 1));
             fence_after();
-            issue_proj();
+            issue_proj(dbuf);
             umma_commit(alldone);
         }
         __syncwarp();
         mbar_wait(alldone, (uint32_t)(S & 1));
         fence_after();
-        emit(S - 1, res_prev);
+        emit(S - 1, res_prev, dbuf);
     } else {
         // =============================================================================================================
         // cell-update group: thread (row, hf) owns units 32hf + 8k .. + 7 for k = 0..3 (register c[8k + j])
@@ -510,9 +536,9 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         if (lane == 0) mbar_arrive(hready);
 
         float* const hN = (a.hN && valid) ? a.hN + (long long)grow * kH + 32 * hf : nullptr;
-        const uint32_t gcol = tmem + lane_base + 128 * hf;
         for (int s = 0; s < S; ++s) {
             const uint32_t par = (uint32_t)(s & 1);
+            const uint32_t gcol = tmem + lane_base + 256u * par + 128 * hf;       // gate buffer of this step
             uint4 p_hi = make_uint4(0u, 0u, 0u, 0u), p_lo = p_hi;    // chunk k - 1 as operand rows, stored one chunk late
             mbar_wait(gates + hf, par);
             fence_after();
