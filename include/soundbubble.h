@@ -52,6 +52,8 @@ extern "C" {
                                 /* (cp.async.bulk.tensor), LayerNorm / output warps, one MMA-issuing thread, 8 cell-update */
                                 /* warps, mbarriers instead of block barriers (sb_lstm_tcp.cu; C = 32, projected mode)     */
                                 /* (3 products, fp32 accumulation in TMEM), cell update from TMEM (C = 32, projected mode) */
+#define SB_ALGO_TCQ   10        /* SB_ALGO_TCP with two 128-row tiles per CTA in ping-pong: the cell warps alternate between the tiles  */
+                                /* while the tensor pipe and the stream group prepare the other one (sb_lstm_tcp.cu::lstm_tcq_kernel)  */
 #define SB_ALGO_WS2   8         /* the WS kernel with 2 sequences per CTA sharing the weights in registers, their steps     */
                                 /* interleaved phase by phase: 1.6x the latency, 0.81x the SM-time per sequence             */
 #define SB_ALGO_WS    5         /* 1 sequence per CTA, warp-specialised: 4 recurrence warps (2 units x 4 gates x K/4 per   */

@@ -11,6 +11,7 @@ SB_MAX_MICS = 8
 SB_ALGO_AUTO, SB_ALGO_TILE, SB_ALGO_LANE1, SB_ALGO_LANE2, SB_ALGO_LANE4, SB_ALGO_WS, SB_ALGO_TILE4, SB_ALGO_TC = 0, 1, 2, 3, 4, 5, 6, 7
 SB_ALGO_WS2 = 8
 SB_ALGO_TCP = 9
+SB_ALGO_TCQ = 10
 SB_FEAT_NONE, SB_FEAT_OMNI, SB_FEAT_DIRECTIONAL = 0, 1, 2
 SB_EMB_CONV, SB_EMB_LINEAR = 0, 1
 SB_CONVLSTM_PADCROP, SB_CONVLSTM_OUTPAD = 0, 1

@@ -964,9 +964,10 @@ int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t s
     SB_REQUIRE(H == 64, SB_E_UNSUPP, "LSTM kernels are instantiated for H=64 only (got H=%d)", H);
     SB_REQUIRE(C == 32 || C == 16, SB_E_UNSUPP, "LSTM kernels are instantiated for C in {16, 32} (got C=%d)", C);
     SB_REQUIRE(a.n_rows > 0 && a.n_steps > 0, SB_E_BADARG, "empty LSTM problem (%d rows, %d steps)", a.n_rows, a.n_steps);
-    if (algo == SB_ALGO_TC || algo == SB_ALGO_TCP) {
-        SB_REQUIRE(C == 32 && !raw_h, SB_E_UNSUPP, "SB_ALGO_TC / SB_ALGO_TCP support C=32 in projected mode only");
+    if (algo == SB_ALGO_TC || algo == SB_ALGO_TCP || algo == SB_ALGO_TCQ) {
+        SB_REQUIRE(C == 32 && !raw_h, SB_E_UNSUPP, "SB_ALGO_TC / SB_ALGO_TCP / SB_ALGO_TCQ support C=32 in projected mode only");
         if (algo == SB_ALGO_TCP) return run_seq_tcp(a, st);
+        if (algo == SB_ALGO_TCQ) return run_seq_tcq(a, st);
         return (!tc_v1_enabled() && seq_tcp_supported(a)) ? run_seq_tcp(a, st) : run_seq_tc(a, st);
     }
     if (C == 32) return raw_h ? run_seq_c<32, true>(a, algo, st) : run_seq_c<32, false>(a, algo, st);

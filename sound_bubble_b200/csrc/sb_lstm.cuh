@@ -32,6 +32,8 @@ int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t s
 int run_seq_tc(const SeqArgs& a, cudaStream_t st);
 // warp-specialised tcgen05 + TMA variant (sb_lstm_tcp.cu): same conditions, plus a TMA-addressable activation layout
 int run_seq_tcp(const SeqArgs& a, cudaStream_t st);
+// the same with two 128-row tiles per CTA in ping-pong (cell warps alternate between the tiles)
+int run_seq_tcq(const SeqArgs& a, cudaStream_t st);
 bool seq_tcp_supported(const SeqArgs& a);
 
 }  // namespace sb

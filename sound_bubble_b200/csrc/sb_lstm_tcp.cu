@@ -117,6 +117,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
     asm volatile("trap;");
 }
+// One lane of a CONVERGED warp.  MMA issue sits behind `warp == 1 && elect_one()`, a warp-uniform branch plus an elected lane:
+// behind a per-thread predicate (`tid == 32`) the compiler wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// loop over the active lanes, ~150 cycles per MMA, and MMA ISSUE - not execution - was the serial part of a step.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -396,6 +404,9 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         // TMEM: two gate buffers of 256 columns (step s accumulates into buffer s & 1); the projection of h_{s-1}, issued with
         // step s, lands in columns 0..31 of the OTHER buffer - the one step s - 1 used, which every cell warp has finished
         // reading - and is read back by this group before the x part of step s + 1 overwrites that buffer.
+        // (Dependent MMAs on one accumulator cost ~150 cycles each whatever N is - 12 of them: 0.93 us by globaltimer stamps -
+        // but splitting the three terms over three accumulators that are summed at read-back was slower, 658 vs 635 us per 145
+        // steps: the projection is not on the serial path of this kernel, the extra tcgen05.ld are.)
         auto issue_proj = [&](uint32_t col) {               // proj[128 x 32] = h (k chunks 4..11 of A) . lin^T
             uint32_t acc = 0;
 #pragma unroll
@@ -457,7 +468,7 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
             fence_before();
             bar_sync(1, 128);                               // x part of step s complete, its stage read by all four warps
             if (tid == 0 && s + nslots < S) issue_loads(s + nslots);
-            if (tid == 32) {
+            if (warp == 1 && elect_one()) {
                 if (s == 0) {
                     bulk_wait(wbar, 0);                     // the operand images have landed
                     fence_after();
@@ -486,7 +497,7 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
                 fence_async_smem();
                 fence_before();
                 bar_sync(2, 128);                           // x part of step s + 1 in A; every warp has read the projection
-                if (kPreX && tid == 32) {                   // ... so the other buffer may take the x part of step s + 1 now,
+                if (kPreX && warp == 1 && elect_one()) {    // ... so the other buffer may take the x part of step s + 1 now,
                     fence_after();                          // while the cell warps are still busy with step s
                     for (int q = 0; q < 256 / kGateN; ++q) issue_gates(obuf, q, 0, kXs, true);
                 }
@@ -496,7 +507,7 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         const uint32_t dbuf = 256u - 256u * (uint32_t)(S & 1);
         fence_before();
         bar_sync(1, 128);
-        if (tid == 32) {
+        if (warp == 1 && elect_one()) {
             mbar_wait(hready, (uint32_t)(S & 1));
             fence_after();
             issue_proj(dbuf);
@@ -602,6 +613,474 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
+// =================================================================================================================
+// lstm_tcq_kernel: TWO 128-row tiles per CTA in ping-pong (SB_ALGO_TCQ; chosen for SB_ALGO_TC when a direction has at least
+// two tiles).  In lstm_tcp_kernel a step is [MMAs that need the complete h: 0.8 us] + [handshakes: 0.6 us] + [cell update:
+// 3 us] in series, and the tensor pipe idles while the cell warps work.  Here the eight cell warps alternate between tile A
+// and tile B and never wait: while they update the cells of one tile, the stream group and the tensor pipe prepare the other
+// (projection of the previous h -> output rows, x part of the next step, gate MMAs), all of which fits in one cell phase.
+//
+// What had to give for two tiles to fit one SM:
+//   * shared memory (227 KB): the gate / projection images are shared (104 KB), each tile owns its A operand (2 x 48 KB), and
+//     the TMA ring shrinks to ONE 16 KB stage the tiles take turns on (a build every 3 us leaves the next load ample time);
+//     calls with two addends (the inter-frame path) would need a 32 KB stage and stay on lstm_tcp_kernel;
+//   * TMEM (512 columns): 256 gate columns per tile and no room for the 32 projection columns, so the projection of h_{s-1}
+//     goes into columns 0..31 of the tile's own gate buffer right after the cell warps have released it, the stream group
+//     reads it back, and only then the gate MMAs of the next step overwrite the buffer (no x part ahead of time);
+//   * registers: a cell thread carries c of both tiles (64 registers), so the gate columns are loaded single-buffered; the
+//     stream threads re-read x' for the residual (FiLM / second addend re-applied) instead of holding it across a step.
+// Same arithmetic and operand images as lstm_tcp_kernel<true> (the terms of the split are accumulated pass-major here: results
+// agree to 1e-6, tools/tcp_check.py tcq).  Build index j = 2 * step + tile orders everything the stream group does; every
+// wait is bounded and traps.
+//
+// STATUS (round 2): correct on the B200 (oracle parity 2e-6, state hand-over, tail tiles) but NOT faster - 1 680 us per 145
+// steps for two tiles against 2 x 635 us for lstm_tcp_kernel - so nothing selects it by default (SB_ALGO_TCQ only).  The
+// globaltimer timeline of one CTA (tools/tcq_timeline.py, build with -DSB_TCQ_DEBUG; profiles/r02_tcq_timeline.txt) shows why:
+// the cell phases are 3.0 us as planned, but the lane that issues the tcgen05.mma blocks for as long as the MMAs EXECUTE (the
+// queue is a few instructions deep; 18 gate MMAs: 1.5 us; 12 dependent N = 32 projection MMAs: 0.93 us, ~150 cycles each
+// whatever N is), and that lane lives in the stream group, whose other three warps meet it at the next named barrier: MMA
+// execution is serialised into the stream program (build 1.3 + projection 0.9 + read-back 0.5 + gates 1.5 + stores ~ 5.6 us per
+// tile-step) instead of overlapping the other tile's cells.  What it needs next: a dedicated MMA-issue warp (a 13th warp leaves
+// 152 registers per thread; the cell threads use 168) - i.e. setmaxnreg-balanced warpgroups.
+// =================================================================================================================
+#ifdef SB_TCQ_DEBUG
+__device__ long long g_tcq_dbg[16384];
+__device__ int g_tcq_dbg_n;
+#define TCQ_STAMP(role, ev, X, step)                                                                       \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && (step) < 12 && (threadIdx.x & 31) == 0) {                \
+            long long t_;                                                                                  \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                         \
+            const int i_ = atomicAdd(&g_tcq_dbg_n, 1);                                                     \
+            if (i_ < 4096) { g_tcq_dbg[4 * i_] = t_; g_tcq_dbg[4 * i_ + 1] = (role) * 100 + (ev); g_tcq_dbg[4 * i_ + 2] = (X); g_tcq_dbg[4 * i_ + 3] = (step) * 100 + (threadIdx.x >> 5); } \
+        }                                                                                                  \
+    } while (0)
+#else
+#define TCQ_STAMP(role, ev, X, step) do {} while (0)
+#endif
+
+namespace tcq {
+using namespace tcp;
+constexpr int kStageBytes = kSlabBytes;                    // ONE 16 KB TMA stage the tiles take turns on (single-addend calls only)
+constexpr int kOffW2 = kStageBytes;
+constexpr int kAxBytes = kRows * kC * 2, kAhBytes = kRows * kH * 2;       // one bf16 image of the x part / of the h part of a tile
+constexpr int kOffAx = kOffW2 + 2 * kWBytes + 2 * kPBytes;  // x part: tile 0 hi, lo, tile 1 hi, lo
+constexpr int kOffAh = kOffAx + 4 * kAxBytes;               // h part: tile 0 hi, lo, tile 1 hi, lo
+constexpr int kOffBias2 = kOffAh + 4 * kAhBytes;
+constexpr int kOffLn2 = kOffBias2 + kN * 4;
+constexpr int kOffBar2 = kOffLn2 + 3 * kC * 4;
+constexpr int kSmemBytes2 = kOffBar2 + 256 + 1024;
+struct TileGeo {
+    bool active, tail_tile, valid;
+    int outer0, inner0, grow;
+    long long rbase;
+};
+__device__ __forceinline__ TileGeo tile_geo(const SeqArgs& a, const Geom& g, int tile, int n_tiles, int r) {
+    TileGeo t{};
+    t.active = tile < n_tiles;
+    if (!t.active) return t;
+    t.tail_tile = tile >= g.n_full_tiles;
+    int o_row, i_row;
+    if (!t.tail_tile) {
+        t.outer0 = tile / g.nfull;
+        t.inner0 = (tile - t.outer0 * g.nfull) * kRows;
+        o_row = t.outer0; i_row = t.inner0 + r; t.valid = true;
+    } else {
+        t.outer0 = (tile - g.n_full_tiles) * g.P;
+        t.inner0 = g.nfull * kRows;
+        const int qq = r / g.tail;
+        o_row = t.outer0 + qq; i_row = t.inner0 + (r - qq * g.tail);
+        t.valid = qq < g.P && o_row < g.n_outer;
+    }
+    t.grow = t.valid ? o_row * a.rows_inner + i_row : 0;
+    t.rbase = t.valid ? (long long)o_row * a.stride_outer + (long long)i_row * a.stride_inner : 0;
+    return t;
+}
+// operand rows of the h part: chunk = 0..7 within the tile's own image
+__device__ __forceinline__ void store_pair_h(unsigned char* hi, unsigned char* lo, int row, int chunk, const uint4 hi4, const uint4 lo4) {
+    const int off = ((chunk * (kRows / 8) + (row >> 3)) * 8 + (row & 7)) * 16;
+    sts16(hi + off, hi4);
+    sts16(lo + off, lo4);
+}
+}  // namespace tcq
+
+__global__ void __launch_bounds__(tcp::kThreads, 1)
+lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __grid_constant__ CUtensorMap map_x0,
+                const __grid_constant__ CUtensorMap map_x0_tail, const __grid_constant__ CUtensorMap map_x1,
+                const __grid_constant__ CUtensorMap map_x1_tail) {
+    using namespace tcq;
+    extern __shared__ unsigned char sm_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* stages = sm;
+    unsigned char* w_hi = sm + kOffW2;
+    unsigned char* w_lo = w_hi + kWBytes;
+    unsigned char* p_hi = w_lo + kWBytes;
+    unsigned char* p_lo = p_hi + kPBytes;
+    unsigned char* ax = sm + kOffAx;                        // tile X: hi at ax + 2 X kAxBytes, lo right behind
+    unsigned char* ah = sm + kOffAh;                        // tile X: hi at ah + 2 X kAhBytes, lo right behind
+    float* bias_s = reinterpret_cast<float*>(sm + kOffBias2);
+    float* ln_s = reinterpret_cast<float*>(sm + kOffLn2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kOffBar2);
+    uint64_t* full = bars;                                  // [2] TMA bytes of a stage
+    uint64_t* gbar = bars + 2;                              // [2] tcgen05.commit: gate MMAs of tile X (A's x part free, gates ready)
+    uint64_t* pbar = bars + 4;                              // [2] tcgen05.commit: projection of tile X
+    uint64_t* hready = bars + 6;                            // [2] 8 cell-update warps have published h of tile X
+    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(bars + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const sb_lstm_dir& w = a.w[dir];
+    const int S = a.n_steps;
+    const int q = warp & 3;
+    const int r = 32 * q + lane;
+    constexpr int nld = 1, nst = 1;                         // one addend (the host sends two-addend calls to lstm_tcp_kernel), one stage
+    const TileGeo t0 = tile_geo(a, g, 2 * blockIdx.x, n_tiles, r), t1 = tile_geo(a, g, 2 * blockIdx.x + 1, n_tiles, r);
+    const int nact = t1.active ? 2 : 1;                     // tiles of this CTA; builds are numbered j = nact * step + tile
+
+    for (int i = tid; i < kN; i += kThreads) bias_s[i] = __ldg(w.tc_b + i) * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
+    if (tid < kC) {
+        ln_s[tid] = __ldg(w.ln_g + tid);
+        ln_s[kC + tid] = __ldg(w.ln_b + tid);
+        ln_s[2 * kC + tid] = dir == 0 ? __ldg(w.lin_b + tid) : 0.0f;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(gbar + i, 1);
+            mbar_init(pbar + i, 1);
+            mbar_init(hready + i, 8);
+        }
+        bulk_barrier_init(wbar);
+        bulk_expect(wbar, 2 * kWBytes + 2 * kPBytes);
+        bulk_copy_g2s(reinterpret_cast<float*>(w_hi), w.tc_w, 2 * kWBytes + 2 * kPBytes, wbar);
+    }
+    pdl_trigger();
+    pdl_wait();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+    const int n_builds = nact * S;
+
+    if (warp < 4) {
+        // =============================================================================================================
+        // stream group
+        // =============================================================================================================
+        auto issue_loads = [&](int j) {                     // one thread: the slab(s) of build j -> stage j % nst
+            const int X = j % nact, step = j / nact;
+            const TileGeo& t = X ? t1 : t0;
+            const int pos = dir ? S - 1 - step : step;
+            const int sg = j % nst;
+            unsigned char* dst = stages + (size_t)sg * nld * kSlabBytes;
+            uint64_t* bar = full + sg;
+            const int c1 = g.mode == 0 ? pos : t.inner0, c2 = g.mode == 0 ? t.inner0 : pos;
+            if (!t.tail_tile) {
+                mbar_expect(bar, (uint32_t)(nld * kSlabBytes));
+                tma_load_4d(dst, &map_x0, bar, 0, c1, c2, t.outer0);
+            } else {
+                int nq = g.n_outer - t.outer0;
+                nq = nq < g.P ? nq : g.P;
+                mbar_expect(bar, (uint32_t)(nld * nq * g.tail * kC * 4));
+                for (int qq = 0; qq < nq; ++qq)
+                    tma_load_4d(dst + (size_t)qq * g.tail * kC * 4, &map_x0_tail, bar, 0, c1, c2, t.outer0 + qq);
+            }
+        };
+        if (tid == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x0) : "memory");
+            for (int j = 0; j < nst && j < n_builds; ++j) issue_loads(j);
+        }
+
+        // x' of (tile, position) as the LSTM sees it before the LayerNorm: x0 [+ x1], FiLM
+        auto film_apply = [&](float4 (&xv)[8], const TileGeo& t, int pos) {
+            if (a.film_scale) {
+                const long long film_row = (long long)(t.grow / a.film_row_div) * S * kC;
+                const float4* fs = reinterpret_cast<const float4*>(a.film_scale + film_row + (long long)pos * kC);
+                const float4* fb = reinterpret_cast<const float4*>(a.film_shift + film_row + (long long)pos * kC);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 s4 = __ldg(fs + i), h4 = __ldg(fb + i);
+                    xv[i].x = fmaf(xv[i].x, s4.x, h4.x); xv[i].y = fmaf(xv[i].y, s4.y, h4.y);
+                    xv[i].z = fmaf(xv[i].z, s4.z, h4.z); xv[i].w = fmaf(xv[i].w, s4.w, h4.w);
+                }
+            }
+        };
+        auto build = [&](int j, float4 (&xv)[8]) {          // x part of build j into the shared region; x' returned for the residual
+            const int X = j % nact, step = j / nact;
+            const TileGeo& t = X ? t1 : t0;
+            const int pos = dir ? S - 1 - step : step;
+            const int sg = j % nst;
+            mbar_wait(full + sg, (uint32_t)((j / nst) & 1));
+            const unsigned char* base = stages + (size_t)sg * nld * kSlabBytes + (size_t)r * (kC * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = lds4(base + ((i ^ (r & 7)) << 4));
+            film_apply(xv, t, pos);
+            if (a.film_scale && step + 1 < S) {             // the FiLM rows of this tile's next step: into L1 while nobody waits for them
+                const long long nxt = (long long)(t.grow / a.film_row_div) * S * kC + (long long)(dir ? pos - 1 : pos + 1) * kC;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.film_scale + nxt));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.film_shift + nxt));
+            }
+            unsigned char* ax_hi = ax + 2 * X * kAxBytes;
+            unsigned char* ax_lo = ax_hi + kAxBytes;
+            float s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s1 += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+            const float mean = s1 * (1.0f / kC);
+            float s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dx = xv[i].x - mean, dy = xv[i].y - mean, dz = xv[i].z - mean, dw = xv[i].w - mean;
+                s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+            const float rstd = rsqrtf(s2 * (1.0f / kC) + kLnEps);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 tt = xv[2 * ch + i];
+                    const float4 gg = lds4_ro(ln_s + 4 * (2 * ch + i)), bb = lds4_ro(ln_s + kC + 4 * (2 * ch + i));
+                    v[4 * i + 0] = fmaf((tt.x - mean) * rstd, gg.x, bb.x); v[4 * i + 1] = fmaf((tt.y - mean) * rstd, gg.y, bb.y);
+                    v[4 * i + 2] = fmaf((tt.z - mean) * rstd, gg.z, bb.z); v[4 * i + 3] = fmaf((tt.w - mean) * rstd, gg.w, bb.w);
+                }
+                uint4 hi4, lo4;
+                split8(v, hi4, lo4);
+                store_pair_h(ax_hi, ax_lo, r, ch, hi4, lo4);
+            }
+        };
+
+        const uint32_t ax_s = smem_u32(ax), w_hi_s = smem_u32(w_hi), w_lo_s = smem_u32(w_lo);
+        const uint32_t p_hi_s = smem_u32(p_hi), p_lo_s = smem_u32(p_lo), ah_s = smem_u32(ah);
+        constexpr uint32_t idesc_g = make_idesc(128, 256), idesc_p = make_idesc(128, 32);
+        auto issue_proj = [&](int X) {                      // proj[128 x 32] = h_X . lin^T -> columns 0..31 of tile X's gate buffer
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ab = ah_s + (2 * X + (pass == 2 ? 1 : 0)) * kAhBytes, pb = pass == 1 ? p_lo_s : p_hi_s;
+#pragma unroll
+                for (int ks = 0; ks < kH / 16; ++ks) {
+                    umma(tmem + 256 * X, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
+                         make_desc(pb + 2 * ks * kPChunkBytes, kPChunkBytes, 128), idesc_p, acc);
+                    acc = 1;
+                }
+            }
+        };
+        auto issue_gates = [&](int X) {                     // gates[128 x 256] of tile X = [x part | h] of the tile . W^T, three terms
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t axb = ax_s + (2 * X + (pass == 2 ? 1 : 0)) * kAxBytes, ahb = ah_s + (2 * X + (pass == 2 ? 1 : 0)) * kAhBytes;
+                const uint32_t wb = pass == 1 ? w_lo_s : w_hi_s;
+#pragma unroll
+                for (int ks = 0; ks < kK / 16; ++ks) {
+                    const uint32_t ab = ks < kC / 16 ? axb + 2 * ks * kAChunkBytes : ahb + 2 * (ks - kC / 16) * kAChunkBytes;
+                    umma(tmem + 256 * X, make_desc(ab, kAChunkBytes, 128), make_desc(wb + 2 * ks * kWChunkBytes, kWChunkBytes, 128), idesc_g, acc);
+                    acc = 1;
+                }
+            }
+        };
+        // y of (tile X, step) = lin h [+ b + x']: the projection is read back first (the gate MMAs may then overwrite the
+        // buffer), the rows are stored after the MMAs have been issued
+        auto proj_read = [&](int X, int step, uint32_t (&pr)[32]) {
+            mbar_wait(pbar + X, (uint32_t)(step & 1));      // pbar[X] completes once per emitted step
+            fence_after();
+            tmem_ld32_issue(tmem + lane_base + 256 * X, pr);
+            tmem_wait_ld();
+            pin(pr);
+        };
+        auto emit_store = [&](int X, int step, const uint32_t (&pr)[32], const float4 (&resv)[8]) {
+            const TileGeo& t = X ? t1 : t0;
+            if (!t.valid) return;
+            const int pos = dir ? S - 1 - step : step;
+            float* dst = a.out[dir] + t.rbase + (long long)pos * a.stride_pos;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 o = make_float4(__uint_as_float(pr[4 * i]), __uint_as_float(pr[4 * i + 1]), __uint_as_float(pr[4 * i + 2]),
+                                       __uint_as_float(pr[4 * i + 3]));
+                if (dir == 0) {
+                    const float4 bl = lds4_ro(ln_s + 2 * kC + 4 * i);
+                    o.x += bl.x + resv[i].x; o.y += bl.y + resv[i].y;
+                    o.z += bl.z + resv[i].z; o.w += bl.w + resv[i].w;
+                }
+                st4(dst + 4 * i, o);
+            }
+        };
+
+        // One iteration per build j = (step, tile): the x part first - it does not need h, so it is ready before the cell warps
+        // release the tile -, then, from the moment h arrives: projection of the previous step -> its output rows -> gate MMAs.
+        float4 res[2][8];                                   // x' of the step each tile is working on (residual of its output rows)
+        for (int step = 0; step < S; ++step) {
+#pragma unroll
+            for (int X = 0; X < 2; ++X) {
+                if (X >= nact) continue;
+                const int j = nact * step + X;
+                if (step > 0) {                             // the tile's x part is free once its previous gate MMAs have completed
+                    mbar_wait(gbar + X, (uint32_t)((step - 1) & 1));    // (long ago: the cell warps have worked on them since)
+                    fence_after();
+                }
+                float4 xv[8];
+                TCQ_STAMP(1, 0, X, step);
+                build(j, xv);                               // does not need h: done while the cell warps still work on this tile
+                fence_async_smem();
+                fence_before();
+                bar_sync(1, 128);                           // x part complete, the stage has been read by all four warps
+                TCQ_STAMP(1, 1, X, step);
+                if (tid == 0 && j + nst < n_builds) issue_loads(j + nst);
+                if (warp == 1 && elect_one()) {
+                    if (j == 0) bulk_wait(wbar, 0);
+                    mbar_wait(hready + X, (uint32_t)(step & 1));        // h_{step-1} of tile X is in A, its gate columns have been read
+                    fence_after();
+                    TCQ_STAMP(1, 2, X, step);
+                    if (step > 0) {
+                        issue_proj(X);
+                        umma_commit(pbar + X);
+                    }
+                    TCQ_STAMP(1, 3, X, step);
+                }
+                uint32_t pr[32];
+                if (step > 0) {
+                    proj_read(X, step - 1, pr);
+                    TCQ_STAMP(1, 4, X, step);
+                    fence_before();
+                    bar_sync(2, 128);                       // every warp has read the projection columns
+                }
+                if (warp == 1 && elect_one()) {
+                    fence_after();
+                    issue_gates(X);
+                    umma_commit(gbar + X);
+                    TCQ_STAMP(1, 5, X, step);
+                }
+                __syncwarp();
+                if (step > 0) emit_store(X, step - 1, pr, res[X]);
+                TCQ_STAMP(1, 6, X, step);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) res[X][i] = xv[i];
+            }
+        }
+        // ---- drain: projection of the last step of each tile --------------------------------------------------------
+#pragma unroll
+        for (int X = 0; X < 2; ++X) {
+            if (X >= nact) continue;
+            if (warp == 1 && elect_one()) {
+                mbar_wait(hready + X, (uint32_t)(S & 1));
+                fence_after();
+                issue_proj(X);
+                umma_commit(pbar + X);
+            }
+            __syncwarp();
+            uint32_t pr[32];
+            proj_read(X, S - 1, pr);
+            emit_store(X, S - 1, pr, res[X]);
+        }
+    } else {
+        // =============================================================================================================
+        // cell-update group: thread (row, hf) owns units 32hf + 8k .. + 7 of BOTH tiles (registers c[X][8k + j])
+        // =============================================================================================================
+        const int hf = (warp - 4) >> 2;
+        float c[2][32];
+#pragma unroll
+        for (int X = 0; X < 2; ++X) {
+            const TileGeo& t = X ? t1 : t0;
+            unsigned char* h_hi = ah + 2 * X * kAhBytes;
+            unsigned char* h_lo = h_hi + kAhBytes;
+            if (X < nact) {
+                if (a.h0 && t.valid) {
+                    const float* cp = a.c0 + (long long)t.grow * kH + 32 * hf;
+                    const float* hp = a.h0 + (long long)t.grow * kH + 32 * hf;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {        // plain loads: hN / cN may alias h0 / c0
+                        const float4 c0 = ld_plain4(cp + 8 * ch), c1 = ld_plain4(cp + 8 * ch + 4);
+                        c[X][8 * ch] = c0.x; c[X][8 * ch + 1] = c0.y; c[X][8 * ch + 2] = c0.z; c[X][8 * ch + 3] = c0.w;
+                        c[X][8 * ch + 4] = c1.x; c[X][8 * ch + 5] = c1.y; c[X][8 * ch + 6] = c1.z; c[X][8 * ch + 7] = c1.w;
+                        const float4 v0 = ld_plain4(hp + 8 * ch), v1 = ld_plain4(hp + 8 * ch + 4);
+                        const float h8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                        uint4 hi4, lo4;
+                        split8(h8, hi4, lo4);
+                        store_pair_h(h_hi, h_lo, r, 4 * hf + ch, hi4, lo4);
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) c[X][jj] = 0.0f;
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) store_pair_h(h_hi, h_lo, r, 4 * hf + ch, z4, z4);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(hready + X);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) c[X][jj] = 0.0f;
+            }
+        }
+        for (int s = 0; s < S; ++s) {
+            const uint32_t par = (uint32_t)(s & 1);
+#pragma unroll
+            for (int X = 0; X < 2; ++X) {
+                if (X >= nact) continue;
+                const TileGeo& t = X ? t1 : t0;
+                unsigned char* h_hi = ah + 2 * X * kAhBytes;
+                unsigned char* h_lo = h_hi + kAhBytes;
+                float* const hN = (a.hN && t.valid) ? a.hN + (long long)t.grow * kH + 32 * hf : nullptr;
+                const uint32_t gcol = tmem + lane_base + 256u * X + 128 * hf;
+                TCQ_STAMP(2, 0, X, s);
+                mbar_wait(gbar + X, par);                   // gate MMAs of (X, s) complete: they have also finished reading h_{s-1}
+                fence_after();
+                TCQ_STAMP(2, 1, X, s);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t cur[32];
+                    tmem_ld32_issue(gcol + 32 * ch, cur);
+                    const float* bp = bias_s + 4 * (32 * hf + 8 * ch);
+                    float4 nb_next = lds4_ro(bp);
+                    tmem_wait_ld();
+                    pin(cur);
+                    float h8[8];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const float4 nb = nb_next;
+                        if (jj < 7) nb_next = lds4_ro(bp + 4 * (jj + 1));
+                        h8[jj] = cell7(__uint_as_float(cur[4 * jj + 0]), __uint_as_float(cur[4 * jj + 1]), __uint_as_float(cur[4 * jj + 2]),
+                                       __uint_as_float(cur[4 * jj + 3]), nb, c[X][8 * ch + jj]);
+                    }
+                    if (s == S - 1 && hN) {
+                        st4(hN + 8 * ch, make_float4(h8[0], h8[1], h8[2], h8[3]));
+                        st4(hN + 8 * ch + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
+                    }
+                    uint4 hi4, lo4;
+                    split8(h8, hi4, lo4);
+                    store_pair_h(h_hi, h_lo, r, 4 * hf + ch, hi4, lo4);
+                }
+                fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(hready + X);
+                TCQ_STAMP(2, 2, X, s);
+            }
+        }
+#pragma unroll
+        for (int X = 0; X < 2; ++X) {
+            const TileGeo& t = X ? t1 : t0;
+            if (X < nact && a.cN && t.valid) {
+                float* cp = a.cN + (long long)t.grow * kH + 32 * hf;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    st4(cp + 8 * ch, make_float4(c[X][8 * ch], c[X][8 * ch + 1], c[X][8 * ch + 2], c[X][8 * ch + 3]));
+                    st4(cp + 8 * ch + 4, make_float4(c[X][8 * ch + 4], c[X][8 * ch + 5], c[X][8 * ch + 6], c[X][8 * ch + 7]));
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
 // ---- host: tensor maps ------------------------------------------------------------------------------------------
 namespace tcp {
 
@@ -660,26 +1139,59 @@ bool seq_tcp_supported(const SeqArgs& a) {
     return al && strides && ordered && tcp::encode_fn() != nullptr;
 }
 
-int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
+static int tcp_setup(const SeqArgs& a, tcp::Geom& g, int& n_tiles, CUtensorMap (&m)[4]) {
     using namespace tcp;
     SB_REQUIRE(seq_tcp_supported(a), SB_E_UNSUPP, "SB_ALGO_TCP: activation layout not addressable by a TMA tensor map");
-    Geom g{};
+    g = Geom{};
     g.mode = a.stride_pos < a.stride_inner ? 0 : 1;
     g.n_outer = a.n_rows / a.rows_inner;
     g.nfull = a.rows_inner / kRows;
     g.tail = a.rows_inner % kRows;
     g.P = g.tail ? kRows / g.tail : 1;
     g.n_full_tiles = g.n_outer * g.nfull;
-    const int n_tiles = g.n_full_tiles + (g.tail ? ceil_div(g.n_outer, g.P) : 0);
-    CUtensorMap m0, m0t, m1, m1t;
-    SB_CHECK(make_map(&m0, a.x0, a, g, kRows));
-    SB_CHECK(make_map(&m0t, a.x0, a, g, g.tail ? g.tail : kRows));
-    SB_CHECK(make_map(&m1, a.x1 ? a.x1 : a.x0, a, g, kRows));
-    SB_CHECK(make_map(&m1t, a.x1 ? a.x1 : a.x0, a, g, g.tail ? g.tail : kRows));
+    n_tiles = g.n_full_tiles + (g.tail ? ceil_div(g.n_outer, g.P) : 0);
+    SB_CHECK(make_map(&m[0], a.x0, a, g, kRows));
+    SB_CHECK(make_map(&m[1], a.x0, a, g, g.tail ? g.tail : kRows));
+    SB_CHECK(make_map(&m[2], a.x1 ? a.x1 : a.x0, a, g, kRows));
+    SB_CHECK(make_map(&m[3], a.x1 ? a.x1 : a.x0, a, g, g.tail ? g.tail : kRows));
+    return 0;
+}
+
+int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
+    using namespace tcp;
+    Geom g;
+    int n_tiles;
+    CUtensorMap m[4];
+    SB_CHECK(tcp_setup(a, g, n_tiles, m));
     dim3 grid(n_tiles, a.n_dirs);
     if (tc_cell7_enabled())
-        return launch("lstm_tcp", lstm_tcp_kernel<true>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m0, m0t, m1, m1t);
-    return launch("lstm_tcp", lstm_tcp_kernel<false>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m0, m0t, m1, m1t);
+        return launch("lstm_tcp", lstm_tcp_kernel<true>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m[0], m[1], m[2], m[3]);
+    return launch("lstm_tcp", lstm_tcp_kernel<false>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m[0], m[1], m[2], m[3]);
+}
+
+#ifdef SB_TCQ_DEBUG
+extern "C" int sb_tcq_debug_read(long long* out, int max_events) {
+    int n = 0;
+    cudaMemcpyFromSymbol(&n, g_tcq_dbg_n, sizeof(int));
+    if (n > max_events) n = max_events;
+    if (n > 4096) n = 4096;
+    cudaMemcpyFromSymbol(out, g_tcq_dbg, sizeof(long long) * 4 * n);
+    int zero = 0;
+    cudaMemcpyToSymbol(g_tcq_dbg_n, &zero, sizeof(int));
+    return n;
+}
+#endif
+
+// two tiles per CTA in ping-pong; falls back to one tile per CTA when there is only one
+int run_seq_tcq(const SeqArgs& a, cudaStream_t st) {
+    using namespace tcp;
+    Geom g;
+    int n_tiles;
+    CUtensorMap m[4];
+    SB_CHECK(tcp_setup(a, g, n_tiles, m));
+    if (n_tiles < 2 || a.x1) return run_seq_tcp(a, st);       // one tile, or two addends (no room for a 32 KB stage)
+    dim3 grid(ceil_div(n_tiles, 2), a.n_dirs);
+    return launch("lstm_tcq", lstm_tcq_kernel, grid, dim3(kThreads), (size_t)tcq::kSmemBytes2, st, a, g, n_tiles, m[0], m[1], m[2], m[3]);
 }
 
 #else   // SB_EMU: tensor-core / TMA instructions cannot be emulated on the host
@@ -688,6 +1200,10 @@ bool seq_tcp_supported(const SeqArgs&) { return false; }
 
 int run_seq_tcp(const SeqArgs&, cudaStream_t) {
     set_error("SB_ALGO_TCP (tcgen05 + TMA) is not available in the host-emulated test build");
+    return SB_E_UNSUPP;
+}
+int run_seq_tcq(const SeqArgs&, cudaStream_t) {
+    set_error("SB_ALGO_TCQ (tcgen05 + TMA) is not available in the host-emulated test build");
     return SB_E_UNSUPP;
 }
 

@@ -345,3 +345,13 @@ def test_headline_configuration_against_oracle(mode):
     assert r["rms"] <= 5e-5 and r["rel_rms"] <= 1e-4 and r["rms"] <= pc.RMS_BAR, r
     assert r["worst_second_rms"] <= 1e-4, r
     assert r["si_sdr_vs_oracle_db"] >= 60.0 and r["si_sdr_delta_db"] <= 0.05, r
+
+
+def test_two_tile_ping_pong_kernel_against_oracle(lib):
+    """SB_ALGO_TCQ (lstm_tcq_kernel: two 128-row tiles per CTA, cell warps alternate) is selectable and correct - an odd number
+    of tiles (one CTA runs a single tile), tail tiles, carried state - although nothing selects it by default."""
+    for kw in (dict(B=5, T=64, block=2), dict(B=2, T=5, block=1)):
+        r = kc.check_intra(lib, DEV, "dis_embed", SYN, abi.SB_ALGO_TCQ, **kw)
+        assert all(v <= TOL for v in r.values()), r
+    r = kc.check_inter(lib, DEV, "dis_embed", SYN, abi.SB_ALGO_TCQ, B=9, T=8)
+    assert all(v <= TOL for v in r.values()), r

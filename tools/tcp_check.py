@@ -142,3 +142,36 @@ if which == "cell7":
         nan = bool(torch.isnan(nf).any() or torch.isnan(nb).any() or torch.isnan(ny).any() or torch.isnan(nh).any() or torch.isnan(nc).any())
         print("B=%3d T=%3d scale=%4.0f  intra maxabs %.2e  %8.1f -> %8.1f us   inter maxabs %.2e  %8.1f -> %8.1f us  nan=%s"
               % (B, T, scale, d_intra, t_old, t_new, d_inter, u_old, u_new, nan), flush=True)
+
+if which == "tcq":
+    # two tiles per CTA in ping-pong (SB_ALGO_TCQ): oracle parity, bits against SB_ALGO_TCP, time per launch
+    TCQ = abi.SB_ALGO_TCQ
+    print("inter  T=3  B=1 :", kc.check_inter(lib, "cuda:0", "dis_embed", SYN, TCQ, B=1, T=3), flush=True)
+    print("inter  T=40 B=2 :", kc.check_inter(lib, "cuda:0", "dis_embed", SYN, TCQ, B=2, T=40, alias_state=True), flush=True)
+    print("inter  T=8  B=9 :", kc.check_inter(lib, "cuda:0", "dis_embed", SYN, TCQ, B=9, T=8), flush=True)
+    print("intra  T=5  B=2 :", kc.check_intra(lib, "cuda:0", "dis_embed", SYN, TCQ, B=2, T=5, block=1), flush=True)
+    print("intra  T=300 B=1:", kc.check_intra(lib, "cuda:0", "dis_embed", SYN, TCQ, B=1, T=300, block=0), flush=True)
+    print("intra  T=64 B=5 :", kc.check_intra(lib, "cuda:0", "dis_embed", SYN, TCQ, B=5, T=64, block=2), flush=True)
+    torch.manual_seed(0)
+    net = Net(**SYN).to(dev).eval()
+    pk = net.engine().packed
+    F, C, H = 145, 32, 64
+    for (B, T) in ((32, 8), (32, 32), (7, 100), (32, 125), (32, 625)):
+        g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
+        x = torch.randn(B, T, F, C, generator=g).to(dev)
+        x1 = torch.randn(B, T, F, C, generator=g).to(dev)
+        film = torch.randn(2, B, F, C, generator=g).to(dev)
+        h = (0.3 * torch.randn(B * F, H, generator=g)).to(dev)
+        c = (0.3 * torch.randn(B * F, H, generator=g)).to(dev)
+        rf, rb, f_old = intra_call(pk, x, film, TCP)
+        nf, nb, f_new = intra_call(pk, x, film, TCQ)
+        d = max(float((rf - nf).abs().max()), float((rb - nb).abs().max()))
+        nan = bool(torch.isnan(nf).any() or torch.isnan(nb).any())
+        print("B=%3d T=%3d intra rows=%6d  maxabs(tcq - tcp) = %.3e nan=%s   tcp %9.1f us   tcq %9.1f us"
+              % (B, T, B * T, d, nan, timeit(f_old), timeit(f_new)), flush=True)
+        ry, rh, rc, g_old = inter_call(pk, x, x1, h, c, TCP)
+        ny, nh, nc, g_new = inter_call(pk, x, x1, h, c, TCQ)
+        d = max(float((ry - ny).abs().max()), float((rh - nh).abs().max()), float((rc - nc).abs().max()))
+        nan = bool(torch.isnan(ny).any() or torch.isnan(nh).any() or torch.isnan(nc).any())
+        print("B=%3d T=%3d inter rows=%6d  maxabs(tcq - tcp) = %.3e nan=%s   tcp %9.1f us   tcq %9.1f us"
+              % (B, T, B * F, d, nan, timeit(g_old), timeit(g_new)), flush=True)
