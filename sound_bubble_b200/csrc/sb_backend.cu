@@ -91,6 +91,102 @@ __global__ void __launch_bounds__(256) deconv_spec_kernel(const sb_backend_args 
     }
 }
 
+// The same arithmetic with the input tile in shared memory: CTA = (4 frames + the 2 frames of history, utterance), the
+// TT + 2 rows of x are one contiguous block of HBM (18 560 B per frame) copied with 16-byte loads, after which the nine taps of
+// a position are LDS.128 instead of L2 round trips (the kernel above waits on the long scoreboard for 59 % of its samples,
+// profiles/r02_prof_frontback.txt).  111 KB of shared memory: two CTAs per SM.  Used for calls of more than kIstftTT frames.
+constexpr int kDeconvTT = 4;
+template <int C, int NO>
+__global__ void __launch_bounds__(256, 2) deconv_spec_tile_kernel(const sb_backend_args a) {
+    constexpr int LPP = C / 4, PPB = 256 / LPP;
+    SB_DYN_SMEM(float, in_s);                   // [kDeconvTT + 2][F][C]; frame slot j <-> frame t0 - 2 + j
+    const int tid = threadIdx.x;
+    const int cq = tid % LPP, pslot = tid / LPP;
+    const int b = blockIdx.y, F = a.F, T = a.T;
+    const int t0 = blockIdx.x * kDeconvTT;
+    const int nvalid = min(kDeconvTT, T - t0);
+
+    float w[NO][9][4];
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[o][k][j] = __ldg(a.w + ((size_t)(4 * cq + j) * NO + o) * 9 + k);
+    float bias[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) bias[o] = __ldg(a.bias + o);
+    pdl_trigger();
+    pdl_wait();
+
+    const float* xb = a.x + (size_t)b * T * F * C;
+    const float* hist = a.deconv_buf_in + (size_t)b * C * 2 * F;
+    const int fc4 = F * C / 4;                  // float4 per frame
+    for (int j = 0; j < nvalid + 2; ++j) {
+        const int ft = t0 - 2 + j;
+        float* dst = in_s + (size_t)j * F * C;
+        if (ft >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(xb + (size_t)ft * F * C);
+            for (int i = tid; i < fc4; i += 256) st4(dst + 4 * i, ldg4_stream(reinterpret_cast<const float*>(src + i)));
+        } else {                                // history frame 2 + ft of deconv_buf [C][2][F]: a transposing gather
+            const float* hp = hist + (size_t)(2 + ft) * F;
+            for (int i = tid; i < F * C; i += 256) {
+                const int c = i / F, f = i - c * F;
+                dst[f * C + c] = __ldg(hp + (size_t)c * 2 * F + f);
+            }
+        }
+    }
+    __syncthreads();
+
+    const int n_pos = nvalid * F;
+    for (int base = 0; base < n_pos; base += PPB) {
+        const int pos = base + pslot;
+        const bool valid = pos < n_pos;
+        const int pp = valid ? pos : 0;
+        const int tt = pp / F, f = pp - tt * F;
+        const int t = t0 + tt;
+        float acc[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            const float* fr = in_s + (size_t)(tt + 2 - kt) * F * C;      // frame t - kt sits in slot tt + 2 - kt
+#pragma unroll
+            for (int kf = 0; kf < 3; ++kf) {
+                const int ff = f + 1 - kf;
+                if (ff < 0 || ff >= F) continue;
+                const float4 v = ld4(fr + (size_t)ff * C + 4 * cq);
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    acc[o] = fmaf(v.x, w[o][kt * 3 + kf][0], acc[o]); acc[o] = fmaf(v.y, w[o][kt * 3 + kf][1], acc[o]);
+                    acc[o] = fmaf(v.z, w[o][kt * 3 + kf][2], acc[o]); acc[o] = fmaf(v.w, w[o][kt * 3 + kf][3], acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = group_sum<LPP>(acc[o]) + bias[o];
+        if (valid && cq == 0) {
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {      // channel o -> (source s = o/2, re/im = o%2)   (view :521)
+                const size_t in_frame = (size_t)(o & 1) * F + f;
+                float v = acc[o];
+                if (a.mask_spec) v *= __ldg(a.mask_spec + ((size_t)(b * T + t) * (NO / 2) + (o >> 1)) * 2 * F + in_frame);
+                a.ws[(((size_t)b * (NO / 2) + (o >> 1)) * T + t) * 2 * F + in_frame] = v;      // ws [B][S][T][2F]
+                if (t == T - 1) a.istft_buf_out[((size_t)b * (NO / 2) + (o >> 1)) * 2 * F + (size_t)(o & 1) * F + f] = v;
+            }
+        }
+    }
+
+    if (t0 + nvalid == T) {                     // this CTA holds the last two frames of [history ; x]: new deconv_buf [C][2][F]
+        float* dst = a.deconv_buf_out + (size_t)b * C * 2 * F;
+        for (int i = tid; i < C * 2 * F; i += 256) {
+            const int c = i / (2 * F), r = i - c * 2 * F;
+            const int j = r / F, f = r - j * F;
+            dst[i] = in_s[((size_t)(nvalid + j) * F + f) * C + c];      // frame T - 2 + j sits in slot nvalid + j
+        }
+    }
+}
+
 // wave[t*hop + r] = sum_k spec_t[k] basis[k][r]  +  (r < n_fft-hop) sum_k spec_{t-1}[k] basis[k][hop + r]
 // CTA = (tile of TT frames, (utterance, source)); thread r owns sample r of every frame in the tile (+ the carried
 // one): the basis value basis[k][r] is read once per k (coalesced over r) and reused for TT+1 frames whose spectra are
@@ -129,8 +225,12 @@ __global__ void __launch_bounds__(1024) istft_ola_kernel(const sb_backend_args a
         for (int i = 0; i < NF; ++i) acc[i] = 0.f;
         const float* bp = a.filt + r0;
         const int kper = (F2 + KS - 1) / KS, k0 = grp * kper, k1 = min(F2, k0 + kper);
+        // every CTA reads the same basis rows: start each CTA at a different k so that they do not all queue on the same
+        // L2 lines at the same moment (the kernel waits on these loads for 79 % of its samples, profiles/r02_prof_frontback.txt)
+        const int nk = k1 - k0, rot = nk > 0 ? (int)((blockIdx.x * 13u + blockIdx.y * 29u) % (unsigned)nk) : 0;
 #pragma unroll 16
-        for (int k = k0; k < k1; ++k) {
+        for (int i = 0; i < nk; ++i) {
+            const int k = k0 + (i + rot >= nk ? i + rot - nk : i + rot);
             const float bv = __ldg(bp + (size_t)k * n_fft);
             const float4 s0 = ld4(sp + k * NFP), s1 = ld4(sp + k * NFP + 4);
             const float s8 = sp[k * NFP + 8];
@@ -296,9 +396,18 @@ static int launch_backend(const sb_backend_args& a, cudaStream_t st) {
     const int cap = ceil_div(4 * sm_count(), a.B);
     if (gx > cap) gx = cap;
     dim3 grid(gx, a.B);
+    const size_t smem_t = (size_t)(kDeconvTT + 2) * a.F * C * sizeof(float);
+    const bool tiled = smem_t <= 113 * 1024;    // shared-memory tiles (two CTAs per SM); the direct kernel for wider grids
+    dim3 grid_t(ceil_div(a.T, kDeconvTT), a.B);
     switch (a.n_src) {
-        case 1: SB_CHECK(launch("deconv_spec", deconv_spec_kernel<C, 2>, grid, dim3(256), 0, st, a)); break;
-        case 2: SB_CHECK(launch("deconv_spec", deconv_spec_kernel<C, 4>, grid, dim3(256), 0, st, a)); break;
+        case 1:
+            if (tiled) SB_CHECK(launch("deconv_spec", deconv_spec_tile_kernel<C, 2>, grid_t, dim3(256), smem_t, st, a));
+            else SB_CHECK(launch("deconv_spec", deconv_spec_kernel<C, 2>, grid, dim3(256), 0, st, a));
+            break;
+        case 2:
+            if (tiled) SB_CHECK(launch("deconv_spec", deconv_spec_tile_kernel<C, 4>, grid_t, dim3(256), smem_t, st, a));
+            else SB_CHECK(launch("deconv_spec", deconv_spec_kernel<C, 4>, grid, dim3(256), 0, st, a));
+            break;
         default:
             set_error("sb_backend_fwd: n_src must be 1 or 2 (got %d)", a.n_src);
             return SB_E_UNSUPP;
