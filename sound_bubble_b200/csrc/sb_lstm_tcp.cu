@@ -142,6 +142,18 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void pin16(uint32_t (&r)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(r[i]));
+}
 // keeps the compiler from using registers of an asynchronous tcgen05.ld before the wait that precedes this call
 __device__ __forceinline__ void pin(uint32_t (&r)[32]) {
 #pragma unroll
@@ -633,16 +645,20 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
 // agree to 1e-6, tools/tcp_check.py tcq).  Build index j = 2 * step + tile orders everything the stream group does; every
 // wait is bounded and traps.
 //
-// STATUS (round 2): correct on the B200 (oracle parity 2e-6, state hand-over, tail tiles) but NOT faster - 1 680 us per 145
-// steps for two tiles against 2 x 635 us for lstm_tcp_kernel - so nothing selects it by default (SB_ALGO_TCQ only).  The
-// globaltimer timeline of one CTA (tools/tcq_timeline.py, build with -DSB_TCQ_DEBUG; profiles/r02_tcq_timeline.txt) shows why:
-// the cell phases are 3.0 us as planned, but the lane that issues the tcgen05.mma blocks for as long as the MMAs EXECUTE (the
-// queue is a few instructions deep; 18 gate MMAs: 1.5 us; 12 dependent N = 32 projection MMAs: 0.93 us, ~150 cycles each
-// whatever N is), and that lane lives in the stream group, whose other three warps meet it at the next named barrier: MMA
-// execution is serialised into the stream program (build 1.3 + projection 0.9 + read-back 0.5 + gates 1.5 + stores ~ 5.6 us per
-// tile-step) instead of overlapping the other tile's cells.  What it needs next: a dedicated MMA-issue warp (a 13th warp leaves
-// 152 registers per thread; the cell threads use 168) - i.e. setmaxnreg-balanced warpgroups.
-// =================================================================================================================
+// STATUS (round 2): correct on the B200 (oracle parity 2e-6, state hand-over, odd tile counts, tail tiles; tests/test_gpu_parity.py)
+// but NOT faster than lstm_tcp_kernel, so nothing selects it by default (SB_ALGO_TCQ only).  Measured, us per 145 steps for two
+// tiles (2 x 635 on lstm_tcp_kernel):
+//   1 680  MMA issue by a lane of the stream group.  The globaltimer timeline of one CTA (tools/tcq_timeline.py, build with
+//          -DSB_TCQ_DEBUG; profiles/r02_tcq_timeline.txt) shows the cell phases at 3.0 us as planned, but the issuing lane blocks
+//          for as long as the MMAs EXECUTE (the queue is a few instructions deep; 18 gate MMAs: 1.5 us; 12 dependent N = 32
+//          projection MMAs: 0.93 us, ~150 cycles each whatever N is) and the other stream warps meet it at the next barrier.
+//   1 403  this version: a fourth warpgroup whose one working warp only issues MMAs, stream warps and MMA warp talk through
+//          mbarriers (xready, pbar, pfree, gbar), and setmaxnreg moves the registers to where they are needed (512 threads
+//          compiled for 128 registers; issue warpgroup 40, stream 104, cell 184; each setmaxnreg must be the first statement of
+//          its role branch or ptxas budgets nothing).  Now the four stream warps are the bottleneck: 5.7 us per tile-step
+//          (x part 2.0 us, projection read-back, residual re-read + output rows 2.7 us) against the 3.0 us of a cell phase.
+// What it needs next: the stream work spread over more warps (two threads per row) or the FiLM / residual taken off it.
+//
 #ifdef SB_TCQ_DEBUG
 __device__ long long g_tcq_dbg[16384];
 __device__ int g_tcq_dbg_n;
@@ -670,6 +686,7 @@ constexpr int kOffBias2 = kOffAh + 4 * kAhBytes;
 constexpr int kOffLn2 = kOffBias2 + kN * 4;
 constexpr int kOffBar2 = kOffLn2 + 3 * kC * 4;
 constexpr int kSmemBytes2 = kOffBar2 + 256 + 1024;
+constexpr int kThreads2 = 512;                             // warpgroups: 0 stream (rows), 1-2 cell update, 3 = one MMA-issue warp + 3 idle
 struct TileGeo {
     bool active, tail_tile, valid;
     int outer0, inner0, grow;
@@ -704,7 +721,7 @@ __device__ __forceinline__ void store_pair_h(unsigned char* hi, unsigned char* l
 }
 }  // namespace tcq
 
-__global__ void __launch_bounds__(tcp::kThreads, 1)
+__global__ void __launch_bounds__(tcq::kThreads2, 1)
 lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __grid_constant__ CUtensorMap map_x0,
                 const __grid_constant__ CUtensorMap map_x0_tail, const __grid_constant__ CUtensorMap map_x1,
                 const __grid_constant__ CUtensorMap map_x1_tail) {
@@ -725,8 +742,10 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
     uint64_t* gbar = bars + 2;                              // [2] tcgen05.commit: gate MMAs of tile X (A's x part free, gates ready)
     uint64_t* pbar = bars + 4;                              // [2] tcgen05.commit: projection of tile X
     uint64_t* hready = bars + 6;                            // [2] 8 cell-update warps have published h of tile X
-    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(bars + 8);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* xready = bars + 8;                            // [2] 4 stream warps have written the x part of tile X
+    uint64_t* pfree = bars + 10;                            // [2] 4 stream warps have read the projection columns of tile X
+    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(bars + 12);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
@@ -738,7 +757,7 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
     const TileGeo t0 = tile_geo(a, g, 2 * blockIdx.x, n_tiles, r), t1 = tile_geo(a, g, 2 * blockIdx.x + 1, n_tiles, r);
     const int nact = t1.active ? 2 : 1;                     // tiles of this CTA; builds are numbered j = nact * step + tile
 
-    for (int i = tid; i < kN; i += kThreads) bias_s[i] = __ldg(w.tc_b + i) * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
+    for (int i = tid; i < kN; i += kThreads2) bias_s[i] = __ldg(w.tc_b + i) * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
     if (tid < kC) {
         ln_s[tid] = __ldg(w.ln_g + tid);
         ln_s[kC + tid] = __ldg(w.ln_b + tid);
@@ -754,6 +773,8 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
             mbar_init(gbar + i, 1);
             mbar_init(pbar + i, 1);
             mbar_init(hready + i, 8);
+            mbar_init(xready + i, 4);
+            mbar_init(pfree + i, 4);
         }
         bulk_barrier_init(wbar);
         bulk_expect(wbar, 2 * kWBytes + 2 * kPBytes);
@@ -768,10 +789,82 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
     const uint32_t lane_base = (uint32_t)(32 * q) << 16;
     const int n_builds = nact * S;
 
-    if (warp < 4) {
+    // Register budgets (setmaxnreg, warpgroup-wide): the kernel is compiled for 128 registers per thread (512 threads); the
+    // fourth warpgroup gives its registers up (its one working warp only issues MMAs), the two cell warpgroups take them.
+    // (each setmaxnreg is the first statement of its role branch: ptxas budgets the code a setmaxnreg dominates)
+
+    if (warp >= 12) {
+        // =============================================================================================================
+        // MMA issue: one lane of warp 12; it may block for as long as the tensor pipe is busy without holding anybody else up
+        // =============================================================================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 12 && elect_one()) {
+            // The shared-memory base is made opaque HERE so that the compiler cannot hoist the descriptor arithmetic of this
+            // region above the role branch, where it would stay live through the stream and cell regions (it did: 3.7 KB of spills).
+            uint32_t sm_base = smem_u32(sm);
+            asm volatile("" : "+r"(sm_base));
+            const uint32_t ax_s = sm_base + kOffAx, w_hi_s = sm_base + kOffW2, w_lo_s = w_hi_s + kWBytes;
+            const uint32_t p_hi_s = w_lo_s + kWBytes, p_lo_s = p_hi_s + kPBytes, ah_s = sm_base + kOffAh;
+            constexpr uint32_t idesc_g = make_idesc(128, 256), idesc_p = make_idesc(128, 32);
+            // rolled loops: this warpgroup runs on a small register budget, the descriptors are computed as they are needed
+            auto issue_proj = [&](int X) {                  // proj[128 x 32] = h_X . lin^T -> columns 0..31 of tile X's gate buffer
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ab = ah_s + (2 * X + (pass == 2 ? 1 : 0)) * kAhBytes, pb = pass == 1 ? p_lo_s : p_hi_s;
+#pragma unroll 1
+                    for (int ks = 0; ks < kH / 16; ++ks) {
+                        umma(tmem + 256 * X, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
+                             make_desc(pb + 2 * ks * kPChunkBytes, kPChunkBytes, 128), idesc_p, acc);
+                        acc = 1;
+                    }
+                }
+            };
+            auto issue_gates = [&](int X) {                 // gates[128 x 256] of tile X = [x part | h] of the tile . W^T, three terms
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t axb = ax_s + (2 * X + (pass == 2 ? 1 : 0)) * kAxBytes, ahb = ah_s + (2 * X + (pass == 2 ? 1 : 0)) * kAhBytes;
+                    const uint32_t wb = pass == 1 ? w_lo_s : w_hi_s;
+#pragma unroll 1
+                    for (int ks = 0; ks < kK / 16; ++ks) {
+                        const uint32_t ab = ks < kC / 16 ? axb + 2 * ks * kAChunkBytes : ahb + 2 * (ks - kC / 16) * kAChunkBytes;
+                        umma(tmem + 256 * X, make_desc(ab, kAChunkBytes, 128), make_desc(wb + 2 * ks * kWChunkBytes, kWChunkBytes, 128), idesc_g, acc);
+                        acc = 1;
+                    }
+                }
+            };
+            bulk_wait(wbar, 0);                             // the operand images have landed
+#pragma unroll 1
+            for (int step = 0; step <= S; ++step) {
+#pragma unroll 1
+                for (int X = 0; X < nact; ++X) {
+                    TCQ_STAMP(3, 0, X, step);
+                    mbar_wait(hready + X, (uint32_t)(step & 1));        // h_{step-1} of tile X is in A, its gate columns have been read
+                    fence_after();
+                    TCQ_STAMP(3, 1, X, step);
+                    if (step > 0) {
+                        issue_proj(X);
+                        umma_commit(pbar + X);
+                    }
+                    TCQ_STAMP(3, 2, X, step);
+                    if (step == S) continue;                // drain: only the projection of the last step
+                    mbar_wait(xready + X, (uint32_t)(step & 1));        // the x part of (X, step) is in A
+                    if (step > 0) mbar_wait(pfree + X, (uint32_t)((step - 1) & 1));     // the projection columns have been read back
+                    fence_after();
+                    TCQ_STAMP(3, 3, X, step);
+                    issue_gates(X);
+                    umma_commit(gbar + X);
+                    TCQ_STAMP(3, 4, X, step);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 4) {
         // =============================================================================================================
         // stream group
         // =============================================================================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
         auto issue_loads = [&](int j) {                     // one thread: the slab(s) of build j -> stage j % nst
             const int X = j % nact, step = j / nact;
             const TileGeo& t = X ? t1 : t0;
@@ -854,36 +947,6 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
             }
         };
 
-        const uint32_t ax_s = smem_u32(ax), w_hi_s = smem_u32(w_hi), w_lo_s = smem_u32(w_lo);
-        const uint32_t p_hi_s = smem_u32(p_hi), p_lo_s = smem_u32(p_lo), ah_s = smem_u32(ah);
-        constexpr uint32_t idesc_g = make_idesc(128, 256), idesc_p = make_idesc(128, 32);
-        auto issue_proj = [&](int X) {                      // proj[128 x 32] = h_X . lin^T -> columns 0..31 of tile X's gate buffer
-            uint32_t acc = 0;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t ab = ah_s + (2 * X + (pass == 2 ? 1 : 0)) * kAhBytes, pb = pass == 1 ? p_lo_s : p_hi_s;
-#pragma unroll
-                for (int ks = 0; ks < kH / 16; ++ks) {
-                    umma(tmem + 256 * X, make_desc(ab + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
-                         make_desc(pb + 2 * ks * kPChunkBytes, kPChunkBytes, 128), idesc_p, acc);
-                    acc = 1;
-                }
-            }
-        };
-        auto issue_gates = [&](int X) {                     // gates[128 x 256] of tile X = [x part | h] of the tile . W^T, three terms
-            uint32_t acc = 0;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t axb = ax_s + (2 * X + (pass == 2 ? 1 : 0)) * kAxBytes, ahb = ah_s + (2 * X + (pass == 2 ? 1 : 0)) * kAhBytes;
-                const uint32_t wb = pass == 1 ? w_lo_s : w_hi_s;
-#pragma unroll
-                for (int ks = 0; ks < kK / 16; ++ks) {
-                    const uint32_t ab = ks < kC / 16 ? axb + 2 * ks * kAChunkBytes : ahb + 2 * (ks - kC / 16) * kAChunkBytes;
-                    umma(tmem + 256 * X, make_desc(ab, kAChunkBytes, 128), make_desc(wb + 2 * ks * kWChunkBytes, kWChunkBytes, 128), idesc_g, acc);
-                    acc = 1;
-                }
-            }
-        };
         // y of (tile X, step) = lin h [+ b + x']: the projection is read back first (the gate MMAs may then overwrite the
         // buffer), the rows are stored after the MMAs have been issued
         auto proj_read = [&](int X, int step, uint32_t (&pr)[32]) {
@@ -893,10 +956,22 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
             tmem_wait_ld();
             pin(pr);
         };
-        auto emit_store = [&](int X, int step, const uint32_t (&pr)[32], const float4 (&resv)[8]) {
+        // the rows are stored after the projection columns have been handed back; x' for the residual is re-read (and FiLM
+        // re-applied) here, off the path that the MMA warp and the cell warps wait on
+        // the rows are stored after the projection columns have been handed back; x' for the residual is re-read (and FiLM
+        // re-applied) here, off the path that the MMA warp and the cell warps wait on.  (Requesting the row before the wait for
+        // the projection was slower: 1 529 vs 1 403 us.)
+        auto emit_store = [&](int X, int step, const uint32_t (&pr)[32]) {
             const TileGeo& t = X ? t1 : t0;
             if (!t.valid) return;
             const int pos = dir ? S - 1 - step : step;
+            float4 xv[8];
+            if (dir == 0) {
+                const float* src = a.x0 + t.rbase + (long long)pos * a.stride_pos;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xv[i] = ld_plain4(src + 4 * i);
+                film_apply(xv, t, pos);
+            }
             float* dst = a.out[dir] + t.rbase + (long long)pos * a.stride_pos;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -904,83 +979,58 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
                                        __uint_as_float(pr[4 * i + 3]));
                 if (dir == 0) {
                     const float4 bl = lds4_ro(ln_s + 2 * kC + 4 * i);
-                    o.x += bl.x + resv[i].x; o.y += bl.y + resv[i].y;
-                    o.z += bl.z + resv[i].z; o.w += bl.w + resv[i].w;
+                    o.x += bl.x + xv[i].x; o.y += bl.y + xv[i].y;
+                    o.z += bl.z + xv[i].z; o.w += bl.w + xv[i].w;
                 }
                 st4(dst + 4 * i, o);
             }
         };
 
-        // One iteration per build j = (step, tile): the x part first - it does not need h, so it is ready before the cell warps
-        // release the tile -, then, from the moment h arrives: projection of the previous step -> its output rows -> gate MMAs.
-        float4 res[2][8];                                   // x' of the step each tile is working on (residual of its output rows)
+        // One iteration per build j = (step, tile): x part -> hand it to the MMA warp -> read the projection of the previous step
+        // back -> hand the columns back -> store the output rows.  Nothing here waits for MMAs other than that projection.
         for (int step = 0; step < S; ++step) {
 #pragma unroll
             for (int X = 0; X < 2; ++X) {
                 if (X >= nact) continue;
                 const int j = nact * step + X;
                 if (step > 0) {                             // the tile's x part is free once its previous gate MMAs have completed
-                    mbar_wait(gbar + X, (uint32_t)((step - 1) & 1));    // (long ago: the cell warps have worked on them since)
+                    mbar_wait(gbar + X, (uint32_t)((step - 1) & 1));
                     fence_after();
                 }
                 float4 xv[8];
                 TCQ_STAMP(1, 0, X, step);
-                build(j, xv);                               // does not need h: done while the cell warps still work on this tile
+                build(j, xv);
                 fence_async_smem();
-                fence_before();
-                bar_sync(1, 128);                           // x part complete, the stage has been read by all four warps
-                TCQ_STAMP(1, 1, X, step);
-                if (tid == 0 && j + nst < n_builds) issue_loads(j + nst);
-                if (warp == 1 && elect_one()) {
-                    if (j == 0) bulk_wait(wbar, 0);
-                    mbar_wait(hready + X, (uint32_t)(step & 1));        // h_{step-1} of tile X is in A, its gate columns have been read
-                    fence_after();
-                    TCQ_STAMP(1, 2, X, step);
-                    if (step > 0) {
-                        issue_proj(X);
-                        umma_commit(pbar + X);
-                    }
-                    TCQ_STAMP(1, 3, X, step);
-                }
-                uint32_t pr[32];
-                if (step > 0) {
-                    proj_read(X, step - 1, pr);
-                    TCQ_STAMP(1, 4, X, step);
-                    fence_before();
-                    bar_sync(2, 128);                       // every warp has read the projection columns
-                }
-                if (warp == 1 && elect_one()) {
-                    fence_after();
-                    issue_gates(X);
-                    umma_commit(gbar + X);
-                    TCQ_STAMP(1, 5, X, step);
-                }
                 __syncwarp();
-                if (step > 0) emit_store(X, step - 1, pr, res[X]);
-                TCQ_STAMP(1, 6, X, step);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) res[X][i] = xv[i];
+                if (lane == 0) mbar_arrive(xready + X);
+                TCQ_STAMP(1, 1, X, step);
+                bar_sync(1, 128);                           // the stage has been read by all four warps
+                if (tid == 0 && j + nst < n_builds) issue_loads(j + nst);
+                if (step > 0) {
+                    uint32_t pr[32];
+                    proj_read(X, step - 1, pr);
+                    fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pfree + X);
+                    TCQ_STAMP(1, 4, X, step);
+                    emit_store(X, step - 1, pr);
+                    TCQ_STAMP(1, 6, X, step);
+                }
             }
         }
         // ---- drain: projection of the last step of each tile --------------------------------------------------------
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
             if (X >= nact) continue;
-            if (warp == 1 && elect_one()) {
-                mbar_wait(hready + X, (uint32_t)(S & 1));
-                fence_after();
-                issue_proj(X);
-                umma_commit(pbar + X);
-            }
-            __syncwarp();
             uint32_t pr[32];
             proj_read(X, S - 1, pr);
-            emit_store(X, S - 1, pr, res[X]);
+            emit_store(X, S - 1, pr);
         }
-    } else {
+    } else if (warp < 12) {
         // =============================================================================================================
         // cell-update group: thread (row, hf) owns units 32hf + 8k .. + 7 of BOTH tiles (registers c[X][8k + j])
         // =============================================================================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
         const int hf = (warp - 4) >> 2;
         float c[2][32];
 #pragma unroll
@@ -1034,19 +1084,22 @@ lstm_tcq_kernel(const SeqArgs a, const tcp::Geom g, const int n_tiles, const __g
                 TCQ_STAMP(2, 1, X, s);
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t cur[32];
-                    tmem_ld32_issue(gcol + 32 * ch, cur);
-                    const float* bp = bias_s + 4 * (32 * hf + 8 * ch);
-                    float4 nb_next = lds4_ro(bp);
-                    tmem_wait_ld();
-                    pin(cur);
                     float h8[8];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const float4 nb = nb_next;
-                        if (jj < 7) nb_next = lds4_ro(bp + 4 * (jj + 1));
-                        h8[jj] = cell7(__uint_as_float(cur[4 * jj + 0]), __uint_as_float(cur[4 * jj + 1]), __uint_as_float(cur[4 * jj + 2]),
-                                       __uint_as_float(cur[4 * jj + 3]), nb, c[X][8 * ch + jj]);
+                    for (int hh = 0; hh < 2; ++hh) {        // 4 units = 16 gate columns at a time: the thread also carries c of both tiles
+                        uint32_t cur[16];
+                        tmem_ld16_issue(gcol + 32 * ch + 16 * hh, cur);
+                        const float* bp = bias_s + 4 * (32 * hf + 8 * ch + 4 * hh);
+                        float4 nb_next = lds4_ro(bp);
+                        tmem_wait_ld();
+                        pin16(cur);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const float4 nb = nb_next;
+                            if (jj < 3) nb_next = lds4_ro(bp + 4 * (jj + 1));
+                            h8[4 * hh + jj] = cell7(__uint_as_float(cur[4 * jj + 0]), __uint_as_float(cur[4 * jj + 1]), __uint_as_float(cur[4 * jj + 2]),
+                                                    __uint_as_float(cur[4 * jj + 3]), nb, c[X][8 * ch + 4 * hh + jj]);
+                        }
                     }
                     if (s == S - 1 && hN) {
                         st4(hN + 8 * ch, make_float4(h8[0], h8[1], h8[2], h8[3]));
@@ -1191,7 +1244,7 @@ int run_seq_tcq(const SeqArgs& a, cudaStream_t st) {
     SB_CHECK(tcp_setup(a, g, n_tiles, m));
     if (n_tiles < 2 || a.x1) return run_seq_tcp(a, st);       // one tile, or two addends (no room for a 32 KB stage)
     dim3 grid(ceil_div(n_tiles, 2), a.n_dirs);
-    return launch("lstm_tcq", lstm_tcq_kernel, grid, dim3(kThreads), (size_t)tcq::kSmemBytes2, st, a, g, n_tiles, m[0], m[1], m[2], m[3]);
+    return launch("lstm_tcq", lstm_tcq_kernel, grid, dim3(tcq::kThreads2), (size_t)tcq::kSmemBytes2, st, a, g, n_tiles, m[0], m[1], m[2], m[3]);
 }
 
 #else   // SB_EMU: tensor-core / TMA instructions cannot be emulated on the host

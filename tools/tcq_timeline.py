@@ -29,10 +29,12 @@ for rep in range(2):
 ev = sorted((buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]) for i in range(n))
 t0 = ev[0][0]
 names = {100: "S build.begin", 101: "S build.done", 102: "S hready.seen", 103: "S proj.issued", 104: "S proj.read", 105: "S gates.issued", 106: "S iter.end",
-         200: "C wait.begin", 201: "C gates.seen", 202: "C cell.done"}
+         200: "C wait.begin", 201: "C gates.seen", 202: "C cell.done",
+         300: "M wait.h", 301: "M h.seen", 302: "M proj.issued", 303: "M gates.begin", 304: "M gates.issued"}
 for t, code, X, sw in ev:
     step, warp = sw // 100, sw % 100
     if step < 2 or step > 6: continue
     if code // 100 == 1 and warp not in (0, 1): continue
     if code // 100 == 2 and warp not in (4, 8): continue
+    if code // 100 == 3 and warp != 12: continue
     print("%8.2f us  %-16s tile %d step %d warp %d" % ((t - t0) / 1e3, names.get(code, code), X, step, warp))
