@@ -86,6 +86,8 @@ extern "C" {
                                 /* the kernel is bound by the XU pipe).  Default set from the measured A/B, see DESIGN.md section 4.  */
 #define SB_OPT_TRAIN_TC 7       /* 1 (default) = LSTM weight gradients (dW_ih, dW_hh, db) of the C = 32 paths as a tcgen05 reduction GEMM */
                                 /* with bf16 hi/lo three-term operands (sb_train_tc.cu); 0 = the fp32 SIMT outer_kernel                 */
+#define SB_OPT_TC_PIPE 8        /* single-addend calls of SB_ALGO_TC run lstm_tcr_kernel: the h part of step s + 1 is issued chunk by   */
+                                /* chunk while the cell update of step s is still running (default 1)                                   */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

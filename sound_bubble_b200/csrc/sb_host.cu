@@ -19,6 +19,7 @@ static std::atomic<int> g_train_ffma2{1};
 static std::atomic<int> g_tc_v1{0};
 static std::atomic<int> g_tc_cell7{1};
 static std::atomic<int> g_train_tc{1};
+static std::atomic<int> g_tc_pipe{1};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -43,6 +44,7 @@ bool train_ffma2_enabled() { return g_train_ffma2.load(std::memory_order_relaxed
 bool tc_v1_enabled() { return g_tc_v1.load(std::memory_order_relaxed) != 0; }
 bool tc_cell7_enabled() { return g_tc_cell7.load(std::memory_order_relaxed) != 0; }
 bool train_tc_enabled() { return g_train_tc.load(std::memory_order_relaxed) != 0; }
+bool tc_pipe_enabled() { return g_tc_pipe.load(std::memory_order_relaxed) != 0; }
 
 int sm_count() {
     static thread_local int dev_cached = -1, sms = 0;
@@ -99,6 +101,10 @@ extern "C" int sb_set_option(int option, int value) {
     }
     if (option == SB_OPT_TRAIN_FFMA2) {
         sb::g_train_ffma2.store(value ? 1 : 0);
+        return 0;
+    }
+    if (option == SB_OPT_TC_PIPE) {
+        sb::g_tc_pipe.store(value ? 1 : 0);
         return 0;
     }
     if (option == SB_OPT_TRAIN_TC) {

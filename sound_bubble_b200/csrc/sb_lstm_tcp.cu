@@ -38,6 +38,7 @@
 #ifndef SB_EMU
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstring>
 #include <mutex>
 #endif
 
@@ -211,6 +212,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // LSTM cell with shared reciprocals.  With e_x = 2^(-x log2 e):  sigmoid(x) = 1 / (1 + e_x),  tanh(x) = (1 - e_2x) / (1 + e_2x), so
 //   f     = (1 + e_i)(1 + e_2g) / D,   i * tanh(g) = (1 + e_f)(1 - e_2g) / D,   D = (1 + e_i)(1 + e_f)(1 + e_2g)
@@ -626,6 +635,430 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
 }
 
 // =================================================================================================================
+// lstm_tcr_kernel: lstm_tcp_kernel with the recurrence pipelined at the granularity of one k step (single-addend calls:
+// the intra-frame LSTMs, 78 % of the headline's SM time).
+//
+// In lstm_tcp_kernel a step is a chain  [12 h-part MMAs, ~1.0 us] -> [cell update of 64 units, ~3.0 us] -> handshake.  But k step
+// j of the h part only reads units 16j .. 16j + 15 of h, so here
+//   * a cell thread (row, half) works through its units in the order 16k + 8 half + (0..7), k = 0..3, and publishes every
+//     chunk at once: after chunk k of both halves the 16 units of k step k are in A (mbarrier hk[k], 8 warps);
+//   * a 13th warp only issues MMAs: it waits for hk[k] and issues the three MMAs (hi.hi, hi.lo, lo.hi) of gate k step k of
+//     step s + 1 into the OTHER gate buffer, plus the three of projection k step k of h_s into columns 0..31 of the buffer
+//     the cell warps are reading (free as soon as hk[0] says chunk 0 = columns 0..63 has been loaded).  Only the three gate
+//     MMAs of k step 3 remain between the end of a cell update and the start of the next;
+//   * the stream warps keep x' (input + FiLM, the residual of direction 0) in the TMA stage it came from instead of in
+//     registers, prepare the bf16 images of step s + 2 in registers while step s runs, and at the start of a step only
+//     read the projection back, write the output rows and store the prepared images, so the x part of the next step is
+//     in TMEM long before its h part arrives.
+// The accumulation order of a gate differs from lstm_tcp_kernel (k-step-major instead of term-major), so results agree
+// with it to rounding (1e-6), not bitwise.
+// =================================================================================================================
+// globaltimer stamps of one CTA's roles (debug builds only, -DSB_TCQ_DEBUG; tools/tcq_timeline.py)
+#ifdef SB_TCQ_DEBUG
+// one slot per (step < 8, warp < 16, event < 32), written with plain stores: an atomic counter would stall the stamping lane for
+// a global round trip (~0.5 us) and distort the very chain that is being looked at
+__device__ long long g_tcq_dbg[16384];
+#define TCQ_STAMP(role, ev, X, step)                                                                       \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && blockIdx.y == 0 && (step) >= 0 && (step) < 8 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 16) { \
+            long long t_;                                                                                  \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                         \
+            const int i_ = (((step) * 16 + (threadIdx.x >> 5)) * 32 + (ev));                               \
+            g_tcq_dbg[4 * i_] = t_; g_tcq_dbg[4 * i_ + 1] = (role) * 100 + (ev); g_tcq_dbg[4 * i_ + 2] = (X); g_tcq_dbg[4 * i_ + 3] = (step) * 100 + (threadIdx.x >> 5); \
+        }                                                                                                  \
+    } while (0)
+#else
+#define TCQ_STAMP(role, ev, X, step) do {} while (0)
+#endif
+
+namespace tcr {
+constexpr int kThreadsR = 416;                              // 4 stream warps, 8 cell-update warps, 1 MMA-issue warp
+}
+
+__global__ void __launch_bounds__(tcr::kThreadsR, 1)
+lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUtensorMap map_x0,
+                const __grid_constant__ CUtensorMap map_x0_tail, const __grid_constant__ CUtensorMap map_o0,
+                const __grid_constant__ CUtensorMap map_o0_tail, const __grid_constant__ CUtensorMap map_o1,
+                const __grid_constant__ CUtensorMap map_o1_tail) {
+    using namespace tcp;
+    extern __shared__ unsigned char sm_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* slabs = sm;
+    unsigned char* w_hi = sm + kOffW;
+    unsigned char* w_lo = w_hi + kWBytes;
+    unsigned char* p_hi = w_lo + kWBytes;
+    unsigned char* p_lo = p_hi + kPBytes;
+    unsigned char* a_hi = sm + kOffA;
+    unsigned char* a_lo = a_hi + kABytes;
+    float* bias_s = reinterpret_cast<float*>(sm + kOffBias);
+    float* ln_s = reinterpret_cast<float*>(sm + kOffLn);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kOffBar);
+    uint64_t* full = bars;                                  // [kSlabs]  TMA bytes of a step's stage
+    uint64_t* gates = bars + kSlabs;                        //           tcgen05.commit: the gates of a step (and every MMA before them)
+    uint64_t* pdone = bars + kSlabs + 1;                    //           tcgen05.commit: the projection of a step's h
+    uint64_t* hk = bars + kSlabs + 2;                       // [4]       8 cell warps have published units 16k .. 16k + 15 of h
+    uint64_t* xready = bars + kSlabs + 6;                   //           stream group: projection read back, next x part in A
+    BulkBarrier* wbar = reinterpret_cast<BulkBarrier*>(bars + kSlabs + 7);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kSlabs + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const sb_lstm_dir& w = a.w[dir];
+    const int S = a.n_steps;
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+    const int r = 32 * q + lane;                            // tile row of this thread
+
+    const int tile = blockIdx.x;
+    const bool tail_tile = tile >= g.n_full_tiles;
+    int outer0, inner0, o_row, i_row;
+    bool valid;
+    if (!tail_tile) {
+        outer0 = tile / g.nfull;
+        inner0 = (tile - outer0 * g.nfull) * kRows;
+        o_row = outer0; i_row = inner0 + r; valid = true;
+    } else {
+        outer0 = (tile - g.n_full_tiles) * g.P;
+        inner0 = g.nfull * kRows;
+        const int qq = r / g.tail;
+        o_row = outer0 + qq; i_row = inner0 + (r - qq * g.tail);
+        valid = qq < g.P && o_row < g.n_outer;
+    }
+    const int grow = valid ? o_row * a.rows_inner + i_row : 0;
+    const long long rbase = valid ? (long long)o_row * a.stride_outer + (long long)i_row * a.stride_inner : 0;
+
+    for (int i = tid; i < kN; i += tcr::kThreadsR)          // bias folded into the exponent argument, see cell7
+        bias_s[i] = __ldg(w.tc_b + i) * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
+    if (tid < kC) {
+        ln_s[tid] = __ldg(w.ln_g + tid);
+        ln_s[kC + tid] = __ldg(w.ln_b + tid);
+        ln_s[2 * kC + tid] = dir == 0 ? __ldg(w.lin_b + tid) : 0.0f;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < kSlabs; ++i) mbar_init(full + i, 1);
+        mbar_init(gates, 1);
+        mbar_init(pdone, 1);
+        for (int k = 0; k < 4; ++k) mbar_init(hk + k, 8);
+        mbar_init(xready, 1);
+        bulk_barrier_init(wbar);
+        bulk_expect(wbar, 2 * kWBytes + 2 * kPBytes);
+        bulk_copy_g2s(reinterpret_cast<float*>(w_hi), w.tc_w, 2 * kWBytes + 2 * kPBytes, wbar);
+    }
+    pdl_trigger();
+    pdl_wait();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+
+    if (warp < 4) {
+        // =============================================================================================================
+        // stream group: TMA producer, LayerNorm / operand builder, output writer
+        // =============================================================================================================
+        auto issue_loads = [&](int step) {                  // one thread
+            const int pos = dir ? S - 1 - step : step;
+            unsigned char* dst = slabs + (size_t)(step % kSlabs) * kSlabBytes;
+            uint64_t* bar = full + step % kSlabs;
+            const int c1 = g.mode == 0 ? pos : inner0, c2 = g.mode == 0 ? inner0 : pos;
+            if (!tail_tile) {
+                mbar_expect(bar, (uint32_t)kSlabBytes);
+                tma_load_4d(dst, &map_x0, bar, 0, c1, c2, outer0);
+            } else {
+                int nq = g.n_outer - outer0;
+                nq = nq < g.P ? nq : g.P;
+                mbar_expect(bar, (uint32_t)(nq * g.tail * kC * 4));
+                for (int qq = 0; qq < nq; ++qq) tma_load_4d(dst + (size_t)qq * g.tail * kC * 4, &map_x0_tail, bar, 0, c1, c2, outer0 + qq);
+            }
+        };
+        if (tid == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x0) : "memory");
+            const int n0 = S < kSlabs ? S : kSlabs;
+            for (int j = 0; j < n0; ++j) issue_loads(j);
+        }
+        const long long film_row = (long long)(grow / a.film_row_div) * S * kC;
+        const int swz = r & 7;                              // 128-byte swizzle: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+
+        // the row of step `step` out of its stage, FiLM on the way; x' goes BACK into the stage (direction 0 adds it to the
+        // output one step after the step has run); LayerNorm; bf16 hi / lo of the four k chunks stay in registers
+        uint4 xh[4], xl[4];
+        auto prepare = [&](int step) {
+            const int pos = dir ? S - 1 - step : step;
+            const int slot = step % kSlabs;
+            mbar_wait(full + slot, (uint32_t)((step / kSlabs) & 1));
+            unsigned char* base = slabs + (size_t)slot * kSlabBytes + (size_t)r * (kC * 4);
+            float4 xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xv[i] = lds4(base + ((i ^ swz) << 4));
+            if (a.film_scale) {
+                const float4* fs = reinterpret_cast<const float4*>(a.film_scale + film_row + (long long)pos * kC);
+                const float4* fb = reinterpret_cast<const float4*>(a.film_shift + film_row + (long long)pos * kC);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 s4 = __ldg(fs + i), h4 = __ldg(fb + i);
+                    xv[i].x = fmaf(xv[i].x, s4.x, h4.x); xv[i].y = fmaf(xv[i].y, s4.y, h4.y);
+                    xv[i].z = fmaf(xv[i].z, s4.z, h4.z); xv[i].w = fmaf(xv[i].w, s4.w, h4.w);
+                }
+                if (dir == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        sts16(base + ((i ^ swz) << 4), make_uint4(__float_as_uint(xv[i].x), __float_as_uint(xv[i].y),
+                                                                  __float_as_uint(xv[i].z), __float_as_uint(xv[i].w)));
+                }
+            }
+            float s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s1 += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+            const float mean = s1 * (1.0f / kC);
+            float s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float dx = xv[i].x - mean, dy = xv[i].y - mean, dz = xv[i].z - mean, dw = xv[i].w - mean;
+                s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+            const float rstd = rsqrtf(s2 * (1.0f / kC) + kLnEps);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 t = xv[2 * ch + i];
+                    const float4 gg = lds4_ro(ln_s + 4 * (2 * ch + i)), bb = lds4_ro(ln_s + kC + 4 * (2 * ch + i));
+                    v[4 * i + 0] = fmaf((t.x - mean) * rstd, gg.x, bb.x); v[4 * i + 1] = fmaf((t.y - mean) * rstd, gg.y, bb.y);
+                    v[4 * i + 2] = fmaf((t.z - mean) * rstd, gg.z, bb.z); v[4 * i + 3] = fmaf((t.w - mean) * rstd, gg.w, bb.w);
+                }
+                split8(v, xh[ch], xl[ch]);
+            }
+        };
+        auto publish = [&]() {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) store_pair(a_hi, a_lo, r, ch, xh[ch], xl[ch]);
+        };
+        // y_step = lin h_step [+ b + x'_step] goes into the stage x'_step sits in (same swizzled position, own row) and leaves
+        // as ONE TMA tensor store per step: written from registers, the rows of a warp are 32 different 128-byte lines per
+        // st.global.v4 - 1024 L1 wavefronts per step that the cell warps' LDS / STS / tcgen05.ld queued behind (globaltimer
+        // timeline: a chunk of the cell update took 1.1 us while these stores were in flight, 0.62 us otherwise)
+        auto emit = [&](int step, uint32_t col) {
+            uint32_t pr[32];
+            tmem_ld32_issue(tmem + lane_base + col, pr);
+            tmem_wait_ld();
+            pin(pr);
+            unsigned char* base = slabs + (size_t)(step % kSlabs) * kSlabBytes + (size_t)r * (kC * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 o = make_float4(__uint_as_float(pr[4 * i]), __uint_as_float(pr[4 * i + 1]), __uint_as_float(pr[4 * i + 2]),
+                                       __uint_as_float(pr[4 * i + 3]));
+                if (dir == 0) {
+                    const float4 bl = lds4_ro(ln_s + 2 * kC + 4 * i), xr = lds4(base + ((i ^ swz) << 4));
+                    o.x += bl.x + xr.x; o.y += bl.y + xr.y;
+                    o.z += bl.z + xr.z; o.w += bl.w + xr.w;
+                }
+                sts16(base + ((i ^ swz) << 4), make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w)));
+            }
+        };
+        auto store_out = [&](int step) {                     // one thread, after the barrier that follows emit(step)
+            const int pos = dir ? S - 1 - step : step;
+            const unsigned char* src = slabs + (size_t)(step % kSlabs) * kSlabBytes;
+            const int c1 = g.mode == 0 ? pos : inner0, c2 = g.mode == 0 ? inner0 : pos;
+            if (!tail_tile) {
+                tma_store_4d(dir ? &map_o1 : &map_o0, src, 0, c1, c2, outer0);
+            } else {
+                int nq = g.n_outer - outer0;
+                nq = nq < g.P ? nq : g.P;
+                for (int qq = 0; qq < nq; ++qq)
+                    tma_store_4d(dir ? &map_o1_tail : &map_o0_tail, src + (size_t)qq * g.tail * kC * 4, 0, c1, c2, outer0 + qq);
+            }
+            tma_store_commit();
+        };
+
+        prepare(0);
+        publish();
+        fence_async_smem();
+        bar_sync(1, 128);
+        if (tid == 0) mbar_arrive(xready);                  // phase 0: x_0 is in A
+        if (S > 1) prepare(1);
+        for (int i = 0; i < S; ++i) {
+            // gates(i) complete = the x-part MMAs of step i have read A; pdone(i - 1) is committed after gates(i)
+            TCQ_STAMP(4, 0, 0, i);
+            if (i == 0) mbar_wait(gates, 0u);
+            else mbar_wait(pdone, (uint32_t)((i - 1) & 1));
+            fence_after();
+            TCQ_STAMP(4, 1, 0, i);
+            if (i > 0) emit(i - 1, 256u * (uint32_t)((i - 1) & 1));
+            TCQ_STAMP(4, 2, 0, i);
+            if (i + 1 < S) publish();
+            fence_async_smem();
+            fence_before();
+            bar_sync(1, 128);                               // every row: y_{i-1} in its stage, x_{i+1} in A
+            if (tid == 0) {
+                mbar_arrive(xready);                        // phase i + 1
+                if (i > 0) store_out(i - 1);
+            }
+            TCQ_STAMP(4, 3, 0, i);
+            if (i + 2 < S) prepare(i + 2);
+            if (tid == 0 && i > 0) {
+                tma_store_wait_read();                      // the stage of step i - 1 has been read by the store: it takes step i + 3
+                if (i + 3 < S) issue_loads(i + 3);
+            }
+            TCQ_STAMP(4, 4, 0, i);
+        }
+        mbar_wait(pdone, (uint32_t)((S - 1) & 1));
+        fence_after();
+        emit(S - 1, 256u * (uint32_t)((S - 1) & 1));
+        fence_async_smem();
+        bar_sync(1, 128);
+        if (tid == 0) {
+            store_out(S - 1);
+            tma_store_wait_read();
+        }
+    } else if (warp == 12) {
+        // =============================================================================================================
+        // MMA issue: iteration i (while the cell warps update step i) builds the gates of step i + 1 and the projection of h_i
+        // =============================================================================================================
+        if (elect_one()) {
+            const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), w_hi_s = smem_u32(w_hi), w_lo_s = smem_u32(w_lo);
+            const uint32_t p_hi_s = smem_u32(p_hi), p_lo_s = smem_u32(p_lo);
+            constexpr uint32_t idesc_g = make_idesc(128, 256), idesc_p = make_idesc(128, 32);
+            bulk_wait(wbar, 0);                             // the operand images have landed
+            fence_after();
+            for (int i = -1; i < S; ++i) {
+                const uint32_t par = (uint32_t)((i + 1) & 1);
+                const uint32_t nbuf = tmem + 256u * par, pbuf = tmem + 256u - 256u * par;       // buffer of step i + 1 / of step i
+                const bool more = i + 1 < S;
+                mbar_wait(xready, par);                     // x_{i+1} in A; projection of h_{i-1} read out of nbuf
+                fence_after();
+                TCQ_STAMP(6, 0, 0, i + 1);
+                if (more) {
+#pragma unroll
+                    for (int ks = 0; ks < kC / 16; ++ks)
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass)
+                            umma(nbuf, make_desc((pass == 2 ? a_lo_s : a_hi_s) + 2 * ks * kAChunkBytes, kAChunkBytes, 128),
+                                 make_desc((pass == 1 ? w_lo_s : w_hi_s) + 2 * ks * kWChunkBytes, kWChunkBytes, 128), idesc_g,
+                                 (ks | pass) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k == 0) TCQ_STAMP(6, 1, 0, i + 1);
+                    mbar_wait(hk + k, par);                 // units 16k .. 16k + 15 of h_i (i = -1: the initial state) are in A
+                    fence_after();
+                    TCQ_STAMP(6, 10 + k, 0, i + 1);
+                    if (more) {
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass)
+                            umma(nbuf, make_desc((pass == 2 ? a_lo_s : a_hi_s) + (4 + 2 * k) * kAChunkBytes, kAChunkBytes, 128),
+                                 make_desc((pass == 1 ? w_lo_s : w_hi_s) + (4 + 2 * k) * kWChunkBytes, kWChunkBytes, 128), idesc_g, 1u);
+                        if (k == 3) umma_commit(gates);
+                    }
+                    if (i >= 0) {
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass)
+                            umma(pbuf, make_desc((pass == 2 ? a_lo_s : a_hi_s) + (4 + 2 * k) * kAChunkBytes, kAChunkBytes, 128),
+                                 make_desc((pass == 1 ? p_lo_s : p_hi_s) + 2 * k * kPChunkBytes, kPChunkBytes, 128), idesc_p,
+                                 (k | pass) ? 1u : 0u);
+                    }
+                }
+                if (i >= 0) umma_commit(pdone);
+                TCQ_STAMP(6, 30, 0, i + 1);
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================================================================================================
+        // cell-update group: thread (row, half), chunk k = units 16k + 8 half .. + 7 (register c[8k + j])
+        // =============================================================================================================
+        const int half = (warp - 4) >> 2;
+        float c[32];
+        if (a.h0 && valid) {
+            const float* cp = a.c0 + (long long)grow * kH + 8 * half;
+            const float* hp = a.h0 + (long long)grow * kH + 8 * half;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {                // plain loads: hN / cN may alias h0 / c0
+                const float4 c0 = ld_plain4(cp + 16 * ch), c1 = ld_plain4(cp + 16 * ch + 4);
+                c[8 * ch] = c0.x; c[8 * ch + 1] = c0.y; c[8 * ch + 2] = c0.z; c[8 * ch + 3] = c0.w;
+                c[8 * ch + 4] = c1.x; c[8 * ch + 5] = c1.y; c[8 * ch + 6] = c1.z; c[8 * ch + 7] = c1.w;
+                const float4 v0 = ld_plain4(hp + 16 * ch), v1 = ld_plain4(hp + 16 * ch + 4);
+                const float h8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                store_split8(a_hi, a_lo, r, 4 + 2 * ch + half, h8);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c[j] = 0.0f;
+            const float h8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) store_split8(a_hi, a_lo, r, 4 + 2 * ch + half, h8);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0)
+            for (int k = 0; k < 4; ++k) mbar_arrive(hk + k);
+
+        float* const hN = (a.hN && valid) ? a.hN + (long long)grow * kH + 8 * half : nullptr;
+        for (int s = 0; s < S; ++s) {
+            const uint32_t par = (uint32_t)(s & 1);
+            const uint32_t gcol = tmem + lane_base + 256u * par + 32u * half;     // chunk k: 32 columns at + 64 k
+            uint32_t ga[32], gb[32];
+            mbar_wait(gates, par);
+            fence_after();
+            TCQ_STAMP(5, 0, 0, s);
+            tmem_ld32_issue(gcol, ga);
+            tmem_wait_ld();
+            pin(ga);
+            TCQ_STAMP(5, 10, 0, s);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t (&cur)[32] = (ch & 1) ? gb : ga;
+                uint32_t (&nxt)[32] = (ch & 1) ? ga : gb;
+                if (ch < 3) tmem_ld32_issue(gcol + 64 * (ch + 1), nxt);
+                const float* bp = bias_s + 4 * (16 * ch + 8 * half);
+                float4 nb_next = lds4_ro(bp);
+                float h8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 nb = nb_next;
+                    if (j < 7) nb_next = lds4_ro(bp + 4 * (j + 1));
+                    h8[j] = cell7(__uint_as_float(cur[4 * j + 0]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
+                                  __uint_as_float(cur[4 * j + 3]), nb, c[8 * ch + j]);
+                }
+                if (s == S - 1 && hN) {
+                    st4(hN + 16 * ch, make_float4(h8[0], h8[1], h8[2], h8[3]));
+                    st4(hN + 16 * ch + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
+                }
+                // the last projection k step of h_{s-1} reads k chunks 10, 11 of A (every other reader of h_{s-1} is older than
+                // gates(s)); it was issued right after the gates of this step, 3 us ago
+                TCQ_STAMP(5, 11 + 3 * ch, 0, s);
+                if (ch == 3 && s > 0) mbar_wait(pdone, (uint32_t)((s - 1) & 1));
+                store_split8(a_hi, a_lo, r, 4 + 2 * ch + half, h8);
+                TCQ_STAMP(5, 12 + 3 * ch, 0, s);
+                if (ch < 3) {
+                    tmem_wait_ld();
+                    pin(nxt);
+                }
+                fence_before();
+                fence_async_smem();
+                __syncwarp();
+                TCQ_STAMP(5, 1 + ch, 0, s);
+                if (lane == 0) mbar_arrive(hk + ch);        // 16 more units of h_s in A; the columns of chunks <= ch have been read
+            }
+        }
+        if (a.cN && valid) {
+            float* cp = a.cN + (long long)grow * kH + 8 * half;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                st4(cp + 16 * ch, make_float4(c[8 * ch], c[8 * ch + 1], c[8 * ch + 2], c[8 * ch + 3]));
+                st4(cp + 16 * ch + 4, make_float4(c[8 * ch + 4], c[8 * ch + 5], c[8 * ch + 6], c[8 * ch + 7]));
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+// =================================================================================================================
 // lstm_tcq_kernel: TWO 128-row tiles per CTA in ping-pong (SB_ALGO_TCQ; chosen for SB_ALGO_TC when a direction has at least
 // two tiles).  In lstm_tcp_kernel a step is [MMAs that need the complete h: 0.8 us] + [handshakes: 0.6 us] + [cell update:
 // 3 us] in series, and the tensor pipe idles while the cell warps work.  Here the eight cell warps alternate between tile A
@@ -659,21 +1092,6 @@ lstm_tcp_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
 //          (x part 2.0 us, projection read-back, residual re-read + output rows 2.7 us) against the 3.0 us of a cell phase.
 // What it needs next: the stream work spread over more warps (two threads per row) or the FiLM / residual taken off it.
 //
-#ifdef SB_TCQ_DEBUG
-__device__ long long g_tcq_dbg[16384];
-__device__ int g_tcq_dbg_n;
-#define TCQ_STAMP(role, ev, X, step)                                                                       \
-    do {                                                                                                   \
-        if (blockIdx.x == 0 && blockIdx.y == 0 && (step) < 12 && (threadIdx.x & 31) == 0) {                \
-            long long t_;                                                                                  \
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                         \
-            const int i_ = atomicAdd(&g_tcq_dbg_n, 1);                                                     \
-            if (i_ < 4096) { g_tcq_dbg[4 * i_] = t_; g_tcq_dbg[4 * i_ + 1] = (role) * 100 + (ev); g_tcq_dbg[4 * i_ + 2] = (X); g_tcq_dbg[4 * i_ + 3] = (step) * 100 + (threadIdx.x >> 5); } \
-        }                                                                                                  \
-    } while (0)
-#else
-#define TCQ_STAMP(role, ev, X, step) do {} while (0)
-#endif
 
 namespace tcq {
 using namespace tcp;
@@ -1210,6 +1628,12 @@ static int tcp_setup(const SeqArgs& a, tcp::Geom& g, int& n_tiles, CUtensorMap (
     return 0;
 }
 
+static bool tcr_outputs_ok(const SeqArgs& a) {
+    for (int d = 0; d < a.n_dirs; ++d)
+        if (!a.out[d] || ((uintptr_t)a.out[d] & 15)) return false;
+    return true;
+}
+
 int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
     using namespace tcp;
     Geom g;
@@ -1217,6 +1641,15 @@ int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
     CUtensorMap m[4];
     SB_CHECK(tcp_setup(a, g, n_tiles, m));
     dim3 grid(n_tiles, a.n_dirs);
+    if (!a.x1 && tc_cell7_enabled() && tc_pipe_enabled() && tcr_outputs_ok(a)) {
+        CUtensorMap mo[4];                                  // the outputs leave through TMA tensor stores: same geometry as x0
+        for (int d = 0; d < 2; ++d) {
+            float* base = a.out[d < a.n_dirs ? d : 0];
+            SB_CHECK(make_map(&mo[2 * d], base, a, g, kRows));
+            SB_CHECK(make_map(&mo[2 * d + 1], base, a, g, g.tail ? g.tail : kRows));
+        }
+        return launch("lstm_tcr", lstm_tcr_kernel, grid, dim3(tcr::kThreadsR), (size_t)kSmemBytes, st, a, g, m[0], m[1], mo[0], mo[1], mo[2], mo[3]);
+    }
     if (tc_cell7_enabled())
         return launch("lstm_tcp", lstm_tcp_kernel<true>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m[0], m[1], m[2], m[3]);
     return launch("lstm_tcp", lstm_tcp_kernel<false>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m[0], m[1], m[2], m[3]);
@@ -1224,13 +1657,16 @@ int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
 
 #ifdef SB_TCQ_DEBUG
 extern "C" int sb_tcq_debug_read(long long* out, int max_events) {
+    static long long host[16384];
+    cudaMemcpyFromSymbol(host, g_tcq_dbg, sizeof(host));
     int n = 0;
-    cudaMemcpyFromSymbol(&n, g_tcq_dbg_n, sizeof(int));
-    if (n > max_events) n = max_events;
-    if (n > 4096) n = 4096;
-    cudaMemcpyFromSymbol(out, g_tcq_dbg, sizeof(long long) * 4 * n);
-    int zero = 0;
-    cudaMemcpyToSymbol(g_tcq_dbg_n, &zero, sizeof(int));
+    for (int i = 0; i < 4096 && n < max_events; ++i)
+        if (host[4 * i]) {
+            for (int j = 0; j < 4; ++j) out[4 * n + j] = host[4 * i + j];
+            ++n;
+        }
+    std::memset(host, 0, sizeof(host));
+    cudaMemcpyToSymbol(g_tcq_dbg, host, sizeof(host));
     return n;
 }
 #endif

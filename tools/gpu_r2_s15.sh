@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python tools/tcp_check.py cell7 > gpurun_out/r02_tcp_n256.txt 2>&1; cat gpurun_out/r02_tcp_n256.txt | tail -6
-timeout 300 python tools/tcp_check.py parity > gpurun_out/r02_tcp_parity_n256.txt 2>&1; tail -8 gpurun_out/r02_tcp_parity_n256.txt
+timeout 120 python tools/tcp_check.py pipe > gpurun_out/r02_tcp_pipe.txt 2>&1; tail -8 gpurun_out/r02_tcp_pipe.txt
+timeout 150 python tools/tcp_check.py parity > gpurun_out/r02_tcp_parity_pipe.txt 2>&1; tail -8 gpurun_out/r02_tcp_parity_pipe.txt
