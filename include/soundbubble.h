@@ -180,6 +180,10 @@ int sb_film_params_fwd(const sb_film_args* a, void* stream);
 /*   x [B][T][F][C] -> y_fwd, y_bwd [B][T][F][C] with  y_fwd + y_bwd = intra_linear(BiLSTM(LN(x'))) + x',        */
 /*   x' = x*film_scale + film_shift (film_* NULL for block 0 / the OPT variant).  The two directions are written */
 /*   by different CTAs to different buffers; the consumer (sb_inter_lstm_fwd) adds them while loading.           */
+/*   SUM MODE, y_bwd == y_fwd: the call zeroes the buffer and both directions add their rows into it (TMA reduce  */
+/*   stores, the sum of two addends onto zero is order-independent), so the consumer reads ONE operand.  Only the */
+/*   pipelined tensor-core kernel implements it: sb_intra_sum_supported() says whether this call would run; a    */
+/*   call it answers 0 for fails with SB_E_UNSUPP.                                                                */
 /* ---------------------------------------------------------------------------------------------------------- */
 typedef struct sb_intra_args {
     const float* x;
@@ -192,6 +196,7 @@ typedef struct sb_intra_args {
     int algo;
 } sb_intra_args;
 int sb_intra_lstm_fwd(const sb_intra_args* a, void* stream);
+int sb_intra_sum_supported(const sb_intra_args* a);     /* 1 / 0, no launch */
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* a8 (apply) + a9': the conv-LSTM intra branch (DE3:800-815, OPT:684-697, 494-510):                             */

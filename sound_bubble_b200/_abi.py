@@ -210,6 +210,7 @@ PROTOTYPES = {
     "sb_conv_in_fwd": (C.c_int, [C.POINTER(ConvInArgs), C.c_void_p]),
     "sb_film_params_fwd": (C.c_int, [C.POINTER(FilmArgs), C.c_void_p]),
     "sb_intra_lstm_fwd": (C.c_int, [C.POINTER(IntraArgs), C.c_void_p]),
+    "sb_intra_sum_supported": (C.c_int, [C.POINTER(IntraArgs)]),
     "sb_intra_convlstm_fwd": (C.c_int, [C.POINTER(IntraConvArgs), C.c_void_p]),
     "sb_inter_lstm_fwd": (C.c_int, [C.POINTER(InterArgs), C.c_void_p]),
     "sb_attn_workspace_floats": (C.c_size_t, [C.c_int] * 7),

@@ -960,7 +960,22 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
     return SB_E_BADARG;
 }
 
+// SeqArgs::sum_dirs is implemented by lstm_tcr_kernel alone: would this call end up there?
+static bool seq_sum_supported(const SeqArgs& a, int C, int H, bool raw_h, int algo) {
+#ifdef SB_EMU
+    (void)a; (void)C; (void)H; (void)raw_h; (void)algo;
+    return false;
+#else
+    if (C != 32 || H != 64 || raw_h || a.n_rows <= 0 || a.n_steps <= 0) return false;
+    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sm_count(), true);
+    if (algo == SB_ALGO_TCP) return seq_tcr_selected(a);
+    return algo == SB_ALGO_TC && !tc_v1_enabled() && seq_tcr_selected(a);
+#endif
+}
+
 int run_seq(const SeqArgs& a, int C, int H, bool raw_h, int algo, cudaStream_t st) {
+    SB_REQUIRE(!a.sum_dirs || seq_sum_supported(a, C, H, raw_h, algo), SB_E_UNSUPP,
+               "summed directions (y_bwd == y_fwd) need the pipelined tensor-core LSTM kernel, which this call does not select");
     SB_REQUIRE(H == 64, SB_E_UNSUPP, "LSTM kernels are instantiated for H=64 only (got H=%d)", H);
     SB_REQUIRE(C == 32 || C == 16, SB_E_UNSUPP, "LSTM kernels are instantiated for C in {16, 32} (got C=%d)", C);
     SB_REQUIRE(a.n_rows > 0 && a.n_steps > 0, SB_E_BADARG, "empty LSTM problem (%d rows, %d steps)", a.n_rows, a.n_steps);
@@ -990,7 +1005,30 @@ extern "C" int sb_intra_lstm_fwd(const sb_intra_args* p, void* stream) {
     a.rows_inner = a.n_rows;                               // row (b,t) -> row * F * C
     a.stride_outer = 0; a.stride_inner = (long long)p->F * p->C; a.stride_pos = p->C;
     a.film_row_div = p->T;                                 // film[b][f][c]
+    a.sum_dirs = p->y_bwd == p->y_fwd;
+    if (a.sum_dirs) {
+        SB_REQUIRE(seq_sum_supported(a, p->C, p->H, false, p->algo), SB_E_UNSUPP,
+                   "sb_intra_lstm_fwd: y_bwd == y_fwd (summed directions) is not available for this call, see sb_intra_sum_supported");
+#ifndef SB_EMU
+        const cudaError_t e = cudaMemsetAsync(p->y_fwd, 0, (size_t)a.n_rows * p->F * p->C * sizeof(float), (cudaStream_t)stream);
+        SB_REQUIRE(e == cudaSuccess, (int)e, "sb_intra_lstm_fwd: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+#endif
+    }
     return run_seq(a, p->C, p->H, false, p->algo, (cudaStream_t)stream);
+}
+
+extern "C" int sb_intra_sum_supported(const sb_intra_args* p) {
+    using namespace sb;
+    if (!p || !p->x || !p->y_fwd || p->B <= 0 || p->T <= 0 || p->F <= 0) return 0;
+    SeqArgs a{};
+    a.x0 = p->x;
+    a.out[0] = p->y_fwd; a.out[1] = p->y_fwd;
+    a.n_rows = p->B * p->T; a.n_steps = p->F; a.n_dirs = 2;
+    a.rows_inner = a.n_rows;
+    a.stride_outer = 0; a.stride_inner = (long long)p->F * p->C; a.stride_pos = p->C;
+    a.film_row_div = p->T;
+    a.sum_dirs = 1;
+    return seq_sum_supported(a, p->C, p->H, false, p->algo) ? 1 : 0;
 }
 
 extern "C" int sb_inter_lstm_fwd(const sb_inter_args* p, void* stream) {

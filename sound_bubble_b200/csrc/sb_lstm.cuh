@@ -19,6 +19,7 @@ struct SeqArgs {
     int rows_inner;             // row -> (row / rows_inner, row % rows_inner)
     long long stride_outer, stride_inner, stride_pos;      // in floats
     int film_row_div;
+    int sum_dirs;               // both directions ADD their result into out[0] (zeroed by the caller): lstm_tcr_kernel only
 };
 
 __device__ __forceinline__ long long row_base(const SeqArgs& a, int row) {
@@ -35,5 +36,7 @@ int run_seq_tcp(const SeqArgs& a, cudaStream_t st);
 // the same with two 128-row tiles per CTA in ping-pong (cell warps alternate between the tiles)
 int run_seq_tcq(const SeqArgs& a, cudaStream_t st);
 bool seq_tcp_supported(const SeqArgs& a);
+// would run_seq_tcp take lstm_tcr_kernel for this call (the only kernel that implements SeqArgs::sum_dirs)?
+bool seq_tcr_selected(const SeqArgs& a);
 
 }  // namespace sb

@@ -218,6 +218,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
@@ -863,13 +868,17 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
             const int pos = dir ? S - 1 - step : step;
             const unsigned char* src = slabs + (size_t)(step % kSlabs) * kSlabBytes;
             const int c1 = g.mode == 0 ? pos : inner0, c2 = g.mode == 0 ? inner0 : pos;
-            if (!tail_tile) {
-                tma_store_4d(dir ? &map_o1 : &map_o0, src, 0, c1, c2, outer0);
-            } else {
-                int nq = g.n_outer - outer0;
+            // SeqArgs::sum_dirs: both directions ADD into the (zeroed) buffer of direction 0 - 0 + a + b does not depend on the order
+            const CUtensorMap* mo = tail_tile ? ((dir && !a.sum_dirs) ? &map_o1_tail : &map_o0_tail) : ((dir && !a.sum_dirs) ? &map_o1 : &map_o0);
+            int nq = 1;
+            if (tail_tile) {
+                nq = g.n_outer - outer0;
                 nq = nq < g.P ? nq : g.P;
-                for (int qq = 0; qq < nq; ++qq)
-                    tma_store_4d(dir ? &map_o1_tail : &map_o0_tail, src + (size_t)qq * g.tail * kC * 4, 0, c1, c2, outer0 + qq);
+            }
+            const size_t box_bytes = tail_tile ? (size_t)g.tail * kC * 4 : 0;
+            for (int qq = 0; qq < nq; ++qq) {
+                if (a.sum_dirs) tma_reduce_add_4d(mo, src + qq * box_bytes, 0, c1, c2, outer0 + qq);
+                else tma_store_4d(mo, src + qq * box_bytes, 0, c1, c2, outer0 + qq);
             }
             tma_store_commit();
         };
@@ -1005,44 +1014,56 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
             fence_after();
             TCQ_STAMP(5, 0, 0, s);
             tmem_ld32_issue(gcol, ga);
+            float4 nb_next = lds4_ro(bias_s + 4 * (8 * half));
             tmem_wait_ld();
             pin(ga);
             TCQ_STAMP(5, 10, 0, s);
+            // One straight line of 32 cells.  The asynchronous pieces are placed so that no chunk boundary drains the MUFU
+            // pipeline: the columns of chunk k + 1 are requested at the top of chunk k and waited for in its middle, the first
+            // bias of chunk k + 1 is loaded before chunk k is stored, the fence + arrive of chunk k sit in the middle of k + 1.
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t (&cur)[32] = (ch & 1) ? gb : ga;
                 uint32_t (&nxt)[32] = (ch & 1) ? ga : gb;
                 if (ch < 3) tmem_ld32_issue(gcol + 64 * (ch + 1), nxt);
                 const float* bp = bias_s + 4 * (16 * ch + 8 * half);
-                float4 nb_next = lds4_ro(bp);
                 float h8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 nb = nb_next;
                     if (j < 7) nb_next = lds4_ro(bp + 4 * (j + 1));
+                    else if (ch < 3) nb_next = lds4_ro(bp + 4 * 16);
                     h8[j] = cell7(__uint_as_float(cur[4 * j + 0]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
                                   __uint_as_float(cur[4 * j + 3]), nb, c[8 * ch + j]);
+                    if (j == 3 && ch > 0) {
+                        // chunk ch - 1 was stored before this chunk began (only hk[3] is on the serial path of a step)
+                        fence_before();
+                        fence_async_smem();
+                        __syncwarp();
+                        TCQ_STAMP(5, ch, 0, s);
+                        if (lane == 0) mbar_arrive(hk + ch - 1);
+                    }
+                    if (j == 4 && ch < 3) {
+                        tmem_wait_ld();
+                        pin(nxt);
+                    }
                 }
                 if (s == S - 1 && hN) {
                     st4(hN + 16 * ch, make_float4(h8[0], h8[1], h8[2], h8[3]));
                     st4(hN + 16 * ch + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
                 }
+                TCQ_STAMP(5, 11 + 3 * ch, 0, s);
                 // the last projection k step of h_{s-1} reads k chunks 10, 11 of A (every other reader of h_{s-1} is older than
                 // gates(s)); it was issued right after the gates of this step, 3 us ago
-                TCQ_STAMP(5, 11 + 3 * ch, 0, s);
                 if (ch == 3 && s > 0) mbar_wait(pdone, (uint32_t)((s - 1) & 1));
                 store_split8(a_hi, a_lo, r, 4 + 2 * ch + half, h8);
                 TCQ_STAMP(5, 12 + 3 * ch, 0, s);
-                if (ch < 3) {
-                    tmem_wait_ld();
-                    pin(nxt);
-                }
-                fence_before();
-                fence_async_smem();
-                __syncwarp();
-                TCQ_STAMP(5, 1 + ch, 0, s);
-                if (lane == 0) mbar_arrive(hk + ch);        // 16 more units of h_s in A; the columns of chunks <= ch have been read
             }
+            fence_before();
+            fence_async_smem();
+            __syncwarp();
+            TCQ_STAMP(5, 4, 0, s);
+            if (lane == 0) mbar_arrive(hk + 3);             // all of h_s is in A, every gate column of the step has been read
         }
         if (a.cN && valid) {
             float* cp = a.cN + (long long)grow * kH + 8 * half;
@@ -1634,6 +1655,10 @@ static bool tcr_outputs_ok(const SeqArgs& a) {
     return true;
 }
 
+bool seq_tcr_selected(const SeqArgs& a) {
+    return seq_tcp_supported(a) && !a.x1 && tc_cell7_enabled() && tc_pipe_enabled() && tcr_outputs_ok(a);
+}
+
 int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
     using namespace tcp;
     Geom g;
@@ -1641,7 +1666,8 @@ int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
     CUtensorMap m[4];
     SB_CHECK(tcp_setup(a, g, n_tiles, m));
     dim3 grid(n_tiles, a.n_dirs);
-    if (!a.x1 && tc_cell7_enabled() && tc_pipe_enabled() && tcr_outputs_ok(a)) {
+    SB_REQUIRE(!a.sum_dirs || seq_tcr_selected(a), SB_E_UNSUPP, "SB_ALGO_TCP: summed directions need lstm_tcr_kernel (single addend, SB_OPT_TC_PIPE, SB_OPT_TC_CELL7)");
+    if (seq_tcr_selected(a)) {
         CUtensorMap mo[4];                                  // the outputs leave through TMA tensor stores: same geometry as x0
         for (int d = 0; d < 2; ++d) {
             float* base = a.out[d < a.n_dirs ? d : 0];

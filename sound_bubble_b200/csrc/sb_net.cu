@@ -136,21 +136,27 @@ extern "C" int sb_net_forward_range(const sb_net_desc* d, const sb_net_io* io, i
         const sb_block_desc& bd = d->blocks[i];
         const float* fscale = (film && i > 0) ? film + (size_t)(i - 1) * 2 * film_stride : nullptr;
         const float* fshift = fscale ? fscale + film_stride : nullptr;
-        const float* inter_x1 = d->conv_lstm ? nullptr : w.x2;      // the second intra direction, added on load
+        // Plain LSTM blocks: where the pipelined tensor-core kernel runs the intra unit, both directions are summed into ONE
+        // buffer (TMA reduce stores) and the inter LSTM reads a single operand - which puts it on the same kernel.  The
+        // decision depends only on sizes, pointers and options, so calls that run the two units separately (sb_pipe's
+        // single-unit ranges) agree on it.
+        sb_intra_args ia{};
+        ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y_fwd = w.x1; ia.y_bwd = w.x1;
+        ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
+        ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H; ia.algo = io->intra_algo;
+        const bool summed = !d->conv_lstm && sb_intra_sum_supported(&ia);
+        if (!summed) ia.y_bwd = w.x2;
+        const float* inter_x1 = (d->conv_lstm || summed) ? nullptr : w.x2;   // else: the second intra direction, added on load
         if (do_intra && d->conv_lstm) {
-            sb_intra_conv_args ia{};
-            ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y = w.x1;
-            ia.conv_w = bd.cl_conv_w; ia.conv_b = bd.cl_conv_b; ia.prelu = bd.cl_prelu;
-            ia.deconv_w = bd.cl_deconv_w; ia.deconv_b = bd.cl_deconv_b;
-            ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
-            ia.ws = w.extra; ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H;
-            ia.down = d->lstm_down; ia.tail_mode = d->tail_mode; ia.algo = io->intra_algo;
-            { StageTimer tm(stream, SB_STAGE_INTRA); SB_CHECK(sb_intra_convlstm_fwd(&ia, stream)); }
+            sb_intra_conv_args ca{};
+            ca.x = w.x0; ca.film_scale = fscale; ca.film_shift = fshift; ca.y = w.x1;
+            ca.conv_w = bd.cl_conv_w; ca.conv_b = bd.cl_conv_b; ca.prelu = bd.cl_prelu;
+            ca.deconv_w = bd.cl_deconv_w; ca.deconv_b = bd.cl_deconv_b;
+            ca.dir[0] = bd.intra[0]; ca.dir[1] = bd.intra[1];
+            ca.ws = w.extra; ca.B = B; ca.T = T; ca.F = d->F; ca.C = d->C; ca.H = d->H;
+            ca.down = d->lstm_down; ca.tail_mode = d->tail_mode; ca.algo = io->intra_algo;
+            { StageTimer tm(stream, SB_STAGE_INTRA); SB_CHECK(sb_intra_convlstm_fwd(&ca, stream)); }
         } else if (do_intra) {
-            sb_intra_args ia{};
-            ia.x = w.x0; ia.film_scale = fscale; ia.film_shift = fshift; ia.y_fwd = w.x1; ia.y_bwd = w.x2;
-            ia.dir[0] = bd.intra[0]; ia.dir[1] = bd.intra[1];
-            ia.B = B; ia.T = T; ia.F = d->F; ia.C = d->C; ia.H = d->H; ia.algo = io->intra_algo;
             { StageTimer tm(stream, SB_STAGE_INTRA); SB_CHECK(sb_intra_lstm_fwd(&ia, stream)); }
         }
         if (!do_inter) continue;

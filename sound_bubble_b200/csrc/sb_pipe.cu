@@ -201,6 +201,47 @@ static int run_ranges(sb_pipe* p, long long t, int n_frames) {
     return 0;
 }
 
+// Device-resident windows / results of a group move with ONE kernel each way: as n pitched cudaMemcpy2DAsync calls they ran as
+// n small copy kernels per direction that each had to find a free SM among the one-CTA-per-SM LSTM kernels of the other groups
+// in flight (the device-resident pass of bench.py was 14 % slower than the pass from pinned host memory, whose copies use the
+// copy engines).
+constexpr int kMaxGather = 64;
+struct ChunkPtrs { const float* src[kMaxGather]; float* dst[kMaxGather]; };
+
+// window c = [rows][nfft] contiguous -> wave[row * pitch + c * hop + i]
+__global__ void gather_windows_kernel(const ChunkPtrs ptrs, float* wave, int n, int rows, int nfft, int hop, long long pitch) {
+    pdl_wait();
+    const long long per = (long long)rows * nfft, total = per * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / per);
+        const long long e = idx - (long long)c * per;
+        const int row = (int)(e / nfft), i = (int)(e - (long long)row * nfft);
+        wave[(long long)row * pitch + (long long)c * hop + i] = __ldg(ptrs.src[c] + e);
+    }
+}
+// wave_out[row * pitch + c * hop + i] -> result c = [rows][hop] contiguous (NULL: not wanted)
+__global__ void scatter_results_kernel(const ChunkPtrs ptrs, const float* wave_out, int n, int rows, int hop, long long pitch) {
+    pdl_wait();
+    const long long per = (long long)rows * hop, total = per * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / per);
+        float* dst = ptrs.dst[c];
+        if (!dst) continue;
+        const long long e = idx - (long long)c * per;
+        const int row = (int)(e / hop), i = (int)(e - (long long)row * hop);
+        dst[e] = wave_out[(long long)row * pitch + (long long)c * hop + i];
+    }
+}
+
+static bool on_device(const void* ptr) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice;
+}
+
 // launches the chunks gathered so far as one call of n = pend_win.size() frames (n == G: the captured graphs)
 static int launch_group(sb_pipe* p) {
     const int n = (int)p->pend_win.size();
@@ -212,14 +253,34 @@ static int launch_group(sb_pipe* p) {
     const sb_net_desc* d = p->desc;
     const size_t hop = (size_t)d->stride, nfft = (size_t)d->n_fft;
     const size_t in_pitch = sizeof(float) * (hop * n + nfft - hop), out_pitch = sizeof(float) * hop * n;
-    for (int c = 0; c < n; ++c)                 // window c covers samples [c*hop, c*hop + n_fft) of the group's wave
-        SB_CUDA(cudaMemcpy2DAsync(const_cast<float*>(io.wave) + c * hop, in_pitch, p->pend_win[c], sizeof(float) * nfft,
-                                  sizeof(float) * nfft, (size_t)p->B * d->M, cudaMemcpyDefault, st));
+    // the memory kind of a group is taken from its first window / first wanted result (a group does not mix kinds)
+    float* first_out = nullptr;
+    for (int c = 0; c < n && !first_out; ++c) first_out = p->pend_out[c];
+    const bool dev_in = n <= kMaxGather && on_device(p->pend_win[0]);
+    const bool dev_out = n <= kMaxGather && first_out && on_device(first_out);
+    ChunkPtrs ptrs{};
+    if (dev_in || dev_out)
+        for (int c = 0; c < n; ++c) { ptrs.src[c] = p->pend_win[c]; ptrs.dst[c] = p->pend_out[c]; }
+    if (dev_in) {
+        const long long total = (long long)n * p->B * d->M * (long long)nfft;
+        SB_CHECK(launch("gather_windows", gather_windows_kernel, dim3((unsigned)ceil_div_ll(total, 256 * 8)), dim3(256), 0, st, ptrs,
+                        const_cast<float*>(io.wave), n, p->B * d->M, (int)nfft, (int)hop, (long long)(in_pitch / sizeof(float))));
+    } else {
+        for (int c = 0; c < n; ++c)             // window c covers samples [c*hop, c*hop + n_fft) of the group's wave
+            SB_CUDA(cudaMemcpy2DAsync(const_cast<float*>(io.wave) + c * hop, in_pitch, p->pend_win[c], sizeof(float) * nfft,
+                                      sizeof(float) * nfft, (size_t)p->B * d->M, cudaMemcpyDefault, st));
+    }
     SB_CHECK(run_ranges(p, t, n == p->G ? 0 : n));
-    for (int c = 0; c < n; ++c)
-        if (p->pend_out[c])
-            SB_CUDA(cudaMemcpy2DAsync(p->pend_out[c], sizeof(float) * hop, io.wave_out + c * hop, out_pitch,
-                                      sizeof(float) * hop, (size_t)p->B * d->n_src, cudaMemcpyDefault, st));
+    if (dev_out) {
+        const long long total = (long long)n * p->B * d->n_src * (long long)hop;
+        SB_CHECK(launch("scatter_results", scatter_results_kernel, dim3((unsigned)ceil_div_ll(total, 256 * 8)), dim3(256), 0, st, ptrs,
+                        (const float*)io.wave_out, n, p->B * d->n_src, (int)hop, (long long)(out_pitch / sizeof(float))));
+    } else {
+        for (int c = 0; c < n; ++c)
+            if (p->pend_out[c])
+                SB_CUDA(cudaMemcpy2DAsync(p->pend_out[c], sizeof(float) * hop, io.wave_out + c * hop, out_pitch,
+                                          sizeof(float) * hop, (size_t)p->B * d->n_src, cudaMemcpyDefault, st));
+    }
     p->pend_win.clear();
     p->pend_out.clear();
     p->n_calls = t + 1;

@@ -113,7 +113,7 @@ def check_film(lib, device, variant, kwargs, B=3):
     return {"film": err}
 
 
-def check_intra(lib, device, variant, kwargs, algo, B=2, T=3, block=1, seed=5, use_film=True):
+def check_intra(lib, device, variant, kwargs, algo, B=2, T=3, block=1, seed=5, use_film=True, summed=False):
     ocfg, sd, cfg, pk = make_model(variant, kwargs, device)
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, T, cfg.n_freqs, cfg.D, generator=g)
@@ -152,6 +152,14 @@ def check_intra(lib, device, variant, kwargs, algo, B=2, T=3, block=1, seed=5, u
     a.B, a.T, a.F, a.C, a.H, a.algo = B, T, cfg.n_freqs, cfg.D, cfg.H, algo
     abi.check(lib, lib.sb_intra_lstm_fwd(ctypes.byref(a), _stream(device)), "sb_intra_lstm_fwd")
     _sync(device)
+    if summed:
+        # y_bwd == y_fwd: both directions add into one buffer; bitwise the sum the consumer would have formed on load
+        ys = torch.full_like(xd, float("nan"))
+        a.y_fwd = a.y_bwd = ys.data_ptr()
+        assert lib.sb_intra_sum_supported(ctypes.byref(a)) == 1
+        abi.check(lib, lib.sb_intra_lstm_fwd(ctypes.byref(a), _stream(device)), "sb_intra_lstm_fwd")
+        _sync(device)
+        assert torch.equal(ys, yf + yb)
     return {"y": maxerr(yf + yb, ref)}
 
 

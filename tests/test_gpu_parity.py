@@ -355,3 +355,27 @@ def test_two_tile_ping_pong_kernel_against_oracle(lib):
         assert all(v <= TOL for v in r.values()), r
     r = kc.check_inter(lib, DEV, "dis_embed", SYN, abi.SB_ALGO_TCQ, B=9, T=8)
     assert all(v <= TOL for v in r.values()), r
+
+
+def test_pipelined_tensor_core_kernel_against_oracle(lib):
+    """lstm_tcr_kernel (single-addend SB_ALGO_TC calls: k-step pipelined recurrence, TMA tensor stores): intra with FiLM and
+    without, one frame, tail tiles, many tiles; inter with carried state (aliased in place), tail tiles that pack several
+    batch items, one step; both directions summed into one buffer (y_bwd == y_fwd) equal to the sum of the two buffers
+    bitwise; the option that switches back to lstm_tcp_kernel; summed mode refused where the kernel does not run."""
+    TC = abi.SB_ALGO_TC
+    for kw in (dict(B=2, T=5, block=1), dict(B=1, T=1, block=0), dict(B=5, T=64, block=2), dict(B=3, T=43, block=0, use_film=False)):
+        r = kc.check_intra(lib, DEV, "dis_embed", SYN, TC, summed=True, **kw)
+        assert all(v <= TOL for v in r.values()), (kw, r)
+    for kw in (dict(B=1, T=3), dict(B=9, T=8), dict(B=2, T=40, alias_state=True), dict(B=8, T=1), dict(B=15, T=2)):
+        r = kc.check_inter(lib, DEV, "dis_embed", SYN, TC, two_inputs=False, **kw)
+        assert all(v <= TOL for v in r.values()), (kw, r)
+    assert lib.sb_set_option(abi.SB_OPT_TC_PIPE, 0) == 0
+    try:
+        r = kc.check_intra(lib, DEV, "dis_embed", SYN, TC, B=2, T=5, block=1)
+        assert all(v <= TOL for v in r.values()), r
+        with pytest.raises(Exception):
+            kc.check_intra(lib, DEV, "dis_embed", SYN, TC, B=2, T=5, block=1, summed=True)
+    finally:
+        assert lib.sb_set_option(abi.SB_OPT_TC_PIPE, 1) == 0
+    with pytest.raises(Exception):
+        kc.check_intra(lib, DEV, "dis_embed", SYN, abi.SB_ALGO_TILE, B=2, T=5, block=1, summed=True)
