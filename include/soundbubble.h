@@ -88,6 +88,8 @@ extern "C" {
                                 /* with bf16 hi/lo three-term operands (sb_train_tc.cu); 0 = the fp32 SIMT outer_kernel                 */
 #define SB_OPT_TC_PIPE 8        /* single-addend calls of SB_ALGO_TC run lstm_tcr_kernel: the h part of step s + 1 is issued chunk by   */
                                 /* chunk while the cell update of step s is still running (default 1)                                   */
+#define SB_OPT_TC_CW16 9        /* lstm_tcr_kernel with 16 cell-update warps (768 threads, setmaxnreg) instead of 8                    */
+#define SB_OPT_FRONT_TC 10      /* conv-in of calls with T >= 4 frames on the tensor cores (conv_in_tc_kernel), default 1              */
 int sb_set_option(int option, int value);
 
 /* ---------------------------------------------------------------------------------------------------------- */

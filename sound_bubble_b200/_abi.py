@@ -23,6 +23,8 @@ SB_OPT_TC_V1 = 5
 SB_OPT_TC_CELL7 = 6
 SB_OPT_TRAIN_TC = 7
 SB_OPT_TC_PIPE = 8
+SB_OPT_TC_CW16 = 9
+SB_OPT_FRONT_TC = 10
 SB_STAGES = ("stft_features", "conv_in", "film_params", "intra", "inter", "attention", "backend")
 
 fp = C.c_void_p          # device float* (raw address)

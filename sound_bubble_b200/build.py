@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(PKG, "csrc", "build")
 LIB = os.path.join(PKG, "libsoundbubble_sm100a.so")
-SOURCES = ["sb_host.cu", "sb_lstm.cu", "sb_lstm_tc.cu", "sb_lstm_tcp.cu", "sb_frontend.cu", "sb_backend.cu", "sb_convlstm.cu", "sb_attn.cu", "sb_attn_tc.cu", "sb_net.cu", "sb_pipe.cu", "sb_prepare.cu", "sb_train.cu", "sb_train_tc.cu"]
+SOURCES = ["sb_host.cu", "sb_lstm.cu", "sb_lstm_tc.cu", "sb_lstm_tcp.cu", "sb_frontend.cu", "sb_frontend_tc.cu", "sb_backend.cu", "sb_convlstm.cu", "sb_attn.cu", "sb_attn_tc.cu", "sb_net.cu", "sb_pipe.cu", "sb_prepare.cu", "sb_train.cu", "sb_train_tc.cu"]
 HEADERS = [os.path.join(CSRC, "sb_common.cuh"), os.path.join(CSRC, "sb_lstm.cuh"), os.path.join(INCLUDE, "soundbubble.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-I" + INCLUDE, "-I" + CSRC]

@@ -26,6 +26,11 @@ bool pdl_enabled();                         // programmatic dependent launch (sb
 bool attn_tc_enabled();                     // tcgen05 attention core for T >= 64 (sb_set_option(SB_OPT_ATTN_TC, 0) turns it off)
 bool train_one_row_enabled();                // training LSTM kernels with one gate row / one W_hh column per thread (sb_set_option(SB_OPT_TRAIN_ONE_ROW, 1))
 bool train_tc_enabled();                     // LSTM weight gradients on tcgen05 (sb_train_tc.cu; sb_set_option(SB_OPT_TRAIN_TC, v))
+bool tc_cw16_enabled();                      // lstm_tcr_kernel with 16 cell-update warps (sb_set_option(SB_OPT_TC_CW16, v))
+bool front_tc_enabled();                     // conv-in on the tensor cores (sb_set_option(SB_OPT_FRONT_TC, v))
+int front_tc_mode();
+bool conv_in_tc_supported(const sb_conv_in_args& p);
+int run_conv_in_tc(const sb_conv_in_args& p, cudaStream_t st);   // sb_frontend_tc.cu
 bool tc_pipe_enabled();                      // single-addend SB_ALGO_TC calls on lstm_tcr_kernel (sb_set_option(SB_OPT_TC_PIPE, v))
 bool tc_cell7_enabled();                     // shared-reciprocal cell update in lstm_tcp_kernel (sb_set_option(SB_OPT_TC_CELL7, v))
 bool tc_v1_enabled();                        // SB_ALGO_TC on the first tcgen05 kernel instead of the TMA pipeline (sb_set_option(SB_OPT_TC_V1, 1))

@@ -479,6 +479,7 @@ extern "C" int sb_conv_in_fwd(const sb_conv_in_args* p, void* stream) {
     SB_REQUIRE(p->conv_buf_in != p->conv_buf_out, SB_E_BADARG, "sb_conv_in_fwd: conv_buf_in and conv_buf_out must not alias");
     // offline: 4 frames x all bins per CTA; streaming-sized calls: 1 frame x 16 bins per CTA so the few frames still
     // spread over the whole chip (B * T * ceil(F/16) CTAs)
+    if (front_tc_enabled() && conv_in_tc_supported(*p)) return run_conv_in_tc(*p, (cudaStream_t)stream);
     const bool big = p->T >= 4;
     const int TT = big ? 4 : 1;
     const int FC = big ? p->F : 16;

@@ -20,6 +20,8 @@ static std::atomic<int> g_tc_v1{0};
 static std::atomic<int> g_tc_cell7{1};
 static std::atomic<int> g_train_tc{1};
 static std::atomic<int> g_tc_pipe{1};
+static std::atomic<int> g_front_tc{1};
+static std::atomic<int> g_tc_cw16{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -44,6 +46,9 @@ bool train_ffma2_enabled() { return g_train_ffma2.load(std::memory_order_relaxed
 bool tc_v1_enabled() { return g_tc_v1.load(std::memory_order_relaxed) != 0; }
 bool tc_cell7_enabled() { return g_tc_cell7.load(std::memory_order_relaxed) != 0; }
 bool train_tc_enabled() { return g_train_tc.load(std::memory_order_relaxed) != 0; }
+bool tc_cw16_enabled() { return g_tc_cw16.load(std::memory_order_relaxed) != 0; }
+bool front_tc_enabled() { return g_front_tc.load(std::memory_order_relaxed) != 0; }
+int front_tc_mode() { return g_front_tc.load(std::memory_order_relaxed); }
 bool tc_pipe_enabled() { return g_tc_pipe.load(std::memory_order_relaxed) != 0; }
 
 int sm_count() {
@@ -101,6 +106,14 @@ extern "C" int sb_set_option(int option, int value) {
     }
     if (option == SB_OPT_TRAIN_FFMA2) {
         sb::g_train_ffma2.store(value ? 1 : 0);
+        return 0;
+    }
+    if (option == SB_OPT_TC_CW16) {
+        sb::g_tc_cw16.store(value ? 1 : 0);
+        return 0;
+    }
+    if (option == SB_OPT_FRONT_TC) {
+        sb::g_front_tc.store(value);
         return 0;
     }
     if (option == SB_OPT_TC_PIPE) {

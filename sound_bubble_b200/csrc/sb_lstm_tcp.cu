@@ -677,10 +677,18 @@ __device__ long long g_tcq_dbg[16384];
 #endif
 
 namespace tcr {
-constexpr int kThreadsR = 416;                              // 4 stream warps, 8 cell-update warps, 1 MMA-issue warp
+// 4 stream warps, NCW cell-update warps, 1 MMA-issue warp.  NCW = 16: a thread owns a QUARTER of a row's units (4 units = 16 gate
+// columns per chunk), four cell warps per scheduler; six warpgroups (the last one holds the issue warp and three idle warps)
+// compiled for 80 registers, setmaxnreg moves the issue group's to the stream group (24 / 128).
+constexpr int threads(int ncw) { return ncw == 8 ? 416 : 768; }
 }
 
-__global__ void __launch_bounds__(tcr::kThreadsR, 1)
+__device__ __forceinline__ void sts8(void* p, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tcp::smem_u32(p)), "r"(x), "r"(y) : "memory");
+}
+
+template <int NCW>
+__global__ void __launch_bounds__(tcr::threads(NCW), 1)
 lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUtensorMap map_x0,
                 const __grid_constant__ CUtensorMap map_x0_tail, const __grid_constant__ CUtensorMap map_o0,
                 const __grid_constant__ CUtensorMap map_o0_tail, const __grid_constant__ CUtensorMap map_o1,
@@ -731,7 +739,7 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
     const int grow = valid ? o_row * a.rows_inner + i_row : 0;
     const long long rbase = valid ? (long long)o_row * a.stride_outer + (long long)i_row * a.stride_inner : 0;
 
-    for (int i = tid; i < kN; i += tcr::kThreadsR)          // bias folded into the exponent argument, see cell7
+    for (int i = tid; i < kN; i += tcr::threads(NCW))          // bias folded into the exponent argument, see cell7
         bias_s[i] = __ldg(w.tc_b + i) * ((i & 3) == 2 ? -2.0f * kLog2e : -kLog2e);
     if (tid < kC) {
         ln_s[tid] = __ldg(w.ln_g + tid);
@@ -746,7 +754,7 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         for (int i = 0; i < kSlabs; ++i) mbar_init(full + i, 1);
         mbar_init(gates, 1);
         mbar_init(pdone, 1);
-        for (int k = 0; k < 4; ++k) mbar_init(hk + k, 8);
+        for (int k = 0; k < 4; ++k) mbar_init(hk + k, NCW);
         mbar_init(xready, 1);
         bulk_barrier_init(wbar);
         bulk_expect(wbar, 2 * kWBytes + 2 * kPBytes);
@@ -764,6 +772,7 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
         // =============================================================================================================
         // stream group: TMA producer, LayerNorm / operand builder, output writer
         // =============================================================================================================
+        if (NCW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         auto issue_loads = [&](int step) {                  // one thread
             const int pos = dir ? S - 1 - step : step;
             unsigned char* dst = slabs + (size_t)(step % kSlabs) * kSlabBytes;
@@ -923,17 +932,21 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
             store_out(S - 1);
             tma_store_wait_read();
         }
-    } else if (warp == 12) {
+    } else if (warp >= 4 + NCW) {
         // =============================================================================================================
         // MMA issue: iteration i (while the cell warps update step i) builds the gates of step i + 1 and the projection of h_i
         // =============================================================================================================
-        if (elect_one()) {
-            const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), w_hi_s = smem_u32(w_hi), w_lo_s = smem_u32(w_lo);
-            const uint32_t p_hi_s = smem_u32(p_hi), p_lo_s = smem_u32(p_lo);
+        if (NCW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 4 + NCW && elect_one()) {
+            uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), w_hi_s = smem_u32(w_hi), w_lo_s = smem_u32(w_lo);
+            uint32_t p_hi_s = smem_u32(p_hi), p_lo_s = smem_u32(p_lo);
             constexpr uint32_t idesc_g = make_idesc(128, 256), idesc_p = make_idesc(128, 32);
             bulk_wait(wbar, 0);                             // the operand images have landed
             fence_after();
             for (int i = -1; i < S; ++i) {
+                // opaque bases: the ~70 descriptors of an iteration are rebuilt from six registers every time instead of being
+                // hoisted out of the loop (this warp has registers to spare only in the 8-cell-warp form, and nothing else to do)
+                asm volatile("" : "+r"(a_hi_s), "+r"(a_lo_s), "+r"(w_hi_s), "+r"(w_lo_s), "+r"(p_hi_s), "+r"(p_lo_s));
                 const uint32_t par = (uint32_t)((i + 1) & 1);
                 const uint32_t nbuf = tmem + 256u * par, pbuf = tmem + 256u - 256u * par;       // buffer of step i + 1 / of step i
                 const bool more = i + 1 < S;
@@ -975,7 +988,7 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
             }
         }
         __syncwarp();
-    } else {
+    } else if constexpr (NCW == 8) {
         // =============================================================================================================
         // cell-update group: thread (row, half), chunk k = units 16k + 8 half .. + 7 (register c[8k + j])
         // =============================================================================================================
@@ -1072,6 +1085,76 @@ lstm_tcr_kernel(const SeqArgs a, const tcp::Geom g, const __grid_constant__ CUte
                 st4(cp + 16 * ch, make_float4(c[8 * ch], c[8 * ch + 1], c[8 * ch + 2], c[8 * ch + 3]));
                 st4(cp + 16 * ch + 4, make_float4(c[8 * ch + 4], c[8 * ch + 5], c[8 * ch + 6], c[8 * ch + 7]));
             }
+        }
+    } else {
+        // =============================================================================================================
+        // cell-update group, 16 warps: thread (row, quarter), chunk k = units 16k + 4 quarter .. + 3 (register c[4k + j])
+        // =============================================================================================================
+        const int qt = (warp - 4) >> 2;
+        float c[16];
+        auto store4 = [&](int ch, const float (&h4)[4]) {    // 4 units = half a 16-byte core-matrix row of the hi and the lo image
+            const __nv_bfloat162 a0 = __floats2bfloat162_rn(h4[0], h4[1]), a1 = __floats2bfloat162_rn(h4[2], h4[3]);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(h4[0] - __bfloat162float(a0.x), h4[1] - __bfloat162float(a0.y));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(h4[2] - __bfloat162float(a1.x), h4[3] - __bfloat162float(a1.y));
+            const int chunk = 4 + 2 * ch + (qt >> 1);
+            const int off = ((chunk * (kRows / 8) + (r >> 3)) * 8 + (r & 7)) * 16 + 8 * (qt & 1);
+            sts8(a_hi + off, *reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+            sts8(a_lo + off, *reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        };
+        if (a.h0 && valid) {
+            const float* cp = a.c0 + (long long)grow * kH + 4 * qt;
+            const float* hp = a.h0 + (long long)grow * kH + 4 * qt;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {                // plain loads: hN / cN may alias h0 / c0
+                const float4 c0 = ld_plain4(cp + 16 * ch), v0 = ld_plain4(hp + 16 * ch);
+                c[4 * ch] = c0.x; c[4 * ch + 1] = c0.y; c[4 * ch + 2] = c0.z; c[4 * ch + 3] = c0.w;
+                const float h4[4] = {v0.x, v0.y, v0.z, v0.w};
+                store4(ch, h4);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) c[j] = 0.0f;
+            const float h4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) store4(ch, h4);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0)
+            for (int k = 0; k < 4; ++k) mbar_arrive(hk + k);
+
+        float* const hN = (a.hN && valid) ? a.hN + (long long)grow * kH + 4 * qt : nullptr;
+        for (int s = 0; s < S; ++s) {
+            const uint32_t par = (uint32_t)(s & 1);
+            const uint32_t gcol = tmem + lane_base + 256u * par + 16u * qt;       // chunk k: 16 columns at + 64 k
+            mbar_wait(gates, par);
+            fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t cur[16];
+                tmem_ld16_issue(gcol + 64 * ch, cur);
+                const float* bp = bias_s + 4 * (16 * ch + 4 * qt);
+                const float4 nb0 = lds4_ro(bp), nb1 = lds4_ro(bp + 4), nb2 = lds4_ro(bp + 8), nb3 = lds4_ro(bp + 12);
+                tmem_wait_ld();
+                pin16(cur);
+                float h4[4];
+                h4[0] = cell7(__uint_as_float(cur[0]), __uint_as_float(cur[1]), __uint_as_float(cur[2]), __uint_as_float(cur[3]), nb0, c[4 * ch]);
+                h4[1] = cell7(__uint_as_float(cur[4]), __uint_as_float(cur[5]), __uint_as_float(cur[6]), __uint_as_float(cur[7]), nb1, c[4 * ch + 1]);
+                h4[2] = cell7(__uint_as_float(cur[8]), __uint_as_float(cur[9]), __uint_as_float(cur[10]), __uint_as_float(cur[11]), nb2, c[4 * ch + 2]);
+                h4[3] = cell7(__uint_as_float(cur[12]), __uint_as_float(cur[13]), __uint_as_float(cur[14]), __uint_as_float(cur[15]), nb3, c[4 * ch + 3]);
+                if (s == S - 1 && hN) st4(hN + 16 * ch, make_float4(h4[0], h4[1], h4[2], h4[3]));
+                if (ch == 3 && s > 0) mbar_wait(pdone, (uint32_t)((s - 1) & 1));     // see the 8-warp form
+                store4(ch, h4);
+                fence_before();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(hk + ch);
+            }
+        }
+        if (a.cN && valid) {
+            float* cp = a.cN + (long long)grow * kH + 4 * qt;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) st4(cp + 16 * ch, make_float4(c[4 * ch], c[4 * ch + 1], c[4 * ch + 2], c[4 * ch + 3]));
         }
     }
     fence_before();
@@ -1674,7 +1757,9 @@ int run_seq_tcp(const SeqArgs& a, cudaStream_t st) {
             SB_CHECK(make_map(&mo[2 * d], base, a, g, kRows));
             SB_CHECK(make_map(&mo[2 * d + 1], base, a, g, g.tail ? g.tail : kRows));
         }
-        return launch("lstm_tcr", lstm_tcr_kernel, grid, dim3(tcr::kThreadsR), (size_t)kSmemBytes, st, a, g, m[0], m[1], mo[0], mo[1], mo[2], mo[3]);
+        if (tc_cw16_enabled())
+            return launch("lstm_tcr16", lstm_tcr_kernel<16>, grid, dim3(tcr::threads(16)), (size_t)kSmemBytes, st, a, g, m[0], m[1], mo[0], mo[1], mo[2], mo[3]);
+        return launch("lstm_tcr", lstm_tcr_kernel<8>, grid, dim3(tcr::threads(8)), (size_t)kSmemBytes, st, a, g, m[0], m[1], mo[0], mo[1], mo[2], mo[3]);
     }
     if (tc_cell7_enabled())
         return launch("lstm_tcp", lstm_tcp_kernel<true>, grid, dim3(kThreads), (size_t)kSmemBytes, st, a, g, m[0], m[1], m[2], m[3]);

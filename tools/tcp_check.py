@@ -143,7 +143,7 @@ if which == "cell7":
         print("B=%3d T=%3d scale=%4.0f  intra maxabs %.2e  %8.1f -> %8.1f us   inter maxabs %.2e  %8.1f -> %8.1f us  nan=%s"
               % (B, T, scale, d_intra, t_old, t_new, d_inter, u_old, u_new, nan), flush=True)
 
-if which == "pipe":
+if which in ("pipe", "cw16"):
     # A/B of lstm_tcr_kernel (SB_OPT_TC_PIPE: h part of the next step issued under the cell update) against lstm_tcp_kernel
     torch.manual_seed(0)
     net = Net(**SYN).to(dev).eval()
@@ -151,7 +151,7 @@ if which == "pipe":
     F, C, H = 145, 32, 64
 
     def opt16(v):
-        abi.check(lib, lib.sb_set_option(abi.SB_OPT_TC_PIPE, v), "sb_set_option")
+        abi.check(lib, lib.sb_set_option(abi.SB_OPT_TC_PIPE if which == "pipe" else abi.SB_OPT_TC_CW16, v), "sb_set_option")
     for (B, T) in ((32, 8), (7, 100), (32, 32), (32, 125), (32, 625)):
         g = torch.Generator(device="cpu").manual_seed(B * 1000 + T)
         x = torch.randn(B, T, F, C, generator=g).to(dev)
@@ -162,12 +162,12 @@ if which == "pipe":
         opt16(0)
         rf, rb, f_old = intra_call(pk, x, film, TCP)
         t_old = timeit(f_old)
-        ry, rh, rc, g_old = inter_call(pk, x, x1, h, c, TCP)
+        ry, rh, rc, g_old = inter_call(pk, x, x1 if which == "pipe" else None, h, c, TCP)
         u_old = timeit(g_old)
         opt16(1)
         nf, nb, f_new = intra_call(pk, x, film, TCP)
         t_new = timeit(f_new)
-        ny, nh, nc, g_new = inter_call(pk, x, x1, h, c, TCP)
+        ny, nh, nc, g_new = inter_call(pk, x, x1 if which == "pipe" else None, h, c, TCP)
         u_new = timeit(g_new)
         d_intra = max(float((rf - nf).abs().max()), float((rb - nb).abs().max()))
         d_inter = max(float((ry - ny).abs().max()), float((rh - nh).abs().max()), float((rc - nc).abs().max()))
