@@ -595,7 +595,11 @@ def run_ours(args, rank, world, local_rank):
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                      # 74.4 TFLOP/s fp32 FMA (tools/ubench: 72.7 measured)
     fracs = {"hbm": by / t_s / 1e9 / bw_peak, "tensor": (3 * fl / t_s / 1e12 / tensor_peak) if tc_family else 0.0,
              "fp32_fma": 0.0 if tc_family else fl / t_s / 1e12 / fp32_peak}
-    kernel_name = {"intra": "lstm_tcp_kernel" if tc_family else "lstm_ws_kernel", "inter": "lstm_tcp_kernel" if tc_family else "lstm_tile_kernel"}.get(dom, dom)
+    kernel_name = {"intra": "lstm_tcr_kernel" if tc_family else "lstm_ws_kernel", "inter": "lstm_tcr_kernel" if tc_family else "lstm_tile_kernel"}.get(dom, dom)
+    # the roof this kernel actually leans on: the XU (MUFU) pipe, 16 lanes per clock and SM; 7 ex2 / rcp per LSTM cell
+    cells = {"intra": 2 * F * H, "inter": F * H}.get(dom, 0) * units
+    n_ctas = {"intra": 2 * -(-units // 128), "inter": BATCH * (F // 128) + -(-BATCH // (128 // (F % 128)))}.get(dom, 148)
+    fracs["xu"] = (7 * cells / t_s) / (min(n_ctas, 148) * 16 * 1.965e9) if tc_family else 0.0      # of the SMs the launch occupies
     if tc_family:
         bound, achieved, peak, unit = "tensor", fl / t_s / 1e12, tensor_peak, "TFLOP/s"
     elif dom in alg_flops:
@@ -609,7 +613,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {
         "kernel": "%s (%s stage)" % (kernel_name, dom), "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
         "frac": achieved / peak,
-        "traffic": ncu_dram_traffic("lstm_tcp_kernel" if tc_family else {"intra": "lstm_ws_kernel<32, 0, 2>", "inter": "lstm_t"}.get(dom, dom)),
+        "traffic": ncu_dram_traffic("lstm_tcr_kernel" if tc_family else {"intra": "lstm_ws_kernel<32, 0, 2>", "inter": "lstm_t"}.get(dom, dom)),
         "peak_source": ("MEASURED_PEAKS.json (measured)" if peaks else "fallback of B200_PROFILING.md") + (
             "; fp32 FMA peak = 148 SMs x 128 FMA/clk x 1.965 GHz (tools/ubench measured 72.7)" if bound == "fp32_fma" else ""),
         "avg_launch_us": dom_ms * 1e3, "launch_units": "%d utterances x %d frames" % (BATCH, G),
@@ -618,10 +622,12 @@ def run_ours(args, rank, world, local_rank):
                   "T = %d launch sequence the timed region runs as graphs; share checked against profiles/r02_launches_bench.txt" % G,
         "share_of_group": per_call_ms[dom] / tot,
         "all_roofs": {"hbm_frac": fracs["hbm"], "tensor_frac_executed_3term": fracs["tensor"], "fp32_fma_frac": fracs["fp32_fma"],
-                      "max": max(fracs.values()),
+                      "xu_frac": fracs["xu"], "max": max(fracs.values()),
                       "note": "tcgen05 path: algorithmic 2*MAC FLOPs in `achieved`; the bf16 hi/lo three-term split executes 3x that on "
-                              "the tensor pipe.  ncu (profiles/r02_prof_tcp.txt): XU (MUFU: 10 ex2/rcp per cell) 54 %, tensor pipe 26 %, "
-                              "issue 34 % of active cycles - the serial cell update, not a memory or tensor roof, bounds the kernel"},
+                              "the tensor pipe.  The recurrence is serial in the step: what bounds a step is the XU pipe (7 MUFU per "
+                              "cell; xu_frac = 7 x cells / launch time / (CTAs of the launch x 16 lanes x 1.965 GHz), one CTA per SM) "
+                              "plus the three MMAs that cannot overlap the cell update.  ncu "
+                              "(profiles/r02_prof_tcr.txt): XU 58 %, tensor pipe 40 %, issue 53 % of active cycles"},
         "stage_us_per_group": {k: 1e3 * v for k, v in per_call_ms.items()},
         "step": {"alg_tflop": step_flops / 1e12, "alg_gbyte": step_bytes / 1e9, "tflops": step_flops / (ms_dev * 1e-3) / 1e12,
                  "frac_of_fp32_fma_peak": step_flops / (ms_dev * 1e-3) / 1e12 / fp32_peak,
@@ -719,7 +725,7 @@ def main():
     ap.add_argument("--ranges", type=int, default=0, help="pipelined session: number of unit ranges (0 = default)")
     ap.add_argument("--pipe-intra-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the intra path")
     ap.add_argument("--pipe-inter-algo", type=int, default=0, help="pipelined session: force an SB_ALGO_* for the inter path")
-    ap.add_argument("--group", type=int, default=int(os.environ.get("SB_GROUP", "32")), help="pipelined session: chunks per launch")
+    ap.add_argument("--group", type=int, default=int(os.environ.get("SB_GROUP", "64")), help="pipelined session: chunks per launch")
     ap.add_argument("--depth", type=int, default=int(os.environ.get("SB_DEPTH", "16")), help="pipelined session: groups in flight")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed output")
     ap.add_argument("--no-library", action="store_true", help="skip the stock-PyTorch-on-GPU context baseline")
