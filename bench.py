@@ -704,7 +704,8 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "dp%d (utterances sharded, no collective on the data path)" % world},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(win_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
-        "gpu_launches": int(launches_per_call * calls * args.steps),
+        # + the gather / scatter kernel of a device-resident group (sb_pipe.cu), which the eager twin of a call does not launch
+        "gpu_launches": int((launches_per_call + (2 if pipe is not None and G > 1 else 0)) * calls * args.steps),
         "launches_per_call": int(launches_per_call), "calls_per_step": calls,
         "in_order": {"value": frames / (ms_in_order * 1e-3), "unit": UNIT, "ms_per_step": ms_in_order,
                      "note": "latency mode: one stream, one chunk per launch sequence, chunk t+1 starts when chunk t has finished"},
