@@ -58,13 +58,27 @@ class NetBase(nn.Module):
     # -- engine (packed weights on the device of the parameters) ---------------------------------------------
     def _named_weights(self) -> dict:
         """name -> tensor for every state_dict() key, by attribute walk (works on nn.DataParallel replicas too, whose
-        tensors are autograd-connected broadcast copies held as plain attributes)."""
+        tensors are autograd-connected broadcast copies held as plain attributes).  The walk down to the module that holds
+        each tensor is done once per instance: a replica's __dict__ is a shallow copy of the original's, so the cache
+        records whose it is and a replica rebuilds it against its own submodules."""
+        holders = self.__dict__.get("_weight_holders")
+        if holders is None or holders[0] is not self:
+            pairs = []
+            for name in self._weight_names:
+                obj, parts = self, name.split(".")
+                for part in parts[:-1]:
+                    obj = getattr(obj, part)
+                pairs.append((name, obj, parts[-1]))
+            holders = (self, pairs)
+            self.__dict__["_weight_holders"] = holders
         out = {}
-        for name in self._weight_names:
-            obj = self
-            for part in name.split("."):
-                obj = getattr(obj, part)
-            out[name] = obj
+        for name, mod, leaf in holders[1]:
+            t = mod._parameters.get(leaf)
+            if t is None:
+                t = mod._buffers.get(leaf)
+            if t is None:
+                t = mod.__dict__[leaf]                   # replica: plain attribute
+            out[name] = t
         return out
 
     def _weights_key(self, named):
