@@ -28,7 +28,6 @@ bool train_one_row_enabled();                // training LSTM kernels with one g
 bool train_tc_enabled();                     // LSTM weight gradients on tcgen05 (sb_train_tc.cu; sb_set_option(SB_OPT_TRAIN_TC, v))
 bool tc_cw16_enabled();                      // lstm_tcr_kernel with 16 cell-update warps (sb_set_option(SB_OPT_TC_CW16, v))
 bool front_tc_enabled();                     // conv-in on the tensor cores (sb_set_option(SB_OPT_FRONT_TC, v))
-int front_tc_mode();
 bool conv_in_tc_supported(const sb_conv_in_args& p);
 int run_conv_in_tc(const sb_conv_in_args& p, cudaStream_t st);   // sb_frontend_tc.cu
 bool tc_pipe_enabled();                      // single-addend SB_ALGO_TC calls on lstm_tcr_kernel (sb_set_option(SB_OPT_TC_PIPE, v))

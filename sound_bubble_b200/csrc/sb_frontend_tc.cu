@@ -120,7 +120,7 @@ __host__ __device__ inline int rows_padded(int FP) {
 }  // namespace cit
 
 // grid (ceil(T * FP / 512), B)
-__global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_conv_in_args a, const int dbg) {
+__global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_conv_in_args a) {
     using namespace cit;
     extern __shared__ unsigned char sm_raw[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 127) & ~uintptr_t(127));
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_c
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(128, kC);
 #pragma unroll 1
-            for (int tile = 0; tile < (dbg == 2 ? 0 : kTiles); ++tile) {
+            for (int tile = 0; tile < kTiles; ++tile) {
                 mbar_wait(staged + tile, 0u);
                 fence_after();
                 const uint32_t arow = img_s + (uint32_t)tile * 128 * 16;
@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_c
                             }
                 umma_commit(done + tile);
             }
-            if (dbg == 2) for (int tile = 0; tile < kTiles; ++tile) umma_commit(done + tile);
         }
         __syncwarp();
     } else {
@@ -265,10 +264,8 @@ __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_c
         int row0 = 0;
         for (int k = 0; k < kTiles; ++k) {
             const int row1 = min(R, 128 * (k + 1) + 2 * FP + 2);         // tile k reads rows 128 k .. 128 k + 127 + 2 FP + 2
-            if (dbg != 3) {
-                if (k == 0) stage_rows(row0, row1, std::integral_constant<int, 7>{});
-                else stage_rows(row0, row1, std::integral_constant<int, 4>{});
-            }
+            if (k == 0) stage_rows(row0, row1, std::integral_constant<int, 7>{});
+            else stage_rows(row0, row1, std::integral_constant<int, 4>{});
             row0 = row1;
             fence_async_smem();
             __syncwarp();
@@ -336,7 +333,7 @@ bool conv_in_tc_supported(const sb_conv_in_args& p) {
 int run_conv_in_tc(const sb_conv_in_args& p, cudaStream_t st) {
     const int FP = p.F + 2;
     dim3 grid(ceil_div(p.T * FP, cit::kRowsOut), p.B);
-    return launch("conv_in_tc", conv_in_tc_kernel, grid, dim3(cit::kThreads), conv_in_tc_smem(p.F), st, p, front_tc_mode());
+    return launch("conv_in_tc", conv_in_tc_kernel, grid, dim3(cit::kThreads), conv_in_tc_smem(p.F), st, p);
 }
 
 #else   // SB_EMU: tensor-core instructions cannot be emulated on the host

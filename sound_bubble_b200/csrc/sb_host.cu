@@ -48,7 +48,6 @@ bool tc_cell7_enabled() { return g_tc_cell7.load(std::memory_order_relaxed) != 0
 bool train_tc_enabled() { return g_train_tc.load(std::memory_order_relaxed) != 0; }
 bool tc_cw16_enabled() { return g_tc_cw16.load(std::memory_order_relaxed) != 0; }
 bool front_tc_enabled() { return g_front_tc.load(std::memory_order_relaxed) != 0; }
-int front_tc_mode() { return g_front_tc.load(std::memory_order_relaxed); }
 bool tc_pipe_enabled() { return g_tc_pipe.load(std::memory_order_relaxed) != 0; }
 
 int sm_count() {
@@ -113,7 +112,7 @@ extern "C" int sb_set_option(int option, int value) {
         return 0;
     }
     if (option == SB_OPT_FRONT_TC) {
-        sb::g_front_tc.store(value);
+        sb::g_front_tc.store(value ? 1 : 0);
         return 0;
     }
     if (option == SB_OPT_TC_PIPE) {

@@ -396,3 +396,11 @@ def test_pipelined_tensor_core_kernel_against_oracle(lib):
         assert lib.sb_set_option(abi.SB_OPT_TC_PIPE, 1) == 0
     with pytest.raises(Exception):
         kc.check_intra(lib, DEV, "dis_embed", SYN, abi.SB_ALGO_TILE, B=2, T=5, block=1, summed=True)
+    assert lib.sb_set_option(abi.SB_OPT_TC_CW16, 1) == 0          # the 16-cell-warp form (setmaxnreg budgets) stays correct
+    try:
+        r = kc.check_intra(lib, DEV, "dis_embed", SYN, TC, B=5, T=64, block=2, summed=True)
+        assert all(v <= TOL for v in r.values()), r
+        r = kc.check_inter(lib, DEV, "dis_embed", SYN, TC, two_inputs=False, B=9, T=8)
+        assert all(v <= TOL for v in r.values()), r
+    finally:
+        assert lib.sb_set_option(abi.SB_OPT_TC_CW16, 0) == 0
