@@ -235,7 +235,7 @@ def stage_profile(lib, fn):
     return {name: (ms[i], calls[i]) for i, name in enumerate(abi.SB_STAGES) if calls[i]}
 
 
-def ncu_dram_traffic(kernel_substr):
+def ncu_dram_traffic(kernel_substr, grid_substr=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of its
     `ncu --set full` capture (profiles/rNN_prof_*.txt, written by tools/summarize_profiles.py).  None if there is none."""
     import glob
@@ -247,7 +247,7 @@ def ncu_dram_traffic(kernel_substr):
             if line.startswith("== "):
                 cur = {"name": line, "r": None, "w": None}
             m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
-            if m and cur is not None and kernel_substr in cur["name"]:
+            if m and cur is not None and kernel_substr in cur["name"] and (grid_substr is None or grid_substr in cur["name"]):
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
                 cur["r" if m.group(1) == "read" else "w"] = float(m.group(2)) * scale
                 if cur["r"] is not None and cur["w"] is not None:
@@ -613,7 +613,9 @@ def run_ours(args, rank, world, local_rank):
     roofline = {
         "kernel": "%s (%s stage)" % (kernel_name, dom), "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
         "frac": achieved / peak,
-        "traffic": ncu_dram_traffic("lstm_tcr_kernel" if tc_family else {"intra": "lstm_ws_kernel<32, 0, 2>", "inter": "lstm_t"}.get(dom, dom)),
+        # the capture of the same launch shape (profiles/r02_prof_tcr.txt: 32 utterances x G frames, tools/gpu_r2_final.sh)
+        "traffic": ncu_dram_traffic("lstm_tcr_kernel", "grid (%d, %d, 1)" % ((n_ctas // 2, 2) if dom == "intra" else (n_ctas, 1))) if tc_family
+        else ncu_dram_traffic({"intra": "lstm_ws_kernel<32, 0, 2>", "inter": "lstm_t"}.get(dom, dom)),
         "peak_source": ("MEASURED_PEAKS.json (measured)" if peaks else "fallback of B200_PROFILING.md") + (
             "; fp32 FMA peak = 148 SMs x 128 FMA/clk x 1.965 GHz (tools/ubench measured 72.7)" if bound == "fp32_fma" else ""),
         "avg_launch_us": dom_ms * 1e3, "launch_units": "%d utterances x %d frames" % (BATCH, G),

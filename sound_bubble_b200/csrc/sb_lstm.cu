@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(256, 1) lstm_ws_kernel(const SeqArgs a) {
 //   tc   : ~15.5k per step for up to one wave of 128-sequence CTAs (tcgen05 gate GEMM + 256-thread cell update), ~10.8k
 //          per wave once several waves keep every SM busy; wins when the tile family needs several rounds (offline)
 // plus a launch + prologue constant; the cheapest family for (rows, dirs, steps) wins.
-static int pick_algo(int n_rows, int n_dirs, int S, int sms, bool tc_ok) {
+static int pick_algo(int n_rows, int n_dirs, int S, int sms, bool tc_ok, bool single_addend) {
     const int tasks = ceil_div(n_rows, 8) * n_dirs;
     const int resident = sms * 8;
     const double rounds = tasks <= resident ? 1.0 : (double)ceil_div(tasks, resident);
@@ -901,9 +901,11 @@ static int pick_algo(int n_rows, int n_dirs, int S, int sms, bool tc_ok) {
     if (ws2 < best_cost) { best = SB_ALGO_WS2; best_cost = ws2; }
     if (tc_ok) {
         const double waves = (double)(ceil_div(n_rows, 128) * n_dirs) / sms;
-        // lstm_tcp_kernel (profiles/r02_tcp_time.txt): 5.25 us = 10.3k cycles per step and round of CTAs, one CTA per SM
+        // per step and round of CTAs (one CTA per SM): lstm_tcr_kernel 3.45 us = 6.8k cycles (single-addend calls, profiles/
+        // r02_tcr_ab.txt), lstm_tcp_kernel 4.36 us = 8.6k cycles
+        const double step = single_addend && tc_pipe_enabled() && tc_cell7_enabled() ? 6800.0 : 8600.0;
         const double tc = tc_v1_enabled() ? S * (waves <= 1.0 ? 15500.0 : waves * 10800.0) + 60000.0
-                                          : S * ceil(waves) * 10300.0 + 40000.0;
+                                          : S * ceil(waves) * step + 40000.0;
         if (tc < best_cost) return SB_ALGO_TC;
     }
     return best;
@@ -917,7 +919,7 @@ static int run_seq_c(const SeqArgs& a, int algo, cudaStream_t st) {
 #else
     constexpr bool tc_ok = C == 32 && !RAW_H;
 #endif
-    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sms, tc_ok);
+    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sms, tc_ok, a.x1 == nullptr);
     switch (algo) {
         case SB_ALGO_TC:
             if constexpr (C == 32 && !RAW_H)
@@ -967,7 +969,7 @@ static bool seq_sum_supported(const SeqArgs& a, int C, int H, bool raw_h, int al
     return false;
 #else
     if (C != 32 || H != 64 || raw_h || a.n_rows <= 0 || a.n_steps <= 0) return false;
-    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sm_count(), true);
+    if (algo == SB_ALGO_AUTO) algo = pick_algo(a.n_rows, a.n_dirs, a.n_steps, sm_count(), true, a.x1 == nullptr);
     if (algo == SB_ALGO_TCP) return seq_tcr_selected(a);
     return algo == SB_ALGO_TC && !tc_v1_enabled() && seq_tcr_selected(a);
 #endif
