@@ -256,7 +256,7 @@ def ncu_dram_traffic(kernel_substr, grid_substr=None):
     return sum(vals) / len(vals) if vals else None
 
 
-def training_leg(dev, rank, world, batch=8, steps=3):
+def training_leg(dev, rank, world, batch=8, steps=5):
     """BASELINE config 4's shape, for context next to the headline: one data-parallel training step of the same TFG_S
     model (forward + hand-written backward kernels + ONE NCCL all-reduce of the flat gradient + clip + Adam) on `batch`
     5 s clips per GPU, fp32.  Device-timed, max over ranks.  A failure is reported in the line, never hidden."""
@@ -316,23 +316,26 @@ def training_leg(dev, rank, world, batch=8, steps=3):
             snr_grads(0, 2 * world)
             grad_relerr = float((red.flat - reduced).abs().max() / red.flat.abs().max())
         dist.barrier()
-    step()
+    for _ in range(2):                                             # the caching allocator settles on the step's 22 GB working set
+        step()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
+    per_step = []
+    for _ in range(steps):                                         # every step device-timed on its own; the median is reported
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # (a step that has to go back to
+        a.record()                                                 # cudaMalloc after the other legs' allocations costs 1.5x)
         loss = step()
-    b.record()
-    b.synchronize()
-    t = torch.tensor([a.elapsed_time(b) / steps], device=dev, dtype=torch.float64)
+        b.record()
+        b.synchronize()
+        per_step.append(a.elapsed_time(b))
+    t = torch.tensor([statistics.median(per_step)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     frames = batch * T_FRAMES * world
     return {"value": frames / (ms * 1e-3), "unit": "training frames/s", "ms_per_step": ms, "global_batch": batch * world,
-            "clip_seconds": 5.0, "dtype": "f32", "steps": steps, "loss": float(loss.detach()),
+            "clip_seconds": 5.0, "dtype": "f32", "steps": steps, "ms_each_step": per_step, "loss": float(loss.detach()),
             "grad_relerr_vs_global_batch": grad_relerr,
             "collective": "one all-reduce of %d fp32 gradients per step (NCCL)" % red.numel if world > 1 else "none (1 GPU)",
             "note": "forward + backward through csrc/sb_train.cu, clip after the reduction, Adam; see tools/train_bench.py"}
