@@ -39,11 +39,19 @@ struct sb_pipe {
     std::vector<cudaEvent_t> joins;             // [depth]
     std::vector<cudaGraphExec_t> graphs;        // [n_ios][n_ranges]
     cudaEvent_t fork = nullptr;
+    // grouped mode, host windows / results that are consecutive pieces of ONE host array (a recording read into memory, the
+    // bench's pinned clip): per slot, room for G contiguous windows and G contiguous results on the device - the only device
+    // memory the pipe owns - so that a group costs one copy each way plus the gather / scatter kernels
+    float* stage_in = nullptr;
+    float* stage_out = nullptr;
+    size_t win_floats = 0, res_floats = 0;      // one chunk's window [B][M][n_fft] / result [B][S][stride]
 #endif
 };
 
 #ifndef SB_EMU
 namespace sb {
+
+constexpr int kMaxGather = 64;              // chunks of a group the gather / scatter kernels take (pointer table in the parameters)
 
 static int cuda_fail(const char* what, cudaError_t e) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -62,6 +70,8 @@ static void destroy(sb_pipe* p) {
     for (auto e : p->events) if (e) cudaEventDestroy(e);
     for (auto e : p->joins) if (e) cudaEventDestroy(e);
     if (p->fork) cudaEventDestroy(p->fork);
+    if (p->stage_in) cudaFree(p->stage_in);
+    if (p->stage_out) cudaFree(p->stage_out);
     for (auto s : p->streams) if (s) cudaStreamDestroy(s);
     delete p;
 }
@@ -129,6 +139,12 @@ extern "C" int sb_pipe_create(const sb_net_desc* d, const sb_net_io* ios, int n_
     auto fail = [&](int rc) { destroy(p); return rc; };
     cudaError_t e = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming);
     if (e != cudaSuccess) return fail(cuda_fail("cudaEventCreate", e));
+    p->win_floats = (size_t)p->B * d->M * d->n_fft;
+    p->res_floats = (size_t)p->B * d->n_src * d->stride;
+    if (p->G > 1 && p->G <= kMaxGather) {
+        if ((e = cudaMalloc(&p->stage_in, sizeof(float) * p->win_floats * p->G * depth)) != cudaSuccess) return fail(cuda_fail("cudaMalloc (window staging)", e));
+        if ((e = cudaMalloc(&p->stage_out, sizeof(float) * p->res_floats * p->G * depth)) != cudaSuccess) return fail(cuda_fail("cudaMalloc (result staging)", e));
+    }
     for (int s = 0; s < depth; ++s) {
         if ((e = cudaStreamCreateWithFlags(&p->streams[s], cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail("cudaStreamCreate", e));
         if ((e = cudaEventCreateWithFlags(&p->joins[s], cudaEventDisableTiming)) != cudaSuccess) return fail(cuda_fail("cudaEventCreate", e));
@@ -205,7 +221,6 @@ static int run_ranges(sb_pipe* p, long long t, int n_frames) {
 // n small copy kernels per direction that each had to find a free SM among the one-CTA-per-SM LSTM kernels of the other groups
 // in flight (the device-resident pass of bench.py was 14 % slower than the pass from pinned host memory, whose copies use the
 // copy engines).
-constexpr int kMaxGather = 64;
 struct ChunkPtrs { const float* src[kMaxGather]; float* dst[kMaxGather]; };
 
 // window c = [rows][nfft] contiguous -> wave[row * pitch + c * hop + i]
@@ -258,10 +273,23 @@ static int launch_group(sb_pipe* p) {
     for (int c = 0; c < n && !first_out; ++c) first_out = p->pend_out[c];
     const bool dev_in = n <= kMaxGather && on_device(p->pend_win[0]);
     const bool dev_out = n <= kMaxGather && first_out && on_device(first_out);
+    // Host windows / results that are consecutive pieces of one array travel as ONE copy through the pipe's device staging
+    // (64 pitched copies cost 0.6 ms before a group's first kernel can start - exposed at the start of a pass - and 64 API calls)
+    auto consecutive = [&](auto get, size_t floats) {
+        for (int c = 1; c < n; ++c)
+            if (!get(c) || get(c) != get(c - 1) + floats) return false;
+        return n > 1 && get(0) != nullptr;
+    };
+    const bool stage_in = !dev_in && p->stage_in && n <= p->G && consecutive([&](int c) { return p->pend_win[c]; }, p->win_floats);
+    const bool stage_out = !dev_out && p->stage_out && n <= p->G && consecutive([&](int c) { return (const float*)p->pend_out[c]; }, p->res_floats);
     ChunkPtrs ptrs{};
-    if (dev_in || dev_out)
-        for (int c = 0; c < n; ++c) { ptrs.src[c] = p->pend_win[c]; ptrs.dst[c] = p->pend_out[c]; }
-    if (dev_in) {
+    for (int c = 0; c < n && c < kMaxGather; ++c) {
+        ptrs.src[c] = stage_in ? p->stage_in + ((size_t)slot * p->G + c) * p->win_floats : p->pend_win[c];
+        ptrs.dst[c] = !p->pend_out[c] ? nullptr : stage_out ? p->stage_out + ((size_t)slot * p->G + c) * p->res_floats : p->pend_out[c];
+    }
+    if (stage_in)
+        SB_CUDA(cudaMemcpyAsync(const_cast<float*>(ptrs.src[0]), p->pend_win[0], sizeof(float) * p->win_floats * n, cudaMemcpyDefault, st));
+    if (dev_in || stage_in) {
         const long long total = (long long)n * p->B * d->M * (long long)nfft;
         SB_CHECK(launch("gather_windows", gather_windows_kernel, dim3((unsigned)ceil_div_ll(total, 256 * 8)), dim3(256), 0, st, ptrs,
                         const_cast<float*>(io.wave), n, p->B * d->M, (int)nfft, (int)hop, (long long)(in_pitch / sizeof(float))));
@@ -271,10 +299,12 @@ static int launch_group(sb_pipe* p) {
                                       sizeof(float) * nfft, (size_t)p->B * d->M, cudaMemcpyDefault, st));
     }
     SB_CHECK(run_ranges(p, t, n == p->G ? 0 : n));
-    if (dev_out) {
+    if (dev_out || stage_out) {
         const long long total = (long long)n * p->B * d->n_src * (long long)hop;
         SB_CHECK(launch("scatter_results", scatter_results_kernel, dim3((unsigned)ceil_div_ll(total, 256 * 8)), dim3(256), 0, st, ptrs,
                         (const float*)io.wave_out, n, p->B * d->n_src, (int)hop, (long long)(out_pitch / sizeof(float))));
+        if (stage_out)
+            SB_CUDA(cudaMemcpyAsync(p->pend_out[0], ptrs.dst[0], sizeof(float) * p->res_floats * n, cudaMemcpyDefault, st));
     } else {
         for (int c = 0; c < n; ++c)
             if (p->pend_out[c])

@@ -404,3 +404,44 @@ def test_pipelined_tensor_core_kernel_against_oracle(lib):
         assert all(v <= TOL for v in r.values()), r
     finally:
         assert lib.sb_set_option(abi.SB_OPT_TC_CW16, 0) == 0
+
+
+def test_grouped_pipe_moves_windows_and_results_the_same_way_from_every_kind_of_memory():
+    """Grouped throughput mode (sb_pipe_feed_chunk): device tensors (one gather / scatter kernel per group), pieces of ONE pinned
+    host array (one copy each way through the pipe's device staging) and separate pinned host tensors (a pitched copy per
+    window) give bit-identical results, with a partial last group, and match the in-order session within the tight bar."""
+    g = Golden("syn_nopad")
+    m = _net_for(g)
+    cfg = m.cfg
+    x = g.mixture.to(DEV)
+    dis = g.dis_embed.to(DEV) if g.dis_embed is not None else None
+    T = (x.shape[-1] - cfg.n_fft) // cfg.stft_chunk_size + 1
+    wins = [x[..., t * cfg.stft_chunk_size: t * cfg.stft_chunk_size + cfg.n_fft].contiguous() for t in range(T)]
+    seq = m.streaming(x.shape[0], dis)
+    ref = torch.cat([seq.feed(w).clone() for w in wins], dim=-1)
+    G = 3
+    assert T % G != 0 and T > 2 * G, "the fixture should end in a partial group"
+    pipe = m.streaming(x.shape[0], dis, pipelined=True, group=G, depth=2)
+    shape_o = (x.shape[0], cfg.num_src, cfg.stft_chunk_size)
+    results = {}
+    for kind in ("device", "host_array", "host_pieces"):
+        if kind == "device":
+            src, dst = wins, [torch.full(shape_o, float("nan"), device=DEV) for _ in wins]
+        elif kind == "host_array":
+            big_in = torch.stack([w.cpu() for w in wins]).pin_memory()
+            big_out = torch.full((T,) + shape_o, float("nan")).pin_memory()
+            src, dst = [big_in[t] for t in range(T)], [big_out[t] for t in range(T)]
+        else:
+            src = [w.cpu().pin_memory() for w in wins]
+            dst = [torch.full(shape_o, float("nan")).pin_memory() for _ in wins]
+        pipe.reset()
+        pipe.begin()
+        for t in range(T):
+            pipe.feed(src[t], out=dst[t])
+        pipe.end()
+        torch.cuda.synchronize()
+        results[kind] = torch.cat([d.to(DEV) for d in dst], dim=-1)
+        assert not torch.isnan(results[kind]).any(), kind
+    assert torch.equal(results["device"], results["host_array"]) and torch.equal(results["device"], results["host_pieces"])
+    r = pc.compare(results["device"], ref)
+    assert r["rms"] <= pc.RMS_TIGHT and r["maxabs"] <= pc.MAXABS_TIGHT, r
