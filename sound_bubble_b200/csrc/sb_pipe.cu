@@ -15,9 +15,10 @@
 // call, so that the intra-frame recurrences of G chunks share tcgen05 tiles (G x B rows per direction) and the
 // inter-frame kernel walks G steps per launch.  A partial last group is run eagerly with T = the number of pending chunks.
 //
-// All device memory (windows, results, workspaces, both state arenas) belongs to the caller and arrives inside the
+// All device memory of the network (windows, results, workspaces, both state arenas) belongs to the caller and arrives inside the
 // sb_net_io array: entry k describes chunk numbers t with t % n_ios == k (n_ios = lcm(depth, 2): slot t % depth for
-// wave / wave_out / workspace, arena t % 2 for the state inputs, the other arena for the state outputs).
+// wave / wave_out / workspace, arena t % 2 for the state inputs, the other arena for the state outputs).  The pipe itself
+// allocates only the staging of the grouped mode's host path: G windows + G results per slot.
 #include <vector>
 
 #include "sb_common.cuh"
