@@ -708,7 +708,9 @@ __global__ void __launch_bounds__(256) film_apply_fwd_kernel(const sb_film_apply
     }
 }
 
-// thread (b, f, c) walks the frames: dL/dx = g * scale; dL/dscale += sum_t g * x; dL/dshift += sum_t g
+// thread (b, f, c) walks a slice of the frames: dL/dx = g * scale; dL/dscale += sum_t g * x; dL/dshift += sum_t g.
+// blockIdx.y = one of gridDim.y frame slices (one thread per (b, f, c) over all 625 frames of a 5 s clip was a serial chain of
+// 625 dependent round trips on 145 CTAs: 282 us for 280 MB); the slices meet in the accumulating gradient buffers by atomics.
 __global__ void __launch_bounds__(256) film_apply_bwd_kernel(const sb_film_apply_args a) {
     pdl_wait();
     const long long fc = (long long)a.F * a.C, total = fc * a.B;
@@ -716,16 +718,24 @@ __global__ void __launch_bounds__(256) film_apply_bwd_kernel(const sb_film_apply
     if (i >= total) return;
     const long long b = i / fc, r = i - b * fc;
     const float sc = __ldg(a.film_scale + i);
+    const int per = (a.T + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int t_begin = (int)blockIdx.y * per, t_end = min(a.T, t_begin + per);
     float gs = 0.f, gh = 0.f;
-    for (int t = 0; t < a.T; ++t) {
-        const long long p = (b * a.T + t) * fc + r;
+    long long p = (b * a.T + t_begin) * fc + r;
+#pragma unroll 4
+    for (int t = t_begin; t < t_end; ++t, p += fc) {
         const float g = ld_plain(a.gy + p), x = ldg1_stream(a.x + p);
         gs = fmaf(g, x, gs);
         gh += g;
         a.gx[p] = g * sc;
     }
-    a.g_scale[i] += gs;
-    a.g_shift[i] += gh;
+    if (gridDim.y == 1) {
+        a.g_scale[i] += gs;
+        a.g_shift[i] += gh;
+    } else if (t_begin < t_end) {
+        atomic_add(a.g_scale + i, gs);
+        atomic_add(a.g_shift + i, gh);
+    }
 }
 
 // Dis_Embed_Conv / Dis_Embed_Linear + the 1x1 convs of every FilmLayer, backward.  CTA = one utterance.
@@ -938,14 +948,31 @@ __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const sb_conv_in_tra
             }
             __syncthreads();
             if (worker) {
+                // (t, f) of the block's first position once, then carried along (two 64-bit divisions per position were most
+                // of this kernel's 1.6 ms); the g row of a position arrives as eight LDS.128
+                int fq = (int)(n0 % F), t = (int)((n0 / F) % T);
+                float vr[RB];                               // the block's 32 input values first: all loads in flight together
+                const float* fp = a.feats + (n0 + (long long)(kt - 2) * F + (kf - 1)) * Cin + c;
+#pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     const long long n = n0 + r;
-                    if (n >= n_end) break;
-                    const int fq = (int)(n % F), t = (int)((n / F) % T), ff = fq + kf - 1;
-                    if (t + kt - 2 < 0 || ff < 0 || ff >= F) continue;
-                    const float v = __ldg(a.feats + (n + (long long)(kt - 2) * F + (kf - 1)) * Cin + c);
+                    const int ff = fq + kf - 1;
+                    const bool in = n < n_end && t + kt - 2 >= 0 && ff >= 0 && ff < F;
+                    vr[r] = in ? __ldg(fp + r * Cin) : 0.f;
+                    if (++fq == F) {
+                        fq = 0;
+                        if (++t == T) t = 0;
+                    }
+                }
 #pragma unroll
-                    for (int o = 0; o < C; ++o) acc[o] = fmaf(v, g_s[r][o], acc[o]);
+                for (int r = 0; r < RB; ++r) {              // (a position outside the input contributes v = 0: acc unchanged)
+                    const float v = vr[r];
+#pragma unroll
+                    for (int o = 0; o < C; o += 4) {
+                        const float4 gv = ld4(&g_s[r][o]);
+                        acc[o] = fmaf(v, gv.x, acc[o]); acc[o + 1] = fmaf(v, gv.y, acc[o + 1]);
+                        acc[o + 2] = fmaf(v, gv.z, acc[o + 2]); acc[o + 3] = fmaf(v, gv.w, acc[o + 3]);
+                    }
                 }
             }
             if (pair0 == 0 && tid < C)
@@ -1039,19 +1066,51 @@ __global__ void __launch_bounds__(320) deconv_wgrad_kernel(const sb_backend_bwd_
     const long long n_end = n_begin + rows_per_cta < N ? n_begin + rows_per_cta : N;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
     pdl_wait();
-    for (long long n = n_begin; n < n_end; ++n) {
-        const int fq = (int)(n % F), t = (int)((n / F) % T), ff = fq + 1 - kf;
-        const long long b = n / ((long long)F * T);
-        const bool in = t - kt >= 0 && ff >= 0 && ff < F;
-        const float v = in ? __ldg(a.x + (n + (long long)(-kt) * F + (1 - kf)) * C + c) : 0.f;
+    // (b, t, f) of the position are carried along instead of being re-derived with two 64-bit divisions per position, which
+    // were most of this kernel's 1.9 ms (profiles/r02_launches_train.txt)
+    int fq = (int)(n_begin % F), t = (int)((n_begin / F) % T);
+    long long b = n_begin / ((long long)F * T);
+    // four positions per pass (20 loads in flight together), and the loads of pass p + 1 are issued before the FMAs of pass p:
+    // a warp issues in order, so without the second register set every pass exposed one full memory latency
+    // (pointers are advanced, not recomputed: the 64-bit multiplies of the index arithmetic were the bulk of the instructions)
+    const float* xp = a.x + (n_begin + (long long)(-kt) * F + (1 - kf)) * C + c;
+    const float* gp = a.ws + ((size_t)b * T + t) * a.n_src * 2 * F + fq;
+    const long long g_wrap = (long long)a.n_src * 2 * F - F;
+    const long long g_src = 2 * F;
+    auto load_pass = [&](long long n, float (&v)[4], float (&gq)[4][4]) {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            if (o < O) {
-                const float g = __ldg(a.ws + (((size_t)b * T + t) * a.n_src + (o >> 1)) * 2 * F + (o & 1) * F + fq);
-                acc[o] = fmaf(v, g, acc[o]);
-                accb[o] += g;
+        for (int i = 0; i < 4; ++i) {
+            const bool live = n + i < n_end;
+            const int ff = fq + 1 - kf;
+            const bool in = live && t - kt >= 0 && ff >= 0 && ff < F;
+            v[i] = in ? __ldg(xp) : 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) gq[i][o] = (live && o < O) ? __ldg(gp + (o >> 1) * g_src + (o & 1) * F) : 0.f;
+            xp += C;
+            ++gp;
+            if (++fq == F) {
+                fq = 0;
+                gp += g_wrap;
+                if (++t == T) { t = 0; ++b; }
             }
         }
+    };
+    auto fma_pass = [&](const float (&v)[4], const float (&gq)[4][4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                acc[o] = fmaf(v[i], gq[i][o], acc[o]);
+                accb[o] += gq[i][o];
+            }
+    };
+    float v0[4], g0[4][4], v1[4], g1[4][4];
+    load_pass(n_begin, v0, g0);
+    for (long long n = n_begin; n < n_end; n += 8) {
+        load_pass(n + 4, v1, g1);                           // (positions past n_end load nothing and contribute zeros)
+        fma_pass(v0, g0);
+        load_pass(n + 8, v0, g0);
+        fma_pass(v1, g1);
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -2094,7 +2153,8 @@ extern "C" int sb_film_apply_bwd(const sb_film_apply_args* p, void* stream) {
     SB_CHECK(check_film_apply(p, "sb_film_apply_bwd"));
     SB_REQUIRE(p->gy && p->gx && p->g_scale && p->g_shift, SB_E_BADARG, "sb_film_apply_bwd: null pointer");
     const long long total = (long long)p->B * p->F * p->C;
-    return launch("film_apply_bwd", film_apply_bwd_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, (cudaStream_t)stream, *p);
+    const int slices = p->T >= 64 ? 8 : 1;                      // whole clips: eight frame slices per (b, f, c)
+    return launch("film_apply_bwd", film_apply_bwd_kernel, dim3((unsigned)ceil_div_ll(total, 256), slices), dim3(256), 0, (cudaStream_t)stream, *p);
 }
 
 extern "C" int sb_film_params_bwd(const sb_film_bwd_args* p, void* stream) {

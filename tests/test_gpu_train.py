@@ -52,6 +52,12 @@ def test_tfg_s_gradients_against_oracle_autograd(lib):
     _ok(tc.check_net(lib, DEV, "dis_embed", SYN, B=3, T=6))
 
 
+def test_long_clip_gradients_against_oracle_autograd(lib):
+    """T >= 64 frames: the FiLM backward runs as eight frame slices that meet by atomics, the conv-in / deconv weight
+    gradients walk thousands of positions per CTA with carried (b, t, f) counters across frame and utterance boundaries"""
+    _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=2), B=2, T=70))
+
+
 def test_variants_against_oracle_autograd(lib):
     _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=1, num_src=2, spectral_masking=True), B=2, T=4))
     _ok(tc.check_net(lib, DEV, "dis_embed", dict(SYN, B=2, merge_method="None", use_first_ln=False), B=1, T=9))

@@ -21,8 +21,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--seconds", type=float, default=5.0)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cpu", type=int, default=0, help="ignored (the CPU figure beside the training step is bench.py's cpu_baseline.train)")
     ap.add_argument("--config", default="syn", choices=["syn", "rpi"], help="syn = TFG_S (config 4), rpi = Raspberry-Pi conv-LSTM model (config 5)")
     ap.add_argument("--ffma2", type=int, default=-1, help="0 / 1 = SB_OPT_TRAIN_FFMA2 (packed FMAs in the training GEMM kernels); -1 = library default")
@@ -66,15 +66,17 @@ def main():
     torch.cuda.reset_peak_memory_stats()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    each = []
+    for _ in range(args.steps):                                 # every step timed on its own, the median reported: a step that
+        e0.record()                                             # sends the caching allocator back to cudaMalloc costs 1.5x
         loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+        e1.record()
+        torch.cuda.synchronize()
+        each.append(e0.elapsed_time(e1))
+    ms = sorted(each)[len(each) // 2]
     frames = args.batch * (n // 192)
     res = {"what": "training step (forward + backward + clip + Adam), %s, fp32" % ("TFG_S" if args.config == "syn" else "Raspberry-Pi conv-LSTM model"), "batch": args.batch, "seconds": args.seconds, "one_row_kernels": bool(args.one_row), "ffma2_gemms": args.ffma2, "train_tc": args.train_tc,
-           "ms_per_step": ms, "train_frames_per_s": frames / ms * 1e3, "clips_per_s": args.batch / ms * 1e3,
+           "ms_per_step": ms, "ms_each_step": each, "train_frames_per_s": frames / ms * 1e3, "clips_per_s": args.batch / ms * 1e3,
            "launches_per_step": (_lib.launch_count() - l0) / args.steps,
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": float(loss)}
     # forward-only and backward-only split
