@@ -41,38 +41,33 @@ __device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v);
 #endif
 
 // ------------------------------------------------------------------------------------------------------------
-// LayerNorm over C, one position per thread.  in: rows of C floats at map_pos(n) (or n); out: xhat[n], xn[n], rstd[n].
+// LayerNorm over C: C / 4 adjacent lanes per position, one float4 each (a warp reads 512 contiguous bytes; with one position
+// per thread every load instruction touched 32 different 128-byte lines and the kernels ran at a third of the HBM rate).
+// in: rows of C floats at map_pos(n) (or n); out: xhat[n], xn[n], rstd[n].  Grid: ln_rows_per_block<C>() positions per block.
 // ------------------------------------------------------------------------------------------------------------
+template <int C>
+constexpr int ln_rows_per_block() { return 256 / (C / 4); }
+
 template <int C>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* x, RowMap map, const float* g, const float* bta,
                                                      float* xhat, float* xn, float* rstd, long long N, float eps) {
+    constexpr int LPR = C / 4, RPB = 256 / LPR;
     pdl_wait();
-    const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (n >= N) return;
-    const float* xr = x + map_pos(map, n) * C;
-    float v[C];
-    float mean = 0.f;
-#pragma unroll
-    for (int i = 0; i < C / 4; ++i) {
-        const float4 t = ldg4_stream(xr + 4 * i);
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-        mean += (t.x + t.y) + (t.z + t.w);
-    }
-    mean *= 1.0f / C;
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < C; ++i) { v[i] -= mean; var = fmaf(v[i], v[i], var); }
+    const int li = threadIdx.x % LPR;
+    const long long n = (long long)blockIdx.x * RPB + threadIdx.x / LPR;
+    const bool live = n < N;                                // uniform over the lanes of a position
+    const long long nc = live ? n : N - 1;
+    const float4 t = ldg4_stream(x + map_pos(map, nc) * C + 4 * li);
+    const float mean = group_sum<LPR>((t.x + t.y) + (t.z + t.w)) * (1.0f / C);
+    const float dx = t.x - mean, dy = t.y - mean, dz = t.z - mean, dw = t.w - mean;
+    const float var = group_sum<LPR>(fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw))));
     const float r = rsqrtf(var * (1.0f / C) + eps);
-    rstd[n] = r;
-#pragma unroll
-    for (int i = 0; i < C / 4; ++i) {
-        float4 h, o;
-        h.x = v[4 * i] * r; h.y = v[4 * i + 1] * r; h.z = v[4 * i + 2] * r; h.w = v[4 * i + 3] * r;
-        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i), bb = __ldg(reinterpret_cast<const float4*>(bta) + i);
-        o.x = fmaf(h.x, gg.x, bb.x); o.y = fmaf(h.y, gg.y, bb.y); o.z = fmaf(h.z, gg.z, bb.z); o.w = fmaf(h.w, gg.w, bb.w);
-        st4(xhat + n * C + 4 * i, h);
-        st4(xn + n * C + 4 * i, o);
-    }
+    if (!live) return;
+    if (li == 0) rstd[n] = r;
+    const float4 h = make_float4(dx * r, dy * r, dz * r, dw * r);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + li), bb = __ldg(reinterpret_cast<const float4*>(bta) + li);
+    st4(xhat + n * C + 4 * li, h);
+    st4(xn + n * C + 4 * li, make_float4(fmaf(h.x, gg.x, bb.x), fmaf(h.y, gg.y, bb.y), fmaf(h.z, gg.z, bb.z), fmaf(h.w, gg.w, bb.w)));
 }
 
 // dL/dLN-output (dxn[n]) -> dL/dx at map_pos(n) (+ the residual branch's gradient gy), and the gain / bias gradients.
@@ -80,54 +75,47 @@ template <int C>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* dxn, const float* xhat, const float* rstd, const float* g,
                                                      const float* gy, float* gx, RowMap map, float* g_g, float* g_b,
                                                      long long N) {
+    constexpr int LPR = C / 4, RPB = 256 / LPR;
     __shared__ float red[2 * C];
     pdl_wait();
     if (threadIdx.x < 2 * C) red[threadIdx.x] = 0.f;
     __syncthreads();
-    float ag[C], ab[C];
-#pragma unroll
-    for (int i = 0; i < C; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
-    for (long long n = (long long)blockIdx.x * 256 + threadIdx.x; n < N; n += (long long)gridDim.x * 256) {
-        float d[C], h[C];
-        float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < C / 4; ++i) {
-            const float4 t = ldg4_stream(dxn + n * C + 4 * i), u = ldg4_stream(xhat + n * C + 4 * i);
-            d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
-            h[4 * i] = u.x; h[4 * i + 1] = u.y; h[4 * i + 2] = u.z; h[4 * i + 3] = u.w;
+    const int li = threadIdx.x % LPR;
+    const float4 gw = __ldg(reinterpret_cast<const float4*>(g) + li);
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;   // this lane's four channels, over the positions it visits
+    const long long n_iter = (N + (long long)gridDim.x * RPB - 1) / ((long long)gridDim.x * RPB);
+    for (long long it = 0; it < n_iter; ++it) {             // same trip count for every thread: the shuffles stay converged
+        const long long n = (it * gridDim.x + blockIdx.x) * RPB + threadIdx.x / LPR;
+        const bool live = n < N;
+        const long long nc = live ? n : N - 1;
+        float4 d = ldg4_stream(dxn + nc * C + 4 * li);
+        const float4 h = ldg4_stream(xhat + nc * C + 4 * li);
+        if (live) {
+            ag.x = fmaf(d.x, h.x, ag.x); ag.y = fmaf(d.y, h.y, ag.y); ag.z = fmaf(d.z, h.z, ag.z); ag.w = fmaf(d.w, h.w, ag.w);
+            ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
         }
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            ag[i] = fmaf(d[i], h[i], ag[i]);
-            ab[i] += d[i];
-            d[i] *= __ldg(g + i);
-            m1 += d[i];
-            m2 = fmaf(d[i], h[i], m2);
-        }
-        m1 *= 1.0f / C;
-        m2 *= 1.0f / C;
-        const float r = rstd[n];
-        const long long p = map_pos(map, n) * C;
-#pragma unroll
-        for (int i = 0; i < C / 4; ++i) {
-            float4 o;
-            o.x = r * (d[4 * i] - m1 - h[4 * i] * m2);
-            o.y = r * (d[4 * i + 1] - m1 - h[4 * i + 1] * m2);
-            o.z = r * (d[4 * i + 2] - m1 - h[4 * i + 2] * m2);
-            o.w = r * (d[4 * i + 3] - m1 - h[4 * i + 3] * m2);
+        d.x *= gw.x; d.y *= gw.y; d.z *= gw.z; d.w *= gw.w;
+        const float m1 = group_sum<LPR>((d.x + d.y) + (d.z + d.w)) * (1.0f / C);
+        const float m2 = group_sum<LPR>(fmaf(d.x, h.x, fmaf(d.y, h.y, fmaf(d.z, h.z, d.w * h.w)))) * (1.0f / C);
+        if (live) {
+            const float r = rstd[n];
+            const long long p = map_pos(map, n) * C + 4 * li;
+            float4 o = make_float4(r * (d.x - m1 - h.x * m2), r * (d.y - m1 - h.y * m2), r * (d.z - m1 - h.z * m2), r * (d.w - m1 - h.w * m2));
             if (gy) {
-                const float4 t = ld_plain4(gy + p + 4 * i);
+                const float4 t = ld_plain4(gy + p);
                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
             }
-            st4(gx + p + 4 * i, o);
+            st4(gx + p, o);
         }
     }
+    // lanes li, li + LPR, ... of a warp hold the same four channels
+    float a4[4] = {ag.x, ag.y, ag.z, ag.w}, b4[4] = {ab.x, ab.y, ab.z, ab.w};
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-        float a = ag[i], b = ab[i];
+    for (int i = 0; i < 4; ++i) {
+        float a = a4[i], b = b4[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-        if ((threadIdx.x & 31) == 0) { atomic_add(&red[i], a); atomic_add(&red[C + i], b); }
+        for (int o = 16; o >= LPR; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if ((threadIdx.x & 31) < LPR) { atomic_add(&red[4 * li + i], a); atomic_add(&red[C + 4 * li + i], b); }
     }
     __syncthreads();
     if (threadIdx.x < C) atomic_add(g_g + threadIdx.x, red[threadIdx.x]);
@@ -1762,7 +1750,7 @@ static int run_outer(Outer o, cudaStream_t st, const char* name) {
 static int path_train_fwd(const sb_path_train_args& a, cudaStream_t st) {
     const PathDims d = path_dims(a);
     const SavedView v = saved_view(a, d);
-    const unsigned gN = (unsigned)ceil_div_ll(d.N, 256);
+    const unsigned gN = (unsigned)ceil_div_ll(d.N, a.C == 32 ? ln_rows_per_block<32>() : ln_rows_per_block<16>());
     if (a.C == 32) SB_CHECK(launch("ln_fwd", ln_fwd_kernel<32>, dim3(gN), dim3(256), 0, st, a.x, d.map, a.ln_g, a.ln_b, v.xhat, v.xn, v.rstd, d.N, 1e-5f));
     else SB_CHECK(launch("ln_fwd", ln_fwd_kernel<16>, dim3(gN), dim3(256), 0, st, a.x, d.map, a.ln_g, a.ln_b, v.xhat, v.xn, v.rstd, d.N, 1e-5f));
     LstmTrain l{};
@@ -1836,7 +1824,7 @@ static int path_bwd(const sb_path_bwd_args& b, cudaStream_t st) {
     for (int k = 0; k < d.nd; ++k) { g.A[k] = v.gates[k]; g.W[k] = a.w_ih[k]; }
     g.out = dxn; g.map = d.map; g.a_mapped = 0; g.o_mapped = 0; g.N = d.N;
     SB_CHECK(rowgemm(g, a.C, st, "lstm_dx"));
-    const unsigned grid = (unsigned)(ceil_div_ll(d.N, 256) < 2LL * sm_count() ? ceil_div_ll(d.N, 256) : 2LL * sm_count());
+    const unsigned grid = (unsigned)(ceil_div_ll(d.N, 32) < 8LL * sm_count() ? ceil_div_ll(d.N, 32) : 8LL * sm_count());   // ln_bwd: eight resident CTAs per SM
     if (a.C == 32) return launch("ln_bwd", ln_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, (const float*)dxn, (const float*)v.xhat, (const float*)v.rstd, a.ln_g, b.gy, b.gx, d.map, b.g_ln_g, b.g_ln_b, d.N);
     return launch("ln_bwd", ln_bwd_kernel<16>, dim3(grid), dim3(256), 0, st, (const float*)dxn, (const float*)v.xhat, (const float*)v.rstd, a.ln_g, b.gy, b.gx, d.map, b.g_ln_g, b.g_ln_b, d.N);
 }
@@ -1903,7 +1891,7 @@ static int convpath_fwd(const sb_convpath_train_args& a, cudaStream_t st) {
     const unsigned ge = (unsigned)(ceil_div_ll(n4, 256) < 8LL * sm_count() ? ceil_div_ll(n4, 256) : 8LL * sm_count());
     SB_CHECK(launch("prelu_fwd", prelu_fwd_kernel, dim3(ge), dim3(256), 0, st, (const float*)v.zraw, a.prelu, v.pz, n4));
     const RowMap ident{cp.J, cp.F, 0};
-    SB_CHECK(launch("ln_fwd", ln_fwd_kernel<C>, dim3((unsigned)ceil_div_ll(NP, 256)), dim3(256), 0, st, (const float*)v.pz, ident, a.ln_g,
+    SB_CHECK(launch("ln_fwd", ln_fwd_kernel<C>, dim3((unsigned)ceil_div_ll(NP, ln_rows_per_block<C>())), dim3(256), 0, st, (const float*)v.pz, ident, a.ln_g,
                     a.ln_b, v.xhat, v.xn, v.rstd, NP, 1e-5f));
     LstmTrain l{};
     l.xn = v.xn;
@@ -1953,7 +1941,7 @@ static int convpath_bwd(const sb_convpath_bwd_args& b, cudaStream_t st) {
     g.out = dxn; g.map = ident; g.a_mapped = 0; g.o_mapped = 0; g.N = NP;
     SB_CHECK(rowgemm(g, C, st, "lstm_dx"));
     // LayerNorm backward -> gradient of the PReLU output (written over the PReLU output slot), PReLU backward in place
-    const unsigned gl = (unsigned)(ceil_div_ll(NP, 256) < 2LL * sm_count() ? ceil_div_ll(NP, 256) : 2LL * sm_count());
+    const unsigned gl = (unsigned)(ceil_div_ll(NP, 32) < 8LL * sm_count() ? ceil_div_ll(NP, 32) : 8LL * sm_count());
     SB_CHECK(launch("ln_bwd", ln_bwd_kernel<C>, dim3(gl), dim3(256), 0, st, (const float*)dxn, (const float*)v.xhat, (const float*)v.rstd, a.ln_g,
                     (const float*)nullptr, v.pz, ident, b.g_ln_g, b.g_ln_b, NP));
     const long long ne = NP * C;
@@ -2192,7 +2180,7 @@ extern "C" int sb_conv_in_train_fwd(const sb_conv_in_train_args* p, void* stream
     float* xhat = p->saved + N * C;
     float* rstd = p->saved + 2 * N * C;
     const RowMap map{1, p->F, 0};
-    const unsigned gN = (unsigned)ceil_div_ll(N, 256);
+    const unsigned gN = (unsigned)ceil_div_ll(N, C == 32 ? ln_rows_per_block<32>() : ln_rows_per_block<16>());
     if (C == 32) return launch("ln_fwd", ln_fwd_kernel<32>, dim3(gN), dim3(256), 0, st, (const float*)raw, map, p->ln_g, p->ln_b, xhat, p->x, rstd, N, 1e-5f);
     return launch("ln_fwd", ln_fwd_kernel<16>, dim3(gN), dim3(256), 0, st, (const float*)raw, map, p->ln_g, p->ln_b, xhat, p->x, rstd, N, 1e-5f);
 }
@@ -2207,7 +2195,7 @@ extern "C" int sb_conv_in_bwd(const sb_conv_in_train_args* p, void* stream) {
     const float* g = p->gx;
     if (p->ln_g) {
         const RowMap map{1, p->F, 0};
-        const unsigned grid = (unsigned)(ceil_div_ll(N, 256) < 2LL * sm_count() ? ceil_div_ll(N, 256) : 2LL * sm_count());
+        const unsigned grid = (unsigned)(ceil_div_ll(N, 32) < 8LL * sm_count() ? ceil_div_ll(N, 32) : 8LL * sm_count());
         const float* xhat = p->saved + N * C;
         const float* rstd = p->saved + 2 * N * C;
         if (C == 32) SB_CHECK(launch("ln_bwd", ln_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, p->gx, xhat, rstd, p->ln_g, (const float*)nullptr, p->ws, map, p->g_ln_g, p->g_ln_b, N));
