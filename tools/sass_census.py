@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """SASS opcode census of libsoundbubble_sm100a.so (cuobjdump -sass): per kernel, how many tensor-core (UTCHMMA), tensor-memory
-(LDTM / STTM), TMA (UBLKCP = bulk copy, UTMALDG / UTMASTG = tensor-map load / store), packed-FMA (FFMA2), MUFU and mbarrier
+(LDTM / STTM), TMA (UBLKCP = bulk copy, UTMALDG / UTMASTG / UTMAREDG = tensor-map load / store / reduce-store), packed-FMA (FFMA2), MUFU and mbarrier
 (SYNCS) instructions the build contains.  Evidence that the tcgen05 / TMA paths are what was compiled, next to the ncu captures.
 
     python tools/sass_census.py > profiles/r02_sass_census.txt
@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "sound_bubble_b200", "libsoundbubble_sm100a.so")
-OPS = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "FFMA2", "FFMA", "MUFU", "SYNCS", "LDGSTS", "RED", "ATOMG", "HMMA"]
+OPS = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "UTMAREDG", "FFMA2", "FFMA", "MUFU", "SYNCS", "LDGSTS", "RED", "ATOMG", "HMMA"]
 
 
 def main():
