@@ -30,6 +30,8 @@ bool tc_cw16_enabled();                      // lstm_tcr_kernel with 16 cell-upd
 bool front_tc_enabled();                     // conv-in on the tensor cores (sb_set_option(SB_OPT_FRONT_TC, v))
 bool conv_in_tc_supported(const sb_conv_in_args& p);
 int run_conv_in_tc(const sb_conv_in_args& p, cudaStream_t st);   // sb_frontend_tc.cu
+bool conv_in_tc_train_supported(int B, int T, int F, int Cin, int C);
+int run_conv_in_tc_train(const float* feats, const float* w, const float* bias, float* raw, int B, int T, int F, int Cin, cudaStream_t st);
 bool tc_pipe_enabled();                      // single-addend SB_ALGO_TC calls on lstm_tcr_kernel (sb_set_option(SB_OPT_TC_PIPE, v))
 bool tc_cell7_enabled();                     // shared-reciprocal cell update in lstm_tcp_kernel (sb_set_option(SB_OPT_TC_CELL7, v))
 bool tc_v1_enabled();                        // SB_ALGO_TC on the first tcgen05 kernel instead of the TMA pipeline (sb_set_option(SB_OPT_TC_V1, 1))

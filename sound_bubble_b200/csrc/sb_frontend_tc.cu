@@ -119,7 +119,9 @@ __host__ __device__ inline int rows_padded(int FP) {
 
 }  // namespace cit
 
-// grid (ceil(T * FP / 512), B)
+// grid (ceil(T * FP / 512), B).  TRAIN: the training forward (sb_conv_in_train_fwd): weights as stored [o][c][kt][kf], zero history,
+// no new history, no LayerNorm (ln_fwd_kernel keeps what the backward needs).
+template <bool TRAIN>
 __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_conv_in_args a) {
     using namespace cit;
     extern __shared__ unsigned char sm_raw[];
@@ -160,8 +162,9 @@ __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_c
             const int e = it * kStageThreads + tid;
             const int n = e & 31, c2 = (e >> 5) & 15, tap = e >> 9;
             const int kt = tap / 3, kf = tap - 3 * kt, c = 2 * c2;
-            const float v0 = c < Cin ? __ldg(a.w_pack + ((size_t)(kt * Cin + c) * 3 + kf) * kC + n) : 0.0f;
-            const float v1 = c + 1 < Cin ? __ldg(a.w_pack + ((size_t)(kt * Cin + c + 1) * 3 + kf) * kC + n) : 0.0f;
+            auto widx = [&](int cc) { return TRAIN ? ((size_t)n * Cin + cc) * 9 + tap : ((size_t)(kt * Cin + cc) * 3 + kf) * kC + n; };
+            const float v0 = c < Cin ? __ldg(a.w_pack + widx(c)) : 0.0f;
+            const float v1 = c + 1 < Cin ? __ldg(a.w_pack + widx(c + 1)) : 0.0f;
             uint32_t hi, lo;
             split2(v0, v1, hi, lo);
             const uint32_t off = (uint32_t)(((tap * 4 + (c2 >> 2)) * kC + n) * 16 + (c2 & 3) * 4);
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_c
         int code = -1;
         if (u >= 0 && u < n_u) {
             const int fr = u / FP, j = u - fr * FP, f = j - 1, t = fr - 2;
-            if (f >= 0 && f < F) code = t >= 0 ? ((b * T + t) * F + f) * Cin : -2 - ((2 + t) * F + f);
+            if (f >= 0 && f < F) code = t >= 0 ? ((b * T + t) * F + f) * Cin : (TRAIN ? -1 : -2 - ((2 + t) * F + f));
         }
         rowoff[s] = code;
     }
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_c
         // ---- stage the operand: one (row, channel pair) per thread and pass, coalesced along the channels of a position ---
         // Every load is unconditional - rows and channels that do not exist read a zero word - so that the U passes of a
         // round have their 2 U loads in flight together (with branches around the loads a pass cost a full L2 latency).
-        const float* hist = a.conv_buf_in + (size_t)b * Cin * 2 * F;
+        const float* hist = TRAIN ? a.feats : a.conv_buf_in + (size_t)b * Cin * 2 * F;      // (TRAIN: no row refers to it)
         auto stage_rows = [&](int row0, int row1, auto unroll_tag) {
             constexpr int U = decltype(unroll_tag)::value;
             const int first = row0 * 16, n_pairs = (row1 - row0) * 16;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(cit::kThreads, 1) conv_in_tc_kernel(const sb_c
         }
 
         // ---- the new history (fp32, exact): last two frames of [history ; feats] = frames T - 2, T - 1 (T >= 4 on this path) --
-        if (blockIdx.x == 0) {
+        if (!TRAIN && blockIdx.x == 0) {
             float* dst = a.conv_buf_out + (size_t)b * Cin * 2 * F;
 #pragma unroll 8
             for (int i = tid; i < 2 * F * Cin; i += kStageThreads) {
@@ -333,12 +336,30 @@ bool conv_in_tc_supported(const sb_conv_in_args& p) {
 int run_conv_in_tc(const sb_conv_in_args& p, cudaStream_t st) {
     const int FP = p.F + 2;
     dim3 grid(ceil_div(p.T * FP, cit::kRowsOut), p.B);
-    return launch("conv_in_tc", conv_in_tc_kernel, grid, dim3(cit::kThreads), conv_in_tc_smem(p.F), st, p);
+    return launch("conv_in_tc", conv_in_tc_kernel<false>, grid, dim3(cit::kThreads), conv_in_tc_smem(p.F), st, p);
+}
+
+// the training forward on the same kernel: raw[B][T][F][C] = conv(feats from zero history) + bias, weights as stored
+bool conv_in_tc_train_supported(int B, int T, int F, int Cin, int C) {
+    if (C != 32 || Cin > cit::kKPad || T < 1) return false;
+    if ((long long)B * T * F * Cin >= (1ll << 31)) return false;
+    return conv_in_tc_smem(F) <= 227 * 1024;
+}
+int run_conv_in_tc_train(const float* feats, const float* w, const float* bias, float* raw, int B, int T, int F, int Cin, cudaStream_t st) {
+    sb_conv_in_args p{};
+    p.feats = feats; p.w_pack = w; p.bias = bias; p.x = raw; p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.C = 32;
+    dim3 grid(ceil_div(T * (F + 2), cit::kRowsOut), B);
+    return launch("conv_in_tc_train", conv_in_tc_kernel<true>, grid, dim3(cit::kThreads), conv_in_tc_smem(F), st, p);
 }
 
 #else   // SB_EMU: tensor-core instructions cannot be emulated on the host
 
 bool conv_in_tc_supported(const sb_conv_in_args&) { return false; }
+bool conv_in_tc_train_supported(int, int, int, int, int) { return false; }
+int run_conv_in_tc_train(const float*, const float*, const float*, float*, int, int, int, int, cudaStream_t) {
+    set_error("conv_in_tc: not available in the host-emulated test build");
+    return SB_E_UNSUPP;
+}
 int run_conv_in_tc(const sb_conv_in_args&, cudaStream_t) {
     set_error("conv_in_tc: not available in the host-emulated test build");
     return SB_E_UNSUPP;

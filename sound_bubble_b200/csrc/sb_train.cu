@@ -2174,7 +2174,9 @@ extern "C" int sb_conv_in_train_fwd(const sb_conv_in_train_args* p, void* stream
     float* raw = p->ln_g ? p->saved : p->x;
     const size_t smem = (size_t)9 * p->Cin * C * sizeof(float);
     const unsigned grid = (unsigned)ceil_div_ll(N, 256 / (C / 8));
-    if (C == 32) SB_CHECK(launch("conv_in_train", conv_in_train_kernel<32>, dim3(grid), dim3(256), smem, st, *p, raw));
+    if (front_tc_enabled() && conv_in_tc_train_supported(p->B, p->T, p->F, p->Cin, C))      // tcgen05 implicit GEMM (sb_frontend_tc.cu)
+        SB_CHECK(run_conv_in_tc_train(p->feats, p->w, p->bias, raw, p->B, p->T, p->F, p->Cin, st));
+    else if (C == 32) SB_CHECK(launch("conv_in_train", conv_in_train_kernel<32>, dim3(grid), dim3(256), smem, st, *p, raw));
     else SB_CHECK(launch("conv_in_train", conv_in_train_kernel<16>, dim3(grid), dim3(256), smem, st, *p, raw));
     if (!p->ln_g) return 0;
     float* xhat = p->saved + N * C;
