@@ -978,35 +978,57 @@ __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const sb_conv_in_tra
 // wave[192 t' + r] += sum_k spec_k[t'] filt[k][r] over frames t' in {t, t-1} (iSTFT/OLA, first `stride` samples dropped).
 // ------------------------------------------------------------------------------------------------------------
 // g_spec[b][t][s][k] = sum_r filt[k][r] * g_wave[b][s][stride*t + r]   (samples past stride*T are the cropped look-ahead)
+// Thread k walks the n_fft taps of basis row k; the basis is staged through shared memory 32 taps at a time with coalesced
+// reads (thread k reading filt[k][r] straight from global touched 32 different lines per load instruction, and ten warps of
+// four resident CTAs thrashed the L1: 280 us for a 0.4 GMAC job).
 __global__ void __launch_bounds__(320) istft_bwd_kernel(const sb_backend_bwd_args a) {
-    constexpr int TT = 8;
-    SB_DYN_SMEM(float, g_s);                        // [(TT-1)*stride + n_fft]
+    constexpr int TT = 8, RC = 32;
+    SB_DYN_SMEM(float, g_s);                        // [(TT-1)*stride + n_fft] then the basis chunk [2F][RC + 1]
     const int F2 = 2 * a.F, S = a.n_src, t0 = blockIdx.x * TT, bs = blockIdx.y, tid = threadIdx.x;
     const int span = (TT - 1) * a.stride + a.n_fft, len = a.stride * a.T;
+    float* f_s = g_s + span;
     pdl_wait();
     const float* gw = a.g_wave + (size_t)bs * len;
     for (int i = tid; i < span; i += 320) {
         const long long p = (long long)t0 * a.stride + i;
         g_s[i] = p < len ? ldg1_stream(gw + p) : 0.f;
     }
-    __syncthreads();
     const int b = bs / S, s = bs - b * S;
-    for (int k = tid; k < F2; k += 320) {
-        float acc[TT];
+    float acc[2][TT];                               // basis rows tid and tid + 320 (2F <= 640)
 #pragma unroll
-        for (int j = 0; j < TT; ++j) acc[j] = 0.f;
-        const float* fr = a.filt + (size_t)k * a.n_fft;
-        for (int r = 0; r < a.n_fft; ++r) {
-            const float w = __ldg(fr + r);
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int j = 0; j < TT; ++j) acc[j] = fmaf(w, g_s[j * a.stride + r], acc[j]);
+        for (int j = 0; j < TT; ++j) acc[h][j] = 0.f;
+    for (int r0 = 0; r0 < a.n_fft; r0 += RC) {
+        const int nr = min(RC, a.n_fft - r0);
+        __syncthreads();                            // g_s staged / the previous chunk consumed
+        for (int i = tid; i < F2 * RC; i += 320) {
+            const int k = i / RC, rr = i - k * RC;
+            f_s[k * (RC + 1) + rr] = rr < nr ? __ldg(a.filt + (size_t)k * a.n_fft + r0 + rr) : 0.f;
         }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = tid + 320 * h;
+            if (k < F2) {
+                for (int rr = 0; rr < nr; ++rr) {
+                    const float w = f_s[k * (RC + 1) + rr];
+#pragma unroll
+                    for (int j = 0; j < TT; ++j) acc[h][j] = fmaf(w, g_s[j * a.stride + r0 + rr], acc[h][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = tid + 320 * h;
+        if (k >= F2) continue;
 #pragma unroll
         for (int j = 0; j < TT; ++j) {
             const int t = t0 + j;
             if (t >= a.T) break;
             const size_t idx = (((size_t)b * a.T + t) * S + s) * F2 + k;
-            a.ws[idx] = a.mask_spec ? acc[j] * __ldg(a.mask_spec + idx) : acc[j];
+            a.ws[idx] = a.mask_spec ? acc[h][j] * __ldg(a.mask_spec + idx) : acc[h][j];
         }
     }
 }
@@ -2216,10 +2238,11 @@ extern "C" int sb_backend_bwd(const sb_backend_bwd_args* p, void* stream) {
     SB_REQUIRE(p->C == 16 || p->C == 32, SB_E_UNSUPP, "sb_backend_bwd: C must be 16 or 32 (got %d)", p->C);
     SB_REQUIRE(p->n_src == 1 || p->n_src == 2, SB_E_UNSUPP, "sb_backend_bwd: 1 or 2 sources (got %d)", p->n_src);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = ((size_t)7 * p->stride + p->n_fft) * sizeof(float);
+    SB_REQUIRE(2 * p->F <= 640, SB_E_UNSUPP, "sb_backend_bwd: more than 640 basis rows (F = %d)", p->F);
+    const size_t smem = ((size_t)7 * p->stride + p->n_fft + (size_t)2 * p->F * 33) * sizeof(float);
     SB_CHECK(launch("istft_bwd", istft_bwd_kernel, dim3(ceil_div(p->T, 8), p->B * p->n_src), dim3(320), smem, st, *p));
     const long long N = (long long)p->B * p->T * p->F;
-    const long long rows = reduction_rows(N, 1);
+    const long long rows = ceil_div_ll(N, 6LL * sm_count()) < 1 ? 1 : ceil_div_ll(N, 6LL * sm_count());      // deconv_wgrad: three resident CTAs per SM, two rounds
     if (p->C == 32) {
         SB_CHECK(launch("deconv_bwd_x", deconv_bwd_x_kernel<32>, dim3((unsigned)ceil_div_ll(N, 8)), dim3(256), 0, st, *p));
         return launch("deconv_wgrad", deconv_wgrad_kernel<32>, dim3((unsigned)ceil_div_ll(N, rows)), dim3(288), 0, st, *p, rows);
