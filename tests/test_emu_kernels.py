@@ -53,3 +53,20 @@ def test_streaming_attention_path(lib):
 
 def test_whole_path_golden_plain(lib):
     pc.assert_parity(pc.run_golden(lib, "cpu", "syn_plain"))
+
+
+def test_summed_directions_are_refused_where_the_tensor_core_kernel_cannot_run(lib):
+    """y_bwd == y_fwd (both intra directions summed into one buffer) exists only on lstm_tcr_kernel: the host-emulated
+    build has no tensor-core kernels, so the query answers 0, the call fails with SB_E_UNSUPP instead of racing two
+    directions into one buffer, and sb_net_forward keeps the two-buffer path (the whole-path goldens above)."""
+    with pytest.raises(AssertionError):
+        kc.check_intra(lib, "cpu", "dis_embed", SYN, abi.SB_ALGO_AUTO, B=1, T=2, block=1, summed=True)
+    import ctypes
+    import torch
+    x = torch.zeros(1, 2, 145, 32)
+    y = torch.zeros_like(x)
+    a = abi.IntraArgs()
+    a.x, a.y_fwd, a.y_bwd = x.data_ptr(), y.data_ptr(), y.data_ptr()
+    a.B, a.T, a.F, a.C, a.H, a.algo = 1, 2, 145, 32, 64, abi.SB_ALGO_AUTO
+    assert lib.sb_intra_sum_supported(ctypes.byref(a)) == 0
+    assert lib.sb_intra_lstm_fwd(ctypes.byref(a), None) == -2          # SB_E_UNSUPP (include/soundbubble.h)
